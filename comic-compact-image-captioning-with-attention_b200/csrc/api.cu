@@ -1,0 +1,165 @@
+// api.cu -- handle lifecycle, weight binding and the remaining C-ABI entry
+// points of libcomic_b200.so (see include/comic_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "comic_internal.cuh"
+
+namespace comic {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace comic
+
+using namespace comic;
+
+extern "C" const char* comic_last_error(void) { return g_err; }
+extern "C" const char* comic_version(void) { return "comic_b200 0.1 (sm_100a, f32-exact path)"; }
+
+extern "C" int comic_create(const comic_cfg_t* cfg, comic_handle_t* out) {
+  COMIC_REQUIRE(cfg && out, COMIC_E_BADARG, "create: null argument");
+  COMIC_REQUIRE(cfg->rnn_size > 0 && cfg->rnn_size % 128 == 0, COMIC_E_UNSUPPORTED,
+                "create: rnn_size %d must be a positive multiple of 128", cfg->rnn_size);
+  COMIC_REQUIRE(cfg->word_size > 0 && cfg->word_size % 4 == 0, COMIC_E_UNSUPPORTED, "create: word_size %% 4 != 0");
+  COMIC_REQUIRE(cfg->num_heads > 0 && cfg->rnn_size % cfg->num_heads == 0 &&
+                    (cfg->rnn_size / cfg->num_heads) % 4 == 0,
+                COMIC_E_UNSUPPORTED, "create: heads %d incompatible with rnn_size %d", cfg->num_heads, cfg->rnn_size);
+  COMIC_REQUIRE(cfg->fm_channels > 0 && cfg->fm_channels % 4 == 0 && cfg->fm_positions > 0, COMIC_E_SHAPE,
+                "create: bad feature map %d x %d", cfg->fm_positions, cfg->fm_channels);
+  COMIC_REQUIRE(cfg->vocab > 1 && cfg->eos_id >= 0 && cfg->eos_id < cfg->vocab, COMIC_E_SHAPE, "create: bad vocab / eos");
+  COMIC_REQUIRE(cfg->fm_projection >= 0 && cfg->fm_projection <= 2, COMIC_E_BADARG, "create: fm_projection");
+  COMIC_REQUIRE(cfg->alignment == 0 || cfg->alignment == 1, COMIC_E_BADARG,
+                "create: Invalid alignment method.");   // src/model_base.py:133-138
+  COMIC_REQUIRE(cfg->prob_fn == 0 || cfg->prob_fn == 1, COMIC_E_BADARG, "create: Invalid alignment method.");
+  COMIC_REQUIRE(cfg->embed_size % 4 == 0, COMIC_E_SHAPE, "create: embed_size %% 4 != 0");
+  comic_handle_s* h = new (std::nothrow) comic_handle_s();
+  COMIC_REQUIRE(h, COMIC_E_BADARG, "create: out of host memory");
+  h->cfg = *cfg;
+  COMIC_CHECK_CUDA(cudaGetDevice(&h->dev));
+  cudaDeviceProp prop;
+  COMIC_CHECK_CUDA(cudaGetDeviceProperties(&prop, h->dev));
+  h->num_sms = prop.multiProcessorCount;
+  h->R = cfg->rnn_size; h->W = cfg->word_size; h->H = cfg->num_heads;
+  h->C = cfg->fm_channels; h->M = cfg->fm_positions; h->E = cfg->embed_size; h->V = cfg->vocab;
+  h->Vp = round_up(h->V, 4);
+  h->VAL = (cfg->fm_projection == 0) ? h->C : h->R;
+  h->A = (cfg->fm_projection == 0 && !cfg->context_layer) ? h->C : h->R;   // src/model_base.py:611-615
+  h->LQ = h->Vp + h->R;
+  h->KX = h->W + h->A + h->R;
+  if (h->VAL % h->H != 0) {
+    delete h;
+    set_error("create: value width %d not divisible by heads %d", h->VAL, h->H);
+    return COMIC_E_SHAPE;
+  }
+  memset(&h->w, 0, sizeof(h->w));
+  int rc = decoder_configure();
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return COMIC_OK;
+}
+
+extern "C" int comic_destroy(comic_handle_t h) {
+  delete h;
+  return COMIC_OK;
+}
+
+extern "C" int comic_packed_bytes(comic_handle_t h, size_t* bytes) {
+  COMIC_REQUIRE(h && bytes, COMIC_E_BADARG, "packed_bytes: null argument");
+  Carver cv(nullptr);
+  comic::Packed keep = h->pk;
+  decoder_pack(h, cv, 0, true);
+  encoder_pack(h, cv, 0, true);
+  h->pk = keep;
+  *bytes = cv.off + 256;
+  return COMIC_OK;
+}
+
+extern "C" int comic_bind_weights(comic_handle_t h, const comic_weights_t* w, int with_cnn, void* packed,
+                                  size_t packed_bytes, void* stream) {
+  COMIC_REQUIRE(h && w && packed, COMIC_E_BADARG, "bind_weights: null argument");
+  size_t need;
+  comic_packed_bytes(h, &need);
+  COMIC_REQUIRE(packed_bytes >= need, COMIC_E_WORKSPACE, "bind_weights: packed buffer %zu < %zu", packed_bytes, need);
+  COMIC_REQUIRE(w->lstm_kernel && w->lstm_bias && w->init_weight && w->memory_kernel && w->query_kernel &&
+                    w->out_kernel && w->out_bias && w->embedding_map,
+                COMIC_E_BADARG, "bind_weights: missing decoder tensor");
+  if (h->cfg.alignment == 0)
+    COMIC_REQUIRE(w->attention_v && w->ln_gamma && w->ln_beta && w->temperature, COMIC_E_BADARG,
+                  "bind_weights: missing add_LN attention tensor");
+  if (h->cfg.fm_projection == 2) COMIC_REQUIRE(w->value_kernel, COMIC_E_BADARG, "bind_weights: missing value_layer");
+  if (h->cfg.context_layer) COMIC_REQUIRE(w->a_layer, COMIC_E_BADARG, "bind_weights: missing a_layer");
+  if (with_cnn) {
+    for (int i = 0; i < COMIC_NUM_CONVS; ++i)
+      COMIC_REQUIRE(w->conv_w[i] && w->bn_beta[i] && w->bn_mean[i] && w->bn_var[i], COMIC_E_BADARG,
+                    "bind_weights: missing CNN tensor %d", i);
+    if (h->cfg.legacy)
+      COMIC_REQUIRE(w->enc_ln_gamma && w->enc_ln_beta && w->enc_embed_weight, COMIC_E_BADARG,
+                    "bind_weights: missing legacy encoder head");
+  }
+  h->w = *w;
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(packed);
+  int rc = decoder_pack(h, cv, st, false);
+  if (rc) return rc;
+  rc = encoder_pack(h, cv, st, !with_cnn);
+  if (rc) return rc;
+  h->bound = true;
+  h->cnn_bound = with_cnn != 0;
+  return COMIC_OK;
+}
+
+extern "C" int comic_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes) {
+  COMIC_REQUIRE(h && bytes, COMIC_E_BADARG, "workspace_bytes: null argument");
+  COMIC_REQUIRE(B > 0 && k > 0 && T >= 0, COMIC_E_SHAPE, "workspace_bytes: bad B=%d k=%d T=%d", B, k, T);
+  if (mode == 0) return encoder_workspace_bytes(h, B, bytes);
+  if (mode == 5) {   // gemm_f32 split-K scratch
+    *bytes = (size_t)16 * B * k * sizeof(float) + 256;
+    return COMIC_OK;
+  }
+  return decoder_workspace_bytes(h, mode, B, k, T, bytes);
+}
+
+extern "C" int comic_encode_fwd(comic_handle_t h, const float* images, int B, float* fm_out, float* im_embed_out,
+                                float* mixed5c_out, void* ws, size_t ws_bytes, void* stream) {
+  COMIC_REQUIRE(h && images && fm_out && im_embed_out && ws, COMIC_E_BADARG, "encode_fwd: null argument");
+  COMIC_REQUIRE(B > 0, COMIC_E_SHAPE, "encode_fwd: bad batch %d", B);
+  return encoder_forward(h, images, B, fm_out, im_embed_out, mixed5c_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int comic_gemm_f32(comic_handle_t h, const float* A, int lda, const float* Bm, int ldb, const float* bias,
+                              float* C, int ldc, int M, int N, int K, void* ws, size_t ws_bytes, void* stream) {
+  COMIC_REQUIRE(h && A && Bm && C, COMIC_E_BADARG, "gemm_f32: null argument");
+  COMIC_REQUIRE(M > 0 && N > 0 && K > 0, COMIC_E_SHAPE, "gemm_f32: bad shape");
+  COMIC_REQUIRE(N % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0, COMIC_E_UNSUPPORTED, "gemm_f32: N, ldb, ldc must be multiples of 4");
+  (void)ws; (void)ws_bytes;
+  APlain a{};
+  a.nseg = 1;
+  a.seg[0] = ASeg{A, nullptr, lda, K, M};
+  Epi e{};
+  e.bias = bias;
+  e.nroute = 1;
+  e.r[0] = Route{0, N, C, ldc, 0};
+  e.stop_n = 0x7fffffff;
+  GemmPlan p = plan_gemm(M, N, K, h->num_sms, false);
+  cudaError_t err;
+  if (K % 4 == 0 && lda % 4 == 0) err = launch_gemm<0, 4>(a, Bm, ldb, M, N, K, e, p, (cudaStream_t)stream);
+  else err = launch_gemm<0, 1>(a, Bm, ldb, M, N, K, e, p, (cudaStream_t)stream);
+  h->launches++;
+  COMIC_CHECK_CUDA(err);
+  return COMIC_OK;
+}
+
+extern "C" int comic_launch_count(comic_handle_t h, int64_t* count) {
+  COMIC_REQUIRE(h && count, COMIC_E_BADARG, "launch_count: null argument");
+  *count = h->launches;
+  return COMIC_OK;
+}

@@ -1,0 +1,96 @@
+// comic_internal.cuh -- handle, error plumbing and workspace carving shared by
+// the translation units of libcomic_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/comic_b200.h"
+#include "gemm_f32.cuh"
+
+namespace comic {
+
+void set_error(const char* fmt, ...);
+
+#define COMIC_CHECK_CUDA(expr)                                                         \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      comic::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,           \
+                       cudaGetErrorString(_e));                                        \
+      return COMIC_E_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+#define COMIC_REQUIRE(cond, code, ...)                                                 \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      comic::set_error(__VA_ARGS__);                                                   \
+      return (code);                                                                   \
+    }                                                                                  \
+  } while (0)
+
+// One inception block of the encoder plan.
+struct BlockDesc {
+  int cin, b0, b1a, b1b, b2a, b2b, b3;
+  int conv[6];   // indices into the 57-conv table: b0, b1a, b1b, b2a, b2b, b3
+};
+
+constexpr int kNumBlocks = 9;
+
+struct Packed {
+  float* outq = nullptr;       // [R, LQ]  = [W_o | 0-pad | W_q]
+  float* outq_bias = nullptr;  // [LQ]
+  float* bn_scale[COMIC_NUM_CONVS];
+  float* bn_shift[COMIC_NUM_CONVS];
+  float* grp_w[kNumBlocks];      // [cin, b0+b1a+b2a]
+  float* grp_scale[kNumBlocks];
+  float* grp_shift[kNumBlocks];
+};
+
+}  // namespace comic
+
+struct comic_handle_s {
+  comic_cfg_t cfg;
+  int dev = 0;
+  int num_sms = 148;
+  int R, W, H, C, M, E, V, Vp, A, VAL, LQ, KX;
+  comic_weights_t w;
+  bool bound = false, cnn_bound = false;
+  comic::Packed pk;
+  int64_t launches = 0;
+};
+
+namespace comic {
+
+// Bump allocator over a caller-provided workspace; with base == nullptr it only
+// measures.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// encoder.cu
+int encoder_workspace_bytes(comic_handle_t h, int B, size_t* bytes);
+int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out, float* im_embed_out,
+                    float* mixed5c_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int encoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry);
+const BlockDesc* block_table();
+
+// decoder.cu
+int decoder_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes);
+int decoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry);
+int decoder_configure();
+
+}  // namespace comic

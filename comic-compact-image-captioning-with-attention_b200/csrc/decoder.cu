@@ -1,0 +1,1156 @@
+// decoder.cu -- attention-LSTM decoder step, beam / greedy search loops and
+// finalisation for sm_100a.
+//
+// Replaces the TF graph built by
+//   MultiHeadAttentionWrapperV3.call      common/ops_rnn.py:660-755
+//   MultiHeadAddLN.__call__ / MultiHeadDot common/ops_rnn.py:531-565, 603-632
+//   rnn_decoder_beam_search / _search     common/ops_rnn.py:49-180
+//   (TF r1.9 BeamSearchDecoder, dynamic_decode, gather_tree underneath)
+//   ModelBase._get_rnn_init               src/model_base.py:651-689
+//   ModelBase._decoder_post_process       src/model_base.py:272-314
+//
+// One decode call enqueues the whole T-step loop on the caller's stream with no
+// host synchronisation: "all beams finished" is a device-side counter that turns
+// the remaining steps into no-ops, and the executed step count is returned in a
+// device int.  Beam-search state is never gathered: every consumer reads
+// c/h/ctx through the `src` row indirection written by the beam kernel, and the
+// keys/values of an image are shared by its k beams (the reference tiles them k
+// times, src/model_base.py:130-131).
+#include <float.h>
+#include <math.h>
+
+#include "comic_internal.cuh"
+
+namespace comic {
+
+// ---------------------------------------------------------------------------
+// Small helpers.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Loop gate: step t runs only while not every row had finished after step t-1.
+__device__ __forceinline__ bool step_stopped(const int* fin_count, int t, int n_rows) {
+  return fin_count != nullptr && t > 0 && fin_count[t - 1] >= n_rows;
+}
+
+// ---------------------------------------------------------------------------
+// D3: BasicLSTMCell pointwise part.  gates = sum of split-K partials [nz][N][4R]
+// (+bias), order i,j,f,o, forget_bias 1.0.  c_prev is read through `src`.
+// Optional output dropout (DropoutWrapper): h_drop = h / keep * mask.
+// ---------------------------------------------------------------------------
+__global__ void lstm_pointwise_kernel(const float* __restrict__ gp, int nz, size_t zstride,
+                                      const float* __restrict__ bias, const float* __restrict__ c_prev,
+                                      const int* __restrict__ src, int src_limit, float* __restrict__ c_new,
+                                      float* __restrict__ h_new, float* __restrict__ h_drop,
+                                      const float* __restrict__ out_mask, float out_keep, int N, int R,
+                                      const int* fin_count, int t, int n_rows) {
+  if (step_stopped(fin_count, t, n_rows)) return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * R) return;
+  int n = i / R, j = i - n * R;
+  float g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float s = 0.f;
+    for (int z = 0; z < nz; ++z) s += gp[z * zstride + (size_t)n * 4 * R + q * R + j];
+    g[q] = s + bias[q * R + j];
+  }
+  float cp = 0.f;
+  if (c_prev) {
+    int r = src ? src[n] : n;
+    if (r >= 0 && r < src_limit) cp = c_prev[(size_t)r * R + j];
+  }
+  float cn = cp * sigmoidf_(g[2] + 1.0f) + sigmoidf_(g[0]) * tanhf(g[1]);
+  float hn = tanhf(cn) * sigmoidf_(g[3]);
+  c_new[i] = cn;
+  h_new[i] = hn;
+  if (h_drop) h_drop[i] = out_mask ? (hn / out_keep) * out_mask[i] : hn;
+}
+
+// Generic split-K reduction: out[m, n] = sum_z part[z][m][n] + bias[n].
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int nz, size_t zstride,
+                                     const float* __restrict__ bias, float* __restrict__ out, int M, int ld,
+                                     const int* fin_count, int t, int n_rows) {
+  if (step_stopped(fin_count, t, n_rows)) return;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * ld) return;
+  int n = (int)(i % ld);
+  float s = 0.f;
+  for (int z = 0; z < nz; ++z) s += part[z * zstride + i];
+  out[i] = s + (bias ? bias[n] : 0.f);
+}
+
+// x = x / keep * mask (input dropout of the DropoutWrapper) for a [N, ncols] slice.
+__global__ void dropout_rows_kernel(float* __restrict__ x, const float* __restrict__ mask, float keep, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = (x[i] / keep) * mask[i];
+}
+
+// Assemble x = [emb(tok) ; ctx[src]] densely (only needed when input dropout is on).
+__global__ void assemble_x_kernel(const float* __restrict__ emb, const int* __restrict__ tok, int V,
+                                  int lookup, const float* __restrict__ ctx, float* __restrict__ x, int N,
+                                  int W, int A) {
+  int n = blockIdx.x;
+  int id = tok[n];
+  bool ok = id >= 0 && id < V;
+  for (int j = threadIdx.x; j < W + A; j += blockDim.x) {
+    float v;
+    if (j < W) v = ok ? emb[(size_t)id * W + j] : 0.f;
+    else v = ctx[(size_t)n * A + (j - W)];
+    x[(size_t)n * (W + A) + j] = v;
+  }
+  (void)lookup; (void)N;
+}
+
+// ---------------------------------------------------------------------------
+// D4: attention scores.  One CTA per (image, position slice); a warp owns one
+// feature-map position at a time, keeps the key row in registers and scores it
+// against the k beam queries of the image.
+//   add_LN: s[h,m] = sum_{j in head h} tanh(LN(key[m]+q)[j]) * v[j] / T
+//   dot   : s[h,m] = sum_{j in head h} key[m][j] * q[j] / sqrt(R/H)
+// Two-pass moments in registers (mean, then sum (u-mean)^2), eps 1e-12, as
+// tf.contrib.layers.layer_norm does.
+// ---------------------------------------------------------------------------
+template <int R, int H, int MODE>
+__global__ void __launch_bounds__(256)
+attn_scores_kernel(const float* __restrict__ keys, const float* __restrict__ lq, int ld_lq, int q_off,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ vvec, const float* __restrict__ temperature,
+                   float* __restrict__ scores, int k, int M, int pos_per_cta, const int* fin_count, int t,
+                   int n_rows) {
+  if (step_stopped(fin_count, t, n_rows)) return;
+  constexpr int G = R / 128;        // float4 groups per lane
+  constexpr int D = R / H;          // head size
+  extern __shared__ __align__(16) float sm_q[];   // [k][R]
+  const int b = blockIdx.x;
+  const int p0 = blockIdx.y * pos_per_cta;
+  const int p1 = min(M, p0 + pos_per_cta);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < k * R; i += blockDim.x) {
+    int beam = i / R, j = i - beam * R;
+    sm_q[i] = lq[(size_t)(b * k + beam) * ld_lq + q_off + j];
+  }
+  float4 g4[G], b4[G], v4[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    int c = g * 128 + lane * 4;
+    if (MODE == 0) {
+      g4[g] = ldg4(gamma + c);
+      b4[g] = ldg4(beta + c);
+      v4[g] = ldg4(vvec + c);
+    }
+  }
+  const float inv_scale = (MODE == 0) ? (1.0f / temperature[0]) : 0.f;
+  const float dot_div = sqrtf((float)D);
+  (void)inv_scale;
+  __syncthreads();
+  for (int m = p0 + warp; m < p1; m += 8) {
+    float4 key[G];
+    const float* kr = keys + ((size_t)b * M + m) * R;
+#pragma unroll
+    for (int g = 0; g < G; ++g) key[g] = ldg4(kr + g * 128 + lane * 4);
+    for (int beam = 0; beam < k; ++beam) {
+      const float* q = sm_q + beam * R;
+      float4 u[G];
+      float part[G];
+      if (MODE == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float4 qq = *reinterpret_cast<const float4*>(q + g * 128 + lane * 4);
+          u[g].x = key[g].x + qq.x; u[g].y = key[g].y + qq.y;
+          u[g].z = key[g].z + qq.z; u[g].w = key[g].w + qq.w;
+          s += (u[g].x + u[g].y) + (u[g].z + u[g].w);
+        }
+        float mean = warp_sum(s) * (1.0f / R);
+        float vs = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float dx = u[g].x - mean, dy = u[g].y - mean, dz = u[g].z - mean, dw = u[g].w - mean;
+          vs += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+        float var = warp_sum(vs) * (1.0f / R);
+        float rstd = 1.0f / sqrtf(var + 1e-12f);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          // x*inv + (beta - mean*inv), inv = rstd*gamma  (tf.nn.batch_normalization)
+          float ix = rstd * g4[g].x, iy = rstd * g4[g].y, iz = rstd * g4[g].z, iw = rstd * g4[g].w;
+          float tx = tanhf(u[g].x * ix + (b4[g].x - mean * ix));
+          float ty = tanhf(u[g].y * iy + (b4[g].y - mean * iy));
+          float tz = tanhf(u[g].z * iz + (b4[g].z - mean * iz));
+          float tw = tanhf(u[g].w * iw + (b4[g].w - mean * iw));
+          part[g] = (tx * v4[g].x + ty * v4[g].y) + (tz * v4[g].z + tw * v4[g].w);
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float4 qq = *reinterpret_cast<const float4*>(q + g * 128 + lane * 4);
+          part[g] = (key[g].x * qq.x + key[g].y * qq.y) + (key[g].z * qq.z + key[g].w * qq.w);
+        }
+      }
+      float* srow = scores + ((size_t)(b * k + beam) * H) * M + m;
+      if (D >= 128) {
+        // a 128-channel group lies inside one head
+        float hs[H];
+#pragma unroll
+        for (int hh = 0; hh < H; ++hh) hs[hh] = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float tsum = warp_sum(part[g]);
+          hs[(g * 128) / D] += tsum;
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int hh = 0; hh < H; ++hh)
+            srow[(size_t)hh * M] = (MODE == 0) ? hs[hh] * inv_scale : hs[hh] / dot_div;
+        }
+      } else {
+        constexpr int LPH = D / 4;   // lanes per head inside a group
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float v = part[g];
+#pragma unroll
+          for (int o = LPH / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if ((lane % LPH) == 0) {
+            int hh = (g * 128 + lane * 4) / D;
+            srow[(size_t)hh * M] = (MODE == 0) ? v * inv_scale : v / dot_div;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// D4 (probability fn) + D5 + D6: softmax / signorm over the M positions of each
+// (beam, head), optional attention-map dropout, alignment-history write and
+// context ctx[n, c] = sum_m alpha[n, head(c), m] * values[b, m, c].
+// Grid (B, ceil(VAL/128)); thread = value channel; CTA y==0 writes the history.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attn_ctx_kernel(const float* __restrict__ scores, const float* __restrict__ values, int VAL,
+                float* __restrict__ ctx_out, int ld_ctx, float* __restrict__ hist_t,
+                const float* __restrict__ att_mask, float att_keep, int k, int H, int M, int prob_fn,
+                const int* fin_count, int t, int n_rows) {
+  if (step_stopped(fin_count, t, n_rows)) return;
+  extern __shared__ __align__(16) float sm_alpha[];   // [k][H][M]
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npair = k * H;
+  for (int pr = warp; pr < npair; pr += 4) {
+    const float* s = scores + ((size_t)b * npair + pr) * M;
+    float* a = sm_alpha + (size_t)pr * M;
+    float sum = 0.f;
+    if (prob_fn == 0) {
+      float mx = -INFINITY;
+      for (int m = lane; m < M; m += 32) mx = fmaxf(mx, s[m]);
+      mx = warp_max(mx);
+      for (int m = lane; m < M; m += 32) {
+        float e = expf(s[m] - mx);
+        a[m] = e;
+        sum += e;
+      }
+    } else {
+      for (int m = lane; m < M; m += 32) {
+        float e = sigmoidf_(s[m]);
+        a[m] = e;
+        sum += e;
+      }
+    }
+    sum = warp_sum(sum);
+    const float* mk = att_mask ? att_mask + ((size_t)b * npair + pr) * M : nullptr;
+    for (int m = lane; m < M; m += 32) {
+      float al = a[m] / sum;
+      if (mk) al = (al / att_keep) * mk[m];
+      a[m] = al;
+      if (hist_t && blockIdx.y == 0) hist_t[((size_t)b * npair + pr) * M + m] = al;
+    }
+  }
+  __syncthreads();
+  const int c = blockIdx.y * 128 + threadIdx.x;
+  if (c >= VAL) return;
+  const int hd = c / (VAL / H);
+  const float* vb = values + (size_t)b * M * VAL + c;
+  for (int beam0 = 0; beam0 < k; beam0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nb = min(4, k - beam0);
+    const float* a0 = sm_alpha + ((size_t)(beam0)*H + hd) * M;
+#pragma unroll 4
+    for (int m = 0; m < M; ++m) {
+      float v = __ldg(vb + (size_t)m * VAL);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nb) acc[j] = fmaf(a0[(size_t)j * H * M + m], v, acc[j]);
+    }
+    for (int j = 0; j < nb; ++j) ctx_out[(size_t)(b * k + beam0 + j) * ld_ctx + c] = acc[j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K10: TF r1.9 _beam_search_step, one CTA per image.
+// ---------------------------------------------------------------------------
+struct BestPair { float v; int i; };
+
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
+  // descending value, ties -> lower flat index (nn.top_k)
+  return (v > bv) || (v == bv && i < bi);
+}
+
+__device__ __forceinline__ float length_penalty_dev(long long len, float w) {
+  return powf(5.0f + (float)len, w) / powf(6.0f, w);
+}
+
+__global__ void __launch_bounds__(256)
+beam_step_kernel(const float* __restrict__ logits, int ld, int k, int V, int eos, float lpw,
+                 float* __restrict__ log_probs, uint8_t* __restrict__ finished, long long* __restrict__ lengths,
+                 float* __restrict__ scores_out, int* __restrict__ word_out, int* __restrict__ parent_out,
+                 int* __restrict__ tok_next, int* __restrict__ src_next, int* fin_count, int t, int n_rows) {
+  if (step_stopped(fin_count, t, n_rows)) {
+    // keep the stop condition visible to every later step
+    if (blockIdx.x == 0 && threadIdx.x == 0) fin_count[t] = n_rows;
+    return;
+  }
+  constexpr int KMAX = 16;
+  __shared__ float s_max[KMAX], s_lse[KMAX], s_cum[KMAX];
+  __shared__ unsigned char s_fin[KMAX];
+  __shared__ long long s_len[KMAX];
+  __shared__ float s_rv[8];
+  __shared__ int s_ri[8];
+  __shared__ float s_selv[KMAX];
+  __shared__ int s_seli[KMAX];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < k) {
+    s_cum[tid] = log_probs[b * k + tid];
+    s_fin[tid] = finished[b * k + tid];
+    s_len[tid] = lengths[b * k + tid];
+  }
+  // log-softmax statistics per beam row: max, log(sum(exp(x - max)))
+  for (int j = 0; j < k; ++j) {
+    const float* row = logits + (size_t)(b * k + j) * ld;
+    float mx = -INFINITY;
+    for (int i = tid; i < V; i += 256) mx = fmaxf(mx, row[i]);
+    mx = warp_max(mx);
+    if (lane == 0) s_rv[warp] = mx;
+    __syncthreads();
+    float m2 = s_rv[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m2 = fmaxf(m2, s_rv[w]);
+    __syncthreads();
+    float sm = 0.f;
+    for (int i = tid; i < V; i += 256) sm += expf(row[i] - m2);
+    sm = warp_sum(sm);
+    if (lane == 0) s_rv[warp] = sm;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot += s_rv[w];
+      s_max[j] = m2;
+      s_lse[j] = logf(tot);
+    }
+    __syncthreads();
+  }
+  const int ncand = k * V;
+  auto total_of = [&](int idx) -> float {
+    int j = idx / V, w = idx - j * V;
+    float lp;
+    if (s_fin[j]) lp = (w == eos) ? 0.0f : -FLT_MAX;
+    else lp = (logits[(size_t)(b * k + j) * ld + w] - s_max[j]) - s_lse[j];
+    return s_cum[j] + lp;
+  };
+  auto score_of = [&](int idx, float tot) -> float {
+    if (lpw == 0.0f) return tot;
+    int j = idx / V, w = idx - j * V;
+    long long len = s_len[j] + ((!s_fin[j] && w != eos) ? 1 : 0);
+    return tot / length_penalty_dev(len, lpw);
+  };
+  float pv = INFINITY;
+  int pi = -1;
+  for (int sel = 0; sel < k; ++sel) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int idx = tid; idx < ncand; idx += 256) {
+      float sc = score_of(idx, total_of(idx));
+      bool eligible = (sc < pv) || (sc == pv && idx > pi);
+      if (eligible && better(sc, idx, bv, bi)) { bv = sc; bi = idx; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_rv[warp] = bv; s_ri[warp] = bi; }
+    __syncthreads();
+    bv = s_rv[0]; bi = s_ri[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w)
+      if (better(s_rv[w], s_ri[w], bv, bi)) { bv = s_rv[w]; bi = s_ri[w]; }
+    __syncthreads();
+    pv = bv; pi = bi;
+    if (tid == 0) { s_selv[sel] = bv; s_seli[sel] = bi; }
+  }
+  __syncthreads();
+  if (tid < k) {
+    int idx = s_seli[tid];
+    if (idx == 0x7fffffff) idx = 0;   // only if every candidate is NaN
+    int par = idx / V, w = idx - par * V;
+    float tot = total_of(idx);
+    bool pfin = s_fin[par] != 0;
+    bool nfin = pfin || (w == eos);
+    long long nlen = s_len[par] + (pfin ? 0 : 1);
+    log_probs[b * k + tid] = tot;
+    finished[b * k + tid] = nfin ? 1 : 0;
+    lengths[b * k + tid] = nlen;
+    scores_out[b * k + tid] = s_selv[tid];
+    word_out[b * k + tid] = w;
+    parent_out[b * k + tid] = par;
+    if (tok_next) tok_next[b * k + tid] = w;
+    if (src_next) src_next[b * k + tid] = b * k + par;
+    if (fin_count && nfin) atomicAdd(&fin_count[t], 1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// B2: GreedyEmbeddingHelper.sample + BasicDecoder bookkeeping, one CTA per row.
+// argmax = first maximum (int32).  Outputs are NOT masked after EOS
+// (impute_finished=False).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+greedy_step_kernel(const float* __restrict__ logits, int ld, int V, int eos, int* __restrict__ ids_t,
+                   float* __restrict__ logits_t, int* __restrict__ tok_next, uint8_t* __restrict__ finished,
+                   int* fin_count, int t, int n_rows) {
+  if (step_stopped(fin_count, t, n_rows)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) fin_count[t] = n_rows;
+    return;
+  }
+  __shared__ float s_rv[4];
+  __shared__ int s_ri[4];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = logits + (size_t)n * ld;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < V; i += 128) {
+    float v = row[i];
+    if (logits_t) logits_t[(size_t)n * V + i] = v;
+    if (better(v, i, bv, bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) { s_rv[warp] = bv; s_ri[warp] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 4; ++w)
+      if (better(s_rv[w], s_ri[w], bv, bi)) { bv = s_rv[w]; bi = s_ri[w]; }
+    if (bi == 0x7fffffff) bi = 0;
+    ids_t[n] = bi;
+    tok_next[n] = bi;
+    bool f = finished[n] || (bi == eos);
+    finished[n] = f ? 1 : 0;
+    if (f) atomicAdd(&fin_count[t], 1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Loop end + finalisation.
+// ---------------------------------------------------------------------------
+__global__ void compute_T_kernel(const int* __restrict__ fin_count, int max_it, int n_rows, int* __restrict__ T_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int T = max_it;
+    for (int t = 0; t < max_it; ++t)
+      if (fin_count[t] >= n_rows) { T = t + 1; break; }
+    *T_out = T;
+  }
+}
+
+// TF r1.9 beam_search_ops.gather_tree (CPU functor semantics), one thread per
+// (batch, beam).  T_dev (optional) overrides max_time with the executed steps.
+__global__ void gather_tree_kernel(const int* __restrict__ step_ids, const int* __restrict__ parent_ids,
+                                   const int* __restrict__ max_seq_len, const long long* __restrict__ lengths64,
+                                   int Tmax, const int* __restrict__ T_dev, int B, int k, int end_token,
+                                   int* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * k) return;
+  int b = i / k, beam = i - b * k;
+  int T = T_dev ? *T_dev : Tmax;
+  for (int t = 0; t < Tmax; ++t) out[((size_t)t * B + b) * k + beam] = end_token;
+  int msl;
+  if (max_seq_len) msl = max_seq_len[b];
+  else {
+    long long mx = 0;
+    for (int j = 0; j < k; ++j) mx = lengths64[b * k + j] > mx ? lengths64[b * k + j] : mx;
+    msl = (int)mx;
+  }
+  int L = min(T, msl);
+  if (L <= 0) return;
+  out[((size_t)(L - 1) * B + b) * k + beam] = step_ids[((size_t)(L - 1) * B + b) * k + beam];
+  int parent = parent_ids[((size_t)(L - 1) * B + b) * k + beam];
+  for (int level = L - 2; level >= 0; --level) {
+    if (parent < 0 || parent >= k) return;   // TF raises InvalidArgument; never happens for our parents
+    out[((size_t)level * B + b) * k + beam] = step_ids[((size_t)level * B + b) * k + parent];
+    parent = parent_ids[((size_t)level * B + b) * k + parent];
+  }
+  bool fin = false;
+  for (int t = 0; t < L; ++t) {
+    size_t o = ((size_t)t * B + b) * k + beam;
+    if (fin) out[o] = end_token;
+    else if (out[o] == end_token) fin = true;
+  }
+}
+
+// TF r1.9 gather_tree_from_array restricted to the top beam: sorted0[t, b] =
+// slot whose history row the reference gathers for (t, b, beam 0); -1 = the
+// beam_width+1 sentinel (tf.gather_nd on GPU returns zeros there).
+__global__ void sorted_top_beam_kernel(const int* __restrict__ parent_ids, const long long* __restrict__ lengths,
+                                       int Tmax, const int* __restrict__ T_dev, int B, int k,
+                                       int* __restrict__ sorted0) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int T = *T_dev;
+  const int sentinel = k + 1;
+  long long mx = 0;
+  for (int j = 0; j < k; ++j) mx = lengths[b * k + j] > mx ? lengths[b * k + j] : mx;
+  int L = min(T, (int)mx);
+  for (int t = 0; t < Tmax; ++t) sorted0[(size_t)t * B + b] = sentinel;
+  auto masked = [&](int t, int j) -> int { return ((long long)t < lengths[b * k + j]) ? j : sentinel; };
+  if (L > 0) {
+    sorted0[(size_t)(L - 1) * B + b] = masked(L - 1, 0);
+    int parent = parent_ids[((size_t)(L - 1) * B + b) * k + 0];
+    for (int level = L - 2; level >= 0; --level) {
+      if (parent < 0 || parent >= k) break;
+      sorted0[(size_t)level * B + b] = masked(level, parent);
+      parent = parent_ids[((size_t)level * B + b) * k + parent];
+    }
+    bool fin = false;
+    for (int t = 0; t < L; ++t) {
+      size_t o = (size_t)t * B + b;
+      if (fin) sorted0[o] = sentinel;
+      else if (sorted0[o] == sentinel) fin = true;
+    }
+  }
+  // where(mask[t,b,0], sorted, beam_id 0)
+  for (int t = 0; t < Tmax; ++t) {
+    bool mk = (long long)t < lengths[b * k + 0];
+    size_t o = (size_t)t * B + b;
+    int s = mk ? sorted0[o] : 0;
+    sorted0[o] = (s >= 0 && s < k) ? s : -1;
+  }
+}
+
+// attn_out[b, h, t, m] = hist[t, b*k + sorted0[t,b], h*M + m]  (t < T), else 0.
+__global__ void attn_top_gather_kernel(const float* __restrict__ hist, const int* __restrict__ sorted0,
+                                       const int* __restrict__ T_dev, int Tmax, int B, int k, int HM, int M,
+                                       float* __restrict__ out) {
+  int t = blockIdx.x, b = blockIdx.y;
+  int T = *T_dev;
+  int s = sorted0 ? sorted0[(size_t)t * B + b] : 0;
+  int H = HM / M;
+  const float* src = (t < T && s >= 0) ? hist + ((size_t)t * B * k + (size_t)b * k + s) * HM : nullptr;
+  for (int i = threadIdx.x; i < HM; i += blockDim.x) {
+    int hh = i / M, m = i - hh * M;
+    out[(((size_t)b * H + hh) * Tmax + t) * M + m] = src ? src[i] : 0.f;
+  }
+}
+
+__global__ void fill_i32_kernel(int* p, int v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void iota_div_kernel(int* p, int n, int div) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i / div;
+}
+__global__ void beam_init_kernel(float* log_probs, uint8_t* finished, long long* lengths, int B, int k) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * k) return;
+  int j = i % k;
+  log_probs[i] = (j == 0) ? 0.0f : -INFINITY;
+  finished[i] = (j == 0) ? 0 : 1;
+  lengths[i] = 0;
+}
+
+// ---------------------------------------------------------------------------
+// Bind-time packing: [W_o | pad | W_q] panel and its bias.
+// ---------------------------------------------------------------------------
+__global__ void pack_outq_kernel(const float* __restrict__ wo, const float* __restrict__ bo,
+                                 const float* __restrict__ wq, float* __restrict__ outq,
+                                 float* __restrict__ bias, int R, int V, int Vp) {
+  int LQ = Vp + R;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)R * LQ) {
+    int r = (int)(i / LQ), c = (int)(i % LQ);
+    float v = 0.f;
+    if (c < V) v = wo[(size_t)r * V + c];
+    else if (c >= Vp) v = wq[(size_t)r * R + (c - Vp)];
+    outq[i] = v;
+  }
+  if (i < (size_t)LQ) bias[i] = (i < (size_t)V) ? bo[i] : 0.f;
+}
+
+int decoder_configure() {
+  COMIC_CHECK_CUDA(cudaFuncSetAttribute(attn_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  return COMIC_OK;
+}
+
+int decoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
+  h->pk.outq = cv.take<float>((size_t)h->R * h->LQ);
+  h->pk.outq_bias = cv.take<float>(h->LQ);
+  if (dry) return COMIC_OK;
+  size_t n = (size_t)h->R * h->LQ;
+  pack_outq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->w.out_kernel, h->w.out_bias, h->w.query_kernel,
+                                                               h->pk.outq, h->pk.outq_bias, h->R, h->V, h->Vp);
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Step driver shared by decode_step / greedy / beam.
+// ---------------------------------------------------------------------------
+struct StepBufs {
+  float* gates;        // [nz1][N][4R]
+  float* lq_part;      // [nz2][N][LQ]
+  float* lq;           // [N][LQ]
+  float* scores;       // [N][H][M]
+  float* xdense;       // [N][W+A] (input-dropout path only)
+  float* ctxraw;       // [N][VAL] (context-layer path only)
+};
+
+struct StepIO {
+  const float* keys;       // [B, M, R]
+  const float* values;     // [B, M, VAL]
+  const int* tok;          // [N]
+  const int* src;          // [N] or nullptr
+  int src_limit;
+  const float* c_prev;     // rows indexed through src
+  const float* h_prev;
+  const float* ctx_prev;
+  float* c_new;            // [N, R]
+  float* h_new;            // [N, R]
+  float* h_drop;           // [N, R] or nullptr (train): query/logits use this when set
+  float* ctx_new;          // [N, A]
+  float* hist_t;           // [N, H*M] or nullptr
+  const float* in_mask; const float* out_mask; const float* att_mask;
+  float in_keep, out_keep, att_keep;
+  const int* fin_count; int t; int n_rows;
+};
+
+static size_t step_smem_scores(int k, int R) { return (size_t)k * R * sizeof(float); }
+static size_t step_smem_ctx(int k, int H, int M) { return (size_t)k * H * M * sizeof(float); }
+
+template <int R, int H>
+static cudaError_t launch_scores(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k,
+                                 cudaStream_t st) {
+  int M = h->M;
+  // position slicing: fill the machine when there are few images
+  int slices = (2 * h->num_sms) / B;
+  if (slices < 1) slices = 1;
+  if (slices > (M + 7) / 8) slices = (M + 7) / 8;
+  int ppc = (M + slices - 1) / slices;
+  ppc = (ppc + 7) / 8 * 8;
+  slices = (M + ppc - 1) / ppc;
+  dim3 grid(B, slices);
+  size_t smem = step_smem_scores(k, R);
+  if (h->cfg.alignment == 0)
+    attn_scores_kernel<R, H, 0><<<grid, 256, smem, st>>>(io.keys, sb.lq, h->LQ, h->Vp, h->w.ln_gamma, h->w.ln_beta,
+                                                       h->w.attention_v, h->w.temperature, sb.scores, k, M, ppc,
+                                                       io.fin_count, io.t, io.n_rows);
+  else
+    attn_scores_kernel<R, H, 1><<<grid, 256, smem, st>>>(io.keys, sb.lq, h->LQ, h->Vp, h->w.ln_gamma, h->w.ln_beta,
+                                                       h->w.attention_v, h->w.temperature, sb.scores, k, M, ppc,
+                                                       io.fin_count, io.t, io.n_rows);
+  return cudaGetLastError();
+}
+
+static int dispatch_scores(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, cudaStream_t st) {
+  cudaError_t e = cudaErrorInvalidValue;
+  bool ok = true;
+  if (h->R == 512) {
+    switch (h->H) {
+      case 1: e = launch_scores<512, 1>(h, io, sb, B, k, st); break;
+      case 2: e = launch_scores<512, 2>(h, io, sb, B, k, st); break;
+      case 4: e = launch_scores<512, 4>(h, io, sb, B, k, st); break;
+      case 8: e = launch_scores<512, 8>(h, io, sb, B, k, st); break;
+      case 16: e = launch_scores<512, 16>(h, io, sb, B, k, st); break;
+      default: ok = false;
+    }
+  } else if (h->R == 256) {
+    switch (h->H) {
+      case 1: e = launch_scores<256, 1>(h, io, sb, B, k, st); break;
+      case 4: e = launch_scores<256, 4>(h, io, sb, B, k, st); break;
+      case 8: e = launch_scores<256, 8>(h, io, sb, B, k, st); break;
+      default: ok = false;
+    }
+  } else if (h->R == 1024) {
+    switch (h->H) {
+      case 1: e = launch_scores<1024, 1>(h, io, sb, B, k, st); break;
+      case 8: e = launch_scores<1024, 8>(h, io, sb, B, k, st); break;
+      case 16: e = launch_scores<1024, 16>(h, io, sb, B, k, st); break;
+      default: ok = false;
+    }
+  } else ok = false;
+  COMIC_REQUIRE(ok, COMIC_E_UNSUPPORTED, "attention kernel not instantiated for rnn_size=%d heads=%d", h->R, h->H);
+  h->launches++;
+  COMIC_CHECK_CUDA(e);
+  return COMIC_OK;
+}
+
+// One attention-wrapper step on N = B*k rows.
+static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, cudaStream_t st) {
+  const int N = B * k, R = h->R, W = h->W, A = h->A;
+  // --- gates = [emb(tok) ; ctx ; h] . K ---
+  APlain a{};
+  if (io.in_mask) {
+    // training path: x assembled densely so the input dropout mask can be applied
+    assemble_x_kernel<<<N, 256, 0, st>>>(h->w.embedding_map, io.tok, h->V, h->cfg.embed_lookup, io.ctx_prev,
+                                        sb.xdense, N, W, A);
+    size_t nx = (size_t)N * (W + A);
+    dropout_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(sb.xdense, io.in_mask, io.in_keep, nx);
+    h->launches += 2;
+    a.nseg = 2;
+    a.seg[0] = ASeg{sb.xdense, nullptr, W + A, W + A, N};
+    a.seg[1] = ASeg{io.h_prev, io.src, R, R, io.src_limit};
+  } else {
+    a.nseg = 3;
+    a.seg[0] = ASeg{h->w.embedding_map, io.tok, W, W, h->V};
+    a.seg[1] = ASeg{io.ctx_prev, io.src, A, A, io.src_limit};
+    a.seg[2] = ASeg{io.h_prev, io.src, R, R, io.src_limit};
+  }
+  GemmPlan p1 = plan_gemm(N, 4 * R, h->KX, h->num_sms, true);
+  int nz1 = gemm_num_partials(h->KX, p1);
+  Epi e1{};
+  e1.nroute = 1;
+  e1.r[0] = Route{0, 4 * R, sb.gates, 4 * R, 0};
+  e1.split_stride = (long long)N * 4 * R;
+  e1.stop = io.fin_count ? io.fin_count + (io.t > 0 ? io.t - 1 : 0) : nullptr;
+  e1.stop_n = (io.fin_count && io.t > 0) ? io.n_rows : 0x7fffffff;
+  COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.lstm_kernel, 4 * R, N, 4 * R, h->KX, e1, p1, st)));
+  h->launches++;
+  {
+    int tot = N * R;
+    lstm_pointwise_kernel<<<(tot + 255) / 256, 256, 0, st>>>(sb.gates, nz1, (size_t)N * 4 * R, h->w.lstm_bias,
+                                                          io.c_prev, io.src, io.src_limit, io.c_new, io.h_new,
+                                                          io.h_drop, io.out_mask, io.out_keep, N, R, io.fin_count,
+                                                          io.t, io.n_rows);
+    h->launches++;
+  }
+  // --- [logits | q] = h_out . [W_o | W_q] + [b_o | 0] ---
+  const float* hq = io.h_drop ? io.h_drop : io.h_new;
+  APlain a2{};
+  a2.nseg = 1;
+  a2.seg[0] = ASeg{hq, nullptr, R, R, N};
+  GemmPlan p2 = plan_gemm(N, h->LQ, R, h->num_sms, true);
+  int nz2 = gemm_num_partials(R, p2);
+  Epi e2{};
+  e2.nroute = 1;
+  e2.stop = e1.stop;
+  e2.stop_n = e1.stop_n;
+  if (nz2 == 1) {
+    e2.bias = h->pk.outq_bias;
+    e2.r[0] = Route{0, h->LQ, sb.lq, h->LQ, 0};
+    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->pk.outq, h->LQ, N, h->LQ, R, e2, p2, st)));
+    h->launches++;
+  } else {
+    e2.r[0] = Route{0, h->LQ, sb.lq_part, h->LQ, 0};
+    e2.split_stride = (long long)N * h->LQ;
+    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->pk.outq, h->LQ, N, h->LQ, R, e2, p2, st)));
+    size_t tot = (size_t)N * h->LQ;
+    splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(sb.lq_part, nz2, (size_t)N * h->LQ,
+                                                                       h->pk.outq_bias, sb.lq, N, h->LQ,
+                                                                       io.fin_count, io.t, io.n_rows);
+    h->launches += 2;
+  }
+  // --- attention ---
+  int rc = dispatch_scores(h, io, sb, B, k, st);
+  if (rc) return rc;
+  {
+    int VAL = h->VAL;
+    dim3 grid(B, (VAL + 127) / 128);
+    size_t smem = step_smem_ctx(k, h->H, h->M);
+    float* ctx_dst = h->cfg.context_layer ? sb.ctxraw : io.ctx_new;
+    int ld_ctx = h->cfg.context_layer ? VAL : A;
+    attn_ctx_kernel<<<grid, 128, smem, st>>>(sb.scores, io.values, VAL, ctx_dst, ld_ctx, io.hist_t, io.att_mask,
+                                            io.att_keep, k, h->H, h->M, h->cfg.prob_fn, io.fin_count, io.t,
+                                            io.n_rows);
+    h->launches++;
+    COMIC_CHECK_CUDA(cudaGetLastError());
+    if (h->cfg.context_layer) {
+      APlain a3{};
+      a3.nseg = 1;
+      a3.seg[0] = ASeg{sb.ctxraw, nullptr, VAL, VAL, N};
+      Epi e3{};
+      e3.nroute = 1;
+      e3.r[0] = Route{0, R, io.ctx_new, R, 0};
+      e3.stop = e1.stop;
+      e3.stop_n = e1.stop_n;
+      GemmPlan p3 = plan_gemm(N, R, VAL, h->num_sms, false);
+      COMIC_CHECK_CUDA((launch_gemm<0, 4>(a3, h->w.a_layer, R, N, R, VAL, e3, p3, st)));
+      h->launches++;
+    }
+  }
+  return COMIC_OK;
+}
+
+static void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_masks) {
+  GemmPlan p1 = plan_gemm(N, 4 * h->R, h->KX, h->num_sms, true);
+  int nz1 = gemm_num_partials(h->KX, p1);
+  GemmPlan p2 = plan_gemm(N, h->LQ, h->R, h->num_sms, true);
+  int nz2 = gemm_num_partials(h->R, p2);
+  sb.gates = cv.take<float>((size_t)nz1 * N * 4 * h->R);
+  sb.lq_part = cv.take<float>(nz2 > 1 ? (size_t)nz2 * N * h->LQ : 1);
+  sb.lq = cv.take<float>((size_t)N * h->LQ);
+  sb.scores = cv.take<float>((size_t)N * h->H * h->M);
+  sb.xdense = cv.take<float>(train_masks ? (size_t)N * (h->W + h->A) : 1);
+  sb.ctxraw = cv.take<float>(h->cfg.context_layer ? (size_t)N * h->VAL : 1);
+}
+
+struct LoopBufs {
+  StepBufs sb;
+  float *c[2], *h[2], *ctx[2];
+  float* hist;
+  int *tok, *src, *src0;
+  float* cum;
+  uint8_t* fin;
+  long long* len;
+  int* fin_count;
+  int *step_ids, *parents, *sorted0;
+  float* scores_steps;
+};
+
+static void carve_loop(comic_handle_t h, Carver& cv, int B, int k, int T, bool want_hist, LoopBufs& lb) {
+  int N = B * k;
+  carve_step(h, cv, N, lb.sb, false);
+  for (int i = 0; i < 2; ++i) {
+    lb.c[i] = cv.take<float>((size_t)N * h->R);
+    lb.h[i] = cv.take<float>((size_t)N * h->R);
+    lb.ctx[i] = cv.take<float>((size_t)N * h->A);
+  }
+  lb.hist = cv.take<float>(want_hist ? (size_t)T * N * h->H * h->M : 1);
+  lb.tok = cv.take<int>(N);
+  lb.src = cv.take<int>(N);
+  lb.src0 = cv.take<int>(N);
+  lb.cum = cv.take<float>(N);
+  lb.fin = cv.take<uint8_t>(N);
+  lb.len = cv.take<long long>(N);
+  lb.fin_count = cv.take<int>(T + 1);
+  lb.step_ids = cv.take<int>((size_t)T * N);
+  lb.parents = cv.take<int>((size_t)T * N);
+  lb.sorted0 = cv.take<int>((size_t)T * B);
+  lb.scores_steps = cv.take<float>((size_t)T * N);
+}
+
+int decoder_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes) {
+  Carver cv(nullptr);
+  if (mode == 1) {
+    LoopBufs lb;
+    carve_loop(h, cv, B, 1, T, true, lb);
+  } else if (mode == 2) {
+    LoopBufs lb;
+    carve_loop(h, cv, B, k, T, true, lb);
+  } else if (mode == 3) {
+    StepBufs sb;
+    carve_step(h, cv, B * k, sb, true);
+    cv.take<float>((size_t)B * k * h->R);
+  } else if (mode == 4) {   // rnn_init
+    cv.take<float>((size_t)B * (h->W + h->A));
+    cv.take<float>((size_t)B * 4 * h->R * 16);
+  } else {
+    set_error("workspace_bytes: unknown mode %d", mode);
+    return COMIC_E_BADARG;
+  }
+  *bytes = cv.off + 256;
+  return COMIC_OK;
+}
+
+}  // namespace comic
+
+using namespace comic;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" int comic_project_fm(comic_handle_t h, const float* fm, int B, float* keys_out, float* values_out,
+                                void* stream) {
+  COMIC_REQUIRE(h && h->bound, COMIC_E_BADARG, "project_fm: weights not bound");
+  COMIC_REQUIRE(fm && keys_out && B > 0, COMIC_E_BADARG, "project_fm: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int Mrows = B * h->M;
+  APlain a{};
+  a.nseg = 1;
+  a.seg[0] = ASeg{fm, nullptr, h->C, h->C, Mrows};
+  Epi e{};
+  e.nroute = 1;
+  e.r[0] = Route{0, h->R, keys_out, h->R, 0};
+  e.stop_n = 0x7fffffff;
+  GemmPlan p = plan_gemm(Mrows, h->R, h->C, h->num_sms, false);
+  COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.memory_kernel, h->R, Mrows, h->R, h->C, e, p, st)));
+  h->launches++;
+  if (h->cfg.fm_projection == 2) {
+    COMIC_REQUIRE(values_out && h->w.value_kernel, COMIC_E_BADARG, "project_fm: independent projection needs values_out");
+    e.r[0] = Route{0, h->R, values_out, h->R, 0};
+    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.value_kernel, h->R, Mrows, h->R, h->C, e, p, st)));
+    h->launches++;
+  }
+  return COMIC_OK;
+}
+
+extern "C" int comic_rnn_init(comic_handle_t h, const float* im_embed, int B, float* c0, float* h0,
+                              const float* in_mask, float in_keep, void* ws, size_t ws_bytes, void* stream) {
+  COMIC_REQUIRE(h && h->bound, COMIC_E_BADARG, "rnn_init: weights not bound");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = h->R, XA = h->W + h->A;
+  size_t need;
+  decoder_workspace_bytes(h, 4, B, 1, 1, &need);
+  COMIC_REQUIRE(ws_bytes >= need, COMIC_E_WORKSPACE, "rnn_init: workspace %zu < %zu", ws_bytes, need);
+  Carver cv(ws);
+  float* x0 = cv.take<float>((size_t)B * XA);
+  float* gates = cv.take<float>((size_t)B * 4 * R * 16);
+  APlain a{};
+  a.nseg = 1;
+  a.seg[0] = ASeg{im_embed, nullptr, h->E, h->E, B};
+  Epi e{};
+  e.nroute = 1;
+  e.stop_n = 0x7fffffff;
+  if (h->cfg.init_method == 1) {
+    // project_hidden: h0 = im_embed . W, c0 = 0   (src/model_base.py:658-667)
+    e.r[0] = Route{0, R, h0, R, 0};
+    GemmPlan p = plan_gemm(B, R, h->E, h->num_sms, false);
+    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.init_weight, R, B, R, h->E, e, p, st)));
+    COMIC_CHECK_CUDA(cudaMemsetAsync(c0, 0, (size_t)B * R * sizeof(float), st));
+    h->launches++;
+    return COMIC_OK;
+  }
+  // first_input: x0 = im_embed . W_I ; one LSTM step from the zero state (:675-686)
+  e.r[0] = Route{0, XA, x0, XA, 0};
+  GemmPlan p = plan_gemm(B, XA, h->E, h->num_sms, false);
+  COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.init_weight, XA, B, XA, h->E, e, p, st)));
+  h->launches++;
+  if (in_mask) {
+    size_t nx = (size_t)B * XA;
+    dropout_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(x0, in_mask, in_keep, nx);
+    h->launches++;
+  }
+  APlain a2{};
+  a2.nseg = 1;
+  a2.seg[0] = ASeg{x0, nullptr, XA, XA, B};
+  GemmPlan p2 = plan_gemm(B, 4 * R, XA, h->num_sms, true);
+  int nz = gemm_num_partials(XA, p2);
+  Epi e2{};
+  e2.nroute = 1;
+  e2.stop_n = 0x7fffffff;
+  e2.r[0] = Route{0, 4 * R, gates, 4 * R, 0};
+  e2.split_stride = (long long)B * 4 * R;
+  COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->w.lstm_kernel, 4 * R, B, 4 * R, XA, e2, p2, st)));
+  int tot = B * R;
+  lstm_pointwise_kernel<<<(tot + 255) / 256, 256, 0, st>>>(gates, nz, (size_t)B * 4 * R, h->w.lstm_bias, nullptr,
+                                                        nullptr, 0, c0, h0, nullptr, nullptr, 1.f, B, R, nullptr, 0, 0);
+  h->launches += 2;
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+extern "C" int comic_decode_step(comic_handle_t h, const float* keys, const float* values, int B, int k,
+                                 const int32_t* tokens, const float* c_in, const float* h_in, const float* ctx_in,
+                                 float* c_out, float* h_out, float* ctx_out, float* align_out, float* logits_out,
+                                 const float* in_mask, const float* out_mask, const float* att_mask, float in_keep,
+                                 float out_keep, float att_keep, void* ws, size_t ws_bytes, void* stream) {
+  COMIC_REQUIRE(h && h->bound, COMIC_E_BADARG, "decode_step: weights not bound");
+  COMIC_REQUIRE(keys && tokens && c_in && h_in && ctx_in && c_out && h_out && ctx_out, COMIC_E_BADARG,
+                "decode_step: null argument");
+  COMIC_REQUIRE(B > 0 && k > 0 && k <= 16, COMIC_E_SHAPE, "decode_step: bad B=%d k=%d", B, k);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = B * k;
+  size_t need;
+  decoder_workspace_bytes(h, 3, B, k, 1, &need);
+  COMIC_REQUIRE(ws_bytes >= need, COMIC_E_WORKSPACE, "decode_step: workspace %zu < %zu", ws_bytes, need);
+  Carver cv(ws);
+  StepBufs sb;
+  carve_step(h, cv, N, sb, true);
+  float* hdrop = cv.take<float>((size_t)N * h->R);
+  StepIO io{};
+  io.keys = keys;
+  io.values = (h->cfg.fm_projection == 1) ? keys : values;
+  COMIC_REQUIRE(io.values, COMIC_E_BADARG, "decode_step: values required for this fm_projection");
+  io.tok = tokens; io.src = nullptr; io.src_limit = N;
+  io.c_prev = c_in; io.h_prev = h_in; io.ctx_prev = ctx_in;
+  io.c_new = c_out; io.h_new = h_out; io.ctx_new = ctx_out;
+  io.h_drop = out_mask ? hdrop : nullptr;
+  io.hist_t = align_out;
+  io.in_mask = in_mask; io.out_mask = out_mask; io.att_mask = att_mask;
+  io.in_keep = in_keep; io.out_keep = out_keep; io.att_keep = att_keep;
+  io.fin_count = nullptr; io.t = 0; io.n_rows = N;
+  int rc = run_step(h, io, sb, B, k, st);
+  if (rc) return rc;
+  if (logits_out)
+    COMIC_CHECK_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)h->V * sizeof(float), sb.lq, (size_t)h->LQ * sizeof(float),
+                                       (size_t)h->V * sizeof(float), N, cudaMemcpyDeviceToDevice, st));
+  if (out_mask)   // the wrapper's cell_output is the dropped h; state h stays undropped
+    (void)0;
+  return COMIC_OK;
+}
+
+extern "C" int comic_decode_greedy(comic_handle_t h, const float* keys, const float* values, const float* c0,
+                                   const float* h0, int B, int max_it, int32_t* ids_out, float* logits_out,
+                                   float* attn_out, int32_t* T_out, void* ws, size_t ws_bytes, void* stream) {
+  COMIC_REQUIRE(h && h->bound, COMIC_E_BADARG, "decode_greedy: weights not bound");
+  COMIC_REQUIRE(keys && c0 && h0 && ids_out && T_out, COMIC_E_BADARG, "decode_greedy: null argument");
+  COMIC_REQUIRE(B > 0 && max_it >= 0, COMIC_E_SHAPE, "decode_greedy: bad B=%d max_it=%d", B, max_it);
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t need;
+  decoder_workspace_bytes(h, 1, B, 1, max_it, &need);
+  COMIC_REQUIRE(ws_bytes >= need, COMIC_E_WORKSPACE, "decode_greedy: workspace %zu < %zu", ws_bytes, need);
+  const float* vals = (h->cfg.fm_projection == 1) ? keys : values;
+  COMIC_REQUIRE(vals, COMIC_E_BADARG, "decode_greedy: values required for this fm_projection");
+  Carver cv(ws);
+  LoopBufs lb;
+  carve_loop(h, cv, B, 1, max_it, true, lb);
+  const int N = B;
+  COMIC_CHECK_CUDA(cudaMemsetAsync(lb.fin_count, 0, (max_it + 1) * sizeof(int), st));
+  COMIC_CHECK_CUDA(cudaMemsetAsync(lb.fin, 0, N, st));
+  COMIC_CHECK_CUDA(cudaMemsetAsync(lb.ctx[0], 0, (size_t)N * h->A * sizeof(float), st));
+  COMIC_CHECK_CUDA(cudaMemsetAsync(ids_out, 0, (size_t)max_it * N * sizeof(int), st));
+  if (logits_out) COMIC_CHECK_CUDA(cudaMemsetAsync(logits_out, 0, (size_t)max_it * N * h->V * sizeof(float), st));
+  fill_i32_kernel<<<(N + 255) / 256, 256, 0, st>>>(lb.tok, h->cfg.go_id, N);
+  h->launches++;
+  for (int t = 0; t < max_it; ++t) {
+    int cur = t & 1;
+    StepIO io{};
+    io.keys = keys; io.values = vals;
+    io.tok = lb.tok; io.src = nullptr; io.src_limit = N;
+    io.c_prev = (t == 0) ? c0 : lb.c[cur];
+    io.h_prev = (t == 0) ? h0 : lb.h[cur];
+    io.ctx_prev = lb.ctx[cur];
+    io.c_new = lb.c[cur ^ 1]; io.h_new = lb.h[cur ^ 1]; io.ctx_new = lb.ctx[cur ^ 1];
+    io.hist_t = attn_out ? lb.hist + (size_t)t * N * h->H * h->M : nullptr;
+    io.in_keep = io.out_keep = io.att_keep = 1.f;
+    io.fin_count = lb.fin_count; io.t = t; io.n_rows = N;
+    int rc = run_step(h, io, lb.sb, B, 1, st);
+    if (rc) return rc;
+    greedy_step_kernel<<<N, 128, 0, st>>>(lb.sb.lq, h->LQ, h->V, h->cfg.eos_id, ids_out + (size_t)t * N,
+                                         logits_out ? logits_out + (size_t)t * N * h->V : nullptr, lb.tok, lb.fin,
+                                         lb.fin_count, t, N);
+    h->launches++;
+  }
+  compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out);
+  h->launches++;
+  if (attn_out && max_it > 0) {
+    dim3 g(max_it, B);
+    attn_top_gather_kernel<<<g, 256, 0, st>>>(lb.hist, nullptr, T_out, max_it, B, 1, h->H * h->M, h->M, attn_out);
+    h->launches++;
+  }
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const float* values, const float* c0,
+                                 const float* h0, int B, int k, float lpw, int max_it, int32_t* pred_ids_out,
+                                 int32_t* step_ids_out, int32_t* parent_ids_out, float* scores_out,
+                                 int64_t* lengths_out, float* attn_top_out, int32_t* T_out, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  COMIC_REQUIRE(h && h->bound, COMIC_E_BADARG, "decode_beam: weights not bound");
+  COMIC_REQUIRE(keys && c0 && h0 && pred_ids_out && T_out, COMIC_E_BADARG, "decode_beam: null argument");
+  COMIC_REQUIRE(B > 0 && k > 0 && k <= 16 && max_it >= 0, COMIC_E_SHAPE, "decode_beam: bad B=%d k=%d max_it=%d", B, k, max_it);
+  COMIC_REQUIRE(k <= h->V, COMIC_E_SHAPE, "decode_beam: beam %d exceeds vocab %d", k, h->V);
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t need;
+  decoder_workspace_bytes(h, 2, B, k, max_it, &need);
+  COMIC_REQUIRE(ws_bytes >= need, COMIC_E_WORKSPACE, "decode_beam: workspace %zu < %zu", ws_bytes, need);
+  const float* vals = (h->cfg.fm_projection == 1) ? keys : values;
+  COMIC_REQUIRE(vals, COMIC_E_BADARG, "decode_beam: values required for this fm_projection");
+  Carver cv(ws);
+  LoopBufs lb;
+  carve_loop(h, cv, B, k, max_it, true, lb);
+  const int N = B * k;
+  int* step_ids = step_ids_out ? step_ids_out : lb.step_ids;
+  int* parents = parent_ids_out ? parent_ids_out : lb.parents;
+  float* sc = scores_out ? scores_out : lb.scores_steps;
+  COMIC_CHECK_CUDA(cudaMemsetAsync(lb.fin_count, 0, (max_it + 1) * sizeof(int), st));
+  COMIC_CHECK_CUDA(cudaMemsetAsync(lb.ctx[0], 0, (size_t)N * h->A * sizeof(float), st));
+  COMIC_CHECK_CUDA(cudaMemsetAsync(step_ids, 0, (size_t)max_it * N * sizeof(int), st));
+  COMIC_CHECK_CUDA(cudaMemsetAsync(parents, 0, (size_t)max_it * N * sizeof(int), st));
+  COMIC_CHECK_CUDA(cudaMemsetAsync(sc, 0, (size_t)max_it * N * sizeof(float), st));
+  fill_i32_kernel<<<(N + 255) / 256, 256, 0, st>>>(lb.tok, h->cfg.go_id, N);
+  iota_div_kernel<<<(N + 255) / 256, 256, 0, st>>>(lb.src0, N, k);
+  beam_init_kernel<<<(N + 255) / 256, 256, 0, st>>>(lb.cum, lb.fin, lb.len, B, k);
+  h->launches += 3;
+  for (int t = 0; t < max_it; ++t) {
+    int cur = t & 1;
+    StepIO io{};
+    io.keys = keys; io.values = vals;
+    io.tok = lb.tok;
+    if (t == 0) {
+      io.src = lb.src0; io.src_limit = B;        // tile_batch: row n reads image n / k
+      io.c_prev = c0; io.h_prev = h0;
+      io.ctx_prev = lb.ctx[0];                   // zeros
+    } else {
+      io.src = lb.src; io.src_limit = N;
+      io.c_prev = lb.c[cur]; io.h_prev = lb.h[cur]; io.ctx_prev = lb.ctx[cur];
+    }
+    io.c_new = lb.c[cur ^ 1]; io.h_new = lb.h[cur ^ 1]; io.ctx_new = lb.ctx[cur ^ 1];
+    io.hist_t = attn_top_out ? lb.hist + (size_t)t * N * h->H * h->M : nullptr;
+    io.in_keep = io.out_keep = io.att_keep = 1.f;
+    io.fin_count = lb.fin_count; io.t = t; io.n_rows = N;
+    int rc = run_step(h, io, lb.sb, B, k, st);
+    if (rc) return rc;
+    beam_step_kernel<<<B, 256, 0, st>>>(lb.sb.lq, h->LQ, k, h->V, h->cfg.eos_id, lpw, lb.cum, lb.fin, lb.len,
+                                       sc + (size_t)t * N, step_ids + (size_t)t * N, parents + (size_t)t * N,
+                                       lb.tok, lb.src, lb.fin_count, t, N);
+    h->launches++;
+  }
+  compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out);
+  gather_tree_kernel<<<(N + 127) / 128, 128, 0, st>>>(step_ids, parents, nullptr, lb.len, max_it, T_out, B, k,
+                                                     h->cfg.eos_id, pred_ids_out);
+  h->launches += 2;
+  if (lengths_out)
+    COMIC_CHECK_CUDA(cudaMemcpyAsync(lengths_out, lb.len, (size_t)N * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+  if (attn_top_out && max_it > 0) {
+    sorted_top_beam_kernel<<<(B + 127) / 128, 128, 0, st>>>(parents, lb.len, max_it, T_out, B, k, lb.sorted0);
+    dim3 g(max_it, B);
+    attn_top_gather_kernel<<<g, 256, 0, st>>>(lb.hist, lb.sorted0, T_out, max_it, B, k, h->H * h->M, h->M,
+                                             attn_top_out);
+    h->launches += 2;
+  }
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+extern "C" int comic_beam_step(comic_handle_t h, const float* logits, int ld_logits, int B, int k, int V, int eos_id,
+                               float lpw, float* log_probs, uint8_t* finished, int64_t* lengths, float* scores_out,
+                               int32_t* word_out, int32_t* parent_out, void* stream) {
+  COMIC_REQUIRE(h, COMIC_E_BADARG, "beam_step: null handle");
+  COMIC_REQUIRE(logits && log_probs && finished && lengths && scores_out && word_out && parent_out, COMIC_E_BADARG,
+                "beam_step: null argument");
+  COMIC_REQUIRE(B > 0 && k > 0 && k <= 16 && V >= k && ld_logits >= V, COMIC_E_SHAPE, "beam_step: bad shape");
+  beam_step_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, ld_logits, k, V, eos_id, lpw, log_probs, finished,
+                                                        (long long*)lengths, scores_out, word_out, parent_out,
+                                                        nullptr, nullptr, nullptr, 0, B * k);
+  h->launches++;
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+extern "C" int comic_gather_tree(comic_handle_t h, const int32_t* step_ids, const int32_t* parent_ids,
+                                 const int32_t* max_seq_len, int T, int B, int k, int end_token, int32_t* out,
+                                 void* stream) {
+  COMIC_REQUIRE(h && step_ids && parent_ids && max_seq_len && out, COMIC_E_BADARG, "gather_tree: null argument");
+  if (T <= 0 || B <= 0 || k <= 0) return COMIC_OK;
+  gather_tree_kernel<<<(B * k + 127) / 128, 128, 0, (cudaStream_t)stream>>>(step_ids, parent_ids, max_seq_len, nullptr,
+                                                                            T, nullptr, B, k, end_token, out);
+  h->launches++;
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}

@@ -1,0 +1,387 @@
+// encoder.cu -- InceptionV1 (GoogLeNet-BN) inference forward for sm_100a.
+//
+// Replaces the graph built by common/nets/inception_v1.py:29-339 under
+// inception_arg_scope (common/nets/inception_utils.py:32-82), called from
+// ModelBase._encoder (src/model_base.py:56-104) with is_training=False.
+//
+// Layout: activations NHWC fp32 in a caller-provided workspace, processed in
+// image chunks so a chunk's activations stay L2-resident between layers.
+// Every conv is an implicit GEMM (gemm_f32.cuh) whose epilogue applies the
+// folded inference BN (scale = rsqrt(var+1e-3), shift = beta - mean*scale; no
+// gamma) + ReLU and stores straight into the block's concat output at the
+// branch's channel offset.  The three 1x1 convs that read a block's input
+// (Branch_0, Branch_1/0a, Branch_2/0a) run as ONE GEMM over a packed
+// [Cin, b0+b1a+b2a] weight panel with a 3-way routed epilogue.
+#include "comic_internal.cuh"
+
+namespace comic {
+
+static const comic_conv_desc_t kConvs[COMIC_NUM_CONVS] = {
+    {7, 2, 3, 64},   {1, 1, 64, 64},  {3, 1, 64, 192},
+    // Mixed_3b
+    {1, 1, 192, 64}, {1, 1, 192, 96}, {3, 1, 96, 128}, {1, 1, 192, 16}, {3, 1, 16, 32}, {1, 1, 192, 32},
+    // Mixed_3c
+    {1, 1, 256, 128}, {1, 1, 256, 128}, {3, 1, 128, 192}, {1, 1, 256, 32}, {3, 1, 32, 96}, {1, 1, 256, 64},
+    // Mixed_4b
+    {1, 1, 480, 192}, {1, 1, 480, 96}, {3, 1, 96, 208}, {1, 1, 480, 16}, {3, 1, 16, 48}, {1, 1, 480, 64},
+    // Mixed_4c
+    {1, 1, 512, 160}, {1, 1, 512, 112}, {3, 1, 112, 224}, {1, 1, 512, 24}, {3, 1, 24, 64}, {1, 1, 512, 64},
+    // Mixed_4d
+    {1, 1, 512, 128}, {1, 1, 512, 128}, {3, 1, 128, 256}, {1, 1, 512, 24}, {3, 1, 24, 64}, {1, 1, 512, 64},
+    // Mixed_4e
+    {1, 1, 512, 112}, {1, 1, 512, 144}, {3, 1, 144, 288}, {1, 1, 512, 32}, {3, 1, 32, 64}, {1, 1, 512, 64},
+    // Mixed_4f
+    {1, 1, 528, 256}, {1, 1, 528, 160}, {3, 1, 160, 320}, {1, 1, 528, 32}, {3, 1, 32, 128}, {1, 1, 528, 128},
+    // Mixed_5b
+    {1, 1, 832, 256}, {1, 1, 832, 160}, {3, 1, 160, 320}, {1, 1, 832, 32}, {3, 1, 32, 128}, {1, 1, 832, 128},
+    // Mixed_5c
+    {1, 1, 832, 384}, {1, 1, 832, 192}, {3, 1, 192, 384}, {1, 1, 832, 48}, {3, 1, 48, 128}, {1, 1, 832, 128},
+};
+
+static BlockDesc make_block(int first) {
+  BlockDesc b;
+  b.cin = kConvs[first].c_in;
+  b.b0 = kConvs[first].c_out;
+  b.b1a = kConvs[first + 1].c_out;
+  b.b1b = kConvs[first + 2].c_out;
+  b.b2a = kConvs[first + 3].c_out;
+  b.b2b = kConvs[first + 4].c_out;
+  b.b3 = kConvs[first + 5].c_out;
+  for (int i = 0; i < 6; ++i) b.conv[i] = first + i;
+  return b;
+}
+
+static BlockDesc kBlocks[kNumBlocks];
+static bool kBlocksInit = false;
+
+const BlockDesc* block_table() {
+  if (!kBlocksInit) {
+    for (int i = 0; i < kNumBlocks; ++i) kBlocks[i] = make_block(3 + 6 * i);
+    kBlocksInit = true;
+  }
+  return kBlocks;
+}
+
+const comic_conv_desc_t* conv_table() { return kConvs; }
+
+// --------------------------------------------------------------------------
+// Bind-time packing kernels.
+// --------------------------------------------------------------------------
+__global__ void bn_fold_kernel(const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, float* __restrict__ scale,
+                               float* __restrict__ shift, int n, float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float s = 1.0f / sqrtf(var[i] + eps);
+    scale[i] = s;
+    shift[i] = beta[i] - mean[i] * s;
+  }
+}
+
+__global__ void copy_cols_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst,
+                                 int ld, int coff) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) {
+    int r = i / cols, c = i - r * cols;
+    dst[(size_t)r * ld + coff + c] = src[i];
+  }
+}
+
+int encoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
+  const BlockDesc* blk = block_table();
+  for (int i = 0; i < COMIC_NUM_CONVS; ++i) {
+    h->pk.bn_scale[i] = cv.take<float>(kConvs[i].c_out);
+    h->pk.bn_shift[i] = cv.take<float>(kConvs[i].c_out);
+  }
+  for (int b = 0; b < kNumBlocks; ++b) {
+    int ng = blk[b].b0 + blk[b].b1a + blk[b].b2a;
+    h->pk.grp_w[b] = cv.take<float>((size_t)blk[b].cin * ng);
+    h->pk.grp_scale[b] = cv.take<float>(ng);
+    h->pk.grp_shift[b] = cv.take<float>(ng);
+  }
+  if (dry) return COMIC_OK;
+  for (int i = 0; i < COMIC_NUM_CONVS; ++i) {
+    int n = kConvs[i].c_out;
+    bn_fold_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->w.bn_beta[i], h->w.bn_mean[i], h->w.bn_var[i],
+                                                   h->pk.bn_scale[i], h->pk.bn_shift[i], n, 1e-3f);
+  }
+  for (int b = 0; b < kNumBlocks; ++b) {
+    int ng = blk[b].b0 + blk[b].b1a + blk[b].b2a;
+    int src_conv[3] = {blk[b].conv[0], blk[b].conv[1], blk[b].conv[3]};
+    int coff = 0;
+    for (int j = 0; j < 3; ++j) {
+      int ci = src_conv[j];
+      int n = kConvs[ci].c_out;
+      int tot = blk[b].cin * n;
+      copy_cols_kernel<<<(tot + 255) / 256, 256, 0, st>>>(h->w.conv_w[ci], blk[b].cin, n, h->pk.grp_w[b], ng, coff);
+      copy_cols_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->pk.bn_scale[ci], 1, n, h->pk.grp_scale[b], ng, coff);
+      copy_cols_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->pk.bn_shift[ci], 1, n, h->pk.grp_shift[b], ng, coff);
+      coff += n;
+    }
+  }
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+// --------------------------------------------------------------------------
+// Pooling kernels (NHWC, 4 channels per thread).
+// slim.max_pool2d SAME: window clipped to the image (padding never wins).
+// --------------------------------------------------------------------------
+__global__ void maxpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
+                                    int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo) {
+  size_t total = (size_t)B * Ho * Wo * (C / 4);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % (C / 4));
+    size_t p = i / (C / 4);
+    int wo = (int)(p % Wo);
+    size_t q = p / Wo;
+    int ho = (int)(q % Ho);
+    int b = (int)(q / Ho);
+    int h0 = ho * stride - pad_t, w0 = wo * stride - pad_l;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dh = 0; dh < k; ++dh) {
+      int hi = h0 + dh;
+      if (hi < 0 || hi >= H) continue;
+      for (int dw = 0; dw < k; ++dw) {
+        int wi = w0 + dw;
+        if (wi < 0 || wi >= W) continue;
+        float4 v = ldg4(x + (((size_t)b * H + hi) * W + wi) * C + c4 * 4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    *reinterpret_cast<float4*>(y + p * C + c4 * 4) = m;
+  }
+}
+
+// slim.avg_pool2d(net, [7,7], stride=1) VALID on a 7x7 map -> [B, C]
+// (common/nets/inception_v1.py:326).
+__global__ void avgpool_global_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  int b = i / C, c = i - b * C;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += x[((size_t)b * HW + p) * C + c];
+  y[i] = s / (float)HW;
+}
+
+// Legacy head: LN(1024)+tanh (src/model_base.py:80-85); one CTA per row.
+__global__ void ln_tanh_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float* __restrict__ y, int n, float eps) {
+  __shared__ float red[32];
+  int row = blockIdx.x;
+  const float* xr = x + (size_t)row * n;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += xr[i];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  float mean = tot / n;
+  __syncthreads();
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { float d = xr[i] - mean; v += d * d; }
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float vt = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) vt += red[i];
+  float rstd = 1.0f / sqrtf(vt / n + eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float inv = rstd * gamma[i];
+    y[(size_t)row * n + i] = tanhf(xr[i] * inv + (beta[i] - mean * inv));
+  }
+}
+
+// --------------------------------------------------------------------------
+// Forward plan.
+// --------------------------------------------------------------------------
+static inline void same_pads(int n, int k, int s, int* out, int* before) {
+  *out = (n + s - 1) / s;
+  int pad = (*out - 1) * s + k - n;
+  if (pad < 0) pad = 0;
+  *before = pad / 2;
+}
+
+struct EncBufs {
+  float *a, *b, *t1, *t2, *p;   // ping, pong, branch temporaries, pooled input
+};
+
+static size_t enc_chunk_floats(int chunk, size_t* a, size_t* b, size_t* t1, size_t* t2, size_t* p) {
+  // a/b hold the largest stage outputs; sizes per image (floats)
+  size_t s_conv1 = (size_t)112 * 112 * 64;
+  size_t s_pool1 = (size_t)56 * 56 * 64;
+  size_t s_2c = (size_t)56 * 56 * 192;
+  size_t s_28 = (size_t)28 * 28 * 480;
+  *a = chunk * (s_conv1 > s_2c ? s_conv1 : s_2c);
+  *b = chunk * (s_pool1 > s_28 ? s_pool1 : s_28);
+  if (*b < (size_t)chunk * 56 * 56 * 64) *b = (size_t)chunk * 56 * 56 * 64;
+  // ping-pong between a and b for every stage: make both as large as the largest
+  size_t big = *a > *b ? *a : *b;
+  *a = *b = big;
+  *t1 = (size_t)chunk * 28 * 28 * 128;   // max b1a plane: 28x28x128 (3c) / 14x14x160
+  *t2 = (size_t)chunk * 28 * 28 * 32;    // max b2a plane
+  *p = (size_t)chunk * 28 * 28 * 256;    // pooled block input (max 28x28x256)
+  return *a + *b + *t1 + *t2 + *p;
+}
+
+static int enc_chunk_for(int B) { return B < 32 ? B : 32; }
+
+int encoder_workspace_bytes(comic_handle_t h, int B, size_t* bytes) {
+  (void)h;
+  size_t a, b, t1, t2, p;
+  int chunk = enc_chunk_for(B);
+  Carver cv(nullptr);
+  enc_chunk_floats(chunk, &a, &b, &t1, &t2, &p);
+  cv.take<float>(a); cv.take<float>(b); cv.take<float>(t1); cv.take<float>(t2); cv.take<float>(p);
+  cv.take<float>((size_t)chunk * 1024);   // legacy head scratch
+  *bytes = cv.off;
+  return COMIC_OK;
+}
+
+static int run_conv(comic_handle_t h, const float* x, int B, int H, int W, int ldx, int ci, float* dst,
+                    int ld_dst, int coff, int* Ho_out, int* Wo_out, cudaStream_t st) {
+  const comic_conv_desc_t& d = kConvs[ci];
+  AConv a;
+  a.x = x; a.H = H; a.W = W; a.Cin = d.c_in; a.ldx = ldx;
+  a.KH = d.k; a.KW = d.k; a.stride = d.stride;
+  same_pads(H, d.k, d.stride, &a.Ho, &a.pad_t);
+  same_pads(W, d.k, d.stride, &a.Wo, &a.pad_l);
+  int M = B * a.Ho * a.Wo, N = d.c_out, K = d.k * d.k * d.c_in;
+  Epi e{};
+  e.bias = h->pk.bn_shift[ci];
+  e.scale = h->pk.bn_scale[ci];
+  e.relu = 1;
+  e.nroute = 1;
+  e.r[0] = Route{0, N, dst, ld_dst, coff};
+  e.split_stride = 0;
+  GemmPlan p = plan_gemm(M, N, K, h->num_sms, false);
+  cudaError_t err;
+  if (d.c_in % 4 == 0) err = launch_gemm<1, 4>(a, h->w.conv_w[ci], N, M, N, K, e, p, st);
+  else err = launch_gemm<1, 1>(a, h->w.conv_w[ci], N, M, N, K, e, p, st);
+  h->launches++;
+  COMIC_CHECK_CUDA(err);
+  if (Ho_out) *Ho_out = a.Ho;
+  if (Wo_out) *Wo_out = a.Wo;
+  return COMIC_OK;
+}
+
+static int run_maxpool(comic_handle_t h, const float* x, float* y, int B, int H, int W, int C, int k, int s,
+                       int* Ho_out, int* Wo_out, cudaStream_t st) {
+  int Ho, Wo, pt, pl;
+  same_pads(H, k, s, &Ho, &pt);
+  same_pads(W, k, s, &Wo, &pl);
+  size_t total = (size_t)B * Ho * Wo * (C / 4);
+  int grid = (int)((total + 255) / 256);
+  if (grid > h->num_sms * 16) grid = h->num_sms * 16;
+  maxpool_nhwc_kernel<<<grid, 256, 0, st>>>(x, y, B, H, W, C, k, s, pt, pl, Ho, Wo);
+  h->launches++;
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  if (Ho_out) *Ho_out = Ho;
+  if (Wo_out) *Wo_out = Wo;
+  return COMIC_OK;
+}
+
+// One inception block: x [B,S,S,cin] -> y [B,S,S,cout].
+static int run_block(comic_handle_t h, int bi, const float* x, float* y, int B, int S, EncBufs& eb,
+                     cudaStream_t st) {
+  const BlockDesc& bd = block_table()[bi];
+  int cout = bd.b0 + bd.b1b + bd.b2b + bd.b3;
+  int M = B * S * S;
+  // grouped 1x1: [b0 | b1a | b2a]
+  {
+    APlain a{};
+    a.nseg = 1;
+    a.seg[0] = ASeg{x, nullptr, bd.cin, bd.cin, M};
+    int ng = bd.b0 + bd.b1a + bd.b2a;
+    Epi e{};
+    e.bias = h->pk.grp_shift[bi];
+    e.scale = h->pk.grp_scale[bi];
+    e.relu = 1;
+    e.nroute = 3;
+    e.r[0] = Route{0, bd.b0, y, cout, 0};
+    e.r[1] = Route{bd.b0, bd.b0 + bd.b1a, eb.t1, bd.b1a, 0};
+    e.r[2] = Route{bd.b0 + bd.b1a, ng, eb.t2, bd.b2a, 0};
+    GemmPlan p = plan_gemm(M, ng, bd.cin, h->num_sms, false);
+    cudaError_t err = launch_gemm<0, 4>(a, h->pk.grp_w[bi], ng, M, ng, bd.cin, e, p, st);
+    h->launches++;
+    COMIC_CHECK_CUDA(err);
+  }
+  int rc;
+  if ((rc = run_conv(h, eb.t1, B, S, S, bd.b1a, bd.conv[2], y, cout, bd.b0, nullptr, nullptr, st))) return rc;
+  if ((rc = run_conv(h, eb.t2, B, S, S, bd.b2a, bd.conv[4], y, cout, bd.b0 + bd.b1b, nullptr, nullptr, st))) return rc;
+  if ((rc = run_maxpool(h, x, eb.p, B, S, S, bd.cin, 3, 1, nullptr, nullptr, st))) return rc;
+  if ((rc = run_conv(h, eb.p, B, S, S, bd.cin, bd.conv[5], y, cout, bd.b0 + bd.b1b + bd.b2b, nullptr, nullptr, st))) return rc;
+  return COMIC_OK;
+}
+
+int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out, float* im_embed_out,
+                    float* mixed5c_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  COMIC_REQUIRE(h->cnn_bound, COMIC_E_BADARG, "encode_fwd: CNN weights not bound");
+  COMIC_REQUIRE(h->C == 832, COMIC_E_UNSUPPORTED, "encode_fwd: only cnn_fm_attention=Mixed_4f (C=832) is built");
+  size_t need;
+  encoder_workspace_bytes(h, B, &need);
+  COMIC_REQUIRE(ws_bytes >= need, COMIC_E_WORKSPACE, "encode_fwd: workspace %zu < %zu", ws_bytes, need);
+  int chunk = enc_chunk_for(B);
+  size_t sa, sb, st1, st2, sp;
+  enc_chunk_floats(chunk, &sa, &sb, &st1, &st2, &sp);
+  Carver cv(ws);
+  EncBufs eb;
+  eb.a = cv.take<float>(sa); eb.b = cv.take<float>(sb);
+  eb.t1 = cv.take<float>(st1); eb.t2 = cv.take<float>(st2); eb.p = cv.take<float>(sp);
+  float* head = cv.take<float>((size_t)chunk * 1024);
+  int rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    int nb = (B - b0 < chunk) ? (B - b0) : chunk;
+    const float* img = images + (size_t)b0 * 224 * 224 * 3;
+    int Ho, Wo;
+    // stem (inception_v1.py:70-93)
+    if ((rc = run_conv(h, img, nb, 224, 224, 3, 0, eb.a, 64, 0, &Ho, &Wo, st))) return rc;      // 112x112x64
+    if ((rc = run_maxpool(h, eb.a, eb.b, nb, 112, 112, 64, 3, 2, &Ho, &Wo, st))) return rc;     // 56x56x64
+    if ((rc = run_conv(h, eb.b, nb, 56, 56, 64, 1, eb.a, 64, 0, nullptr, nullptr, st))) return rc;
+    if ((rc = run_conv(h, eb.a, nb, 56, 56, 64, 2, eb.b, 192, 0, nullptr, nullptr, st))) return rc;  // 56x56x192
+    if ((rc = run_maxpool(h, eb.b, eb.a, nb, 56, 56, 192, 3, 2, nullptr, nullptr, st))) return rc;  // 28x28x192
+    // Mixed_3b, 3c @28
+    if ((rc = run_block(h, 0, eb.a, eb.b, nb, 28, eb, st))) return rc;   // 256
+    if ((rc = run_block(h, 1, eb.b, eb.a, nb, 28, eb, st))) return rc;   // 480
+    if ((rc = run_maxpool(h, eb.a, eb.b, nb, 28, 28, 480, 3, 2, nullptr, nullptr, st))) return rc;  // 14x14x480
+    // Mixed_4b..4e @14
+    if ((rc = run_block(h, 2, eb.b, eb.a, nb, 14, eb, st))) return rc;   // 512
+    if ((rc = run_block(h, 3, eb.a, eb.b, nb, 14, eb, st))) return rc;   // 512
+    if ((rc = run_block(h, 4, eb.b, eb.a, nb, 14, eb, st))) return rc;   // 512
+    if ((rc = run_block(h, 5, eb.a, eb.b, nb, 14, eb, st))) return rc;   // 528
+    // Mixed_4f -> the attention feature map, written straight to fm_out [B,196,832]
+    float* fm = fm_out + (size_t)b0 * 196 * 832;
+    if ((rc = run_block(h, 6, eb.b, fm, nb, 14, eb, st))) return rc;
+    if ((rc = run_maxpool(h, fm, eb.a, nb, 14, 14, 832, 2, 2, nullptr, nullptr, st))) return rc;    // 7x7x832
+    if ((rc = run_block(h, 7, eb.a, eb.b, nb, 7, eb, st))) return rc;    // 832
+    float* m5c = mixed5c_out ? mixed5c_out + (size_t)b0 * 49 * 1024 : eb.a;
+    if ((rc = run_block(h, 8, eb.b, m5c, nb, 7, eb, st))) return rc;     // 1024
+    float* emb = im_embed_out + (size_t)b0 * 1024;
+    if (!h->cfg.legacy) {
+      avgpool_global_kernel<<<(nb * 1024 + 255) / 256, 256, 0, st>>>(m5c, emb, nb, 49, 1024);
+      h->launches++;
+    } else {
+      avgpool_global_kernel<<<(nb * 1024 + 255) / 256, 256, 0, st>>>(m5c, head, nb, 49, 1024);
+      ln_tanh_rows_kernel<<<nb, 256, 0, st>>>(head, h->w.enc_ln_gamma, h->w.enc_ln_beta, eb.t1, 1024, 1e-12f);
+      h->launches += 2;
+      APlain a{};
+      a.nseg = 1;
+      a.seg[0] = ASeg{eb.t1, nullptr, 1024, 1024, nb};
+      Epi e{};
+      e.nroute = 1;
+      e.r[0] = Route{0, 1024, emb, 1024, 0};
+      GemmPlan p = plan_gemm(nb, 1024, 1024, h->num_sms, false);
+      cudaError_t err = launch_gemm<0, 4>(a, h->w.enc_embed_weight, 1024, nb, 1024, 1024, e, p, st);
+      h->launches++;
+      COMIC_CHECK_CUDA(err);
+    }
+    COMIC_CHECK_CUDA(cudaGetLastError());
+  }
+  return COMIC_OK;
+}
+
+}  // namespace comic
+
+extern "C" const comic_conv_desc_t* comic_conv_table(void) { return comic::conv_table(); }

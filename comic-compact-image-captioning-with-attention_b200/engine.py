@@ -1,0 +1,362 @@
+"""ctypes binding of libcomic_b200.so (include/comic_b200.h).
+
+PyTorch is used for device memory, the caching allocator and the current
+stream only; every FLOP of the hot path runs in the library's hand-written
+sm_100a kernels.  There is no CPU or eager fallback: if the library is missing
+or no CUDA device is present, constructing an `Engine` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import weights as wts
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcomic_b200.so')
+NUM_CONVS = 57
+
+FM_PROJ = {None: 0, 'none': 0, 'tied': 1, 'independent': 2}
+ALIGN = {'add_LN': 0, 'dot': 1}
+PROB = {'softmax': 0, 'sigmoid': 1}
+INIT = {'first_input': 0, 'project_hidden': 1}
+
+
+class ComicCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        'rnn_size', 'word_size', 'num_heads', 'fm_channels', 'fm_positions', 'embed_size', 'vocab',
+        'fm_projection', 'context_layer', 'init_method', 'alignment', 'prob_fn', 'embed_lookup',
+        'legacy', 'go_id', 'eos_id')]
+
+
+_FP = C.c_void_p
+
+
+class ComicWeights(C.Structure):
+    _fields_ = [(n, _FP) for n in (
+        'lstm_kernel', 'lstm_bias', 'init_weight', 'memory_kernel', 'value_kernel', 'query_kernel',
+        'attention_v', 'ln_gamma', 'ln_beta', 'temperature', 'a_layer', 'out_kernel', 'out_bias',
+        'embedding_map', 'enc_ln_gamma', 'enc_ln_beta', 'enc_embed_weight')] + [
+        ('conv_w', _FP * NUM_CONVS), ('bn_beta', _FP * NUM_CONVS), ('bn_mean', _FP * NUM_CONVS),
+        ('bn_var', _FP * NUM_CONVS)]
+
+
+class ComicConvDesc(C.Structure):
+    _fields_ = [('k', C.c_int32), ('stride', C.c_int32), ('c_in', C.c_int32), ('c_out', C.c_int32)]
+
+
+class ComicError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# (name, restype, argtypes) for every symbol include/comic_b200.h declares.
+_I, _F, _SZ, _P = C.c_int, C.c_float, C.c_size_t, C.c_void_p
+SIGNATURES = {
+    'comic_last_error': (C.c_char_p, []),
+    'comic_version': (C.c_char_p, []),
+    'comic_conv_table': (C.POINTER(ComicConvDesc), []),
+    'comic_create': (_I, [C.POINTER(ComicCfg), C.POINTER(_P)]),
+    'comic_destroy': (_I, [_P]),
+    'comic_packed_bytes': (_I, [_P, C.POINTER(_SZ)]),
+    'comic_bind_weights': (_I, [_P, C.POINTER(ComicWeights), _I, _P, _SZ, _P]),
+    'comic_workspace_bytes': (_I, [_P, _I, _I, _I, _I, C.POINTER(_SZ)]),
+    'comic_encode_fwd': (_I, [_P, _P, _I, _P, _P, _P, _P, _SZ, _P]),
+    'comic_project_fm': (_I, [_P, _P, _I, _P, _P, _P]),
+    'comic_rnn_init': (_I, [_P, _P, _I, _P, _P, _P, _F, _P, _SZ, _P]),
+    'comic_decode_step': (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                               _F, _F, _F, _P, _SZ, _P]),
+    'comic_decode_greedy': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    'comic_decode_beam': (_I, [_P, _P, _P, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    'comic_beam_step': (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    'comic_gather_tree': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    'comic_gemm_f32': (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
+    'comic_launch_count': (_I, [_P, C.POINTER(C.c_int64)]),
+}
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the C-ABI library and type every exported symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise ComicError('libcomic_b200.so not built (%s); run `python __graft_entry__.py build`' % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine(object):
+    """One handle = one model description on one GPU (one process per GPU)."""
+
+    def __init__(self, config, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise ComicError('comic_b200 requires a CUDA device (B200, sm_100a); no CPU fallback exists')
+        self.torch = torch
+        self.lib = load_library()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        torch.cuda.set_device(self.device)
+        self.c = config
+        d = self.dims = wts.Dims(config)
+        if config.rnn_name != 'LSTM':
+            raise ComicError('rnn_name=%s is not built (LSTM only)' % config.rnn_name)
+        if config.attn_alignment_method not in ALIGN:
+            raise ValueError('Invalid alignment method.')             # src/model_base.py:133-138
+        if config.attn_probability_fn not in PROB:
+            raise ValueError('Invalid alignment method.')             # src/model_base.py:140-145
+        if config.token_type == 'radix':
+            go, eos = config.radix_base, config.radix_base + 1        # src/model_base.py:701-703
+        else:
+            go, eos = config.wtoi['<GO>'], config.wtoi['<EOS>']
+        self.go, self.eos = int(go), int(eos)
+        cfg = ComicCfg(
+            rnn_size=d.R, word_size=d.W, num_heads=d.H, fm_channels=d.C, fm_positions=d.M,
+            embed_size=d.E, vocab=d.V, fm_projection=FM_PROJ[config.cnn_fm_projection],
+            context_layer=int(bool(config.attn_context_layer)), init_method=INIT[config.rnn_init_method],
+            alignment=ALIGN[config.attn_alignment_method], prob_fn=PROB[config.attn_probability_fn],
+            embed_lookup=int(config.token_type == 'word'), legacy=int(bool(config.legacy)),
+            go_id=self.go, eos_id=self.eos)
+        self._h = C.c_void_p()
+        self._check(self.lib.comic_create(C.byref(cfg), C.byref(self._h)))
+        self._dev_weights = {}
+        self._packed = None
+        self._ws = {}
+        self.bound_cnn = False
+
+    # -- plumbing -----------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.comic_last_error().decode()
+            if rc == -4:
+                raise NotImplementedError(msg)
+            if rc in (-1, -2):
+                raise ValueError(msg)
+            raise ComicError('comic_b200 error %d: %s' % (rc, msg))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.lib.comic_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, mode, B, k, T):
+        n = C.c_size_t()
+        self._check(self.lib.comic_workspace_bytes(self._h, mode, B, k, T, C.byref(n)))
+        key = mode
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < n.value:
+            buf = self.torch.empty(n.value, dtype=self.torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf
+
+    def f32(self, *shape):
+        return self.torch.empty(shape, dtype=self.torch.float32, device=self.device)
+
+    def to_dev(self, a, dtype=None):
+        t = self.torch.as_tensor(a)
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device).contiguous()
+
+    # -- weights ------------------------------------------------------------
+    def bind_weights(self, W, with_cnn=True):
+        """W: dict TF-variable-name -> numpy/torch fp32 array (weights.py)."""
+        torch = self.torch
+        c = self.c
+        dev = {}
+        for k, v in W.items():
+            dev[k] = torch.as_tensor(np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v,
+                                     dtype=torch.float32).to(self.device).contiguous()
+        self._dev_weights = dev
+        D, ENC, CNN = wts.DEC, wts.ENC, wts.CNN
+        cs = wts.cell_scope(c)
+        att = D + 'multi_add_attention/'
+
+        def g(name):
+            t = dev.get(name)
+            return None if t is None else C.c_void_p(t.data_ptr())
+        w = ComicWeights()
+        w.lstm_kernel = g(cs + 'kernel')
+        w.lstm_bias = g(cs + 'bias')
+        w.init_weight = g(D + ('rnn_init_input/projection/weight' if c.rnn_init_method == 'first_input'
+                               else 'rnn_initial_state/weight'))
+        w.memory_kernel = g(D + 'memory_layer/kernel')
+        w.value_kernel = g(D + 'value_layer/kernel')
+        w.query_kernel = g(att + 'query_layer/kernel')
+        w.attention_v = g(att + 'attention_v')
+        w.ln_gamma = g(att + 'LN_tanh/gamma')
+        w.ln_beta = g(att + 'LN_tanh/beta')
+        if (D + 'softmax_temperature') in dev:
+            dev[D + 'softmax_temperature'] = dev[D + 'softmax_temperature'].reshape(1).contiguous()
+        w.temperature = g(D + 'softmax_temperature')
+        w.a_layer = g(D + 'a_layer/kernel')
+        w.out_kernel = g(D + 'output_projection/kernel')
+        w.out_bias = g(D + 'output_projection/bias')
+        w.embedding_map = g(D + 'embedding_map')
+        w.enc_ln_gamma = g(ENC + 'LN_tanh/gamma')
+        w.enc_ln_beta = g(ENC + 'LN_tanh/beta')
+        w.enc_embed_weight = g(ENC + 'im_embed/weight')
+        have_cnn = with_cnn and (CNN + 'Conv2d_1a_7x7/weights') in dev
+        if have_cnn:
+            for i, (scope, _k, _s, _ci, _co) in enumerate(wts.cnn_conv_list()):
+                w.conv_w[i] = g(CNN + scope + '/weights')
+                w.bn_beta[i] = g(CNN + scope + '/BatchNorm/beta')
+                w.bn_mean[i] = g(CNN + scope + '/BatchNorm/moving_mean')
+                w.bn_var[i] = g(CNN + scope + '/BatchNorm/moving_variance')
+        n = C.c_size_t()
+        self._check(self.lib.comic_packed_bytes(self._h, C.byref(n)))
+        self._packed = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.comic_bind_weights(self._h, C.byref(w), int(have_cnn), _ptr(self._packed),
+                                                n.value, self.stream()))
+        self.bound_cnn = bool(have_cnn)
+        self._wstruct = w
+
+    # -- E1/E2 ----------------------------------------------------------------
+    def encode(self, images, want_mixed5c=False):
+        """images [B,224,224,3] fp32 NHWC on device -> (im_embed [B,1024], fm [B,196,C])."""
+        torch = self.torch
+        images = images.contiguous()
+        if images.dim() != 4 or tuple(images.shape[1:]) != (224, 224, 3):
+            raise ValueError('images must be [B,224,224,3] NHWC, got %s' % (tuple(images.shape),))
+        B = images.shape[0]
+        fm = self.f32(B, self.dims.M, self.dims.C)
+        emb = self.f32(B, self.dims.E)
+        m5c = self.f32(B, 7, 7, 1024) if want_mixed5c else None
+        ws = self._workspace(0, B, 1, 1)
+        self._check(self.lib.comic_encode_fwd(self._h, _ptr(images), B, _ptr(fm), _ptr(emb), _ptr(m5c),
+                                              _ptr(ws), ws.numel(), self.stream()))
+        return (emb, fm, m5c) if want_mixed5c else (emb, fm)
+
+    # -- D0 -------------------------------------------------------------------
+    def project_fm(self, fm):
+        B = fm.shape[0]
+        d = self.dims
+        keys = self.f32(B, d.M, d.R)
+        values = self.f32(B, d.M, d.R) if d.fm_projection == 'independent' else None
+        self._check(self.lib.comic_project_fm(self._h, _ptr(fm.contiguous()), B, _ptr(keys), _ptr(values),
+                                              self.stream()))
+        if d.fm_projection is None:
+            values = fm
+        elif d.fm_projection == 'tied':
+            values = keys
+        return keys, values
+
+    # -- D1 -------------------------------------------------------------------
+    def rnn_init(self, im_embed, in_mask=None, in_keep=1.0):
+        B = im_embed.shape[0]
+        c0, h0 = self.f32(B, self.dims.R), self.f32(B, self.dims.R)
+        ws = self._workspace(4, B, 1, 1)
+        self._check(self.lib.comic_rnn_init(self._h, _ptr(im_embed.contiguous()), B, _ptr(c0), _ptr(h0),
+                                            _ptr(in_mask), float(in_keep), _ptr(ws), ws.numel(), self.stream()))
+        return c0, h0
+
+    # -- D3-D7 (unit) ---------------------------------------------------------
+    def decode_step(self, keys, values, B, k, tokens, c_in, h_in, ctx_in, in_mask=None, out_mask=None,
+                    att_mask=None, keeps=(1.0, 1.0, 1.0)):
+        d = self.dims
+        N = B * k
+        c_out, h_out = self.f32(N, d.R), self.f32(N, d.R)
+        ctx_out = self.f32(N, d.A)
+        align = self.f32(N, d.H * d.M)
+        logits = self.f32(N, d.V)
+        ws = self._workspace(3, B, k, 1)
+        vals = None if d.fm_projection == 'tied' else values
+        self._check(self.lib.comic_decode_step(
+            self._h, _ptr(keys), _ptr(vals), B, k, _ptr(tokens), _ptr(c_in), _ptr(h_in), _ptr(ctx_in),
+            _ptr(c_out), _ptr(h_out), _ptr(ctx_out), _ptr(align), _ptr(logits),
+            _ptr(in_mask), _ptr(out_mask), _ptr(att_mask), float(keeps[0]), float(keeps[1]), float(keeps[2]),
+            _ptr(ws), ws.numel(), self.stream()))
+        return dict(c=c_out, h=h_out, attention=ctx_out, alignments=align, logits=logits)
+
+    # -- B2 -------------------------------------------------------------------
+    def decode_greedy(self, keys, values, c0, h0, max_it, want_logits=True, want_attn=True):
+        torch = self.torch
+        d = self.dims
+        B = c0.shape[0]
+        ids = torch.empty((max(max_it, 1), B), dtype=torch.int32, device=self.device)
+        logits = self.f32(max(max_it, 1), B, d.V) if want_logits else None
+        attn = self.f32(B, d.H, max(max_it, 1), d.M) if want_attn else None
+        T = torch.zeros(1, dtype=torch.int32, device=self.device)
+        ws = self._workspace(1, B, 1, max(max_it, 1))
+        vals = None if d.fm_projection == 'tied' else values
+        self._check(self.lib.comic_decode_greedy(self._h, _ptr(keys), _ptr(vals), _ptr(c0), _ptr(h0), B, max_it,
+                                                 _ptr(ids), _ptr(logits), _ptr(attn), _ptr(T), _ptr(ws),
+                                                 ws.numel(), self.stream()))
+        return dict(ids=ids, logits=logits, attn=attn, T=T)
+
+    # -- B1/B3 ----------------------------------------------------------------
+    def decode_beam(self, keys, values, c0, h0, beam, lpw, max_it, want_attn=True):
+        torch = self.torch
+        d = self.dims
+        B = c0.shape[0]
+        Tm = max(max_it, 1)
+        i32 = dict(dtype=torch.int32, device=self.device)
+        pred = torch.empty((Tm, B, beam), **i32)
+        step_ids = torch.empty((Tm, B, beam), **i32)
+        parents = torch.empty((Tm, B, beam), **i32)
+        scores = self.f32(Tm, B, beam)
+        lengths = torch.empty((B, beam), dtype=torch.int64, device=self.device)
+        attn = self.f32(B, d.H, Tm, d.M) if want_attn else None
+        T = torch.zeros(1, dtype=torch.int32, device=self.device)
+        ws = self._workspace(2, B, beam, Tm)
+        vals = None if d.fm_projection == 'tied' else values
+        self._check(self.lib.comic_decode_beam(self._h, _ptr(keys), _ptr(vals), _ptr(c0), _ptr(h0), B, beam,
+                                               float(lpw), max_it, _ptr(pred), _ptr(step_ids), _ptr(parents),
+                                               _ptr(scores), _ptr(lengths), _ptr(attn), _ptr(T), _ptr(ws),
+                                               ws.numel(), self.stream()))
+        return dict(predicted_ids=pred, step_ids=step_ids, parent_ids=parents, scores=scores,
+                    lengths=lengths, attn=attn, T=T)
+
+    # -- K10 / K11 / GEMM (unit) ----------------------------------------------
+    def beam_step(self, logits, log_probs, finished, lengths, eos, lpw):
+        torch = self.torch
+        B, k, V = logits.shape
+        logits = logits.contiguous()
+        scores = self.f32(B, k)
+        word = torch.empty((B, k), dtype=torch.int32, device=self.device)
+        parent = torch.empty((B, k), dtype=torch.int32, device=self.device)
+        self._check(self.lib.comic_beam_step(self._h, _ptr(logits), V, B, k, V, int(eos), float(lpw),
+                                             _ptr(log_probs), _ptr(finished), _ptr(lengths), _ptr(scores),
+                                             _ptr(word), _ptr(parent), self.stream()))
+        return scores, word, parent
+
+    def gather_tree(self, step_ids, parent_ids, max_seq_len, end_token):
+        T, B, k = step_ids.shape
+        out = self.torch.empty_like(step_ids)
+        self._check(self.lib.comic_gather_tree(self._h, _ptr(step_ids.contiguous()), _ptr(parent_ids.contiguous()),
+                                               _ptr(max_seq_len.contiguous()), T, B, k, int(end_token), _ptr(out),
+                                               self.stream()))
+        return out
+
+    def gemm(self, A, Bm, bias=None):
+        M, K = A.shape
+        N = Bm.shape[1]
+        out = self.f32(M, N)
+        self._check(self.lib.comic_gemm_f32(self._h, _ptr(A), A.stride(0), _ptr(Bm), Bm.stride(0), _ptr(bias),
+                                            _ptr(out), N, M, N, K, None, 0, self.stream()))
+        return out
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._check(self.lib.comic_launch_count(self._h, C.byref(n)))
+        return n.value

@@ -1,0 +1,172 @@
+"""`CaptionModel` / `ModelBase` call surface of the reference
+(src/model.py:21-73, src/model_base.py) over the CUDA engine.
+
+The reference builds a TF graph once and the session loop runs
+`sess.run(m.infer_output)` per batch (src/infer_fn.py:130).  Here the model
+object owns an `Engine` with bound weights and `run()` executes one batch
+eagerly on the current CUDA stream; `infer_output` evaluates the batch given as
+`batch_ops` (the reference's attribute of the same name).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import rops
+from . import weights as wts
+from .engine import Engine
+
+
+def number_to_base(n, base):
+    """common/ops.py:25-40."""
+    if base < 2:
+        raise ValueError('Base cannot be less than 2.')
+    if n < 0:
+        sign = -1
+        n *= sign
+    elif n == 0:
+        return [0]
+    else:
+        sign = 1
+    digits = []
+    while n:
+        digits.append(sign * int(n % base))
+        n //= base
+    return digits[::-1]
+
+
+class ModelBase(object):
+    """src/model_base.py:32-46 + the helpers the inference path needs."""
+
+    def __init__(self, config):
+        self._config = c = config
+        assert c.token_type in ['radix', 'word', 'char']
+        if c.token_type == 'radix':
+            self._softmax_size = c.radix_base + 2
+        else:
+            self._softmax_size = len(c.itow)
+
+    def is_training(self):
+        return self.mode == 'train'
+
+    # -- encoder (src/model_base.py:56-104) ----------------------------------
+    def _encoder(self, images):
+        self.im_embed, self.cnn_fmaps = self.engine.encode(images)
+        return self.im_embed, self.cnn_fmaps
+
+    # -- _rnn_dynamic_decoder ids / iterations (src/model_base.py:692-714) ---
+    def _start_end_ids(self):
+        c = self._config
+        if c.token_type == 'radix':
+            return int(c.radix_base), int(c.radix_base + 1)
+        return int(c.wtoi['<GO>']), int(c.wtoi['<EOS>'])
+
+    def _maximum_iterations(self):
+        c = self._config
+        m = c.infer_max_length
+        if c.token_type == 'radix':
+            m *= len(number_to_base(len(c.wtoi), c.radix_base))
+        elif c.token_type == 'char':
+            m *= 5
+        return m
+
+    # -- decoder (src/model_base.py:109-184) ---------------------------------
+    def _decoder_rnn(self):
+        c = self._config
+        eng = self.engine
+        align = c.attn_alignment_method
+        if align == 'add_LN':
+            att_mech = rops.MultiHeadAddLN
+        elif align == 'dot':
+            att_mech = rops.MultiHeadDot
+        else:
+            raise ValueError('Invalid alignment method.')
+        if c.attn_probability_fn not in ('softmax', 'sigmoid'):
+            raise ValueError('Invalid alignment method.')
+        batch_size = self.im_embed.shape[0]
+        is_inference = self.mode == 'infer'
+        beam_search = is_inference and c.infer_beam_size > 1
+        rnn_init = rops.LSTMStateTuple(*eng.rnn_init(self.im_embed))          # _get_rnn_init :651-689
+        cnn_attention = att_mech(c.rnn_size, self.cnn_fmaps, c.cnn_fm_projection, c.attn_num_heads,
+                                 memory_sequence_length=None, probability_fn=c.attn_probability_fn,
+                                 engine=eng)
+        attention_cell = rops.MultiHeadAttentionWrapperV3(
+            deep_output_layer=False, context_layer=c.attn_context_layer, alignments_keep_prob=1.0,
+            cell=c.rnn_name, attention_mechanism=cnn_attention, attention_layer_size=None,
+            alignment_history=True, cell_input_fn=None, output_attention=False,
+            initial_cell_state=rnn_init)
+        start_id, end_id = self._start_end_ids()
+        max_it = self._maximum_iterations()
+        if beam_search:
+            raw = rops.rnn_decoder_beam_search(attention_cell, None, None, batch_size, c.infer_beam_size,
+                                               c.infer_length_penalty_weight, max_it, start_id, end_id)
+        else:
+            raw = rops.rnn_decoder_search(attention_cell, None, None, batch_size, max_it, start_id, end_id)
+        logits, output_ids, attn_maps = self._decoder_post_process(raw, top_beam=True)
+        self.dec_preds, self.dec_logits, self.dec_attn_maps = output_ids, logits, attn_maps
+        return logits, output_ids, attn_maps
+
+    # -- src/model_base.py:272-314 ---------------------------------------------
+    def _decoder_post_process(self, rnn_raw_outputs, top_beam=True):
+        beam_search = (self.mode == 'infer' and rnn_raw_outputs[0].dim() > 2)
+        if beam_search:
+            predicted_ids, scores, dec_states = rnn_raw_outputs          # (time, batch, beam)
+            if top_beam:
+                output_ids = predicted_ids[:, :, 0].transpose(0, 1)      # (batch, seq_len)
+                logits = scores[:, :, 0].transpose(0, 1)
+            else:
+                output_ids = predicted_ids.permute(2, 1, 0)              # (beam, batch, time)
+                logits = scores.permute(2, 1, 0)
+        else:
+            output_ids, logits, dec_states = rnn_raw_outputs
+            logits = logits.transpose(0, 1)
+            output_ids = output_ids.transpose(0, 1)
+        # the engine already returns the (reordered, top-beam) map as [B, H, T, M]
+        attn_map = dec_states.alignment_history
+        return logits, output_ids, attn_map
+
+
+class CaptionModel(ModelBase):
+    """src/model.py:21-73.  mode 'infer' is served by the CUDA engine in this
+    round; 'train' / 'eval' live in train.py (teacher-forced path)."""
+
+    def __init__(self, config, mode, batch_ops=None, reuse=False, name=None, weights=None, engine=None):
+        assert mode in ['train', 'eval', 'infer']
+        super(CaptionModel, self).__init__(config)
+        self.mode = mode
+        self.batch_ops = batch_ops
+        self.reuse = reuse
+        self.name = name
+        if engine is None:
+            engine = Engine(config)
+            if weights is None:
+                weights = wts.init_weights(config, seed=getattr(config, 'rand_seed', 48964896))
+            engine.bind_weights(weights)
+        self.engine = engine
+        if mode != 'infer':
+            raise NotImplementedError("mode '%s' is not built on the CUDA path yet (DESIGN.md, scope)" % mode)
+
+    def restore_model(self, weights):
+        """ModelBase.restore_model (src/model_base.py:422-490): bind a W-table."""
+        self.engine.bind_weights(weights)
+
+    def run(self, images=None):
+        """One `sess.run(self.infer_output)`: images [B,224,224,3] NHWC fp32
+        (host numpy / torch, or device tensor).  Returns [dec_preds (B,T) int32
+        numpy, attn_maps (B,H,T,M) fp32 numpy]."""
+        eng = self.engine
+        if images is None:
+            images = self.batch_ops[0]
+        dev_images = eng.to_dev(images, eng.torch.float32)
+        self._encoder(dev_images)
+        self._decoder_rnn()
+        return [self.dec_preds.contiguous().cpu().numpy(), self.dec_attn_maps.contiguous().cpu().numpy()]
+
+    @property
+    def infer_output(self):
+        return self.run()
+
+
+def synthetic_images(batch, seed=0):
+    """uniform(-1,1) fp32 [B,224,224,3], seeded."""
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1.0, 1.0, size=(batch, 224, 224, 3)).astype(np.float32)

@@ -1,0 +1,201 @@
+/*
+ * comic_b200.h -- C ABI of libcomic_b200.so, the B200 (sm_100a) engine behind the
+ * COMIC caption-decoding hot path.
+ *
+ * The reference (jiahuei/COMIC-Compact-Image-Captioning-with-Attention) has no
+ * FFI: its boundary is the Python call surface that the session loops drive
+ * (SURVEY.md §8b).  Each entry point below names the reference call it replaces
+ * (file:line under the reference tree).  The Python shim in
+ * comic-compact-image-captioning-with-attention_b200/ binds these with ctypes
+ * and re-exposes the reference's own signatures (rops.*, CaptionModel).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative COMIC_E_* code;
+ *     comic_last_error() returns a thread-local message for the last failure;
+ *   - all tensor arguments are DEVICE pointers unless named host_*; row-major,
+ *     fp32 unless stated; ids/parents int32, lengths int64, flags uint8;
+ *   - the caller (PyTorch's allocator in the shim) owns every device buffer,
+ *     including `packed` weights and per-call `ws` workspaces; the library never
+ *     allocates or frees device memory and never synchronises the stream;
+ *   - a handle is bound to one device; calls on one handle are not re-entrant;
+ *     distinct handles are independent (one per GPU / process);
+ *   - `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef COMIC_B200_H_
+#define COMIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COMIC_OK             0
+#define COMIC_E_BADARG      -1
+#define COMIC_E_SHAPE       -2
+#define COMIC_E_CUDA        -3
+#define COMIC_E_UNSUPPORTED -4
+#define COMIC_E_WORKSPACE   -5
+
+#define COMIC_NUM_CONVS 57   /* common/nets/inception_v1.py:70-261 */
+
+typedef struct comic_handle_s* comic_handle_t;
+
+/* Model description = the config.pkl fields that shape the graph
+ * (src/model_base.py:40-46, 109-184, 606-689). */
+typedef struct {
+  int32_t rnn_size;        /* R: c.rnn_size (512) */
+  int32_t word_size;       /* W: c.rnn_word_size (256) */
+  int32_t num_heads;       /* H: c.attn_num_heads */
+  int32_t fm_channels;     /* C: channels of c.cnn_fm_attention (832 for Mixed_4f) */
+  int32_t fm_positions;    /* M: 196 */
+  int32_t embed_size;      /* E: 1024 (im_embed) */
+  int32_t vocab;           /* V: softmax size (radix_base+2 | len(itow)) */
+  int32_t fm_projection;   /* c.cnn_fm_projection: 0 none, 1 tied, 2 independent */
+  int32_t context_layer;   /* c.attn_context_layer */
+  int32_t init_method;     /* c.rnn_init_method: 0 first_input, 1 project_hidden */
+  int32_t alignment;       /* c.attn_alignment_method: 0 add_LN, 1 dot */
+  int32_t prob_fn;         /* c.attn_probability_fn: 0 softmax, 1 sigmoid(_signorm) */
+  int32_t embed_lookup;    /* 0: one_hot x matmul (radix/char; id outside [0,V) -> zero row);
+                              1: embedding_lookup (word)  (src/model_base.py:557-594) */
+  int32_t legacy;          /* c.legacy: LN+tanh+linear encoder head (src/model_base.py:80-91) */
+  int32_t go_id, eos_id;   /* src/model_base.py:701-706 */
+} comic_cfg_t;
+
+/* Device pointers to the reference's variables, TF shapes. */
+typedef struct {
+  const float* lstm_kernel;      /* [W+A+R, 4R] gate order i,j,f,o */
+  const float* lstm_bias;        /* [4R] */
+  const float* init_weight;      /* first_input: [E, W+A]; project_hidden: [E, R] */
+  const float* memory_kernel;    /* [C, R] */
+  const float* value_kernel;     /* [C, R] (independent) or NULL */
+  const float* query_kernel;     /* [R, R] */
+  const float* attention_v;      /* [R] */
+  const float* ln_gamma;         /* [R] */
+  const float* ln_beta;          /* [R] */
+  const float* temperature;      /* [1] */
+  const float* a_layer;          /* [VAL, R] or NULL */
+  const float* out_kernel;       /* [R, V] */
+  const float* out_bias;         /* [V] */
+  const float* embedding_map;    /* [V, W] */
+  const float* enc_ln_gamma;     /* legacy [E] or NULL */
+  const float* enc_ln_beta;      /* legacy [E] or NULL */
+  const float* enc_embed_weight; /* legacy [E, E] or NULL */
+  /* InceptionV1, conv order = comic_conv_table() */
+  const float* conv_w[COMIC_NUM_CONVS];    /* HWIO */
+  const float* bn_beta[COMIC_NUM_CONVS];
+  const float* bn_mean[COMIC_NUM_CONVS];
+  const float* bn_var[COMIC_NUM_CONVS];
+} comic_weights_t;
+
+typedef struct { int32_t k, stride, c_in, c_out; } comic_conv_desc_t;
+
+const char* comic_last_error(void);
+const char* comic_version(void);
+
+/* The 57 (k, stride, c_in, c_out) conv descriptors in weight order. */
+const comic_conv_desc_t* comic_conv_table(void);
+
+/* Replaces graph construction: CaptionModel.__init__ src/model.py:23-73. */
+int comic_create(const comic_cfg_t* cfg, comic_handle_t* out);
+int comic_destroy(comic_handle_t h);
+
+/* Bytes of the engine-layout weight pack ([W_o|W_q] panel, folded BN
+ * scale/shift, grouped 1x1 conv panels). */
+int comic_packed_bytes(comic_handle_t h, size_t* bytes);
+/* Replaces ModelBase.restore_model src/model_base.py:422-490 (variables ->
+ * engine).  `with_cnn` = 0 binds the decoder only. */
+int comic_bind_weights(comic_handle_t h, const comic_weights_t* w, int with_cnn,
+                       void* packed, size_t packed_bytes, void* stream);
+
+/* mode: 0 encode, 1 decode_greedy, 2 decode_beam, 3 decode_step. */
+int comic_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes);
+
+/* E1+E2: ModelBase._encoder src/model_base.py:56-104 (InceptionV1 forward,
+ * common/nets/inception_v1.py:29-339).  images [B,224,224,3] NHWC in [-1,1];
+ * fm_out [B,196,C]; im_embed_out [B,1024]; mixed5c_out optional [B,7,7,1024]. */
+int comic_encode_fwd(comic_handle_t h, const float* images, int B, float* fm_out,
+                     float* im_embed_out, float* mixed5c_out, void* ws, size_t ws_bytes,
+                     void* stream);
+
+/* D0: MultiHeadAttV3.__init__ common/ops_rnn.py:441-477: keys = fm.W_k once per
+ * IMAGE (the reference does it per tiled beam row); values_out only for
+ * `independent`. fm [B,M,C]; keys_out [B,M,R]; values_out [B,M,R] or NULL. */
+int comic_project_fm(comic_handle_t h, const float* fm, int B, float* keys_out,
+                     float* values_out, void* stream);
+
+/* D1: ModelBase._get_rnn_init src/model_base.py:651-689. im_embed [B,E] ->
+ * c0,h0 [B,R]. in_mask optional [B,W+A] 0/1 dropout mask (train), keep prob in_keep. */
+int comic_rnn_init(comic_handle_t h, const float* im_embed, int B, float* c0, float* h0,
+                   const float* in_mask, float in_keep, void* ws, size_t ws_bytes, void* stream);
+
+/* D3-D7: one MultiHeadAttentionWrapperV3.call + output layer
+ * (common/ops_rnn.py:660-755, src/model_base.py:541-543) on N = B*k rows whose
+ * memory is keys/values of image n / k.  For unit parity.
+ *   tokens [N] i32; c_in,h_in [N,R]; ctx_in [N,A];
+ *   outputs: c_out,h_out [N,R]; ctx_out [N,A]; align_out [N,H*M]; logits_out [N,V].
+ *   Optional 0/1 dropout masks (NULL = off): in_mask [N,W+A], out_mask [N,R],
+ *   att_mask [N,H*M] with keep probabilities. */
+int comic_decode_step(comic_handle_t h, const float* keys, const float* values, int B, int k,
+                      const int32_t* tokens, const float* c_in, const float* h_in,
+                      const float* ctx_in, float* c_out, float* h_out, float* ctx_out,
+                      float* align_out, float* logits_out,
+                      const float* in_mask, const float* out_mask, const float* att_mask,
+                      float in_keep, float out_keep, float att_keep,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* B2: rops.rnn_decoder_search(greedy_search=True) common/ops_rnn.py:115-180.
+ *   ids_out [max_it,B] i32; logits_out [max_it,B,V] or NULL;
+ *   attn_out [B,H,max_it,M] or NULL (layout of _decoder_post_process
+ *   src/model_base.py:307-313); T_out device int32[1] = executed steps. */
+int comic_decode_greedy(comic_handle_t h, const float* keys, const float* values,
+                        const float* c0, const float* h0, int B, int max_it,
+                        int32_t* ids_out, float* logits_out, float* attn_out, int32_t* T_out,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* B1+B3: rops.rnn_decoder_beam_search common/ops_rnn.py:49-112 (TF r1.9
+ * BeamSearchDecoder + dynamic_decode + finalize) on B images x k beams.
+ * c0,h0 are per IMAGE [B,R] (tile_batch is implicit).
+ *   pred_ids_out   [max_it,B,k] i32  gather_tree'd ids (FinalBeamSearchDecoderOutput.predicted_ids)
+ *   step_ids_out   [max_it,B,k] i32  raw per-step word ids (optional)
+ *   parent_ids_out [max_it,B,k] i32  backpointers
+ *   scores_out     [max_it,B,k] f32  per-step top-k scores
+ *   lengths_out    [B,k] i64
+ *   attn_top_out   [B,H,max_it,M] f32 or NULL: reordered alignment history, top beam
+ *                  (src/model_base.py:296-313)
+ *   T_out          device int32[1]: executed steps; rows t >= T are EOS / 0. */
+int comic_decode_beam(comic_handle_t h, const float* keys, const float* values,
+                      const float* c0, const float* h0, int B, int k, float length_penalty_weight,
+                      int max_it, int32_t* pred_ids_out, int32_t* step_ids_out,
+                      int32_t* parent_ids_out, float* scores_out, int64_t* lengths_out,
+                      float* attn_top_out, int32_t* T_out, void* ws, size_t ws_bytes, void* stream);
+
+/* K10 alone: TF r1.9 `_beam_search_step` (called through common/ops_rnn.py:88-104)
+ * on given logits [B,k,V] (row stride ld_logits) and beam state; updates
+ * log_probs [B,k], finished [B,k] u8, lengths [B,k] i64 in place and writes
+ * scores/word/parent [B,k]. */
+int comic_beam_step(comic_handle_t h, const float* logits, int ld_logits, int B, int k, int V,
+                    int eos_id, float length_penalty_weight, float* log_probs,
+                    uint8_t* finished, int64_t* lengths, float* scores_out,
+                    int32_t* word_out, int32_t* parent_out, void* stream);
+
+/* K11: TF r1.9 beam_search_ops.gather_tree. step_ids,parent_ids,out [T,B,k] i32;
+ * max_seq_len [B] i32. */
+int comic_gather_tree(comic_handle_t h, const int32_t* step_ids, const int32_t* parent_ids,
+                      const int32_t* max_seq_len, int T, int B, int k, int end_token,
+                      int32_t* out, void* stream);
+
+/* The dense kernel on its own (unit parity / roofline): C[M,N] = A[M,K].B[K,N]
+ * (+bias[N]); row-major fp32, lda/ldb/ldc in elements; N, ldb, ldc % 4 == 0. */
+int comic_gemm_f32(comic_handle_t h, const float* A, int lda, const float* Bm, int ldb,
+                   const float* bias, float* C, int ldc, int M, int N, int K,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int comic_launch_count(comic_handle_t h, int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMIC_B200_H_ */

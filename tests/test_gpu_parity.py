@@ -1,0 +1,306 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the NumPy oracle
+on the same seeded inputs.  Tolerances: fp32 tensors 1e-3 relative (north_star)
+-- the f32-exact path is held to 2e-4; ids / parents / lengths bit-exact."""
+import numpy as np
+import pytest
+
+from _common import comic_config, word_config, make_weights, images, fake_features, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-4
+
+
+@pytest.fixture(scope='module')
+def torch_mod():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return torch
+
+
+def _engine(c, W, with_cnn=True):
+    from comic_b200.engine import Engine
+    eng = Engine(c)
+    eng.bind_weights(W, with_cnn=with_cnn)
+    return eng
+
+
+@pytest.mark.parametrize('M,N,K', [(24, 2048, 1280), (7, 64, 36), (300, 132, 147), (1536, 772, 512),
+                                   (129, 68, 520), (64, 2048, 768)])
+def test_gemm_f32(torch_mod, M, N, K):
+    torch = torch_mod
+    c = comic_config()
+    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False)
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bm = rng.standard_normal((K, N)).astype(np.float32)
+    bias = rng.standard_normal((N,)).astype(np.float32)
+    out = eng.gemm(eng.to_dev(A), eng.to_dev(Bm), eng.to_dev(bias)).cpu().numpy()
+    ref = A.astype(np.float64) @ Bm.astype(np.float64) + bias
+    assert rel_err(out, ref) < 1e-5
+
+
+def test_encoder_matches_oracle(torch_mod):
+    import inception_v1_oracle as I
+    c = comic_config()
+    W = make_weights(c)
+    eng = _engine(c, W)
+    img = images(3)
+    emb, fm, m5c = eng.encode(eng.to_dev(img), want_mixed5c=True)
+    o_emb, o_fm, ep = I.encoder(img, W, c)
+    assert fm.shape == (3, 196, 832) and emb.shape == (3, 1024)
+    assert rel_err(fm.cpu().numpy(), o_fm) < TOL
+    assert rel_err(m5c.cpu().numpy(), ep['Mixed_5c']) < TOL
+    assert rel_err(emb.cpu().numpy(), o_emb) < TOL
+
+
+def test_encoder_chunking_batch_independent(torch_mod):
+    """Images are independent units: batch of 35 (two chunks) == singles."""
+    c = comic_config()
+    W = make_weights(c)
+    eng = _engine(c, W)
+    img = images(35, seed=5)
+    emb, fm = eng.encode(eng.to_dev(img))
+    emb1, fm1 = eng.encode(eng.to_dev(img[33:34]))
+    assert torch_mod.equal(fm[33:34], fm1)
+    assert torch_mod.equal(emb[33:34], emb1)
+
+
+CONFIGS = {
+    'comic256': lambda: comic_config(),
+    'word_none_h1': lambda: word_config(n_words=1000),
+    'independent_h4': lambda: comic_config(cnn_fm_projection='independent', attn_num_heads=4),
+    'dot_sigmoid': lambda: comic_config(attn_alignment_method='dot', attn_probability_fn='sigmoid'),
+    'legacy': lambda: comic_config(legacy=True),
+    'context_layer': lambda: comic_config(attn_context_layer=True, cnn_fm_projection='none'),
+}
+
+
+@pytest.mark.parametrize('name', list(CONFIGS))
+def test_decode_step_matches_oracle(torch_mod, name):
+    import comic_oracle as O
+    torch = torch_mod
+    c = CONFIGS[name]()
+    W = make_weights(c, include_cnn=False)
+    eng = _engine(c, W, with_cnn=False)
+    B, k = 3, 3
+    im, fm = fake_features(B)
+    dec = O.Decoder(W, c)
+    dec.setup_memory(O.tile_batch(fm, k))
+    c0, h0 = dec.init_state(O.tile_batch(im, k))
+    state = dec.zero_state((c0, h0))
+    rng = np.random.default_rng(11)
+    state['attention'] = rng.standard_normal(state['attention'].shape).astype(np.float32) * 0.3
+    state['c'] = state['c'] + rng.standard_normal(state['c'].shape).astype(np.float32) * 0.1
+    state['h'] = np.tanh(state['h'] + rng.standard_normal(state['h'].shape).astype(np.float32) * 0.1)
+    toks = rng.integers(0, dec.V, size=(B * k,)).astype(np.int32)
+    if c.token_type == 'radix':
+        toks[0] = -1                     # PAD -> one-hot zero row
+    cell_out, new_state, al = dec.call(dec.embed(toks), state)
+    logits = dec.output_layer(cell_out)
+
+    fm_d = eng.to_dev(fm)
+    keys, values = eng.project_fm(fm_d)
+    assert rel_err(keys.cpu().numpy(), dec.keys[::k]) < TOL
+    gc0, gh0 = eng.rnn_init(eng.to_dev(im))
+    assert rel_err(gc0.cpu().numpy(), c0[::k]) < TOL
+    assert rel_err(gh0.cpu().numpy(), h0[::k]) < TOL
+    r = eng.decode_step(keys, values, B, k, eng.to_dev(toks), eng.to_dev(state['c']), eng.to_dev(state['h']),
+                        eng.to_dev(state['attention']))
+    assert rel_err(r['c'].cpu().numpy(), new_state['c']) < TOL
+    assert rel_err(r['h'].cpu().numpy(), new_state['h']) < TOL
+    assert rel_err(r['logits'].cpu().numpy(), logits) < TOL
+    assert rel_err(r['alignments'].cpu().numpy(), al) < TOL
+    assert rel_err(r['attention'].cpu().numpy(), new_state['attention']) < TOL
+    a = r['alignments'].cpu().numpy().reshape(B * k, c.attn_num_heads, -1)
+    np.testing.assert_allclose(a.sum(-1), 1.0, atol=1e-5)       # alpha sums to 1 per head
+
+
+def test_decode_step_train_masks(torch_mod):
+    """DropoutWrapper in/out masks + attention-map dropout with explicit masks."""
+    import comic_oracle as O
+    c = comic_config()
+    W = make_weights(c, include_cnn=False)
+    eng = _engine(c, W, with_cnn=False)
+    B = 4
+    im, fm = fake_features(B)
+    dec = O.Decoder(W, c)
+    dec.setup_memory(fm)
+    rng = np.random.default_rng(2)
+    keeps = (0.65, 0.65, 0.9)
+    init_mask = (rng.uniform(size=(B, 768)) < keeps[0]).astype(np.float32)
+    c0, h0 = dec.init_state(im, init_mask, keeps[0])
+    state = dec.zero_state((c0, h0))
+    state['attention'] = rng.standard_normal(state['attention'].shape).astype(np.float32) * 0.3
+    toks = rng.integers(0, 258, size=(B,)).astype(np.int32)
+    in_mask = (rng.uniform(size=(B, 768)) < keeps[0]).astype(np.float32)
+    out_mask = (rng.uniform(size=(B, 512)) < keeps[1]).astype(np.float32)
+    att_mask = (rng.uniform(size=(B, 8, 196)) < keeps[2]).astype(np.float32)
+    cell_out, ns, al = dec.call(dec.embed(toks), state, in_mask, out_mask, att_mask, *keeps)
+    logits = dec.output_layer(cell_out)
+    keys, values = eng.project_fm(eng.to_dev(fm))
+    gc0, gh0 = eng.rnn_init(eng.to_dev(im), eng.to_dev(init_mask), keeps[0])
+    assert rel_err(gc0.cpu().numpy(), c0) < TOL
+    r = eng.decode_step(keys, values, B, 1, eng.to_dev(toks), eng.to_dev(state['c']), eng.to_dev(state['h']),
+                        eng.to_dev(state['attention']), eng.to_dev(in_mask), eng.to_dev(out_mask),
+                        eng.to_dev(att_mask.reshape(B, -1)), keeps)
+    assert rel_err(r['h'].cpu().numpy(), ns['h']) < TOL          # state h is undropped
+    assert rel_err(r['logits'].cpu().numpy(), logits) < TOL      # logits use the dropped output
+    assert rel_err(r['alignments'].cpu().numpy(), al) < TOL
+    assert rel_err(r['attention'].cpu().numpy(), ns['attention']) < TOL
+
+
+def _beam_state(rng, B, k, V, with_finished):
+    log_probs = -rng.uniform(0, 10, size=(B, k)).astype(np.float32)
+    finished = np.zeros((B, k), bool)
+    lengths = rng.integers(0, 9, size=(B, k)).astype(np.int64)
+    if with_finished:
+        finished = rng.uniform(size=(B, k)) < 0.4
+    return log_probs, finished, lengths
+
+
+@pytest.mark.parametrize('B,k,V,lpw,fin', [(5, 3, 258, 0.0, False), (4, 3, 258, 0.0, True),
+                                           (3, 7, 258, 0.7, True), (2, 3, 10000, 0.0, True),
+                                           (1, 1, 300, 0.0, False), (6, 5, 64, 1.0, True)])
+def test_beam_step_bit_exact(torch_mod, B, k, V, lpw, fin):
+    """K10 given identical total log-probs: ids / parents / lengths / finished
+    bit-exact, ties -> lower flat index."""
+    import comic_oracle as O
+    torch = torch_mod
+    c = comic_config()
+    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False)
+    rng = np.random.default_rng(B * 100 + k)
+    # coarse grid of logits so that exact ties occur and log-softmax differences are far above 1 ulp
+    logits = (rng.integers(-8, 8, size=(B, k, V)) * 0.5).astype(np.float32)
+    eos = V - 1
+    lp, finished, lengths = _beam_state(rng, B, k, V, fin)
+    if not fin:
+        lp[:, 1:] = -np.inf; lp[:, 0] = 0          # the init state of BeamSearchDecoder.initialize
+        finished[:, 1:] = True
+        lengths[:] = 0
+    top, word, parent, new_lp, new_fin, new_len, total = O.beam_search_step(
+        logits, lp.copy(), finished.copy(), lengths.copy(), k, eos, lpw)
+    d_lp, d_fin, d_len = eng.to_dev(lp), eng.to_dev(finished.astype(np.uint8)), eng.to_dev(lengths)
+    g_top, g_word, g_parent = eng.beam_step(eng.to_dev(logits), d_lp, d_fin, d_len, eos, lpw)
+    # device log-softmax (expf/logf) may differ from NumPy by an ulp: ids must agree wherever the
+    # oracle's margin to the next candidate is not a float tie-break artefact.
+    np.testing.assert_array_equal(g_word.cpu().numpy(), word)
+    np.testing.assert_array_equal(g_parent.cpu().numpy(), parent)
+    np.testing.assert_array_equal(d_fin.cpu().numpy().astype(bool), new_fin)
+    np.testing.assert_array_equal(d_len.cpu().numpy(), new_len)
+    np.testing.assert_allclose(g_top.cpu().numpy(), top, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(d_lp.cpu().numpy(), new_lp, rtol=1e-5, atol=1e-5)
+
+
+def test_gather_tree_bit_exact(torch_mod):
+    import comic_oracle as O
+    c = comic_config()
+    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False)
+    rng = np.random.default_rng(9)
+    T, B, k, eos = 13, 6, 4, 257
+    step_ids = rng.integers(0, 256, size=(T, B, k)).astype(np.int32)
+    step_ids[rng.uniform(size=step_ids.shape) < 0.08] = eos
+    parents = rng.integers(0, k, size=(T, B, k)).astype(np.int32)
+    msl = np.array([13, 0, 5, 20, 1, 9], np.int32)
+    ref = O.gather_tree(step_ids, parents, msl, eos)
+    out = eng.gather_tree(eng.to_dev(step_ids), eng.to_dev(parents), eng.to_dev(msl), eos)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+def _decode_inputs(c, B, seed=0):
+    W = make_weights(c, include_cnn=False)
+    im, fm = fake_features(B, seed=seed + 3)
+    return W, im, fm
+
+
+@pytest.mark.parametrize('name,B,k,max_it', [('comic256', 4, 3, 14), ('word_none_h1', 3, 3, 8),
+                                             ('comic256', 2, 7, 10), ('independent_h4', 2, 2, 6)])
+def test_beam_search_matches_oracle(torch_mod, name, B, k, max_it):
+    import comic_oracle as O
+    c = CONFIGS[name]()
+    W, im, fm = _decode_inputs(c, B)
+    eng = _engine(c, W, with_cnn=False)
+    ref = O.beam_search_decode(O.Decoder(W, c), im, fm, k, 0.0, max_it)
+    keys, values = eng.project_fm(eng.to_dev(fm))
+    c0, h0 = eng.rnn_init(eng.to_dev(im))
+    r = eng.decode_beam(keys, values, c0, h0, k, 0.0, max_it)
+    T = int(r['T'].item())
+    assert T == ref['T']
+    np.testing.assert_array_equal(r['step_ids'][:T].cpu().numpy(), ref['step_ids'])
+    np.testing.assert_array_equal(r['parent_ids'][:T].cpu().numpy(), ref['parent_ids'])
+    np.testing.assert_array_equal(r['predicted_ids'][:T].cpu().numpy(), ref['predicted_ids'])
+    np.testing.assert_array_equal(r['lengths'].cpu().numpy(), ref['lengths'])
+    np.testing.assert_allclose(r['scores'][:T].cpu().numpy(), ref['scores'], rtol=1e-4, atol=1e-4)
+    _, _, am = O.post_process_beam(ref, c.attn_num_heads, k)
+    assert rel_err(r['attn'][:, :, :T].cpu().numpy(), am) < 1e-3
+
+
+def test_beam_search_eos_and_early_stop(torch_mod):
+    """Bias the output layer towards EOS so beams finish: exercises _mask_probs,
+    length bookkeeping, gather_tree EOS back-fill and the all-finished stop."""
+    import comic_oracle as O
+    from comic_b200 import weights as wts
+    c = comic_config()
+    W, im, fm = _decode_inputs(c, 5, seed=4)
+    b = W[wts.DEC + 'output_projection/bias'].copy()
+    b[257] += 3.2
+    W[wts.DEC + 'output_projection/bias'] = b
+    eng = _engine(c, W, with_cnn=False)
+    ref = O.beam_search_decode(O.Decoder(W, c), im, fm, 3, 0.0, 40)
+    keys, values = eng.project_fm(eng.to_dev(fm))
+    c0, h0 = eng.rnn_init(eng.to_dev(im))
+    r = eng.decode_beam(keys, values, c0, h0, 3, 0.0, 40)
+    T = int(r['T'].item())
+    assert ref['T'] < 40, 'test should stop early'
+    assert T == ref['T']
+    np.testing.assert_array_equal(r['predicted_ids'][:T].cpu().numpy(), ref['predicted_ids'])
+    np.testing.assert_array_equal(r['parent_ids'][:T].cpu().numpy(), ref['parent_ids'])
+    np.testing.assert_array_equal(r['lengths'].cpu().numpy(), ref['lengths'])
+    _, _, am = O.post_process_beam(ref, 8, 3)
+    assert rel_err(r['attn'][:, :, :T].cpu().numpy(), am) < 1e-3
+
+
+def test_greedy_matches_oracle(torch_mod):
+    import comic_oracle as O
+    c = comic_config()
+    W, im, fm = _decode_inputs(c, 5)
+    eng = _engine(c, W, with_cnn=False)
+    ref = O.greedy_decode(O.Decoder(W, c), im, fm, 12)
+    keys, values = eng.project_fm(eng.to_dev(fm))
+    c0, h0 = eng.rnn_init(eng.to_dev(im))
+    r = eng.decode_greedy(keys, values, c0, h0, 12)
+    T = int(r['T'].item())
+    assert T == ref['T']
+    np.testing.assert_array_equal(r['ids'][:T].cpu().numpy(), ref['ids'])
+    assert rel_err(r['logits'][:T].cpu().numpy(), ref['logits']) < TOL
+    _, _, am = O.post_process_plain(ref['logits'], ref['ids'], ref['alignment_history'], 8)
+    assert rel_err(r['attn'][:, :, :T].cpu().numpy(), am) < 1e-3
+
+
+def test_caption_model_end_to_end(torch_mod):
+    """images -> CaptionModel('infer').infer_output vs oracle encoder+beam search."""
+    import comic_oracle as O
+    import inception_v1_oracle as I
+    from comic_b200.model import CaptionModel
+    c = comic_config(infer_max_length=6)           # 12 radix steps
+    W = make_weights(c)
+    img = images(3, seed=8)
+    m = CaptionModel(c, 'infer', batch_ops=[img], weights=W)
+    preds, attn = m.infer_output
+    o_emb, o_fm, _ = I.encoder(img, W, c)
+    ref = O.beam_search_decode(O.Decoder(W, c), o_emb, o_fm, 3, 0.0)
+    _, ids, am = O.post_process_beam(ref, 8, 3)
+    np.testing.assert_array_equal(preds, ids)
+    assert attn.shape == am.shape
+    assert rel_err(attn, am) < 1e-3
+
+
+def test_errors(torch_mod):
+    from comic_b200.engine import Engine
+    with pytest.raises(ValueError):
+        Engine(comic_config(attn_alignment_method='add'))        # src/model_base.py:133-138
+    c = comic_config()
+    eng = Engine(c)
+    with pytest.raises(Exception):
+        eng.project_fm(eng.f32(2, 196, 832))                     # weights not bound
