@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- captions/sec of the COMIC caption-decoding hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (NumPy oracle)
+
+A "step" = one pass of the hot path over one batch of synthetic images on every
+rank: InceptionV1 encode -> key projection -> rnn init -> 60-step beam-3 decode
+(COMIC-256, radix tokens, max_it = infer_max_length 30 x 2 digits) -> gather_tree
++ top-beam attention maps.  Images are sharded across ranks with no collective
+(weak scaling: --batch images per GPU).  `value` times the K steps with inputs
+resident in HBM; `e2e` times the same K steps through the public API
+(`CaptionModel.run`) from pinned HOST images, host<->device copies included.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'oracle')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'captions/sec COMIC-256 beam-3'
+UNIT = 'captions/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=512, help='images per GPU per step')
+    ap.add_argument('--beam', type=int, default=3)
+    ap.add_argument('--workload', default='comic256', choices=['comic256', 'word'])
+    ap.add_argument('--ref-batch', type=int, default=8, help='images per step of the CPU reference arm')
+    ap.add_argument('--cpu-sample', type=int, default=4, help='images of the cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--breakdown', action='store_true', help='also print a per-kernel-class time table to stderr')
+    return ap.parse_args()
+
+
+def make_config(workload):
+    import comic_b200  # noqa: F401
+    from comic_b200 import configuration as conf
+    if workload == 'comic256':
+        return conf.make_config()                       # COMIC-256 defaults, V=258, 60 radix steps
+    return conf.make_config(token_type='word', cnn_fm_projection='none', attn_num_heads=1, n_words=10000)
+
+
+def workload_name(workload, batch, beam, c):
+    steps = c.infer_max_length * (2 if c.token_type == 'radix' else 1)
+    if workload == 'comic256':
+        return ('COMIC-256 (radix-256, 8-head add_LN softmax attention, tied projection) beam-%d, %d synthetic '
+                '224x224 images/GPU/step, encoder + %d decode steps' % (beam, batch, steps))
+    return ('baseline word model (V=10000, fm_projection none, 1 head) beam-%d, %d synthetic 224x224 images/GPU/step, '
+            'encoder + %d decode steps' % (beam, batch, steps))
+
+
+# ---------------------------------------------------------------------------
+# clocks sampler (NVML)
+# ---------------------------------------------------------------------------
+class ClockSampler(object):
+    REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+               0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+
+    def __init__(self, index):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != 'gpu_idle':
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# CPU side: the reference's algorithm on host cores (NumPy oracle)
+# ---------------------------------------------------------------------------
+def cpu_reference_step(c, W, images, beam):
+    import comic_oracle as O
+    import inception_v1_oracle as I
+    emb, fm, _ = I.encoder(images, W, c)
+    res = O.beam_search_decode(O.Decoder(W, c), emb, fm, beam, c.infer_length_penalty_weight)
+    O.post_process_beam(res, c.attn_num_heads, beam)
+    return res['T']
+
+
+def time_cpu(c, W, n_images, beam, steps, warmup):
+    rng = np.random.default_rng(123)
+    img = rng.uniform(-1, 1, (n_images, 224, 224, 3)).astype(np.float32)
+    for _ in range(warmup):
+        cpu_reference_step(c, W, img, beam)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(c, W, img, beam)
+    dt = time.perf_counter() - t0
+    return n_images * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    import comic_b200  # noqa: F401
+    from comic_b200 import weights as wts
+    c = make_config(args.workload)
+    W = wts.init_weights(c, seed=c.rand_seed, cnn_init='he')
+    cores = os.cpu_count()
+    val, sec = time_cpu(c, W, args.ref_batch, args.beam, args.steps, max(args.warmup, 1))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.workload, args.batch, args.beam, c),
+                   'note': 'reference arm: NumPy restatement of the TF1.9 graph (TF 1.9 / py2.7 not installable '
+                           'offline), %d images per step on the host cores' % args.ref_batch},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d images x %d steps, encoder + beam-%d decode, NumPy/OpenBLAS all cores'
+                                   % (args.ref_batch, args.steps, args.beam)},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# roofline accounting (DESIGN.md "Kernels")
+# ---------------------------------------------------------------------------
+def algorithmic_work(tag, eng, B, beam, T):
+    """(amount per STEP, kind) for one kernel class; kind 'flop' or 'byte'."""
+    d = eng.dims
+    N = B * beam
+    if tag == 'conv':
+        from comic_b200 import weights as wts
+        macs = 0
+        hw = {'Conv2d_1a_7x7': 112, 'Conv2d_2b_1x1': 56, 'Conv2d_2c_3x3': 56}
+        for scope, k, s, cin, cout in wts.cnn_conv_list():
+            name = scope.split('/')[0]
+            if name in hw:
+                side = hw[name]
+            elif name.startswith('Mixed_3'):
+                side = 28
+            elif name.startswith('Mixed_4'):
+                side = 14
+            else:
+                side = 7
+            macs += side * side * k * k * cin * cout
+        return 2.0 * macs * B, 'flop'
+    if tag == 'gates':
+        return 2.0 * N * (d.W + d.A + d.R) * 4 * d.R * T, 'flop'
+    if tag == 'lq':
+        return 2.0 * N * d.R * (d.V + d.R) * T, 'flop'
+    if tag == 'project':
+        return 2.0 * B * d.M * d.C * d.R * (2 if d.fm_projection == 'independent' else 1), 'flop'
+    if tag == 'scores':
+        return (B * d.M * d.R * 4.0 + N * d.R * 4.0 + N * d.H * d.M * 4.0) * T, 'byte'
+    if tag == 'ctx':
+        return (B * d.M * d.VAL * 4.0 + 2.0 * N * d.H * d.M * 4.0 + N * d.A * 4.0) * T, 'byte'
+    if tag == 'beam':
+        return (N * d.V * 4.0 + N * 32.0) * T, 'byte'
+    if tag == 'lstm':
+        return (N * 4 * d.R * 4.0 + 3.0 * N * d.R * 4.0) * T, 'byte'
+    return 0.0, 'byte'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return {'hbm': j['hbm_gbs'], 'tensor': j.get('bf16_tflops_sustained', j['bf16_tflops']), 'which': 'measured'}
+    return {'hbm': 6650.0, 'tensor': 1590.0, 'which': 'fallback'}
+
+
+def load_traffic(tag):
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(tag)
+    return None
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import comic_b200  # noqa: F401
+    from comic_b200 import weights as wts
+    from comic_b200.engine import Engine, KERNEL_TAGS
+    from comic_b200.model import CaptionModel
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the hot path has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    c = make_config(args.workload)
+    c.infer_beam_size = args.beam
+    c.batch_size_infer = args.batch
+    W = wts.init_weights(c, seed=c.rand_seed, cnn_init='he')
+    eng = Engine(c)
+    eng.bind_weights(W)
+    model = CaptionModel(c, 'infer', batch_ops=None, engine=eng)
+    B, beam = args.batch, args.beam
+    T = model._maximum_iterations()
+
+    # synthetic inputs: pinned host copy (e2e) + device-resident copy (value); 308 MB/step > 126 MB L2
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_images = torch.empty((B, 224, 224, 3), dtype=torch.float32).pin_memory()
+    host_images.uniform_(-1.0, 1.0, generator=g)
+    dev_images = host_images.to(eng.device, non_blocking=False)
+
+    def step_device():
+        emb, fm = eng.encode(dev_images)
+        keys, values = eng.project_fm(fm)
+        c0, h0 = eng.rnn_init(emb)
+        return eng.decode_beam(keys, values, c0, h0, beam, c.infer_length_penalty_weight, T)
+
+    def step_e2e():
+        return model.run(host_images)
+
+    # ---- kernel-class breakdown (outside the timed region) -> dominant kernel
+    for _ in range(max(args.warmup, 3)):
+        r = step_device()
+    torch.cuda.synchronize()
+    eng.profile_enable(KERNEL_TAGS)
+    step_device()
+    torch.cuda.synchronize()
+    table = {t: eng.profile_read(t) for t in KERNEL_TAGS}
+    eng.profile_enable([])
+    dominant = max(table, key=lambda t: table[t][0])
+    if args.breakdown and rank == 0:
+        tot = sum(v[0] for v in table.values())
+        for t in KERNEL_TAGS:
+            ms, n = table[t]
+            sys.stderr.write('%-8s %9.3f ms %6d launches %5.1f%%\n' % (t, ms, n, 100 * ms / max(tot, 1e-9)))
+
+    # ---- timed region 1: device-resident inputs (value) + roofline of the dominant kernel
+    sampler = ClockSampler(local)
+    eng.profile_enable([dominant])
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        r = step_device()
+    ev1.record()
+    barrier()
+    sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    dom_ms, dom_n = eng.profile_read(dominant)
+    eng.profile_enable([])
+    T_exec = int(r['T'].item())
+
+    # ---- timed region 2: end to end through CaptionModel.run from pinned host memory
+    for _ in range(2):
+        out = step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = host_images.numel() * 4
+    d2h = int(out[0].nbytes + out[1].nbytes)
+
+    t_dev = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = [float(x) for x in t_dev.tolist()]
+
+    if rank == 0:
+        peaks = load_peaks()
+        work, kind = algorithmic_work(dominant, eng, B, beam, T_exec)
+        per_launch = work * args.steps / max(dom_n, 1)
+        avg_s = dom_ms * 1e-3 / max(dom_n, 1)
+        if kind == 'flop':
+            achieved = per_launch / avg_s / 1e12
+            roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tensor'], 'unit': 'TFLOP/s',
+                    'frac': achieved / peaks['tensor']}
+        else:
+            achieved = per_launch / avg_s / 1e9
+            roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm'], 'unit': 'GB/s',
+                    'frac': achieved / peaks['hbm']}
+        roof.update({'traffic': load_traffic(dominant), 'kernel': dominant, 'launches': dom_n,
+                     'avg_launch_us': avg_s * 1e6, 'share_of_step': dom_ms / ms_total,
+                     'peak_source': peaks['which'] + (' sustained' if kind == 'flop' else ''),
+                     'arithmetic': 'fp32 FFMA (exact-parity path)' if kind == 'flop' else 'fp32'})
+        caps = B * world * args.steps
+        line = {
+            'metric': METRIC, 'value': caps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': workload_name(args.workload, B, beam, c), 'images_per_gpu': B,
+                       'global_batch': B * world, 'beam': beam, 'decode_steps': T_exec,
+                       'parallelism': 'image-sharded x%d, no collective' % world,
+                       'l2_policy': 'inputs larger than L2 (308 MB images + 206 MB keys per step)'},
+            'decoder_step_us': None,
+            'roofline': roof,
+            'e2e': {'value': caps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps},
+            'gpu_launches': int(launches),
+            'clocks': sampler.summary(),
+            'kernel_ms_per_step': {t: round(table[t][0], 3) for t in KERNEL_TAGS if table[t][1]},
+        }
+        dec_ms = sum(table[t][0] for t in ('gates', 'lstm', 'lq', 'scores', 'ctx', 'beam'))
+        line['decoder_step_us'] = dec_ms * 1e3 / max(T_exec, 1)
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count()
+            val, _sec = time_cpu(c, W, args.cpu_sample, beam, 1, 1)
+            line['cpu_baseline'] = {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': '%d images, encoder + %d-step beam-%d decode, NumPy oracle on all host cores'
+                                              % (args.cpu_sample, T, beam)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -68,7 +68,41 @@ extern "C" int comic_create(const comic_cfg_t* cfg, comic_handle_t* out) {
 }
 
 extern "C" int comic_destroy(comic_handle_t h) {
+  if (h && h->prof_ev) {
+    for (int i = 0; i < 2 * kMaxProfEvents; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev;
+    delete[] h->prof_tag;
+  }
   delete h;
+  return COMIC_OK;
+}
+
+extern "C" int comic_profile_enable(comic_handle_t h, uint32_t tag_mask) {
+  COMIC_REQUIRE(h, COMIC_E_BADARG, "profile_enable: null handle");
+  if (tag_mask && !h->prof_ev) {
+    h->prof_ev = new cudaEvent_t[2 * kMaxProfEvents];
+    h->prof_tag = new int[kMaxProfEvents];
+    for (int i = 0; i < 2 * kMaxProfEvents; ++i) COMIC_CHECK_CUDA(cudaEventCreate(&h->prof_ev[i]));
+  }
+  h->prof_mask = tag_mask;
+  h->prof_used = 0;
+  return COMIC_OK;
+}
+
+extern "C" int comic_profile_read(comic_handle_t h, int tag, double* total_ms, int64_t* count) {
+  COMIC_REQUIRE(h && total_ms && count, COMIC_E_BADARG, "profile_read: null argument");
+  double tot = 0.0;
+  int64_t n = 0;
+  for (int i = 0; i < h->prof_used; ++i) {
+    if (h->prof_tag[i] != tag) continue;
+    COMIC_CHECK_CUDA(cudaEventSynchronize(h->prof_ev[2 * i + 1]));
+    float ms = 0.f;
+    COMIC_CHECK_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    tot += ms;
+    ++n;
+  }
+  *total_ms = tot;
+  *count = n;
   return COMIC_OK;
 }
 

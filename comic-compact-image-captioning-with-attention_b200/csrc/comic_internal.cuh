@@ -51,6 +51,11 @@ struct Packed {
 
 }  // namespace comic
 
+namespace comic {
+enum Tag { T_CONV = 0, T_POOL, T_PROJECT, T_INIT, T_GATES, T_LSTM, T_LQ, T_SCORES, T_CTX, T_BEAM, T_FINAL, T_MISC, T_COUNT };
+constexpr int kMaxProfEvents = 16384;
+}  // namespace comic
+
 struct comic_handle_s {
   comic_cfg_t cfg;
   int dev = 0;
@@ -60,7 +65,33 @@ struct comic_handle_s {
   bool bound = false, cnn_bound = false;
   comic::Packed pk;
   int64_t launches = 0;
+  // optional per-kernel-class device timing (bench.py roofline): CUDA events
+  // recorded on the launching stream around every launch of the enabled tags.
+  uint32_t prof_mask = 0;
+  cudaEvent_t* prof_ev = nullptr;   // 2 * kMaxProfEvents
+  int* prof_tag = nullptr;
+  int prof_used = 0;
 };
+
+namespace comic {
+// Counts a launch and, when its tag is enabled, brackets it with events.
+struct Prof {
+  comic_handle_t h;
+  cudaStream_t st;
+  int slot;
+  Prof(comic_handle_t h_, int tag, cudaStream_t st_, int n = 1) : h(h_), st(st_), slot(-1) {
+    h->launches += n;
+    if (((h->prof_mask >> tag) & 1u) && h->prof_ev && h->prof_used < kMaxProfEvents) {
+      slot = h->prof_used++;
+      h->prof_tag[slot] = tag;
+      cudaEventRecord(h->prof_ev[2 * slot], st);
+    }
+  }
+  ~Prof() {
+    if (slot >= 0) cudaEventRecord(h->prof_ev[2 * slot + 1], st);
+  }
+};
+}  // namespace comic
 
 namespace comic {
 

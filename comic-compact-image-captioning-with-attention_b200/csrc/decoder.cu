@@ -679,6 +679,7 @@ static cudaError_t launch_scores(comic_handle_t h, const StepIO& io, const StepB
 static int dispatch_scores(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, cudaStream_t st) {
   cudaError_t e = cudaErrorInvalidValue;
   bool ok = true;
+  Prof pf(h, T_SCORES, st, 0);
   if (h->R == 512) {
     switch (h->H) {
       case 1: e = launch_scores<512, 1>(h, io, sb, B, k, st); break;
@@ -738,15 +739,17 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
   e1.split_stride = (long long)N * 4 * R;
   e1.stop = io.fin_count ? io.fin_count + (io.t > 0 ? io.t - 1 : 0) : nullptr;
   e1.stop_n = (io.fin_count && io.t > 0) ? io.n_rows : 0x7fffffff;
-  COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.lstm_kernel, 4 * R, N, 4 * R, h->KX, e1, p1, st)));
-  h->launches++;
   {
+    Prof pf(h, T_GATES, st);
+    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.lstm_kernel, 4 * R, N, 4 * R, h->KX, e1, p1, st)));
+  }
+  {
+    Prof pf(h, T_LSTM, st);
     int tot = N * R;
     lstm_pointwise_kernel<<<(tot + 255) / 256, 256, 0, st>>>(sb.gates, nz1, (size_t)N * 4 * R, h->w.lstm_bias,
                                                           io.c_prev, io.src, io.src_limit, io.c_new, io.h_new,
                                                           io.h_drop, io.out_mask, io.out_keep, N, R, io.fin_count,
                                                           io.t, io.n_rows);
-    h->launches++;
   }
   // --- [logits | q] = h_out . [W_o | W_q] + [b_o | 0] ---
   const float* hq = io.h_drop ? io.h_drop : io.h_new;
@@ -762,17 +765,17 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
   if (nz2 == 1) {
     e2.bias = h->pk.outq_bias;
     e2.r[0] = Route{0, h->LQ, sb.lq, h->LQ, 0};
+    Prof pf(h, T_LQ, st);
     COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->pk.outq, h->LQ, N, h->LQ, R, e2, p2, st)));
-    h->launches++;
   } else {
     e2.r[0] = Route{0, h->LQ, sb.lq_part, h->LQ, 0};
     e2.split_stride = (long long)N * h->LQ;
+    Prof pf(h, T_LQ, st, 2);
     COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->pk.outq, h->LQ, N, h->LQ, R, e2, p2, st)));
     size_t tot = (size_t)N * h->LQ;
     splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(sb.lq_part, nz2, (size_t)N * h->LQ,
                                                                        h->pk.outq_bias, sb.lq, N, h->LQ,
                                                                        io.fin_count, io.t, io.n_rows);
-    h->launches += 2;
   }
   // --- attention ---
   int rc = dispatch_scores(h, io, sb, B, k, st);
@@ -783,10 +786,12 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
     size_t smem = step_smem_ctx(k, h->H, h->M);
     float* ctx_dst = h->cfg.context_layer ? sb.ctxraw : io.ctx_new;
     int ld_ctx = h->cfg.context_layer ? VAL : A;
-    attn_ctx_kernel<<<grid, 128, smem, st>>>(sb.scores, io.values, VAL, ctx_dst, ld_ctx, io.hist_t, io.att_mask,
-                                            io.att_keep, k, h->H, h->M, h->cfg.prob_fn, io.fin_count, io.t,
-                                            io.n_rows);
-    h->launches++;
+    {
+      Prof pf(h, T_CTX, st);
+      attn_ctx_kernel<<<grid, 128, smem, st>>>(sb.scores, io.values, VAL, ctx_dst, ld_ctx, io.hist_t, io.att_mask,
+                                              io.att_keep, k, h->H, h->M, h->cfg.prob_fn, io.fin_count, io.t,
+                                              io.n_rows);
+    }
     COMIC_CHECK_CUDA(cudaGetLastError());
     if (h->cfg.context_layer) {
       APlain a3{};
@@ -798,8 +803,8 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
       e3.stop = e1.stop;
       e3.stop_n = e1.stop_n;
       GemmPlan p3 = plan_gemm(N, R, VAL, h->num_sms, false);
+      Prof pf(h, T_CTX, st);
       COMIC_CHECK_CUDA((launch_gemm<0, 4>(a3, h->w.a_layer, R, N, R, VAL, e3, p3, st)));
-      h->launches++;
     }
   }
   return COMIC_OK;
@@ -897,13 +902,15 @@ extern "C" int comic_project_fm(comic_handle_t h, const float* fm, int B, float*
   e.r[0] = Route{0, h->R, keys_out, h->R, 0};
   e.stop_n = 0x7fffffff;
   GemmPlan p = plan_gemm(Mrows, h->R, h->C, h->num_sms, false);
-  COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.memory_kernel, h->R, Mrows, h->R, h->C, e, p, st)));
-  h->launches++;
+  {
+    Prof pf(h, T_PROJECT, st);
+    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.memory_kernel, h->R, Mrows, h->R, h->C, e, p, st)));
+  }
   if (h->cfg.fm_projection == 2) {
     COMIC_REQUIRE(values_out && h->w.value_kernel, COMIC_E_BADARG, "project_fm: independent projection needs values_out");
     e.r[0] = Route{0, h->R, values_out, h->R, 0};
+    Prof pf(h, T_PROJECT, st);
     COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.value_kernel, h->R, Mrows, h->R, h->C, e, p, st)));
-    h->launches++;
   }
   return COMIC_OK;
 }
@@ -1045,12 +1052,14 @@ extern "C" int comic_decode_greedy(comic_handle_t h, const float* keys, const fl
                                          lb.fin_count, t, N);
     h->launches++;
   }
-  compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out);
-  h->launches++;
-  if (attn_out && max_it > 0) {
-    dim3 g(max_it, B);
-    attn_top_gather_kernel<<<g, 256, 0, st>>>(lb.hist, nullptr, T_out, max_it, B, 1, h->H * h->M, h->M, attn_out);
-    h->launches++;
+  {
+    Prof pf(h, T_FINAL, st);
+    compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out);
+    if (attn_out && max_it > 0) {
+      dim3 g(max_it, B);
+      attn_top_gather_kernel<<<g, 256, 0, st>>>(lb.hist, nullptr, T_out, max_it, B, 1, h->H * h->M, h->M, attn_out);
+      h->launches++;
+    }
   }
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;
@@ -1106,15 +1115,17 @@ extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const floa
     io.fin_count = lb.fin_count; io.t = t; io.n_rows = N;
     int rc = run_step(h, io, lb.sb, B, k, st);
     if (rc) return rc;
-    beam_step_kernel<<<B, 256, 0, st>>>(lb.sb.lq, h->LQ, k, h->V, h->cfg.eos_id, lpw, lb.cum, lb.fin, lb.len,
-                                       sc + (size_t)t * N, step_ids + (size_t)t * N, parents + (size_t)t * N,
-                                       lb.tok, lb.src, lb.fin_count, t, N);
-    h->launches++;
+    {
+      Prof pf(h, T_BEAM, st);
+      beam_step_kernel<<<B, 256, 0, st>>>(lb.sb.lq, h->LQ, k, h->V, h->cfg.eos_id, lpw, lb.cum, lb.fin, lb.len,
+                                         sc + (size_t)t * N, step_ids + (size_t)t * N, parents + (size_t)t * N,
+                                         lb.tok, lb.src, lb.fin_count, t, N);
+    }
   }
+  Prof pf_final(h, T_FINAL, st, 2);
   compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out);
   gather_tree_kernel<<<(N + 127) / 128, 128, 0, st>>>(step_ids, parents, nullptr, lb.len, max_it, T_out, B, k,
                                                      h->cfg.eos_id, pred_ids_out);
-  h->launches += 2;
   if (lengths_out)
     COMIC_CHECK_CUDA(cudaMemcpyAsync(lengths_out, lb.len, (size_t)N * sizeof(long long), cudaMemcpyDeviceToDevice, st));
   if (attn_top_out && max_it > 0) {

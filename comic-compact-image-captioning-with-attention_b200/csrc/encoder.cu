@@ -258,9 +258,11 @@ static int run_conv(comic_handle_t h, const float* x, int B, int H, int W, int l
   e.split_stride = 0;
   GemmPlan p = plan_gemm(M, N, K, h->num_sms, false);
   cudaError_t err;
-  if (d.c_in % 4 == 0) err = launch_gemm<1, 4>(a, h->w.conv_w[ci], N, M, N, K, e, p, st);
-  else err = launch_gemm<1, 1>(a, h->w.conv_w[ci], N, M, N, K, e, p, st);
-  h->launches++;
+  {
+    Prof pf(h, T_CONV, st);
+    if (d.c_in % 4 == 0) err = launch_gemm<1, 4>(a, h->w.conv_w[ci], N, M, N, K, e, p, st);
+    else err = launch_gemm<1, 1>(a, h->w.conv_w[ci], N, M, N, K, e, p, st);
+  }
   COMIC_CHECK_CUDA(err);
   if (Ho_out) *Ho_out = a.Ho;
   if (Wo_out) *Wo_out = a.Wo;
@@ -275,8 +277,10 @@ static int run_maxpool(comic_handle_t h, const float* x, float* y, int B, int H,
   size_t total = (size_t)B * Ho * Wo * (C / 4);
   int grid = (int)((total + 255) / 256);
   if (grid > h->num_sms * 16) grid = h->num_sms * 16;
-  maxpool_nhwc_kernel<<<grid, 256, 0, st>>>(x, y, B, H, W, C, k, s, pt, pl, Ho, Wo);
-  h->launches++;
+  {
+    Prof pf(h, T_POOL, st);
+    maxpool_nhwc_kernel<<<grid, 256, 0, st>>>(x, y, B, H, W, C, k, s, pt, pl, Ho, Wo);
+  }
   COMIC_CHECK_CUDA(cudaGetLastError());
   if (Ho_out) *Ho_out = Ho;
   if (Wo_out) *Wo_out = Wo;
@@ -304,8 +308,11 @@ static int run_block(comic_handle_t h, int bi, const float* x, float* y, int B, 
     e.r[1] = Route{bd.b0, bd.b0 + bd.b1a, eb.t1, bd.b1a, 0};
     e.r[2] = Route{bd.b0 + bd.b1a, ng, eb.t2, bd.b2a, 0};
     GemmPlan p = plan_gemm(M, ng, bd.cin, h->num_sms, false);
-    cudaError_t err = launch_gemm<0, 4>(a, h->pk.grp_w[bi], ng, M, ng, bd.cin, e, p, st);
-    h->launches++;
+    cudaError_t err;
+    {
+      Prof pf(h, T_CONV, st);
+      err = launch_gemm<0, 4>(a, h->pk.grp_w[bi], ng, M, ng, bd.cin, e, p, st);
+    }
     COMIC_CHECK_CUDA(err);
   }
   int rc;
@@ -360,8 +367,8 @@ int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out,
     if ((rc = run_block(h, 8, eb.b, m5c, nb, 7, eb, st))) return rc;     // 1024
     float* emb = im_embed_out + (size_t)b0 * 1024;
     if (!h->cfg.legacy) {
+      Prof pf(h, T_POOL, st);
       avgpool_global_kernel<<<(nb * 1024 + 255) / 256, 256, 0, st>>>(m5c, emb, nb, 49, 1024);
-      h->launches++;
     } else {
       avgpool_global_kernel<<<(nb * 1024 + 255) / 256, 256, 0, st>>>(m5c, head, nb, 49, 1024);
       ln_tanh_rows_kernel<<<nb, 256, 0, st>>>(head, h->w.enc_ln_gamma, h->w.enc_ln_beta, eb.t1, 1024, 1e-12f);
@@ -373,8 +380,11 @@ int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out,
       e.nroute = 1;
       e.r[0] = Route{0, 1024, emb, 1024, 0};
       GemmPlan p = plan_gemm(nb, 1024, 1024, h->num_sms, false);
-      cudaError_t err = launch_gemm<0, 4>(a, h->w.enc_embed_weight, 1024, nb, 1024, 1024, e, p, st);
-      h->launches++;
+      cudaError_t err;
+      {
+        Prof pf(h, T_MISC, st);
+        err = launch_gemm<0, 4>(a, h->w.enc_embed_weight, 1024, nb, 1024, 1024, e, p, st);
+      }
       COMIC_CHECK_CUDA(err);
     }
     COMIC_CHECK_CUDA(cudaGetLastError());

@@ -75,7 +75,12 @@ SIGNATURES = {
     'comic_gather_tree': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     'comic_gemm_f32': (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
     'comic_launch_count': (_I, [_P, C.POINTER(C.c_int64)]),
+    'comic_profile_enable': (_I, [_P, C.c_uint32]),
+    'comic_profile_read': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
+
+KERNEL_TAGS = ['conv', 'pool', 'project', 'init', 'gates', 'lstm', 'lq', 'scores', 'ctx', 'beam',
+               'final', 'misc']
 
 
 def load_library(path=LIB_PATH):
@@ -355,6 +360,17 @@ class Engine(object):
         self._check(self.lib.comic_gemm_f32(self._h, _ptr(A), A.stride(0), _ptr(Bm), Bm.stride(0), _ptr(bias),
                                             _ptr(out), N, M, N, K, None, 0, self.stream()))
         return out
+
+    def profile_enable(self, tags):
+        mask = 0
+        for t in tags:
+            mask |= 1 << KERNEL_TAGS.index(t)
+        self._check(self.lib.comic_profile_enable(self._h, mask))
+
+    def profile_read(self, tag):
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self.lib.comic_profile_read(self._h, KERNEL_TAGS.index(tag), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def launch_count(self):
         n = C.c_int64()

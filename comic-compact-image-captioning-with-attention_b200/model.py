@@ -142,6 +142,7 @@ class CaptionModel(ModelBase):
                 weights = wts.init_weights(config, seed=getattr(config, 'rand_seed', 48964896))
             engine.bind_weights(weights)
         self.engine = engine
+        self._pinned = {}
         if mode != 'infer':
             raise NotImplementedError("mode '%s' is not built on the CUDA path yet (DESIGN.md, scope)" % mode)
 
@@ -149,17 +150,37 @@ class CaptionModel(ModelBase):
         """ModelBase.restore_model (src/model_base.py:422-490): bind a W-table."""
         self.engine.bind_weights(weights)
 
+    def _to_host(self, t, key):
+        """Device -> pinned host staging buffer (reused across calls)."""
+        torch = self.engine.torch
+        t = t.contiguous()
+        buf = self._pinned.get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._pinned[key] = buf
+        buf.copy_(t, non_blocking=True)
+        return buf
+
     def run(self, images=None):
-        """One `sess.run(self.infer_output)`: images [B,224,224,3] NHWC fp32
-        (host numpy / torch, or device tensor).  Returns [dec_preds (B,T) int32
-        numpy, attn_maps (B,H,T,M) fp32 numpy]."""
+        """One `sess.run(self.infer_output)` (src/infer_fn.py:130): images
+        [B,224,224,3] NHWC fp32 (host numpy / torch -- pinned memory copies
+        asynchronously -- or a device tensor).  Returns [dec_preds (B,T) int32,
+        attn_maps (B,H,T,M) fp32] as numpy views of pinned staging buffers that
+        the next call overwrites."""
         eng = self.engine
+        torch = eng.torch
         if images is None:
             images = self.batch_ops[0]
-        dev_images = eng.to_dev(images, eng.torch.float32)
+        images = torch.as_tensor(images)
+        if images.dtype != torch.float32:
+            images = images.float()
+        dev_images = images.to(eng.device, non_blocking=True).contiguous()
         self._encoder(dev_images)
         self._decoder_rnn()
-        return [self.dec_preds.contiguous().cpu().numpy(), self.dec_attn_maps.contiguous().cpu().numpy()]
+        preds = self._to_host(self.dec_preds, 'preds')
+        attn = self._to_host(self.dec_attn_maps, 'attn')
+        torch.cuda.current_stream(eng.device).synchronize()
+        return [preds.numpy(), attn.numpy()]
 
     @property
     def infer_output(self):

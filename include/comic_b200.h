@@ -195,6 +195,18 @@ int comic_gemm_f32(comic_handle_t h, const float* A, int lda, const float* Bm, i
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int comic_launch_count(comic_handle_t h, int64_t* count);
 
+/* Per-kernel-class device timing for the roofline report (no reference
+ * counterpart; the reference only logs wall-clock, src/infer_fn.py:176-184).
+ * Kernel classes (bit i of tag_mask): 0 conv implicit-GEMM, 1 pooling, 2 key
+ * projection, 3 rnn init, 4 gate GEMM, 5 LSTM pointwise, 6 logits|query GEMM,
+ * 7 attention scores, 8 attention softmax+context, 9 beam step, 10 finalise,
+ * 11 misc.  While a class is enabled every launch of it is bracketed by CUDA
+ * events on the launching stream; comic_profile_read synchronises those events
+ * and returns the summed duration and the launch count.  enable(0) switches
+ * timing off; enable() always resets the counters. */
+int comic_profile_enable(comic_handle_t h, uint32_t tag_mask);
+int comic_profile_read(comic_handle_t h, int tag, double* total_ms, int64_t* count);
+
 #ifdef __cplusplus
 }
 #endif
