@@ -106,6 +106,35 @@ extern "C" int comic_profile_read(comic_handle_t h, int tag, double* total_ms, i
   return COMIC_OK;
 }
 
+namespace comic {
+int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, int ldw, int cin_src, int cin_dst,
+                   tc::TcWeight& out, cudaStream_t st, bool dry) {
+  (void)h;
+  int ntaps = K / cin_src;
+  int Kd = (cin_src == cin_dst) ? K : ntaps * cin_dst;
+  out.N = N;
+  out.K = Kd;
+  out.Npad = round_up(N, 16);
+  out.Kpad = round_up(Kd, tc::BK);
+  size_t n = (size_t)out.Npad * out.Kpad;
+  out.hi = cv.take<float>(n);
+  out.lo = cv.take<float>(n);
+  out.ready = false;
+  if (dry) return COMIC_OK;
+  tc::pack_bt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, K, N, ldw, out.hi, out.lo, out.Kpad, out.Npad,
+                                                                 cin_src, cin_dst);
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  COMIC_REQUIRE(tc::make_weight_maps(out), COMIC_E_CUDA, "cuTensorMapEncodeTiled failed for a %d x %d weight", N, Kd);
+  return COMIC_OK;
+}
+}  // namespace comic
+
+extern "C" int comic_set_precision(comic_handle_t h, int mode) {
+  COMIC_REQUIRE(h && (mode == 0 || mode == 1), COMIC_E_BADARG, "set_precision: mode must be 0 (f32) or 1 (3xtf32)");
+  h->precision = mode;
+  return COMIC_OK;
+}
+
 extern "C" int comic_packed_bytes(comic_handle_t h, size_t* bytes) {
   COMIC_REQUIRE(h && bytes, COMIC_E_BADARG, "packed_bytes: null argument");
   Carver cv(nullptr);
@@ -155,8 +184,8 @@ extern "C" int comic_workspace_bytes(comic_handle_t h, int mode, int B, int k, i
   COMIC_REQUIRE(h && bytes, COMIC_E_BADARG, "workspace_bytes: null argument");
   COMIC_REQUIRE(B > 0 && k > 0 && T >= 0, COMIC_E_SHAPE, "workspace_bytes: bad B=%d k=%d T=%d", B, k, T);
   if (mode == 0) return encoder_workspace_bytes(h, B, bytes);
-  if (mode == 5) {   // gemm_f32 split-K scratch
-    *bytes = (size_t)16 * B * k * sizeof(float) + 256;
+  if (mode == 5) {   // gemm_f32 tensor-path scratch: B = N, k = K of the GEMM (B^T hi/lo pack)
+    *bytes = 2 * (size_t)round_up(B, 16) * round_up(k, tc::BK) * sizeof(float) + 2048;
     return COMIC_OK;
   }
   return decoder_workspace_bytes(h, mode, B, k, T, bytes);
@@ -174,7 +203,6 @@ extern "C" int comic_gemm_f32(comic_handle_t h, const float* A, int lda, const f
   COMIC_REQUIRE(h && A && Bm && C, COMIC_E_BADARG, "gemm_f32: null argument");
   COMIC_REQUIRE(M > 0 && N > 0 && K > 0, COMIC_E_SHAPE, "gemm_f32: bad shape");
   COMIC_REQUIRE(N % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0, COMIC_E_UNSUPPORTED, "gemm_f32: N, ldb, ldc must be multiples of 4");
-  (void)ws; (void)ws_bytes;
   APlain a{};
   a.nseg = 1;
   a.seg[0] = ASeg{A, nullptr, lda, K, M};
@@ -185,6 +213,19 @@ extern "C" int comic_gemm_f32(comic_handle_t h, const float* A, int lda, const f
   e.stop_n = 0x7fffffff;
   GemmPlan p = plan_gemm(M, N, K, h->num_sms, false);
   cudaError_t err;
+  if (h->precision == 1 && M >= 128 && K % 4 == 0 && lda % 4 == 0) {
+    // tensor path: pack B on the fly into the caller's workspace
+    size_t need = 2 * (size_t)round_up(N, 16) * round_up(K, tc::BK) * sizeof(float) + 1024;
+    COMIC_REQUIRE(ws && ws_bytes >= need, COMIC_E_WORKSPACE, "gemm_f32: tensor path needs %zu workspace bytes", need);
+    Carver cv(ws);
+    tc::TcWeight tw;
+    int rc = pack_tc_weight(h, cv, Bm, K, N, ldb, 1, 1, tw, (cudaStream_t)stream, false);
+    if (rc) return rc;
+    err = tc::launch_gemm_tc<0>(a, tw, M, N, e, h->num_sms, (cudaStream_t)stream);
+    h->launches += 2;
+    COMIC_CHECK_CUDA(err);
+    return COMIC_OK;
+  }
   if (K % 4 == 0 && lda % 4 == 0) err = launch_gemm<0, 4>(a, Bm, ldb, M, N, K, e, p, (cudaStream_t)stream);
   else err = launch_gemm<0, 1>(a, Bm, ldb, M, N, K, e, p, (cudaStream_t)stream);
   h->launches++;

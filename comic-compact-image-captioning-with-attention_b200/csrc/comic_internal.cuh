@@ -8,6 +8,7 @@
 
 #include "../../include/comic_b200.h"
 #include "gemm_f32.cuh"
+#include "gemm_tc.cuh"
 
 namespace comic {
 
@@ -47,6 +48,10 @@ struct Packed {
   float* grp_w[kNumBlocks];      // [cin, b0+b1a+b2a]
   float* grp_scale[kNumBlocks];
   float* grp_shift[kNumBlocks];
+  // tensor-core path: B^T hi/lo panels + TMA descriptors
+  tc::TcWeight tc_conv[COMIC_NUM_CONVS];
+  tc::TcWeight tc_grp[kNumBlocks];
+  tc::TcWeight tc_lstm, tc_outq, tc_mem, tc_val, tc_init;
 };
 
 }  // namespace comic
@@ -63,6 +68,7 @@ struct comic_handle_s {
   int R, W, H, C, M, E, V, Vp, A, VAL, LQ, KX;
   comic_weights_t w;
   bool bound = false, cnn_bound = false;
+  int precision = 1;   // 0: fp32 FFMA everywhere; 1: tcgen05 3xTF32 for GEMMs with M >= 128
   comic::Packed pk;
   int64_t launches = 0;
   // optional per-kernel-class device timing (bench.py roofline): CUDA events
@@ -111,6 +117,11 @@ struct Carver {
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Carve + (unless dry) fill one tensor-path weight pack from W[K][N] (row stride ldw).
+int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, int ldw, int cin_src, int cin_dst,
+                   tc::TcWeight& out, cudaStream_t st, bool dry);
+inline bool use_tc(comic_handle_t h, const tc::TcWeight& w, int M) { return h->precision == 1 && w.ready && M >= 128; }
 
 // encoder.cu
 int encoder_workspace_bytes(comic_handle_t h, int B, size_t* bytes);

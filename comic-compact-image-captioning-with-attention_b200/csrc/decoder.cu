@@ -607,15 +607,29 @@ int decoder_configure() {
   return COMIC_OK;
 }
 
+// Tensor-path (3xTF32) panels of the decoder weights.
+static int decoder_pack_tc(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
+  int rc;
+  const int XA = h->W + h->A;
+  if ((rc = pack_tc_weight(h, cv, h->w.lstm_kernel, h->KX, 4 * h->R, 4 * h->R, 1, 1, h->pk.tc_lstm, st, dry))) return rc;
+  if ((rc = pack_tc_weight(h, cv, h->pk.outq, h->R, h->LQ, h->LQ, 1, 1, h->pk.tc_outq, st, dry))) return rc;
+  if ((rc = pack_tc_weight(h, cv, h->w.memory_kernel, h->C, h->R, h->R, 1, 1, h->pk.tc_mem, st, dry))) return rc;
+  if (h->cfg.fm_projection == 2)
+    if ((rc = pack_tc_weight(h, cv, h->w.value_kernel, h->C, h->R, h->R, 1, 1, h->pk.tc_val, st, dry))) return rc;
+  int ninit = (h->cfg.init_method == 1) ? h->R : XA;
+  if ((rc = pack_tc_weight(h, cv, h->w.init_weight, h->E, ninit, ninit, 1, 1, h->pk.tc_init, st, dry))) return rc;
+  return COMIC_OK;
+}
+
 int decoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
   h->pk.outq = cv.take<float>((size_t)h->R * h->LQ);
   h->pk.outq_bias = cv.take<float>(h->LQ);
-  if (dry) return COMIC_OK;
+  if (dry) return decoder_pack_tc(h, cv, st, true);
   size_t n = (size_t)h->R * h->LQ;
   pack_outq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->w.out_kernel, h->w.out_bias, h->w.query_kernel,
                                                                h->pk.outq, h->pk.outq_bias, h->R, h->V, h->Vp);
   COMIC_CHECK_CUDA(cudaGetLastError());
-  return COMIC_OK;
+  return decoder_pack_tc(h, cv, st, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -731,8 +745,9 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
     a.seg[1] = ASeg{io.ctx_prev, io.src, A, A, io.src_limit};
     a.seg[2] = ASeg{io.h_prev, io.src, R, R, io.src_limit};
   }
+  const bool tc1 = use_tc(h, h->pk.tc_lstm, N);
   GemmPlan p1 = plan_gemm(N, 4 * R, h->KX, h->num_sms, true);
-  int nz1 = gemm_num_partials(h->KX, p1);
+  int nz1 = tc1 ? 1 : gemm_num_partials(h->KX, p1);
   Epi e1{};
   e1.nroute = 1;
   e1.r[0] = Route{0, 4 * R, sb.gates, 4 * R, 0};
@@ -741,7 +756,8 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
   e1.stop_n = (io.fin_count && io.t > 0) ? io.n_rows : 0x7fffffff;
   {
     Prof pf(h, T_GATES, st);
-    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.lstm_kernel, 4 * R, N, 4 * R, h->KX, e1, p1, st)));
+    if (tc1) COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a, h->pk.tc_lstm, N, 4 * R, e1, h->num_sms, st)));
+    else COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.lstm_kernel, 4 * R, N, 4 * R, h->KX, e1, p1, st)));
   }
   {
     Prof pf(h, T_LSTM, st);
@@ -756,8 +772,9 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
   APlain a2{};
   a2.nseg = 1;
   a2.seg[0] = ASeg{hq, nullptr, R, R, N};
+  const bool tc2 = use_tc(h, h->pk.tc_outq, N);
   GemmPlan p2 = plan_gemm(N, h->LQ, R, h->num_sms, true);
-  int nz2 = gemm_num_partials(R, p2);
+  int nz2 = tc2 ? 1 : gemm_num_partials(R, p2);
   Epi e2{};
   e2.nroute = 1;
   e2.stop = e1.stop;
@@ -766,7 +783,8 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
     e2.bias = h->pk.outq_bias;
     e2.r[0] = Route{0, h->LQ, sb.lq, h->LQ, 0};
     Prof pf(h, T_LQ, st);
-    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->pk.outq, h->LQ, N, h->LQ, R, e2, p2, st)));
+    if (tc2) COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a2, h->pk.tc_outq, N, h->LQ, e2, h->num_sms, st)));
+    else COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->pk.outq, h->LQ, N, h->LQ, R, e2, p2, st)));
   } else {
     e2.r[0] = Route{0, h->LQ, sb.lq_part, h->LQ, 0};
     e2.split_stride = (long long)N * h->LQ;
@@ -904,13 +922,15 @@ extern "C" int comic_project_fm(comic_handle_t h, const float* fm, int B, float*
   GemmPlan p = plan_gemm(Mrows, h->R, h->C, h->num_sms, false);
   {
     Prof pf(h, T_PROJECT, st);
-    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.memory_kernel, h->R, Mrows, h->R, h->C, e, p, st)));
+    if (use_tc(h, h->pk.tc_mem, Mrows)) COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a, h->pk.tc_mem, Mrows, h->R, e, h->num_sms, st)));
+    else COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.memory_kernel, h->R, Mrows, h->R, h->C, e, p, st)));
   }
   if (h->cfg.fm_projection == 2) {
     COMIC_REQUIRE(values_out && h->w.value_kernel, COMIC_E_BADARG, "project_fm: independent projection needs values_out");
     e.r[0] = Route{0, h->R, values_out, h->R, 0};
     Prof pf(h, T_PROJECT, st);
-    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.value_kernel, h->R, Mrows, h->R, h->C, e, p, st)));
+    if (use_tc(h, h->pk.tc_val, Mrows)) COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a, h->pk.tc_val, Mrows, h->R, e, h->num_sms, st)));
+    else COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.value_kernel, h->R, Mrows, h->R, h->C, e, p, st)));
   }
   return COMIC_OK;
 }

@@ -99,6 +99,26 @@ int encoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
     h->pk.grp_scale[b] = cv.take<float>(ng);
     h->pk.grp_shift[b] = cv.take<float>(ng);
   }
+  // tensor-path panels: the stem conv reads an NHWC4-padded image (cin 3 -> 4);
+  // Branch_0 / Branch_1a / Branch_2a only exist inside the grouped panels.
+  for (int i = 0; i < COMIC_NUM_CONVS; ++i) {
+    bool grouped = false;
+    for (int b = 0; b < kNumBlocks; ++b)
+      if (i == blk[b].conv[0] || i == blk[b].conv[1] || i == blk[b].conv[3]) grouped = true;
+    if (grouped) continue;
+    const comic_conv_desc_t& d = kConvs[i];
+    int K = d.k * d.k * d.c_in;
+    int cdst = (d.c_in == 3) ? 4 : d.c_in;
+    int rc = pack_tc_weight(h, cv, dry ? nullptr : h->w.conv_w[i], K, d.c_out, d.c_out, d.c_in, cdst,
+                            h->pk.tc_conv[i], st, dry);
+    if (rc) return rc;
+  }
+  for (int b = 0; b < kNumBlocks; ++b) {
+    h->pk.tc_grp[b].hi = cv.take<float>((size_t)round_up(blk[b].b0 + blk[b].b1a + blk[b].b2a, 16) *
+                                        round_up(blk[b].cin, tc::BK));
+    h->pk.tc_grp[b].lo = cv.take<float>((size_t)round_up(blk[b].b0 + blk[b].b1a + blk[b].b2a, 16) *
+                                        round_up(blk[b].cin, tc::BK));
+  }
   if (dry) return COMIC_OK;
   for (int i = 0; i < COMIC_NUM_CONVS; ++i) {
     int n = kConvs[i].c_out;
@@ -118,9 +138,25 @@ int encoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
       copy_cols_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->pk.bn_shift[ci], 1, n, h->pk.grp_shift[b], ng, coff);
       coff += n;
     }
+    // grouped panel for the tensor path (packed from the fp32 grouped panel above)
+    tc::TcWeight& tw = h->pk.tc_grp[b];
+    tw.N = ng; tw.K = blk[b].cin; tw.Npad = round_up(ng, 16); tw.Kpad = round_up(blk[b].cin, tc::BK);
+    size_t n = (size_t)tw.Npad * tw.Kpad;
+    tc::pack_bt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pk.grp_w[b], blk[b].cin, ng, ng, tw.hi, tw.lo,
+                                                                   tw.Kpad, tw.Npad, 1, 1);
+    COMIC_REQUIRE(tc::make_weight_maps(tw), COMIC_E_CUDA, "cuTensorMapEncodeTiled failed (grouped panel %d)", b);
   }
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;
+}
+
+// NHWC3 -> NHWC4 (zero 4th channel) so the stem conv's im2col rows are 16-byte vectors.
+__global__ void pad_c3_c4_kernel(const float* __restrict__ x, float* __restrict__ y, size_t npix) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npix) {
+    float4 v = make_float4(x[i * 3 + 0], x[i * 3 + 1], x[i * 3 + 2], 0.f);
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -226,7 +262,7 @@ static size_t enc_chunk_floats(int chunk, size_t* a, size_t* b, size_t* t1, size
   return *a + *b + *t1 + *t2 + *p;
 }
 
-static int enc_chunk_for(int B) { return B < 32 ? B : 32; }
+static int enc_chunk_for(int B) { return B < 64 ? B : 64; }
 
 int encoder_workspace_bytes(comic_handle_t h, int B, size_t* bytes) {
   (void)h;
@@ -244,7 +280,7 @@ static int run_conv(comic_handle_t h, const float* x, int B, int H, int W, int l
                     int ld_dst, int coff, int* Ho_out, int* Wo_out, cudaStream_t st) {
   const comic_conv_desc_t& d = kConvs[ci];
   AConv a;
-  a.x = x; a.H = H; a.W = W; a.Cin = d.c_in; a.ldx = ldx;
+  a.x = x; a.H = H; a.W = W; a.Cin = (d.c_in == 3 && ldx == 4) ? 4 : d.c_in; a.ldx = ldx;
   a.KH = d.k; a.KW = d.k; a.stride = d.stride;
   same_pads(H, d.k, d.stride, &a.Ho, &a.pad_t);
   same_pads(W, d.k, d.stride, &a.Wo, &a.pad_l);
@@ -258,7 +294,10 @@ static int run_conv(comic_handle_t h, const float* x, int B, int H, int W, int l
   e.split_stride = 0;
   GemmPlan p = plan_gemm(M, N, K, h->num_sms, false);
   cudaError_t err;
-  {
+  if (use_tc(h, h->pk.tc_conv[ci], M) && a.Cin % 4 == 0) {
+    Prof pf(h, T_CONV, st);
+    err = tc::launch_gemm_tc<1>(a, h->pk.tc_conv[ci], M, N, e, h->num_sms, st);
+  } else {
     Prof pf(h, T_CONV, st);
     if (d.c_in % 4 == 0) err = launch_gemm<1, 4>(a, h->w.conv_w[ci], N, M, N, K, e, p, st);
     else err = launch_gemm<1, 1>(a, h->w.conv_w[ci], N, M, N, K, e, p, st);
@@ -311,7 +350,8 @@ static int run_block(comic_handle_t h, int bi, const float* x, float* y, int B, 
     cudaError_t err;
     {
       Prof pf(h, T_CONV, st);
-      err = launch_gemm<0, 4>(a, h->pk.grp_w[bi], ng, M, ng, bd.cin, e, p, st);
+      if (use_tc(h, h->pk.tc_grp[bi], M)) err = tc::launch_gemm_tc<0>(a, h->pk.tc_grp[bi], M, ng, e, h->num_sms, st);
+      else err = launch_gemm<0, 4>(a, h->pk.grp_w[bi], ng, M, ng, bd.cin, e, p, st);
     }
     COMIC_CHECK_CUDA(err);
   }
@@ -344,7 +384,16 @@ int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out,
     const float* img = images + (size_t)b0 * 224 * 224 * 3;
     int Ho, Wo;
     // stem (inception_v1.py:70-93)
-    if ((rc = run_conv(h, img, nb, 224, 224, 3, 0, eb.a, 64, 0, &Ho, &Wo, st))) return rc;      // 112x112x64
+    if (use_tc(h, h->pk.tc_conv[0], nb * 112 * 112)) {
+      size_t npix = (size_t)nb * 224 * 224;
+      {
+        Prof pf(h, T_POOL, st);
+        pad_c3_c4_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(img, eb.b, npix);
+      }
+      if ((rc = run_conv(h, eb.b, nb, 224, 224, 4, 0, eb.a, 64, 0, &Ho, &Wo, st))) return rc;
+    } else {
+      if ((rc = run_conv(h, img, nb, 224, 224, 3, 0, eb.a, 64, 0, &Ho, &Wo, st))) return rc;    // 112x112x64
+    }
     if ((rc = run_maxpool(h, eb.a, eb.b, nb, 112, 112, 64, 3, 2, &Ho, &Wo, st))) return rc;     // 56x56x64
     if ((rc = run_conv(h, eb.b, nb, 56, 56, 64, 1, eb.a, 64, 0, nullptr, nullptr, st))) return rc;
     if ((rc = run_conv(h, eb.a, nb, 56, 56, 64, 2, eb.b, 192, 0, nullptr, nullptr, st))) return rc;  // 56x56x192

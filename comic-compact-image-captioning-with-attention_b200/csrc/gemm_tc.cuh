@@ -1,0 +1,490 @@
+// gemm_tc.cuh -- tcgen05 (5th-gen tensor core) GEMM / implicit-GEMM convolution
+// for sm_100a with fp32-equivalent accuracy ("3xTF32" error-compensated split).
+//
+//   C[M,N] = A[M,K] . B[K,N]      A, B, C fp32 in HBM
+//   A = A_hi + A_lo, B = B_hi + B_lo  (hi = tf32(x), lo = tf32(x - hi))
+//   C ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo   (dropped term ~2^-22 |a||b|)
+// accumulated in fp32 in tensor memory.  This keeps the reference's fp32
+// numerics (logits / attention maps within 1e-3) while moving the
+// contraction from the FFMA pipe to `tcgen05.mma.kind::tf32`.
+//
+// CTA = one 128 x BN output tile, 192 threads, warp-specialised:
+//   warps 0-3  A loaders: gather fp32 rows from global (plain segments with row
+//              indirection, or NHWC im2col with TF SAME padding), split into
+//              hi/lo in registers and store both tiles to shared memory in the
+//              canonical K-major SWIZZLE_128B layout; afterwards the epilogue
+//              (tcgen05.ld -> scale/shift/ReLU -> routed fp32 stores).
+//   warp 4     TMEM allocator + MMA issuer (one elected lane): 12 UMMAs
+//              (128 x BN x 8) per 32-wide K block, tcgen05.commit frees the stage.
+//   warp 5     TMA producer for the pre-split, pre-transposed weight panels
+//              B_hi / B_lo ([Npad, Kpad] K-major, packed at bind time).
+// mbarrier ring of STAGES shared-memory stages; accumulator 128 lanes x BN
+// fp32 columns of TMEM.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_f32.cuh"
+
+namespace comic {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // fp32 elements = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// K-major SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(1)<<16 | SBO(1024B>>4)<<32 | version 1 <<46 | layout SWIZZLE_128B(2)<<61.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
+// K-major A and B, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct RowEntry {   // 16 bytes, one per tile row
+  long long off;    // AConv: element offset of the image base; APlain: unused
+  int hi0, wi0;     // AConv: top-left input coordinate of the receptive field
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int ROWTAB_BYTES = BM * 3 * 8;          // 3 segment row pointers or RowEntry
+  static constexpr int BAR_BYTES = (3 * STAGES + 1) * 8 + 8;
+  static constexpr int TOTAL = TILES_BYTES + ROWTAB_BYTES + BAR_BYTES + 1024;   // + alignment slack
+};
+
+template <int BN, int STAGES, int AMODE>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
+                   const __grid_constant__ CUtensorMap tm_lo, int M, int N, int K, Epi epi) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  if (epi.stop != nullptr && *epi.stop >= epi.stop_n) return;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* rowtab = smem + L::TILES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowtab + L::ROWTAB_BYTES);
+  uint64_t* full_a = bars;
+  uint64_t* full_b = bars + STAGES;
+  uint64_t* empty = bars + 2 * STAGES;
+  uint64_t* accum_bar = bars + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int nk = (K + BK - 1) / BK;
+
+  // ---- one-time setup ----
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_a[s], 128);
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (tid < BM) {
+    int m = m0 + tid;
+    if constexpr (AMODE == 0) {
+      const float** rp = reinterpret_cast<const float**>(rowtab);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const float* p = nullptr;
+        if (s < a.nseg && m < M) {
+          int r = m;
+          if (a.seg[s].idx) r = a.seg[s].idx[m];
+          if (r >= 0 && r < a.seg[s].idx_limit) p = a.seg[s].ptr + (size_t)r * a.seg[s].ld;
+        }
+        rp[s * BM + tid] = p;
+      }
+    } else {
+      RowEntry* re = reinterpret_cast<RowEntry*>(rowtab);
+      RowEntry e;
+      e.off = -1; e.hi0 = 0; e.wi0 = 0;
+      if (m < M) {
+        int hw = a.Ho * a.Wo;
+        int b = m / hw, rem = m - b * hw;
+        int ho = rem / a.Wo, wo = rem - ho * a.Wo;
+        e.off = (long long)b * a.H * a.W * a.ldx;
+        e.hi0 = ho * a.stride - a.pad_t;
+        e.wi0 = wo * a.stride - a.pad_l;
+      }
+      re[tid] = e;
+    }
+  }
+  if (warp == 4) {
+    // allocate BN fp32 accumulator columns of tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =====================  A loaders  =====================
+    const int chunk = lane & 7;          // 16-byte chunk within the 128-byte K row
+    const int rsub = lane >> 3;          // 4 rows per warp instruction
+    float4 cur[8], nxt[8];
+    auto gload = [&](int kt, float4* dst) {
+      const int kk = kt * BK + chunk * 4;
+      if constexpr (AMODE == 0) {
+        const float* const* rp = reinterpret_cast<const float* const*>(rowtab);
+        int seg = -1, col = kk;
+        if (kk < K) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            if (seg < 0 && s < a.nseg) {
+              if (col < a.seg[s].ncols) seg = s;
+              else col -= a.seg[s].ncols;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int row = warp * 32 + i * 4 + rsub;
+          const float* p = (seg >= 0) ? rp[seg * BM + row] : nullptr;
+          dst[i] = p ? ldg4(p + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        const RowEntry* re = reinterpret_cast<const RowEntry*>(rowtab);
+        int kh = 0, kw = 0, ci = 0;
+        bool kvalid = kk < K;
+        if (kvalid) {
+          int tap = kk / a.Cin;
+          ci = kk - tap * a.Cin;
+          kh = tap / a.KW;
+          kw = tap - kh * a.KW;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int row = warp * 32 + i * 4 + rsub;
+          RowEntry e = re[row];
+          int hi = e.hi0 + kh, wi = e.wi0 + kw;
+          bool ok = kvalid && e.off >= 0 && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+          dst[i] = ok ? ldg4(a.x + e.off + ((long long)hi * a.W + wi) * a.ldx + ci)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    gload(0, cur);
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % STAGES;
+      const uint32_t ph = (kt / STAGES) & 1;
+      if (kt + 1 < nk) gload(kt + 1, nxt);
+      mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* a_hi = smem + s * L::STAGE_BYTES;
+      uint8_t* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int row = warp * 32 + i * 4 + rsub;
+        uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
+        float4 v = cur[i];
+        uint4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - __uint_as_float(h.x));
+        l.y = tf32_rna(v.y - __uint_as_float(h.y));
+        l.z = tf32_rna(v.z - __uint_as_float(h.z));
+        l.w = tf32_rna(v.w - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(a_hi + off) = h;
+        *reinterpret_cast<uint4*>(a_lo + off) = l;
+      }
+      fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(&full_a[s]);
+      if (kt + 1 < nk) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      }
+    }
+    // =====================  epilogue  =====================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+          "%14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < M) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          int n = n0 + c0 + g * 4;
+          if (n >= N) continue;
+          float4 v = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                 __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+          if (epi.scale) {
+            float4 sc = ldg4(epi.scale + n);
+            v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+          }
+          if (epi.bias) {
+            float4 bs = ldg4(epi.bias + n);
+            v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w;
+          }
+          if (epi.relu) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          }
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr) {
+            if (rr < epi.nroute && n >= epi.r[rr].n0 && n < epi.r[rr].n1) {
+              float* dst = epi.r[rr].dst + (size_t)m * epi.r[rr].ld + epi.r[rr].coff + (n - epi.r[rr].n0);
+              *reinterpret_cast<float4*>(dst) = v;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =====================  MMA issuer  =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&full_a[s], ph);
+        mbar_wait(&full_b[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+        const uint32_t b_hi = a_lo + A_TILE_BYTES;
+        const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
+        const uint64_t dah = make_desc_sw128(a_hi), dal = make_desc_sw128(a_lo);
+        const uint64_t dbh = make_desc_sw128(b_hi), dbl = make_desc_sw128(b_lo);
+#pragma unroll
+        for (int k8 = 0; k8 < BK / 8; ++k8) {
+          const uint64_t adv = (uint64_t)((k8 * 8 * 4) >> 4);     // 32 bytes per K=8 step inside the swizzle row
+          umma_tf32(tmem_base, dah + adv, dbh + adv, idesc, (kt > 0 || k8 > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, dal + adv, dbh + adv, idesc, 1u);
+          umma_tf32(tmem_base, dah + adv, dbl + adv, idesc, 1u);
+        }
+        umma_commit(&empty[s]);            // frees the stage when the MMAs above retire
+      }
+      umma_commit(accum_bar);              // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  } else {
+    // =====================  TMA producer (weights)  =====================
+    if (lane == 0) {
+      for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const uint32_t b_hi = smem_u32(smem + s * L::STAGE_BYTES + 2 * A_TILE_BYTES);
+        const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
+        mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES);
+        tma_load_2d(b_hi, &tm_hi, &full_b[s], kt * BK, n0);
+        tma_load_2d(b_lo, &tm_lo, &full_b[s], kt * BK, n0);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side.
+// ---------------------------------------------------------------------------
+// A weight matrix packed for the tensor path: B^T split into hi / lo, [Npad, Kpad]
+// row-major (K-major), zero padded; one tensor map per BN option.
+struct TcWeight {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  int N = 0, K = 0, Npad = 0, Kpad = 0;   // K = extent of the A operand's K index space
+  CUtensorMap tm_hi[3], tm_lo[3];   // BN = 64, 128, 256
+  bool ready = false;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+inline bool make_weight_maps(TcWeight& w) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  const int bns[3] = {64, 128, 256};
+  for (int i = 0; i < 3; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)w.Kpad, (cuuint64_t)w.Npad};
+    cuuint64_t strides[1] = {(cuuint64_t)w.Kpad * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bns[i]};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r1 = enc(&w.tm_hi[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.hi, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&w.tm_lo[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.lo, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return false;
+  }
+  w.ready = true;
+  return true;
+}
+
+// B^T hi/lo packing: src W[k][n] (row stride ldw); optional channel padding of an
+// HWIO conv kernel (cin_src -> cin_dst, e.g. 3 -> 4 for the NHWC4 stem input).
+static __global__ void pack_bt_kernel(const float* __restrict__ W, int K, int N, int ldw, float* __restrict__ hi,
+                               float* __restrict__ lo, int Kpad, int Npad, int cin_src, int cin_dst) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Npad * Kpad) return;
+  int n = (int)(i / Kpad), kp = (int)(i % Kpad);
+  float v = 0.f;
+  if (n < N) {
+    int k = kp;
+    bool ok = kp < K;
+    if (cin_src != cin_dst) {
+      int tap = kp / cin_dst, ci = kp - tap * cin_dst;
+      ok = ci < cin_src && tap < K / cin_src;
+      k = tap * cin_src + ci;
+    }
+    if (ok) v = W[(size_t)k * ldw + n];
+  }
+  float h = __uint_as_float(tf32_rna(v));
+  hi[i] = h;
+  lo[i] = __uint_as_float(tf32_rna(v - h));
+}
+
+template <int BN, int STAGES, int AMODE>
+inline cudaError_t launch_one(const typename AParam<AMODE>::type& a, const TcWeight& w, int bn_idx, int M, int N,
+                              const Epi& epi, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, AMODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
+  gemm_tf32x3_kernel<BN, STAGES, AMODE><<<grid, 192, L::TOTAL, st>>>(a, w.tm_hi[bn_idx], w.tm_lo[bn_idx], M, N,
+                                                                    w.K, epi);
+  return cudaGetLastError();
+}
+
+// Pick the N tile: the widest that still yields >= ~1 wave of CTAs.
+inline int pick_bn(int M, int N, int num_sms) {
+  int mt = (M + BM - 1) / BM;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  int t256 = mt * ((N + 255) / 256);
+  if (t256 >= num_sms) return 256;
+  return 128;
+}
+
+template <int AMODE>
+inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const TcWeight& w, int M, int N,
+                                  const Epi& epi, int num_sms, cudaStream_t st) {
+  int bn = pick_bn(M, N, num_sms);
+  if (bn == 64) return launch_one<64, 4, AMODE>(a, w, 0, M, N, epi, st);
+  if (bn == 128) return launch_one<128, 3, AMODE>(a, w, 1, M, N, epi, st);
+  return launch_one<256, 2, AMODE>(a, w, 2, M, N, epi, st);
+}
+
+}  // namespace tc
+}  // namespace comic

@@ -75,6 +75,7 @@ SIGNATURES = {
     'comic_gather_tree': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     'comic_gemm_f32': (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
     'comic_launch_count': (_I, [_P, C.POINTER(C.c_int64)]),
+    'comic_set_precision': (_I, [_P, _I]),
     'comic_profile_enable': (_I, [_P, C.c_uint32]),
     'comic_profile_read': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
@@ -357,9 +358,14 @@ class Engine(object):
         M, K = A.shape
         N = Bm.shape[1]
         out = self.f32(M, N)
+        ws = self._workspace(5, N, K, 1)
         self._check(self.lib.comic_gemm_f32(self._h, _ptr(A), A.stride(0), _ptr(Bm), Bm.stride(0), _ptr(bias),
-                                            _ptr(out), N, M, N, K, None, 0, self.stream()))
+                                            _ptr(out), N, M, N, K, _ptr(ws), ws.numel(), self.stream()))
         return out
+
+    def set_precision(self, mode):
+        """'f32' (FFMA everywhere) or 'tf32x3' (tcgen05, fp32-equivalent; default)."""
+        self._check(self.lib.comic_set_precision(self._h, {'f32': 0, 'tf32x3': 1}[mode]))
 
     def profile_enable(self, tags):
         mask = 0

@@ -109,7 +109,15 @@ int comic_packed_bytes(comic_handle_t h, size_t* bytes);
 int comic_bind_weights(comic_handle_t h, const comic_weights_t* w, int with_cnn,
                        void* packed, size_t packed_bytes, void* stream);
 
-/* mode: 0 encode, 1 decode_greedy, 2 decode_beam, 3 decode_step. */
+/* Arithmetic of the dense contractions (GEMMs / convolutions with >= 128 rows):
+ *   0  fp32 FFMA (bit-for-bit the reference's fp32 arithmetic up to summation order);
+ *   1  tcgen05 tensor cores, error-compensated 3xTF32 split with fp32 accumulation
+ *      (fp32-equivalent: ~1e-6 relative; default).
+ * Small-row GEMMs (M < 128, e.g. batch-8 decode) always use the FFMA kernel. */
+int comic_set_precision(comic_handle_t h, int mode);
+
+/* mode: 0 encode, 1 decode_greedy, 2 decode_beam, 3 decode_step, 4 rnn_init,
+ * 5 gemm_f32 (B = N, k = K of the GEMM). */
 int comic_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes);
 
 /* E1+E2: ModelBase._encoder src/model_base.py:56-104 (InceptionV1 forward,

@@ -19,33 +19,40 @@ def torch_mod():
     return torch
 
 
-def _engine(c, W, with_cnn=True):
+def _engine(c, W, with_cnn=True, precision='tf32x3'):
     from comic_b200.engine import Engine
     eng = Engine(c)
     eng.bind_weights(W, with_cnn=with_cnn)
+    eng.set_precision(precision)
     return eng
 
 
+@pytest.mark.parametrize('precision', ['f32', 'tf32x3'])
 @pytest.mark.parametrize('M,N,K', [(24, 2048, 1280), (7, 64, 36), (300, 132, 147), (1536, 772, 512),
-                                   (129, 68, 520), (64, 2048, 768)])
-def test_gemm_f32(torch_mod, M, N, K):
+                                   (129, 68, 520), (64, 2048, 768), (1000, 448, 528), (4096, 64, 32),
+                                   (256, 2048, 1280)])
+def test_gemm_f32(torch_mod, M, N, K, precision):
+    """The dense kernel alone: FFMA path and tcgen05 3xTF32 path (M >= 128) vs fp64."""
     torch = torch_mod
     c = comic_config()
-    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False)
+    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False, precision=precision)
     rng = np.random.default_rng(M + N + K)
     A = rng.standard_normal((M, K)).astype(np.float32)
     Bm = rng.standard_normal((K, N)).astype(np.float32)
     bias = rng.standard_normal((N,)).astype(np.float32)
     out = eng.gemm(eng.to_dev(A), eng.to_dev(Bm), eng.to_dev(bias)).cpu().numpy()
     ref = A.astype(np.float64) @ Bm.astype(np.float64) + bias
-    assert rel_err(out, ref) < 1e-5
+    # FFMA: fp32 round-off only.  3xTF32: dropped lo*lo term (2^-22) plus the tensor core's
+    # truncating fp32 accumulation, measured ~6e-6 at K = 1280.
+    assert rel_err(out, ref) < (1e-5 if precision == 'f32' else 5e-5)
 
 
-def test_encoder_matches_oracle(torch_mod):
+@pytest.mark.parametrize('precision', ['f32', 'tf32x3'])
+def test_encoder_matches_oracle(torch_mod, precision):
     import inception_v1_oracle as I
     c = comic_config()
     W = make_weights(c)
-    eng = _engine(c, W)
+    eng = _engine(c, W, precision=precision)
     img = images(3)
     emb, fm, m5c = eng.encode(eng.to_dev(img), want_mixed5c=True)
     o_emb, o_fm, ep = I.encoder(img, W, c)
@@ -56,15 +63,21 @@ def test_encoder_matches_oracle(torch_mod):
 
 
 def test_encoder_chunking_batch_independent(torch_mod):
-    """Images are independent units: batch of 35 (two chunks) == singles."""
+    """Images are independent units: a batch of 70 (two chunks) == singles.  Bit-identical
+    on the FFMA path; the tensor path switches kernels with the row count (M < 128 -> FFMA),
+    so it is compared at tolerance."""
     c = comic_config()
     W = make_weights(c)
-    eng = _engine(c, W)
-    img = images(35, seed=5)
+    img = images(70, seed=5)
+    eng = _engine(c, W, precision='f32')
     emb, fm = eng.encode(eng.to_dev(img))
-    emb1, fm1 = eng.encode(eng.to_dev(img[33:34]))
-    assert torch_mod.equal(fm[33:34], fm1)
-    assert torch_mod.equal(emb[33:34], emb1)
+    emb1, fm1 = eng.encode(eng.to_dev(img[67:68]))
+    assert torch_mod.equal(fm[67:68], fm1)
+    assert torch_mod.equal(emb[67:68], emb1)
+    eng.set_precision('tf32x3')
+    emb2, fm2 = eng.encode(eng.to_dev(img))
+    assert rel_err(fm2.cpu().numpy(), fm.cpu().numpy()) < 1e-4
+    assert rel_err(emb2.cpu().numpy(), emb.cpu().numpy()) < 1e-4
 
 
 CONFIGS = {
@@ -115,6 +128,34 @@ def test_decode_step_matches_oracle(torch_mod, name):
     assert rel_err(r['attention'].cpu().numpy(), new_state['attention']) < TOL
     a = r['alignments'].cpu().numpy().reshape(B * k, c.attn_num_heads, -1)
     np.testing.assert_allclose(a.sum(-1), 1.0, atol=1e-5)       # alpha sums to 1 per head
+
+
+@pytest.mark.parametrize('name', ['comic256', 'word_none_h1'])
+def test_decode_step_large_rows_tensor_path(torch_mod, name):
+    """N = 144 rows: gate / logits|query GEMMs run on the tcgen05 3xTF32 kernel with
+    the beam-state row indirection and the 3-segment A operand."""
+    import comic_oracle as O
+    c = CONFIGS[name]()
+    W = make_weights(c, include_cnn=False)
+    eng = _engine(c, W, with_cnn=False)
+    B, k = 48, 3
+    im, fm = fake_features(B)
+    dec = O.Decoder(W, c)
+    dec.setup_memory(O.tile_batch(fm, k))
+    c0, h0 = dec.init_state(O.tile_batch(im, k))
+    state = dec.zero_state((c0, h0))
+    rng = np.random.default_rng(5)
+    state['attention'] = rng.standard_normal(state['attention'].shape).astype(np.float32) * 0.3
+    toks = rng.integers(0, dec.V, size=(B * k,)).astype(np.int32)
+    cell_out, ns, al = dec.call(dec.embed(toks), state)
+    logits = dec.output_layer(cell_out)
+    keys, values = eng.project_fm(eng.to_dev(fm))
+    r = eng.decode_step(keys, values, B, k, eng.to_dev(toks), eng.to_dev(state['c']), eng.to_dev(state['h']),
+                        eng.to_dev(state['attention']))
+    assert rel_err(r['h'].cpu().numpy(), ns['h']) < TOL
+    assert rel_err(r['logits'].cpu().numpy(), logits) < TOL
+    assert rel_err(r['alignments'].cpu().numpy(), al) < TOL
+    assert rel_err(r['attention'].cpu().numpy(), ns['attention']) < TOL
 
 
 def test_decode_step_train_masks(torch_mod):
