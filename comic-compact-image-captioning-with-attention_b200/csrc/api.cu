@@ -130,9 +130,19 @@ int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, i
 }  // namespace comic
 
 extern "C" int comic_set_precision(comic_handle_t h, int mode) {
-  COMIC_REQUIRE(h && (mode == 0 || mode == 1), COMIC_E_BADARG, "set_precision: mode must be 0 (f32) or 1 (3xtf32)");
+  COMIC_REQUIRE(h && mode >= 0 && mode <= 2, COMIC_E_BADARG, "set_precision: mode must be 0 (f32), 1 (split tensor) or 2 (fast)");
   h->precision = mode;
   return COMIC_OK;
+}
+
+extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
+  COMIC_REQUIRE(h, COMIC_E_BADARG, "set_option: null handle");
+  switch (option) {
+    case COMIC_OPT_FUSED_ATTN_MIN_IMAGES: h->fused_min_images = value; return COMIC_OK;
+    default: break;
+  }
+  set_error("set_option: unknown option %d", option);
+  return COMIC_E_BADARG;
 }
 
 extern "C" int comic_packed_bytes(comic_handle_t h, size_t* bytes) {
@@ -213,7 +223,7 @@ extern "C" int comic_gemm_f32(comic_handle_t h, const float* A, int lda, const f
   e.stop_n = 0x7fffffff;
   GemmPlan p = plan_gemm(M, N, K, h->num_sms, false);
   cudaError_t err;
-  if (h->precision == 1 && M >= 128 && K % 4 == 0 && lda % 4 == 0) {
+  if (h->precision >= 1 && M >= 128 && K % 4 == 0 && lda % 4 == 0) {
     // tensor path: pack B on the fly into the caller's workspace
     size_t need = 2 * (size_t)round_up(N, 16) * round_up(K, tc::BK) * sizeof(float) + 1024;
     COMIC_REQUIRE(ws && ws_bytes >= need, COMIC_E_WORKSPACE, "gemm_f32: tensor path needs %zu workspace bytes", need);

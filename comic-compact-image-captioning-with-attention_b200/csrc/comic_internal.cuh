@@ -68,7 +68,8 @@ struct comic_handle_s {
   int R, W, H, C, M, E, V, Vp, A, VAL, LQ, KX;
   comic_weights_t w;
   bool bound = false, cnn_bound = false;
-  int precision = 1;   // 0: fp32 FFMA everywhere; 1: tcgen05 3xTF32 for GEMMs with M >= 128
+  int precision = 1;   // 0: fp32 FFMA everywhere; 1: tcgen05 split-precision GEMMs with M >= 128; 2: 1 + tanh.approx
+  int fused_min_images = 48;   // fused attention kernel (one CTA per image) from this batch size on
   comic::Packed pk;
   int64_t launches = 0;
   // optional per-kernel-class device timing (bench.py roofline): CUDA events
@@ -121,7 +122,7 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Carve + (unless dry) fill one tensor-path weight pack from W[K][N] (row stride ldw).
 int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, int ldw, int cin_src, int cin_dst,
                    tc::TcWeight& out, cudaStream_t st, bool dry);
-inline bool use_tc(comic_handle_t h, const tc::TcWeight& w, int M) { return h->precision == 1 && w.ready && M >= 128; }
+inline bool use_tc(comic_handle_t h, const tc::TcWeight& w, int M) { return h->precision >= 1 && w.ready && M >= 128; }
 
 // encoder.cu
 int encoder_workspace_bytes(comic_handle_t h, int B, size_t* bytes);

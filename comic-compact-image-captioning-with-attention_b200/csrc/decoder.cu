@@ -19,6 +19,7 @@
 #include <float.h>
 #include <math.h>
 
+#include "attention.cuh"
 #include "comic_internal.cuh"
 
 namespace comic {
@@ -724,6 +725,72 @@ static int dispatch_scores(comic_handle_t h, const StepIO& io, const StepBufs& s
   return COMIC_OK;
 }
 
+// Fused scores + softmax + context (attention.cuh), one CTA per image.
+template <int R, int H, int MODE, bool FAST>
+static cudaError_t launch_fused_one(const AttnArgs& aa, int B, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<R, H, MODE, FAST>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  attn_fused_kernel<R, H, MODE, FAST><<<B, kAttnThreads, smem, st>>>(aa);
+  return cudaGetLastError();
+}
+
+template <int R, int H>
+static cudaError_t launch_fused(comic_handle_t h, const AttnArgs& aa, int B, size_t smem, cudaStream_t st) {
+  if (h->cfg.alignment != 0) return launch_fused_one<R, H, 1, false>(aa, B, smem, st);
+  if (h->precision == 2) return launch_fused_one<R, H, 0, true>(aa, B, smem, st);
+  return launch_fused_one<R, H, 0, false>(aa, B, smem, st);
+}
+
+// Returns 1 when the fused kernel was launched, 0 when the configuration is not covered
+// (caller falls back to the sliced scores + context kernels), < 0 on error.
+static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, float* ctx_dst,
+                          int ld_ctx, cudaStream_t st) {
+  if (B < h->fused_min_images || h->VAL > 1024 || h->VAL % 4 != 0) return 0;
+  size_t smem = attn_fused_smem(k, h->R, h->H, h->M, h->VAL);
+  if (smem > 200 * 1024) return 0;
+  AttnArgs aa{};
+  aa.keys = io.keys; aa.values = io.values; aa.lq = sb.lq; aa.ld_lq = h->LQ; aa.q_off = h->Vp;
+  aa.gamma = h->w.ln_gamma; aa.beta = h->w.ln_beta; aa.vvec = h->w.attention_v; aa.temperature = h->w.temperature;
+  aa.ctx_out = ctx_dst; aa.ld_ctx = ld_ctx; aa.hist_t = io.hist_t; aa.att_mask = io.att_mask;
+  aa.att_keep = io.att_keep; aa.k = k; aa.M = h->M; aa.VAL = h->VAL; aa.prob_fn = h->cfg.prob_fn;
+  aa.fin_count = io.fin_count; aa.t = io.t; aa.n_rows = io.n_rows;
+  cudaError_t e = cudaErrorInvalidValue;
+  bool ok = true;
+  Prof pf(h, T_SCORES, st);
+  if (h->R == 512) {
+    switch (h->H) {
+      case 1: e = launch_fused<512, 1>(h, aa, B, smem, st); break;
+      case 2: e = launch_fused<512, 2>(h, aa, B, smem, st); break;
+      case 4: e = launch_fused<512, 4>(h, aa, B, smem, st); break;
+      case 8: e = launch_fused<512, 8>(h, aa, B, smem, st); break;
+      case 16: e = launch_fused<512, 16>(h, aa, B, smem, st); break;
+      default: ok = false;
+    }
+  } else if (h->R == 256) {
+    switch (h->H) {
+      case 1: e = launch_fused<256, 1>(h, aa, B, smem, st); break;
+      case 4: e = launch_fused<256, 4>(h, aa, B, smem, st); break;
+      case 8: e = launch_fused<256, 8>(h, aa, B, smem, st); break;
+      default: ok = false;
+    }
+  } else if (h->R == 1024) {
+    switch (h->H) {
+      case 1: e = launch_fused<1024, 1>(h, aa, B, smem, st); break;
+      case 8: e = launch_fused<1024, 8>(h, aa, B, smem, st); break;
+      case 16: e = launch_fused<1024, 16>(h, aa, B, smem, st); break;
+      default: ok = false;
+    }
+  } else ok = false;
+  if (!ok) { h->launches--; return 0; }
+  COMIC_CHECK_CUDA(e);
+  return 1;
+}
+
 // One attention-wrapper step on N = B*k rows.
 static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, cudaStream_t st) {
   const int N = B * k, R = h->R, W = h->W, A = h->A;
@@ -796,15 +863,16 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
                                                                        io.fin_count, io.t, io.n_rows);
   }
   // --- attention ---
-  int rc = dispatch_scores(h, io, sb, B, k, st);
-  if (rc) return rc;
   {
     int VAL = h->VAL;
-    dim3 grid(B, (VAL + 127) / 128);
-    size_t smem = step_smem_ctx(k, h->H, h->M);
     float* ctx_dst = h->cfg.context_layer ? sb.ctxraw : io.ctx_new;
     int ld_ctx = h->cfg.context_layer ? VAL : A;
-    {
+    int rc = dispatch_fused(h, io, sb, B, k, ctx_dst, ld_ctx, st);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if ((rc = dispatch_scores(h, io, sb, B, k, st))) return rc;
+      dim3 grid(B, (VAL + 127) / 128);
+      size_t smem = step_smem_ctx(k, h->H, h->M);
       Prof pf(h, T_CTX, st);
       attn_ctx_kernel<<<grid, 128, smem, st>>>(sb.scores, io.values, VAL, ctx_dst, ld_ctx, io.hist_t, io.att_mask,
                                               io.att_keep, k, h->H, h->M, h->cfg.prob_fn, io.fin_count, io.t,

@@ -76,6 +76,7 @@ SIGNATURES = {
     'comic_gemm_f32': (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
     'comic_launch_count': (_I, [_P, C.POINTER(C.c_int64)]),
     'comic_set_precision': (_I, [_P, _I]),
+    'comic_set_option': (_I, [_P, _I, _I]),
     'comic_profile_enable': (_I, [_P, C.c_uint32]),
     'comic_profile_read': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
@@ -365,7 +366,10 @@ class Engine(object):
 
     def set_precision(self, mode):
         """'f32' (FFMA everywhere) or 'tf32x3' (tcgen05, fp32-equivalent; default)."""
-        self._check(self.lib.comic_set_precision(self._h, {'f32': 0, 'tf32x3': 1}[mode]))
+        self._check(self.lib.comic_set_precision(self._h, {'f32': 0, 'tf32x3': 1, 'split': 1, 'fast': 2}[mode]))
+
+    def set_option(self, name, value):
+        self._check(self.lib.comic_set_option(self._h, {'fused_attn_min_images': 0}[name], int(value)))
 
     def profile_enable(self, tags):
         mask = 0

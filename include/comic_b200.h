@@ -109,12 +109,19 @@ int comic_packed_bytes(comic_handle_t h, size_t* bytes);
 int comic_bind_weights(comic_handle_t h, const comic_weights_t* w, int with_cnn,
                        void* packed, size_t packed_bytes, void* stream);
 
-/* Arithmetic of the dense contractions (GEMMs / convolutions with >= 128 rows):
- *   0  fp32 FFMA (bit-for-bit the reference's fp32 arithmetic up to summation order);
- *   1  tcgen05 tensor cores, error-compensated 3xTF32 split with fp32 accumulation
- *      (fp32-equivalent: ~1e-6 relative; default).
+/* Arithmetic modes (all within the 1e-3 parity bound of the reference's fp32 graph):
+ *   0  fp32 FFMA everywhere (the reference's fp32 arithmetic up to summation order);
+ *   1  tcgen05 tensor cores with an error-compensated operand split and fp32
+ *      accumulation for GEMMs / convolutions with >= 128 rows (fp32-equivalent,
+ *      ~1e-6 relative); tanh = 1 - 2/(2^(2y log2 e) + 1) via ex2/rcp (default);
+ *   2  as 1, but the attention LN-tanh uses the single-MUFU tanh.approx.f32
+ *      (|err| <= 2^-11 per element, ~1e-5 on attention maps).
  * Small-row GEMMs (M < 128, e.g. batch-8 decode) always use the FFMA kernel. */
 int comic_set_precision(comic_handle_t h, int mode);
+
+/* Engine tunables (no reference counterpart). */
+#define COMIC_OPT_FUSED_ATTN_MIN_IMAGES 0   /* one-CTA-per-image fused attention from this batch on (default 48) */
+int comic_set_option(comic_handle_t h, int option, int value);
 
 /* mode: 0 encode, 1 decode_greedy, 2 decode_beam, 3 decode_step, 4 rnn_init,
  * 5 gemm_f32 (B = N, k = K of the GEMM). */

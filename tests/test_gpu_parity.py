@@ -19,11 +19,13 @@ def torch_mod():
     return torch
 
 
-def _engine(c, W, with_cnn=True, precision='tf32x3'):
+def _engine(c, W, with_cnn=True, precision='tf32x3', fused=None):
     from comic_b200.engine import Engine
     eng = Engine(c)
     eng.bind_weights(W, with_cnn=with_cnn)
     eng.set_precision(precision)
+    if fused is not None:      # True: one-CTA-per-image fused attention at any batch; False: sliced kernels
+        eng.set_option('fused_attn_min_images', 1 if fused else 1 << 30)
     return eng
 
 
@@ -90,13 +92,14 @@ CONFIGS = {
 }
 
 
+@pytest.mark.parametrize('fused', [False, True])
 @pytest.mark.parametrize('name', list(CONFIGS))
-def test_decode_step_matches_oracle(torch_mod, name):
+def test_decode_step_matches_oracle(torch_mod, name, fused):
     import comic_oracle as O
     torch = torch_mod
     c = CONFIGS[name]()
     W = make_weights(c, include_cnn=False)
-    eng = _engine(c, W, with_cnn=False)
+    eng = _engine(c, W, with_cnn=False, fused=fused)
     B, k = 3, 3
     im, fm = fake_features(B)
     dec = O.Decoder(W, c)
@@ -158,12 +161,13 @@ def test_decode_step_large_rows_tensor_path(torch_mod, name):
     assert rel_err(r['attention'].cpu().numpy(), ns['attention']) < TOL
 
 
-def test_decode_step_train_masks(torch_mod):
+@pytest.mark.parametrize('fused', [False, True])
+def test_decode_step_train_masks(torch_mod, fused):
     """DropoutWrapper in/out masks + attention-map dropout with explicit masks."""
     import comic_oracle as O
     c = comic_config()
     W = make_weights(c, include_cnn=False)
-    eng = _engine(c, W, with_cnn=False)
+    eng = _engine(c, W, with_cnn=False, fused=fused)
     B = 4
     im, fm = fake_features(B)
     dec = O.Decoder(W, c)
@@ -255,13 +259,14 @@ def _decode_inputs(c, B, seed=0):
     return W, im, fm
 
 
+@pytest.mark.parametrize('fused', [False, True])
 @pytest.mark.parametrize('name,B,k,max_it', [('comic256', 4, 3, 14), ('word_none_h1', 3, 3, 8),
                                              ('comic256', 2, 7, 10), ('independent_h4', 2, 2, 6)])
-def test_beam_search_matches_oracle(torch_mod, name, B, k, max_it):
+def test_beam_search_matches_oracle(torch_mod, name, B, k, max_it, fused):
     import comic_oracle as O
     c = CONFIGS[name]()
     W, im, fm = _decode_inputs(c, B)
-    eng = _engine(c, W, with_cnn=False)
+    eng = _engine(c, W, with_cnn=False, fused=fused)
     ref = O.beam_search_decode(O.Decoder(W, c), im, fm, k, 0.0, max_it)
     keys, values = eng.project_fm(eng.to_dev(fm))
     c0, h0 = eng.rnn_init(eng.to_dev(im))
@@ -302,11 +307,12 @@ def test_beam_search_eos_and_early_stop(torch_mod):
     assert rel_err(r['attn'][:, :, :T].cpu().numpy(), am) < 1e-3
 
 
-def test_greedy_matches_oracle(torch_mod):
+@pytest.mark.parametrize('fused', [False, True])
+def test_greedy_matches_oracle(torch_mod, fused):
     import comic_oracle as O
     c = comic_config()
     W, im, fm = _decode_inputs(c, 5)
-    eng = _engine(c, W, with_cnn=False)
+    eng = _engine(c, W, with_cnn=False, fused=fused)
     ref = O.greedy_decode(O.Decoder(W, c), im, fm, 12)
     keys, values = eng.project_fm(eng.to_dev(fm))
     c0, h0 = eng.rnn_init(eng.to_dev(im))
@@ -317,6 +323,67 @@ def test_greedy_matches_oracle(torch_mod):
     assert rel_err(r['logits'][:T].cpu().numpy(), ref['logits']) < TOL
     _, _, am = O.post_process_plain(ref['logits'], ref['ids'], ref['alignment_history'], 8)
     assert rel_err(r['attn'][:, :, :T].cpu().numpy(), am) < 1e-3
+
+
+def test_fast_tanh_mode_within_north_star_tolerance(torch_mod):
+    """precision 'fast' (tanh.approx.f32 in the LN-tanh) stays inside the 1e-3 bound."""
+    import comic_oracle as O
+    c = comic_config()
+    W = make_weights(c, include_cnn=False)
+    eng = _engine(c, W, with_cnn=False, precision='fast', fused=True)
+    B, k = 4, 3
+    im, fm = fake_features(B)
+    dec = O.Decoder(W, c)
+    dec.setup_memory(O.tile_batch(fm, k))
+    state = dec.zero_state(dec.init_state(O.tile_batch(im, k)))
+    rng = np.random.default_rng(3)
+    toks = rng.integers(0, dec.V, size=(B * k,)).astype(np.int32)
+    cell_out, ns, al = dec.call(dec.embed(toks), state)
+    keys, values = eng.project_fm(eng.to_dev(fm))
+    r = eng.decode_step(keys, values, B, k, eng.to_dev(toks), eng.to_dev(state['c']), eng.to_dev(state['h']),
+                        eng.to_dev(state['attention']))
+    assert rel_err(r['alignments'].cpu().numpy(), al) < 1e-3
+    assert rel_err(r['attention'].cpu().numpy(), ns['attention']) < 1e-3
+
+
+def test_golden_decoder_beam_fixture_gpu(torch_mod):
+    """The committed fixture tests/golden/decoder_beam_comic256.npz (oracle output, frozen)."""
+    import os
+    import make_golden as G
+    g = np.load(os.path.join(os.path.dirname(G.__file__), 'decoder_beam_comic256.npz'))
+    c = comic_config()
+    W = G.golden_weights(c, False)
+    im, fm = G.decoder_inputs(4, 77)
+    for fused in (False, True):
+        eng = _engine(c, W, with_cnn=False, fused=fused)
+        keys, values = eng.project_fm(eng.to_dev(fm))
+        c0, h0 = eng.rnn_init(eng.to_dev(im))
+        r = eng.decode_beam(keys, values, c0, h0, 3, 0.0, 10)
+        np.testing.assert_array_equal(r['predicted_ids'].cpu().numpy(), g['predicted_ids'])
+        np.testing.assert_array_equal(r['parent_ids'].cpu().numpy(), g['parent_ids'])
+        np.testing.assert_array_equal(r['lengths'].cpu().numpy(), g['lengths'])
+        assert rel_err(r['scores'].cpu().numpy(), g['scores']) < 1e-4
+        assert rel_err(r['attn'].cpu().numpy(), g['attn_top']) < 1e-3
+
+
+def test_golden_encoder_fixture_gpu(torch_mod):
+    import os
+    import make_golden as G
+    g = np.load(os.path.join(os.path.dirname(G.__file__), 'encoder_2img.npz'))
+    c = comic_config()
+    W = G.golden_weights(c, True)
+    rng = np.random.default_rng(5)
+    img = rng.uniform(-1, 1, (2, 224, 224, 3)).astype(np.float32)
+    for precision in ('f32', 'tf32x3'):
+        eng = _engine(c, W, precision=precision)
+        emb, fm = eng.encode(eng.to_dev(img))
+        fm = fm.cpu().numpy()
+        assert rel_err(emb.cpu().numpy(), g['im_embed']) < TOL
+        assert rel_err(fm[:, ::7, ::13], g['fm_sample']) < TOL
+        # checksum of the whole map: the tensor-core path accumulates with truncation (round toward
+        # zero) inside the MMA, a systematic ~4e-5 shrink after 20 layers; FFMA rounds to nearest
+        bias = abs(float(fm.astype(np.float64).sum()) - float(g['fm_sum'])) / float(g['fm_sum'])
+        assert bias < (1e-5 if precision == 'f32' else 2e-4), (precision, bias)
 
 
 def test_caption_model_end_to_end(torch_mod):
