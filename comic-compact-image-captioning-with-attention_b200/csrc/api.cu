@@ -23,7 +23,7 @@ void set_error(const char* fmt, ...) {
 using namespace comic;
 
 extern "C" const char* comic_last_error(void) { return g_err; }
-extern "C" const char* comic_version(void) { return "comic_b200 0.1 (sm_100a, f32-exact path)"; }
+extern "C" const char* comic_version(void) { return "comic_b200 0.2 (sm_100a; fp32 FFMA + tcgen05 bf16x3)"; }
 
 extern "C" int comic_create(const comic_cfg_t* cfg, comic_handle_t* out) {
   COMIC_REQUIRE(cfg && out, COMIC_E_BADARG, "create: null argument");
@@ -117,8 +117,8 @@ int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, i
   out.Npad = round_up(N, 16);
   out.Kpad = round_up(Kd, tc::BK);
   size_t n = (size_t)out.Npad * out.Kpad;
-  out.hi = cv.take<float>(n);
-  out.lo = cv.take<float>(n);
+  out.hi = cv.take<uint16_t>(n);
+  out.lo = cv.take<uint16_t>(n);
   out.ready = false;
   if (dry) return COMIC_OK;
   tc::pack_bt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, K, N, ldw, out.hi, out.lo, out.Kpad, out.Npad,

@@ -10,7 +10,9 @@
 //            queries of the image: LN over R channels (two-pass variance on the
 //            centred row), tanh, * v, per-head sums, / T.  The key row is read
 //            from HBM once per step and shared by the k beams (the reference
-//            tiles the keys k times).
+//            tiles the keys k times).  A lane owns R/32 CONTIGUOUS channels, so a
+//            head lives in D/(R/32) adjacent lanes (2 shuffles for 8 heads) and
+//            the LN / head reductions of up to 4 beams are interleaved for ILP.
 //   phase 2  softmax / signorm over the M positions of every (beam, head) in
 //            shared memory (+ attention-map dropout), alignment-history write.
 //   phase 3  context: ctx[beam, c] = sum_m alpha[beam, head(c), m] * values[m, c],
@@ -75,62 +77,122 @@ struct AttnArgs {
   int t, n_rows;
 };
 
-constexpr int kAttnThreads = 256;
+constexpr int kAttnThreads = 512;
+constexpr int kAttnBeamChunk = 4;
 
-// dynamic shared memory: q_c [k][R] | alpha [k][H][M] | (phase 3 partials alias q_c.. when split)
-template <int R, int H, int MODE, bool FAST>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+// Shared-memory carve-up shared by host and device.
+struct AttnSmem {
+  int tpc, nsplit, qfloats;
+  size_t bytes;
+};
+__host__ __device__ inline AttnSmem attn_smem_layout(int k, int R, int H, int M, int VAL) {
+  AttnSmem L;
+  L.tpc = (VAL / 4 + 31) / 32 * 32;                  // phase 3: threads per position group
+  L.nsplit = kAttnThreads / L.tpc;
+  if (L.nsplit < 1) L.nsplit = 1;
+  int red = (L.nsplit - 1) * kAttnBeamChunk * VAL;   // phase-3 partial sums alias the query block
+  L.qfloats = k * R > red ? k * R : red;
+  L.bytes = ((size_t)L.qfloats + (size_t)k * H * M) * sizeof(float);
+  return L;
+}
+
+// scores of one position against KB beams (add_LN).  kc = centred key slice of this lane.
+template <int CPL, int KB, bool FAST>
+__device__ __forceinline__ void ln_tanh_scores(const float (&kc)[CPL], const float* __restrict__ qs, int R,
+                                               int lane, const float (&gm)[CPL], const float (&bt)[CPL],
+                                               const float (&vv)[CPL], float sv, float inv_R,
+                                               float (&out)[KB]) {
+  constexpr int G4 = CPL / 4;
+  float ss[KB];
+#pragma unroll
+  for (int j = 0; j < KB; ++j) {
+    float acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < G4; ++g) {
+      float4 q = *reinterpret_cast<const float4*>(qs + (size_t)j * R + (g * 32 + lane) * 4);
+      float d0 = kc[g * 4 + 0] + q.x, d1 = kc[g * 4 + 1] + q.y, d2 = kc[g * 4 + 2] + q.z, d3 = kc[g * 4 + 3] + q.w;
+      acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+    }
+    ss[j] = acc;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < KB; ++j) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], o);
+  }
+#pragma unroll
+  for (int j = 0; j < KB; ++j) {
+    const float rstd = rsqrtf(ss[j] * inv_R + 1e-12f);
+    float acc = FAST ? 0.f : sv;
+#pragma unroll
+    for (int g = 0; g < G4; ++g) {
+      float4 q = *reinterpret_cast<const float4*>(qs + (size_t)j * R + (g * 32 + lane) * 4);
+      const float qa[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = g * 4 + e;
+        float y = fmaf((kc[c] + qa[e]) * rstd, gm[c], bt[c]);
+        if (FAST) acc = fmaf(tanh_approx(y), vv[c], acc);
+        else acc = fmaf(rcp_approx(ex2_approx(y) + 1.0f), vv[c], acc);   // vv = -2 v, y pre-scaled by 2 log2 e
+      }
+    }
+    out[j] = acc;
+  }
+}
+
+// dynamic shared memory: q_c [k][R] (lane-permuted) | alpha [k][H][M]; phase-3 partials alias q_c
+template <int R, int H, int MODE, bool FAST, int KB>
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fused_kernel(const AttnArgs a) {
   if (a.fin_count != nullptr && a.t > 0 && a.fin_count[a.t - 1] >= a.n_rows) return;
-  constexpr int G = R / 128;   // float4 groups per lane
-  constexpr int D = R / H;     // head width
+  constexpr int CPL = R / 32;      // contiguous channels per lane
+  constexpr int G4 = CPL / 4;      // float4 per lane
+  constexpr int D = R / H;         // head width
+  constexpr int LPH = (D >= CPL) ? D / CPL : 1;   // lanes per head
+  static_assert(D % CPL == 0 || CPL % D == 0, "head width vs lane slice");
+  static_assert(D >= CPL, "more than 32 heads per warp row is not built");
   constexpr float kTwoLog2e = 2.885390081777927f;
   extern __shared__ __align__(16) float sm[];
-  const int k = a.k, M = a.M;
-  // phase-3 geometry (also fixes the shared-memory carve-up)
-  const int VAL = a.VAL;
-  const int tpc = (VAL / 4 + 31) / 32 * 32;          // threads per position group
-  const int nsplit = (kAttnThreads / tpc) > 0 ? (kAttnThreads / tpc) : 1;
-  const int qfloats = max(k * R, (nsplit - 1) * 4 * VAL);
-  float* sm_q = sm;                                 // [k][R] centred queries (phase 3: partial sums)
-  float* sm_s = sm + qfloats;                       // [k][H][M] scores -> alpha
+  const int k = a.k, M = a.M, VAL = a.VAL;
+  const AttnSmem L = attn_smem_layout(k, R, H, M, VAL);
+  float* sm_q = sm;                                 // [k][G4][32] float4: lane-permuted centred queries
+  float* sm_s = sm + L.qfloats;                     // [k][H][M] scores -> alpha
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kAttnThreads / 32;
+  const int c0 = lane * CPL;                        // first channel of this lane
 
-  // ---- queries: load, centre (add_LN) ----
+  // ---- queries: load, centre (add_LN), store lane-permuted ----
   for (int beam = warp; beam < k; beam += NW) {
-    const float* q = a.lq + (size_t)(b * k + beam) * a.ld_lq + a.q_off;
-    float4 v[G];
+    const float* q = a.lq + (size_t)(b * k + beam) * a.ld_lq + a.q_off + c0;
+    float4 v[G4];
     float s = 0.f;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      v[g] = ldg4(q + g * 128 + lane * 4);
+    for (int g = 0; g < G4; ++g) {
+      v[g] = ldg4(q + g * 4);
       s += (v[g].x + v[g].y) + (v[g].z + v[g].w);
     }
     float mean = (MODE == 0) ? wsum(s) * (1.0f / R) : 0.f;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
+    for (int g = 0; g < G4; ++g) {
       float4 c = make_float4(v[g].x - mean, v[g].y - mean, v[g].z - mean, v[g].w - mean);
-      *reinterpret_cast<float4*>(sm_q + (size_t)beam * R + g * 128 + lane * 4) = c;
+      *reinterpret_cast<float4*>(sm_q + (size_t)beam * R + (g * 32 + lane) * 4) = c;
     }
   }
-  // per-lane constants
-  float4 g4[G], b4[G], v4[G];
-  float sv[G];
+  // per-lane constants (add_LN): gamma', beta' pre-scaled by 2 log2(e); vv = -2 v; sv = sum v
+  float gm[CPL], bt[CPL], vv[CPL];
+  float sv = 0.f;
+  if (MODE == 0) {
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
-    sv[g] = 0.f;
-    if (MODE == 0) {
-      int c = g * 128 + lane * 4;
-      g4[g] = ldg4(a.gamma + c);
-      b4[g] = ldg4(a.beta + c);
-      v4[g] = ldg4(a.vvec + c);
-      if (!FAST) {
-        g4[g].x *= kTwoLog2e; g4[g].y *= kTwoLog2e; g4[g].z *= kTwoLog2e; g4[g].w *= kTwoLog2e;
-        b4[g].x *= kTwoLog2e; b4[g].y *= kTwoLog2e; b4[g].z *= kTwoLog2e; b4[g].w *= kTwoLog2e;
-        sv[g] = (v4[g].x + v4[g].y) + (v4[g].z + v4[g].w);
-        v4[g].x *= -2.0f; v4[g].y *= -2.0f; v4[g].z *= -2.0f; v4[g].w *= -2.0f;
+    for (int g = 0; g < G4; ++g) {
+      float4 g4 = ldg4(a.gamma + c0 + g * 4), b4 = ldg4(a.beta + c0 + g * 4), v4 = ldg4(a.vvec + c0 + g * 4);
+      const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, ba[4] = {b4.x, b4.y, b4.z, b4.w}, va[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        gm[g * 4 + e] = FAST ? ga[e] : ga[e] * kTwoLog2e;
+        bt[g * 4 + e] = FAST ? ba[e] : ba[e] * kTwoLog2e;
+        vv[g * 4 + e] = FAST ? va[e] : -2.0f * va[e];
+        sv += va[e];
       }
     }
   }
@@ -138,84 +200,54 @@ attn_fused_kernel(const AttnArgs a) {
   __syncthreads();
 
   // ---- phase 1: scores ----
-  const float* kbase = a.keys + (size_t)b * M * R;
+  const float* kbase = a.keys + (size_t)b * M * R + c0;
   for (int m = warp; m < M; m += NW) {
-    float4 key[G];
-    const float* kr = kbase + (size_t)m * R;
-    float s = 0.f;
+    float kc[CPL];
+    {
+      const float* kr = kbase + (size_t)m * R;
+      float s = 0.f;
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      key[g] = ldg4(kr + g * 128 + lane * 4);
-      s += (key[g].x + key[g].y) + (key[g].z + key[g].w);
-    }
-    if (MODE == 0) {
-      float mean = wsum(s) * (1.0f / R);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        key[g].x -= mean; key[g].y -= mean; key[g].z -= mean; key[g].w -= mean;
+      for (int g = 0; g < G4; ++g) {
+        float4 t = ldg4(kr + g * 4);
+        kc[g * 4 + 0] = t.x; kc[g * 4 + 1] = t.y; kc[g * 4 + 2] = t.z; kc[g * 4 + 3] = t.w;
+        s += (t.x + t.y) + (t.z + t.w);
       }
-    }
-    for (int beam = 0; beam < k; ++beam) {
-      const float* q = sm_q + (size_t)beam * R;
-      float part[G];
       if (MODE == 0) {
-        float4 d[G];
-        float ss = 0.f;
+        float mean = wsum(s) * (1.0f / R);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          float4 qq = *reinterpret_cast<const float4*>(q + g * 128 + lane * 4);
-          d[g].x = key[g].x + qq.x; d[g].y = key[g].y + qq.y;
-          d[g].z = key[g].z + qq.z; d[g].w = key[g].w + qq.w;
-          ss = fmaf(d[g].x, d[g].x, ss); ss = fmaf(d[g].y, d[g].y, ss);
-          ss = fmaf(d[g].z, d[g].z, ss); ss = fmaf(d[g].w, d[g].w, ss);
-        }
-        float var = wsum(ss) * (1.0f / R);
-        float rstd = rsqrtf(var + 1e-12f);
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          float yx = fmaf(d[g].x * rstd, g4[g].x, b4[g].x);
-          float yy = fmaf(d[g].y * rstd, g4[g].y, b4[g].y);
-          float yz = fmaf(d[g].z * rstd, g4[g].z, b4[g].z);
-          float yw = fmaf(d[g].w * rstd, g4[g].w, b4[g].w);
-          if (FAST) {
-            part[g] = (tanh_approx(yx) * v4[g].x + tanh_approx(yy) * v4[g].y) +
-                      (tanh_approx(yz) * v4[g].z + tanh_approx(yw) * v4[g].w);
-          } else {
-            // tanh = 1 - 2r, r = 1/(2^y' + 1);  sum v*tanh = sum v + sum (-2v)*r   (v4 holds -2v, sv the sum)
-            float rx = rcp_approx(ex2_approx(yx) + 1.0f);
-            float ry = rcp_approx(ex2_approx(yy) + 1.0f);
-            float rz = rcp_approx(ex2_approx(yz) + 1.0f);
-            float rw = rcp_approx(ex2_approx(yw) + 1.0f);
-            part[g] = sv[g] + ((rx * v4[g].x + ry * v4[g].y) + (rz * v4[g].z + rw * v4[g].w));
-          }
-        }
+        for (int c = 0; c < CPL; ++c) kc[c] -= mean;
+      }
+    }
+    // KB beams at a time; a short last chunk re-scores the final beams (results identical, stores idempotent)
+    for (int beam0 = 0; beam0 < k; beam0 += KB) {
+      const int bs = min(beam0, k - KB);               // chunk start, clamped so that bs + KB <= k
+      float part[KB];
+      const float* qs = sm_q + (size_t)bs * R;
+      if (MODE == 0) {
+        ln_tanh_scores<CPL, KB, FAST>(kc, qs, R, lane, gm, bt, vv, sv, 1.0f / R, part);
       } else {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          float4 qq = *reinterpret_cast<const float4*>(q + g * 128 + lane * 4);
-          part[g] = (key[g].x * qq.x + key[g].y * qq.y) + (key[g].z * qq.z + key[g].w * qq.w);
+        for (int j = 0; j < KB; ++j) {
+          float acc = 0.f;
+#pragma unroll
+          for (int g = 0; g < G4; ++g) {
+            float4 q = *reinterpret_cast<const float4*>(qs + (size_t)j * R + (g * 32 + lane) * 4);
+            acc = fmaf(kc[g * 4 + 0], q.x, acc); acc = fmaf(kc[g * 4 + 1], q.y, acc);
+            acc = fmaf(kc[g * 4 + 2], q.z, acc); acc = fmaf(kc[g * 4 + 3], q.w, acc);
+          }
+          part[j] = acc;
         }
       }
-      float* srow = sm_s + (size_t)beam * H * M + m;
-      if (D >= 128) {
-        float hs[H];
+      // head sums: a head occupies LPH adjacent lanes
 #pragma unroll
-        for (int hh = 0; hh < H; ++hh) hs[hh] = 0.f;
+      for (int o = LPH / 2; o; o >>= 1) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) hs[(g * 128) / D] += wsum(part[g]);
-        if (lane == 0) {
+        for (int j = 0; j < KB; ++j) part[j] += __shfl_xor_sync(0xffffffffu, part[j], o);
+      }
+      if ((lane % LPH) == 0) {
+        const int hh = lane / LPH;
 #pragma unroll
-          for (int hh = 0; hh < H; ++hh) srow[(size_t)hh * M] = hs[hh] * out_scale;
-        }
-      } else {
-        constexpr int LPH = D / 4;   // lanes per head inside a 128-channel group
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          float v = part[g];
-#pragma unroll
-          for (int o = LPH / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if ((lane % LPH) == 0) srow[(size_t)((g * 128 + lane * 4) / D) * M] = v * out_scale;
-        }
+        for (int j = 0; j < KB; ++j) sm_s[((size_t)(bs + j) * H + hh) * M + m] = part[j] * out_scale;
       }
     }
   }
@@ -255,8 +287,9 @@ attn_fused_kernel(const AttnArgs a) {
   __syncthreads();
 
   // ---- phase 3: context ----
-  // thread -> 4 value channels; the CTA's 256 threads are split into `nsplit` position
-  // groups when VAL/4 <= 128; partial sums are combined through shared memory (sm_q).
+  // thread -> 4 value channels; the CTA's threads are split into `nsplit` position groups;
+  // partial sums are combined through shared memory (aliases the query block).
+  const int tpc = L.tpc, nsplit = L.nsplit;
   const int grp = tid / tpc, ct = tid - grp * tpc;
   const int c = ct * 4;
   const bool active = grp < nsplit && c < VAL;
@@ -264,19 +297,19 @@ attn_fused_kernel(const AttnArgs a) {
   const int hd = active ? c / dv : 0;
   const float* vb = a.values + (size_t)b * M * VAL + c;
   const int m_lo = (int)(((long long)M * grp) / nsplit), m_hi = (int)(((long long)M * (grp + 1)) / nsplit);
-  float* red = sm_q;                                  // [nsplit-1][4][VAL] scratch (k*R >= needed, checked on host)
-  for (int beam0 = 0; beam0 < k; beam0 += 4) {
-    const int nb = min(4, k - beam0);
-    float4 acc[4];
+  float* red = sm_q;                                  // [nsplit-1][4][VAL]
+  for (int beam0 = 0; beam0 < k; beam0 += kAttnBeamChunk) {
+    const int nb = min(kAttnBeamChunk, k - beam0);
+    float4 acc[kAttnBeamChunk];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kAttnBeamChunk; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) {
       const float* a0 = sm_s + ((size_t)beam0 * H + hd) * M;
 #pragma unroll 4
       for (int m = m_lo; m < m_hi; ++m) {
         float4 v = ldg4(vb + (size_t)m * VAL);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kAttnBeamChunk; ++j) {
           if (j < nb) {
             float al = a0[(size_t)j * H * M + m];
             acc[j].x = fmaf(al, v.x, acc[j].x); acc[j].y = fmaf(al, v.y, acc[j].y);
@@ -286,18 +319,18 @@ attn_fused_kernel(const AttnArgs a) {
       }
     }
     if (nsplit > 1) {
-      __syncthreads();                                // sm_q no longer needed / previous chunk consumed
+      __syncthreads();                                // query block no longer needed / previous chunk consumed
       if (active && grp > 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(red + ((size_t)(grp - 1) * 4 + j) * VAL + c) = acc[j];
+        for (int j = 0; j < kAttnBeamChunk; ++j)
+          *reinterpret_cast<float4*>(red + ((size_t)(grp - 1) * kAttnBeamChunk + j) * VAL + c) = acc[j];
       }
       __syncthreads();
       if (active && grp == 0) {
         for (int g2 = 1; g2 < nsplit; ++g2) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4 p = *reinterpret_cast<const float4*>(red + ((size_t)(g2 - 1) * 4 + j) * VAL + c);
+          for (int j = 0; j < kAttnBeamChunk; ++j) {
+            float4 p = *reinterpret_cast<const float4*>(red + ((size_t)(g2 - 1) * kAttnBeamChunk + j) * VAL + c);
             acc[j].x += p.x; acc[j].y += p.y; acc[j].z += p.z; acc[j].w += p.w;
           }
         }
@@ -305,22 +338,13 @@ attn_fused_kernel(const AttnArgs a) {
     }
     if (active && grp == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < kAttnBeamChunk; ++j)
         if (j < nb)
           *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * k + beam0 + j) * a.ld_ctx + c) = acc[j];
     }
   }
 }
 
-// Shared memory the fused kernel needs; the phase-3 scratch aliases the query block.
-inline size_t attn_fused_smem(int k, int R, int H, int M, int VAL) {
-  int tpc = (VAL / 4 + 31) / 32 * 32;
-  int nsplit = kAttnThreads / tpc;
-  if (nsplit < 1) nsplit = 1;
-  size_t qfloats = (size_t)k * R;
-  size_t red = (size_t)(nsplit - 1) * 4 * VAL;
-  if (red > qfloats) qfloats = red;
-  return (qfloats + (size_t)k * H * M) * sizeof(float);
-}
+inline size_t attn_fused_smem(int k, int R, int H, int M, int VAL) { return attn_smem_layout(k, R, H, M, VAL).bytes; }
 
 }  // namespace comic

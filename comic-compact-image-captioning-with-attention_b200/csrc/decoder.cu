@@ -726,17 +726,26 @@ static int dispatch_scores(comic_handle_t h, const StepIO& io, const StepBufs& s
 }
 
 // Fused scores + softmax + context (attention.cuh), one CTA per image.
-template <int R, int H, int MODE, bool FAST>
-static cudaError_t launch_fused_one(const AttnArgs& aa, int B, size_t smem, cudaStream_t st) {
+template <int R, int H, int MODE, bool FAST, int KB>
+static cudaError_t launch_fused_kb(const AttnArgs& aa, int B, size_t smem, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<R, H, MODE, FAST>,
+    cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<R, H, MODE, FAST, KB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  attn_fused_kernel<R, H, MODE, FAST><<<B, kAttnThreads, smem, st>>>(aa);
+  attn_fused_kernel<R, H, MODE, FAST, KB><<<B, kAttnThreads, smem, st>>>(aa);
   return cudaGetLastError();
+}
+
+// KB = beams scored together per key row (register-resident ILP); k is covered by ceil(k / KB) chunks.
+template <int R, int H, int MODE, bool FAST>
+static cudaError_t launch_fused_one(const AttnArgs& aa, int B, size_t smem, cudaStream_t st) {
+  const int k = aa.k;
+  if (k == 1) return launch_fused_kb<R, H, MODE, FAST, 1>(aa, B, smem, st);
+  if (k == 2 || k == 4) return launch_fused_kb<R, H, MODE, FAST, 2>(aa, B, smem, st);
+  return launch_fused_kb<R, H, MODE, FAST, 3>(aa, B, smem, st);
 }
 
 template <int R, int H>
@@ -774,7 +783,6 @@ static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb
   } else if (h->R == 256) {
     switch (h->H) {
       case 1: e = launch_fused<256, 1>(h, aa, B, smem, st); break;
-      case 4: e = launch_fused<256, 4>(h, aa, B, smem, st); break;
       case 8: e = launch_fused<256, 8>(h, aa, B, smem, st); break;
       default: ok = false;
     }
@@ -782,7 +790,6 @@ static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb
     switch (h->H) {
       case 1: e = launch_fused<1024, 1>(h, aa, B, smem, st); break;
       case 8: e = launch_fused<1024, 8>(h, aa, B, smem, st); break;
-      case 16: e = launch_fused<1024, 16>(h, aa, B, smem, st); break;
       default: ok = false;
     }
   } else ok = false;

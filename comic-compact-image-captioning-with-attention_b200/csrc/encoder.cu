@@ -114,9 +114,9 @@ int encoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
     if (rc) return rc;
   }
   for (int b = 0; b < kNumBlocks; ++b) {
-    h->pk.tc_grp[b].hi = cv.take<float>((size_t)round_up(blk[b].b0 + blk[b].b1a + blk[b].b2a, 16) *
+    h->pk.tc_grp[b].hi = cv.take<uint16_t>((size_t)round_up(blk[b].b0 + blk[b].b1a + blk[b].b2a, 16) *
                                         round_up(blk[b].cin, tc::BK));
-    h->pk.tc_grp[b].lo = cv.take<float>((size_t)round_up(blk[b].b0 + blk[b].b1a + blk[b].b2a, 16) *
+    h->pk.tc_grp[b].lo = cv.take<uint16_t>((size_t)round_up(blk[b].b0 + blk[b].b1a + blk[b].b2a, 16) *
                                         round_up(blk[b].cin, tc::BK));
   }
   if (dry) return COMIC_OK;

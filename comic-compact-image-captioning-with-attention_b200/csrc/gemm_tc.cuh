@@ -1,27 +1,32 @@
-// gemm_tc.cuh -- tcgen05 (5th-gen tensor core) GEMM / implicit-GEMM convolution
-// for sm_100a with fp32-equivalent accuracy ("3xTF32" error-compensated split).
+// gemm_tc.cuh -- persistent tcgen05 (5th-gen tensor core) GEMM / implicit-GEMM
+// convolution for sm_100a with fp32-equivalent accuracy: "bf16x3" operand split.
 //
 //   C[M,N] = A[M,K] . B[K,N]      A, B, C fp32 in HBM
-//   A = A_hi + A_lo, B = B_hi + B_lo  (hi = tf32(x), lo = tf32(x - hi))
-//   C ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo   (dropped term ~2^-22 |a||b|)
-// accumulated in fp32 in tensor memory.  This keeps the reference's fp32
-// numerics (logits / attention maps within 1e-3) while moving the
-// contraction from the FFMA pipe to `tcgen05.mma.kind::tf32`.
+//   A = A_hi + A_lo, B = B_hi + B_lo   (hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits)
+//   C ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo   (dropped terms ~2^-16 |a||b|)
+// accumulated in fp32 in tensor memory with `tcgen05.mma.kind::f16`.  This keeps
+// the reference's fp32 numerics (logits / attention maps within 1e-3, SURVEY.md
+// §8; measured ~1e-5) at 3 bf16 MMAs per product instead of FFMA.
 //
-// CTA = one 128 x BN output tile, 192 threads, warp-specialised:
-//   warps 0-3  A loaders: gather fp32 rows from global (plain segments with row
-//              indirection, or NHWC im2col with TF SAME padding), split into
-//              hi/lo in registers and store both tiles to shared memory in the
-//              canonical K-major SWIZZLE_128B layout; afterwards the epilogue
-//              (tcgen05.ld -> scale/shift/ReLU -> routed fp32 stores).
-//   warp 4     TMEM allocator + MMA issuer (one elected lane): 12 UMMAs
-//              (128 x BN x 8) per 32-wide K block, tcgen05.commit frees the stage.
-//   warp 5     TMA producer for the pre-split, pre-transposed weight panels
-//              B_hi / B_lo ([Npad, Kpad] K-major, packed at bind time).
-// mbarrier ring of STAGES shared-memory stages; accumulator 128 lanes x BN
-// fp32 columns of TMEM.
+// Persistent CTAs (one per SM) walk a static tile schedule; 448 threads,
+// warp-specialised:
+//   warps 0-3    epilogue: tcgen05.ld of accumulator buffer (tile & 1) -> folded-BN
+//                scale/shift, bias, ReLU -> routed fp32 stores; overlaps the next
+//                tile's main loop (TMEM holds two 128 x BN fp32 accumulators).
+//   warp 4       TMEM allocator + MMA issuer (one elected lane): 12 UMMAs
+//                (128 x n x 16) per 64-wide K block, tcgen05.commit frees the stage.
+//   warp 5       TMA producer for the pre-split, pre-transposed weight panels
+//                B_hi / B_lo ([Npad, Kpad] bf16 K-major, packed at bind time).
+//   warps 6-13   two A-loader groups that alternate K blocks: gather fp32 rows from
+//                global (plain segments with row indirection = the beam-search
+//                state gather, or NHWC im2col with TF SAME padding), split into
+//                hi/lo bf16 in registers and store both tiles to shared memory in
+//                the canonical K-major SWIZZLE_128B layout.
+// mbarrier ring of STAGES shared-memory stages (full_a / full_b / empty) plus
+// tmem_full / tmem_empty for the two accumulator buffers.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,8 +36,12 @@ namespace comic {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                 // fp32 elements = one 128-byte swizzle row
-constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KB
+constexpr int BK = 64;                      // bf16 elements = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int kEpiWarps = 4;
+constexpr int kLoaderGroups = 2;
+constexpr int kFirstLoaderWarp = 6;
+constexpr int kThreads = (kFirstLoaderWarp + 4 * kLoaderGroups) * 32;   // 448
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -72,6 +81,9 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0,
                                             int c1) {
   asm volatile(
@@ -79,12 +91,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -92,10 +104,21 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
+
+// (x, y) -> packed bf16x2 {lo half = bf16(x), hi half = bf16(y)}, round to nearest even.
+__device__ __forceinline__ uint32_t pack_bf16x2(float x, float y) {
   uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
   return r;
+}
+// Split four fp32 values into bf16 hi / lo pairs (8 bytes each).
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+  hi.x = pack_bf16x2(v.x, v.y);
+  hi.y = pack_bf16x2(v.z, v.w);
+  float hx = __uint_as_float(hi.x << 16), hy = __uint_as_float(hi.x & 0xffff0000u);
+  float hz = __uint_as_float(hi.y << 16), hw = __uint_as_float(hi.y & 0xffff0000u);
+  lo.x = pack_bf16x2(v.x - hx, v.y - hy);
+  lo.y = pack_bf16x2(v.z - hz, v.w - hw);
 }
 
 // K-major SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
@@ -110,47 +133,50 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
-// K-major A and B, N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (1) @4, a/b format BF16 (1)
+// @7/@10, K-major A and B, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct RowEntry {   // 16 bytes, one per tile row
-  long long off;    // AConv: element offset of the image base; APlain: unused
-  int hi0, wi0;     // AConv: top-left input coordinate of the receptive field
+struct RowEntry {   // 16 bytes, one per tile row (AConv)
+  long long off;    // element offset of the image base, -1 = row beyond M
+  int hi0, wi0;     // top-left input coordinate of the receptive field
 };
 
 template <int BN, int STAGES>
 struct SmemLayout {
-  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int ROWTAB_BYTES = BM * 3 * 8;          // 3 segment row pointers or RowEntry
-  static constexpr int BAR_BYTES = (3 * STAGES + 1) * 8 + 8;
-  static constexpr int TOTAL = TILES_BYTES + ROWTAB_BYTES + BAR_BYTES + 1024;   // + alignment slack
+  static constexpr int ROWTAB_BYTES = BM * 3 * 8;                 // 3 segment row pointers or RowEntry
+  static constexpr int BAR_BYTES = (3 * STAGES + 4) * 8 + 8;
+  static constexpr int TOTAL = TILES_BYTES + kLoaderGroups * ROWTAB_BYTES + BAR_BYTES + 1024;   // + alignment slack
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
 };
 
 template <int BN, int STAGES, int AMODE>
-__global__ void __launch_bounds__(192, 1)
-gemm_tf32x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
                    const __grid_constant__ CUtensorMap tm_lo, int M, int N, int K, Epi epi) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   if (epi.stop != nullptr && *epi.stop >= epi.stop_n) return;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* rowtab = smem + L::TILES_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rowtab + L::ROWTAB_BYTES);
+  uint8_t* rowtab0 = smem + L::TILES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowtab0 + kLoaderGroups * L::ROWTAB_BYTES);
   uint64_t* full_a = bars;
   uint64_t* full_b = bars + STAGES;
   uint64_t* empty = bars + 2 * STAGES;
-  uint64_t* accum_bar = bars + 3 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  uint64_t* tmem_full = bars + 3 * STAGES;        // [2]
+  uint64_t* tmem_empty = bars + 3 * STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * BM;
-  const int n0 = blockIdx.x * BN;
   const int nk = (K + BK - 1) / BK;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int total_tiles = m_tiles * n_tiles;
 
   // ---- one-time setup ----
   if (tid == 0) {
@@ -159,42 +185,15 @@ gemm_tf32x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
       mbar_init(&full_b[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiWarps);
+    }
     fence_barrier_init();
   }
-  if (tid < BM) {
-    int m = m0 + tid;
-    if constexpr (AMODE == 0) {
-      const float** rp = reinterpret_cast<const float**>(rowtab);
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const float* p = nullptr;
-        if (s < a.nseg && m < M) {
-          int r = m;
-          if (a.seg[s].idx) r = a.seg[s].idx[m];
-          if (r >= 0 && r < a.seg[s].idx_limit) p = a.seg[s].ptr + (size_t)r * a.seg[s].ld;
-        }
-        rp[s * BM + tid] = p;
-      }
-    } else {
-      RowEntry* re = reinterpret_cast<RowEntry*>(rowtab);
-      RowEntry e;
-      e.off = -1; e.hi0 = 0; e.wi0 = 0;
-      if (m < M) {
-        int hw = a.Ho * a.Wo;
-        int b = m / hw, rem = m - b * hw;
-        int ho = rem / a.Wo, wo = rem - ho * a.Wo;
-        e.off = (long long)b * a.H * a.W * a.ldx;
-        e.hi0 = ho * a.stride - a.pad_t;
-        e.wi0 = wo * a.stride - a.pad_l;
-      }
-      re[tid] = e;
-    }
-  }
   if (warp == 4) {
-    // allocate BN fp32 accumulator columns of tensor memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 "r"((uint32_t)L::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -203,168 +202,221 @@ gemm_tf32x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // =====================  A loaders  =====================
-    const int chunk = lane & 7;          // 16-byte chunk within the 128-byte K row
-    const int rsub = lane >> 3;          // 4 rows per warp instruction
-    float4 cur[8], nxt[8];
-    auto gload = [&](int kt, float4* dst) {
-      const int kk = kt * BK + chunk * 4;
-      if constexpr (AMODE == 0) {
-        const float* const* rp = reinterpret_cast<const float* const*>(rowtab);
-        int seg = -1, col = kk;
-        if (kk < K) {
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            if (seg < 0 && s < a.nseg) {
-              if (col < a.seg[s].ncols) seg = s;
-              else col -= a.seg[s].ncols;
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int row = warp * 32 + i * 4 + rsub;
-          const float* p = (seg >= 0) ? rp[seg * BM + row] : nullptr;
-          dst[i] = p ? ldg4(p + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      } else {
-        const RowEntry* re = reinterpret_cast<const RowEntry*>(rowtab);
-        int kh = 0, kw = 0, ci = 0;
-        bool kvalid = kk < K;
-        if (kvalid) {
-          int tap = kk / a.Cin;
-          ci = kk - tap * a.Cin;
-          kh = tap / a.KW;
-          kw = tap - kh * a.KW;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int row = warp * 32 + i * 4 + rsub;
-          RowEntry e = re[row];
-          int hi = e.hi0 + kh, wi = e.wi0 + kw;
-          bool ok = kvalid && e.off >= 0 && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
-          dst[i] = ok ? ldg4(a.x + e.off + ((long long)hi * a.W + wi) * a.ldx + ci)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    };
-    gload(0, cur);
-    for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % STAGES;
-      const uint32_t ph = (kt / STAGES) & 1;
-      if (kt + 1 < nk) gload(kt + 1, nxt);
-      mbar_wait(&empty[s], ph ^ 1);
-      uint8_t* a_hi = smem + s * L::STAGE_BYTES;
-      uint8_t* a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int row = warp * 32 + i * 4 + rsub;
-        uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
-        float4 v = cur[i];
-        uint4 h, l;
-        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-        l.x = tf32_rna(v.x - __uint_as_float(h.x));
-        l.y = tf32_rna(v.y - __uint_as_float(h.y));
-        l.z = tf32_rna(v.z - __uint_as_float(h.z));
-        l.w = tf32_rna(v.w - __uint_as_float(h.w));
-        *reinterpret_cast<uint4*>(a_hi + off) = h;
-        *reinterpret_cast<uint4*>(a_lo + off) = l;
-      }
-      fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(&full_a[s]);
-      if (kt + 1 < nk) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-      }
-    }
+  if (warp < kEpiWarps) {
     // =====================  epilogue  =====================
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const int row = warp * 32 + lane;
-    const int m = m0 + row;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int m0 = (tile / n_tiles) * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int acc = iter & 1;
+      const int n_umma = min(BN, ((N - n0) + 15) & ~15);
+      mbar_wait(&tmem_full[acc], (uint32_t)((iter >> 1) & 1));
+      tc_fence_after();
+      const int m = m0 + warp * 32 + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-          "%14, %15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < M) {
+      for (int c0 = 0; c0 < n_umma; c0 += 16) {
+        uint32_t r[16];
+        uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+            "%14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m < M) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          int n = n0 + c0 + g * 4;
-          if (n >= N) continue;
-          float4 v = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                                 __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
-          if (epi.scale) {
-            float4 sc = ldg4(epi.scale + n);
-            v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
-          }
-          if (epi.bias) {
-            float4 bs = ldg4(epi.bias + n);
-            v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w;
-          }
-          if (epi.relu) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-          }
+          for (int g = 0; g < 4; ++g) {
+            int n = n0 + c0 + g * 4;
+            if (n >= N) continue;
+            float4 v = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                   __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+            if (epi.scale) {
+              float4 sc = ldg4(epi.scale + n);
+              v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+            }
+            if (epi.bias) {
+              float4 bs = ldg4(epi.bias + n);
+              v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w;
+            }
+            if (epi.relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
 #pragma unroll
-          for (int rr = 0; rr < 3; ++rr) {
-            if (rr < epi.nroute && n >= epi.r[rr].n0 && n < epi.r[rr].n1) {
-              float* dst = epi.r[rr].dst + (size_t)m * epi.r[rr].ld + epi.r[rr].coff + (n - epi.r[rr].n0);
-              *reinterpret_cast<float4*>(dst) = v;
+            for (int rr = 0; rr < 3; ++rr) {
+              if (rr < epi.nroute && n >= epi.r[rr].n0 && n < epi.r[rr].n1) {
+                float* dst = epi.r[rr].dst + (size_t)m * epi.r[rr].ld + epi.r[rr].coff + (n - epi.r[rr].n0);
+                *reinterpret_cast<float4*>(dst) = v;
+              }
             }
           }
         }
       }
+      // accumulator buffer drained -> the MMA warp may overwrite it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
   } else if (warp == 4) {
     // =====================  MMA issuer  =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-      for (int kt = 0; kt < nk; ++kt) {
-        const int s = kt % STAGES;
-        const uint32_t ph = (kt / STAGES) & 1;
-        mbar_wait(&full_a[s], ph);
-        mbar_wait(&full_b[s], ph);
+      int iter = 0;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int n0 = (tile % n_tiles) * BN;
+        const int acc = iter & 1;
+        const int n_umma = min(BN, ((N - n0) + 15) & ~15);
+        const uint32_t idesc = make_idesc_bf16(BM, n_umma);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        mbar_wait(&tmem_empty[acc], (uint32_t)(((iter >> 1) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t a_lo = a_hi + A_TILE_BYTES;
-        const uint32_t b_hi = a_lo + A_TILE_BYTES;
-        const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
-        const uint64_t dah = make_desc_sw128(a_hi), dal = make_desc_sw128(a_lo);
-        const uint64_t dbh = make_desc_sw128(b_hi), dbl = make_desc_sw128(b_lo);
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_a[s], ph);
+          mbar_wait(&full_b[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_lo + A_TILE_BYTES;
+          const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
+          const uint64_t dah = make_desc_sw128(a_hi), dal = make_desc_sw128(a_lo);
+          const uint64_t dbh = make_desc_sw128(b_hi), dbl = make_desc_sw128(b_lo);
 #pragma unroll
-        for (int k8 = 0; k8 < BK / 8; ++k8) {
-          const uint64_t adv = (uint64_t)((k8 * 8 * 4) >> 4);     // 32 bytes per K=8 step inside the swizzle row
-          umma_tf32(tmem_base, dah + adv, dbh + adv, idesc, (kt > 0 || k8 > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, dal + adv, dbh + adv, idesc, 1u);
-          umma_tf32(tmem_base, dah + adv, dbl + adv, idesc, 1u);
+          for (int k16 = 0; k16 < BK / 16; ++k16) {
+            const uint64_t adv = (uint64_t)((k16 * 16 * 2) >> 4);    // 32 bytes per K=16 step inside the swizzle row
+            umma_bf16(d_tmem, dah + adv, dbh + adv, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, dal + adv, dbh + adv, idesc, 1u);
+            umma_bf16(d_tmem, dah + adv, dbl + adv, idesc, 1u);
+          }
+          umma_commit(&empty[s]);            // frees the stage when the MMAs above retire
         }
-        umma_commit(&empty[s]);            // frees the stage when the MMAs above retire
+        umma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
       }
-      umma_commit(accum_bar);              // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // =====================  TMA producer (weights)  =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          const uint32_t b_hi = smem_u32(smem + s * L::STAGE_BYTES + 2 * A_TILE_BYTES);
+          const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
+          mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES);
+          tma_load_2d(b_hi, &tm_hi, &full_b[s], kt * BK, n0);
+          tma_load_2d(b_lo, &tm_lo, &full_b[s], kt * BK, n0);
+        }
+      }
     }
     __syncwarp();
   } else {
-    // =====================  TMA producer (weights)  =====================
-    if (lane == 0) {
-      for (int kt = 0; kt < nk; ++kt) {
-        const int s = kt % STAGES;
-        const uint32_t ph = (kt / STAGES) & 1;
+    // =====================  A loaders  =====================
+    const int grp = (warp - kFirstLoaderWarp) >> 2;         // loader group 0 / 1
+    const int wg = (warp - kFirstLoaderWarp) & 3;           // warp inside the group
+    const int tg = wg * 32 + lane;                          // thread inside the group
+    const int chunk = lane & 15;                            // float4 chunk within the 64-float K row
+    const int rsub = lane >> 4;                             // 2 rows per warp instruction
+    uint8_t* rowtab = rowtab0 + grp * L::ROWTAB_BYTES;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * BM;
+      // per-tile row table (this group's private copy)
+      named_bar_sync(1 + grp, 128);
+      {
+        int m = m0 + tg;
+        if constexpr (AMODE == 0) {
+          const float** rp = reinterpret_cast<const float**>(rowtab);
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const float* p = nullptr;
+            if (s < a.nseg && m < M) {
+              int r = m;
+              if (a.seg[s].idx) r = a.seg[s].idx[m];
+              if (r >= 0 && r < a.seg[s].idx_limit) p = a.seg[s].ptr + (size_t)r * a.seg[s].ld;
+            }
+            rp[s * BM + tg] = p;
+          }
+        } else {
+          RowEntry* re = reinterpret_cast<RowEntry*>(rowtab);
+          RowEntry e;
+          e.off = -1; e.hi0 = 0; e.wi0 = 0;
+          if (m < M) {
+            int hw = a.Ho * a.Wo;
+            int b = m / hw, rem = m - b * hw;
+            int ho = rem / a.Wo, wo = rem - ho * a.Wo;
+            e.off = (long long)b * a.H * a.W * a.ldx;
+            e.hi0 = ho * a.stride - a.pad_t;
+            e.wi0 = wo * a.stride - a.pad_l;
+          }
+          re[tg] = e;
+        }
+      }
+      named_bar_sync(1 + grp, 128);
+      for (int kt = 0; kt < nk; ++kt, ++it) {
+        if ((int)(it & 1) != grp) continue;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        float4 v[16];
+        const int kk = kt * BK + chunk * 4;
+        if constexpr (AMODE == 0) {
+          const float* const* rp = reinterpret_cast<const float* const*>(rowtab);
+          int seg = -1, col = kk;
+          if (kk < K) {
+#pragma unroll
+            for (int sg = 0; sg < 3; ++sg) {
+              if (seg < 0 && sg < a.nseg) {
+                if (col < a.seg[sg].ncols) seg = sg;
+                else col -= a.seg[sg].ncols;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            int row = wg * 32 + i * 2 + rsub;
+            const float* p = (seg >= 0) ? rp[seg * BM + row] : nullptr;
+            v[i] = p ? ldg4(p + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+          const RowEntry* re = reinterpret_cast<const RowEntry*>(rowtab);
+          int kh = 0, kw = 0, ci = 0;
+          const bool kvalid = kk < K;
+          if (kvalid) {
+            int tap = kk / a.Cin;
+            ci = kk - tap * a.Cin;
+            kh = tap / a.KW;
+            kw = tap - kh * a.KW;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            int row = wg * 32 + i * 2 + rsub;
+            RowEntry e = re[row];
+            int hi = e.hi0 + kh, wi = e.wi0 + kw;
+            bool ok = kvalid && e.off >= 0 && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+            v[i] = ok ? ldg4(a.x + e.off + ((long long)hi * a.W + wi) * a.ldx + ci)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         mbar_wait(&empty[s], ph ^ 1);
-        const uint32_t b_hi = smem_u32(smem + s * L::STAGE_BYTES + 2 * A_TILE_BYTES);
-        const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
-        mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES);
-        tma_load_2d(b_hi, &tm_hi, &full_b[s], kt * BK, n0);
-        tma_load_2d(b_lo, &tm_lo, &full_b[s], kt * BK, n0);
+        uint8_t* a_hi = smem + s * L::STAGE_BYTES;
+        uint8_t* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          int row = wg * 32 + i * 2 + rsub;
+          uint32_t off = row * 128 + ((((uint32_t)chunk >> 1) ^ (row & 7)) << 4) + ((chunk & 1) << 3);
+          uint2 h, l;
+          split4(v[i], h, l);
+          *reinterpret_cast<uint2*>(a_hi + off) = h;
+          *reinterpret_cast<uint2*>(a_lo + off) = l;
+        }
+        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&full_a[s]);
       }
     }
-    __syncwarp();
   }
 
   // ---- teardown ----
@@ -372,7 +424,7 @@ gemm_tf32x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
   __syncthreads();
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 "r"((uint32_t)L::TMEM_COLS)
                  : "memory");
   }
 }
@@ -380,11 +432,11 @@ gemm_tf32x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
 // ---------------------------------------------------------------------------
 // Host side.
 // ---------------------------------------------------------------------------
-// A weight matrix packed for the tensor path: B^T split into hi / lo, [Npad, Kpad]
+// A weight matrix packed for the tensor path: B^T split into bf16 hi / lo, [Npad, Kpad]
 // row-major (K-major), zero padded; one tensor map per BN option.
 struct TcWeight {
-  float* hi = nullptr;
-  float* lo = nullptr;
+  uint16_t* hi = nullptr;
+  uint16_t* lo = nullptr;
   int N = 0, K = 0, Npad = 0, Kpad = 0;   // K = extent of the A operand's K index space
   CUtensorMap tm_hi[3], tm_lo[3];   // BN = 64, 128, 256
   bool ready = false;
@@ -412,13 +464,13 @@ inline bool make_weight_maps(TcWeight& w) {
   const int bns[3] = {64, 128, 256};
   for (int i = 0; i < 3; ++i) {
     cuuint64_t dims[2] = {(cuuint64_t)w.Kpad, (cuuint64_t)w.Npad};
-    cuuint64_t strides[1] = {(cuuint64_t)w.Kpad * sizeof(float)};
+    cuuint64_t strides[1] = {(cuuint64_t)w.Kpad * sizeof(uint16_t)};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bns[i]};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r1 = enc(&w.tm_hi[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.hi, dims, strides, box, estr,
+    CUresult r1 = enc(&w.tm_hi[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.hi, dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r2 = enc(&w.tm_lo[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.lo, dims, strides, box, estr,
+    CUresult r2 = enc(&w.tm_lo[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.lo, dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return false;
@@ -427,10 +479,10 @@ inline bool make_weight_maps(TcWeight& w) {
   return true;
 }
 
-// B^T hi/lo packing: src W[k][n] (row stride ldw); optional channel padding of an
+// B^T bf16 hi/lo packing: src W[k][n] (row stride ldw); optional channel padding of an
 // HWIO conv kernel (cin_src -> cin_dst, e.g. 3 -> 4 for the NHWC4 stem input).
-static __global__ void pack_bt_kernel(const float* __restrict__ W, int K, int N, int ldw, float* __restrict__ hi,
-                               float* __restrict__ lo, int Kpad, int Npad, int cin_src, int cin_dst) {
+static __global__ void pack_bt_kernel(const float* __restrict__ W, int K, int N, int ldw, uint16_t* __restrict__ hi,
+                                      uint16_t* __restrict__ lo, int Kpad, int Npad, int cin_src, int cin_dst) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)Npad * Kpad) return;
   int n = (int)(i / Kpad), kp = (int)(i % Kpad);
@@ -445,45 +497,45 @@ static __global__ void pack_bt_kernel(const float* __restrict__ W, int K, int N,
     }
     if (ok) v = W[(size_t)k * ldw + n];
   }
-  float h = __uint_as_float(tf32_rna(v));
-  hi[i] = h;
-  lo[i] = __uint_as_float(tf32_rna(v - h));
+  uint32_t h = pack_bf16x2(v, 0.f) & 0xffffu;
+  float hf = __uint_as_float(h << 16);
+  uint32_t l = pack_bf16x2(v - hf, 0.f) & 0xffffu;
+  hi[i] = (uint16_t)h;
+  lo[i] = (uint16_t)l;
 }
 
 template <int BN, int STAGES, int AMODE>
 inline cudaError_t launch_one(const typename AParam<AMODE>::type& a, const TcWeight& w, int bn_idx, int M, int N,
-                              const Epi& epi, cudaStream_t st) {
+                              const Epi& epi, int num_sms, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES, AMODE>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BN, STAGES, AMODE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
-  gemm_tf32x3_kernel<BN, STAGES, AMODE><<<grid, 192, L::TOTAL, st>>>(a, w.tm_hi[bn_idx], w.tm_lo[bn_idx], M, N,
-                                                                    w.K, epi);
+  int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_bf16x3_kernel<BN, STAGES, AMODE><<<grid, kThreads, L::TOTAL, st>>>(a, w.tm_hi[bn_idx], w.tm_lo[bn_idx], M,
+                                                                          N, w.K, epi);
   return cudaGetLastError();
 }
 
-// Pick the N tile: the widest that still yields >= ~1 wave of CTAs.
-inline int pick_bn(int M, int N, int num_sms) {
-  int mt = (M + BM - 1) / BM;
+// N tile = shared-memory / TMEM allocation; the UMMA N is the exact remainder per tile.
+inline int pick_bn(int N) {
   if (N <= 64) return 64;
   if (N <= 128) return 128;
-  int t256 = mt * ((N + 255) / 256);
-  if (t256 >= num_sms) return 256;
-  return 128;
+  return 256;
 }
 
 template <int AMODE>
 inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const TcWeight& w, int M, int N,
                                   const Epi& epi, int num_sms, cudaStream_t st) {
-  int bn = pick_bn(M, N, num_sms);
-  if (bn == 64) return launch_one<64, 4, AMODE>(a, w, 0, M, N, epi, st);
-  if (bn == 128) return launch_one<128, 3, AMODE>(a, w, 1, M, N, epi, st);
-  return launch_one<256, 2, AMODE>(a, w, 2, M, N, epi, st);
+  int bn = pick_bn(N);
+  if (bn == 64) return launch_one<64, 4, AMODE>(a, w, 0, M, N, epi, num_sms, st);
+  if (bn == 128) return launch_one<128, 3, AMODE>(a, w, 1, M, N, epi, num_sms, st);
+  return launch_one<256, 2, AMODE>(a, w, 2, M, N, epi, num_sms, st);
 }
 
 }  // namespace tc
