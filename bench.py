@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument('--ref-batch', type=int, default=8, help='images per step of the CPU reference arm')
     ap.add_argument('--cpu-sample', type=int, default=4, help='images of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='split', choices=['f32', 'split', 'fast'],
+                    help='engine arithmetic mode (include/comic_b200.h comic_set_precision)')
     ap.add_argument('--breakdown', action='store_true', help='also print a per-kernel-class time table to stderr')
     return ap.parse_args()
 
@@ -259,6 +261,7 @@ def run_ours(args):
     W = wts.init_weights(c, seed=c.rand_seed, cnn_init='he')
     eng = Engine(c)
     eng.bind_weights(W)
+    eng.set_precision(args.precision)
     model = CaptionModel(c, 'infer', batch_ops=None, engine=eng)
     B, beam = args.batch, args.beam
     T = model._maximum_iterations()

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcomic_b200.so')
-SOURCES = ['api.cu', 'encoder.cu', 'decoder.cu']
+SOURCES = ['api.cu', 'encoder.cu', 'decoder.cu', 'train.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC']
 

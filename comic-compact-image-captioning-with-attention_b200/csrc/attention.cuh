@@ -21,9 +21,11 @@
 //
 // tanh(y) is evaluated as 1 - 2 / (exp2(2*log2(e)*y) + 1) with ex2.approx /
 // rcp.approx (~1e-6 abs), the 2*log2(e) factor folded into gamma / beta, and
-//   sum_j v_j tanh_j = sum_j v_j - 2 sum_j v_j r_j
-// so the inner loop is FADD FFMA | FMUL FFMA EX2 FADD RCP FFMA per element.
-// FAST (precision mode 2) uses the single-MUFU tanh.approx.f32 instead.
+//   sum_j v_j tanh_j = sum_j v_j - 2 sum_j v_j r_j.
+// Measured (ncu, profiles/): the kernel is bound by the MUFU (XU) pipe, whose
+// EX2/RCP rate is far below the FMA pipe's, so four reciprocals share one
+// MUFU.RCP (1.25 MUFU per element).  FAST (precision mode 2) uses the
+// single-MUFU tanh.approx.f32 instead.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -47,6 +49,16 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -69,7 +81,8 @@ struct AttnArgs {
   const float* temperature;
   float* ctx_out;         // [N, ld_ctx]
   int ld_ctx;
-  float* hist_t;          // [N, H*M] or nullptr
+  float* hist_t;          // [N, H*M] or nullptr (post-dropout alignments = the reference's history)
+  float* hist_pre;        // [N, H*M] or nullptr (pre-dropout alignments, training tape)
   const float* att_mask;  // [N, H*M] 0/1 or nullptr
   float att_keep;
   int k, M, VAL, prob_fn;
@@ -77,12 +90,13 @@ struct AttnArgs {
   int t, n_rows;
 };
 
-constexpr int kAttnThreads = 512;
+constexpr int kAttnThreads = 768;
+constexpr int kAttnRing = 2;        // key-row slots per warp (prefetch distance 1)
 constexpr int kAttnBeamChunk = 4;
 
 // Shared-memory carve-up shared by host and device.
 struct AttnSmem {
-  int tpc, nsplit, qfloats;
+  int tpc, nsplit, qfloats, sfloats;
   size_t bytes;
 };
 __host__ __device__ inline AttnSmem attn_smem_layout(int k, int R, int H, int M, int VAL) {
@@ -92,55 +106,81 @@ __host__ __device__ inline AttnSmem attn_smem_layout(int k, int R, int H, int M,
   if (L.nsplit < 1) L.nsplit = 1;
   int red = (L.nsplit - 1) * kAttnBeamChunk * VAL;   // phase-3 partial sums alias the query block
   L.qfloats = k * R > red ? k * R : red;
-  L.bytes = ((size_t)L.qfloats + (size_t)k * H * M) * sizeof(float);
+  L.sfloats = (k * H * M + 3) & ~3;
+  // + LN constants [3][R] + per-warp key-row ring (cp.async staging, lane-private layout)
+  L.bytes = ((size_t)L.qfloats + (size_t)L.sfloats + 3 * (size_t)R + (size_t)(kAttnThreads / 32) * kAttnRing * R) *
+            sizeof(float);
   return L;
 }
 
-// scores of one position against KB beams (add_LN).  kc = centred key slice of this lane.
+// scores of one position against KB beams (add_LN).  kc = centred key slice of this lane;
+// qs = lane-permuted centred queries; cs = lane-permuted constants [gamma' | beta' | vv].
 template <int CPL, int KB, bool FAST>
-__device__ __forceinline__ void ln_tanh_scores(const float (&kc)[CPL], const float* __restrict__ qs, int R,
-                                               int lane, const float (&gm)[CPL], const float (&bt)[CPL],
-                                               const float (&vv)[CPL], float sv, float inv_R,
-                                               float (&out)[KB]) {
+__device__ __forceinline__ void ln_tanh_scores(const float (&kc)[CPL], const float* __restrict__ qs,
+                                               const float* __restrict__ cs, int R, int lane, float sv,
+                                               float inv_R, float (&out)[KB]) {
   constexpr int G4 = CPL / 4;
   float ss[KB];
 #pragma unroll
-  for (int j = 0; j < KB; ++j) {
-    float acc = 0.f;
+  for (int j = 0; j < KB; ++j) ss[j] = 0.f;
 #pragma unroll
-    for (int g = 0; g < G4; ++g) {
+  for (int g = 0; g < G4; ++g) {
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
       float4 q = *reinterpret_cast<const float4*>(qs + (size_t)j * R + (g * 32 + lane) * 4);
       float d0 = kc[g * 4 + 0] + q.x, d1 = kc[g * 4 + 1] + q.y, d2 = kc[g * 4 + 2] + q.z, d3 = kc[g * 4 + 3] + q.w;
-      acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+      ss[j] = fmaf(d0, d0, ss[j]); ss[j] = fmaf(d1, d1, ss[j]);
+      ss[j] = fmaf(d2, d2, ss[j]); ss[j] = fmaf(d3, d3, ss[j]);
     }
-    ss[j] = acc;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
 #pragma unroll
     for (int j = 0; j < KB; ++j) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], o);
   }
+  float rstd[KB];
 #pragma unroll
   for (int j = 0; j < KB; ++j) {
-    const float rstd = rsqrtf(ss[j] * inv_R + 1e-12f);
-    float acc = FAST ? 0.f : sv;
+    rstd[j] = rsqrtf(ss[j] * inv_R + 1e-12f);
+    out[j] = FAST ? 0.f : sv;
+  }
 #pragma unroll
-    for (int g = 0; g < G4; ++g) {
+  for (int g = 0; g < G4; ++g) {
+    const float4 gm = *reinterpret_cast<const float4*>(cs + (g * 32 + lane) * 4);
+    const float4 bt = *reinterpret_cast<const float4*>(cs + R + (g * 32 + lane) * 4);
+    const float4 vv = *reinterpret_cast<const float4*>(cs + 2 * R + (g * 32 + lane) * 4);
+    const float ga[4] = {gm.x, gm.y, gm.z, gm.w}, ba[4] = {bt.x, bt.y, bt.z, bt.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int j = 0; j < KB; ++j) {
       float4 q = *reinterpret_cast<const float4*>(qs + (size_t)j * R + (g * 32 + lane) * 4);
       const float qa[4] = {q.x, q.y, q.z, q.w};
+      float y[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = g * 4 + e;
-        float y = fmaf((kc[c] + qa[e]) * rstd, gm[c], bt[c]);
-        if (FAST) acc = fmaf(tanh_approx(y), vv[c], acc);
-        else acc = fmaf(rcp_approx(ex2_approx(y) + 1.0f), vv[c], acc);   // vv = -2 v, y pre-scaled by 2 log2 e
+      for (int e = 0; e < 4; ++e) y[e] = fmaf((kc[g * 4 + e] + qa[e]) * rstd[j], ga[e], ba[e]);
+      if (FAST) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) out[j] = fmaf(tanh_approx(y[e]), va[e], out[j]);
+      } else {
+        // tanh = 1 - 2/(2^y' + 1), y' pre-scaled by 2 log2 e and clamped at 30 (tanh == 1 in fp32 there);
+        // the four reciprocals share ONE MUFU.RCP: 1/x_i = (prod of the others) / (x0 x1 x2 x3), products
+        // <= 2^124.  The kernel is MUFU-bound, so 1.25 instead of 2 MUFU per element is a 1.6x win.
+        float x[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = ex2_approx(fminf(y[e], 30.0f)) + 1.0f;
+        const float p01 = x[0] * x[1], p23 = x[2] * x[3];
+        const float rp = rcp_approx(p01 * p23);
+        const float r01 = rp * p23, r23 = rp * p01;
+        out[j] = fmaf(r01 * x[1], va[0], out[j]);
+        out[j] = fmaf(r01 * x[0], va[1], out[j]);
+        out[j] = fmaf(r23 * x[3], va[2], out[j]);
+        out[j] = fmaf(r23 * x[2], va[3], out[j]);
       }
     }
-    out[j] = acc;
   }
 }
 
-// dynamic shared memory: q_c [k][R] (lane-permuted) | alpha [k][H][M]; phase-3 partials alias q_c
+// dynamic shared memory: q_c [k][R] (lane-permuted) | alpha [k][H][M] | LN constants [3][R] | key ring [warps][2][R];
+// phase-3 partials alias q_c
 template <int R, int H, int MODE, bool FAST, int KB>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fused_kernel(const AttnArgs a) {
@@ -160,6 +200,8 @@ attn_fused_kernel(const AttnArgs a) {
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kAttnThreads / 32;
+  float* sm_c = sm + L.qfloats + L.sfloats;          // [3][R] lane-permuted gamma', beta', vv
+  float* ring = sm_c + 3 * R + (size_t)warp * kAttnRing * R;   // this warp's key-row slots
   const int c0 = lane * CPL;                        // first channel of this lane
 
   // ---- queries: load, centre (add_LN), store lane-permuted ----
@@ -179,36 +221,54 @@ attn_fused_kernel(const AttnArgs a) {
       *reinterpret_cast<float4*>(sm_q + (size_t)beam * R + (g * 32 + lane) * 4) = c;
     }
   }
-  // per-lane constants (add_LN): gamma', beta' pre-scaled by 2 log2(e); vv = -2 v; sv = sum v
-  float gm[CPL], bt[CPL], vv[CPL];
+  // LN constants (add_LN) in the lane-permuted layout: gamma', beta' pre-scaled by 2 log2(e);
+  // vv = -2 v; sv = sum of this lane's v
   float sv = 0.f;
   if (MODE == 0) {
+    if (warp == NW - 1) {
+#pragma unroll
+      for (int g = 0; g < G4; ++g) {
+        float4 g4 = ldg4(a.gamma + c0 + g * 4), b4 = ldg4(a.beta + c0 + g * 4), v4 = ldg4(a.vvec + c0 + g * 4);
+        const float sc = FAST ? 1.0f : kTwoLog2e, vs = FAST ? 1.0f : -2.0f;
+        *reinterpret_cast<float4*>(sm_c + (g * 32 + lane) * 4) = make_float4(g4.x * sc, g4.y * sc, g4.z * sc, g4.w * sc);
+        *reinterpret_cast<float4*>(sm_c + R + (g * 32 + lane) * 4) = make_float4(b4.x * sc, b4.y * sc, b4.z * sc, b4.w * sc);
+        *reinterpret_cast<float4*>(sm_c + 2 * R + (g * 32 + lane) * 4) = make_float4(v4.x * vs, v4.y * vs, v4.z * vs, v4.w * vs);
+      }
+    }
 #pragma unroll
     for (int g = 0; g < G4; ++g) {
-      float4 g4 = ldg4(a.gamma + c0 + g * 4), b4 = ldg4(a.beta + c0 + g * 4), v4 = ldg4(a.vvec + c0 + g * 4);
-      const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, ba[4] = {b4.x, b4.y, b4.z, b4.w}, va[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        gm[g * 4 + e] = FAST ? ga[e] : ga[e] * kTwoLog2e;
-        bt[g * 4 + e] = FAST ? ba[e] : ba[e] * kTwoLog2e;
-        vv[g * 4 + e] = FAST ? va[e] : -2.0f * va[e];
-        sv += va[e];
-      }
+      float4 v4 = ldg4(a.vvec + c0 + g * 4);
+      sv += (v4.x + v4.y) + (v4.z + v4.w);
     }
   }
   const float out_scale = (MODE == 0) ? (1.0f / a.temperature[0]) : (1.0f / sqrtf((float)D));
   __syncthreads();
 
   // ---- phase 1: scores ----
+  // Key rows are staged through a per-warp 2-slot cp.async ring (the next row is in flight
+  // while the current one is scored); every lane copies exactly the 16-byte chunks it reads
+  // back, in a bank-conflict-free [g][lane] layout, so no cross-lane synchronisation is needed.
   const float* kbase = a.keys + (size_t)b * M * R + c0;
+  auto stage_row = [&](int m, int slot) {
+    if (m < M) {
+      const float* kr = kbase + (size_t)m * R;
+      float* dst = ring + (size_t)slot * R + lane * 4;
+#pragma unroll
+      for (int g = 0; g < G4; ++g) cp_async16(dst + g * 128, kr + g * 4);
+    }
+    cp_async_commit();
+  };
+  stage_row(warp, 0);
+  int slot = 0;
   for (int m = warp; m < M; m += NW) {
     float kc[CPL];
+    cp_async_wait<0>();
     {
-      const float* kr = kbase + (size_t)m * R;
+      const float* src = ring + (size_t)slot * R + lane * 4;
       float s = 0.f;
 #pragma unroll
       for (int g = 0; g < G4; ++g) {
-        float4 t = ldg4(kr + g * 4);
+        float4 t = *reinterpret_cast<const float4*>(src + g * 128);
         kc[g * 4 + 0] = t.x; kc[g * 4 + 1] = t.y; kc[g * 4 + 2] = t.z; kc[g * 4 + 3] = t.w;
         s += (t.x + t.y) + (t.z + t.w);
       }
@@ -218,13 +278,15 @@ attn_fused_kernel(const AttnArgs a) {
         for (int c = 0; c < CPL; ++c) kc[c] -= mean;
       }
     }
+    slot ^= 1;
+    stage_row(m + NW, slot);   // next row lands in the slot read one iteration ago while this row is scored
     // KB beams at a time; a short last chunk re-scores the final beams (results identical, stores idempotent)
     for (int beam0 = 0; beam0 < k; beam0 += KB) {
       const int bs = min(beam0, k - KB);               // chunk start, clamped so that bs + KB <= k
       float part[KB];
       const float* qs = sm_q + (size_t)bs * R;
       if (MODE == 0) {
-        ln_tanh_scores<CPL, KB, FAST>(kc, qs, R, lane, gm, bt, vv, sv, 1.0f / R, part);
+        ln_tanh_scores<CPL, KB, FAST>(kc, qs, sm_c, R, lane, sv, 1.0f / R, part);
       } else {
 #pragma unroll
         for (int j = 0; j < KB; ++j) {
@@ -279,6 +341,7 @@ attn_fused_kernel(const AttnArgs a) {
     const float* mk = a.att_mask ? a.att_mask + grow : nullptr;
     for (int m = lane; m < M; m += 32) {
       float al = s[m] / sum;
+      if (a.hist_pre) a.hist_pre[grow + m] = al;
       if (mk) al = (al / a.att_keep) * mk[m];
       s[m] = al;
       if (a.hist_t) a.hist_t[grow + m] = al;
@@ -298,23 +361,22 @@ attn_fused_kernel(const AttnArgs a) {
   const float* vb = a.values + (size_t)b * M * VAL + c;
   const int m_lo = (int)(((long long)M * grp) / nsplit), m_hi = (int)(((long long)M * (grp + 1)) / nsplit);
   float* red = sm_q;                                  // [nsplit-1][4][VAL]
-  for (int beam0 = 0; beam0 < k; beam0 += kAttnBeamChunk) {
-    const int nb = min(kAttnBeamChunk, k - beam0);
-    float4 acc[kAttnBeamChunk];
+  for (int beam0 = 0; beam0 < k; beam0 += KB) {
+    const int bs = min(beam0, k - KB);                // clamped chunk start (a short last chunk recomputes)
+    float4 acc[KB];
 #pragma unroll
-    for (int j = 0; j < kAttnBeamChunk; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < KB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (active) {
-      const float* a0 = sm_s + ((size_t)beam0 * H + hd) * M;
-#pragma unroll 4
-      for (int m = m_lo; m < m_hi; ++m) {
-        float4 v = ldg4(vb + (size_t)m * VAL);
+      const float* a0 = sm_s + ((size_t)bs * H + hd) * M;
+      const float* vp = vb + (size_t)m_lo * VAL;
+#pragma unroll 7
+      for (int m = m_lo; m < m_hi; ++m, vp += VAL) {
+        float4 v = ldg4(vp);
 #pragma unroll
-        for (int j = 0; j < kAttnBeamChunk; ++j) {
-          if (j < nb) {
-            float al = a0[(size_t)j * H * M + m];
-            acc[j].x = fmaf(al, v.x, acc[j].x); acc[j].y = fmaf(al, v.y, acc[j].y);
-            acc[j].z = fmaf(al, v.z, acc[j].z); acc[j].w = fmaf(al, v.w, acc[j].w);
-          }
+        for (int j = 0; j < KB; ++j) {
+          float al = a0[(size_t)j * H * M + m];
+          acc[j].x = fmaf(al, v.x, acc[j].x); acc[j].y = fmaf(al, v.y, acc[j].y);
+          acc[j].z = fmaf(al, v.z, acc[j].z); acc[j].w = fmaf(al, v.w, acc[j].w);
         }
       }
     }
@@ -322,14 +384,14 @@ attn_fused_kernel(const AttnArgs a) {
       __syncthreads();                                // query block no longer needed / previous chunk consumed
       if (active && grp > 0) {
 #pragma unroll
-        for (int j = 0; j < kAttnBeamChunk; ++j)
+        for (int j = 0; j < KB; ++j)
           *reinterpret_cast<float4*>(red + ((size_t)(grp - 1) * kAttnBeamChunk + j) * VAL + c) = acc[j];
       }
       __syncthreads();
       if (active && grp == 0) {
         for (int g2 = 1; g2 < nsplit; ++g2) {
 #pragma unroll
-          for (int j = 0; j < kAttnBeamChunk; ++j) {
+          for (int j = 0; j < KB; ++j) {
             float4 p = *reinterpret_cast<const float4*>(red + ((size_t)(g2 - 1) * kAttnBeamChunk + j) * VAL + c);
             acc[j].x += p.x; acc[j].y += p.y; acc[j].z += p.z; acc[j].w += p.w;
           }
@@ -338,9 +400,8 @@ attn_fused_kernel(const AttnArgs a) {
     }
     if (active && grp == 0) {
 #pragma unroll
-      for (int j = 0; j < kAttnBeamChunk; ++j)
-        if (j < nb)
-          *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * k + beam0 + j) * a.ld_ctx + c) = acc[j];
+      for (int j = 0; j < KB; ++j)
+        *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * k + bs + j) * a.ld_ctx + c) = acc[j];
     }
   }
 }

@@ -132,6 +132,39 @@ int encoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry);
 const BlockDesc* block_table();
 
 // decoder.cu
+struct StepBufs {
+  float* gates;        // [nz1][N][4R]
+  float* lq_part;      // [nz2][N][LQ]
+  float* lq;           // [N][LQ]
+  float* scores;       // [N][H][M]
+  float* xdense;       // [N][W+A] (input-dropout path only)
+  float* ctxraw;       // [N][VAL] (context-layer path only)
+};
+
+struct StepIO {
+  const float* keys;       // [B, M, R]
+  const float* values;     // [B, M, VAL]
+  const int* tok;          // [N]
+  const int* src;          // [N] or nullptr
+  int src_limit;
+  const float* c_prev;     // rows indexed through src
+  const float* h_prev;
+  const float* ctx_prev;
+  float* c_new;            // [N, R]
+  float* h_new;            // [N, R]
+  float* h_drop;           // [N, R] or nullptr (train): query/logits use this when set
+  float* ctx_new;          // [N, A]
+  float* hist_t;           // [N, H*M] or nullptr
+  const float* in_mask; const float* out_mask; const float* att_mask;
+  float in_keep, out_keep, att_keep;
+  const int* fin_count; int t; int n_rows;
+  // training tape (train.cu): pre-activation gates [N,4R], pre-dropout alignments [N,H*M];
+  // force_dense assembles x = [emb;ctx] into StepBufs::xdense even without an input mask
+  float* gates_save; float* alpha_pre; int force_dense;
+};
+
+int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, cudaStream_t st);
+void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_masks);
 int decoder_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes);
 int decoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry);
 int decoder_configure();

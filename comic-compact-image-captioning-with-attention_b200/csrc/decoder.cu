@@ -55,7 +55,7 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gp, int nz, size
                                       const int* __restrict__ src, int src_limit, float* __restrict__ c_new,
                                       float* __restrict__ h_new, float* __restrict__ h_drop,
                                       const float* __restrict__ out_mask, float out_keep, int N, int R,
-                                      const int* fin_count, int t, int n_rows) {
+                                      const int* fin_count, int t, int n_rows, float* __restrict__ gates_save) {
   if (step_stopped(fin_count, t, n_rows)) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * R) return;
@@ -66,6 +66,7 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gp, int nz, size
     float s = 0.f;
     for (int z = 0; z < nz; ++z) s += gp[z * zstride + (size_t)n * 4 * R + q * R + j];
     g[q] = s + bias[q * R + j];
+    if (gates_save) gates_save[(size_t)n * 4 * R + q * R + j] = g[q];
   }
   float cp = 0.f;
   if (c_prev) {
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(128)
 attn_ctx_kernel(const float* __restrict__ scores, const float* __restrict__ values, int VAL,
                 float* __restrict__ ctx_out, int ld_ctx, float* __restrict__ hist_t,
                 const float* __restrict__ att_mask, float att_keep, int k, int H, int M, int prob_fn,
-                const int* fin_count, int t, int n_rows) {
+                const int* fin_count, int t, int n_rows, float* __restrict__ hist_pre) {
   if (step_stopped(fin_count, t, n_rows)) return;
   extern __shared__ __align__(16) float sm_alpha[];   // [k][H][M]
   const int b = blockIdx.x;
@@ -273,6 +274,7 @@ attn_ctx_kernel(const float* __restrict__ scores, const float* __restrict__ valu
     const float* mk = att_mask ? att_mask + ((size_t)b * npair + pr) * M : nullptr;
     for (int m = lane; m < M; m += 32) {
       float al = a[m] / sum;
+      if (hist_pre && blockIdx.y == 0) hist_pre[((size_t)b * npair + pr) * M + m] = al;
       if (mk) al = (al / att_keep) * mk[m];
       a[m] = al;
       if (hist_t && blockIdx.y == 0) hist_t[((size_t)b * npair + pr) * M + m] = al;
@@ -636,34 +638,6 @@ int decoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
 // ---------------------------------------------------------------------------
 // Step driver shared by decode_step / greedy / beam.
 // ---------------------------------------------------------------------------
-struct StepBufs {
-  float* gates;        // [nz1][N][4R]
-  float* lq_part;      // [nz2][N][LQ]
-  float* lq;           // [N][LQ]
-  float* scores;       // [N][H][M]
-  float* xdense;       // [N][W+A] (input-dropout path only)
-  float* ctxraw;       // [N][VAL] (context-layer path only)
-};
-
-struct StepIO {
-  const float* keys;       // [B, M, R]
-  const float* values;     // [B, M, VAL]
-  const int* tok;          // [N]
-  const int* src;          // [N] or nullptr
-  int src_limit;
-  const float* c_prev;     // rows indexed through src
-  const float* h_prev;
-  const float* ctx_prev;
-  float* c_new;            // [N, R]
-  float* h_new;            // [N, R]
-  float* h_drop;           // [N, R] or nullptr (train): query/logits use this when set
-  float* ctx_new;          // [N, A]
-  float* hist_t;           // [N, H*M] or nullptr
-  const float* in_mask; const float* out_mask; const float* att_mask;
-  float in_keep, out_keep, att_keep;
-  const int* fin_count; int t; int n_rows;
-};
-
 static size_t step_smem_scores(int k, int R) { return (size_t)k * R * sizeof(float); }
 static size_t step_smem_ctx(int k, int H, int M) { return (size_t)k * H * M * sizeof(float); }
 
@@ -765,7 +739,7 @@ static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb
   AttnArgs aa{};
   aa.keys = io.keys; aa.values = io.values; aa.lq = sb.lq; aa.ld_lq = h->LQ; aa.q_off = h->Vp;
   aa.gamma = h->w.ln_gamma; aa.beta = h->w.ln_beta; aa.vvec = h->w.attention_v; aa.temperature = h->w.temperature;
-  aa.ctx_out = ctx_dst; aa.ld_ctx = ld_ctx; aa.hist_t = io.hist_t; aa.att_mask = io.att_mask;
+  aa.ctx_out = ctx_dst; aa.ld_ctx = ld_ctx; aa.hist_t = io.hist_t; aa.hist_pre = io.alpha_pre; aa.att_mask = io.att_mask;
   aa.att_keep = io.att_keep; aa.k = k; aa.M = h->M; aa.VAL = h->VAL; aa.prob_fn = h->cfg.prob_fn;
   aa.fin_count = io.fin_count; aa.t = io.t; aa.n_rows = io.n_rows;
   cudaError_t e = cudaErrorInvalidValue;
@@ -799,17 +773,20 @@ static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb
 }
 
 // One attention-wrapper step on N = B*k rows.
-static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, cudaStream_t st) {
+int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, cudaStream_t st) {
   const int N = B * k, R = h->R, W = h->W, A = h->A;
   // --- gates = [emb(tok) ; ctx ; h] . K ---
   APlain a{};
-  if (io.in_mask) {
-    // training path: x assembled densely so the input dropout mask can be applied
+  if (io.in_mask || io.force_dense) {
+    // training path: x assembled densely so the input dropout mask can be applied (and x kept on the tape)
     assemble_x_kernel<<<N, 256, 0, st>>>(h->w.embedding_map, io.tok, h->V, h->cfg.embed_lookup, io.ctx_prev,
                                         sb.xdense, N, W, A);
-    size_t nx = (size_t)N * (W + A);
-    dropout_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(sb.xdense, io.in_mask, io.in_keep, nx);
-    h->launches += 2;
+    h->launches++;
+    if (io.in_mask) {
+      size_t nx = (size_t)N * (W + A);
+      dropout_rows_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(sb.xdense, io.in_mask, io.in_keep, nx);
+      h->launches++;
+    }
     a.nseg = 2;
     a.seg[0] = ASeg{sb.xdense, nullptr, W + A, W + A, N};
     a.seg[1] = ASeg{io.h_prev, io.src, R, R, io.src_limit};
@@ -839,7 +816,7 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
     lstm_pointwise_kernel<<<(tot + 255) / 256, 256, 0, st>>>(sb.gates, nz1, (size_t)N * 4 * R, h->w.lstm_bias,
                                                           io.c_prev, io.src, io.src_limit, io.c_new, io.h_new,
                                                           io.h_drop, io.out_mask, io.out_keep, N, R, io.fin_count,
-                                                          io.t, io.n_rows);
+                                                          io.t, io.n_rows, io.gates_save);
   }
   // --- [logits | q] = h_out . [W_o | W_q] + [b_o | 0] ---
   const float* hq = io.h_drop ? io.h_drop : io.h_new;
@@ -883,7 +860,7 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
       Prof pf(h, T_CTX, st);
       attn_ctx_kernel<<<grid, 128, smem, st>>>(sb.scores, io.values, VAL, ctx_dst, ld_ctx, io.hist_t, io.att_mask,
                                               io.att_keep, k, h->H, h->M, h->cfg.prob_fn, io.fin_count, io.t,
-                                              io.n_rows);
+                                              io.n_rows, io.alpha_pre);
     }
     COMIC_CHECK_CUDA(cudaGetLastError());
     if (h->cfg.context_layer) {
@@ -903,7 +880,7 @@ static int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int 
   return COMIC_OK;
 }
 
-static void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_masks) {
+void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_masks) {
   GemmPlan p1 = plan_gemm(N, 4 * h->R, h->KX, h->num_sms, true);
   int nz1 = gemm_num_partials(h->KX, p1);
   GemmPlan p2 = plan_gemm(N, h->LQ, h->R, h->num_sms, true);
@@ -1059,7 +1036,7 @@ extern "C" int comic_rnn_init(comic_handle_t h, const float* im_embed, int B, fl
   COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->w.lstm_kernel, 4 * R, B, 4 * R, XA, e2, p2, st)));
   int tot = B * R;
   lstm_pointwise_kernel<<<(tot + 255) / 256, 256, 0, st>>>(gates, nz, (size_t)B * 4 * R, h->w.lstm_bias, nullptr,
-                                                        nullptr, 0, c0, h0, nullptr, nullptr, 1.f, B, R, nullptr, 0, 0);
+                                                        nullptr, 0, c0, h0, nullptr, nullptr, 1.f, B, R, nullptr, 0, 0, nullptr);
   h->launches += 2;
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;

@@ -43,6 +43,19 @@ class ComicWeights(C.Structure):
         ('bn_var', _FP * NUM_CONVS)]
 
 
+class ComicTrainMasks(C.Structure):
+    _fields_ = [('init_in', _FP), ('inp', _FP), ('out', _FP), ('att', _FP),
+                ('in_keep', C.c_float), ('out_keep', C.c_float), ('att_keep', C.c_float)]
+
+
+GRAD_FIELDS = ('lstm_kernel', 'lstm_bias', 'init_weight', 'memory_kernel', 'value_kernel', 'query_kernel',
+               'attention_v', 'ln_gamma', 'ln_beta', 'temperature', 'out_kernel', 'out_bias', 'embedding_map')
+
+
+class ComicDecoderGrads(C.Structure):
+    _fields_ = [(n, _FP) for n in GRAD_FIELDS]
+
+
 class ComicConvDesc(C.Structure):
     _fields_ = [('k', C.c_int32), ('stride', C.c_int32), ('c_in', C.c_int32), ('c_out', C.c_int32)]
 
@@ -77,6 +90,13 @@ SIGNATURES = {
     'comic_launch_count': (_I, [_P, C.POINTER(C.c_int64)]),
     'comic_set_precision': (_I, [_P, _I]),
     'comic_set_option': (_I, [_P, _I, _I]),
+    'comic_train_workspace_bytes': (_I, [_P, _I, _I, C.POINTER(_SZ)]),
+    'comic_dropout_masks': (_I, [_P, _P, _SZ, _F, C.c_uint64, C.c_uint64, _P]),
+    'comic_train_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, C.POINTER(ComicTrainMasks), _F, _P, _P, _P,
+                                 C.POINTER(ComicDecoderGrads), _P, _SZ, _P]),
+    'comic_l2_regularise': (_I, [_P, _P, _P, _SZ, _F, _P, _P, _SZ, _P]),
+    'comic_adam_step': (_I, [_P, _P, _P, _P, _P, _SZ, _F, _F, _F, _F, _I, _F, _P]),
+    'comic_refresh_packed': (_I, [_P, _P, _SZ, _P]),
     'comic_profile_enable': (_I, [_P, C.c_uint32]),
     'comic_profile_read': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
@@ -381,6 +401,74 @@ class Engine(object):
         ms, n = C.c_double(), C.c_int64()
         self._check(self.lib.comic_profile_read(self._h, KERNEL_TAGS.index(tag), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    # -- training (T1-T4) ------------------------------------------------------
+    def variable_to_grad_field(self):
+        """TF variable name -> field of comic_decoder_grads_t."""
+        c = self.c
+        D = wts.DEC
+        att = D + 'multi_add_attention/'
+        cs = wts.cell_scope(c)
+        m = {cs + 'kernel': 'lstm_kernel', cs + 'bias': 'lstm_bias',
+             D + 'rnn_init_input/projection/weight': 'init_weight', D + 'rnn_initial_state/weight': 'init_weight',
+             D + 'memory_layer/kernel': 'memory_kernel', D + 'value_layer/kernel': 'value_kernel',
+             att + 'query_layer/kernel': 'query_kernel', att + 'attention_v': 'attention_v',
+             att + 'LN_tanh/gamma': 'ln_gamma', att + 'LN_tanh/beta': 'ln_beta',
+             D + 'softmax_temperature': 'temperature', D + 'output_projection/kernel': 'out_kernel',
+             D + 'output_projection/bias': 'out_bias', D + 'embedding_map': 'embedding_map'}
+        return m
+
+    def dropout_masks(self, shape, keep, seed, stream_id):
+        out = self.f32(*shape)
+        self._check(self.lib.comic_dropout_masks(self._h, _ptr(out), out.numel(), float(keep), int(seed),
+                                                 int(stream_id), self.stream()))
+        return out
+
+    def train_fwd_bwd(self, fm, im_embed, inputs_tm, targets_tm, coef_tm, lens, T_run, grad_views, masks=None,
+                      keeps=(1.0, 1.0, 1.0), map_loss_scale=1.0, want_logits=False, want_attn=False):
+        """grad_views: dict grad-field -> device tensor view receiving that gradient."""
+        torch = self.torch
+        d = self.dims
+        T, B = inputs_tm.shape
+        loss = torch.zeros(4, dtype=torch.float32, device=self.device)
+        logits = self.f32(B, T, d.V) if want_logits else None
+        attn = self.f32(B, d.H, T_run, d.M) if want_attn else None
+        g = ComicDecoderGrads()
+        for f in GRAD_FIELDS:
+            t = grad_views.get(f)
+            setattr(g, f, None if t is None else C.c_void_p(t.data_ptr()))
+        mk = None
+        if masks is not None:
+            mk = ComicTrainMasks()
+            for f in ('init_in', 'inp', 'out', 'att'):
+                t = masks.get(f)
+                setattr(mk, f, None if t is None else C.c_void_p(t.data_ptr()))
+            mk.in_keep, mk.out_keep, mk.att_keep = [float(x) for x in keeps]
+        n = C.c_size_t()
+        self._check(self.lib.comic_train_workspace_bytes(self._h, B, T_run, C.byref(n)))
+        ws = self._ws.get('train')
+        if ws is None or ws.numel() < n.value:
+            ws = self._ws['train'] = torch.empty(n.value, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.comic_train_fwd_bwd(
+            self._h, _ptr(fm), _ptr(im_embed), B, _ptr(inputs_tm), _ptr(targets_tm), _ptr(coef_tm), _ptr(lens), T,
+            int(T_run), None if mk is None else C.byref(mk), float(map_loss_scale), _ptr(loss), _ptr(logits),
+            _ptr(attn), C.byref(g), _ptr(ws), ws.numel(), self.stream()))
+        return loss, logits, attn
+
+    def l2_regularise(self, params, grads, decay, reg_out):
+        ws = self._ws.get('l2')
+        if ws is None:
+            ws = self._ws['l2'] = self.torch.empty(8192, dtype=self.torch.uint8, device=self.device)
+        self._check(self.lib.comic_l2_regularise(self._h, _ptr(params), _ptr(grads), params.numel(), float(decay),
+                                                 _ptr(reg_out), _ptr(ws), ws.numel(), self.stream()))
+
+    def adam_step(self, params, grads, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-2, grad_scale=1.0):
+        self._check(self.lib.comic_adam_step(self._h, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), params.numel(),
+                                             float(lr), float(beta1), float(beta2), float(eps), int(step),
+                                             float(grad_scale), self.stream()))
+
+    def refresh_packed(self):
+        self._check(self.lib.comic_refresh_packed(self._h, _ptr(self._packed), self._packed.numel(), self.stream()))
 
     def launch_count(self):
         n = C.c_int64()

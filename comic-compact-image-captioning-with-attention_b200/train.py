@@ -1,0 +1,161 @@
+"""Training on the CUDA engine: `train_mode` = decoder | scst (frozen CNN).
+
+Mirrors the pieces of the reference that surround one `sess.run(train_op)`:
+  ModelBase._process_inputs        src/model_base.py:501-528  (inputs / targets / masks)
+  ModelBase._train_caption_model   src/model_base.py:325-405  (loss terms, Adam, no clipping)
+  ModelBase._create_cosine_lr      src/model_base.py:809-820
+  train_fn / train_fn_scst loops   src/train_fn.py:26-147, 150-307 (one step each)
+The arithmetic runs in libcomic_b200.so (csrc/train.cu); this module only prepares the
+int32 / fp32 host arrays, owns the flat parameter / gradient / Adam buffers and calls
+`torch.distributed.all_reduce` on the flat gradient buffer when a process group exists
+(one process per GPU, NCCL over NVLink; the reference is single-GPU).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import weights as wts
+from .engine import Engine
+
+
+def process_inputs(captions, token_type):
+    """_process_inputs (src/model_base.py:501-528): captions [B,L] int32 (PAD = -1) ->
+    (inputs [B,L-1], targets [B,L-1], masks [B,L-1] f32, lens [B] i32)."""
+    cap = np.asarray(captions, np.int32)
+    masks = np.sign((cap[:, 1:] + 1).astype(np.float32))
+    lens = masks.sum(axis=1).astype(np.int32)
+    clipped = np.maximum(cap, 0)
+    inputs = clipped[:, :-1] if token_type == 'word' else cap[:, :-1]
+    return inputs, clipped[:, 1:], masks, lens
+
+
+def loss_coefficients(masks, rewards=None):
+    """Per-token weight of the cross-entropy (src/model_base.py:337-347): XE mode
+    mask / (sum(mask) + 1e-12); SCST mode reward_b / B * mask / (sum_t mask + 1e-12)."""
+    m = masks.astype(np.float32)
+    if rewards is None:
+        return m / (m.sum(dtype=np.float32) + np.float32(1e-12))
+    r = np.asarray(rewards, np.float32)[:, None]
+    return (r / np.float32(m.shape[0])) * m / (m.sum(axis=1, keepdims=True) + np.float32(1e-12))
+
+
+def cosine_lr(step, max_step, lr_start, lr_end):
+    """_create_cosine_lr (src/model_base.py:809-820)."""
+    s = min(1.0, float(step) / float(max_step))
+    return (lr_start - lr_end) * (1.0 + math.cos(s * math.pi)) / 2.0 + lr_end
+
+
+class Trainer(object):
+    """Flat fp32 parameter / gradient / Adam-slot buffers over the decoder variables, one
+    engine handle, one optimiser step per `step()`."""
+
+    def __init__(self, config, weights, engine=None, with_cnn=True):
+        self.c = c = config
+        if c.train_mode not in ('decoder', 'scst'):
+            raise NotImplementedError("train_mode '%s' (encoder backward) is not built on the CUDA path yet"
+                                      % c.train_mode)
+        self.engine = eng = engine or Engine(c)
+        torch = self.torch = eng.torch
+        self.shapes = wts.decoder_shapes(c)
+        self.offsets, off = {}, 0
+        for name, shp in self.shapes.items():
+            n = int(np.prod(shp)) if len(shp) else 1
+            self.offsets[name] = (off, n, shp)
+            off += (n + 3) // 4 * 4                     # 16-byte aligned views
+        self.n_flat = off
+        self.params = torch.zeros(off, dtype=torch.float32, device=eng.device)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=eng.device)
+        self.adam_m = torch.zeros(off, dtype=torch.float32, device=eng.device)
+        self.adam_v = torch.zeros(off, dtype=torch.float32, device=eng.device)
+        W = dict(weights)
+        for name, (o, n, shp) in self.offsets.items():
+            self.params[o:o + n].copy_(torch.as_tensor(np.asarray(W[name], np.float32).reshape(-1)))
+            W[name] = self.params[o:o + n].view(shp if len(shp) else (1,))
+        eng.bind_weights(W, with_cnn=with_cnn)
+        fields = eng.variable_to_grad_field()
+        self.grad_views = {}
+        for name, (o, n, shp) in self.offsets.items():
+            self.grad_views[fields[name]] = self.grads[o:o + n]
+        self.global_step = 0
+        self.reg = torch.zeros(1, dtype=torch.float32, device=eng.device)
+
+    # -- views ------------------------------------------------------------------
+    def variable(self, name):
+        o, n, shp = self.offsets[name]
+        return self.params[o:o + n].view(shp if len(shp) else (1,))
+
+    def gradient(self, name):
+        o, n, shp = self.offsets[name]
+        return self.grads[o:o + n].view(shp if len(shp) else (1,))
+
+    def make_masks(self, B, T_run, seed):
+        """Seeded Philox dropout masks (DropoutWrapper in/out, attention-map dropout)."""
+        c, d, eng = self.c, self.engine.dims, self.engine
+        keeps = (1.0 - c.dropout_rnn_in, 1.0 - c.dropout_rnn_out, c.attn_keep_prob)
+        XA = d.W + d.A
+        masks = dict(init_in=eng.dropout_masks((B, XA), keeps[0], seed, 0),
+                     inp=eng.dropout_masks((T_run, B, XA), keeps[0], seed, 1),
+                     out=eng.dropout_masks((T_run, B, d.R), keeps[1], seed, 2))
+        if keeps[2] < 1.0:
+            masks['att'] = eng.dropout_masks((T_run, B, d.H * d.M), keeps[2], seed, 3)
+        return masks, keeps
+
+    # -- one fwd + bwd (+ optimiser) ---------------------------------------------
+    def forward_backward(self, fm, im_embed, captions, rewards=None, masks=None, keeps=(1.0, 1.0, 1.0),
+                         want_logits=False, want_attn=False):
+        """captions [B,L] int32 host array.  Returns dict(loss=[total, xe, map, reg] device tensor, ...);
+        gradients land in self.grads."""
+        c, eng, torch = self.c, self.engine, self.torch
+        inputs, targets, wmask, lens = process_inputs(captions, c.token_type)
+        coef = loss_coefficients(wmask, rewards)
+        T_run = int(lens.max())
+        dev = eng.device
+        to = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a)).to(dt).to(dev)
+        inputs_tm = to(inputs.T, torch.int32)
+        targets_tm = to(targets.T, torch.int32)
+        coef_tm = to(coef.T, torch.float32)
+        lens_d = to(lens, torch.int32)
+        self.grads.zero_()
+        loss, logits, attn = eng.train_fwd_bwd(fm.contiguous(), im_embed.contiguous(), inputs_tm, targets_tm, coef_tm,
+                                               lens_d, T_run, self.grad_views, masks, keeps, c.rnn_map_loss_scale,
+                                               want_logits, want_attn)
+        if c.l2_decay > 0:
+            eng.l2_regularise(self.params, self.grads, c.l2_decay, loss[3:4])
+        loss[0:1] = loss[1:2] + loss[2:3] + loss[3:4]
+        return dict(loss=loss, logits=logits, attn=attn, T_run=T_run)
+
+    def apply_gradients(self, lr=None):
+        """NCCL all-reduce (mean over ranks) + TF-form Adam + repack (model_base.py:387-401)."""
+        c, eng = self.c, self.engine
+        world = 1
+        dist = None
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                world = dist.get_world_size()
+        except Exception:
+            world = 1
+        if world > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        self.global_step += 1
+        if lr is None:
+            lr = cosine_lr(self.global_step - 1, c.max_step, c.lr_start, c.lr_end)
+        eng.adam_step(self.params, self.grads, self.adam_m, self.adam_v, lr, self.global_step, 0.9, 0.999,
+                      c.adam_epsilon, 1.0 / world)
+        eng.refresh_packed()
+        return lr
+
+    def step(self, images, captions, rewards=None, seed=None, lr=None):
+        """One `sess.run([train_op])`: frozen encoder forward, decoder fwd+bwd, optimiser."""
+        eng = self.engine
+        im_embed, fm = eng.encode(images)
+        B = im_embed.shape[0]
+        masks, keeps = None, (1.0, 1.0, 1.0)
+        if seed is not None:
+            _, _, _, lens = process_inputs(captions, self.c.token_type)
+            masks, keeps = self.make_masks(B, int(lens.max()), seed)
+        out = self.forward_backward(fm, im_embed, captions, rewards, masks, keeps)
+        out['lr'] = self.apply_gradients(lr)
+        return out

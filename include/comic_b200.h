@@ -207,6 +207,69 @@ int comic_gemm_f32(comic_handle_t h, const float* A, int lda, const float* Bm, i
                    const float* bias, float* C, int ldc, int M, int N, int K,
                    void* ws, size_t ws_bytes, void* stream);
 
+
+/* ------------------------------------------------------------------------- *
+ * Training: train_mode = decoder | scst (frozen CNN).  cnn_finetune (encoder
+ * backward) is not built yet.
+ * ------------------------------------------------------------------------- */
+
+/* Explicit 0/1 dropout masks (NULL member = that dropout off) + keep probabilities:
+ * DropoutWrapper input/output dropout (src/model_base.py:637-647) and the
+ * attention-map dropout (common/ops_rnn.py:696-701).  Generate them with
+ * comic_dropout_masks (Philox4x32-10) or inject them for parity tests. */
+typedef struct {
+  const float* init_in;   /* [B, W+A]      input mask of the rnn-init LSTM step */
+  const float* inp;       /* [T_run, B, W+A] */
+  const float* out;       /* [T_run, B, R] */
+  const float* att;       /* [T_run, B, H*M] */
+  float in_keep, out_keep, att_keep;
+} comic_train_masks_t;
+
+/* Device pointers receiving the gradient of each decoder variable (same shapes as
+ * comic_weights_t; normally views into one flat buffer that is all-reduced). */
+typedef struct {
+  float* lstm_kernel; float* lstm_bias; float* init_weight; float* memory_kernel; float* value_kernel;
+  float* query_kernel; float* attention_v; float* ln_gamma; float* ln_beta; float* temperature;
+  float* out_kernel; float* out_bias; float* embedding_map;
+} comic_decoder_grads_t;
+
+int comic_train_workspace_bytes(comic_handle_t h, int B, int T_run, size_t* bytes);
+
+/* 0/1 keep masks: out[i] = uniform(seed, stream_id, i) < keep. */
+int comic_dropout_masks(comic_handle_t h, float* out, size_t n, float keep, uint64_t seed, uint64_t stream_id,
+                        void* stream);
+
+/* T1+T3: rops.rnn_decoder_training (common/ops_rnn.py:183-243, TrainingHelper,
+ * impute_finished=True) + ModelBase._train_caption_model (src/model_base.py:325-383)
+ * forward AND backward on B rows (one image per row; SCST callers repeat images).
+ *   fm [B,M,C], im_embed [B,E]          encoder outputs (frozen CNN)
+ *   inputs_tm, targets_tm [T,B] i32     time-major decoder inputs / targets (_process_inputs :501-528)
+ *   coef_tm [T,B] f32                   weight / normaliser per token: XE: mask/(sum mask + 1e-12);
+ *                                       SCST: reward_b/B * mask/(sum_t mask + 1e-12)  (:337-347)
+ *   lens [B] i32, T_run = max(lens)     executed steps (dynamic_decode stops when all rows finished)
+ *   loss_out [4] device                 [unused, xe, map, unused]  (reg: comic_l2_regularise)
+ *   logits_out [B,T,V] or NULL, attn_out [B,H,T_run,M] or NULL
+ *   grads                               overwritten with dLoss/dvariable (xe + map terms)          */
+int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const float* im_embed, int B,
+                        const int32_t* inputs_tm, const int32_t* targets_tm, const float* coef_tm,
+                        const int32_t* lens, int T, int T_run, const comic_train_masks_t* masks,
+                        float map_loss_scale, float* loss_out, float* logits_out, float* attn_out,
+                        const comic_decoder_grads_t* grads, void* ws, size_t ws_bytes, void* stream);
+
+/* ModelBase._loss_regularisation (src/model_base.py:408-417) on a flat parameter buffer:
+ * grads += decay * params (grads may be NULL); reg_out[0] = decay/2 * sum params^2.  ws >= 4 KB. */
+int comic_l2_regularise(comic_handle_t h, const float* params, float* grads, size_t n, float decay,
+                        float* reg_out, void* ws, size_t ws_bytes, void* stream);
+
+/* tf.train.AdamOptimizer dense update (src/model_base.py:852-861), step >= 1:
+ * lr_t = lr sqrt(1-b2^t)/(1-b1^t); m,v moving averages; params -= lr_t m/(sqrt(v)+eps).
+ * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
+int comic_adam_step(comic_handle_t h, float* params, const float* grads, float* m, float* v, size_t n,
+                    float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+/* After the optimiser changed the variables in place: rebuild the decoder's packed copies. */
+int comic_refresh_packed(comic_handle_t h, void* packed, size_t packed_bytes, void* stream);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int comic_launch_count(comic_handle_t h, int64_t* count);
 

@@ -1,0 +1,130 @@
+"""GPU parity of the training path (csrc/train.cu through the C ABI): losses and every
+decoder-variable gradient against fp64 autograd of the torch restatement
+(tests/torch_ref.py, itself pinned to the NumPy oracle's forward on CPU).
+Tolerance 1e-3 relative to the largest entry of each gradient tensor."""
+import numpy as np
+import pytest
+
+from _common import comic_config, word_config, make_weights, fake_features, rel_err
+from test_oracle_known_answers import _train_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def torch_mod():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return torch
+
+
+def _reference(c, W, im, fm, caps, masks, keeps, rewards):
+    import torch_ref as TR
+    P = TR.to_params(W)
+    tot, xe, mp, reg, aux = TR.training_loss(P, c, im, fm, caps, masks, keeps, rewards)
+    tot.backward()
+    grads = {k: v.grad.numpy() for k, v in P.items()}
+    return dict(total=float(tot), xe=float(xe), map=float(mp), reg=float(reg), grads=grads,
+                logits=aux['logits'].detach().numpy(), attn=aux['attn'].detach().numpy())
+
+
+CASES = {
+    'comic256_xe_dropout': (lambda: comic_config(train_mode='decoder'), True, False),
+    'comic256_scst_dropout': (lambda: comic_config(train_mode='scst'), True, True),
+    'comic256_xe_nodrop': (lambda: comic_config(train_mode='decoder'), False, False),
+    'word_none_h1_xe': (lambda: word_config(n_words=300, train_mode='decoder'), True, False),
+    'independent_h4': (lambda: comic_config(train_mode='decoder', cnn_fm_projection='independent', attn_num_heads=4),
+                       True, False),
+}
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_gradients_match_autograd(torch_mod, name):
+    from comic_b200.train import Trainer
+    from comic_b200 import weights as wts
+    mk, dropout, scst = CASES[name]
+    c = mk()
+    W, im, fm, caps, masks, keeps = _train_case(c, B=4, L=8, seed=3, dropout=dropout)
+    rewards = np.array([0.4, -0.3, 1.2, 0.05], np.float32) if scst else None
+    ref = _reference(c, W, im, fm, caps, masks, keeps, rewards)
+    tr = Trainer(c, W, with_cnn=False)
+    eng = tr.engine
+    eng.set_precision('f32')
+    dmasks = None
+    if masks is not None:
+        dmasks = dict(init_in=eng.to_dev(masks['init_in']), inp=eng.to_dev(masks['inp']), out=eng.to_dev(masks['out']),
+                      att=eng.to_dev(masks['att'].reshape(masks['att'].shape[0], masks['att'].shape[1], -1)))
+    out = tr.forward_backward(eng.to_dev(fm), eng.to_dev(im), caps, rewards, dmasks, keeps, want_logits=True,
+                              want_attn=True)
+    loss = out['loss'].cpu().numpy()
+    assert abs(loss[1] - ref['xe']) < 1e-4 * max(1.0, abs(ref['xe']))
+    assert abs(loss[2] - ref['map']) < 1e-4 * max(1e-3, abs(ref['map']))
+    assert abs(loss[3] - ref['reg']) < 1e-4 * max(1e-3, abs(ref['reg']))
+    assert abs(loss[0] - ref['total']) < 1e-4 * max(1.0, abs(ref['total']))
+    T_run = out['T_run']
+    lg = out['logits'].cpu().numpy().transpose(1, 0, 2)                 # [T,B,V]
+    assert rel_err(lg, ref['logits']) < 2e-4
+    assert rel_err(out['attn'].cpu().numpy(), ref['attn']) < 2e-4
+    worst = {}
+    for vname in wts.decoder_shapes(c):
+        g = tr.gradient(vname).cpu().numpy().reshape(ref['grads'][vname].shape)
+        worst[vname] = rel_err(g, ref['grads'][vname])
+    bad = {k: v for k, v in worst.items() if not v < 1e-3}
+    assert not bad, (bad, worst)
+
+
+def test_adam_and_l2_match_oracle(torch_mod):
+    import comic_oracle as O
+    from comic_b200.engine import Engine
+    torch = torch_mod
+    c = comic_config()
+    eng = Engine(c)
+    rng = np.random.default_rng(0)
+    n = 10007
+    th = rng.standard_normal(n).astype(np.float32)
+    m = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    d_th, d_m, d_v = eng.to_dev(th), eng.to_dev(m), eng.to_dev(v)
+    th64, m64, v64 = th.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    for step in range(1, 4):
+        g = rng.standard_normal(n).astype(np.float32) * 0.1
+        eng.adam_step(d_th, eng.to_dev(g), d_m, d_v, 1e-2, step, eps=1e-2, grad_scale=0.5)
+        th64, m64, v64 = O.adam_step(th64, g.astype(np.float64) * 0.5, m64, v64, 1e-2, step, eps=1e-2)
+    assert rel_err(d_th.cpu().numpy(), th64) < 1e-6
+    assert rel_err(d_m.cpu().numpy(), m64) < 1e-5
+    reg = torch.zeros(1, device=eng.device)
+    gbuf = eng.to_dev(np.zeros(n, np.float32))
+    eng.l2_regularise(d_th, gbuf, 1e-5, reg)
+    assert abs(float(reg.item()) - 0.5e-5 * float((th64 ** 2).sum())) < 1e-6 * float((th64 ** 2).sum())
+    assert rel_err(gbuf.cpu().numpy(), 1e-5 * th64) < 1e-5
+
+
+def test_dropout_masks_are_seeded_bernoulli(torch_mod):
+    from comic_b200.engine import Engine
+    eng = Engine(comic_config())
+    a = eng.dropout_masks((41, 32, 768), 0.65, seed=7, stream_id=1).cpu().numpy()
+    b = eng.dropout_masks((41, 32, 768), 0.65, seed=7, stream_id=1).cpu().numpy()
+    c2 = eng.dropout_masks((41, 32, 768), 0.65, seed=8, stream_id=1).cpu().numpy()
+    assert set(np.unique(a)) <= {0.0, 1.0}
+    np.testing.assert_array_equal(a, b)
+    assert (a != c2).mean() > 0.3
+    assert abs(a.mean() - 0.65) < 5e-3
+    assert abs(np.corrcoef(a.reshape(-1)[:-1], a.reshape(-1)[1:])[0, 1]) < 0.01
+
+
+def test_training_steps_reduce_loss(torch_mod):
+    """A few optimiser steps on one fixed batch (teacher forcing, dropout off): XE loss goes down,
+    and the packed decoder copies follow the updated variables (greedy decode changes)."""
+    from comic_b200.train import Trainer
+    c = comic_config(train_mode='decoder', max_step=100)
+    W, im, fm, caps, _, _ = _train_case(c, B=6, L=9, seed=5, dropout=False)
+    tr = Trainer(c, W, with_cnn=False)
+    eng = tr.engine
+    fm_d, im_d = eng.to_dev(fm), eng.to_dev(im)
+    losses = []
+    for _ in range(6):
+        out = tr.forward_backward(fm_d, im_d, caps)
+        losses.append(float(out['loss'][1].item()))
+        tr.apply_gradients(lr=5e-3)
+    assert losses[-1] < losses[0] - 0.05, losses
+    assert all(np.isfinite(losses))
