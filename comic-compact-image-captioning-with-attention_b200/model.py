@@ -126,16 +126,29 @@ class ModelBase(object):
 
 
 class CaptionModel(ModelBase):
-    """src/model.py:21-73.  mode 'infer' is served by the CUDA engine in this
-    round; 'train' / 'eval' live in train.py (teacher-forced path)."""
+    """src/model.py:21-73.  mode 'infer': `run()` / `infer_output`.  mode 'train' / 'eval':
+    `train_step(images, captions)` = one `sess.run([dec_log_ppl, global_step])` of
+    src/train_fn.py:120 (fwd + bwd + Adam), `eval_step` the teacher-forced perplexity of
+    src/train_fn.py:320-338.  `reuse=True` shares the variables (engine / trainer) of `share`."""
 
-    def __init__(self, config, mode, batch_ops=None, reuse=False, name=None, weights=None, engine=None):
+    def __init__(self, config, mode, batch_ops=None, reuse=False, name=None, weights=None, engine=None,
+                 share=None):
         assert mode in ['train', 'eval', 'infer']
         super(CaptionModel, self).__init__(config)
         self.mode = mode
         self.batch_ops = batch_ops
         self.reuse = reuse
         self.name = name
+        self.trainer = None
+        if share is not None:
+            engine = share.engine
+            self.trainer = share.trainer
+        if mode in ('train', 'eval') and self.trainer is None:
+            from .train import Trainer
+            if weights is None:
+                weights = wts.init_weights(config, seed=getattr(config, 'rand_seed', 48964896))
+            self.trainer = Trainer(config, weights, engine=engine)
+            engine = self.trainer.engine
         if engine is None:
             engine = Engine(config)
             if weights is None:
@@ -143,8 +156,27 @@ class CaptionModel(ModelBase):
             engine.bind_weights(weights)
         self.engine = engine
         self._pinned = {}
-        if mode != 'infer':
-            raise NotImplementedError("mode '%s' is not built on the CUDA path yet (DESIGN.md, scope)" % mode)
+
+    # -- ModelBase.get_global_step / update_lr (src/model_base.py:767-773) ----
+    def get_global_step(self):
+        return 0 if self.trainer is None else self.trainer.global_step
+
+    def train_step(self, images, captions, seed=None, lr=None):
+        """One optimiser step; returns (dec_log_ppl, global_step) like train_fn.py:120."""
+        assert self.mode == 'train'
+        eng = self.engine
+        images = eng.torch.as_tensor(images).to(eng.device, non_blocking=True)
+        out = self.trainer.step(images, np.asarray(captions), None, seed, lr)
+        self.dec_log_ppl = out['loss'][1]
+        return self.dec_log_ppl, self.trainer.global_step
+
+    def eval_step(self, images, captions):
+        """Teacher-forced log-perplexity without dropout or update (_run_eval_loop)."""
+        eng = self.engine
+        images = eng.torch.as_tensor(images).to(eng.device, non_blocking=True)
+        im_embed, fm = eng.encode(images)
+        out = self.trainer.forward_backward(fm, im_embed, np.asarray(captions))
+        return out['loss'][1]
 
     def restore_model(self, weights):
         """ModelBase.restore_model (src/model_base.py:422-490): bind a W-table."""
@@ -185,6 +217,55 @@ class CaptionModel(ModelBase):
     @property
     def infer_output(self):
         return self.run()
+
+
+class CaptionModel_SCST(ModelBase):
+    """src/model.py:76-141.  scst_mode 'sample': `sample(images)` -> (dec_preds_beam [k,B,T],
+    dec_preds_greedy [B,T]) (greedy + beam-`scst_beam_size`, max length 20, no dropout);
+    scst_mode 'train': `train_scst(images_or_features, captions, rewards)` = weighted-XE step."""
+
+    def __init__(self, config, scst_mode, reuse=False, weights=None, share=None):
+        assert scst_mode in ['train', 'sample']
+        super(CaptionModel_SCST, self).__init__(config)
+        self.mode = scst_mode if scst_mode == 'train' else 'infer'
+        self.name = scst_mode
+        self.reuse = reuse
+        if share is not None:
+            self.trainer = share.trainer
+        else:
+            from .train import Trainer
+            if weights is None:
+                weights = wts.init_weights(config, seed=getattr(config, 'rand_seed', 48964896))
+            self.trainer = Trainer(config, weights)
+        self.engine = self.trainer.engine
+
+    def sample(self, images):
+        from . import scst
+        c = self._config
+        eng = self.engine
+        images = eng.torch.as_tensor(images).to(eng.device, non_blocking=True)
+        cap_beam, cap_greedy, self.im_embed, self.cnn_fmaps = scst.sample_captions(eng, c, images, c.scst_beam_size)
+        self.dec_preds_beam, self.dec_preds_greedy = cap_beam, cap_greedy
+        return cap_beam, cap_greedy
+
+    def train_scst(self, images, captions, rewards, seed=None, lr=None):
+        """images: the k-times tiled batch of train_fn.py:251 (or None to reuse the features of the
+        last `sample()` of the shared model, repeated k times)."""
+        c, eng, tr = self._config, self.engine, self.trainer
+        if images is not None:
+            images = eng.torch.as_tensor(images).to(eng.device, non_blocking=True)
+            im_embed, fm = eng.encode(images)
+        else:
+            raise ValueError('images required')
+        captions = np.asarray(captions)
+        masks, keeps = None, (1.0, 1.0, 1.0)
+        if seed is not None:
+            from .train import process_inputs
+            lens = process_inputs(captions, c.token_type)[3]
+            masks, keeps = tr.make_masks(fm.shape[0], int(lens.max()), seed)
+        out = tr.forward_backward(fm, im_embed, captions, np.asarray(rewards, np.float32), masks, keeps)
+        tr.apply_gradients(lr)
+        return out['loss'][1]
 
 
 def synthetic_images(batch, seed=0):

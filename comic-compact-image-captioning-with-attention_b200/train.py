@@ -129,16 +129,8 @@ class Trainer(object):
     def apply_gradients(self, lr=None):
         """NCCL all-reduce (mean over ranks) + TF-form Adam + repack (model_base.py:387-401)."""
         c, eng = self.c, self.engine
-        world = 1
-        dist = None
-        try:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                world = dist.get_world_size()
-        except Exception:
-            world = 1
-        if world > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        from .parallel import allreduce_sum_
+        world = allreduce_sum_(self.grads)
         self.global_step += 1
         if lr is None:
             lr = cosine_lr(self.global_step - 1, c.max_step, c.lr_start, c.lr_end)

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Training throughput (BASELINE.json configs 3 and 5) on N GPUs, one process per GPU.
+
+    python scripts/bench_train.py --mode decoder --batch 32 --steps 20
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/bench_train.py --mode scst --batch 10 --steps 10
+
+decoder: frozen-CNN encoder forward + teacher-forced fwd/bwd (T = 41 radix steps, every row
+full length, seeded Philox dropout) + NCCL all-reduce of the flat gradient + Adam.
+scst: greedy + beam-7 sampling (40 steps), host CIDEr-D/BLEU reward, weighted-XE step.
+Prints one JSON line on rank 0 (device-timed, max over ranks).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--mode', default='decoder', choices=['decoder', 'scst'])
+    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import comic_b200  # noqa: F401
+    from comic_b200 import configuration as conf, weights as wts, scst as S
+    from comic_b200.train import Trainer
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    c = conf.make_config(train_mode=args.mode, batch_size_train=args.batch, max_step=100000)
+    W = wts.init_weights(c, seed=c.rand_seed, cnn_init='he')
+    tr = Trainer(c, W)
+    eng = tr.engine
+    B = args.batch
+    g = torch.Generator().manual_seed(100 + rank)
+    images = torch.empty((B, 224, 224, 3)).uniform_(-1, 1, generator=g).to(eng.device)
+    rng = np.random.default_rng(rank)
+    if args.mode == 'decoder':
+        caps = np.concatenate([np.full((B, 1), 256), rng.integers(0, 256, size=(B, 40)), np.full((B, 1), 257)],
+                              axis=1).astype(np.int32)                     # L = 42 -> T = 41, mask all ones
+
+        def step(i):
+            return tr.step(images, caps, None, seed=1000 + i)
+    else:
+        refs = [[' '.join('w%d' % w for w in rng.integers(0, 997, size=10)) for _ in range(5)] for _ in range(B)]
+        df = {'document_frequency': S.compute_doc_freq(refs), 'ref_len': B}
+        scorer = S.CaptionScorer(df, dict(ciderD=c.scst_weight_ciderD, bleu=c.scst_weight_bleu))
+
+        def step(i):
+            return S.scst_step(tr, scorer, images, refs, seed=1000 + i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for i in range(args.warmup):
+        out = step(i)
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        out = step(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'train steps/sec COMIC-256 train_mode=%s' % args.mode, 'value': args.steps / (ms * 1e-3),
+            'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'examples_per_sec': args.steps * B * world / (ms * 1e-3),
+            'scaling': 'weak', 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'COMIC-256 %s, batch %d/GPU' % (args.mode, B),
+                       'allreduce_bytes': int(tr.n_flat * 4)},
+            'loss': [float(x) for x in out['loss'].cpu().tolist()],
+            'gpu_launches': int(eng.launch_count() - l0)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -60,9 +60,47 @@ def encoder_case():
     return dict(im_embed=emb, fm_sample=fm[:, ::7, ::13].copy(), fm_sum=np.float64(fm.astype(np.float64).sum()))
 
 
+def scst_sentences(seed=11, n_img=6, n_ref=5, n_hyp=3, vocab=40):
+    """Random short sentences over a small vocabulary (so n-grams overlap)."""
+    rng = np.random.default_rng(seed)
+    mk = lambda: ' '.join('w%d' % w for w in rng.integers(0, vocab, size=int(rng.integers(3, 12))))
+    refs = [[mk() for _ in range(n_ref)] for _ in range(n_img)]
+    hyps = []
+    for i in range(n_img):
+        for j in range(n_hyp):
+            base = refs[i][j % n_ref].split()
+            keep = [w for w in base if rng.uniform() < 0.7] or base[:1]
+            hyps.append(' '.join(keep + ['w%d' % rng.integers(0, vocab)]))
+    hyps.append('')                                           # empty hypothesis edge case
+    return refs, hyps
+
+
+def ciderd_case():
+    """CIDEr-D scores from the REFERENCE's own scorer (the one module of /root/reference that
+    imports under Python 3), cached-DF mode (the mode train_fn_scst uses).  Needs /root/reference."""
+    import pickle
+    import tempfile
+    sys.path.insert(0, '/root/reference/common/scst/cider_ruotianluo')
+    from pyciderevalcap.ciderD.ciderD import CiderD as RefCiderD
+    from comic_b200 import scst as S
+    refs, hyps = scst_sentences()
+    n_img = len(refs)
+    gts = {i: refs[i % n_img] for i in range(len(hyps))}
+    res = {i: [hyps[i]] for i in range(len(hyps))}
+    df = S.compute_doc_freq(refs)
+    with tempfile.NamedTemporaryFile(suffix='.p', delete=False) as f:
+        pickle.dump({'document_frequency': df, 'ref_len': n_img}, f, 2)
+        path = f.name
+    mean_c, sc_c = RefCiderD(df=path).compute_score(gts, res)     # (df='corpus' raises in the reference: copy_empty)
+    os.unlink(path)
+    return dict(cached=np.asarray(sc_c, np.float64), mean_cached=np.float64(mean_c))
+
+
 def main():
     np.savez_compressed(os.path.join(HERE, 'decoder_beam_comic256.npz'), **decoder_beam_case())
     np.savez_compressed(os.path.join(HERE, 'encoder_2img.npz'), **encoder_case())
+    if os.path.isdir('/root/reference'):
+        np.savez_compressed(os.path.join(HERE, 'ciderd_reference.npz'), **ciderd_case())
     print('wrote fixtures to', HERE)
 
 

@@ -128,3 +128,61 @@ def test_training_steps_reduce_loss(torch_mod):
         tr.apply_gradients(lr=5e-3)
     assert losses[-1] < losses[0] - 0.05, losses
     assert all(np.isfinite(losses))
+
+
+def _synthetic_refs(B, n_words=1000, seed=0):
+    """5 random 10-word reference sentences per image over a 1,000-word vocabulary."""
+    rng = np.random.default_rng(seed)
+    return [[' '.join('w%d' % w for w in rng.integers(0, n_words - 3, size=10)) for _ in range(5)] for _ in range(B)]
+
+
+def test_scst_step_end_to_end(torch_mod):
+    """train_fn.py:218-256 on the GPU path: greedy + beam-k sampling equals the oracle's decodes,
+    rewards = weighted CIDEr-D + BLEU-4 of the decoded strings, weighted-XE step runs."""
+    import comic_oracle as O
+    import inception_v1_oracle as I
+    from comic_b200 import scst as S
+    from comic_b200.train import Trainer
+    from _common import images
+    c = comic_config(train_mode='scst', scst_beam_size=3, n_words=1000, max_step=50)
+    W = make_weights(c)
+    B = 2
+    img = images(B, seed=12)
+    refs = _synthetic_refs(B)
+    df = {'document_frequency': S.compute_doc_freq(refs), 'ref_len': B}
+    scorer = S.CaptionScorer(df, dict(ciderD=c.scst_weight_ciderD, bleu=c.scst_weight_bleu))
+    tr = Trainer(c, W)
+    eng = tr.engine
+    before = tr.params.clone()
+    cap_beam, cap_greedy, im_embed, fm = S.sample_captions(eng, c, eng.to_dev(img), 3, max_length=4)
+    o_emb, o_fm, _ = I.encoder(img, W, c)
+    rb = O.beam_search_decode(O.Decoder(W, c), o_emb, o_fm, 3, 0.0, 8)
+    rg = O.greedy_decode(O.Decoder(W, c), o_emb, o_fm, 8)
+    np.testing.assert_array_equal(cap_beam.cpu().numpy(), rb['predicted_ids'].transpose(2, 1, 0))
+    np.testing.assert_array_equal(cap_greedy.cpu().numpy(), rg['ids'].T)
+    out = S.scst_step(tr, scorer, eng.to_dev(img), refs, seed=3, lr=1e-3)
+    assert out['rewards'].shape == (B * 3,) and np.isfinite(out['rewards']).all()
+    np.testing.assert_allclose(out['rewards'], out['sc_sample'] - out['sc_greedy'], rtol=1e-6)
+    loss = out['loss'].cpu().numpy()
+    assert np.isfinite(loss).all()
+    assert tr.global_step == 1 and not torch_mod.equal(before, tr.params)
+
+
+def test_caption_model_train_and_eval_surface(torch_mod):
+    from comic_b200.model import CaptionModel
+    from _common import images
+    c = comic_config(train_mode='decoder', max_step=20)
+    W = make_weights(c)
+    m_train = CaptionModel(c, 'train', weights=W)
+    m_eval = CaptionModel(c, 'eval', reuse=True, share=m_train)
+    m_infer = CaptionModel(c, 'infer', reuse=True, share=m_train)
+    _, _, _, caps, _, _ = _train_case(c, B=3, L=7, seed=1, dropout=False)
+    img = images(3, seed=2)
+    p0 = float(m_eval.eval_step(img, caps).item())
+    for _ in range(3):
+        ppl, gs = m_train.train_step(img, caps, seed=11, lr=3e-3)
+    assert gs == 3
+    p1 = float(m_eval.eval_step(img, caps).item())
+    assert p1 < p0
+    preds, attn = m_infer.run(img)                       # shares the updated variables
+    assert preds.shape[0] == 3 and attn.shape[:2] == (3, 8)
