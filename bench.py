@@ -40,8 +40,8 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=512, help='images per GPU per step')
     ap.add_argument('--beam', type=int, default=3)
     ap.add_argument('--workload', default='comic256', choices=['comic256', 'word'])
-    ap.add_argument('--ref-batch', type=int, default=8, help='images per step of the CPU reference arm')
-    ap.add_argument('--cpu-sample', type=int, default=4, help='images of the cpu_baseline sample')
+    ap.add_argument('--ref-batch', type=int, default=32, help='images per step of the CPU reference arm')
+    ap.add_argument('--cpu-sample', type=int, default=96, help='images of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='split', choices=['f32', 'split', 'fast'],
                     help='engine arithmetic mode (include/comic_b200.h comic_set_precision)')
@@ -350,7 +350,8 @@ def run_ours(args):
         roof.update({'traffic': load_traffic(dominant), 'kernel': dominant, 'launches': dom_n,
                      'avg_launch_us': avg_s * 1e6, 'share_of_step': dom_ms / ms_total,
                      'peak_source': peaks['which'] + (' sustained' if kind == 'flop' else ''),
-                     'arithmetic': 'fp32 FFMA (exact-parity path)' if kind == 'flop' else 'fp32'})
+                     'arithmetic': {'f32': 'fp32 FFMA', 'split': 'tcgen05 bf16x3 operand split, fp32 accumulate (fp32-equivalent)',
+                                    'fast': 'tcgen05 bf16x3 + tanh.approx'}[args.precision] if kind == 'flop' else 'fp32'})
         caps = B * world * args.steps
         line = {
             'metric': METRIC, 'value': caps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world,
