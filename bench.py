@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precision', default='split', choices=['f32', 'split', 'fast'],
                     help='engine arithmetic mode (include/comic_b200.h comic_set_precision)')
+    ap.add_argument('--opt', action='append', default=[], help='engine tunable name=value (Engine.set_option)')
     ap.add_argument('--breakdown', action='store_true', help='also print a per-kernel-class time table to stderr')
     return ap.parse_args()
 
@@ -208,6 +209,14 @@ def algorithmic_work(tag, eng, B, beam, T):
         return (B * d.M * d.VAL * 4.0 + 2.0 * N * d.H * d.M * 4.0 + N * d.A * 4.0) * T, 'byte'
     if tag == 'beam':
         return (N * d.V * 4.0 + N * 32.0) * T, 'byte'
+    if tag == 'persist':
+        # per decode step the weights once, the keys (and values) once per IMAGE, the
+        # recurrent state read + written, the alignment history and the selection outputs
+        KX = d.W + d.A + d.R
+        wts_elems = KX * 4 * d.R + 4 * d.R + d.R * d.R + 3 * d.R + 1 + d.R * d.V + d.V
+        per_step = (wts_elems * 4.0 + B * d.M * d.R * 4.0 + (0.0 if d.fm_projection == 'tied' else B * d.M * d.VAL * 4.0)
+                    + 2.0 * N * (2 * d.R + d.A + d.W) * 4.0 + N * d.H * d.M * 4.0 + N * 12.0)
+        return per_step * T, 'byte'
     if tag == 'lstm':
         return (N * 4 * d.R * 4.0 + 3.0 * N * d.R * 4.0) * T, 'byte'
     return 0.0, 'byte'
@@ -262,6 +271,9 @@ def run_ours(args):
     eng = Engine(c)
     eng.bind_weights(W)
     eng.set_precision(args.precision)
+    for kv in args.opt:
+        name, value = kv.split('=')
+        eng.set_option(name, int(value))
     model = CaptionModel(c, 'infer', batch_ops=None, engine=eng)
     B, beam = args.batch, args.beam
     T = model._maximum_iterations()
@@ -314,7 +326,8 @@ def run_ours(args):
     launches = eng.launch_count() - launches0
     dom_ms, dom_n = eng.profile_read(dominant)
     eng.profile_enable([])
-    T_exec = int(r['T'].item())
+    from comic_b200.engine import executed_steps
+    T_exec = executed_steps(r['T'])
 
     # ---- timed region 2: end to end through CaptionModel.run from pinned host memory
     for _ in range(2):
@@ -370,7 +383,7 @@ def run_ours(args):
             'clocks': sampler.summary(),
             'kernel_ms_per_step': {t: round(table[t][0], 3) for t in KERNEL_TAGS if table[t][1]},
         }
-        dec_ms = sum(table[t][0] for t in ('gates', 'lstm', 'lq', 'scores', 'ctx', 'beam'))
+        dec_ms = sum(table[t][0] for t in ('gates', 'lstm', 'lq', 'scores', 'ctx', 'beam', 'persist'))
         line['decoder_step_us'] = dec_ms * 1e3 / max(T_exec, 1)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count()

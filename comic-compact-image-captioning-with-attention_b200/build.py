@@ -9,8 +9,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIB = os.path.join(HERE, 'libcomic_b200.so')
-SOURCES = ['api.cu', 'encoder.cu', 'decoder.cu', 'train.cu']
+LIB = os.path.join(HERE, os.environ.get('COMIC_B200_LIBNAME', 'libcomic_b200.so'))   # env: experiment builds only
+_OBJ_PREFIX = (os.path.splitext(os.path.basename(LIB))[0] + '_') if 'COMIC_B200_LIBNAME' in os.environ else ''
+SOURCES = ['api.cu', 'encoder.cu', 'decoder.cu', 'persistent.cu', 'train.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC']
 
@@ -37,8 +38,8 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace('.cu', '.o'))
-        cmd = [_nvcc()] + NVCC_FLAGS + ['-c', os.path.join(CSRC, s), '-o', o]
+        o = os.path.join(CSRC, _OBJ_PREFIX + s.replace('.cu', '.o'))
+        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get('COMIC_B200_NVCC_EXTRA', '').split() + ['-c', os.path.join(CSRC, s), '-o', o]
         if verbose:
             cmd += ['-Xptxas', '-v']
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -139,6 +139,13 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
   COMIC_REQUIRE(h, COMIC_E_BADARG, "set_option: null handle");
   switch (option) {
     case COMIC_OPT_FUSED_ATTN_MIN_IMAGES: h->fused_min_images = value; return COMIC_OK;
+    case COMIC_OPT_PERSISTENT_MAX_ROWS: h->persist_max_rows = value; return COMIC_OK;
+    case COMIC_OPT_ENC_CHUNK_STEM:
+    case COMIC_OPT_ENC_CHUNK_28:
+    case COMIC_OPT_ENC_CHUNK_14:
+      COMIC_REQUIRE(value >= 1, COMIC_E_BADARG, "set_option: encoder chunk must be >= 1");
+      h->enc_chunk[option - COMIC_OPT_ENC_CHUNK_STEM] = value;
+      return COMIC_OK;
     default: break;
   }
   set_error("set_option: unknown option %d", option);

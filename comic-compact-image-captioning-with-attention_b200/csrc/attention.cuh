@@ -90,7 +90,12 @@ struct AttnArgs {
   int t, n_rows;
 };
 
-constexpr int kAttnThreads = 768;
+#ifndef COMIC_ATTN_THREADS
+#define COMIC_ATTN_THREADS 384
+#endif
+constexpr int kAttnThreads = COMIC_ATTN_THREADS;   // 384: two co-resident CTAs per SM (finer image granularity; measured 146 vs 160 us
+                                                   // per step at 512 images against 768 threads / one CTA per SM)
+constexpr int kAttnMinBlocks = (kAttnThreads <= 384) ? 2 : 1;
 constexpr int kAttnRing = 2;        // key-row slots per warp (prefetch distance 1)
 constexpr int kAttnBeamChunk = 4;
 
@@ -105,7 +110,8 @@ __host__ __device__ inline AttnSmem attn_smem_layout(int k, int R, int H, int M,
   L.nsplit = kAttnThreads / L.tpc;
   if (L.nsplit < 1) L.nsplit = 1;
   int red = (L.nsplit - 1) * kAttnBeamChunk * VAL;   // phase-3 partial sums alias the query block
-  L.qfloats = k * R > red ? k * R : red;
+  int qf = 2 * k * R + ((k + 31) & ~31);           // centred queries | * gamma' | sum of squares
+  L.qfloats = qf > red ? qf : red;
   L.sfloats = (k * H * M + 3) & ~3;
   // + LN constants [3][R] + per-warp key-row ring (cp.async staging, lane-private layout)
   L.bytes = ((size_t)L.qfloats + (size_t)L.sfloats + 3 * (size_t)R + (size_t)(kAttnThreads / 32) * kAttnRing * R) *
@@ -113,76 +119,78 @@ __host__ __device__ inline AttnSmem attn_smem_layout(int k, int R, int H, int M,
   return L;
 }
 
-// scores of one position against KB beams (add_LN).  kc = centred key slice of this lane;
-// qs = lane-permuted centred queries; cs = lane-permuted constants [gamma' | beta' | vv].
+// scores of one position against KB beams (add_LN).
+//   kc = centred key slice of this lane, kg = kc * gamma' (gamma' = gamma * 2 log2 e; FAST: gamma);
+//   qs / qgs = lane-permuted centred queries and centred queries * gamma';
+//   sqq[j] = sum_c qc_j[c]^2, skk = sum_c kc[c]^2 (both warp-uniform);
+//   cs = lane-permuted constants [gamma' (used by the caller for kg) | beta' | vv].
+// Both operands are centred, so sum_c (kc+qc) = 0 and the LN variance is
+//   (skk + sqq + 2 <kc, qc>) / R  -- one FFMA per element instead of add + FFMA,
+// and the normalised argument is  y' = rstd * (kg + qg) + beta'  -- add + FFMA.
+// tanh(y) = 1 - 2/(2^y' + 1); the four reciprocals of a float4 share ONE MUFU.RCP with the
+// v-weights folded into the numerators:
+//   sum_e vv_e / x_e = (p23 (vv0 x1 + vv1 x0) + p01 (vv2 x3 + vv3 x2)) / (p01 p23),  p01 = x0 x1, p23 = x2 x3
+// (y' clamped at 30, products <= 2^120).  Per element: 7.5 FP32 + 1.25 MUFU instructions, which
+// balances the FMA-pipe issue rate against the MUFU pipe (8 clk per warp instruction).
 template <int CPL, int KB, bool FAST>
-__device__ __forceinline__ void ln_tanh_scores(const float (&kc)[CPL], const float* __restrict__ qs,
-                                               const float* __restrict__ cs, int R, int lane, float sv,
-                                               float inv_R, float (&out)[KB]) {
+__device__ __forceinline__ void ln_tanh_scores(const float (&kc)[CPL], const float (&kg)[CPL],
+                                               const float* __restrict__ qs, const float* __restrict__ qgs,
+                                               const float* __restrict__ cs, const float* __restrict__ sqq, float skk,
+                                               int R, int lane, float sv, float inv_R, float (&out)[KB]) {
   constexpr int G4 = CPL / 4;
-  float ss[KB];
+  float dot[KB];
 #pragma unroll
-  for (int j = 0; j < KB; ++j) ss[j] = 0.f;
+  for (int j = 0; j < KB; ++j) dot[j] = 0.f;
 #pragma unroll
   for (int g = 0; g < G4; ++g) {
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
-      float4 q = *reinterpret_cast<const float4*>(qs + (size_t)j * R + (g * 32 + lane) * 4);
-      float d0 = kc[g * 4 + 0] + q.x, d1 = kc[g * 4 + 1] + q.y, d2 = kc[g * 4 + 2] + q.z, d3 = kc[g * 4 + 3] + q.w;
-      ss[j] = fmaf(d0, d0, ss[j]); ss[j] = fmaf(d1, d1, ss[j]);
-      ss[j] = fmaf(d2, d2, ss[j]); ss[j] = fmaf(d3, d3, ss[j]);
+      const float4 q = *reinterpret_cast<const float4*>(qs + (size_t)j * R + (g * 32 + lane) * 4);
+      dot[j] = fmaf(kc[g * 4 + 0], q.x, dot[j]); dot[j] = fmaf(kc[g * 4 + 1], q.y, dot[j]);
+      dot[j] = fmaf(kc[g * 4 + 2], q.z, dot[j]); dot[j] = fmaf(kc[g * 4 + 3], q.w, dot[j]);
     }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
 #pragma unroll
-    for (int j = 0; j < KB; ++j) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], o);
+    for (int j = 0; j < KB; ++j) dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
   }
   float rstd[KB];
 #pragma unroll
   for (int j = 0; j < KB; ++j) {
-    rstd[j] = rsqrtf(ss[j] * inv_R + 1e-12f);
+    const float ss = fmaxf(fmaf(2.0f, dot[j], skk + sqq[j]), 0.f);
+    rstd[j] = rsqrtf(ss * inv_R + 1e-12f);
     out[j] = FAST ? 0.f : sv;
   }
 #pragma unroll
   for (int g = 0; g < G4; ++g) {
-    const float4 gm = *reinterpret_cast<const float4*>(cs + (g * 32 + lane) * 4);
     const float4 bt = *reinterpret_cast<const float4*>(cs + R + (g * 32 + lane) * 4);
     const float4 vv = *reinterpret_cast<const float4*>(cs + 2 * R + (g * 32 + lane) * 4);
-    const float ga[4] = {gm.x, gm.y, gm.z, gm.w}, ba[4] = {bt.x, bt.y, bt.z, bt.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
-      float4 q = *reinterpret_cast<const float4*>(qs + (size_t)j * R + (g * 32 + lane) * 4);
-      const float qa[4] = {q.x, q.y, q.z, q.w};
-      float y[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) y[e] = fmaf((kc[g * 4 + e] + qa[e]) * rstd[j], ga[e], ba[e]);
+      const float4 q = *reinterpret_cast<const float4*>(qgs + (size_t)j * R + (g * 32 + lane) * 4);
+      const float y0 = fmaf(kg[g * 4 + 0] + q.x, rstd[j], bt.x), y1 = fmaf(kg[g * 4 + 1] + q.y, rstd[j], bt.y);
+      const float y2 = fmaf(kg[g * 4 + 2] + q.z, rstd[j], bt.z), y3 = fmaf(kg[g * 4 + 3] + q.w, rstd[j], bt.w);
       if (FAST) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) out[j] = fmaf(tanh_approx(y[e]), va[e], out[j]);
+        out[j] = fmaf(tanh_approx(y0), vv.x, out[j]); out[j] = fmaf(tanh_approx(y1), vv.y, out[j]);
+        out[j] = fmaf(tanh_approx(y2), vv.z, out[j]); out[j] = fmaf(tanh_approx(y3), vv.w, out[j]);
       } else {
-        // tanh = 1 - 2/(2^y' + 1), y' pre-scaled by 2 log2 e and clamped at 30 (tanh == 1 in fp32 there);
-        // the four reciprocals share ONE MUFU.RCP: 1/x_i = (prod of the others) / (x0 x1 x2 x3), products
-        // <= 2^124.  The kernel is MUFU-bound, so 1.25 instead of 2 MUFU per element is a 1.6x win.
-        float x[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) x[e] = ex2_approx(fminf(y[e], 30.0f)) + 1.0f;
-        const float p01 = x[0] * x[1], p23 = x[2] * x[3];
+        const float x0 = ex2_approx(fminf(y0, 30.0f)) + 1.0f, x1 = ex2_approx(fminf(y1, 30.0f)) + 1.0f;
+        const float x2 = ex2_approx(fminf(y2, 30.0f)) + 1.0f, x3 = ex2_approx(fminf(y3, 30.0f)) + 1.0f;
+        const float n01 = fmaf(x0, vv.y, x1 * vv.x), n23 = fmaf(x2, vv.w, x3 * vv.z);
+        const float p01 = x0 * x1, p23 = x2 * x3;
         const float rp = rcp_approx(p01 * p23);
-        const float r01 = rp * p23, r23 = rp * p01;
-        out[j] = fmaf(r01 * x[1], va[0], out[j]);
-        out[j] = fmaf(r01 * x[0], va[1], out[j]);
-        out[j] = fmaf(r23 * x[3], va[2], out[j]);
-        out[j] = fmaf(r23 * x[2], va[3], out[j]);
+        out[j] = fmaf(rp, fmaf(p01, n23, p23 * n01), out[j]);
       }
     }
   }
 }
 
-// dynamic shared memory: q_c [k][R] (lane-permuted) | alpha [k][H][M] | LN constants [3][R] | key ring [warps][2][R];
+// dynamic shared memory: q_c [k][R], q_c*gamma' [k][R] (lane-permuted), sqq [k] | alpha [k][H][M] | LN constants [3][R] |
+// key ring [warps][2][R];
 // phase-3 partials alias q_c
 template <int R, int H, int MODE, bool FAST, int KB>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, kAttnMinBlocks)
 attn_fused_kernel(const AttnArgs a) {
   if (a.fin_count != nullptr && a.t > 0 && a.fin_count[a.t - 1] >= a.n_rows) return;
   constexpr int CPL = R / 32;      // contiguous channels per lane
@@ -204,7 +212,9 @@ attn_fused_kernel(const AttnArgs a) {
   float* ring = sm_c + 3 * R + (size_t)warp * kAttnRing * R;   // this warp's key-row slots
   const int c0 = lane * CPL;                        // first channel of this lane
 
-  // ---- queries: load, centre (add_LN), store lane-permuted ----
+  // ---- queries: load, centre (add_LN), store lane-permuted (+ gamma'-scaled copy and sum of squares) ----
+  float* sm_qg = sm_q + (size_t)k * R;               // [k][G4][32] float4: centred queries * gamma'
+  float* sm_sqq = sm_q + 2 * (size_t)k * R;          // [k]
   for (int beam = warp; beam < k; beam += NW) {
     const float* q = a.lq + (size_t)(b * k + beam) * a.ld_lq + a.q_off + c0;
     float4 v[G4];
@@ -215,10 +225,22 @@ attn_fused_kernel(const AttnArgs a) {
       s += (v[g].x + v[g].y) + (v[g].z + v[g].w);
     }
     float mean = (MODE == 0) ? wsum(s) * (1.0f / R) : 0.f;
+    float sq = 0.f;
 #pragma unroll
     for (int g = 0; g < G4; ++g) {
       float4 c = make_float4(v[g].x - mean, v[g].y - mean, v[g].z - mean, v[g].w - mean);
       *reinterpret_cast<float4*>(sm_q + (size_t)beam * R + (g * 32 + lane) * 4) = c;
+      if (MODE == 0) {
+        sq = fmaf(c.x, c.x, sq); sq = fmaf(c.y, c.y, sq); sq = fmaf(c.z, c.z, sq); sq = fmaf(c.w, c.w, sq);
+        const float sc = FAST ? 1.0f : kTwoLog2e;
+        const float4 g4 = ldg4(a.gamma + c0 + g * 4);
+        *reinterpret_cast<float4*>(sm_qg + (size_t)beam * R + (g * 32 + lane) * 4) =
+            make_float4(c.x * (g4.x * sc), c.y * (g4.y * sc), c.z * (g4.z * sc), c.w * (g4.w * sc));
+      }
+    }
+    if (MODE == 0) {
+      sq = wsum(sq);
+      if (lane == 0) sm_sqq[beam] = sq;
     }
   }
   // LN constants (add_LN) in the lane-permuted layout: gamma', beta' pre-scaled by 2 log2(e);
@@ -261,7 +283,8 @@ attn_fused_kernel(const AttnArgs a) {
   stage_row(warp, 0);
   int slot = 0;
   for (int m = warp; m < M; m += NW) {
-    float kc[CPL];
+    float kc[CPL], kg[CPL];
+    float skk = 0.f;
     cp_async_wait<0>();
     {
       const float* src = ring + (size_t)slot * R + lane * 4;
@@ -274,8 +297,19 @@ attn_fused_kernel(const AttnArgs a) {
       }
       if (MODE == 0) {
         float mean = wsum(s) * (1.0f / R);
+        float sq = 0.f;
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) kc[c] -= mean;
+        for (int c = 0; c < CPL; ++c) {
+          kc[c] -= mean;
+          sq = fmaf(kc[c], kc[c], sq);
+        }
+        skk = wsum(sq);
+#pragma unroll
+        for (int g = 0; g < G4; ++g) {
+          const float4 gm = *reinterpret_cast<const float4*>(sm_c + (g * 32 + lane) * 4);
+          kg[g * 4 + 0] = kc[g * 4 + 0] * gm.x; kg[g * 4 + 1] = kc[g * 4 + 1] * gm.y;
+          kg[g * 4 + 2] = kc[g * 4 + 2] * gm.z; kg[g * 4 + 3] = kc[g * 4 + 3] * gm.w;
+        }
       }
     }
     slot ^= 1;
@@ -286,7 +320,8 @@ attn_fused_kernel(const AttnArgs a) {
       float part[KB];
       const float* qs = sm_q + (size_t)bs * R;
       if (MODE == 0) {
-        ln_tanh_scores<CPL, KB, FAST>(kc, qs, sm_c, R, lane, sv, 1.0f / R, part);
+        ln_tanh_scores<CPL, KB, FAST>(kc, kg, qs, sm_qg + (size_t)bs * R, sm_c, sm_sqq + bs, skk, R, lane, sv,
+                                      1.0f / R, part);
       } else {
 #pragma unroll
         for (int j = 0; j < KB; ++j) {

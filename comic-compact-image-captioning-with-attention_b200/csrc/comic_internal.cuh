@@ -57,7 +57,7 @@ struct Packed {
 }  // namespace comic
 
 namespace comic {
-enum Tag { T_CONV = 0, T_POOL, T_PROJECT, T_INIT, T_GATES, T_LSTM, T_LQ, T_SCORES, T_CTX, T_BEAM, T_FINAL, T_MISC, T_COUNT };
+enum Tag { T_CONV = 0, T_POOL, T_PROJECT, T_INIT, T_GATES, T_LSTM, T_LQ, T_SCORES, T_CTX, T_BEAM, T_FINAL, T_MISC, T_PERSIST, T_COUNT };
 constexpr int kMaxProfEvents = 16384;
 }  // namespace comic
 
@@ -70,6 +70,8 @@ struct comic_handle_s {
   bool bound = false, cnn_bound = false;
   int precision = 1;   // 0: fp32 FFMA everywhere; 1: tcgen05 split-precision GEMMs with M >= 128; 2: 1 + tanh.approx
   int fused_min_images = 48;   // fused attention kernel (one CTA per image) from this batch size on
+  int persist_max_rows = 32;   // whole decode loop as one cooperative kernel up to this many rows (0 = off)
+  int enc_chunk[3] = {64, 256, 512};   // images per encoder chunk: stem / 28x28 blocks / 14x14 + 7x7 blocks
   comic::Packed pk;
   int64_t launches = 0;
   // optional per-kernel-class device timing (bench.py roofline): CUDA events
@@ -168,5 +170,25 @@ void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_ma
 int decoder_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes);
 int decoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry);
 int decoder_configure();
+
+// persistent.cu: the whole decode loop in one cooperative launch (small row counts)
+struct PersistCall {
+  const float *keys, *values, *c0, *h0;
+  int B, k, max_it, greedy;
+  float lpw;
+  float *c[2], *h[2], *ctx[2];
+  float *lq, *scores, *hist;
+  int *tok, *src;
+  float* cum;
+  uint8_t* fin;
+  long long* len;
+  int* fin_count;
+  int *step_ids, *parents;
+  float* sc;
+  float* logits_out;
+  unsigned* bar;   // [2]: barrier counter, abort flag
+};
+bool persist_applicable(comic_handle_t h, int B, int k, bool greedy);
+int decode_persistent(comic_handle_t h, const PersistCall& pc, cudaStream_t st);
 
 }  // namespace comic

@@ -21,29 +21,9 @@
 
 #include "attention.cuh"
 #include "comic_internal.cuh"
+#include "search_steps.cuh"
 
 namespace comic {
-
-// ---------------------------------------------------------------------------
-// Small helpers.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// Loop gate: step t runs only while not every row had finished after step t-1.
-__device__ __forceinline__ bool step_stopped(const int* fin_count, int t, int n_rows) {
-  return fin_count != nullptr && t > 0 && fin_count[t - 1] >= n_rows;
-}
 
 // ---------------------------------------------------------------------------
 // D3: BasicLSTMCell pointwise part.  gates = sum of split-K partials [nz][N][4R]
@@ -73,8 +53,8 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gp, int nz, size
     int r = src ? src[n] : n;
     if (r >= 0 && r < src_limit) cp = c_prev[(size_t)r * R + j];
   }
-  float cn = cp * sigmoidf_(g[2] + 1.0f) + sigmoidf_(g[0]) * tanhf(g[1]);
-  float hn = tanhf(cn) * sigmoidf_(g[3]);
+  float cn, hn;
+  lstm_cell(g[0], g[1], g[2], g[3], cp, &cn, &hn);
   c_new[i] = cn;
   h_new[i] = hn;
   if (h_drop) h_drop[i] = out_mask ? (hn / out_keep) * out_mask[i] : hn;
@@ -301,19 +281,8 @@ attn_ctx_kernel(const float* __restrict__ scores, const float* __restrict__ valu
 }
 
 // ---------------------------------------------------------------------------
-// K10: TF r1.9 _beam_search_step, one CTA per image.
+// K10: TF r1.9 _beam_search_step, one CTA per image (body: search_steps.cuh).
 // ---------------------------------------------------------------------------
-struct BestPair { float v; int i; };
-
-__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
-  // descending value, ties -> lower flat index (nn.top_k)
-  return (v > bv) || (v == bv && i < bi);
-}
-
-__device__ __forceinline__ float length_penalty_dev(long long len, float w) {
-  return powf(5.0f + (float)len, w) / powf(6.0f, w);
-}
-
 __global__ void __launch_bounds__(256)
 beam_step_kernel(const float* __restrict__ logits, int ld, int k, int V, int eos, float lpw,
                  float* __restrict__ log_probs, uint8_t* __restrict__ finished, long long* __restrict__ lengths,
@@ -324,111 +293,13 @@ beam_step_kernel(const float* __restrict__ logits, int ld, int k, int V, int eos
     if (blockIdx.x == 0 && threadIdx.x == 0) fin_count[t] = n_rows;
     return;
   }
-  constexpr int KMAX = 16;
-  __shared__ float s_max[KMAX], s_lse[KMAX], s_cum[KMAX];
-  __shared__ unsigned char s_fin[KMAX];
-  __shared__ long long s_len[KMAX];
-  __shared__ float s_rv[8];
-  __shared__ int s_ri[8];
-  __shared__ float s_selv[KMAX];
-  __shared__ int s_seli[KMAX];
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < k) {
-    s_cum[tid] = log_probs[b * k + tid];
-    s_fin[tid] = finished[b * k + tid];
-    s_len[tid] = lengths[b * k + tid];
-  }
-  // log-softmax statistics per beam row: max, log(sum(exp(x - max)))
-  for (int j = 0; j < k; ++j) {
-    const float* row = logits + (size_t)(b * k + j) * ld;
-    float mx = -INFINITY;
-    for (int i = tid; i < V; i += 256) mx = fmaxf(mx, row[i]);
-    mx = warp_max(mx);
-    if (lane == 0) s_rv[warp] = mx;
-    __syncthreads();
-    float m2 = s_rv[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) m2 = fmaxf(m2, s_rv[w]);
-    __syncthreads();
-    float sm = 0.f;
-    for (int i = tid; i < V; i += 256) sm += expf(row[i] - m2);
-    sm = warp_sum(sm);
-    if (lane == 0) s_rv[warp] = sm;
-    __syncthreads();
-    if (tid == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < 8; ++w) tot += s_rv[w];
-      s_max[j] = m2;
-      s_lse[j] = logf(tot);
-    }
-    __syncthreads();
-  }
-  const int ncand = k * V;
-  auto total_of = [&](int idx) -> float {
-    int j = idx / V, w = idx - j * V;
-    float lp;
-    if (s_fin[j]) lp = (w == eos) ? 0.0f : -FLT_MAX;
-    else lp = (logits[(size_t)(b * k + j) * ld + w] - s_max[j]) - s_lse[j];
-    return s_cum[j] + lp;
-  };
-  auto score_of = [&](int idx, float tot) -> float {
-    if (lpw == 0.0f) return tot;
-    int j = idx / V, w = idx - j * V;
-    long long len = s_len[j] + ((!s_fin[j] && w != eos) ? 1 : 0);
-    return tot / length_penalty_dev(len, lpw);
-  };
-  float pv = INFINITY;
-  int pi = -1;
-  for (int sel = 0; sel < k; ++sel) {
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int idx = tid; idx < ncand; idx += 256) {
-      float sc = score_of(idx, total_of(idx));
-      bool eligible = (sc < pv) || (sc == pv && idx > pi);
-      if (eligible && better(sc, idx, bv, bi)) { bv = sc; bi = idx; }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-    }
-    if (lane == 0) { s_rv[warp] = bv; s_ri[warp] = bi; }
-    __syncthreads();
-    bv = s_rv[0]; bi = s_ri[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w)
-      if (better(s_rv[w], s_ri[w], bv, bi)) { bv = s_rv[w]; bi = s_ri[w]; }
-    __syncthreads();
-    pv = bv; pi = bi;
-    if (tid == 0) { s_selv[sel] = bv; s_seli[sel] = bi; }
-  }
-  __syncthreads();
-  if (tid < k) {
-    int idx = s_seli[tid];
-    if (idx == 0x7fffffff) idx = 0;   // only if every candidate is NaN
-    int par = idx / V, w = idx - par * V;
-    float tot = total_of(idx);
-    bool pfin = s_fin[par] != 0;
-    bool nfin = pfin || (w == eos);
-    long long nlen = s_len[par] + (pfin ? 0 : 1);
-    log_probs[b * k + tid] = tot;
-    finished[b * k + tid] = nfin ? 1 : 0;
-    lengths[b * k + tid] = nlen;
-    scores_out[b * k + tid] = s_selv[tid];
-    word_out[b * k + tid] = w;
-    parent_out[b * k + tid] = par;
-    if (tok_next) tok_next[b * k + tid] = w;
-    if (src_next) src_next[b * k + tid] = b * k + par;
-    if (fin_count && nfin) atomicAdd(&fin_count[t], 1);
-  }
+  __shared__ BeamStepSmem S;
+  beam_step_block<false>(S, threadIdx.x, blockIdx.x, logits, ld, k, V, eos, lpw, log_probs, finished, lengths,
+                         scores_out, word_out, parent_out, tok_next, src_next, fin_count, t);
 }
 
 // ---------------------------------------------------------------------------
 // B2: GreedyEmbeddingHelper.sample + BasicDecoder bookkeeping, one CTA per row.
-// argmax = first maximum (int32).  Outputs are NOT masked after EOS
-// (impute_finished=False).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 greedy_step_kernel(const float* __restrict__ logits, int ld, int V, int eos, int* __restrict__ ids_t,
@@ -438,42 +309,19 @@ greedy_step_kernel(const float* __restrict__ logits, int ld, int V, int eos, int
     if (blockIdx.x == 0 && threadIdx.x == 0) fin_count[t] = n_rows;
     return;
   }
-  __shared__ float s_rv[4];
-  __shared__ int s_ri[4];
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* row = logits + (size_t)n * ld;
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int i = tid; i < V; i += 128) {
-    float v = row[i];
-    if (logits_t) logits_t[(size_t)n * V + i] = v;
-    if (better(v, i, bv, bi)) { bv = v; bi = i; }
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-  }
-  if (lane == 0) { s_rv[warp] = bv; s_ri[warp] = bi; }
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < 4; ++w)
-      if (better(s_rv[w], s_ri[w], bv, bi)) { bv = s_rv[w]; bi = s_ri[w]; }
-    if (bi == 0x7fffffff) bi = 0;
-    ids_t[n] = bi;
-    tok_next[n] = bi;
-    bool f = finished[n] || (bi == eos);
-    finished[n] = f ? 1 : 0;
-    if (f) atomicAdd(&fin_count[t], 1);
-  }
+  __shared__ GreedyStepSmem S;
+  greedy_step_block<false>(S, threadIdx.x, blockIdx.x, logits, ld, V, eos, ids_t, logits_t, tok_next, finished,
+                           fin_count, t);
 }
 
 // ---------------------------------------------------------------------------
 // Loop end + finalisation.
 // ---------------------------------------------------------------------------
-__global__ void compute_T_kernel(const int* __restrict__ fin_count, int max_it, int n_rows, int* __restrict__ T_out) {
+// `abort` (persistent loop only): non-zero when the cooperative kernel gave up at a grid barrier -> T = -1.
+__global__ void compute_T_kernel(const int* __restrict__ fin_count, int max_it, int n_rows, int* __restrict__ T_out,
+                                 const unsigned* __restrict__ abort) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (abort && *abort) { *T_out = -1; return; }
     int T = max_it;
     for (int t = 0; t < max_it; ++t)
       if (fin_count[t] >= n_rows) { T = t + 1; break; }
@@ -904,6 +752,7 @@ struct LoopBufs {
   int* fin_count;
   int *step_ids, *parents, *sorted0;
   float* scores_steps;
+  unsigned* bar;
 };
 
 static void carve_loop(comic_handle_t h, Carver& cv, int B, int k, int T, bool want_hist, LoopBufs& lb) {
@@ -926,6 +775,7 @@ static void carve_loop(comic_handle_t h, Carver& cv, int B, int k, int T, bool w
   lb.parents = cv.take<int>((size_t)T * N);
   lb.sorted0 = cv.take<int>((size_t)T * B);
   lb.scores_steps = cv.take<float>((size_t)T * N);
+  lb.bar = cv.take<unsigned>(64);
 }
 
 int decoder_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes) {
@@ -1105,7 +955,16 @@ extern "C" int comic_decode_greedy(comic_handle_t h, const float* keys, const fl
   if (logits_out) COMIC_CHECK_CUDA(cudaMemsetAsync(logits_out, 0, (size_t)max_it * N * h->V * sizeof(float), st));
   fill_i32_kernel<<<(N + 255) / 256, 256, 0, st>>>(lb.tok, h->cfg.go_id, N);
   h->launches++;
-  for (int t = 0; t < max_it; ++t) {
+  PersistCall pc{};
+  pc.keys = keys; pc.values = vals; pc.c0 = c0; pc.h0 = h0;
+  pc.B = B; pc.k = 1; pc.max_it = max_it; pc.greedy = 1; pc.lpw = 0.f;
+  for (int i = 0; i < 2; ++i) { pc.c[i] = lb.c[i]; pc.h[i] = lb.h[i]; pc.ctx[i] = lb.ctx[i]; }
+  pc.lq = lb.sb.lq; pc.scores = lb.sb.scores; pc.hist = attn_out ? lb.hist : nullptr;
+  pc.tok = lb.tok; pc.src = lb.src; pc.cum = lb.cum; pc.fin = lb.fin; pc.len = lb.len; pc.fin_count = lb.fin_count;
+  pc.step_ids = ids_out; pc.parents = nullptr; pc.sc = nullptr; pc.logits_out = logits_out; pc.bar = lb.bar;
+  int persisted = (max_it > 0) ? decode_persistent(h, pc, st) : 0;
+  if (persisted < 0) return persisted;
+  for (int t = 0; t < max_it && !persisted; ++t) {
     int cur = t & 1;
     StepIO io{};
     io.keys = keys; io.values = vals;
@@ -1126,7 +985,7 @@ extern "C" int comic_decode_greedy(comic_handle_t h, const float* keys, const fl
   }
   {
     Prof pf(h, T_FINAL, st);
-    compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out);
+    compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out, persisted ? lb.bar + 1 : nullptr);
     if (attn_out && max_it > 0) {
       dim3 g(max_it, B);
       attn_top_gather_kernel<<<g, 256, 0, st>>>(lb.hist, nullptr, T_out, max_it, B, 1, h->H * h->M, h->M, attn_out);
@@ -1168,7 +1027,16 @@ extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const floa
   iota_div_kernel<<<(N + 255) / 256, 256, 0, st>>>(lb.src0, N, k);
   beam_init_kernel<<<(N + 255) / 256, 256, 0, st>>>(lb.cum, lb.fin, lb.len, B, k);
   h->launches += 3;
-  for (int t = 0; t < max_it; ++t) {
+  PersistCall pc{};
+  pc.keys = keys; pc.values = vals; pc.c0 = c0; pc.h0 = h0;
+  pc.B = B; pc.k = k; pc.max_it = max_it; pc.greedy = 0; pc.lpw = lpw;
+  for (int i = 0; i < 2; ++i) { pc.c[i] = lb.c[i]; pc.h[i] = lb.h[i]; pc.ctx[i] = lb.ctx[i]; }
+  pc.lq = lb.sb.lq; pc.scores = lb.sb.scores; pc.hist = attn_top_out ? lb.hist : nullptr;
+  pc.tok = lb.tok; pc.src = lb.src; pc.cum = lb.cum; pc.fin = lb.fin; pc.len = lb.len; pc.fin_count = lb.fin_count;
+  pc.step_ids = step_ids; pc.parents = parents; pc.sc = sc; pc.logits_out = nullptr; pc.bar = lb.bar;
+  int persisted = (max_it > 0) ? decode_persistent(h, pc, st) : 0;
+  if (persisted < 0) return persisted;
+  for (int t = 0; t < max_it && !persisted; ++t) {
     int cur = t & 1;
     StepIO io{};
     io.keys = keys; io.values = vals;
@@ -1195,7 +1063,7 @@ extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const floa
     }
   }
   Prof pf_final(h, T_FINAL, st, 2);
-  compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out);
+  compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out, persisted ? lb.bar + 1 : nullptr);
   gather_tree_kernel<<<(N + 127) / 128, 128, 0, st>>>(step_ids, parents, nullptr, lb.len, max_it, T_out, B, k,
                                                      h->cfg.eos_id, pred_ids_out);
   if (lengths_out)

@@ -163,31 +163,36 @@ __global__ void pad_c3_c4_kernel(const float* __restrict__ x, float* __restrict_
 // Pooling kernels (NHWC, 4 channels per thread).
 // slim.max_pool2d SAME: window clipped to the image (padding never wins).
 // --------------------------------------------------------------------------
-__global__ void maxpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
-                                    int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo) {
-  size_t total = (size_t)B * Ho * Wo * (C / 4);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % (C / 4));
-    size_t p = i / (C / 4);
-    int wo = (int)(p % Wo);
-    size_t q = p / Wo;
-    int ho = (int)(q % Ho);
-    int b = (int)(q / Ho);
-    int h0 = ho * stride - pad_t, w0 = wo * stride - pad_l;
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    for (int dh = 0; dh < k; ++dh) {
-      int hi = h0 + dh;
-      if (hi < 0 || hi >= H) continue;
-      for (int dw = 0; dw < k; ++dw) {
-        int wi = w0 + dw;
-        if (wi < 0 || wi >= W) continue;
-        float4 v = ldg4(x + (((size_t)b * H + hi) * W + wi) * C + c4 * 4);
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-      }
+template <int K>
+__global__ void __launch_bounds__(256)
+maxpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned total, int H, int W, int C4,
+                    int stride, int pad_t, int pad_l, int Ho, int Wo) {
+  // one thread per (output pixel, 4 channels); all K*K taps are loaded before the max so the
+  // loads are in flight together (the kernel is a pure L2/HBM stream)
+  unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= total) return;
+  unsigned c4 = i % (unsigned)C4, p = i / (unsigned)C4;
+  unsigned wo = p % (unsigned)Wo, q = p / (unsigned)Wo;
+  unsigned ho = q % (unsigned)Ho, b = q / (unsigned)Ho;
+  const int h0 = (int)ho * stride - pad_t, w0 = (int)wo * stride - pad_l;
+  const float4* xb = reinterpret_cast<const float4*>(x) + (size_t)b * H * W * C4 + c4;
+  float4 v[K * K];
+#pragma unroll
+  for (int dh = 0; dh < K; ++dh) {
+#pragma unroll
+    for (int dw = 0; dw < K; ++dw) {
+      const int hi = h0 + dh, wi = w0 + dw;
+      const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+      v[dh * K + dw] = ok ? __ldg(xb + ((size_t)hi * W + wi) * C4)
+                          : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
-    *reinterpret_cast<float4*>(y + p * C + c4 * 4) = m;
   }
+  float4 m = v[0];
+#pragma unroll
+  for (int j = 1; j < K * K; ++j) {
+    m.x = fmaxf(m.x, v[j].x); m.y = fmaxf(m.y, v[j].y); m.z = fmaxf(m.z, v[j].z); m.w = fmaxf(m.w, v[j].w);
+  }
+  reinterpret_cast<float4*>(y)[(size_t)p * C4 + c4] = m;
 }
 
 // slim.avg_pool2d(net, [7,7], stride=1) VALID on a 7x7 map -> [B, C]
@@ -244,34 +249,38 @@ struct EncBufs {
   float *a, *b, *t1, *t2, *p;   // ping, pong, branch temporaries, pooled input
 };
 
-static size_t enc_chunk_floats(int chunk, size_t* a, size_t* b, size_t* t1, size_t* t2, size_t* p) {
-  // a/b hold the largest stage outputs; sizes per image (floats)
-  size_t s_conv1 = (size_t)112 * 112 * 64;
-  size_t s_pool1 = (size_t)56 * 56 * 64;
-  size_t s_2c = (size_t)56 * 56 * 192;
-  size_t s_28 = (size_t)28 * 28 * 480;
-  *a = chunk * (s_conv1 > s_2c ? s_conv1 : s_2c);
-  *b = chunk * (s_pool1 > s_28 ? s_pool1 : s_28);
-  if (*b < (size_t)chunk * 56 * 56 * 64) *b = (size_t)chunk * 56 * 56 * 64;
-  // ping-pong between a and b for every stage: make both as large as the largest
-  size_t big = *a > *b ? *a : *b;
-  *a = *b = big;
-  *t1 = (size_t)chunk * 28 * 28 * 128;   // max b1a plane: 28x28x128 (3c) / 14x14x160
-  *t2 = (size_t)chunk * 28 * 28 * 32;    // max b2a plane
-  *p = (size_t)chunk * 28 * 28 * 256;    // pooled block input (max 28x28x256)
-  return *a + *b + *t1 + *t2 + *p;
+// The forward runs in three stages with their own image-chunk sizes: the stem (huge
+// activations: 3.2 MB / image after Conv2d_1a) in small chunks, the 28x28 blocks in medium
+// ones and the 14x14 / 7x7 blocks in large ones, so that every launch has several waves of
+// 128-row tiles on the 148 SMs (a 64-image chunk gives a 14x14 layer 98 tiles: < 1 wave).
+// Stage outputs (pool2 [B,28,28,192], pool3 [B,14,14,480]) are whole-batch buffers.
+struct EncPlan {
+  int cs, c3, c4;
+  size_t ab, t1, t2, p, p2, p3, head;   // floats
+};
+
+static EncPlan enc_plan(comic_handle_t h, int B) {
+  EncPlan pl;
+  pl.cs = B < h->enc_chunk[0] ? B : h->enc_chunk[0];
+  pl.c3 = B < h->enc_chunk[1] ? B : h->enc_chunk[1];
+  pl.c4 = B < h->enc_chunk[2] ? B : h->enc_chunk[2];
+  auto mx = [](size_t x, size_t y) { return x > y ? x : y; };
+  // ping/pong: stem conv1 112x112x64 / conv2c 56x56x192; stage 3 28x28x480; stage 4 14x14x528 (832 goes to fm_out)
+  pl.ab = mx(mx((size_t)pl.cs * 112 * 112 * 64, (size_t)pl.c3 * 28 * 28 * 480), (size_t)pl.c4 * 14 * 14 * 832);
+  pl.t1 = mx((size_t)pl.c3 * 28 * 28 * 128, (size_t)pl.c4 * 14 * 14 * 192);
+  pl.t2 = mx((size_t)pl.c3 * 28 * 28 * 32, (size_t)pl.c4 * 14 * 14 * 48);
+  pl.p = mx((size_t)pl.c3 * 28 * 28 * 256, (size_t)pl.c4 * 14 * 14 * 832);
+  pl.p2 = (size_t)B * 28 * 28 * 192;
+  pl.p3 = (size_t)B * 14 * 14 * 480;
+  pl.head = (size_t)pl.c4 * 1024;
+  return pl;
 }
 
-static int enc_chunk_for(int B) { return B < 64 ? B : 64; }
-
 int encoder_workspace_bytes(comic_handle_t h, int B, size_t* bytes) {
-  (void)h;
-  size_t a, b, t1, t2, p;
-  int chunk = enc_chunk_for(B);
+  EncPlan pl = enc_plan(h, B);
   Carver cv(nullptr);
-  enc_chunk_floats(chunk, &a, &b, &t1, &t2, &p);
-  cv.take<float>(a); cv.take<float>(b); cv.take<float>(t1); cv.take<float>(t2); cv.take<float>(p);
-  cv.take<float>((size_t)chunk * 1024);   // legacy head scratch
+  cv.take<float>(pl.ab); cv.take<float>(pl.ab); cv.take<float>(pl.t1); cv.take<float>(pl.t2); cv.take<float>(pl.p);
+  cv.take<float>(pl.p2); cv.take<float>(pl.p3); cv.take<float>(pl.head);
   *bytes = cv.off;
   return COMIC_OK;
 }
@@ -314,11 +323,15 @@ static int run_maxpool(comic_handle_t h, const float* x, float* y, int B, int H,
   same_pads(H, k, s, &Ho, &pt);
   same_pads(W, k, s, &Wo, &pl);
   size_t total = (size_t)B * Ho * Wo * (C / 4);
-  int grid = (int)((total + 255) / 256);
-  if (grid > h->num_sms * 16) grid = h->num_sms * 16;
+  COMIC_REQUIRE(total < 0xffffffffull && C % 4 == 0 && (k == 2 || k == 3), COMIC_E_UNSUPPORTED,
+                "maxpool: unsupported shape (total %zu, C %d, k %d)", total, C, k);
+  unsigned grid = (unsigned)((total + 255) / 256);
   {
     Prof pf(h, T_POOL, st);
-    maxpool_nhwc_kernel<<<grid, 256, 0, st>>>(x, y, B, H, W, C, k, s, pt, pl, Ho, Wo);
+    if (k == 3)
+      maxpool_nhwc_kernel<3><<<grid, 256, 0, st>>>(x, y, (unsigned)total, H, W, C / 4, s, pt, pl, Ho, Wo);
+    else
+      maxpool_nhwc_kernel<2><<<grid, 256, 0, st>>>(x, y, (unsigned)total, H, W, C / 4, s, pt, pl, Ho, Wo);
   }
   COMIC_CHECK_CUDA(cudaGetLastError());
   if (Ho_out) *Ho_out = Ho;
@@ -370,20 +383,20 @@ int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out,
   size_t need;
   encoder_workspace_bytes(h, B, &need);
   COMIC_REQUIRE(ws_bytes >= need, COMIC_E_WORKSPACE, "encode_fwd: workspace %zu < %zu", ws_bytes, need);
-  int chunk = enc_chunk_for(B);
-  size_t sa, sb, st1, st2, sp;
-  enc_chunk_floats(chunk, &sa, &sb, &st1, &st2, &sp);
+  const EncPlan pl = enc_plan(h, B);
   Carver cv(ws);
   EncBufs eb;
-  eb.a = cv.take<float>(sa); eb.b = cv.take<float>(sb);
-  eb.t1 = cv.take<float>(st1); eb.t2 = cv.take<float>(st2); eb.p = cv.take<float>(sp);
-  float* head = cv.take<float>((size_t)chunk * 1024);
+  eb.a = cv.take<float>(pl.ab); eb.b = cv.take<float>(pl.ab);
+  eb.t1 = cv.take<float>(pl.t1); eb.t2 = cv.take<float>(pl.t2); eb.p = cv.take<float>(pl.p);
+  float* pool2 = cv.take<float>(pl.p2);
+  float* pool3 = cv.take<float>(pl.p3);
+  float* head = cv.take<float>(pl.head);
   int rc;
-  for (int b0 = 0; b0 < B; b0 += chunk) {
-    int nb = (B - b0 < chunk) ? (B - b0) : chunk;
+  // ---- stem (inception_v1.py:70-93) -> pool2 [B,28,28,192]
+  for (int b0 = 0; b0 < B; b0 += pl.cs) {
+    int nb = (B - b0 < pl.cs) ? (B - b0) : pl.cs;
     const float* img = images + (size_t)b0 * 224 * 224 * 3;
     int Ho, Wo;
-    // stem (inception_v1.py:70-93)
     if (use_tc(h, h->pk.tc_conv[0], nb * 112 * 112)) {
       size_t npix = (size_t)nb * 224 * 224;
       {
@@ -397,13 +410,21 @@ int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out,
     if ((rc = run_maxpool(h, eb.a, eb.b, nb, 112, 112, 64, 3, 2, &Ho, &Wo, st))) return rc;     // 56x56x64
     if ((rc = run_conv(h, eb.b, nb, 56, 56, 64, 1, eb.a, 64, 0, nullptr, nullptr, st))) return rc;
     if ((rc = run_conv(h, eb.a, nb, 56, 56, 64, 2, eb.b, 192, 0, nullptr, nullptr, st))) return rc;  // 56x56x192
-    if ((rc = run_maxpool(h, eb.b, eb.a, nb, 56, 56, 192, 3, 2, nullptr, nullptr, st))) return rc;  // 28x28x192
-    // Mixed_3b, 3c @28
-    if ((rc = run_block(h, 0, eb.a, eb.b, nb, 28, eb, st))) return rc;   // 256
-    if ((rc = run_block(h, 1, eb.b, eb.a, nb, 28, eb, st))) return rc;   // 480
-    if ((rc = run_maxpool(h, eb.a, eb.b, nb, 28, 28, 480, 3, 2, nullptr, nullptr, st))) return rc;  // 14x14x480
-    // Mixed_4b..4e @14
-    if ((rc = run_block(h, 2, eb.b, eb.a, nb, 14, eb, st))) return rc;   // 512
+    if ((rc = run_maxpool(h, eb.b, pool2 + (size_t)b0 * 28 * 28 * 192, nb, 56, 56, 192, 3, 2, nullptr, nullptr, st)))
+      return rc;                                                                                // 28x28x192
+  }
+  // ---- Mixed_3b, 3c @28 -> pool3 [B,14,14,480]
+  for (int b0 = 0; b0 < B; b0 += pl.c3) {
+    int nb = (B - b0 < pl.c3) ? (B - b0) : pl.c3;
+    if ((rc = run_block(h, 0, pool2 + (size_t)b0 * 28 * 28 * 192, eb.b, nb, 28, eb, st))) return rc;   // 256
+    if ((rc = run_block(h, 1, eb.b, eb.a, nb, 28, eb, st))) return rc;                                   // 480
+    if ((rc = run_maxpool(h, eb.a, pool3 + (size_t)b0 * 14 * 14 * 480, nb, 28, 28, 480, 3, 2, nullptr, nullptr, st)))
+      return rc;                                                                                         // 14x14x480
+  }
+  // ---- Mixed_4b..4f @14, Mixed_5b, 5c @7, head
+  for (int b0 = 0; b0 < B; b0 += pl.c4) {
+    int nb = (B - b0 < pl.c4) ? (B - b0) : pl.c4;
+    if ((rc = run_block(h, 2, pool3 + (size_t)b0 * 14 * 14 * 480, eb.a, nb, 14, eb, st))) return rc;   // 512
     if ((rc = run_block(h, 3, eb.a, eb.b, nb, 14, eb, st))) return rc;   // 512
     if ((rc = run_block(h, 4, eb.b, eb.a, nb, 14, eb, st))) return rc;   // 512
     if ((rc = run_block(h, 5, eb.a, eb.b, nb, 14, eb, st))) return rc;   // 528

@@ -39,7 +39,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;                      // bf16 elements = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int kEpiWarps = 4;
-constexpr int kLoaderGroups = 2;
+constexpr int kLoaderGroups = 2;                // must be <= the smallest STAGES: a group may run at most one
+                                                // mbarrier phase ahead of the stage it refills (parity aliasing otherwise)
 constexpr int kFirstLoaderWarp = 6;
 constexpr int kThreads = (kFirstLoaderWarp + 4 * kLoaderGroups) * 32;   // 448
 
@@ -316,7 +317,7 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
     __syncwarp();
   } else {
     // =====================  A loaders  =====================
-    const int grp = (warp - kFirstLoaderWarp) >> 2;         // loader group 0 / 1
+    const int grp = (warp - kFirstLoaderWarp) >> 2;         // loader group
     const int wg = (warp - kFirstLoaderWarp) & 3;           // warp inside the group
     const int tg = wg * 32 + lane;                          // thread inside the group
     const int chunk = lane & 15;                            // float4 chunk within the 64-float K row
@@ -358,7 +359,7 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
       }
       named_bar_sync(1 + grp, 128);
       for (int kt = 0; kt < nk; ++kt, ++it) {
-        if ((int)(it & 1) != grp) continue;
+        if ((int)(it % kLoaderGroups) != grp) continue;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         float4 v[16];
@@ -523,16 +524,21 @@ inline cudaError_t launch_one(const typename AParam<AMODE>::type& a, const TcWei
 }
 
 // N tile = shared-memory / TMEM allocation; the UMMA N is the exact remainder per tile.
-inline int pick_bn(int N) {
+// A launch that cannot fill the SMs with 256-wide tiles takes 128-wide ones when those still fit in one wave
+// (e.g. the [logits | query] GEMM at 1,536 rows: 48 -> 84 tiles, each half as long).
+inline int pick_bn(int M, int N, int num_sms) {
   if (N <= 64) return 64;
   if (N <= 128) return 128;
+  const int mt = (M + BM - 1) / BM;
+  const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
+  if (t256 < num_sms && t128 <= num_sms) return 128;
   return 256;
 }
 
 template <int AMODE>
 inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const TcWeight& w, int M, int N,
                                   const Epi& epi, int num_sms, cudaStream_t st) {
-  int bn = pick_bn(N);
+  int bn = pick_bn(M, N, num_sms);
   if (bn == 64) return launch_one<64, 4, AMODE>(a, w, 0, M, N, epi, num_sms, st);
   if (bn == 128) return launch_one<128, 3, AMODE>(a, w, 1, M, N, epi, num_sms, st);
   return launch_one<256, 2, AMODE>(a, w, 2, M, N, epi, num_sms, st);

@@ -102,7 +102,7 @@ SIGNATURES = {
 }
 
 KERNEL_TAGS = ['conv', 'pool', 'project', 'init', 'gates', 'lstm', 'lq', 'scores', 'ctx', 'beam',
-               'final', 'misc']
+               'final', 'misc', 'persist']
 
 
 def load_library(path=LIB_PATH):
@@ -110,6 +110,7 @@ def load_library(path=LIB_PATH):
     global _lib
     if _lib is not None:
         return _lib
+    path = os.environ.get('COMIC_B200_LIB', path)      # experiment builds (same ABI); still no fallback
     if not os.path.exists(path):
         raise ComicError('libcomic_b200.so not built (%s); run `python __graft_entry__.py build`' % path)
     lib = C.CDLL(path)
@@ -119,6 +120,15 @@ def load_library(path=LIB_PATH):
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def executed_steps(T):
+    """Host read of a decode call's executed step count (the one device->host sync); -1 is the
+    persistent loop kernel's watchdog verdict (a grid barrier never completed)."""
+    t = int(T.item())
+    if t < 0:
+        raise ComicError('decode loop aborted: the persistent kernel gave up at a grid barrier')
+    return t
 
 
 def _ptr(t):
@@ -389,7 +399,7 @@ class Engine(object):
         self._check(self.lib.comic_set_precision(self._h, {'f32': 0, 'tf32x3': 1, 'split': 1, 'fast': 2}[mode]))
 
     def set_option(self, name, value):
-        self._check(self.lib.comic_set_option(self._h, {'fused_attn_min_images': 0}[name], int(value)))
+        self._check(self.lib.comic_set_option(self._h, {'fused_attn_min_images': 0, 'enc_chunk_stem': 1, 'enc_chunk_28': 2, 'enc_chunk_14': 3, 'persistent_max_rows': 4}[name], int(value)))
 
     def profile_enable(self, tags):
         mask = 0

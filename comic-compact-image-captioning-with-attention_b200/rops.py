@@ -13,6 +13,8 @@ from __future__ import annotations
 
 import collections
 
+from .engine import executed_steps
+
 AttentionWrapperState = collections.namedtuple(
     'AttentionWrapperState',
     ('cell_state', 'attention', 'time', 'alignments', 'alignment_history', 'attention_state'))
@@ -150,7 +152,7 @@ def rnn_decoder_beam_search(cell, embedding_fn, output_layer, batch_size, beam_s
     c0, h0 = cell._initial_cell_state
     r = eng.decode_beam(am.keys, am.values, c0, h0, int(beam_size), float(length_penalty_weight),
                         int(maximum_iterations))
-    T = int(r['T'].item())                       # the one device->host sync of a decode call
+    T = executed_steps(r['T'])                       # the one device->host sync of a decode call
     r['T_host'] = T
     state = AttentionWrapperState(cell_state=None, attention=None, time=T, alignments=None,
                                   alignment_history=r['attn'][:, :, :T, :], attention_state=None)
@@ -174,7 +176,7 @@ def rnn_decoder_search(cell, embedding_fn, output_layer, batch_size, maximum_ite
                          '(decoder output).')
     c0, h0 = cell._initial_cell_state
     r = eng.decode_greedy(am.keys, am.values, c0, h0, int(maximum_iterations))
-    T = int(r['T'].item())
+    T = executed_steps(r['T'])
     state = AttentionWrapperState(cell_state=None, attention=None, time=T, alignments=None,
                                   alignment_history=r['attn'][:, :, :T, :], attention_state=None)
     return r['ids'][:T], r['logits'][:T], state

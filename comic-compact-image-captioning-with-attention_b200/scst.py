@@ -25,6 +25,7 @@ from collections import Counter, defaultdict
 
 import numpy as np
 
+from .engine import executed_steps
 from .model import number_to_base
 
 
@@ -314,7 +315,7 @@ def sample_captions(engine, config, images, beam, max_length=20):
     c0, h0 = engine.rnn_init(im_embed)
     g = engine.decode_greedy(keys, values, c0, h0, max_it, want_logits=False, want_attn=False)
     b = engine.decode_beam(keys, values, c0, h0, beam, 0.0, max_it, want_attn=False)
-    Tg, Tb = int(g['T'].item()), int(b['T'].item())
+    Tg, Tb = executed_steps(g['T']), executed_steps(b['T'])
     cap_greedy = g['ids'][:Tg].transpose(0, 1).contiguous()              # [B, T]
     cap_beam = b['predicted_ids'][:Tb].permute(2, 1, 0).contiguous()     # [k, B, T]  (top_beam=False, :286-288)
     return cap_beam, cap_greedy, im_embed, fm

@@ -20,13 +20,26 @@ def torch_mod():
 
 
 def _engine(c, W, with_cnn=True, precision='tf32x3', fused=None):
+    """fused: True = one-CTA-per-image fused attention at any batch; False = sliced kernels (both on the
+    one-launch-per-op path); 'persistent' = the whole decode loop as one cooperative kernel (the
+    default for <= 32 rows); None = engine defaults."""
     from comic_b200.engine import Engine
     eng = Engine(c)
     eng.bind_weights(W, with_cnn=with_cnn)
     eng.set_precision(precision)
-    if fused is not None:      # True: one-CTA-per-image fused attention at any batch; False: sliced kernels
+    if fused in (True, False):
         eng.set_option('fused_attn_min_images', 1 if fused else 1 << 30)
+        eng.set_option('persistent_max_rows', 0)
     return eng
+
+
+def _check_path(eng, fused, launches_before, max_it):
+    """The persistent path enqueues O(1) kernels per decode call, the per-step path >= 5 per step."""
+    n = eng.launch_count() - launches_before
+    if fused == 'persistent':
+        assert n < 16, 'persistent decode loop was not used (%d launches)' % n
+    elif fused in (True, False):
+        assert n >= 5 * max_it
 
 
 @pytest.mark.parametrize('precision', ['f32', 'tf32x3'])
@@ -259,9 +272,10 @@ def _decode_inputs(c, B, seed=0):
     return W, im, fm
 
 
-@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('fused', [False, True, 'persistent'])
 @pytest.mark.parametrize('name,B,k,max_it', [('comic256', 4, 3, 14), ('word_none_h1', 3, 3, 8),
-                                             ('comic256', 2, 7, 10), ('independent_h4', 2, 2, 6)])
+                                             ('comic256', 2, 7, 10), ('independent_h4', 2, 2, 6),
+                                             ('comic256', 8, 3, 60), ('comic256', 1, 1, 5), ('comic256', 10, 3, 9)])
 def test_beam_search_matches_oracle(torch_mod, name, B, k, max_it, fused):
     import comic_oracle as O
     c = CONFIGS[name]()
@@ -270,7 +284,9 @@ def test_beam_search_matches_oracle(torch_mod, name, B, k, max_it, fused):
     ref = O.beam_search_decode(O.Decoder(W, c), im, fm, k, 0.0, max_it)
     keys, values = eng.project_fm(eng.to_dev(fm))
     c0, h0 = eng.rnn_init(eng.to_dev(im))
+    n0 = eng.launch_count()
     r = eng.decode_beam(keys, values, c0, h0, k, 0.0, max_it)
+    _check_path(eng, fused, n0, max_it)
     T = int(r['T'].item())
     assert T == ref['T']
     np.testing.assert_array_equal(r['step_ids'][:T].cpu().numpy(), ref['step_ids'])
@@ -282,7 +298,8 @@ def test_beam_search_matches_oracle(torch_mod, name, B, k, max_it, fused):
     assert rel_err(r['attn'][:, :, :T].cpu().numpy(), am) < 1e-3
 
 
-def test_beam_search_eos_and_early_stop(torch_mod):
+@pytest.mark.parametrize('fused', [True, 'persistent'])
+def test_beam_search_eos_and_early_stop(torch_mod, fused):
     """Bias the output layer towards EOS so beams finish: exercises _mask_probs,
     length bookkeeping, gather_tree EOS back-fill and the all-finished stop."""
     import comic_oracle as O
@@ -292,7 +309,7 @@ def test_beam_search_eos_and_early_stop(torch_mod):
     b = W[wts.DEC + 'output_projection/bias'].copy()
     b[257] += 3.2
     W[wts.DEC + 'output_projection/bias'] = b
-    eng = _engine(c, W, with_cnn=False)
+    eng = _engine(c, W, with_cnn=False, fused=fused)
     ref = O.beam_search_decode(O.Decoder(W, c), im, fm, 3, 0.0, 40)
     keys, values = eng.project_fm(eng.to_dev(fm))
     c0, h0 = eng.rnn_init(eng.to_dev(im))
@@ -307,7 +324,7 @@ def test_beam_search_eos_and_early_stop(torch_mod):
     assert rel_err(r['attn'][:, :, :T].cpu().numpy(), am) < 1e-3
 
 
-@pytest.mark.parametrize('fused', [False, True])
+@pytest.mark.parametrize('fused', [False, True, 'persistent'])
 def test_greedy_matches_oracle(torch_mod, fused):
     import comic_oracle as O
     c = comic_config()
@@ -316,7 +333,9 @@ def test_greedy_matches_oracle(torch_mod, fused):
     ref = O.greedy_decode(O.Decoder(W, c), im, fm, 12)
     keys, values = eng.project_fm(eng.to_dev(fm))
     c0, h0 = eng.rnn_init(eng.to_dev(im))
+    n0 = eng.launch_count()
     r = eng.decode_greedy(keys, values, c0, h0, 12)
+    _check_path(eng, fused, n0, 12)
     T = int(r['T'].item())
     assert T == ref['T']
     np.testing.assert_array_equal(r['ids'][:T].cpu().numpy(), ref['ids'])
