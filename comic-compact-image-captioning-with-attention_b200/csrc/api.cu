@@ -140,6 +140,7 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
   switch (option) {
     case COMIC_OPT_FUSED_ATTN_MIN_IMAGES: h->fused_min_images = value; return COMIC_OK;
     case COMIC_OPT_PERSISTENT_MAX_ROWS: h->persist_max_rows = value; return COMIC_OK;
+    case COMIC_OPT_PERSISTENT_TRACE: h->persist_trace = value; return COMIC_OK;
     case COMIC_OPT_ENC_CHUNK_STEM:
     case COMIC_OPT_ENC_CHUNK_28:
     case COMIC_OPT_ENC_CHUNK_14:
@@ -150,6 +151,17 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
   }
   set_error("set_option: unknown option %d", option);
   return COMIC_E_BADARG;
+}
+
+extern "C" int comic_decode_trace(comic_handle_t h, int64_t* out, int max_steps, int* steps, void* stream) {
+  COMIC_REQUIRE(h && out && steps, COMIC_E_BADARG, "decode_trace: null argument");
+  int n = h->last_trace_steps < max_steps ? h->last_trace_steps : max_steps;
+  *steps = n;
+  if (n <= 0 || !h->last_trace) { *steps = 0; return COMIC_OK; }
+  COMIC_CHECK_CUDA(cudaMemcpyAsync(out, h->last_trace, (size_t)n * 32 * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                   (cudaStream_t)stream));
+  COMIC_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return COMIC_OK;
 }
 
 extern "C" int comic_packed_bytes(comic_handle_t h, size_t* bytes) {

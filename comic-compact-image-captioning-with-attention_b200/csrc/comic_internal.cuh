@@ -70,6 +70,9 @@ struct comic_handle_s {
   bool bound = false, cnn_bound = false;
   int precision = 1;   // 0: fp32 FFMA everywhere; 1: tcgen05 split-precision GEMMs with M >= 128; 2: 1 + tanh.approx
   int fused_min_images = 48;   // fused attention kernel (one CTA per image) from this batch size on
+  int persist_trace = 0;       // record per-phase clock stamps of the persistent loop (diagnostics)
+  long long* last_trace = nullptr;
+  int last_trace_steps = 0;
   int persist_max_rows = 32;   // whole decode loop as one cooperative kernel up to this many rows (0 = off)
   int enc_chunk[3] = {64, 256, 512};   // images per encoder chunk: stem / 28x28 blocks / 14x14 + 7x7 blocks
   comic::Packed pk;
@@ -187,6 +190,8 @@ struct PersistCall {
   float* sc;
   float* logits_out;
   unsigned* bar;   // [2]: barrier counter, abort flag
+  long long* trace;   // [max_it][2][16] phase time stamps or nullptr
+  float* part;        // [16][N][4R] partial gate sums (K groups of phase A)
 };
 bool persist_applicable(comic_handle_t h, int B, int k, bool greedy);
 int decode_persistent(comic_handle_t h, const PersistCall& pc, cudaStream_t st);

@@ -294,7 +294,8 @@ beam_step_kernel(const float* __restrict__ logits, int ld, int k, int V, int eos
     return;
   }
   __shared__ BeamStepSmem S;
-  beam_step_block<false>(S, threadIdx.x, blockIdx.x, logits, ld, k, V, eos, lpw, log_probs, finished, lengths,
+  __shared__ float s_stage[4096];   // k * V <= 4096 (radix / char vocabularies): logits staged once
+  beam_step_block<false>(S, s_stage, 4096, threadIdx.x, blockIdx.x, logits, ld, k, V, eos, lpw, log_probs, finished, lengths,
                          scores_out, word_out, parent_out, tok_next, src_next, fin_count, t);
 }
 
@@ -753,6 +754,8 @@ struct LoopBufs {
   int *step_ids, *parents, *sorted0;
   float* scores_steps;
   unsigned* bar;
+  long long* trace;
+  float* part;
 };
 
 static void carve_loop(comic_handle_t h, Carver& cv, int B, int k, int T, bool want_hist, LoopBufs& lb) {
@@ -776,6 +779,8 @@ static void carve_loop(comic_handle_t h, Carver& cv, int B, int k, int T, bool w
   lb.sorted0 = cv.take<int>((size_t)T * B);
   lb.scores_steps = cv.take<float>((size_t)T * N);
   lb.bar = cv.take<unsigned>(64);
+  lb.trace = cv.take<long long>((size_t)T * 32 + 1);
+  lb.part = cv.take<float>(N <= 32 ? (size_t)16 * N * 4 * h->R : 1);   // persistent loop only
 }
 
 int decoder_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes) {
@@ -961,7 +966,7 @@ extern "C" int comic_decode_greedy(comic_handle_t h, const float* keys, const fl
   for (int i = 0; i < 2; ++i) { pc.c[i] = lb.c[i]; pc.h[i] = lb.h[i]; pc.ctx[i] = lb.ctx[i]; }
   pc.lq = lb.sb.lq; pc.scores = lb.sb.scores; pc.hist = attn_out ? lb.hist : nullptr;
   pc.tok = lb.tok; pc.src = lb.src; pc.cum = lb.cum; pc.fin = lb.fin; pc.len = lb.len; pc.fin_count = lb.fin_count;
-  pc.step_ids = ids_out; pc.parents = nullptr; pc.sc = nullptr; pc.logits_out = logits_out; pc.bar = lb.bar;
+  pc.step_ids = ids_out; pc.parents = nullptr; pc.sc = nullptr; pc.logits_out = logits_out; pc.bar = lb.bar; pc.trace = h->persist_trace ? lb.trace : nullptr; pc.part = lb.part;
   int persisted = (max_it > 0) ? decode_persistent(h, pc, st) : 0;
   if (persisted < 0) return persisted;
   for (int t = 0; t < max_it && !persisted; ++t) {
@@ -1033,7 +1038,7 @@ extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const floa
   for (int i = 0; i < 2; ++i) { pc.c[i] = lb.c[i]; pc.h[i] = lb.h[i]; pc.ctx[i] = lb.ctx[i]; }
   pc.lq = lb.sb.lq; pc.scores = lb.sb.scores; pc.hist = attn_top_out ? lb.hist : nullptr;
   pc.tok = lb.tok; pc.src = lb.src; pc.cum = lb.cum; pc.fin = lb.fin; pc.len = lb.len; pc.fin_count = lb.fin_count;
-  pc.step_ids = step_ids; pc.parents = parents; pc.sc = sc; pc.logits_out = nullptr; pc.bar = lb.bar;
+  pc.step_ids = step_ids; pc.parents = parents; pc.sc = sc; pc.logits_out = nullptr; pc.bar = lb.bar; pc.trace = h->persist_trace ? lb.trace : nullptr; pc.part = lb.part;
   int persisted = (max_it > 0) ? decode_persistent(h, pc, st) : 0;
   if (persisted < 0) return persisted;
   for (int t = 0; t < max_it && !persisted; ++t) {

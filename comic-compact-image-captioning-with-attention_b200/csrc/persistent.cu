@@ -7,14 +7,15 @@
 // (~150 TF ops per step; 8 kernel launches per step on the per-step path of
 // decoder.cu).  At N = 24 rows a step moves ~16 MB and is pure latency, so the
 // loop runs inside one launch with the operands that do not change between
-// steps resident in shared memory, and the CTAs meet at four grid barriers per
+// steps resident in shared memory, and the CTAs meet at five grid barriers per
 // step:
 //
-//   phase A  gates + LSTM cell: CTA a owns UPC hidden units = 4*UPC columns of
-//            the [W+A+R, 4R] LSTM kernel, RESIDENT in smem for the whole loop
-//            (80 KB at COMIC-256); x = [emb(tok) ; ctx[src] ; h[src]] streams in
-//            through a cp.async double buffer; 16 warps split K, fixed-order
-//            reduction; the cell update is applied in place -> c', h'.
+//   phase A1 gates: the [W+A+R, 4R] LSTM kernel is cut into (K group x 128-column) blocks, one per
+//            CTA, RESIDENT in smem for the whole loop (8 x 16 blocks of 160 x 128 = 80 KB at
+//            COMIC-256).  A CTA reads only its K slice of x = [emb(tok) ; ctx[src] ; h[src]] (15 KB;
+//            every CTA reading all of x measured 15-19 us per step on L2 hot lines) and writes
+//            its partial sums.
+//   phase A2 fixed-order sum over the K groups + bias, LSTM cell -> c', h'  (4 units per CTA).
 //   phase B  [logits | query] = h' . [W_o | W_q] + b: 8-column blocks per CTA.
 //   phase C1 attention scores: CTA (image, position slice) keeps its CENTRED key
 //            rows resident in smem (keys never re-read from HBM after step 0) and
@@ -37,7 +38,7 @@ namespace comic {
 constexpr int kPT = 512;            // threads per CTA
 constexpr int kPW = kPT / 32;       // warps
 constexpr int kPMaxRPL = 4;         // rows per lane group: N <= 8 * 4
-constexpr int kPKC = 256;           // phase-A K chunk (16 warps x 16)
+constexpr int kPCS = 128;           // phase-A column block (16 warps x 8 columns)
 constexpr int kPMaxHeads = 4;       // heads a CTA may need in phase C2
 
 struct PersistArgs {
@@ -74,9 +75,11 @@ struct PersistArgs {
   float* sc;                  // beam: [T][N] scores
   float* logits_out;          // greedy: [T][N][V] or nullptr
   unsigned* bar;              // [0] barrier counter, [1] abort flag
+  long long* trace;           // [max_it][2][16] clock64 stamps of CTA 0 and the first selection CTA, or nullptr
   // partition / smem plan (floats)
-  int nA, UPC, CB, nB, S, rps, cps, nh_max, keys_res, vals_res, n_sel;
-  int off_wA, off_c, off_keys, off_skk, off_vals, off_tr;
+  int KG, KS, CB, nB, S, rps, cps, nh_max, keys_res, vals_res, n_sel;
+  float* part;                // [KG][N][4R] partial gate sums
+  int off_wA, off_c, off_keys, off_skk, off_vals, off_tr, tr_floats;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -109,6 +112,17 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned& target, un
   return *s_abort == 0;
 }
 
+// Arrive without waiting: for a CTA that neither produced anything the next phase consumes nor
+// consumes anything the previous phase produced (the selection CTAs between phases C1 and C2).
+__device__ __forceinline__ void grid_arrive(unsigned* bar, unsigned& target, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += nblocks;
+    __threadfence();
+    atomicAdd(bar, 1u);
+  }
+}
+
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
@@ -117,6 +131,40 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 }
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// Phase-A1 inner product of one lane: RP row groups x 2 columns over KS k's, with the packed
+// fp32 pipe (FFMA2: two FMAs per lane per issue slot; the plain FFMA issues every other cycle
+// per scheduler on sm_100).  The k dimension is packed: acc.x sums even k, acc.y odd k.
+//   wl: this lane's slice of the k-pair-interleaved weight block, [KS/2][kPCS][2]
+template <int RP>
+__device__ __forceinline__ void gemm_a1(const float* __restrict__ xs, int XLD, int N, int ng, const float* __restrict__ wl,
+                                        int KS, float (&out)[kPMaxRPL][2]) {
+  float2 acc[RP][2];
+  const float* xrow[RP];
+#pragma unroll
+  for (int r = 0; r < RP; ++r) {
+    acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+    xrow[r] = xs + (size_t)min(ng + 8 * r, N - 1) * XLD;   // rows beyond N recompute row N-1 (never stored)
+  }
+#pragma unroll 4
+  for (int k4 = 0; k4 < KS; k4 += 4) {
+    const float4 wv0 = *reinterpret_cast<const float4*>(wl + (size_t)(k4 >> 1) * kPCS * 2);
+    const float4 wv1 = *reinterpret_cast<const float4*>(wl + (size_t)((k4 >> 1) + 1) * kPCS * 2);
+#pragma unroll
+    for (int r = 0; r < RP; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(xrow[r] + k4);
+      acc[r][0] = __ffma2_rn(make_float2(x.x, x.y), make_float2(wv0.x, wv0.y), acc[r][0]);
+      acc[r][1] = __ffma2_rn(make_float2(x.x, x.y), make_float2(wv0.z, wv0.w), acc[r][1]);
+      acc[r][0] = __ffma2_rn(make_float2(x.z, x.w), make_float2(wv1.x, wv1.y), acc[r][0]);
+      acc[r][1] = __ffma2_rn(make_float2(x.z, x.w), make_float2(wv1.z, wv1.w), acc[r][1]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RP; ++r) {
+    out[r][0] = acc[r][0].x + acc[r][0].y;
+    out[r][1] = acc[r][1].x + acc[r][1].y;
+  }
+}
 
 template <int H, int KB>
 __global__ void __launch_bounds__(kPT, 1)
@@ -130,7 +178,6 @@ decode_loop_kernel(const PersistArgs a) {
   __shared__ BeamStepSmem s_beam;
   __shared__ GreedyStepSmem s_greedy;
   __shared__ const float* s_xp[3][32];   // x segment row pointers (nullptr = zero row)
-  __shared__ int s_crow[32];             // c_prev row of each output row
   __shared__ int s_abort;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -141,15 +188,16 @@ decode_loop_kernel(const PersistArgs a) {
   const int rpl = (N + 7) >> 3;
   unsigned bar_target = 0;
 
-  float* wA = sm + a.off_wA;          // [KX][4*UPC]
+  float* wA = sm + a.off_wA;          // [KS/2][kPCS][2] block of the LSTM kernel (k pairs interleaved)
   float* sm_c = sm + a.off_c;         // [3][R] lane-permuted gamma', beta', vv
   float* sm_keys = sm + a.off_keys;   // [rps][R] centred key rows, lane-permuted
   float* sm_skk = sm + a.off_skk;     // [rps]
   float* sm_vals = sm + a.off_vals;   // [M][cps]
   float* tr = sm + a.off_tr;          // transient region (per-phase layouts)
 
-  const int NC = 4 * a.UPC;           // gate columns of this CTA
-  const bool has_A = cta < a.nA;
+  const int n_colgrp = 4 * R / kPCS;   // column groups of the [KX, 4R] LSTM kernel
+  const bool has_A = cta < a.KG * n_colgrp;
+  const int kgp = cta / n_colgrp, cgp = cta % n_colgrp;
   const bool has_B = cta < a.nB;
   const bool has_C = cta < a.B * a.S;
   const int img = has_C ? cta / a.S : 0, slc = has_C ? cta % a.S : 0;
@@ -160,12 +208,14 @@ decode_loop_kernel(const PersistArgs a) {
 
   // ------------------------------------------------------------------ setup
   if (has_A) {
-    // column j = g*UPC + u  <-  global column g*R + (cta*UPC + u)
-    const int tot = KX * NC;
-    for (int i = tid; i < tot; i += kPT) {
-      int kk = i / NC, j = i - kk * NC;
-      int g = j / a.UPC, u = j - g * a.UPC;
-      wA[i] = __ldg(a.lstm_kernel + (size_t)kk * 4 * R + g * R + cta * a.UPC + u);
+    // rows [kgp*KS, +KS) x columns [cgp*128, +128) of the LSTM kernel, resident for the whole loop
+    // smem layout [KS/2][128][2]: the two k's of a pair adjacent (operand pairs of the packed FMA)
+    const int tot4 = a.KS * (kPCS / 4);
+    for (int i = tid; i < tot4; i += kPT) {
+      const int kk = i / (kPCS / 4), j4 = i - kk * (kPCS / 4);
+      const float4 w4 = ldg4(a.lstm_kernel + (size_t)(kgp * a.KS + kk) * 4 * R + cgp * kPCS + j4 * 4);
+      float* dst = wA + ((size_t)(kk >> 1) * kPCS + j4 * 4) * 2 + (kk & 1);
+      dst[0] = w4.x; dst[2] = w4.y; dst[4] = w4.z; dst[6] = w4.w;
     }
   }
   float sv = 0.f;
@@ -222,8 +272,13 @@ decode_loop_kernel(const PersistArgs a) {
   __syncthreads();
 
   // ------------------------------------------------------------------ step loop
+  const int trace_slot = (cta == 0) ? 0 : ((cta == a.B * a.S) ? 1 : -1);
+  auto stamp = [&](int t, int i) {
+    if (a.trace != nullptr && trace_slot >= 0 && tid == 0) a.trace[((size_t)t * 2 + trace_slot) * 16 + i] = clock64();
+  };
   for (int t = 0; t < a.max_it; ++t) {
     const int cur = t & 1;
+    stamp(t, 0);
     const float* c_prev = (t == 0) ? a.c0 : a.c[cur];
     const float* h_prev = (t == 0) ? a.h0 : a.h[cur];
     const float* ctx_prev = a.ctx[cur];
@@ -231,7 +286,7 @@ decode_loop_kernel(const PersistArgs a) {
     float* h_new = a.h[cur ^ 1];
     float* ctx_new = a.ctx[cur ^ 1];
 
-    // ============================ phase A: gates + LSTM cell
+    // ============================ phase A1: partial gate sums of this CTA's (K group, column group) block
     if (has_A) {
       if (tid < N) {
         const int n = tid;
@@ -244,110 +299,82 @@ decode_loop_kernel(const PersistArgs a) {
         s_xp[0][n] = (tk >= 0 && tk < a.V) ? a.emb + (size_t)tk * a.W : nullptr;
         s_xp[1][n] = ok ? ctx_prev + (size_t)sr * a.A : nullptr;
         s_xp[2][n] = ok ? h_prev + (size_t)sr * R : nullptr;
-        s_crow[n] = ok ? sr : -1;
       }
       __syncthreads();
-      const int nchunk = (KX + kPKC - 1) / kPKC;
-      const int XLD = kPKC + 4;                       // padded row stride (bank shift of one float4 per row)
-      auto issue = [&](int c) {
-        float* buf = tr + (size_t)(c & 1) * N * XLD;
-        const int kc0 = c * kPKC;
-        const int pieces = N * (kPKC / 4);
-        for (int p = tid; p < pieces; p += kPT) {
-          const int n = p / (kPKC / 4), q = p - n * (kPKC / 4);
-          const int kg = kc0 + q * 4;
-          const float* srcp = nullptr;
-          if (kg < KX) {
-            if (kg < a.W) { const float* b0 = s_xp[0][n]; srcp = b0 ? b0 + kg : nullptr; }
-            else if (kg < a.W + a.A) { const float* b1 = s_xp[1][n]; srcp = b1 ? b1 + (kg - a.W) : nullptr; }
-            else { const float* b2 = s_xp[2][n]; srcp = b2 ? b2 + (kg - a.W - a.A) : nullptr; }
-          }
-          cp_async16_zfill(buf + (size_t)n * XLD + q * 4, srcp ? (const void*)srcp : (const void*)a.emb, srcp != nullptr);
-        }
-        cp_async_commit();
-      };
-      float acc[kPMaxRPL][4];
-#pragma unroll
-      for (int r = 0; r < kPMaxRPL; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-      issue(0);
-      for (int c = 0; c < nchunk; ++c) {
-        if (c + 1 < nchunk) {
-          issue(c + 1);
-          cp_async_wait<1>();
-        } else {
-          cp_async_wait<0>();
-        }
-        __syncthreads();
-        const float* buf = tr + (size_t)(c & 1) * N * XLD;
-        const int kc0 = c * kPKC;
-        // a lane owns rows {ng, ng+8, ...} and, for every group of 4 consecutive columns jg, the 4 columns of it
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int kl = warp * 16 + j * 4;
-          if (kc0 + kl < KX) {
-            float4 x4[kPMaxRPL];
-#pragma unroll
-            for (int r = 0; r < kPMaxRPL; ++r) {
-              const int n = ng + 8 * r;
-              x4[r] = (r < rpl && n < N) ? *reinterpret_cast<const float4*>(buf + (size_t)n * XLD + kl)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            for (int jg = cg; jg * 4 < NC; jg += 4) {
-              // UPC == 4: NC = 16 and every lane has exactly one column group (jg = cg)
-              const float* wp = wA + (size_t)(kc0 + kl) * NC + jg * 4;
-              const float4 w0 = *reinterpret_cast<const float4*>(wp);
-              const float4 w1 = *reinterpret_cast<const float4*>(wp + NC);
-              const float4 w2 = *reinterpret_cast<const float4*>(wp + 2 * NC);
-              const float4 w3 = *reinterpret_cast<const float4*>(wp + 3 * NC);
-#pragma unroll
-              for (int r = 0; r < kPMaxRPL; ++r) {
-                if (r < rpl) {
-                  acc[r][0] = fmaf(x4[r].x, w0.x, acc[r][0]); acc[r][1] = fmaf(x4[r].x, w0.y, acc[r][1]);
-                  acc[r][2] = fmaf(x4[r].x, w0.z, acc[r][2]); acc[r][3] = fmaf(x4[r].x, w0.w, acc[r][3]);
-                  acc[r][0] = fmaf(x4[r].y, w1.x, acc[r][0]); acc[r][1] = fmaf(x4[r].y, w1.y, acc[r][1]);
-                  acc[r][2] = fmaf(x4[r].y, w1.z, acc[r][2]); acc[r][3] = fmaf(x4[r].y, w1.w, acc[r][3]);
-                  acc[r][0] = fmaf(x4[r].z, w2.x, acc[r][0]); acc[r][1] = fmaf(x4[r].z, w2.y, acc[r][1]);
-                  acc[r][2] = fmaf(x4[r].z, w2.z, acc[r][2]); acc[r][3] = fmaf(x4[r].z, w2.w, acc[r][3]);
-                  acc[r][0] = fmaf(x4[r].w, w3.x, acc[r][0]); acc[r][1] = fmaf(x4[r].w, w3.y, acc[r][1]);
-                  acc[r][2] = fmaf(x4[r].w, w3.z, acc[r][2]); acc[r][3] = fmaf(x4[r].w, w3.w, acc[r][3]);
-                }
-              }
-            }
-          }
-        }
-        __syncthreads();
+      stamp(t, 9);
+      const int KS = a.KS, XLD = KS + 4;               // padded row stride: one float4 of bank shift per row
+      const int kbase = kgp * KS;
+      float* xs = tr;                                  // [N][KS + 4]: this K group's slice of x = [emb ; ctx ; h]
+      for (int p = tid; p < N * (KS / 4); p += kPT) {
+        const int n = p / (KS / 4), q = p - n * (KS / 4);
+        const int kg = kbase + q * 4;
+        const float* srcp;
+        if (kg < a.W) { const float* b0 = s_xp[0][n]; srcp = b0 ? b0 + kg : nullptr; }
+        else if (kg < a.W + a.A) { const float* b1 = s_xp[1][n]; srcp = b1 ? b1 + (kg - a.W) : nullptr; }
+        else { const float* b2 = s_xp[2][n]; srcp = b2 ? b2 + (kg - a.W - a.A) : nullptr; }
+        cp_async16_zfill(xs + (size_t)n * XLD + q * 4, srcp ? (const void*)srcp : (const void*)a.emb, srcp != nullptr);
       }
-      // fixed-order reduction over the 16 K slices: red[warp][n][NC] (aliases the x buffers)
-      float* red = tr;
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+      stamp(t, 10);
+      // warp w owns columns [8w, 8w+8) of the block for ALL KS k's (no cross-warp reduction);
+      // a lane owns rows {ng, ng+8, ...} x 2 columns
+      float acc[kPMaxRPL][2];
+      {
+        const float* wl = wA + (size_t)(warp * 8 + cg * 2) * 2;
+        switch (rpl) {
+          case 1: gemm_a1<1>(xs, XLD, N, ng, wl, KS, acc); break;
+          case 2: gemm_a1<2>(xs, XLD, N, ng, wl, KS, acc); break;
+          case 3: gemm_a1<3>(xs, XLD, N, ng, wl, KS, acc); break;
+          default: gemm_a1<4>(xs, XLD, N, ng, wl, KS, acc); break;
+        }
+      }
 #pragma unroll
       for (int r = 0; r < kPMaxRPL; ++r) {
         const int n = ng + 8 * r;
-        if (r < rpl && n < N && cg * 4 < NC)
-          *reinterpret_cast<float4*>(red + ((size_t)warp * N + n) * NC + cg * 4) =
-              make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        if (r < rpl && n < N)
+          *reinterpret_cast<float2*>(a.part + ((size_t)kgp * N + n) * 4 * R + cgp * kPCS + warp * 8 + cg * 2) =
+              make_float2(acc[r][0], acc[r][1]);
       }
-      __syncthreads();
-      if (tid < N * a.UPC) {
-        const int n = tid / a.UPC, u = tid - n * a.UPC;
-        const int unit = cta * a.UPC + u;
-        float g[4];
+    }
+    stamp(t, 11);
+    if (!grid_barrier(a.bar, bar_target, G, &s_abort)) return;
+    stamp(t, 12);
+
+    // ============================ phase A2: fixed-order sum over the K groups + bias, LSTM cell -> c', h'
+    if (cta < R / 4 && tid < ((N * 16 + 31) & ~31)) {   // whole warps (full-mask shuffles below)
+      // thread = (row n, unit u, gate q): the 4 gate sums of a unit sit in 4 adjacent lanes
+      const bool row_ok = (tid >> 4) < N;
+      const int n = row_ok ? (tid >> 4) : N - 1, u = (tid >> 2) & 3, q = tid & 3;
+      const int unit = cta * 4 + u;
+      const float* pp = a.part + (size_t)n * 4 * R + q * R + unit;
+      const size_t kstride = (size_t)N * 4 * R;
+      float v[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float s = 0.f;
-          for (int w = 0; w < kPW; ++w) s += red[((size_t)w * N + n) * NC + q * a.UPC + u];
-          g[q] = s + __ldg(a.lstm_bias + q * R + unit);
-        }
-        const int cr = s_crow[n];
-        const float cp = cr >= 0 ? __ldcg(c_prev + (size_t)cr * R + unit) : 0.f;
+      for (int kg2 = 0; kg2 < 16; ++kg2) v[kg2] = (kg2 < a.KG) ? __ldcg(pp + kg2 * kstride) : 0.f;
+      float sacc = 0.f;
+#pragma unroll
+      for (int kg2 = 0; kg2 < 16; ++kg2) sacc += v[kg2];          // fixed order; + 0 for unused groups
+      sacc += __ldg(a.lstm_bias + q * R + unit);
+      const int l0 = lane & ~3;
+      const float g0 = __shfl_sync(0xffffffffu, sacc, l0), g1 = __shfl_sync(0xffffffffu, sacc, l0 + 1);
+      const float g2 = __shfl_sync(0xffffffffu, sacc, l0 + 2), g3 = __shfl_sync(0xffffffffu, sacc, l0 + 3);
+      if (q == 0 && row_ok) {
+        int sr;
+        if (a.greedy) sr = n;
+        else sr = (t == 0) ? n / k : __ldcg(a.src + n);
+        const int lim = (t == 0 && !a.greedy) ? a.B : N;
+        const float cp = (sr >= 0 && sr < lim) ? __ldcg(c_prev + (size_t)sr * R + unit) : 0.f;
         float cn, hn;
-        lstm_cell(g[0], g[1], g[2], g[3], cp, &cn, &hn);
+        lstm_cell(g0, g1, g2, g3, cp, &cn, &hn);
         c_new[(size_t)n * R + unit] = cn;
         h_new[(size_t)n * R + unit] = hn;
       }
     }
+    stamp(t, 1);
     if (!grid_barrier(a.bar, bar_target, G, &s_abort)) return;
+    stamp(t, 2);
 
     // ============================ phase B: [logits | q] = h' . [W_o | W_q] + bias
     if (has_B) {
@@ -373,8 +400,12 @@ decode_loop_kernel(const PersistArgs a) {
         cp_async_wait<0>();
         __syncthreads();
         float acc2[kPMaxRPL][2];
+        const float* hrow[kPMaxRPL];
 #pragma unroll
-        for (int r = 0; r < kPMaxRPL; ++r) acc2[r][0] = acc2[r][1] = 0.f;
+        for (int r = 0; r < kPMaxRPL; ++r) {
+          acc2[r][0] = acc2[r][1] = 0.f;
+          hrow[r] = hs + (size_t)min(ng + 8 * r, N - 1) * HLD;
+        }
 #pragma unroll
         for (int j = 0; j < R / kPW / 4; ++j) {
           const int kk = warp * (R / kPW) + j * 4;
@@ -383,14 +414,11 @@ decode_loop_kernel(const PersistArgs a) {
           for (int q = 0; q < 4; ++q) w2[q] = *reinterpret_cast<const float2*>(wB + (size_t)(kk + q) * 8 + cg * 2);
 #pragma unroll
           for (int r = 0; r < kPMaxRPL; ++r) {
-            const int n = ng + 8 * r;
-            if (r < rpl && n < N) {
-              const float4 x = *reinterpret_cast<const float4*>(hs + (size_t)n * HLD + kk);
-              acc2[r][0] = fmaf(x.x, w2[0].x, acc2[r][0]); acc2[r][1] = fmaf(x.x, w2[0].y, acc2[r][1]);
-              acc2[r][0] = fmaf(x.y, w2[1].x, acc2[r][0]); acc2[r][1] = fmaf(x.y, w2[1].y, acc2[r][1]);
-              acc2[r][0] = fmaf(x.z, w2[2].x, acc2[r][0]); acc2[r][1] = fmaf(x.z, w2[2].y, acc2[r][1]);
-              acc2[r][0] = fmaf(x.w, w2[3].x, acc2[r][0]); acc2[r][1] = fmaf(x.w, w2[3].y, acc2[r][1]);
-            }
+            const float4 x = *reinterpret_cast<const float4*>(hrow[r] + kk);
+            acc2[r][0] = fmaf(x.x, w2[0].x, acc2[r][0]); acc2[r][1] = fmaf(x.x, w2[0].y, acc2[r][1]);
+            acc2[r][0] = fmaf(x.y, w2[1].x, acc2[r][0]); acc2[r][1] = fmaf(x.y, w2[1].y, acc2[r][1]);
+            acc2[r][0] = fmaf(x.z, w2[2].x, acc2[r][0]); acc2[r][1] = fmaf(x.z, w2[2].y, acc2[r][1]);
+            acc2[r][0] = fmaf(x.w, w2[3].x, acc2[r][0]); acc2[r][1] = fmaf(x.w, w2[3].y, acc2[r][1]);
           }
         }
 #pragma unroll
@@ -413,7 +441,9 @@ decode_loop_kernel(const PersistArgs a) {
       }
       cp_async_wait<0>();
     }
+    stamp(t, 3);
     if (!grid_barrier(a.bar, bar_target, G, &s_abort)) return;
+    stamp(t, 4);
 
     // ============================ phase C1: attention scores  ||  beam / greedy selection
     if (has_C) {
@@ -497,21 +527,28 @@ decode_loop_kernel(const PersistArgs a) {
           }
         }
       }
-    } else if (sel_cta) {
+    }
+    stamp(t, 5);
+    // The selection CTAs only ARRIVE at this barrier and run the beam / greedy step while the others do
+    // phase C2: the step's outputs (tokens, parents, finished counts) are first read after the next barrier.
+    if (sel_cta) {
+      grid_arrive(a.bar, bar_target, G);
       const int si = cta - a.B * a.S;
       if (!a.greedy) {
         if (tid < 256)
-          beam_step_block<true>(s_beam, tid, si, a.lq, LQ, k, a.V, a.eos, a.lpw, a.cum, a.fin, a.len,
-                                a.sc + (size_t)t * N, a.step_ids + (size_t)t * N, a.parents + (size_t)t * N, a.tok,
-                                a.src, a.fin_count, t);
+          beam_step_block<true>(s_beam, tr, a.tr_floats, tid, si, a.lq, LQ, k, a.V, a.eos, a.lpw, a.cum, a.fin,
+                                a.len, a.sc + (size_t)t * N, a.step_ids + (size_t)t * N, a.parents + (size_t)t * N,
+                                a.tok, a.src, a.fin_count, t);
       } else {
         if (tid < 128)
           greedy_step_block<true>(s_greedy, tid, si, a.lq, LQ, a.V, a.eos, a.step_ids + (size_t)t * N,
                                   a.logits_out ? a.logits_out + (size_t)t * N * a.V : nullptr, a.tok, a.fin,
                                   a.fin_count, t);
       }
+    } else if (!grid_barrier(a.bar, bar_target, G, &s_abort)) {
+      return;
     }
-    if (!grid_barrier(a.bar, bar_target, G, &s_abort)) return;
+    stamp(t, 6);
 
     // ============================ phase C2: softmax over positions, history, context
     if (has_C) {
@@ -603,7 +640,9 @@ decode_loop_kernel(const PersistArgs a) {
         }
       }
     }
+    stamp(t, 7);
     if (!grid_barrier(a.bar, bar_target, G, &s_abort)) return;
+    stamp(t, 8);
 
     // every row finished in this step -> the loop ends (dynamic_decode's all(finished))
     if (__ldcg(a.fin_count + t) >= N) break;
@@ -615,8 +654,8 @@ decode_loop_kernel(const PersistArgs a) {
 // ---------------------------------------------------------------------------
 struct PersistPlan {
   bool ok = false;
-  int G, nA, UPC, CB, nB, S, rps, cps, nh_max, keys_res, vals_res;
-  int off_wA, off_c, off_keys, off_skk, off_vals, off_tr;
+  int G, KG, KS, CB, nB, S, rps, cps, nh_max, keys_res, vals_res;
+  int off_wA, off_c, off_keys, off_skk, off_vals, off_tr, tr_floats;
   size_t smem_bytes;
 };
 
@@ -631,10 +670,12 @@ static PersistPlan persist_plan(comic_handle_t h, int B, int k, bool greedy) {
   p.G = h->num_sms;
   const int n_sel = B;   // beam: one CTA per image; greedy: one per row (k == 1)
   if (2 * B > p.G || p.G - n_sel < B) return p;
-  p.UPC = 1;
-  while (R / p.UPC > p.G) p.UPC *= 2;
-  if (p.UPC > 4) return p;                              // phase-A lanes own one 4-column group: 4*UPC <= 16
-  p.nA = R / p.UPC;
+  // phase A: (K group, 128-column group) blocks of the LSTM kernel, one per CTA
+  const int n_colgrp = 4 * R / kPCS;
+  p.KG = p.G / n_colgrp;
+  while (p.KG > 1 && h->KX % (4 * p.KG) != 0) --p.KG;
+  if (p.KG < 1 || R / 4 > p.G) return p;
+  p.KS = h->KX / p.KG;
   p.CB = round_up((h->LQ + p.G - 1) / p.G, 8);
   p.nB = (h->LQ + p.CB - 1) / p.CB;
   p.S = (p.G - n_sel) / B;
@@ -655,7 +696,7 @@ static PersistPlan persist_plan(comic_handle_t h, int B, int k, bool greedy) {
   if (p.nh_max > kPMaxHeads) return p;
   if (k * (p.cps / 4) > kPT) return p;
   // transient region: max over the phase layouts (floats)
-  size_t trA = (size_t)2 * N * (kPKC + 4), trAr = (size_t)kPW * N * 4 * p.UPC;
+  size_t trA = (size_t)N * (p.KS + 4), trAr = 0;
   size_t trB = (size_t)N * (R + 4) + (size_t)R * 8 + (size_t)kPW * N * 8;
   size_t trC1 = (size_t)2 * k * R + 32;
   size_t trC2 = (size_t)k * p.nh_max * M + 4 + (size_t)kPT * 4;
@@ -669,12 +710,13 @@ static PersistPlan persist_plan(comic_handle_t h, int B, int k, bool greedy) {
     p.keys_res = attempt < 2;
     p.vals_res = attempt < 1;
     size_t off = 0;
-    p.off_wA = (int)off; off += (size_t)h->KX * 4 * p.UPC;
+    p.off_wA = (int)off; off += (size_t)p.KS * kPCS;
     p.off_c = (int)off; off += 3 * (size_t)R;
     p.off_keys = (int)off; off += p.keys_res ? (size_t)p.rps * R : 0;
     p.off_skk = (int)off; off += p.keys_res ? (size_t)round_up(p.rps, 4) : 0;
     p.off_vals = (int)off; off += p.vals_res ? (size_t)M * p.cps : 0;
     p.off_tr = (int)off; off += tr;
+    p.tr_floats = (int)tr;
     if (off <= budget) {
       p.smem_bytes = off * sizeof(float);
       p.ok = true;
@@ -722,11 +764,12 @@ int decode_persistent(comic_handle_t h, const PersistCall& pc, cudaStream_t st) 
   for (int i = 0; i < 2; ++i) { a.c[i] = pc.c[i]; a.h[i] = pc.h[i]; a.ctx[i] = pc.ctx[i]; }
   a.lq = pc.lq; a.scores = pc.scores; a.hist = pc.hist; a.tok = pc.tok; a.src = pc.src; a.cum = pc.cum;
   a.fin = pc.fin; a.len = pc.len; a.fin_count = pc.fin_count; a.step_ids = pc.step_ids; a.parents = pc.parents;
-  a.sc = pc.sc; a.logits_out = pc.logits_out; a.bar = pc.bar;
-  a.nA = p.nA; a.UPC = p.UPC; a.CB = p.CB; a.nB = p.nB; a.S = p.S; a.rps = p.rps; a.cps = p.cps;
+  a.sc = pc.sc; a.logits_out = pc.logits_out; a.bar = pc.bar; a.trace = pc.trace;
+  h->last_trace = pc.trace; h->last_trace_steps = pc.trace ? pc.max_it : 0;
+  a.KG = p.KG; a.KS = p.KS; a.part = pc.part; a.CB = p.CB; a.nB = p.nB; a.S = p.S; a.rps = p.rps; a.cps = p.cps;
   a.nh_max = p.nh_max; a.keys_res = p.keys_res; a.vals_res = p.vals_res; a.n_sel = pc.B;
   a.off_wA = p.off_wA; a.off_c = p.off_c; a.off_keys = p.off_keys; a.off_skk = p.off_skk; a.off_vals = p.off_vals;
-  a.off_tr = p.off_tr;
+  a.off_tr = p.off_tr; a.tr_floats = p.tr_floats;
   COMIC_CHECK_CUDA(cudaMemsetAsync(pc.bar, 0, 2 * sizeof(unsigned), st));
   cudaError_t e = cudaErrorInvalidValue;
   {

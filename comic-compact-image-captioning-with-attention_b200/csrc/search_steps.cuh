@@ -67,23 +67,36 @@ struct BeamStepSmem {
 
 // One image's beam step, executed by EXACTLY the first 256 threads of the CTA (tid < 256);
 // CG = true reads the logits with ld.global.cg (written by other CTAs of the same launch).
+// `stage` (capacity stage_cap floats, shared memory): when the image's k logits rows fit they are copied
+// there once and every later pass reads shared memory; the arithmetic and its order do not change.
 template <bool CG>
-__device__ __forceinline__ void beam_step_block(BeamStepSmem& S, int tid, int b, const float* __restrict__ logits, int ld,
+__device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, int stage_cap, int tid, int b,
+                                                const float* __restrict__ logits, int ld,
                                                 int k, int V, int eos, float lpw, float* __restrict__ log_probs,
                                                 uint8_t* __restrict__ finished, long long* __restrict__ lengths,
                                                 float* __restrict__ scores_out, int* __restrict__ word_out,
                                                 int* __restrict__ parent_out, int* __restrict__ tok_next,
                                                 int* __restrict__ src_next, int* fin_count, int t) {
   const int lane = tid & 31, warp = tid >> 5;
-  auto ld_logit = [&](const float* p) -> float { return CG ? __ldcg(p) : *p; };
+  const bool staged = stage != nullptr && k * V <= stage_cap;
+  const float* base = logits + (size_t)b * k * ld;     // row j of this image: base + j * ldr
+  int ldr = ld;
+  if (staged) {
+    for (int j = 0; j < k; ++j)
+      for (int i = tid; i < V; i += 256) stage[j * V + i] = CG ? __ldcg(base + (size_t)j * ld + i) : base[(size_t)j * ld + i];
+    base = stage;
+    ldr = V;
+  }
+  auto ld_logit = [&](const float* p) -> float { return (CG && !staged) ? __ldcg(p) : *p; };
   if (tid < k) {
     S.s_cum[tid] = log_probs[b * k + tid];
     S.s_fin[tid] = finished[b * k + tid];
     S.s_len[tid] = lengths[b * k + tid];
   }
+  if (staged) group_sync(1, 256);
   // log-softmax statistics per beam row: max, log(sum(exp(x - max)))
   for (int j = 0; j < k; ++j) {
-    const float* row = logits + (size_t)(b * k + j) * ld;
+    const float* row = base + (size_t)j * ldr;
     float mx = -INFINITY;
     for (int i = tid; i < V; i += 256) mx = fmaxf(mx, ld_logit(row + i));
     mx = warp_max(mx);
@@ -111,7 +124,7 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, int tid, int b,
     int j = idx / V, w = idx - j * V;
     float lp;
     if (S.s_fin[j]) lp = (w == eos) ? 0.0f : -FLT_MAX;
-    else lp = (ld_logit(logits + (size_t)(b * k + j) * ld + w) - S.s_max[j]) - S.s_lse[j];
+    else lp = (ld_logit(base + (size_t)j * ldr + w) - S.s_max[j]) - S.s_lse[j];
     return S.s_cum[j] + lp;
   };
   auto score_of = [&](int idx, float tot) -> float {

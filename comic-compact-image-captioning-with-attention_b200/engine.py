@@ -90,6 +90,7 @@ SIGNATURES = {
     'comic_launch_count': (_I, [_P, C.POINTER(C.c_int64)]),
     'comic_set_precision': (_I, [_P, _I]),
     'comic_set_option': (_I, [_P, _I, _I]),
+    'comic_decode_trace': (_I, [_P, _P, _I, _P, _P]),
     'comic_train_workspace_bytes': (_I, [_P, _I, _I, C.POINTER(_SZ)]),
     'comic_dropout_masks': (_I, [_P, _P, _SZ, _F, C.c_uint64, C.c_uint64, _P]),
     'comic_train_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, C.POINTER(ComicTrainMasks), _F, _P, _P, _P,
@@ -399,7 +400,16 @@ class Engine(object):
         self._check(self.lib.comic_set_precision(self._h, {'f32': 0, 'tf32x3': 1, 'split': 1, 'fast': 2}[mode]))
 
     def set_option(self, name, value):
-        self._check(self.lib.comic_set_option(self._h, {'fused_attn_min_images': 0, 'enc_chunk_stem': 1, 'enc_chunk_28': 2, 'enc_chunk_14': 3, 'persistent_max_rows': 4}[name], int(value)))
+        self._check(self.lib.comic_set_option(self._h, {'fused_attn_min_images': 0, 'enc_chunk_stem': 1, 'enc_chunk_28': 2, 'enc_chunk_14': 3, 'persistent_max_rows': 4, 'persistent_trace': 5}[name], int(value)))
+
+    def decode_trace(self, max_steps=256):
+        """Per-phase clock stamps of the last persistent decode call: int64 array [steps, 2, 16]."""
+        import numpy as np
+        out = np.zeros((max_steps, 2, 16), np.int64)
+        n = C.c_int()
+        self._check(self.lib.comic_decode_trace(self._h, out.ctypes.data_as(C.c_void_p), max_steps, C.byref(n),
+                                                self.stream()))
+        return out[:n.value]
 
     def profile_enable(self, tags):
         mask = 0

@@ -126,7 +126,15 @@ int comic_set_precision(comic_handle_t h, int mode);
 #define COMIC_OPT_ENC_CHUNK_14 3            /* ... Mixed_4b..5c (default 512); set before comic_workspace_bytes */
 #define COMIC_OPT_PERSISTENT_MAX_ROWS 4      /* decode loops with batch*beam <= this run as ONE cooperative kernel
                                              * (default 32, the kernel's limit; 0 = always one launch per step op) */
+#define COMIC_OPT_PERSISTENT_TRACE 5         /* 1: the persistent loop records per-phase clock stamps (diagnostics) */
 int comic_set_option(comic_handle_t h, int option, int value);
+
+/* Diagnostics: clock64 stamps of the last persistent decode call, [steps][2][16] int64 (CTA 0 and the first
+ * selection CTA); slot order in time: 0 step start, 9 row pointers, 10 x slice loaded, 11 partial gates, 12 barrier,
+ * 1 LSTM cell, 2 barrier, 3 logits|query, 4 barrier, 5 scores, 6 barrier, 7 softmax+context, 8 barrier.
+ * Valid until the workspace of that call is reused.  Synchronises the stream.  *steps = 0 when tracing was off or
+ * the per-step path ran. */
+int comic_decode_trace(comic_handle_t h, int64_t* out, int max_steps, int* steps, void* stream);
 
 /* mode: 0 encode, 1 decode_greedy, 2 decode_beam, 3 decode_step, 4 rnn_init,
  * 5 gemm_f32 (B = N, k = K of the GEMM). */

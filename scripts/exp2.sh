@@ -1,12 +1,12 @@
 #!/bin/bash
 # persistent decode loop: parity first (short timeouts: a grid-barrier bug must not eat the budget), then bench
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "persistent" > gpurun_out/pytest_persist.log 2>&1; rc=$?; echo "pytest exit $rc" >> gpurun_out/pytest_persist.log; tail -25 gpurun_out/pytest_persist.log
+timeout 90 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "persistent" > gpurun_out/pytest_persist.log 2>&1; rc=$?; echo "pytest exit $rc" >> gpurun_out/pytest_persist.log; tail -25 gpurun_out/pytest_persist.log
 if [ $rc -ne 0 ]; then exit 1; fi
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; rc=$?; echo "pytest exit $rc" >> gpurun_out/pytest_gpu.log; tail -4 gpurun_out/pytest_gpu.log
 if [ $rc -ne 0 ]; then exit 1; fi
 run() { tag=$1; shift; timeout 120 python bench.py --no-cpu-baseline --breakdown "$@" > gpurun_out/exp2_$tag.json 2> gpurun_out/exp2_$tag.err || { echo "== $tag FAILED"; tail -3 gpurun_out/exp2_$tag.err; return; }; echo "== $tag"; cat gpurun_out/exp2_$tag.err | tr '\n' ';' ; python -c "import json,sys; d=json.load(open('gpurun_out/exp2_$tag.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['decoder_step_us'], d['roofline'])"; }
 run b8 --batch 8 --steps 20 --warmup 5
-run b8_perstep --batch 8 --steps 20 --warmup 5 --opt persistent_max_rows=0
-run b512
-run b512_big --opt enc_chunk_stem=128 --opt enc_chunk_28=512 --opt enc_chunk_14=512
+
+
+
