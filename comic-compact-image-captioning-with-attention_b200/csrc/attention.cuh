@@ -137,50 +137,60 @@ __device__ __forceinline__ void ln_tanh_scores(const float (&kc)[CPL], const flo
                                                const float* __restrict__ qs, const float* __restrict__ qgs,
                                                const float* __restrict__ cs, const float* __restrict__ sqq, float skk,
                                                int R, int lane, float sv, float inv_R, float (&out)[KB]) {
+  // The arithmetic runs on the packed fp32 pipe (add/mul/fma.f32x2: two lanes of work per issue slot; a plain
+  // FFMA issues every other cycle per scheduler on sm_100), which moves the bound from the FMA pipe to MUFU.
   constexpr int G4 = CPL / 4;
-  float dot[KB];
+  float2 dot2[KB];
 #pragma unroll
-  for (int j = 0; j < KB; ++j) dot[j] = 0.f;
+  for (int j = 0; j < KB; ++j) dot2[j] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int g = 0; g < G4; ++g) {
+    const float2 k01 = make_float2(kc[g * 4 + 0], kc[g * 4 + 1]), k23 = make_float2(kc[g * 4 + 2], kc[g * 4 + 3]);
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
       const float4 q = *reinterpret_cast<const float4*>(qs + (size_t)j * R + (g * 32 + lane) * 4);
-      dot[j] = fmaf(kc[g * 4 + 0], q.x, dot[j]); dot[j] = fmaf(kc[g * 4 + 1], q.y, dot[j]);
-      dot[j] = fmaf(kc[g * 4 + 2], q.z, dot[j]); dot[j] = fmaf(kc[g * 4 + 3], q.w, dot[j]);
+      dot2[j] = __ffma2_rn(k01, make_float2(q.x, q.y), dot2[j]);
+      dot2[j] = __ffma2_rn(k23, make_float2(q.z, q.w), dot2[j]);
     }
   }
+  float dot[KB];
+#pragma unroll
+  for (int j = 0; j < KB; ++j) dot[j] = dot2[j].x + dot2[j].y;
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
 #pragma unroll
     for (int j = 0; j < KB; ++j) dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
   }
-  float rstd[KB];
+  float2 rstd2[KB];
 #pragma unroll
   for (int j = 0; j < KB; ++j) {
     const float ss = fmaxf(fmaf(2.0f, dot[j], skk + sqq[j]), 0.f);
-    rstd[j] = rsqrtf(ss * inv_R + 1e-12f);
+    const float rs = rsqrtf(ss * inv_R + 1e-12f);
+    rstd2[j] = make_float2(rs, rs);
     out[j] = FAST ? 0.f : sv;
   }
+  const float2 one2 = make_float2(1.0f, 1.0f);
 #pragma unroll
   for (int g = 0; g < G4; ++g) {
     const float4 bt = *reinterpret_cast<const float4*>(cs + R + (g * 32 + lane) * 4);
     const float4 vv = *reinterpret_cast<const float4*>(cs + 2 * R + (g * 32 + lane) * 4);
+    const float2 kg01 = make_float2(kg[g * 4 + 0], kg[g * 4 + 1]), kg23 = make_float2(kg[g * 4 + 2], kg[g * 4 + 3]);
 #pragma unroll
     for (int j = 0; j < KB; ++j) {
       const float4 q = *reinterpret_cast<const float4*>(qgs + (size_t)j * R + (g * 32 + lane) * 4);
-      const float y0 = fmaf(kg[g * 4 + 0] + q.x, rstd[j], bt.x), y1 = fmaf(kg[g * 4 + 1] + q.y, rstd[j], bt.y);
-      const float y2 = fmaf(kg[g * 4 + 2] + q.z, rstd[j], bt.z), y3 = fmaf(kg[g * 4 + 3] + q.w, rstd[j], bt.w);
+      const float2 y01 = __ffma2_rn(__fadd2_rn(kg01, make_float2(q.x, q.y)), rstd2[j], make_float2(bt.x, bt.y));
+      const float2 y23 = __ffma2_rn(__fadd2_rn(kg23, make_float2(q.z, q.w)), rstd2[j], make_float2(bt.z, bt.w));
       if (FAST) {
-        out[j] = fmaf(tanh_approx(y0), vv.x, out[j]); out[j] = fmaf(tanh_approx(y1), vv.y, out[j]);
-        out[j] = fmaf(tanh_approx(y2), vv.z, out[j]); out[j] = fmaf(tanh_approx(y3), vv.w, out[j]);
+        out[j] = fmaf(tanh_approx(y01.x), vv.x, out[j]); out[j] = fmaf(tanh_approx(y01.y), vv.y, out[j]);
+        out[j] = fmaf(tanh_approx(y23.x), vv.z, out[j]); out[j] = fmaf(tanh_approx(y23.y), vv.w, out[j]);
       } else {
-        const float x0 = ex2_approx(fminf(y0, 30.0f)) + 1.0f, x1 = ex2_approx(fminf(y1, 30.0f)) + 1.0f;
-        const float x2 = ex2_approx(fminf(y2, 30.0f)) + 1.0f, x3 = ex2_approx(fminf(y3, 30.0f)) + 1.0f;
-        const float n01 = fmaf(x0, vv.y, x1 * vv.x), n23 = fmaf(x2, vv.w, x3 * vv.z);
-        const float p01 = x0 * x1, p23 = x2 * x3;
-        const float rp = rcp_approx(p01 * p23);
-        out[j] = fmaf(rp, fmaf(p01, n23, p23 * n01), out[j]);
+        // pairs (x0, x2) and (x1, x3): p = (x0 x1, x2 x3), n = (x0 vv1 + x1 vv0, x2 vv3 + x3 vv2)
+        const float2 xa = __fadd2_rn(make_float2(ex2_approx(fminf(y01.x, 30.0f)), ex2_approx(fminf(y23.x, 30.0f))), one2);
+        const float2 xb = __fadd2_rn(make_float2(ex2_approx(fminf(y01.y, 30.0f)), ex2_approx(fminf(y23.y, 30.0f))), one2);
+        const float2 p = __fmul2_rn(xa, xb);
+        const float2 n = __ffma2_rn(xa, make_float2(vv.y, vv.w), __fmul2_rn(xb, make_float2(vv.x, vv.z)));
+        const float rp = rcp_approx(p.x * p.y);
+        out[j] = fmaf(rp, fmaf(p.x, n.y, p.y * n.x), out[j]);
       }
     }
   }
