@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, os.environ.get('COMIC_B200_LIBNAME', 'libcomic_b200.so'))   # env: experiment builds only
 _OBJ_PREFIX = (os.path.splitext(os.path.basename(LIB))[0] + '_') if 'COMIC_B200_LIBNAME' in os.environ else ''
-SOURCES = ['api.cu', 'encoder.cu', 'decoder.cu', 'persistent.cu', 'train.cu']
+SOURCES = ['api.cu', 'encoder.cu', 'encoder_train.cu', 'decoder.cu', 'persistent.cu', 'train.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC']
 

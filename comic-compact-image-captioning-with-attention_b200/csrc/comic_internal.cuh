@@ -135,6 +135,18 @@ int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out,
                     float* mixed5c_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int encoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry);
 const BlockDesc* block_table();
+const comic_conv_desc_t* conv_table();
+struct EncBufs {
+  float *a, *b, *t1, *t2, *p;   // ping, pong, branch temporaries (Branch_1/2 1x1 outputs), pooled input
+};
+void same_pads(int n, int k, int s, int* out, int* before);
+int run_conv(comic_handle_t h, const float* x, int B, int H, int W, int ldx, int ci, float* dst, int ld_dst, int coff,
+             int* Ho_out, int* Wo_out, cudaStream_t st);
+int run_maxpool(comic_handle_t h, const float* x, float* y, int B, int H, int W, int C, int k, int s, int* Ho_out,
+                int* Wo_out, cudaStream_t st);
+void run_pad_c3_c4(comic_handle_t h, const float* img, float* dst, size_t npix, cudaStream_t st);
+void run_avgpool_global(comic_handle_t h, const float* x, float* y, int B, int HW, int C, cudaStream_t st);
+int run_block(comic_handle_t h, int bi, const float* x, float* y, int B, int S, EncBufs& eb, cudaStream_t st);
 
 // decoder.cu
 struct StepBufs {

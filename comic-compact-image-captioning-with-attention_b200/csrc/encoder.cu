@@ -238,16 +238,12 @@ __global__ void ln_tanh_rows_kernel(const float* __restrict__ x, const float* __
 // --------------------------------------------------------------------------
 // Forward plan.
 // --------------------------------------------------------------------------
-static inline void same_pads(int n, int k, int s, int* out, int* before) {
+void same_pads(int n, int k, int s, int* out, int* before) {
   *out = (n + s - 1) / s;
   int pad = (*out - 1) * s + k - n;
   if (pad < 0) pad = 0;
   *before = pad / 2;
 }
-
-struct EncBufs {
-  float *a, *b, *t1, *t2, *p;   // ping, pong, branch temporaries, pooled input
-};
 
 // The forward runs in three stages with their own image-chunk sizes: the stem (huge
 // activations: 3.2 MB / image after Conv2d_1a) in small chunks, the 28x28 blocks in medium
@@ -285,7 +281,7 @@ int encoder_workspace_bytes(comic_handle_t h, int B, size_t* bytes) {
   return COMIC_OK;
 }
 
-static int run_conv(comic_handle_t h, const float* x, int B, int H, int W, int ldx, int ci, float* dst,
+int run_conv(comic_handle_t h, const float* x, int B, int H, int W, int ldx, int ci, float* dst,
                     int ld_dst, int coff, int* Ho_out, int* Wo_out, cudaStream_t st) {
   const comic_conv_desc_t& d = kConvs[ci];
   AConv a;
@@ -317,7 +313,7 @@ static int run_conv(comic_handle_t h, const float* x, int B, int H, int W, int l
   return COMIC_OK;
 }
 
-static int run_maxpool(comic_handle_t h, const float* x, float* y, int B, int H, int W, int C, int k, int s,
+int run_maxpool(comic_handle_t h, const float* x, float* y, int B, int H, int W, int C, int k, int s,
                        int* Ho_out, int* Wo_out, cudaStream_t st) {
   int Ho, Wo, pt, pl;
   same_pads(H, k, s, &Ho, &pt);
@@ -339,8 +335,18 @@ static int run_maxpool(comic_handle_t h, const float* x, float* y, int B, int H,
   return COMIC_OK;
 }
 
+void run_pad_c3_c4(comic_handle_t h, const float* img, float* dst, size_t npix, cudaStream_t st) {
+  Prof pf(h, T_POOL, st);
+  pad_c3_c4_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(img, dst, npix);
+}
+
+void run_avgpool_global(comic_handle_t h, const float* x, float* y, int B, int HW, int C, cudaStream_t st) {
+  Prof pf(h, T_POOL, st);
+  avgpool_global_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(x, y, B, HW, C);
+}
+
 // One inception block: x [B,S,S,cin] -> y [B,S,S,cout].
-static int run_block(comic_handle_t h, int bi, const float* x, float* y, int B, int S, EncBufs& eb,
+int run_block(comic_handle_t h, int bi, const float* x, float* y, int B, int S, EncBufs& eb,
                      cudaStream_t st) {
   const BlockDesc& bd = block_table()[bi];
   int cout = bd.b0 + bd.b1b + bd.b2b + bd.b3;

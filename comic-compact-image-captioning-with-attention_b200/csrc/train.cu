@@ -586,6 +586,7 @@ struct TrainBufs {
   float *dlq, *dG, *demb, *gH, *gC, *gCtx, *gHp, *dHout, *dxh, *ds, *dqpart, *cpart, *dTacc, *maprows, *rowloss;
   float *dkeys, *dvals, *keys, *vals, *dx0;
   float *KT, *outqT, *xh, *xhT, *hdT, *fmT, *embT, *dOutQ, *part, *scal;
+  float *encT, *dfm_tmp;   // cnn_finetune: transposed W_k / W_v / W_I, second dfm term (independent)
   size_t part_floats;
   int S, rows_pad;
 };
@@ -644,6 +645,11 @@ static void carve_train(comic_handle_t h, Carver& cv, int B, int T_run, TrainBuf
   tb.part_floats = (size_t)16 * B * (KX > 4 * R ? KX : 4 * R) + (size_t)4 * 1024 * 1024;
   tb.part = cv.take<float>(tb.part_floats);
   tb.scal = cv.take<float>(1024);
+  {
+    size_t a = (size_t)h->R * h->C, b = (size_t)(h->W + h->A) * h->E;
+    tb.encT = cv.take<float>(a > b ? a : b);
+    tb.dfm_tmp = cv.take<float>(h->cfg.fm_projection == 2 ? (size_t)B * h->M * h->C : 1);
+  }
 }
 
 int train_workspace_bytes(comic_handle_t h, int B, int T_run, size_t* bytes) {
@@ -891,6 +897,47 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
     attn_maps_kernel<<<g, 256, 0, st>>>(tb.apost, T_run, B, h->H, M, attn_out);
     h->launches++;
   }
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+extern "C" int comic_train_encoder_grads(comic_handle_t h, int B, int T_run, float* dfm_out, float* dim_embed_out,
+                                         void* ws, size_t ws_bytes, void* stream) {
+  COMIC_REQUIRE(h && h->bound && dfm_out && dim_embed_out && ws, COMIC_E_BADARG, "train_encoder_grads: bad argument");
+  COMIC_REQUIRE(h->cfg.init_method == 0 && !h->cfg.legacy, COMIC_E_UNSUPPORTED,
+                "train_encoder_grads: only the first_input rnn init is built");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t need;
+  train_workspace_bytes(h, B, T_run, &need);
+  COMIC_REQUIRE(ws_bytes >= need, COMIC_E_WORKSPACE, "train_encoder_grads: workspace %zu < %zu", ws_bytes, need);
+  Carver cv(ws);
+  TrainBufs tb;
+  carve_train(h, cv, B, T_run, tb);
+  const int R = h->R, C = h->C, E = h->E, XA = h->W + h->A, M = h->M;
+  const int bm = B * M;
+  int rc;
+  // dfm = dkeys . W_k^T  (tied: dkeys already carries the value-path gradient)
+  transpose(h->w.memory_kernel, C, R, R, tb.encT, C, st);
+  if ((rc = train_gemm(h, tb.dkeys, R, tb.encT, C, dfm_out, C, bm, C, R, tb.part, tb.part_floats, st))) return rc;
+  size_t n = (size_t)bm * C;
+  if (h->cfg.fm_projection == 2) {
+    transpose(h->w.value_kernel, C, R, R, tb.encT, C, st);
+    if ((rc = train_gemm(h, tb.dvals, R, tb.encT, C, tb.dfm_tmp, C, bm, C, R, tb.part, tb.part_floats, st))) return rc;
+    add_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dfm_out, tb.dfm_tmp, n);
+    h->launches += 2;
+  } else if (h->cfg.fm_projection == 0) {
+    add_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dfm_out, tb.dvals, n);   // values = fm itself
+    h->launches++;
+  }
+  // dim_embed = dx0 . W_I^T
+  transpose(h->w.init_weight, E, XA, XA, tb.encT, E, st);
+  if ((rc = train_gemm(h, tb.dx0, XA, tb.encT, E, dim_embed_out, E, B, E, XA, tb.part, tb.part_floats, st))) return rc;
+  h->launches += 2;
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;
 }

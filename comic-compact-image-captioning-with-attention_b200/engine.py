@@ -56,6 +56,10 @@ class ComicDecoderGrads(C.Structure):
     _fields_ = [(n, _FP) for n in GRAD_FIELDS]
 
 
+class ComicCnnGrads(C.Structure):
+    _fields_ = [('conv_w', _FP * NUM_CONVS), ('bn_beta', _FP * NUM_CONVS)]
+
+
 class ComicConvDesc(C.Structure):
     _fields_ = [('k', C.c_int32), ('stride', C.c_int32), ('c_in', C.c_int32), ('c_out', C.c_int32)]
 
@@ -98,6 +102,11 @@ SIGNATURES = {
     'comic_l2_regularise': (_I, [_P, _P, _P, _SZ, _F, _P, _P, _SZ, _P]),
     'comic_adam_step': (_I, [_P, _P, _P, _P, _P, _SZ, _F, _F, _F, _F, _I, _F, _P]),
     'comic_refresh_packed': (_I, [_P, _P, _SZ, _P]),
+    'comic_refresh_packed_cnn': (_I, [_P, _P, _SZ, _P]),
+    'comic_train_encoder_grads': (_I, [_P, _I, _I, _P, _P, _P, _SZ, _P]),
+    'comic_encode_train_bytes': (_I, [_P, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
+    'comic_encode_train_fwd': (_I, [_P, _P, _I, _P, _P, _P, _SZ, _P, _SZ, _P]),
+    'comic_encode_bwd': (_I, [_P, _P, _I, _P, _P, _P, _SZ, C.POINTER(ComicCnnGrads), _P, _SZ, _P]),
     'comic_profile_enable': (_I, [_P, C.c_uint32]),
     'comic_profile_read': (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
@@ -474,6 +483,53 @@ class Engine(object):
             int(T_run), None if mk is None else C.byref(mk), float(map_loss_scale), _ptr(loss), _ptr(logits),
             _ptr(attn), C.byref(g), _ptr(ws), ws.numel(), self.stream()))
         return loss, logits, attn
+
+    # -- cnn_finetune (encoder forward-with-tape + backward) ---------------------
+    def encode_train(self, images):
+        """Forward that keeps every activation: -> (im_embed [B,1024], fm [B,196,C]); the tape stays
+        in this engine until `encode_bwd`."""
+        torch = self.torch
+        images = images.contiguous()
+        if images.dim() != 4 or tuple(images.shape[1:]) != (224, 224, 3):
+            raise ValueError('images must be [B,224,224,3] NHWC, got %s' % (tuple(images.shape),))
+        B = images.shape[0]
+        nt, nw = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.comic_encode_train_bytes(self._h, B, C.byref(nt), C.byref(nw)))
+        for key, n in (('enc_tape', nt.value), ('enc_train_ws', nw.value)):
+            if self._ws.get(key) is None or self._ws[key].numel() < n:
+                self._ws[key] = torch.empty(n, dtype=torch.uint8, device=self.device)
+        tape, ws = self._ws['enc_tape'], self._ws['enc_train_ws']
+        fm = self.f32(B, self.dims.M, self.dims.C)
+        emb = self.f32(B, self.dims.E)
+        self._check(self.lib.comic_encode_train_fwd(self._h, _ptr(images), B, _ptr(fm), _ptr(emb), _ptr(tape),
+                                                    tape.numel(), _ptr(ws), ws.numel(), self.stream()))
+        return emb, fm
+
+    def train_encoder_grads(self, B, T_run):
+        """d loss / d (fm, im_embed) of the `train_fwd_bwd` call that just ran (same B, T_run)."""
+        dfm = self.f32(B, self.dims.M, self.dims.C)
+        demb = self.f32(B, self.dims.E)
+        ws = self._ws['train']
+        self._check(self.lib.comic_train_encoder_grads(self._h, B, int(T_run), _ptr(dfm), _ptr(demb), _ptr(ws),
+                                                       ws.numel(), self.stream()))
+        return dfm, demb
+
+    def encode_bwd(self, images, dfm, dim_embed, conv_grads, beta_grads):
+        """Backward of the last `encode_train`: conv_grads / beta_grads are lists of 57 device tensors
+        (views into the flat gradient buffer) in comic_conv_table() order."""
+        B = images.shape[0]
+        g = ComicCnnGrads()
+        for i in range(NUM_CONVS):
+            g.conv_w[i] = C.c_void_p(conv_grads[i].data_ptr())
+            g.bn_beta[i] = C.c_void_p(beta_grads[i].data_ptr())
+        tape, ws = self._ws['enc_tape'], self._ws['enc_train_ws']
+        self._check(self.lib.comic_encode_bwd(self._h, _ptr(images.contiguous()), B, _ptr(dfm.contiguous()),
+                                              _ptr(dim_embed.contiguous()), _ptr(tape), tape.numel(), C.byref(g),
+                                              _ptr(ws), ws.numel(), self.stream()))
+
+    def refresh_packed_cnn(self):
+        self._check(self.lib.comic_refresh_packed_cnn(self._h, _ptr(self._packed), self._packed.numel(),
+                                                      self.stream()))
 
     def l2_regularise(self, params, grads, decay, reg_out):
         ws = self._ws.get('l2')

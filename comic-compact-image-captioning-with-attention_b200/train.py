@@ -1,4 +1,5 @@
-"""Training on the CUDA engine: `train_mode` = decoder | scst (frozen CNN).
+"""Training on the CUDA engine: `train_mode` = decoder | scst (frozen CNN) | cnn_finetune
+(InceptionV1 conv kernels + BN betas train too; src/train.py:241-250).
 
 Mirrors the pieces of the reference that surround one `sess.run(train_op)`:
   ModelBase._process_inputs        src/model_base.py:501-528  (inputs / targets / masks)
@@ -53,17 +54,28 @@ class Trainer(object):
 
     def __init__(self, config, weights, engine=None, with_cnn=True):
         self.c = c = config
-        if c.train_mode not in ('decoder', 'scst'):
-            raise NotImplementedError("train_mode '%s' (encoder backward) is not built on the CUDA path yet"
-                                      % c.train_mode)
+        if c.train_mode not in ('decoder', 'scst', 'cnn_finetune'):
+            raise ValueError("train_mode must be decoder | cnn_finetune | scst, got '%s'" % c.train_mode)
+        self.finetune_cnn = c.train_mode == 'cnn_finetune'
+        if self.finetune_cnn and not with_cnn:
+            raise ValueError('train_mode=cnn_finetune needs the CNN weights')
         self.engine = eng = engine or Engine(c)
         torch = self.torch = eng.torch
-        self.shapes = wts.decoder_shapes(c)
+        self.shapes = dict(wts.decoder_shapes(c))
+        self.n_decoder_vars = len(self.shapes)
+        if self.finetune_cnn:
+            # trainable CNN variables: conv kernels + BN betas (BN runs with is_training=False,
+            # src/model_base.py:71-77, so the moving statistics are constants)
+            for scope, k, _s, cin, cout in wts.cnn_conv_list():
+                self.shapes[wts.CNN + scope + '/weights'] = (k, k, cin, cout)
+                self.shapes[wts.CNN + scope + '/BatchNorm/beta'] = (cout,)
         self.offsets, off = {}, 0
         for name, shp in self.shapes.items():
             n = int(np.prod(shp)) if len(shp) else 1
             self.offsets[name] = (off, n, shp)
             off += (n + 3) // 4 * 4                     # 16-byte aligned views
+            if len(self.offsets) == self.n_decoder_vars:
+                self.n_decoder_flat = off
         self.n_flat = off
         self.params = torch.zeros(off, dtype=torch.float32, device=eng.device)
         self.grads = torch.zeros(off, dtype=torch.float32, device=eng.device)
@@ -77,7 +89,12 @@ class Trainer(object):
         fields = eng.variable_to_grad_field()
         self.grad_views = {}
         for name, (o, n, shp) in self.offsets.items():
-            self.grad_views[fields[name]] = self.grads[o:o + n]
+            if name in fields:
+                self.grad_views[fields[name]] = self.grads[o:o + n]
+        if self.finetune_cnn:
+            convs = wts.cnn_conv_list()
+            self.cnn_grad_w = [self.gradient(wts.CNN + sc + '/weights') for sc, *_ in convs]
+            self.cnn_grad_b = [self.gradient(wts.CNN + sc + '/BatchNorm/beta') for sc, *_ in convs]
         self.global_step = 0
         self.reg = torch.zeros(1, dtype=torch.float32, device=eng.device)
 
@@ -104,7 +121,7 @@ class Trainer(object):
 
     # -- one fwd + bwd (+ optimiser) ---------------------------------------------
     def forward_backward(self, fm, im_embed, captions, rewards=None, masks=None, keeps=(1.0, 1.0, 1.0),
-                         want_logits=False, want_attn=False):
+                         want_logits=False, want_attn=False, images=None):
         """captions [B,L] int32 host array.  Returns dict(loss=[total, xe, map, reg] device tensor, ...);
         gradients land in self.grads."""
         c, eng, torch = self.c, self.engine, self.torch
@@ -121,6 +138,15 @@ class Trainer(object):
         loss, logits, attn = eng.train_fwd_bwd(fm.contiguous(), im_embed.contiguous(), inputs_tm, targets_tm, coef_tm,
                                                lens_d, T_run, self.grad_views, masks, keeps, c.rnn_map_loss_scale,
                                                want_logits, want_attn)
+        if self.finetune_cnn:
+            if images is None:
+                raise ValueError('cnn_finetune: forward_backward needs the images of the last encode_train')
+            # chain rule into the encoder: d loss / d (fm, im_embed) -> conv kernel / beta gradients
+            dfm, demb = eng.train_encoder_grads(fm.shape[0], T_run)
+            eng.encode_bwd(images, dfm, demb, self.cnn_grad_w, self.cnn_grad_b)
+            mult = float(getattr(c, 'cnn_grad_multiplier', 1.0))
+            if mult != 1.0:                                  # gradient_multipliers (src/model_base.py:387-401)
+                self.grads[self.n_decoder_flat:].mul_(mult)
         if c.l2_decay > 0:
             eng.l2_regularise(self.params, self.grads, c.l2_decay, loss[3:4])
         loss[0:1] = loss[1:2] + loss[2:3] + loss[3:4]
@@ -136,18 +162,27 @@ class Trainer(object):
             lr = cosine_lr(self.global_step - 1, c.max_step, c.lr_start, c.lr_end)
         eng.adam_step(self.params, self.grads, self.adam_m, self.adam_v, lr, self.global_step, 0.9, 0.999,
                       c.adam_epsilon, 1.0 / world)
-        eng.refresh_packed()
+        if self.finetune_cnn:
+            eng.refresh_packed_cnn()
+        else:
+            eng.refresh_packed()
         return lr
 
     def step(self, images, captions, rewards=None, seed=None, lr=None):
-        """One `sess.run([train_op])`: frozen encoder forward, decoder fwd+bwd, optimiser."""
+        """One `sess.run([train_op])`: encoder forward (frozen, or with tape when fine-tuning), decoder
+        fwd+bwd (+ encoder backward), optimiser."""
         eng = self.engine
-        im_embed, fm = eng.encode(images)
+        if self.finetune_cnn:
+            images = eng.to_dev(images)
+            im_embed, fm = eng.encode_train(images)
+        else:
+            im_embed, fm = eng.encode(images)
         B = im_embed.shape[0]
         masks, keeps = None, (1.0, 1.0, 1.0)
         if seed is not None:
             _, _, _, lens = process_inputs(captions, self.c.token_type)
             masks, keeps = self.make_masks(B, int(lens.max()), seed)
-        out = self.forward_backward(fm, im_embed, captions, rewards, masks, keeps)
+        out = self.forward_backward(fm, im_embed, captions, rewards, masks, keeps,
+                                    images=images if self.finetune_cnn else None)
         out['lr'] = self.apply_gradients(lr)
         return out

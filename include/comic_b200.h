@@ -222,8 +222,8 @@ int comic_gemm_f32(comic_handle_t h, const float* A, int lda, const float* Bm, i
 
 
 /* ------------------------------------------------------------------------- *
- * Training: train_mode = decoder | scst (frozen CNN).  cnn_finetune (encoder
- * backward) is not built yet.
+ * Training: train_mode = decoder | scst (frozen CNN) and cnn_finetune (encoder
+ * forward-with-tape + backward, further down).
  * ------------------------------------------------------------------------- */
 
 /* Explicit 0/1 dropout masks (NULL member = that dropout off) + keep probabilities:
@@ -269,6 +269,38 @@ int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const float* im_embed
                         float map_loss_scale, float* loss_out, float* logits_out, float* attn_out,
                         const comic_decoder_grads_t* grads, void* ws, size_t ws_bytes, void* stream);
 
+/* cnn_finetune, decoder side: gradient of the loss with respect to the encoder outputs.  Call right
+ * after comic_train_fwd_bwd with the SAME B, T_run and workspace (it reads the key / value / init-input
+ * gradients that call left there):
+ *   dfm_out [B,M,C]     = dkeys . W_k^T (+ dvalues . W_v^T | + dvalues for cnn_fm_projection none)
+ *   dim_embed_out [B,E] = dx0 . W_I^T   (first_input rnn init, src/model_base.py:675-686)            */
+int comic_train_encoder_grads(comic_handle_t h, int B, int T_run, float* dfm_out, float* dim_embed_out,
+                              void* ws, size_t ws_bytes, void* stream);
+
+/* Gradient buffers of the trainable CNN variables (src/train.py:241-250: cnn_finetune clears
+ * freeze_scopes; BN runs with is_training=False, src/model_base.py:71-77, so only the conv
+ * kernels [HWIO] and the BN betas train).  Order = comic_conv_table(). */
+typedef struct {
+  float* conv_w[COMIC_NUM_CONVS];
+  float* bn_beta[COMIC_NUM_CONVS];
+} comic_cnn_grads_t;
+
+/* Bytes of the activation tape (every conv / pool output of the InceptionV1 forward) and of the
+ * scratch workspace shared by comic_encode_train_fwd and comic_encode_bwd for B images. */
+int comic_encode_train_bytes(comic_handle_t h, int B, size_t* tape_bytes, size_t* ws_bytes);
+
+/* E1+E2 forward that keeps the tape: same outputs as comic_encode_fwd. */
+int comic_encode_train_fwd(comic_handle_t h, const float* images, int B, float* fm_out, float* im_embed_out,
+                           void* tape, size_t tape_bytes, void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of the InceptionV1 graph (TF autodiff of common/nets/inception_v1.py:29-339 under
+ * create_train_op, src/model_base.py:387-401) from dfm [B,196,832] and dim_embed [B,1024]:
+ * overwrites every grads->conv_w[i] / bn_beta[i].  Max-pool gradients go to the first maximum
+ * of each window; all reductions have a fixed order (bit-reproducible). */
+int comic_encode_bwd(comic_handle_t h, const float* images, int B, const float* dfm, const float* dim_embed,
+                     const void* tape, size_t tape_bytes, const comic_cnn_grads_t* grads, void* ws,
+                     size_t ws_bytes, void* stream);
+
 /* ModelBase._loss_regularisation (src/model_base.py:408-417) on a flat parameter buffer:
  * grads += decay * params (grads may be NULL); reg_out[0] = decay/2 * sum params^2.  ws >= 4 KB. */
 int comic_l2_regularise(comic_handle_t h, const float* params, float* grads, size_t n, float decay,
@@ -282,6 +314,8 @@ int comic_adam_step(comic_handle_t h, float* params, const float* grads, float* 
 
 /* After the optimiser changed the variables in place: rebuild the decoder's packed copies. */
 int comic_refresh_packed(comic_handle_t h, void* packed, size_t packed_bytes, void* stream);
+/* Same, decoder AND CNN (folded BN shifts, grouped 1x1 panels, tensor-path panels). */
+int comic_refresh_packed_cnn(comic_handle_t h, void* packed, size_t packed_bytes, void* stream);
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int comic_launch_count(comic_handle_t h, int64_t* count);

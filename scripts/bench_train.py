@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Training throughput (BASELINE.json configs 3 and 5) on N GPUs, one process per GPU.
+"""Training throughput (BASELINE.json configs 3, 4 and 5) on N GPUs, one process per GPU.
 
     python scripts/bench_train.py --mode decoder --batch 32 --steps 20
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
@@ -7,6 +7,7 @@
 
 decoder: frozen-CNN encoder forward + teacher-forced fwd/bwd (T = 41 radix steps, every row
 full length, seeded Philox dropout) + NCCL all-reduce of the flat gradient + Adam.
+cnn_finetune: the same with the InceptionV1 forward-with-tape + backward (conv kernels + BN betas train).
 scst: greedy + beam-7 sampling (40 steps), host CIDEr-D/BLEU reward, weighted-XE step.
 Prints one JSON line on rank 0 (device-timed, max over ranks).
 """
@@ -23,10 +24,11 @@ import numpy as np  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--mode', default='decoder', choices=['decoder', 'scst'])
+    ap.add_argument('--mode', default='decoder', choices=['decoder', 'cnn_finetune', 'scst'])
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--precision', default='split', choices=['f32', 'split', 'fast'])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -43,11 +45,12 @@ def main():
     W = wts.init_weights(c, seed=c.rand_seed, cnn_init='he')
     tr = Trainer(c, W)
     eng = tr.engine
+    eng.set_precision(args.precision)
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
     images = torch.empty((B, 224, 224, 3)).uniform_(-1, 1, generator=g).to(eng.device)
     rng = np.random.default_rng(rank)
-    if args.mode == 'decoder':
+    if args.mode in ('decoder', 'cnn_finetune'):
         caps = np.concatenate([np.full((B, 1), 256), rng.integers(0, 256, size=(B, 40)), np.full((B, 1), 257)],
                               axis=1).astype(np.int32)                     # L = 42 -> T = 41, mask all ones
 

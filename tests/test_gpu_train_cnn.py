@@ -1,0 +1,130 @@
+"""GPU parity of train_mode=cnn_finetune (csrc/encoder_train.cu + comic_train_encoder_grads through
+the C ABI): the InceptionV1 backward against fp64 autograd of the torch restatement
+(tests/torch_ref.py `encoder_forward`, pinned to the NumPy oracle's encoder on CPU in
+tests/test_oracle_known_answers.py).  Tolerance 1e-3 relative to the largest entry of each
+gradient tensor (2e-3 for the bf16x3 tensor path, whose forward differs by ~1e-5)."""
+import numpy as np
+import pytest
+
+from _common import comic_config, make_weights, images, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def torch_mod():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return torch
+
+
+def _grad_names():
+    from comic_b200 import weights as wts
+    out = []
+    for sc, *_ in wts.cnn_conv_list():
+        out += [wts.CNN + sc + '/weights', wts.CNN + sc + '/BatchNorm/beta']
+    return out
+
+
+@pytest.fixture(scope='module')
+def encoder_case(torch_mod):
+    """2 images; loss = <fm, Gf> + <im_embed, Ge> with fixed random cotangents."""
+    import torch_ref as TR
+    torch = torch_mod
+    c = comic_config(train_mode='cnn_finetune')
+    W = make_weights(c, seed=11)
+    img = images(2, seed=5)
+    rng = np.random.default_rng(9)
+    Gf = rng.standard_normal((2, 196, 832)).astype(np.float32)
+    Ge = rng.standard_normal((2, 1024)).astype(np.float32)
+    P = TR.cnn_params(W)
+    emb, fm = TR.encoder_forward(P, img)
+    loss = (fm * torch.as_tensor(Gf, dtype=torch.float64)).sum() + (emb * torch.as_tensor(Ge, dtype=torch.float64)).sum()
+    loss.backward()
+    grads = {k: P[k].grad.numpy() for k in _grad_names()}
+    return dict(c=c, W=W, img=img, Gf=Gf, Ge=Ge, grads=grads, fm=fm.detach().numpy(), emb=emb.detach().numpy())
+
+
+@pytest.mark.parametrize('precision,tol', [('f32', 1e-3), ('split', 2e-3)])
+def test_encoder_backward_matches_autograd(torch_mod, encoder_case, precision, tol):
+    from comic_b200.train import Trainer
+    k = encoder_case
+    tr = Trainer(k['c'], k['W'])
+    eng = tr.engine
+    eng.set_precision(precision)
+    img = eng.to_dev(k['img'])
+    emb, fm = eng.encode_train(img)
+    assert rel_err(fm.cpu().numpy(), k['fm']) < 2e-4
+    assert rel_err(emb.cpu().numpy(), k['emb']) < 2e-4
+    # the tape forward is the inference forward
+    emb2, fm2 = eng.encode(img)
+    assert rel_err(fm.cpu().numpy(), fm2.cpu().numpy()) < 1e-6
+    tr.grads.zero_()
+    eng.encode_bwd(img, eng.to_dev(k['Gf']), eng.to_dev(k['Ge']), tr.cnn_grad_w, tr.cnn_grad_b)
+    worst = {}
+    for name in _grad_names():
+        g = tr.gradient(name).cpu().numpy()
+        worst[name] = rel_err(g, k['grads'][name])
+    bad = {n: v for n, v in worst.items() if not v < tol}
+    assert not bad, (bad, max(worst.values()))
+    # bit-reproducible: fixed-order reductions, no atomics
+    g1 = tr.grads.clone()
+    tr.grads.zero_()
+    eng.encode_bwd(img, eng.to_dev(k['Gf']), eng.to_dev(k['Ge']), tr.cnn_grad_w, tr.cnn_grad_b)
+    assert torch_mod.equal(g1, tr.grads)
+
+
+def test_cnn_finetune_end_to_end_gradients(torch_mod):
+    """images -> encoder -> teacher-forced decoder -> loss: every decoder AND CNN gradient vs autograd."""
+    import torch_ref as TR
+    from comic_b200.train import Trainer
+    from comic_b200 import weights as wts
+    torch = torch_mod
+    c = comic_config(train_mode='cnn_finetune')
+    W = make_weights(c, seed=21)
+    img = images(2, seed=8)
+    rng = np.random.default_rng(4)
+    caps = np.full((2, 7), -1, np.int32)
+    caps[:, 0] = 256
+    caps[0, 1:6] = rng.integers(0, 256, 5); caps[0, 6] = 257
+    caps[1, 1:4] = rng.integers(0, 256, 3); caps[1, 4] = 257
+    # reference: one autograd graph over CNN + decoder leaves
+    P = TR.to_params(W)
+    PC = TR.cnn_params(W)
+    emb, fm = TR.encoder_forward(PC, img)
+    tot, xe, mp, reg, _ = TR.training_loss(P, c, emb, fm, caps)
+    for v in PC.values():
+        if v.requires_grad:
+            reg = reg + (v ** 2).sum() / 2 * c.l2_decay
+            tot = tot + (v ** 2).sum() / 2 * c.l2_decay
+    tot.backward()
+    tr = Trainer(c, W)
+    eng = tr.engine
+    eng.set_precision('f32')
+    d_img = eng.to_dev(img)
+    emb_d, fm_d = eng.encode_train(d_img)
+    out = tr.forward_backward(fm_d, emb_d, caps, images=d_img)
+    loss = out['loss'].cpu().numpy()
+    assert abs(loss[1] - float(xe)) < 1e-4 * max(1.0, abs(float(xe)))
+    assert abs(loss[3] - float(reg)) < 1e-4 * max(1e-3, abs(float(reg)))
+    assert abs(loss[0] - float(tot)) < 1e-4 * max(1.0, abs(float(tot)))
+    worst = {}
+    for name in wts.decoder_shapes(c):
+        worst[name] = rel_err(tr.gradient(name).cpu().numpy().reshape(P[name].shape), P[name].grad.numpy())
+    for name in _grad_names():
+        worst[name] = rel_err(tr.gradient(name).cpu().numpy(), PC[name].grad.numpy())
+    bad = {n: v for n, v in worst.items() if not v < 1e-3}
+    assert not bad, (bad, max(worst.values()))
+    # one optimiser step moves the CNN and the refreshed packs reproduce a fresh bind
+    before = tr.variable(wts.CNN + 'Conv2d_2c_3x3/weights').clone()
+    tr.apply_gradients(lr=1e-3)
+    after = tr.variable(wts.CNN + 'Conv2d_2c_3x3/weights')
+    assert float((after - before).abs().max()) > 0
+    emb1, fm1 = eng.encode(d_img)
+    W2 = {n: tr.variable(n).cpu().numpy().reshape(np.asarray(W[n]).shape) for n in tr.offsets}
+    W3 = dict(W); W3.update(W2)
+    tr2 = Trainer(c, W3)
+    tr2.engine.set_precision('f32')
+    emb2, fm2 = tr2.engine.encode(tr2.engine.to_dev(img))
+    assert torch.equal(fm1.cpu(), fm2.cpu()) and torch.equal(emb1.cpu(), emb2.cpu())

@@ -47,7 +47,8 @@ def training_loss(P, c, im_embed, fm, captions, masks=None, keeps=(1.0, 1.0, 1.0
     """Returns (total, xe, map, reg, aux) as fp64 torch scalars; `aux` holds logits [T,B,V]
     (imputed) and attention maps [B,H,T_run,M].  captions [B,L] int (PAD = -1)."""
     dt = torch.float64
-    t = lambda a: torch.as_tensor(np.asarray(a), dtype=dt)
+    # fm / im_embed may be torch tensors still attached to the CNN graph (cnn_finetune)
+    t = lambda a: a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a), dtype=dt)
     H, R = c.attn_num_heads, c.rnn_size
     in_keep, out_keep, att_keep = keeps
     m = masks or {}
@@ -139,3 +140,75 @@ def training_loss(P, c, im_embed, fm, captions, masks=None, keeps=(1.0, 1.0, 1.0
             reg = reg + (v ** 2).sum() / 2 * c.l2_decay
     total = xe + map_loss + reg
     return total, xe, map_loss, reg, dict(logits=logits, attn=am, fm=fm_t, im=im_t)
+
+
+# ---------------------------------------------------------------------------
+# Encoder (cnn_finetune): differentiable InceptionV1 restatement.
+# Follows common/nets/inception_v1.py:29-339 under inception_arg_scope
+# (common/nets/inception_utils.py:32-82) with is_training=False
+# (src/model_base.py:71-77): conv (no bias, TF SAME) -> BN with MOVING statistics,
+# no gamma, eps 1e-3 -> ReLU.  Trainable: conv kernels and BN betas.
+# ---------------------------------------------------------------------------
+CNN = 'Model/encoder/cnn/InceptionV1/'
+
+
+def _same_pad(n, k, s):
+    out = -(-n // s)
+    pad = max((out - 1) * s + k - n, 0)
+    return pad // 2, pad - pad // 2
+
+
+def cnn_params(W, dtype=torch.float64):
+    """Trainable CNN leaves (weights, betas) + constant moving statistics."""
+    P = {}
+    for k, v in W.items():
+        if not k.startswith(CNN):
+            continue
+        tr = k.endswith('/weights') or k.endswith('/beta')
+        P[k] = torch.tensor(np.asarray(v), dtype=dtype, requires_grad=tr)
+    return P
+
+
+def _cbr(P, x, scope, stride=1):
+    import torch.nn.functional as F
+    w = P[CNN + scope + '/weights']                                            # HWIO
+    k = w.shape[0]
+    pt, pb = _same_pad(x.shape[2], k, stride)
+    pl, pr = _same_pad(x.shape[3], k, stride)
+    y = F.conv2d(F.pad(x, (pl, pr, pt, pb)), w.permute(3, 2, 0, 1), stride=stride)
+    s = torch.rsqrt(P[CNN + scope + '/BatchNorm/moving_variance'] + 1e-3)
+    sh = P[CNN + scope + '/BatchNorm/beta'] - P[CNN + scope + '/BatchNorm/moving_mean'] * s
+    return torch.relu(y * s[None, :, None, None] + sh[None, :, None, None])
+
+
+def _maxpool(x, k, s):
+    import torch.nn.functional as F
+    pt, pb = _same_pad(x.shape[2], k, s)
+    pl, pr = _same_pad(x.shape[3], k, s)
+    return F.max_pool2d(F.pad(x, (pl, pr, pt, pb), value=float('-inf')), k, s)
+
+
+def encoder_forward(P, images):
+    """images [B,224,224,3] NHWC -> (im_embed [B,1024], fm [B,196,832]) differentiable in P."""
+    from comic_b200 import weights as wts
+    x = torch.as_tensor(np.asarray(images), dtype=next(iter(P.values())).dtype).permute(0, 3, 1, 2)
+    x = _cbr(P, x, 'Conv2d_1a_7x7', 2)
+    x = _maxpool(x, 3, 2)
+    x = _cbr(P, x, 'Conv2d_2b_1x1')
+    x = _cbr(P, x, 'Conv2d_2c_3x3')
+    x = _maxpool(x, 3, 2)
+    fm = None
+    for b in wts.BLOCKS:
+        if len(b) == 3:
+            x = _maxpool(x, b[1], b[2])
+            continue
+        sc = wts.block_conv_scopes(b[0])
+        b0 = _cbr(P, x, sc[0])
+        b1 = _cbr(P, _cbr(P, x, sc[1]), sc[2])
+        b2 = _cbr(P, _cbr(P, x, sc[3]), sc[4])
+        b3 = _cbr(P, _maxpool(x, 3, 1), sc[5])
+        x = torch.cat([b0, b1, b2, b3], 1)
+        if b[0] == 'Mixed_4f':
+            fm = x.permute(0, 2, 3, 1).reshape(x.shape[0], 196, 832)
+    im_embed = x.mean(dim=(2, 3))
+    return im_embed, fm
