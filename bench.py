@@ -10,7 +10,8 @@ rank: InceptionV1 encode -> key projection -> rnn init -> 60-step beam-3 decode
 + top-beam attention maps.  Images are sharded across ranks with no collective
 (weak scaling: --batch images per GPU).  `value` times the K steps with inputs
 resident in HBM; `e2e` times the same K steps through the public API
-(`CaptionModel.run`) from pinned HOST images, host<->device copies included.
+(`CaptionModel.run_stream`, the pipelined inference loop) from pinned HOST images,
+host<->device copies of every batch included.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -290,8 +291,17 @@ def run_ours(args):
         c0, h0 = eng.rnn_init(emb)
         return eng.decode_beam(keys, values, c0, h0, beam, c.infer_length_penalty_weight, T)
 
-    def step_e2e():
-        return model.run(host_images)
+    host_images2 = torch.empty((B, 224, 224, 3), dtype=torch.float32).pin_memory()
+    host_images2.copy_(host_images.flip(0))
+
+    def e2e_loop(n):
+        """n batches through the public pipelined inference loop (CaptionModel.run_stream): every batch is
+        copied from pinned host memory and its captions + attention maps are read back to the host."""
+        got, out = 0, None
+        for out in model.run_stream((host_images if j % 2 == 0 else host_images2) for j in range(n)):
+            got += int(out[0].shape[0])
+        assert got == n * B
+        return out
 
     # ---- kernel-class breakdown (outside the timed region) -> dominant kernel
     for _ in range(max(args.warmup, 3)):
@@ -330,14 +340,19 @@ def run_ours(args):
     T_exec = executed_steps(r['T'])
 
     # ---- timed region 2: end to end through CaptionModel.run from pinned host memory
-    for _ in range(2):
-        out = step_e2e()
+    out = e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = step_e2e()
+    out = e2e_loop(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    barrier()
+    # the same K batches one blocking CaptionModel.run call at a time (no copy/compute overlap)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.run(host_images)
+    torch.cuda.synchronize()
+    e2e_serial_s = time.perf_counter() - t0
     barrier()
     h2d = host_images.numel() * 4
     d2h = int(out[0].nbytes + out[1].nbytes)
@@ -378,7 +393,9 @@ def run_ours(args):
             'decoder_step_us': None,
             'roofline': roof,
             'e2e': {'value': caps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps},
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps,
+                    'api': 'CaptionModel.run_stream (H2D / compute / D2H pipelined over 3 streams)',
+                    'serial_run_ms_per_step': e2e_serial_s * 1e3 / args.steps},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
             'kernel_ms_per_step': {t: round(table[t][0], 3) for t in KERNEL_TAGS if table[t][1]},

@@ -214,6 +214,95 @@ class CaptionModel(ModelBase):
         torch.cuda.current_stream(eng.device).synchronize()
         return [preds.numpy(), attn.numpy()]
 
+    def run_stream(self, batches, depth=2):
+        """The inference loop of src/infer_fn.py:166-184 (`for each batch: sess.run(infer_output)`) as a
+        software pipeline: yields [dec_preds, attn_maps] per batch, in order, like `run`.
+
+        Three CUDA streams: the host->device copy of batch i+1 (pinned host memory copies at PCIe
+        speed) and the device->host copy of batch i-1's results run while batch i computes, so in
+        steady state a batch costs max(compute, H2D, D2H) instead of their sum.  `depth` device
+        input buffers / pinned result buffers rotate: a yielded result stays valid until the
+        following `next()`.  Device-resident batches skip the input copy."""
+        eng = self.engine
+        torch = eng.torch
+        dev = eng.device
+        comp = torch.cuda.current_stream(dev)
+        if not hasattr(self, '_pipe_streams'):
+            self._pipe_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            self._pipe_slots = {}
+        s_in, s_out = self._pipe_streams
+        slots = self._pipe_slots.setdefault(depth, [dict() for _ in range(depth)])
+
+        def stage_in(i, images):
+            sl = slots[i % depth]
+            images = torch.as_tensor(images)
+            if images.dtype != torch.float32:
+                images = images.float()
+            if images.is_cuda:
+                sl['dev'], sl['ev_in'] = images.contiguous(), None
+                return
+            buf = sl.get('dev_in')
+            if buf is None or buf.shape != images.shape:
+                buf = sl['dev_in'] = torch.empty(images.shape, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(s_in):
+                if sl.get('ev_comp') is not None:
+                    s_in.wait_event(sl['ev_comp'])          # the slot's previous batch has been consumed
+                buf.copy_(images, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            sl['dev'], sl['ev_in'] = buf, ev
+
+        def pinned(sl, key, t):
+            b = sl.get(key)
+            if b is None or b.shape != t.shape or b.dtype != t.dtype:
+                b = sl[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            return b
+
+        def compute(i):
+            sl = slots[i % depth]
+            if sl['ev_in'] is not None:
+                comp.wait_event(sl['ev_in'])
+            self._encoder(sl['dev'])
+            self._decoder_rnn()
+            preds, attn = self.dec_preds.contiguous(), self.dec_attn_maps.contiguous()
+            ev = torch.cuda.Event()
+            ev.record(comp)
+            sl['ev_comp'] = ev
+            hp, ha = pinned(sl, 'h_preds', preds), pinned(sl, 'h_attn', attn)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev)
+                hp.copy_(preds, non_blocking=True)
+                ha.copy_(attn, non_blocking=True)
+                preds.record_stream(s_out)
+                attn.record_stream(s_out)
+                evo = torch.cuda.Event()
+                evo.record(s_out)
+            sl['ev_out'], sl['out'] = evo, (hp, ha)
+
+        def finish(i):
+            sl = slots[i % depth]
+            sl['ev_out'].synchronize()
+            return [sl['out'][0].numpy(), sl['out'][1].numpy()]
+
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        i, pending = 0, None
+        stage_in(0, cur)
+        while True:
+            nxt = next(it, None)
+            if nxt is not None:
+                stage_in(i + 1, nxt)
+            compute(i)
+            if pending is not None:
+                yield finish(pending)
+            pending = i
+            if nxt is None:
+                break
+            i += 1
+        yield finish(pending)
+
     @property
     def infer_output(self):
         return self.run()
