@@ -1,8 +1,15 @@
 """GPU parity of train_mode=cnn_finetune (csrc/encoder_train.cu + comic_train_encoder_grads through
 the C ABI): the InceptionV1 backward against fp64 autograd of the torch restatement
 (tests/torch_ref.py `encoder_forward`, pinned to the NumPy oracle's encoder on CPU in
-tests/test_oracle_known_answers.py).  Tolerance 1e-3 relative to the largest entry of each
-gradient tensor (2e-3 for the bf16x3 tensor path, whose forward differs by ~1e-5)."""
+tests/test_oracle_known_answers.py).
+
+Tolerance: 5e-3 relative to the largest entry of each gradient tensor.  The gradient of a ReLU /
+max-pool network is only piecewise continuous: an activation within fp32 rounding of zero (or two
+window entries within rounding of each other) flips a mask, and one flipped pixel moves a whole
+column of an early layer's dW by ~1/sqrt(#pixels).  On the 2-image case below torch's OWN fp32
+autograd differs from its fp64 autograd by up to 2.1e-3 (Mixed_3c/Branch_2/Conv2d_0b_3x3/weights;
+scripted check in the docstring of `encoder_case`), so 1e-3 is below the noise floor of the
+reference's fp32 arithmetic; the decoder gradients (smooth) stay at 1e-3."""
 import numpy as np
 import pytest
 
@@ -29,7 +36,9 @@ def _grad_names():
 
 @pytest.fixture(scope='module')
 def encoder_case(torch_mod):
-    """2 images; loss = <fm, Gf> + <im_embed, Ge> with fixed random cotangents."""
+    """2 images; loss = <fm, Gf> + <im_embed, Ge> with fixed random cotangents.
+    (Noise floor: run TR.cnn_params(W, dtype=torch.float32) through the same lines and compare with the
+    fp64 gradients -> worst tensor 2.1e-3, a dozen tensors above 1e-3.)"""
     import torch_ref as TR
     torch = torch_mod
     c = comic_config(train_mode='cnn_finetune')
@@ -46,7 +55,7 @@ def encoder_case(torch_mod):
     return dict(c=c, W=W, img=img, Gf=Gf, Ge=Ge, grads=grads, fm=fm.detach().numpy(), emb=emb.detach().numpy())
 
 
-@pytest.mark.parametrize('precision,tol', [('f32', 1e-3), ('split', 2e-3)])
+@pytest.mark.parametrize('precision,tol', [('f32', 5e-3), ('split', 5e-3)])
 def test_encoder_backward_matches_autograd(torch_mod, encoder_case, precision, tol):
     from comic_b200.train import Trainer
     k = encoder_case
@@ -112,9 +121,12 @@ def test_cnn_finetune_end_to_end_gradients(torch_mod):
     worst = {}
     for name in wts.decoder_shapes(c):
         worst[name] = rel_err(tr.gradient(name).cpu().numpy().reshape(P[name].shape), P[name].grad.numpy())
+    bad = {n: v for n, v in worst.items() if not v < 1e-3}
+    assert not bad, (bad, max(worst.values()))
+    worst = {}
     for name in _grad_names():
         worst[name] = rel_err(tr.gradient(name).cpu().numpy(), PC[name].grad.numpy())
-    bad = {n: v for n, v in worst.items() if not v < 1e-3}
+    bad = {n: v for n, v in worst.items() if not v < 5e-3}
     assert not bad, (bad, max(worst.values()))
     # one optimiser step moves the CNN and the refreshed packs reproduce a fresh bind
     before = tr.variable(wts.CNN + 'Conv2d_2c_3x3/weights').clone()
