@@ -74,6 +74,7 @@ struct comic_handle_s {
   long long* last_trace = nullptr;
   int last_trace_steps = 0;
   int persist_max_rows = 32;   // whole decode loop as one cooperative kernel up to this many rows (0 = off)
+  int enc_planes = 0;          // 1: encoder activations as pre-split bf16 planes on the tensor path (0 = fp32 NHWC)
   int enc_chunk[3] = {64, 256, 512};   // images per encoder chunk: stem / 28x28 blocks / 14x14 + 7x7 blocks
   comic::Packed pk;
   int64_t launches = 0;

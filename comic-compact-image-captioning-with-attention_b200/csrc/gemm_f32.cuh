@@ -43,9 +43,14 @@ struct AConv {
 
 struct Route {
   int n0, n1;   // column range [n0, n1)
-  float* dst;
+  float* dst;   // fp32 destination (nullable on the tensor path when only the bf16 planes are wanted)
   int ld;
   int coff;
+  // tensor path only: the same element also as an error-compensated bf16 pair (hi = bf16(v),
+  // lo = bf16(v - hi)) in two planes with the row stride / channel offset above; the next conv's
+  // loader copies these straight into its shared-memory operand tiles (gemm_tc.cuh AConvP)
+  uint16_t* hi;
+  uint16_t* lo;
 };
 
 struct Epi {
@@ -59,9 +64,18 @@ struct Epi {
   int stop_n;              // (decode loops: every beam finished in the previous step)
 };
 
+// NHWC activations stored pre-split as two bf16 planes (tensor path, gemm_tc.cuh).
+struct AConvP {
+  const uint16_t* hi;
+  const uint16_t* lo;   // [B, H, W, ldx] each, channels [0, Cin), Cin % 8 == 0
+  int H, W, Cin, ldx;
+  int KH, KW, stride, pad_t, pad_l, Ho, Wo;
+};
+
 template <int AMODE> struct AParam;
 template <> struct AParam<0> { typedef APlain type; };
 template <> struct AParam<1> { typedef AConv type; };
+template <> struct AParam<2> { typedef AConvP type; };
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

@@ -246,8 +246,14 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
 #pragma unroll
             for (int rr = 0; rr < 3; ++rr) {
               if (rr < epi.nroute && n >= epi.r[rr].n0 && n < epi.r[rr].n1) {
-                float* dst = epi.r[rr].dst + (size_t)m * epi.r[rr].ld + epi.r[rr].coff + (n - epi.r[rr].n0);
-                *reinterpret_cast<float4*>(dst) = v;
+                const size_t o = (size_t)m * epi.r[rr].ld + epi.r[rr].coff + (n - epi.r[rr].n0);
+                if (epi.r[rr].dst) *reinterpret_cast<float4*>(epi.r[rr].dst + o) = v;
+                if (epi.r[rr].hi) {
+                  uint2 ph, pl;
+                  split4(v, ph, pl);
+                  *reinterpret_cast<uint2*>(epi.r[rr].hi + o) = ph;
+                  *reinterpret_cast<uint2*>(epi.r[rr].lo + o) = pl;
+                }
               }
             }
           }
@@ -342,7 +348,7 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
             }
             rp[s * BM + tg] = p;
           }
-        } else {
+        } else {   // AMODE 1 (fp32 NHWC) and 2 (bf16 planes): im2col row table
           RowEntry* re = reinterpret_cast<RowEntry*>(rowtab);
           RowEntry e;
           e.off = -1; e.hi0 = 0; e.wi0 = 0;
@@ -362,6 +368,42 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
         if ((int)(it % kLoaderGroups) != grp) continue;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
+        if constexpr (AMODE == 2) {
+          // pre-split bf16 planes: no conversion, no register staging -- each thread copies 8 x 16 bytes
+          // (8 channels of one im2col row) per plane with cp.async straight into the swizzled tiles
+          const int c8 = lane & 7, r4 = lane >> 3;
+          const RowEntry* re = reinterpret_cast<const RowEntry*>(rowtab);
+          const int kk8 = kt * BK + c8 * 8;
+          int kh = 0, kw = 0, ci = 0;
+          const bool kvalid = kk8 < K;
+          if (kvalid) {
+            int tap = kk8 / a.Cin;
+            ci = kk8 - tap * a.Cin;
+            kh = tap / a.KW;
+            kw = tap - kh * a.KW;
+          }
+          mbar_wait(&empty[s], ph ^ 1);
+          const uint32_t a_hi = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = wg * 32 + i * 4 + r4;
+            const RowEntry e = re[row];
+            const int hi = e.hi0 + kh, wi = e.wi0 + kw;
+            const bool ok = kvalid && e.off >= 0 && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+            const long long go = ok ? e.off + ((long long)hi * a.W + wi) * a.ldx + ci : 0;
+            const uint32_t so = (uint32_t)row * 128u + ((uint32_t)(c8 ^ (row & 7)) << 4);
+            const uint32_t nbytes = ok ? 16u : 0u;      // src-size 0 -> 16 zero bytes (SAME padding, K tail)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_hi + so), "l"(a.hi + go), "r"(nbytes)
+                         : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_lo + so), "l"(a.lo + go), "r"(nbytes)
+                         : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          fence_proxy_async();
+          mbar_arrive(&full_a[s]);
+        } else {
         float4 v[16];
         const int kk = kt * BK + chunk * 4;
         if constexpr (AMODE == 0) {
@@ -382,7 +424,7 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
             const float* p = (seg >= 0) ? rp[seg * BM + row] : nullptr;
             v[i] = p ? ldg4(p + col) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        } else {
+        } else if constexpr (AMODE == 1) {
           const RowEntry* re = reinterpret_cast<const RowEntry*>(rowtab);
           int kh = 0, kw = 0, ci = 0;
           const bool kvalid = kk < K;
@@ -416,6 +458,7 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
         }
         fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive(&full_a[s]);
+        }   // AMODE != 2
       }
     }
   }

@@ -127,6 +127,11 @@ int comic_set_precision(comic_handle_t h, int mode);
 #define COMIC_OPT_PERSISTENT_MAX_ROWS 4      /* decode loops with batch*beam <= this run as ONE cooperative kernel
                                              * (default 32, the kernel's limit; 0 = always one launch per step op) */
 #define COMIC_OPT_PERSISTENT_TRACE 5         /* 1: the persistent loop records per-phase clock stamps (diagnostics) */
+#define COMIC_OPT_ENC_PLANES 6               /* 1: on the tensor path the encoder keeps its activations as
+                                             * error-compensated bf16 (hi, lo) planes written by each conv's epilogue
+                                             * (cp.async operand loader, no conversion in the consumer);
+                                             * 0 (default): fp32 NHWC activations, split by every consumer.  Measured
+                                             * r01f: the GEMM is L2->SM-bandwidth bound either way, planes 12% slower */
 int comic_set_option(comic_handle_t h, int option, int value);
 
 /* Diagnostics: clock64 stamps of the last persistent decode call, [steps][2][16] int64 (CTA 0 and the first

@@ -93,6 +93,18 @@ def test_encoder_chunking_batch_independent(torch_mod):
     emb2, fm2 = eng.encode(eng.to_dev(img))
     assert rel_err(fm2.cpu().numpy(), fm.cpu().numpy()) < 1e-4
     assert rel_err(emb2.cpu().numpy(), emb.cpu().numpy()) < 1e-4
+    # tensor path, activation storage: fp32 NHWC split by every consumer (default) vs pre-split bf16
+    # (hi, lo) planes written by the producing conv's epilogue (option enc_planes): both feed the MMAs
+    # 16-bit operand pairs and sit inside the tensor path's own error band against FFMA
+    eng.set_option('enc_planes', 1)
+    emb3, fm3 = eng.encode(eng.to_dev(img))
+    assert rel_err(fm3.cpu().numpy(), fm2.cpu().numpy()) < 5e-5
+    assert rel_err(emb3.cpu().numpy(), emb2.cpu().numpy()) < 5e-5
+    assert rel_err(fm3.cpu().numpy(), fm.cpu().numpy()) < 1e-4
+    # odd batch: a 3-image call (one chunk) on planes vs the same images inside the 70-batch
+    emb4, fm4 = eng.encode(eng.to_dev(img[10:13]))
+    assert rel_err(fm4.cpu().numpy(), fm3[10:13].cpu().numpy()) < 5e-5
+    eng.set_option('enc_planes', 0)
 
 
 CONFIGS = {
