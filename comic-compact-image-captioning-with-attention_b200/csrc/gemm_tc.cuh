@@ -140,14 +140,82 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct RowEntry {   // 16 bytes, one per tile row (AConv)
-  long long off;    // element offset of the image base, -1 = row beyond M
-  int hi0, wi0;     // top-left input coordinate of the receptive field
+// ---- CTA-pair helpers (tcgen05 cta_group::2) ---------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA load whose completion bytes are counted on the LEADER CTA's barrier (peer bit of the
+// shared::cluster address cleared), destination in the executing CTA's shared memory.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                                 int c1) {
+  const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+// One im2col row of the tile (AMODE 1 / 2): pointer to channel 0 of the receptive field's top-left
+// pixel (it may lie outside the image: only dereferenced for taps whose mask bit is set) and the
+// validity of each of the KH*KW taps (TF SAME padding; rows beyond M have mask 0).
+struct RowEntry {
+  const void* ptr;
+  unsigned long long mask;
 };
 
-template <int BN, int STAGES>
+// PAIR = false: one CTA per 128 x BN tile.  PAIR = true: the two CTAs of a cluster compute a
+// 256 x BN tile with M = 256 UMMAs issued by the leader (rank 0); each CTA loads its own 128 rows
+// of A and HALF of the weight tile, so a CTA pulls half the weight bytes per output and its stage
+// shrinks (BN = 256: 96 -> 64 KB, 3 stages instead of 2).  full_a / full_b / tmem_empty then live in
+// the leader and collect (remote) arrivals of both CTAs; empty / tmem_full exist in both CTAs and
+// are signalled by the leader's multicast tcgen05.commit.  Operand layouts, epilogue and the UMMA
+// order per accumulator element are the same in both modes: results are bit-identical.
+template <int BN, int STAGES, bool PAIR>
 struct SmemLayout {
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // this CTA's part of one weight tile (hi or lo)
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
   static constexpr int ROWTAB_BYTES = BM * 3 * 8;                 // 3 segment row pointers or RowEntry
@@ -156,15 +224,17 @@ struct SmemLayout {
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
 };
 
-template <int BN, int STAGES, int AMODE>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
-                   const __grid_constant__ CUtensorMap tm_lo, int M, int N, int K, Epi epi) {
-  using L = SmemLayout<BN, STAGES>;
+template <int BN, int STAGES, int AMODE, bool PAIR>
+__device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::type& a, const CUtensorMap* tm_hi,
+                                                 const CUtensorMap* tm_lo, int M, int N, int K, const Epi& epi) {
+  static_assert(!(PAIR && AMODE == 2), "pair kernel: fp32 operand loaders only");
+  using L = SmemLayout<BN, STAGES, PAIR>;
+  constexpr int TM = PAIR ? 2 * BM : BM;        // rows per (pair) tile
   extern __shared__ uint8_t smem_raw[];
-  if (epi.stop != nullptr && *epi.stop >= epi.stop_n) return;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* rowtab0 = smem + L::TILES_BYTES;
+  if (epi.stop != nullptr && *epi.stop >= epi.stop_n) return;      // uniform over the grid
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-window address of the tiles
+  uint8_t* smem_g = smem_raw + (smem - smem_u32(smem_raw));
+  uint8_t* rowtab0 = smem_g + L::TILES_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(rowtab0 + kLoaderGroups * L::ROWTAB_BYTES);
   uint64_t* full_a = bars;
   uint64_t* full_b = bars + STAGES;
@@ -174,46 +244,61 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   const int nk = (K + BK - 1) / BK;
   const int n_tiles = (N + BN - 1) / BN;
-  const int m_tiles = (M + BM - 1) / BM;
+  const int m_tiles = (M + TM - 1) / TM;
   const int total_tiles = m_tiles * n_tiles;
+  const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   // ---- one-time setup ----
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_a[s], 128);
+      mbar_init(&full_a[s], PAIR ? 256 : 128);
       mbar_init(&full_b[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], kEpiWarps);
+      mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_barrier_init();
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)L::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)L::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)L::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kEpiWarps) {
-    // =====================  epilogue  =====================
+    // =====================  epilogue (this CTA's 128 rows)  =====================
+    // one plain fp32 destination: the row pointer is formed once per tile
+    const bool simple = epi.nroute == 1 && epi.r[0].hi == nullptr && epi.r[0].n0 == 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      const int m0 = (tile / n_tiles) * BM;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
+      const int m0 = (tile / n_tiles) * TM + (int)rank * BM;
       const int n0 = (tile % n_tiles) * BN;
       const int acc = iter & 1;
       const int n_umma = min(BN, ((N - n0) + 15) & ~15);
       mbar_wait(&tmem_full[acc], (uint32_t)((iter >> 1) & 1));
       tc_fence_after();
       const int m = m0 + warp * 32 + lane;
+      float* rowp = simple ? epi.r[0].dst + (size_t)m * epi.r[0].ld + epi.r[0].coff : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < n_umma; c0 += 16) {
         uint32_t r[16];
@@ -243,16 +328,20 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
             if (epi.relu) {
               v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
             }
+            if (simple) {
+              *reinterpret_cast<float4*>(rowp + n) = v;
+            } else {
 #pragma unroll
-            for (int rr = 0; rr < 3; ++rr) {
-              if (rr < epi.nroute && n >= epi.r[rr].n0 && n < epi.r[rr].n1) {
-                const size_t o = (size_t)m * epi.r[rr].ld + epi.r[rr].coff + (n - epi.r[rr].n0);
-                if (epi.r[rr].dst) *reinterpret_cast<float4*>(epi.r[rr].dst + o) = v;
-                if (epi.r[rr].hi) {
-                  uint2 ph, pl;
-                  split4(v, ph, pl);
-                  *reinterpret_cast<uint2*>(epi.r[rr].hi + o) = ph;
-                  *reinterpret_cast<uint2*>(epi.r[rr].lo + o) = pl;
+              for (int rr = 0; rr < 3; ++rr) {
+                if (rr < epi.nroute && n >= epi.r[rr].n0 && n < epi.r[rr].n1) {
+                  const size_t o = (size_t)m * epi.r[rr].ld + epi.r[rr].coff + (n - epi.r[rr].n0);
+                  if (epi.r[rr].dst) *reinterpret_cast<float4*>(epi.r[rr].dst + o) = v;
+                  if (epi.r[rr].hi) {
+                    uint2 ph, pl;
+                    split4(v, ph, pl);
+                    *reinterpret_cast<uint2*>(epi.r[rr].hi + o) = ph;
+                    *reinterpret_cast<uint2*>(epi.r[rr].lo + o) = pl;
+                  }
                 }
               }
             }
@@ -262,28 +351,37 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
       // accumulator buffer drained -> the MMA warp may overwrite it
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(&tmem_empty[acc], 0);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
     }
   } else if (warp == 4) {
-    // =====================  MMA issuer  =====================
-    if (lane == 0) {
+    // =====================  MMA issuer (PAIR: leader CTA only)  =====================
+    if (leader && lane == 0) {
       int iter = 0;
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
         const int n0 = (tile % n_tiles) * BN;
         const int acc = iter & 1;
         const int n_umma = min(BN, ((N - n0) + 15) & ~15);
-        const uint32_t idesc = make_idesc_bf16(BM, n_umma);
+        const uint32_t idesc = make_idesc_bf16(TM, n_umma);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        mbar_wait(&tmem_empty[acc], (uint32_t)(((iter >> 1) & 1) ^ 1));
+        if constexpr (PAIR) mbar_wait_cluster(&tmem_empty[acc], (uint32_t)(((iter >> 1) & 1) ^ 1));
+        else mbar_wait(&tmem_empty[acc], (uint32_t)(((iter >> 1) & 1) ^ 1));
         tc_fence_after();
         for (int kt = 0; kt < nk; ++kt, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_a[s], ph);
-          mbar_wait(&full_b[s], ph);
+          if constexpr (PAIR) {
+            mbar_wait_cluster(&full_a[s], ph);
+            mbar_wait_cluster(&full_b[s], ph);
+          } else {
+            mbar_wait(&full_a[s], ph);
+            mbar_wait(&full_b[s], ph);
+          }
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t a_hi = smem + s * L::STAGE_BYTES;
           const uint32_t a_lo = a_hi + A_TILE_BYTES;
           const uint32_t b_hi = a_lo + A_TILE_BYTES;
           const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
@@ -292,46 +390,63 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
 #pragma unroll
           for (int k16 = 0; k16 < BK / 16; ++k16) {
             const uint64_t adv = (uint64_t)((k16 * 16 * 2) >> 4);    // 32 bytes per K=16 step inside the swizzle row
-            umma_bf16(d_tmem, dah + adv, dbh + adv, idesc, (kt > 0 || k16 > 0) ? 1u : 0u);
-            umma_bf16(d_tmem, dal + adv, dbh + adv, idesc, 1u);
-            umma_bf16(d_tmem, dah + adv, dbl + adv, idesc, 1u);
+            const uint32_t first = (kt > 0 || k16 > 0) ? 1u : 0u;
+            if constexpr (PAIR) {
+              umma_bf16_pair(d_tmem, dah + adv, dbh + adv, idesc, first);
+              umma_bf16_pair(d_tmem, dal + adv, dbh + adv, idesc, 1u);
+              umma_bf16_pair(d_tmem, dah + adv, dbl + adv, idesc, 1u);
+            } else {
+              umma_bf16(d_tmem, dah + adv, dbh + adv, idesc, first);
+              umma_bf16(d_tmem, dal + adv, dbh + adv, idesc, 1u);
+              umma_bf16(d_tmem, dah + adv, dbl + adv, idesc, 1u);
+            }
           }
-          umma_commit(&empty[s]);            // frees the stage when the MMAs above retire
+          // frees the stage (PAIR: in both CTAs) when the MMAs above retire
+          if constexpr (PAIR) umma_commit_pair(&empty[s]);
+          else umma_commit(&empty[s]);
         }
-        umma_commit(&tmem_full[acc]);        // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (PAIR: of both CTAs)
+        if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);
       }
     }
     __syncwarp();
   } else if (warp == 5) {
-    // =====================  TMA producer (weights)  =====================
+    // =====================  TMA producer (this CTA's part of the weight tile)  =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int n0 = (tile % n_tiles) * BN;
+        const int n_umma = min(BN, ((N - n0) + 15) & ~15);
+        const int nrow = PAIR ? n0 + (int)rank * (n_umma >> 1) : n0;      // first row of B^T this CTA loads
         for (int kt = 0; kt < nk; ++kt, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          const uint32_t b_hi = smem_u32(smem + s * L::STAGE_BYTES + 2 * A_TILE_BYTES);
+          const uint32_t b_hi = smem + s * L::STAGE_BYTES + 2 * A_TILE_BYTES;
           const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
-          mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES);
-          tma_load_2d(b_hi, &tm_hi, &full_b[s], kt * BK, n0);
-          tma_load_2d(b_lo, &tm_lo, &full_b[s], kt * BK, n0);
+          if constexpr (PAIR) {
+            if (leader) mbar_arrive_expect_tx(&full_b[s], 4 * L::B_TILE_BYTES);   // both CTAs' hi + lo boxes
+            tma_load_2d_pair(b_hi, tm_hi, &full_b[s], kt * BK, nrow);
+            tma_load_2d_pair(b_lo, tm_lo, &full_b[s], kt * BK, nrow);
+          } else {
+            mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES);
+            tma_load_2d(b_hi, tm_hi, &full_b[s], kt * BK, nrow);
+            tma_load_2d(b_lo, tm_lo, &full_b[s], kt * BK, nrow);
+          }
         }
       }
     }
     __syncwarp();
   } else {
-    // =====================  A loaders  =====================
+    // =====================  A loaders (this CTA's 128 rows)  =====================
     const int grp = (warp - kFirstLoaderWarp) >> 2;         // loader group
     const int wg = (warp - kFirstLoaderWarp) & 3;           // warp inside the group
     const int tg = wg * 32 + lane;                          // thread inside the group
-    const int chunk = lane & 15;                            // float4 chunk within the 64-float K row
-    const int rsub = lane >> 4;                             // 2 rows per warp instruction
     uint8_t* rowtab = rowtab0 + grp * L::ROWTAB_BYTES;
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * BM;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int m0 = (tile / n_tiles) * TM + (int)rank * BM;
       // per-tile row table (this group's private copy)
       named_bar_sync(1 + grp, 128);
       {
@@ -351,14 +466,20 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
         } else {   // AMODE 1 (fp32 NHWC) and 2 (bf16 planes): im2col row table
           RowEntry* re = reinterpret_cast<RowEntry*>(rowtab);
           RowEntry e;
-          e.off = -1; e.hi0 = 0; e.wi0 = 0;
+          e.ptr = nullptr; e.mask = 0ull;
           if (m < M) {
-            int hw = a.Ho * a.Wo;
-            int b = m / hw, rem = m - b * hw;
-            int ho = rem / a.Wo, wo = rem - ho * a.Wo;
-            e.off = (long long)b * a.H * a.W * a.ldx;
-            e.hi0 = ho * a.stride - a.pad_t;
-            e.wi0 = wo * a.stride - a.pad_l;
+            const int hw = a.Ho * a.Wo;
+            const int b = m / hw, rem = m - b * hw;
+            const int ho = rem / a.Wo, wo = rem - ho * a.Wo;
+            const int hi0 = ho * a.stride - a.pad_t, wi0 = wo * a.stride - a.pad_l;
+            const long long off = (((long long)b * a.H + hi0) * a.W + wi0) * a.ldx;
+            if constexpr (AMODE == 1) e.ptr = a.x + off;
+            else e.ptr = reinterpret_cast<const void*>(off);       // element offset, shared by both planes
+            for (int kh = 0; kh < a.KH; ++kh)
+              for (int kw = 0; kw < a.KW; ++kw) {
+                const int hi = hi0 + kh, wi = wi0 + kw;
+                if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) e.mask |= 1ull << (kh * a.KW + kw);
+              }
           }
           re[tg] = e;
         }
@@ -368,35 +489,34 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
         if ((int)(it % kLoaderGroups) != grp) continue;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
+        const uint32_t a_hi = smem + s * L::STAGE_BYTES;
         if constexpr (AMODE == 2) {
           // pre-split bf16 planes: no conversion, no register staging -- each thread copies 8 x 16 bytes
           // (8 channels of one im2col row) per plane with cp.async straight into the swizzled tiles
           const int c8 = lane & 7, r4 = lane >> 3;
           const RowEntry* re = reinterpret_cast<const RowEntry*>(rowtab);
           const int kk8 = kt * BK + c8 * 8;
-          int kh = 0, kw = 0, ci = 0;
-          const bool kvalid = kk8 < K;
-          if (kvalid) {
-            int tap = kk8 / a.Cin;
-            ci = kk8 - tap * a.Cin;
-            kh = tap / a.KW;
-            kw = tap - kh * a.KW;
+          unsigned long long bit = 0ull;
+          long long tapoff = 0;
+          if (kk8 < K) {
+            const int tap = kk8 / a.Cin, ci = kk8 - tap * a.Cin;
+            const int kh = tap / a.KW, kw = tap - kh * a.KW;
+            bit = 1ull << tap;
+            tapoff = ((long long)kh * a.W + kw) * a.ldx + ci;
           }
           mbar_wait(&empty[s], ph ^ 1);
-          const uint32_t a_hi = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = wg * 32 + i * 4 + r4;
             const RowEntry e = re[row];
-            const int hi = e.hi0 + kh, wi = e.wi0 + kw;
-            const bool ok = kvalid && e.off >= 0 && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
-            const long long go = ok ? e.off + ((long long)hi * a.W + wi) * a.ldx + ci : 0;
+            const bool ok = (e.mask & bit) != 0ull;
+            const long long go = ok ? reinterpret_cast<long long>(e.ptr) + tapoff : 0;
             const uint32_t so = (uint32_t)row * 128u + ((uint32_t)(c8 ^ (row & 7)) << 4);
             const uint32_t nbytes = ok ? 16u : 0u;      // src-size 0 -> 16 zero bytes (SAME padding, K tail)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_hi + so), "l"(a.hi + go), "r"(nbytes)
                          : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_lo + so), "l"(a.lo + go), "r"(nbytes)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_hi + A_TILE_BYTES + so), "l"(a.lo + go),
+                         "r"(nbytes)
                          : "memory");
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
@@ -404,74 +524,99 @@ gemm_bf16x3_kernel(typename AParam<AMODE>::type a, const __grid_constant__ CUten
           fence_proxy_async();
           mbar_arrive(&full_a[s]);
         } else {
-        float4 v[16];
-        const int kk = kt * BK + chunk * 4;
-        if constexpr (AMODE == 0) {
-          const float* const* rp = reinterpret_cast<const float* const*>(rowtab);
-          int seg = -1, col = kk;
-          if (kk < K) {
+          const int chunk = lane & 15;                            // float4 chunk within the 64-float K row
+          const int rsub = lane >> 4;                             // 2 rows per warp instruction
+          float4 v[16];
+          const int kk = kt * BK + chunk * 4;
+          if constexpr (AMODE == 0) {
+            const float* const* rp = reinterpret_cast<const float* const*>(rowtab);
+            int seg = -1, col = kk;
+            if (kk < K) {
 #pragma unroll
-            for (int sg = 0; sg < 3; ++sg) {
-              if (seg < 0 && sg < a.nseg) {
-                if (col < a.seg[sg].ncols) seg = sg;
-                else col -= a.seg[sg].ncols;
+              for (int sg = 0; sg < 3; ++sg) {
+                if (seg < 0 && sg < a.nseg) {
+                  if (col < a.seg[sg].ncols) seg = sg;
+                  else col -= a.seg[sg].ncols;
+                }
               }
             }
+            const float* const* rps = rp + (seg >= 0 ? seg : 0) * BM + wg * 32 + rsub;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float* p = (seg >= 0) ? rps[i * 2] : nullptr;
+              v[i] = p ? ldg4(p + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          } else {
+            const RowEntry* re = reinterpret_cast<const RowEntry*>(rowtab) + wg * 32 + rsub;
+            unsigned long long bit = 0ull;
+            int tapoff = 0;
+            if (kk < K) {
+              const int tap = kk / a.Cin, ci = kk - tap * a.Cin;
+              const int kh = tap / a.KW, kw = tap - kh * a.KW;
+              bit = 1ull << tap;
+              tapoff = (kh * a.W + kw) * a.ldx + ci;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const RowEntry e = re[i * 2];
+              v[i] = (e.mask & bit) ? ldg4(static_cast<const float*>(e.ptr) + tapoff) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          mbar_wait(&empty[s], ph ^ 1);
+          // K-major SWIZZLE_128B tile: row r at r*128 bytes, its 16-byte chunk c at ((c ^ (r & 7)) << 4).
+          // row = wg*32 + i*2 + rsub: (row & 7) takes 4 values over i, rows 8 apart are 1024 bytes apart
+          uint32_t sw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t r7 = (uint32_t)(j * 2 + rsub);
+            sw[j] = a_hi + (uint32_t)(wg * 32 + j * 2 + rsub) * 128u + ((((uint32_t)chunk >> 1) ^ r7) << 4) +
+                    (((uint32_t)chunk & 1u) << 3);
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            int row = wg * 32 + i * 2 + rsub;
-            const float* p = (seg >= 0) ? rp[seg * BM + row] : nullptr;
-            v[i] = p ? ldg4(p + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint2 h, l;
+            split4(v[i], h, l);
+            const uint32_t dst = sw[i & 3] + (uint32_t)(i >> 2) * 1024u;
+            sts_v2(dst, h.x, h.y);
+            sts_v2(dst + A_TILE_BYTES, l.x, l.y);
           }
-        } else if constexpr (AMODE == 1) {
-          const RowEntry* re = reinterpret_cast<const RowEntry*>(rowtab);
-          int kh = 0, kw = 0, ci = 0;
-          const bool kvalid = kk < K;
-          if (kvalid) {
-            int tap = kk / a.Cin;
-            ci = kk - tap * a.Cin;
-            kh = tap / a.KW;
-            kw = tap - kh * a.KW;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            int row = wg * 32 + i * 2 + rsub;
-            RowEntry e = re[row];
-            int hi = e.hi0 + kh, wi = e.wi0 + kw;
-            bool ok = kvalid && e.off >= 0 && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
-            v[i] = ok ? ldg4(a.x + e.off + ((long long)hi * a.W + wi) * a.ldx + ci)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+          if constexpr (PAIR) mbar_arrive_cluster(&full_a[s], 0);   // the leader counts both CTAs' loader threads
+          else mbar_arrive(&full_a[s]);
         }
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* a_hi = smem + s * L::STAGE_BYTES;
-        uint8_t* a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          int row = wg * 32 + i * 2 + rsub;
-          uint32_t off = row * 128 + ((((uint32_t)chunk >> 1) ^ (row & 7)) << 4) + ((chunk & 1) << 3);
-          uint2 h, l;
-          split4(v[i], h, l);
-          *reinterpret_cast<uint2*>(a_hi + off) = h;
-          *reinterpret_cast<uint2*>(a_lo + off) = l;
-        }
-        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(&full_a[s]);
-        }   // AMODE != 2
       }
     }
   }
 
-  // ---- teardown ----
+  // ---- teardown (PAIR: the peer's shared / tensor memory is in use until the leader's last UMMA retired) ----
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)L::TMEM_COLS)
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TMEM_COLS)
+                   : "memory");
   }
 }
+
+template <int BN, int STAGES, int AMODE>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16x3_kernel(const __grid_constant__ typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
+                   const __grid_constant__ CUtensorMap tm_lo, int M, int N, int K, const __grid_constant__ Epi epi) {
+  gemm_bf16x3_body<BN, STAGES, AMODE, false>(a, &tm_hi, &tm_lo, M, N, K, epi);
+}
+
+template <int BN, int STAGES, int AMODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bf16x3_pair_kernel(const __grid_constant__ typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
+                        const __grid_constant__ CUtensorMap tm_lo, int M, int N, int K,
+                        const __grid_constant__ Epi epi) {
+  gemm_bf16x3_body<BN, STAGES, AMODE, true>(a, &tm_hi, &tm_lo, M, N, K, epi);
+}
+
 
 // ---------------------------------------------------------------------------
 // Host side.
@@ -551,7 +696,7 @@ static __global__ void pack_bt_kernel(const float* __restrict__ W, int K, int N,
 template <int BN, int STAGES, int AMODE>
 inline cudaError_t launch_one(const typename AParam<AMODE>::type& a, const TcWeight& w, int bn_idx, int M, int N,
                               const Epi& epi, int num_sms, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, false>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BN, STAGES, AMODE>,
@@ -578,9 +723,45 @@ inline int pick_bn(int M, int N, int num_sms) {
   return 256;
 }
 
+template <int BN, int STAGES, int AMODE>
+inline cudaError_t launch_pair(const typename AParam<AMODE>::type& a, const TcWeight& w, int half_idx, int M, int N,
+                               const Epi& epi, int num_sms, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_pair_kernel<BN, STAGES, AMODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int tiles = ((N + BN - 1) / BN) * ((M + 2 * BM - 1) / (2 * BM));
+  int grid = 2 * tiles < (num_sms & ~1) ? 2 * tiles : (num_sms & ~1);
+  // the half-width TMA boxes (BN/2 rows) are the maps of the next smaller BN
+  gemm_bf16x3_pair_kernel<BN, STAGES, AMODE><<<grid, kThreads, L::TOTAL, st>>>(a, w.tm_hi[half_idx], w.tm_lo[half_idx],
+                                                                               M, N, w.K, epi);
+  return cudaGetLastError();
+}
+
+// 0: single-CTA kernels only; 1: CTA-pair (cta_group::2) kernel for launches with at least
+// `pair_min_tiles` 256-row pair tiles (process-wide switch, set through comic_set_option).
+inline int& pair_mode() { static int v = 0; return v; }
+inline int& pair_min_tiles() { static int v = 74; return v; }
+
 template <int AMODE>
 inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const TcWeight& w, int M, int N,
                                   const Epi& epi, int num_sms, cudaStream_t st) {
+  if constexpr (AMODE != 2) {
+    if (pair_mode() && N > 64) {
+      bool planes = false;
+      for (int r = 0; r < epi.nroute; ++r) planes = planes || epi.r[r].hi != nullptr;
+      const int mp = (M + 2 * BM - 1) / (2 * BM);
+      const int bnp = (N <= 128) ? 128 : 256;
+      if (!planes && mp * ((N + bnp - 1) / bnp) >= pair_min_tiles()) {
+        if (bnp == 128) return launch_pair<128, 4, AMODE>(a, w, 0, M, N, epi, num_sms, st);
+        return launch_pair<256, 3, AMODE>(a, w, 1, M, N, epi, num_sms, st);
+      }
+    }
+  }
   int bn = pick_bn(M, N, num_sms);
   if (bn == 64) return launch_one<64, 4, AMODE>(a, w, 0, M, N, epi, num_sms, st);
   if (bn == 128) return launch_one<128, 3, AMODE>(a, w, 1, M, N, epi, num_sms, st);

@@ -184,6 +184,11 @@ class Engine(object):
         self._packed = None
         self._ws = {}
         self.bound_cnn = False
+        # experiment hook: COMIC_B200_OPTS="name=value,..." applies engine tunables (set_option) to every
+        # engine of the process, e.g. to run the whole test suite on a non-default kernel variant
+        for kv in filter(None, os.environ.get('COMIC_B200_OPTS', '').split(',')):
+            name, value = kv.split('=')
+            self.set_option(name.strip(), int(value))
 
     # -- plumbing -----------------------------------------------------------
     def _check(self, rc):
@@ -409,7 +414,7 @@ class Engine(object):
         self._check(self.lib.comic_set_precision(self._h, {'f32': 0, 'tf32x3': 1, 'split': 1, 'fast': 2}[mode]))
 
     def set_option(self, name, value):
-        self._check(self.lib.comic_set_option(self._h, {'fused_attn_min_images': 0, 'enc_chunk_stem': 1, 'enc_chunk_28': 2, 'enc_chunk_14': 3, 'persistent_max_rows': 4, 'persistent_trace': 5, 'enc_planes': 6}[name], int(value)))
+        self._check(self.lib.comic_set_option(self._h, {'fused_attn_min_images': 0, 'enc_chunk_stem': 1, 'enc_chunk_28': 2, 'enc_chunk_14': 3, 'persistent_max_rows': 4, 'persistent_trace': 5, 'enc_planes': 6, 'gemm_pair': 7, 'gemm_pair_min_tiles': 8}[name], int(value)))
 
     def decode_trace(self, max_steps=256):
         """Per-phase clock stamps of the last persistent decode call: int64 array [steps, 2, 16]."""

@@ -132,6 +132,9 @@ int comic_set_precision(comic_handle_t h, int mode);
                                              * (cp.async operand loader, no conversion in the consumer);
                                              * 0 (default): fp32 NHWC activations, split by every consumer.  Measured
                                              * r01f: the GEMM is L2->SM-bandwidth bound either way, planes 12% slower */
+#define COMIC_OPT_GEMM_PAIR 7                /* 1: tensor-path GEMMs / convs on CTA pairs (tcgen05 cta_group::2, 256-row
+                                             * tiles, each CTA loads half of the weight tile); process-wide */
+#define COMIC_OPT_GEMM_PAIR_MIN_TILES 8      /* ... for launches with at least this many 256-row tiles (default 74) */
 int comic_set_option(comic_handle_t h, int option, int value);
 
 /* Diagnostics: clock64 stamps of the last persistent decode call, [steps][2][16] int64 (CTA 0 and the first

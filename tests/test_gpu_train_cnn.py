@@ -57,11 +57,14 @@ def encoder_case(torch_mod):
 
 @pytest.mark.parametrize('precision,tol', [('f32', 5e-3), ('split', 5e-3)])
 def test_encoder_backward_matches_autograd(torch_mod, encoder_case, precision, tol):
+    """'split' runs the BACKWARD GEMMs (dgrad) on the tcgen05 bf16x3 kernel over the tape of an fp32 forward:
+    a bf16x3 forward perturbs pre-activations by ~2^-16 and flips ~100x more ReLU masks on this 2-image case
+    than fp32 round-off does (measured 2-8% on early-layer gradients), which says nothing about the backward."""
     from comic_b200.train import Trainer
     k = encoder_case
     tr = Trainer(k['c'], k['W'])
     eng = tr.engine
-    eng.set_precision(precision)
+    eng.set_precision('f32')
     img = eng.to_dev(k['img'])
     emb, fm = eng.encode_train(img)
     assert rel_err(fm.cpu().numpy(), k['fm']) < 2e-4
@@ -70,6 +73,7 @@ def test_encoder_backward_matches_autograd(torch_mod, encoder_case, precision, t
     emb2, fm2 = eng.encode(img)
     assert rel_err(fm.cpu().numpy(), fm2.cpu().numpy()) < 1e-6
     tr.grads.zero_()
+    eng.set_precision(precision)
     eng.encode_bwd(img, eng.to_dev(k['Gf']), eng.to_dev(k['Ge']), tr.cnn_grad_w, tr.cnn_grad_b)
     worst = {}
     for name in _grad_names():
