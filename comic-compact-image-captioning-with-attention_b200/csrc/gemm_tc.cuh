@@ -287,8 +287,12 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
 
   if (warp < kEpiWarps) {
     // =====================  epilogue (this CTA's 128 rows)  =====================
-    // one plain fp32 destination: the row pointer is formed once per tile
-    const bool simple = epi.nroute == 1 && epi.r[0].hi == nullptr && epi.r[0].n0 == 0;
+    // Routing: column ranges are multiples of 8, so a 4-column group never straddles two routes.  The
+    // row pointers of every destination (fp32 and / or the bf16 hi / lo planes), pre-offset so that
+    // column n lands at ptr + n, are formed once per tile; per group the route is two compares.
+    const int nr = epi.nroute;
+    const int b1 = nr > 1 ? epi.r[1].n0 : 0x7fffffff;
+    const int b2 = nr > 2 ? epi.r[2].n0 : 0x7fffffff;
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const int m0 = (tile / n_tiles) * TM + (int)rank * BM;
@@ -298,7 +302,17 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
       mbar_wait(&tmem_full[acc], (uint32_t)((iter >> 1) & 1));
       tc_fence_after();
       const int m = m0 + warp * 32 + lane;
-      float* rowp = simple ? epi.r[0].dst + (size_t)m * epi.r[0].ld + epi.r[0].coff : nullptr;
+      float* fp[3];
+      uint16_t* hp[3];
+      uint16_t* lp[3];
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        const bool on = rr < nr;
+        const long long o = on ? (long long)m * epi.r[rr].ld + epi.r[rr].coff - epi.r[rr].n0 : 0;
+        fp[rr] = (on && epi.r[rr].dst) ? epi.r[rr].dst + o : nullptr;
+        hp[rr] = (on && epi.r[rr].hi) ? epi.r[rr].hi + o : nullptr;
+        lp[rr] = (on && epi.r[rr].hi) ? epi.r[rr].lo + o : nullptr;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < n_umma; c0 += 16) {
         uint32_t r[16];
@@ -328,22 +342,15 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
             if (epi.relu) {
               v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
             }
-            if (simple) {
-              *reinterpret_cast<float4*>(rowp + n) = v;
-            } else {
-#pragma unroll
-              for (int rr = 0; rr < 3; ++rr) {
-                if (rr < epi.nroute && n >= epi.r[rr].n0 && n < epi.r[rr].n1) {
-                  const size_t o = (size_t)m * epi.r[rr].ld + epi.r[rr].coff + (n - epi.r[rr].n0);
-                  if (epi.r[rr].dst) *reinterpret_cast<float4*>(epi.r[rr].dst + o) = v;
-                  if (epi.r[rr].hi) {
-                    uint2 ph, pl;
-                    split4(v, ph, pl);
-                    *reinterpret_cast<uint2*>(epi.r[rr].hi + o) = ph;
-                    *reinterpret_cast<uint2*>(epi.r[rr].lo + o) = pl;
-                  }
-                }
-              }
+            float* f = n >= b2 ? fp[2] : (n >= b1 ? fp[1] : fp[0]);
+            uint16_t* ph = n >= b2 ? hp[2] : (n >= b1 ? hp[1] : hp[0]);
+            if (f) *reinterpret_cast<float4*>(f + n) = v;
+            if (ph) {
+              uint16_t* pl = n >= b2 ? lp[2] : (n >= b1 ? lp[1] : lp[0]);
+              uint2 sh, sl;
+              split4(v, sh, sl);
+              *reinterpret_cast<uint2*>(ph + n) = sh;
+              *reinterpret_cast<uint2*>(pl + n) = sl;
             }
           }
         }
