@@ -219,15 +219,17 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
   static constexpr int ROWTAB_BYTES = BM * 3 * 8;                 // 3 segment row pointers or RowEntry
-  static constexpr int BAR_BYTES = (3 * STAGES + 4) * 8 + 8;
-  static constexpr int TOTAL = TILES_BYTES + kLoaderGroups * ROWTAB_BYTES + BAR_BYTES + 1024;   // + alignment slack
+  static constexpr int BAR_BYTES = ((3 * STAGES + 4) * 8 + 8 + 15) & ~15;
+  static constexpr int EPI_STRIDE = 36;                           // floats per staged row: 32 columns + 4 pad (16-byte rows,
+                                                                  // conflict-free 128-bit row writes and column-group reads)
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_STRIDE * 4;   // per-warp 32 x 32 transpose buffer
+  static constexpr int TOTAL = TILES_BYTES + kLoaderGroups * ROWTAB_BYTES + BAR_BYTES + EPI_BYTES + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
 };
 
 template <int BN, int STAGES, int AMODE, bool PAIR>
 __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::type& a, const CUtensorMap* tm_hi,
                                                  const CUtensorMap* tm_lo, int M, int N, int K, const Epi& epi) {
-  static_assert(!(PAIR && AMODE == 2), "pair kernel: fp32 operand loaders only");
   using L = SmemLayout<BN, STAGES, PAIR>;
   constexpr int TM = PAIR ? 2 * BM : BM;        // rows per (pair) tile
   extern __shared__ uint8_t smem_raw[];
@@ -256,7 +258,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   // ---- one-time setup ----
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_a[s], PAIR ? 256 : 128);
+      mbar_init(&full_a[s], (AMODE == 2 ? 256 : 128) * (PAIR ? 2 : 1));
       mbar_init(&full_b[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -287,12 +289,17 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
 
   if (warp < kEpiWarps) {
     // =====================  epilogue (this CTA's 128 rows)  =====================
-    // Routing: column ranges are multiples of 8, so a 4-column group never straddles two routes.  The
-    // row pointers of every destination (fp32 and / or the bf16 hi / lo planes), pre-offset so that
-    // column n lands at ptr + n, are formed once per tile; per group the route is two compares.
+    // The accumulator comes out of tensor memory one ROW per lane (32x32b); written like that, a
+    // warp store touches 32 different rows (32 sectors per request).  Each 32 x 32 block is therefore
+    // passed through a per-warp shared-memory buffer and stored with 8 lanes per row (4 rows x 128
+    // contiguous bytes per request).  Folded BN / bias / ReLU are applied before staging.
+    // Routing: column ranges are multiples of 8, so a 4-column group never straddles two routes.
     const int nr = epi.nroute;
     const int b1 = nr > 1 ? epi.r[1].n0 : 0x7fffffff;
     const int b2 = nr > 2 ? epi.r[2].n0 : 0x7fffffff;
+    float* stage_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::BAR_BYTES) + warp * 32 * L::EPI_STRIDE;
+    const uint32_t stage_u32 = smem_u32(stage_buf);
+    const int srow = lane >> 3, scol = (lane & 7) * 4;       // store phase: row within a group of 4, first column
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const int m0 = (tile / n_tiles) * TM + (int)rank * BM;
@@ -301,36 +308,26 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
       const int n_umma = min(BN, ((N - n0) + 15) & ~15);
       mbar_wait(&tmem_full[acc], (uint32_t)((iter >> 1) & 1));
       tc_fence_after();
-      const int m = m0 + warp * 32 + lane;
-      float* fp[3];
-      uint16_t* hp[3];
-      uint16_t* lp[3];
-#pragma unroll
-      for (int rr = 0; rr < 3; ++rr) {
-        const bool on = rr < nr;
-        const long long o = on ? (long long)m * epi.r[rr].ld + epi.r[rr].coff - epi.r[rr].n0 : 0;
-        fp[rr] = (on && epi.r[rr].dst) ? epi.r[rr].dst + o : nullptr;
-        hp[rr] = (on && epi.r[rr].hi) ? epi.r[rr].hi + o : nullptr;
-        lp[rr] = (on && epi.r[rr].hi) ? epi.r[rr].lo + o : nullptr;
-      }
+      const int mw = m0 + warp * 32;                           // first row of this warp
 #pragma unroll 1
-      for (int c0 = 0; c0 < n_umma; c0 += 16) {
-        uint32_t r[16];
+      for (int c0 = 0; c0 < n_umma; c0 += 32) {
+        uint32_t r[32];
         uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0);
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-            "%14, %15}, [%16];"
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < M) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            int n = n0 + c0 + g * 4;
-            if (n >= N) continue;
-            float4 v = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                                   __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+        for (int g = 0; g < 8; ++g) {
+          const int n = n0 + c0 + g * 4;
+          float4 v = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                 __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+          if (n < N) {
             if (epi.scale) {
               float4 sc = ldg4(epi.scale + n);
               v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
@@ -342,18 +339,38 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
             if (epi.relu) {
               v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
             }
-            float* f = n >= b2 ? fp[2] : (n >= b1 ? fp[1] : fp[0]);
-            uint16_t* ph = n >= b2 ? hp[2] : (n >= b1 ? hp[1] : hp[0]);
-            if (f) *reinterpret_cast<float4*>(f + n) = v;
-            if (ph) {
-              uint16_t* pl = n >= b2 ? lp[2] : (n >= b1 ? lp[1] : lp[0]);
-              uint2 sh, sl;
-              split4(v, sh, sl);
-              *reinterpret_cast<uint2*>(ph + n) = sh;
-              *reinterpret_cast<uint2*>(pl + n) = sl;
+          }
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_u32 + (uint32_t)(lane * L::EPI_STRIDE + g * 4) * 4u),
+                       "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                       : "memory");
+        }
+        __syncwarp();
+        const int n = n0 + c0 + scol;
+        if (n < N) {
+          const int rt = n >= b2 ? 2 : (n >= b1 ? 1 : 0);
+          float* const fdst = epi.r[rt].dst;
+          uint16_t* const hdst = epi.r[rt].hi;
+          uint16_t* const ldst = epi.r[rt].lo;
+          const long long ld = epi.r[rt].ld;
+          const long long cofs = (long long)epi.r[rt].coff - epi.r[rt].n0 + n;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int row = q * 4 + srow;
+            const int m = mw + row;
+            if (m < M) {
+              const float4 v = *reinterpret_cast<const float4*>(stage_buf + row * L::EPI_STRIDE + scol);
+              const long long o = (long long)m * ld + cofs;
+              if (fdst) *reinterpret_cast<float4*>(fdst + o) = v;
+              if (hdst) {
+                uint2 sh, sl;
+                split4(v, sh, sl);
+                *reinterpret_cast<uint2*>(hdst + o) = sh;
+                *reinterpret_cast<uint2*>(ldst + o) = sl;
+              }
             }
           }
         }
+        __syncwarp();
       }
       // accumulator buffer drained -> the MMA warp may overwrite it
       tc_fence_before();
@@ -447,6 +464,84 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
     __syncwarp();
   } else {
     // =====================  A loaders (this CTA's 128 rows)  =====================
+    if constexpr (AMODE == 2) {
+      // Pre-split bf16 planes: no conversion and no register staging.  All 8 loader warps copy every K
+      // block (thread: 4 rows x one 16-byte chunk = 8 channels, per plane) with cp.async straight into the
+      // swizzled tiles, and up to STAGES blocks stay in flight: block `it` is retired (wait_group ->
+      // proxy fence -> full_a arrive) only when block it + STAGES - 1 has been issued, so the bytes in
+      // flight are bounded by the shared-memory ring, not by registers.
+      const int lw = warp - kFirstLoaderWarp;                 // 0..7
+      const int tg = lw * 32 + lane;                          // 0..255
+      const int c8 = lane & 7, r4 = lane >> 3;
+      RowEntry* re = reinterpret_cast<RowEntry*>(rowtab0);
+      uint32_t it = 0, retired = 0;
+      auto retire = [&]() {
+        fence_proxy_async();
+        uint64_t* bar = &full_a[retired % STAGES];
+        if constexpr (PAIR) mbar_arrive_cluster(bar, 0);
+        else mbar_arrive(bar);
+        ++retired;
+      };
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int m0 = (tile / n_tiles) * TM + (int)rank * BM;
+        named_bar_sync(1, 256);
+        if (tg < BM) {
+          const int m = m0 + tg;
+          RowEntry e;
+          e.ptr = nullptr; e.mask = 0ull;
+          if (m < M) {
+            const int hw = a.Ho * a.Wo;
+            const int b = m / hw, rem = m - b * hw;
+            const int ho = rem / a.Wo, wo = rem - ho * a.Wo;
+            const int hi0 = ho * a.stride - a.pad_t, wi0 = wo * a.stride - a.pad_l;
+            e.ptr = reinterpret_cast<const void*>((((long long)b * a.H + hi0) * a.W + wi0) * a.ldx);   // element offset
+            for (int kh = 0; kh < a.KH; ++kh)
+              for (int kw = 0; kw < a.KW; ++kw) {
+                const int hi = hi0 + kh, wi = wi0 + kw;
+                if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) e.mask |= 1ull << (kh * a.KW + kw);
+              }
+          }
+          re[tg] = e;
+        }
+        named_bar_sync(1, 256);
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          const uint32_t a_hi = smem + s * L::STAGE_BYTES;
+          const int kk8 = kt * BK + c8 * 8;
+          unsigned long long bit = 0ull;
+          long long tapoff = 0;
+          if (kk8 < K) {
+            const int tap = kk8 / a.Cin, ci = kk8 - tap * a.Cin;
+            const int kh = tap / a.KW, kw = tap - kh * a.KW;
+            bit = 1ull << tap;
+            tapoff = ((long long)kh * a.W + kw) * a.ldx + ci;
+          }
+          mbar_wait(&empty[s], ph ^ 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = lw * 16 + i * 4 + r4;
+            const RowEntry e = re[row];
+            const bool ok = (e.mask & bit) != 0ull;
+            const long long go = ok ? reinterpret_cast<long long>(e.ptr) + tapoff : 0;
+            const uint32_t so = (uint32_t)row * 128u + ((uint32_t)(c8 ^ (row & 7)) << 4);
+            const uint32_t nbytes = ok ? 16u : 0u;      // src-size 0 -> 16 zero bytes (SAME padding, K tail)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_hi + so), "l"(a.hi + go), "r"(nbytes)
+                         : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_hi + A_TILE_BYTES + so), "l"(a.lo + go),
+                         "r"(nbytes)
+                         : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (it + 1 - retired == (uint32_t)STAGES) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+            retire();
+          }
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      while (retired < it) retire();
+    } else {
     const int grp = (warp - kFirstLoaderWarp) >> 2;         // loader group
     const int wg = (warp - kFirstLoaderWarp) & 3;           // warp inside the group
     const int tg = wg * 32 + lane;                          // thread inside the group
@@ -497,40 +592,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         const uint32_t a_hi = smem + s * L::STAGE_BYTES;
-        if constexpr (AMODE == 2) {
-          // pre-split bf16 planes: no conversion, no register staging -- each thread copies 8 x 16 bytes
-          // (8 channels of one im2col row) per plane with cp.async straight into the swizzled tiles
-          const int c8 = lane & 7, r4 = lane >> 3;
-          const RowEntry* re = reinterpret_cast<const RowEntry*>(rowtab);
-          const int kk8 = kt * BK + c8 * 8;
-          unsigned long long bit = 0ull;
-          long long tapoff = 0;
-          if (kk8 < K) {
-            const int tap = kk8 / a.Cin, ci = kk8 - tap * a.Cin;
-            const int kh = tap / a.KW, kw = tap - kh * a.KW;
-            bit = 1ull << tap;
-            tapoff = ((long long)kh * a.W + kw) * a.ldx + ci;
-          }
-          mbar_wait(&empty[s], ph ^ 1);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = wg * 32 + i * 4 + r4;
-            const RowEntry e = re[row];
-            const bool ok = (e.mask & bit) != 0ull;
-            const long long go = ok ? reinterpret_cast<long long>(e.ptr) + tapoff : 0;
-            const uint32_t so = (uint32_t)row * 128u + ((uint32_t)(c8 ^ (row & 7)) << 4);
-            const uint32_t nbytes = ok ? 16u : 0u;      // src-size 0 -> 16 zero bytes (SAME padding, K tail)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_hi + so), "l"(a.hi + go), "r"(nbytes)
-                         : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_hi + A_TILE_BYTES + so), "l"(a.lo + go),
-                         "r"(nbytes)
-                         : "memory");
-          }
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          fence_proxy_async();
-          mbar_arrive(&full_a[s]);
-        } else {
+        {
           const int chunk = lane & 15;                            // float4 chunk within the 64-float K row
           const int rsub = lane >> 4;                             // 2 rows per warp instruction
           float4 v[16];
@@ -593,6 +655,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
         }
       }
     }
+    }   // AMODE != 2
   }
 
   // ---- teardown (PAIR: the peer's shared / tensor memory is in use until the leader's last UMMA retired) ----
