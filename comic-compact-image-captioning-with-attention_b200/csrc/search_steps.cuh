@@ -107,7 +107,13 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
     for (int w = 1; w < 8; ++w) m2 = fmaxf(m2, S.s_rv[w]);
     group_sync(1, 256);
     float sm = 0.f;
-    for (int i = tid; i < V; i += 256) sm += expf(ld_logit(row + i) - m2);
+    if (staged) {
+      for (int i = tid; i < V; i += 256) sm += expf(ld_logit(row + i) - m2);
+    } else {
+      // word vocabularies: 10^4 exponentials per row -- ex2.approx-based exp (relative error ~1e-6 per
+      // term, far below the fp32 rounding of the log-prob it feeds)
+      for (int i = tid; i < V; i += 256) sm += __expf(ld_logit(row + i) - m2);
+    }
     sm = warp_sum(sm);
     if (lane == 0) S.s_rv[warp] = sm;
     group_sync(1, 256);
@@ -133,15 +139,99 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
     long long len = S.s_len[j] + ((!S.s_fin[j] && w != eos) ? 1 : 0);
     return tot / length_penalty_dev(len, lpw);
   };
+  if (!staged && k <= 8) {
+    // Large vocabularies: ONE scan.  Every thread keeps the 8 best of its own candidates (sorted by
+    // (score desc, flat index asc), in registers); the k winners are then drawn in k rounds of a block
+    // arg-max over the threads' list heads, the winning thread popping its head.  Same candidates, same
+    // per-candidate arithmetic and the same total order as the k-pass selection below.
+    float tv[8];
+    int ti[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
+    for (int j = 0; j < k; ++j) {
+      const float* row = base + (size_t)j * ldr;
+      const float mxj = S.s_max[j], lsej = S.s_lse[j], cumj = S.s_cum[j];
+      const bool finj = S.s_fin[j] != 0;
+      const long long lenj = S.s_len[j];
+      const float pen_live = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj + (finj ? 0 : 1), lpw);
+      const float pen_eos = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj, lpw);
+      const int off = j * V;
+      for (int w = tid; w < V; w += 256) {
+        float lp;
+        if (finj) lp = (w == eos) ? 0.0f : -FLT_MAX;
+        else lp = (ld_logit(row + w) - mxj) - lsej;
+        const float tot = cumj + lp;
+        const float sc = (lpw == 0.0f) ? tot : tot / ((w == eos) ? pen_eos : pen_live);
+        const int idx = off + w;
+        if (better(sc, idx, tv[7], ti[7])) {
+          tv[7] = sc; ti[7] = idx;
+#pragma unroll
+          for (int q = 7; q > 0; --q) {
+            if (better(tv[q], ti[q], tv[q - 1], ti[q - 1])) {
+              const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
+              const int fi = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = fi;
+            }
+          }
+        }
+      }
+    }
+    for (int sel = 0; sel < k; ++sel) {
+      float bv = tv[0];
+      int bi = ti[0];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { S.s_rv[warp] = bv; S.s_ri[warp] = bi; }
+      group_sync(1, 256);
+      bv = S.s_rv[0]; bi = S.s_ri[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w)
+        if (better(S.s_rv[w], S.s_ri[w], bv, bi)) { bv = S.s_rv[w]; bi = S.s_ri[w]; }
+      group_sync(1, 256);
+      if (ti[0] == bi && bi != 0x7fffffff) {      // this thread owned the winner: pop it
+#pragma unroll
+        for (int q = 0; q < 7; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
+        tv[7] = -INFINITY; ti[7] = 0x7fffffff;
+      }
+      if (tid == 0) { S.s_selv[sel] = bv; S.s_seli[sel] = bi; }
+    }
+  } else {
   float pv = INFINITY;
   int pi = -1;
   for (int sel = 0; sel < k; ++sel) {
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int idx = tid; idx < ncand; idx += 256) {
-      float sc = score_of(idx, total_of(idx));
-      bool eligible = (sc < pv) || (sc == pv && idx > pi);
-      if (eligible && better(sc, idx, bv, bi)) { bv = sc; bi = idx; }
+    if (staged) {
+      for (int idx = tid; idx < ncand; idx += 256) {
+        float sc = score_of(idx, total_of(idx));
+        bool eligible = (sc < pv) || (sc == pv && idx > pi);
+        if (eligible && better(sc, idx, bv, bi)) { bv = sc; bi = idx; }
+      }
+    } else {
+      // large vocabularies (word models): same arithmetic per candidate, but walked row by row so the
+      // flat index never has to be divided by V and the per-row terms are hoisted out of the scan
+      for (int j = 0; j < k; ++j) {
+        const float* row = base + (size_t)j * ldr;
+        const float mxj = S.s_max[j], lsej = S.s_lse[j], cumj = S.s_cum[j];
+        const bool finj = S.s_fin[j] != 0;
+        const long long lenj = S.s_len[j];
+        const float pen_live = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj + (finj ? 0 : 1), lpw);
+        const float pen_eos = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj, lpw);
+        const int off = j * V;
+        for (int w = tid; w < V; w += 256) {
+          float lp;
+          if (finj) lp = (w == eos) ? 0.0f : -FLT_MAX;
+          else lp = (ld_logit(row + w) - mxj) - lsej;
+          const float tot = cumj + lp;
+          const float sc = (lpw == 0.0f) ? tot : tot / ((w == eos) ? pen_eos : pen_live);
+          const int idx = off + w;
+          const bool eligible = (sc < pv) || (sc == pv && idx > pi);
+          if (eligible && better(sc, idx, bv, bi)) { bv = sc; bi = idx; }
+        }
+      }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -159,6 +249,7 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
     pv = bv; pi = bi;
     if (tid == 0) { S.s_selv[sel] = bv; S.s_seli[sel] = bi; }
   }
+  }   // k-pass selection
   group_sync(1, 256);
   if (tid < k) {
     int idx = S.s_seli[tid];
