@@ -52,6 +52,7 @@ struct Packed {
   tc::TcWeight tc_conv[COMIC_NUM_CONVS];
   tc::TcWeight tc_grp[kNumBlocks];
   tc::TcWeight tc_lstm, tc_outq, tc_mem, tc_val, tc_init;
+  tc::TcWeight tc_stem_s2d;      // Conv2d_1a_7x7 as a 4x4 conv over the space-to-depth image: W2 [4,4,16,64]
 };
 
 }  // namespace comic
@@ -74,6 +75,7 @@ struct comic_handle_s {
   long long* last_trace = nullptr;
   int last_trace_steps = 0;
   int persist_max_rows = 32;   // whole decode loop as one cooperative kernel up to this many rows (0 = off)
+  int stem_s2d = 1;            // tensor path: stem conv over the space-to-depth bf16-plane image (0 = fp32 NHWC4 gather)
   int enc_planes = 0;          // 1: encoder activations as pre-split bf16 planes on the tensor path (0 = fp32 NHWC)
   int enc_chunk[3] = {64, 256, 512};   // images per encoder chunk: stem / 28x28 blocks / 14x14 + 7x7 blocks
   comic::Packed pk;

@@ -88,6 +88,8 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int rows, int co
   }
 }
 
+__global__ void pack_stem_s2d_kernel(const float* __restrict__ W, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo);
+
 int encoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
   const BlockDesc* blk = block_table();
   for (int i = 0; i < COMIC_NUM_CONVS; ++i) {
@@ -120,7 +122,16 @@ int encoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
     h->pk.tc_grp[b].lo = cv.take<uint16_t>((size_t)round_up(blk[b].b0 + blk[b].b1a + blk[b].b2a, 16) *
                                         round_up(blk[b].cin, tc::BK));
   }
+  {
+    tc::TcWeight& tw = h->pk.tc_stem_s2d;
+    tw.N = 64; tw.K = 256; tw.Npad = 64; tw.Kpad = 256;
+    tw.hi = cv.take<uint16_t>(64 * 256);
+    tw.lo = cv.take<uint16_t>(64 * 256);
+    tw.ready = false;
+  }
   if (dry) return COMIC_OK;
+  pack_stem_s2d_kernel<<<(64 * 256 + 255) / 256, 256, 0, st>>>(h->w.conv_w[0], h->pk.tc_stem_s2d.hi, h->pk.tc_stem_s2d.lo);
+  COMIC_REQUIRE(tc::make_weight_maps(h->pk.tc_stem_s2d), COMIC_E_CUDA, "cuTensorMapEncodeTiled failed (stem panel)");
   for (int i = 0; i < COMIC_NUM_CONVS; ++i) {
     int n = kConvs[i].c_out;
     bn_fold_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->w.bn_beta[i], h->w.bn_mean[i], h->w.bn_var[i],
@@ -158,6 +169,58 @@ __global__ void pad_c3_c4_kernel(const float* __restrict__ x, float* __restrict_
     float4 v = make_float4(x[i * 3 + 0], x[i * 3 + 1], x[i * 3 + 2], 0.f);
     reinterpret_cast<float4*>(y)[i] = v;
   }
+}
+
+
+// --------------------------------------------------------------------------
+// Stem conv as a 4x4 stride-1 conv over the space-to-depth image (tensor path).
+// Conv2d_1a_7x7 (stride 2, SAME: pad 2 before / 3 after, common/nets/inception_v1.py:70) reads input row
+// 2*ho - 2 + kh = 2*(ho - 1 + (kh >> 1)) + (kh & 1): with X2[n, i, j, (a*2 + b)*3 + c] = x[n, 2i + a, 2j + b, c]
+// it is   y[ho, wo] = sum_{di, dj < 4} sum_{ch < 12} X2[ho - 1 + di, wo - 1 + dj, ch] * W2[di, dj, ch]
+// with W2[di, dj, (a*2 + b)*3 + c] = W[2di + a, 2dj + b, c] (zero where 2di + a or 2dj + b reaches 7): the same
+// products, but 16-channel taps (12 + 4 zero) that the bf16-plane loader copies with cp.async instead of
+// gathering 49 single-pixel taps per output.  X2 is stored directly as bf16 (hi, lo) planes.
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+s2d_split_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, size_t npix2) {
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;      // (n, i2, j2) over [B, 112, 112]
+  if (i >= npix2) return;
+  const size_t j2 = i % 112, t = i / 112;
+  const size_t i2 = t % 112, n = t / 112;
+  const float* r0 = x + ((n * 224 + 2 * i2) * 224 + 2 * j2) * 3;      // x[n, 2i, 2j..2j+1, :] = 6 floats
+  const float* r1 = r0 + 224 * 3;
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) { v[q] = __ldg(r0 + q); v[6 + q] = __ldg(r1 + q); }
+  v[12] = v[13] = v[14] = v[15] = 0.f;
+  uint2 h[4], l[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tc::split4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), h[q], l[q]);
+  uint4* ph = reinterpret_cast<uint4*>(hi + i * 16);
+  uint4* pl = reinterpret_cast<uint4*>(lo + i * 16);
+  ph[0] = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+  ph[1] = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+  pl[0] = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y);
+  pl[1] = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
+}
+
+// W [7,7,3,64] HWIO -> B^T hi/lo panels [64, 256] (K-major) of W2 [4,4,16,64]
+__global__ void pack_stem_s2d_kernel(const float* __restrict__ W, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 256) return;
+  const int n = i / 256, kp = i % 256;
+  const int di = kp / 64, dj = (kp / 16) % 4, ch = kp % 16;
+  float v = 0.f;
+  if (ch < 12) {
+    const int a = ch / 6, b = (ch / 3) % 2, c = ch % 3;
+    const int kh = 2 * di + a, kw = 2 * dj + b;
+    if (kh < 7 && kw < 7) v = W[((kh * 7 + kw) * 3 + c) * 64 + n];
+  }
+  uint32_t h = tc::pack_bf16x2(v, 0.f) & 0xffffu;
+  float hf = __uint_as_float(h << 16);
+  uint32_t l = tc::pack_bf16x2(v - hf, 0.f) & 0xffffu;
+  hi[i] = (uint16_t)h;
+  lo[i] = (uint16_t)l;
 }
 
 // --------------------------------------------------------------------------
@@ -529,6 +592,33 @@ static int run_conv_p(comic_handle_t h, Planes x, int B, int H, int W, int ldx, 
   return COMIC_OK;
 }
 
+// Stem conv on the tensor path through the space-to-depth planes (see s2d_split_kernel): images [nb,224,224,3]
+// -> Conv2d_1a_7x7 output [nb,112,112,64] as fp32 (dst) and / or bf16 planes (dhi / dlo).  `scratch` holds the
+// X2 planes: 2 * nb*112*112*16 bf16.
+static int run_stem_s2d(comic_handle_t h, const float* img, int nb, float* scratch, float* dst, uint16_t* dhi,
+                        uint16_t* dlo, cudaStream_t st) {
+  const size_t npix2 = (size_t)nb * 112 * 112;
+  uint16_t* xh = reinterpret_cast<uint16_t*>(scratch);
+  uint16_t* xl = xh + npix2 * 16;
+  {
+    Prof pf(h, T_POOL, st);
+    s2d_split_kernel<<<(unsigned)((npix2 + 255) / 256), 256, 0, st>>>(img, xh, xl, npix2);
+  }
+  AConvP a;
+  a.hi = xh; a.lo = xl; a.H = 112; a.W = 112; a.Cin = 16; a.ldx = 16;
+  a.KH = 4; a.KW = 4; a.stride = 1; a.pad_t = 1; a.pad_l = 1; a.Ho = 112; a.Wo = 112;
+  Epi e{};
+  e.bias = h->pk.bn_shift[0]; e.scale = h->pk.bn_scale[0]; e.relu = 1; e.nroute = 1;
+  e.r[0] = Route{0, 64, dst, 64, 0, dhi, dlo};
+  cudaError_t err;
+  {
+    Prof pf(h, T_CONV, st);
+    err = tc::launch_gemm_tc<2>(a, h->pk.tc_stem_s2d, nb * 112 * 112, 64, e, h->num_sms, st);
+  }
+  COMIC_CHECK_CUDA(err);
+  return COMIC_OK;
+}
+
 struct PBufs {
   Planes t1, t2, p;
 };
@@ -590,8 +680,10 @@ static int encoder_forward_planes(comic_handle_t h, const float* images, int B, 
   for (int b0 = 0; b0 < B; b0 += pl.cs) {
     int nb = (B - b0 < pl.cs) ? (B - b0) : pl.cs;
     const float* img = images + (size_t)b0 * 224 * 224 * 3;
-    run_pad_c3_c4(h, img, fb, (size_t)nb * 224 * 224, st);
-    {
+    if (h->stem_s2d) {
+      if ((rc = run_stem_s2d(h, img, nb, fb, nullptr, pa.hi, pa.lo, st))) return rc;
+    } else {
+      run_pad_c3_c4(h, img, fb, (size_t)nb * 224 * 224, st);
       const comic_conv_desc_t& d = kConvs[0];
       AConv a;
       a.x = fb; a.H = 224; a.W = 224; a.Cin = 4; a.ldx = 4; a.KH = d.k; a.KW = d.k; a.stride = d.stride;
@@ -669,7 +761,9 @@ int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out,
     int nb = (B - b0 < pl.cs) ? (B - b0) : pl.cs;
     const float* img = images + (size_t)b0 * 224 * 224 * 3;
     int Ho, Wo;
-    if (use_tc(h, h->pk.tc_conv[0], nb * 112 * 112)) {
+    if (use_tc(h, h->pk.tc_stem_s2d, nb * 112 * 112) && h->stem_s2d) {
+      if ((rc = run_stem_s2d(h, img, nb, eb.b, eb.a, nullptr, nullptr, st))) return rc;
+    } else if (use_tc(h, h->pk.tc_conv[0], nb * 112 * 112)) {
       size_t npix = (size_t)nb * 224 * 224;
       {
         Prof pf(h, T_POOL, st);

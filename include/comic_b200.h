@@ -135,6 +135,8 @@ int comic_set_precision(comic_handle_t h, int mode);
 #define COMIC_OPT_GEMM_PAIR 7                /* 1: tensor-path GEMMs / convs on CTA pairs (tcgen05 cta_group::2, 256-row
                                              * tiles, each CTA loads half of the weight tile); process-wide */
 #define COMIC_OPT_GEMM_PAIR_MIN_TILES 8      /* ... for launches with at least this many 256-row tiles (default 74) */
+#define COMIC_OPT_STEM_S2D 9                 /* 1 (default): tensor-path stem conv as a 4x4 stride-1 conv over the
+                                             * space-to-depth image stored as bf16 planes; 0: 7x7/2 gather from NHWC4 fp32 */
 int comic_set_option(comic_handle_t h, int option, int value);
 
 /* Diagnostics: clock64 stamps of the last persistent decode call, [steps][2][16] int64 (CTA 0 and the first

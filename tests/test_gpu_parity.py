@@ -93,6 +93,13 @@ def test_encoder_chunking_batch_independent(torch_mod):
     emb2, fm2 = eng.encode(eng.to_dev(img))
     assert rel_err(fm2.cpu().numpy(), fm.cpu().numpy()) < 1e-4
     assert rel_err(emb2.cpu().numpy(), emb.cpu().numpy()) < 1e-4
+    # tensor path, stem conv: 4x4 stride-1 conv over the space-to-depth bf16-plane image (default) vs the
+    # 7x7 stride-2 gather from the NHWC4 fp32 image -- the same products in a different summation order
+    eng.set_option('stem_s2d', 0)
+    emb5, fm5 = eng.encode(eng.to_dev(img))
+    assert rel_err(fm5.cpu().numpy(), fm2.cpu().numpy()) < 5e-5
+    assert rel_err(emb5.cpu().numpy(), emb2.cpu().numpy()) < 5e-5
+    eng.set_option('stem_s2d', 1)
     # tensor path, activation storage: fp32 NHWC split by every consumer (default) vs pre-split bf16
     # (hi, lo) planes written by the producing conv's epilogue (option enc_planes): both feed the MMAs
     # 16-bit operand pairs and sit inside the tensor path's own error band against FFMA
