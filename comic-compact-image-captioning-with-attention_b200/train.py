@@ -48,6 +48,16 @@ def cosine_lr(step, max_step, lr_start, lr_end):
     return (lr_start - lr_end) * (1.0 + math.cos(s * math.pi)) / 2.0 + lr_end
 
 
+def legacy_lr_reduce(config, epoch, learning_rate):
+    """_lr_reduce_check (src/train_fn.py:310-317): the legacy models halve the rate every
+    `lr_reduce_every_n_epochs` epochs, floored at `lr_end`."""
+    if learning_rate > config.lr_end and epoch % config.lr_reduce_every_n_epochs == 0:
+        learning_rate /= 2
+        if learning_rate < config.lr_end:
+            learning_rate = config.lr_end
+    return learning_rate
+
+
 class Trainer(object):
     """Flat fp32 parameter / gradient / Adam-slot buffers over the decoder variables, one
     engine handle, one optimiser step per `step()`."""

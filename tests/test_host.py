@@ -105,3 +105,67 @@ def test_synthetic_vocab_layout():
     itow, wtoi = conf.synthetic_vocab(1000)
     assert wtoi['<EOS>'] == 999 and wtoi['<GO>'] == 998 and wtoi['<UNK>'] == 997 and wtoi['<PAD>'] == -1
     assert itow['0'] == 'w0' and len(itow) == 1000
+
+
+# ---------------------------------------------------------------------------
+# CLI mirror (src/train.py:25-164, src/infer.py:23-74)
+# ---------------------------------------------------------------------------
+def _reference_flags(path):
+    """(name -> (type name, default literal, choices literal)) parsed from an argparse source file."""
+    import ast
+    import re
+    src = open(path).read()
+    out = {}
+    for m in re.finditer(r"add_argument\(\s*'--(\w+)'(.*?)help=", src, re.S):
+        name, body = m.group(1), m.group(2)
+        t = re.search(r"type=(\w+)", body)
+        d = re.search(r"default=(.+?),\s*(?:choices=|$)", body.strip(), re.S)
+        c = re.search(r"choices=(\[.*?\])", body, re.S)
+        out[name] = (t.group(1) if t else None, d.group(1).strip().rstrip(',') if d else None,
+                     ast.literal_eval(c.group(1)) if c else None)
+    return out
+
+
+def test_cli_parsers_mirror_reference_flags():
+    import os
+    from comic_b200 import cli
+    tp, ip = cli.create_train_parser(), cli.create_infer_parser()
+    ours_t = {a.dest: a for a in tp._actions if a.dest != 'help'}
+    ours_i = {a.dest: a for a in ip._actions if a.dest != 'help'}
+    # known answers (SURVEY.md §8b): every flag of the two reference parsers
+    assert len(ours_t) == 39 and len(ours_i) == 14
+    assert ours_t['attn_num_heads'].default == 8 and ours_t['scst_beam_size'].default == 7
+    assert ours_t['cnn_input_size'].default == '224,224' and ours_t['adam_epsilon'].default == 1e-2
+    assert ours_i['infer_beam_size'].default == 3 and ours_i['batch_size_infer'].default == 25
+    ref_dir = '/root/reference/src'
+    if not os.path.exists(os.path.join(ref_dir, 'train.py')):
+        return
+    for ours, fname in ((ours_t, 'train.py'), (ours_i, 'infer.py')):
+        ref = _reference_flags(os.path.join(ref_dir, fname))
+        assert set(ref) == set(ours), (set(ref) ^ set(ours))
+        for name, (tname, dflt, choices) in ref.items():
+            a = ours[name]
+            assert a.type.__name__ == tname, name
+            assert (list(a.choices) if a.choices else None) == choices, name
+            if name in ('infer_checkpoints_dir', 'dataset_dir'):
+                continue                                   # path expressions of the reference's checkout
+            assert a.default == eval(dflt), (name, a.default, dflt)
+
+
+def test_cli_config_assembly():
+    from comic_b200 import cli
+    args = cli.create_train_parser().parse_args(['--train_mode', 'scst', '--cnn_fm_projection', 'none', '--run', '2'])
+    c = cli.config_from_train_args(args, n_words=500)
+    assert c.batch_size_train == 10 and c.lr_start == 1e-3 and c.max_epoch == 10        # src/train.py:252-262
+    assert c.cnn_fm_projection is None and c.rand_seed == 88888888                      # :277-279, :202-207
+    assert c.scst_weight_bleu == [0.0, 0.0, 0.0, 2.0] and c.cnn_input_size == [224, 224]
+
+
+def test_legacy_lr_schedule():
+    from comic_b200.train import legacy_lr_reduce
+    c = conf.make_config(legacy=True)                   # lr 1e-3 -> 2e-4, halved every 4 epochs (train.py:178-200)
+    lr, seen = c.lr_start, []
+    for epoch in range(1, 13):
+        lr = legacy_lr_reduce(c, epoch, lr)
+        seen.append(lr)
+    assert seen[2] == 1e-3 and seen[3] == 5e-4 and seen[7] == 2.5e-4 and seen[11] == 2e-4
