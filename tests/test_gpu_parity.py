@@ -477,3 +477,13 @@ def test_errors(torch_mod):
     eng = Engine(c)
     with pytest.raises(Exception):
         eng.project_fm(eng.f32(2, 196, 832))                     # weights not bound
+
+
+def test_cli_drivers_run(torch_mod, capsys):
+    """`python -m comic_b200.cli infer|train` (the reference's infer.py / train.py flag surface) on synthetic batches."""
+    from comic_b200 import cli
+    assert cli.main(['infer', '--batch_size_infer', '3', '--infer_max_length', '3', '--synthetic_batches', '2']) == 0
+    assert 'captions/s' in capsys.readouterr().out
+    assert cli.main(['train', '--train_mode', 'decoder', '--batch_size_train', '4', '--synthetic_steps', '2']) == 0
+    out = capsys.readouterr().out
+    assert 'steps/s' in out and 'step    2' in out
