@@ -77,7 +77,8 @@ struct comic_handle_s {
   int persist_max_rows = 32;   // whole decode loop as one cooperative kernel up to this many rows (0 = off)
   int stem_s2d = 1;            // tensor path: stem conv over the space-to-depth bf16-plane image (0 = fp32 NHWC4 gather)
   int enc_planes = 0;          // 1: encoder activations as pre-split bf16 planes on the tensor path (0 = fp32 NHWC)
-  int enc_chunk[3] = {64, 256, 512};   // images per encoder chunk: stem / 28x28 blocks / 14x14 + 7x7 blocks
+  int enc_chunk[3] = {256, 512, 512};  // images per encoder chunk: stem / 28x28 blocks / 14x14 + 7x7 blocks (measured r01p:
+                                       // the GEMMs are L2->SM bound, not HBM bound, so fewer, longer launches win over L2 residency)
   comic::Packed pk;
   int64_t launches = 0;
   // optional per-kernel-class device timing (bench.py roofline): CUDA events

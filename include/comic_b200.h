@@ -121,8 +121,8 @@ int comic_set_precision(comic_handle_t h, int mode);
 
 /* Engine tunables (no reference counterpart). */
 #define COMIC_OPT_FUSED_ATTN_MIN_IMAGES 0   /* one-CTA-per-image fused attention from this batch on (default 48) */
-#define COMIC_OPT_ENC_CHUNK_STEM 1          /* images per encoder chunk, stem convs (default 64) */
-#define COMIC_OPT_ENC_CHUNK_28 2            /* ... Mixed_3b/3c (default 256) */
+#define COMIC_OPT_ENC_CHUNK_STEM 1          /* images per encoder chunk, stem convs (default 256) */
+#define COMIC_OPT_ENC_CHUNK_28 2            /* ... Mixed_3b/3c (default 512) */
 #define COMIC_OPT_ENC_CHUNK_14 3            /* ... Mixed_4b..5c (default 512); set before comic_workspace_bytes */
 #define COMIC_OPT_PERSISTENT_MAX_ROWS 4      /* decode loops with batch*beam <= this run as ONE cooperative kernel
                                              * (default 32, the kernel's limit; 0 = always one launch per step op) */

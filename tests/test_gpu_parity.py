@@ -85,6 +85,8 @@ def test_encoder_chunking_batch_independent(torch_mod):
     W = make_weights(c)
     img = images(70, seed=5)
     eng = _engine(c, W, precision='f32')
+    for name, n in (('enc_chunk_stem', 64), ('enc_chunk_28', 48), ('enc_chunk_14', 40)):   # 64+6, 48+22, 40+30
+        eng.set_option(name, n)
     emb, fm = eng.encode(eng.to_dev(img))
     emb1, fm1 = eng.encode(eng.to_dev(img[67:68]))
     assert torch_mod.equal(fm[67:68], fm1)
