@@ -213,11 +213,14 @@ struct RowEntry {
 // the leader and collect (remote) arrivals of both CTAs; empty / tmem_full exist in both CTAs and
 // are signalled by the leader's multicast tcgen05.commit.  Operand layouts, epilogue and the UMMA
 // order per accumulator element are the same in both modes: results are bit-identical.
-template <int BN, int STAGES, bool PAIR>
+template <int BN, int STAGES, bool PAIR, int NKRES = 0>
 struct SmemLayout {
   static constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // this CTA's part of one weight tile (hi or lo)
-  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int TILES_BYTES = STAGES * STAGE_BYTES;
+  // NKRES > 0: the whole weight panel (<= NKRES K blocks, one N tile) is loaded ONCE per CTA and stays in shared
+  // memory; the ring then stages only A (more stages), and the panel is not re-streamed for every M tile
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + (NKRES ? 0 : 2 * B_TILE_BYTES);
+  static constexpr int PANEL_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TILES_BYTES = PANEL_OFF + NKRES * 2 * B_TILE_BYTES;
   static constexpr int ROWTAB_BYTES = BM * 3 * 8;                 // 3 segment row pointers or RowEntry
   static constexpr int BAR_BYTES = ((3 * STAGES + 4) * 8 + 8 + 15) & ~15;
   static constexpr int EPI_STRIDE = 36;                           // floats per staged row: 32 columns + 4 pad (16-byte rows,
@@ -227,10 +230,11 @@ struct SmemLayout {
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
 };
 
-template <int BN, int STAGES, int AMODE, bool PAIR>
+template <int BN, int STAGES, int AMODE, bool PAIR, int NKRES = 0>
 __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::type& a, const CUtensorMap* tm_hi,
                                                  const CUtensorMap* tm_lo, int M, int N, int K, const Epi& epi) {
-  using L = SmemLayout<BN, STAGES, PAIR>;
+  static_assert(!(PAIR && NKRES), "resident weight panel: single-CTA kernel only");
+  using L = SmemLayout<BN, STAGES, PAIR, NKRES>;
   constexpr int TM = PAIR ? 2 * BM : BM;        // rows per (pair) tile
   extern __shared__ uint8_t smem_raw[];
   if (epi.stop != nullptr && *epi.stop >= epi.stop_n) return;      // uniform over the grid
@@ -385,6 +389,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
     if (leader && lane == 0) {
       int iter = 0;
       uint32_t it = 0;
+      if constexpr (NKRES > 0) mbar_wait(&full_b[0], 0);      // resident weight panel landed
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
         const int n0 = (tile % n_tiles) * BN;
         const int acc = iter & 1;
@@ -402,12 +407,12 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
             mbar_wait_cluster(&full_b[s], ph);
           } else {
             mbar_wait(&full_a[s], ph);
-            mbar_wait(&full_b[s], ph);
+            if constexpr (NKRES == 0) mbar_wait(&full_b[s], ph);
           }
           tc_fence_after();
           const uint32_t a_hi = smem + s * L::STAGE_BYTES;
           const uint32_t a_lo = a_hi + A_TILE_BYTES;
-          const uint32_t b_hi = a_lo + A_TILE_BYTES;
+          const uint32_t b_hi = NKRES ? smem + L::PANEL_OFF + kt * 2 * L::B_TILE_BYTES : a_lo + A_TILE_BYTES;
           const uint32_t b_lo = b_hi + L::B_TILE_BYTES;
           const uint64_t dah = make_desc_sw128(a_hi), dal = make_desc_sw128(a_lo);
           const uint64_t dbh = make_desc_sw128(b_hi), dbl = make_desc_sw128(b_lo);
@@ -437,6 +442,16 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
     __syncwarp();
   } else if (warp == 5) {
     // =====================  TMA producer (this CTA's part of the weight tile)  =====================
+    if constexpr (NKRES > 0) {
+      if (lane == 0 && first_tile < total_tiles) {
+        mbar_arrive_expect_tx(&full_b[0], (uint32_t)nk * 2u * L::B_TILE_BYTES);
+        for (int kt = 0; kt < nk; ++kt) {
+          const uint32_t b_hi = smem + L::PANEL_OFF + kt * 2 * L::B_TILE_BYTES;
+          tma_load_2d(b_hi, tm_hi, &full_b[0], kt * BK, 0);
+          tma_load_2d(b_hi + L::B_TILE_BYTES, tm_lo, &full_b[0], kt * BK, 0);
+        }
+      }
+    } else
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -679,6 +694,14 @@ gemm_bf16x3_kernel(const __grid_constant__ typename AParam<AMODE>::type a, const
   gemm_bf16x3_body<BN, STAGES, AMODE, false>(a, &tm_hi, &tm_lo, M, N, K, epi);
 }
 
+// weights resident in shared memory (N <= 64, K <= NKRES * 64): see SmemLayout
+template <int STAGES, int NKRES, int AMODE>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16x3_bres_kernel(const __grid_constant__ typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
+                        const __grid_constant__ CUtensorMap tm_lo, int M, int N, int K, const __grid_constant__ Epi epi) {
+  gemm_bf16x3_body<64, STAGES, AMODE, false, NKRES>(a, &tm_hi, &tm_lo, M, N, K, epi);
+}
+
 template <int BN, int STAGES, int AMODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_bf16x3_pair_kernel(const __grid_constant__ typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
@@ -793,6 +816,26 @@ inline int pick_bn(int M, int N, int num_sms) {
   return 256;
 }
 
+template <int STAGES, int NKRES, int AMODE>
+inline cudaError_t launch_bres(const typename AParam<AMODE>::type& a, const TcWeight& w, int M, int N, const Epi& epi,
+                               int num_sms, cudaStream_t st) {
+  using L = SmemLayout<64, STAGES, false, NKRES>;
+  static_assert(L::TOTAL <= 232448, "resident-panel kernel exceeds the shared memory of an SM");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_bres_kernel<STAGES, NKRES, AMODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int tiles = (M + BM - 1) / BM;
+  int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_bf16x3_bres_kernel<STAGES, NKRES, AMODE><<<grid, kThreads, L::TOTAL, st>>>(a, w.tm_hi[0], w.tm_lo[0], M, N, w.K, epi);
+  return cudaGetLastError();
+}
+
+inline int& bres_mode() { static int v = 1; return v; }      // 0: always stream the weights (A/B experiment switch)
+
 template <int BN, int STAGES, int AMODE>
 inline cudaError_t launch_pair(const typename AParam<AMODE>::type& a, const TcWeight& w, int half_idx, int M, int N,
                                const Epi& epi, int num_sms, cudaStream_t st) {
@@ -833,6 +876,15 @@ inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const T
     }
   }
   int bn = pick_bn(M, N, num_sms);
+  if constexpr (AMODE != 0) {
+    // narrow convs (N <= 64): the whole weight panel fits beside the A ring -> load it once per CTA
+    if (bn == 64 && bres_mode() && (M + BM - 1) / BM >= 2 * num_sms) {
+      const int nkb = (w.K + BK - 1) / BK;
+      if (nkb <= 4) return launch_bres<4, 4, AMODE>(a, w, M, N, epi, num_sms, st);
+      if (nkb <= 6) return launch_bres<3, 6, AMODE>(a, w, M, N, epi, num_sms, st);
+      if (nkb <= 8) return launch_bres<2, 8, AMODE>(a, w, M, N, epi, num_sms, st);
+    }
+  }
   if (bn == 64) return launch_one<64, 4, AMODE>(a, w, 0, M, N, epi, num_sms, st);
   if (bn == 128) return launch_one<128, 3, AMODE>(a, w, 1, M, N, epi, num_sms, st);
   return launch_one<256, 2, AMODE>(a, w, 2, M, N, epi, num_sms, st);
