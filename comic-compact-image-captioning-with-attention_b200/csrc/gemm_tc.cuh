@@ -38,11 +38,13 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;                      // bf16 elements = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int kEpiWarps = 4;
+constexpr int kEpiWarps = 8;                    // warps w and w + 4 share tensor-memory lane quadrant w & 3 and alternate 16-column chunks
+constexpr int kMmaWarp = kEpiWarps;             // also allocates / frees tensor memory
+constexpr int kTmaWarp = kEpiWarps + 1;
 constexpr int kLoaderGroups = 2;                // must be <= the smallest STAGES: a group may run at most one
                                                 // mbarrier phase ahead of the stage it refills (parity aliasing otherwise)
-constexpr int kFirstLoaderWarp = 6;
-constexpr int kThreads = (kFirstLoaderWarp + 4 * kLoaderGroups) * 32;   // 448
+constexpr int kFirstLoaderWarp = kEpiWarps + 2;
+constexpr int kThreads = (kFirstLoaderWarp + 4 * kLoaderGroups) * 32;   // 576
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -223,9 +225,9 @@ struct SmemLayout {
   static constexpr int TILES_BYTES = PANEL_OFF + NKRES * 2 * B_TILE_BYTES;
   static constexpr int ROWTAB_BYTES = BM * 3 * 8;                 // 3 segment row pointers or RowEntry
   static constexpr int BAR_BYTES = ((3 * STAGES + 4) * 8 + 8 + 15) & ~15;
-  static constexpr int EPI_STRIDE = 36;                           // floats per staged row: 32 columns + 4 pad (16-byte rows,
-                                                                  // conflict-free 128-bit row writes and column-group reads)
-  static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_STRIDE * 4;   // per-warp 32 x 32 transpose buffer
+  static constexpr int EPI_STRIDE = 20;                           // floats per staged row: 16 columns + 4 pad (16-byte rows,
+                                                                  // conflict-free 128-bit row writes)
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_STRIDE * 4;   // per-warp 32 x 16 transpose buffer
   static constexpr int TOTAL = TILES_BYTES + kLoaderGroups * ROWTAB_BYTES + BAR_BYTES + EPI_BYTES + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
 };
@@ -272,7 +274,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
     }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     if constexpr (PAIR) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                    "r"((uint32_t)L::TMEM_COLS)
@@ -294,16 +296,20 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   if (warp < kEpiWarps) {
     // =====================  epilogue (this CTA's 128 rows)  =====================
     // The accumulator comes out of tensor memory one ROW per lane (32x32b); written like that, a
-    // warp store touches 32 different rows (32 sectors per request).  Each 32 x 32 block is therefore
-    // passed through a per-warp shared-memory buffer and stored with 8 lanes per row (4 rows x 128
-    // contiguous bytes per request).  Folded BN / bias / ReLU are applied before staging.
+    // warp store touches 32 different rows (32 sectors per request).  Each 32 x 16 block is therefore
+    // passed through a per-warp shared-memory buffer and stored with 4 lanes per row (8 rows x 64
+    // contiguous bytes per request).  Folded BN / bias / ReLU are applied after the transpose, where a
+    // lane owns 4 fixed columns (their scale / shift are loaded once per block).  Eight epilogue warps:
+    // warp w reads lane quadrant w & 3 and the 16-column blocks with parity w >> 2 -- for the short-K
+    // layers (1x1 convs: 3-8 K blocks per tile) the epilogue, not the main loop, sets the tile time.
     // Routing: column ranges are multiples of 8, so a 4-column group never straddles two routes.
     const int nr = epi.nroute;
     const int b1 = nr > 1 ? epi.r[1].n0 : 0x7fffffff;
     const int b2 = nr > 2 ? epi.r[2].n0 : 0x7fffffff;
+    const int quad = warp & 3, half = warp >> 2;
     float* stage_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::BAR_BYTES) + warp * 32 * L::EPI_STRIDE;
     const uint32_t stage_u32 = smem_u32(stage_buf);
-    const int srow = lane >> 3, scol = (lane & 7) * 4;       // store phase: row within a group of 4, first column
+    const int srow = lane >> 2, scol = (lane & 3) * 4;       // store phase: row within a group of 8, first column
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
       const int m0 = (tile / n_tiles) * TM + (int)rank * BM;
@@ -312,42 +318,23 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
       const int n_umma = min(BN, ((N - n0) + 15) & ~15);
       mbar_wait(&tmem_full[acc], (uint32_t)((iter >> 1) & 1));
       tc_fence_after();
-      const int mw = m0 + warp * 32;                           // first row of this warp
+      const int mw = m0 + quad * 32;                           // first row of this warp
 #pragma unroll 1
-      for (int c0 = 0; c0 < n_umma; c0 += 32) {
-        uint32_t r[32];
-        uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0);
+      for (int c0 = half * 16; c0 < n_umma; c0 += 32) {
+        uint32_t r[16];
+        uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0);
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+            "%14, %15}, [%16];"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int n = n0 + c0 + g * 4;
-          float4 v = make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                                 __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
-          if (n < N) {
-            if (epi.scale) {
-              float4 sc = ldg4(epi.scale + n);
-              v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
-            }
-            if (epi.bias) {
-              float4 bs = ldg4(epi.bias + n);
-              v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w;
-            }
-            if (epi.relu) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-            }
-          }
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_u32 + (uint32_t)(lane * L::EPI_STRIDE + g * 4) * 4u),
-                       "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_u32 + (uint32_t)(lane * L::EPI_STRIDE + g * 4) * 4u),
+                       "r"(r[g * 4 + 0]), "r"(r[g * 4 + 1]), "r"(r[g * 4 + 2]), "r"(r[g * 4 + 3])
                        : "memory");
-        }
         __syncwarp();
         const int n = n0 + c0 + scol;
         if (n < N) {
@@ -357,12 +344,19 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
           uint16_t* const ldst = epi.r[rt].lo;
           const long long ld = epi.r[rt].ld;
           const long long cofs = (long long)epi.r[rt].coff - epi.r[rt].n0 + n;
+          const float4 sc = epi.scale ? ldg4(epi.scale + n) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float4 bs = epi.bias ? ldg4(epi.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int row = q * 4 + srow;
+          for (int q = 0; q < 4; ++q) {
+            const int row = q * 8 + srow;
             const int m = mw + row;
             if (m < M) {
-              const float4 v = *reinterpret_cast<const float4*>(stage_buf + row * L::EPI_STRIDE + scol);
+              float4 v = *reinterpret_cast<const float4*>(stage_buf + row * L::EPI_STRIDE + scol);
+              if (epi.scale) { v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w; }
+              if (epi.bias) { v.x += bs.x; v.y += bs.y; v.z += bs.z; v.w += bs.w; }
+              if (epi.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
               const long long o = (long long)m * ld + cofs;
               if (fdst) *reinterpret_cast<float4*>(fdst + o) = v;
               if (hdst) {
@@ -384,7 +378,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
         else mbar_arrive(&tmem_empty[acc]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // =====================  MMA issuer (PAIR: leader CTA only)  =====================
     if (leader && lane == 0) {
       int iter = 0;
@@ -440,7 +434,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == kTmaWarp) {
     // =====================  TMA producer (this CTA's part of the weight tile)  =====================
     if constexpr (NKRES > 0) {
       if (lane == 0 && first_tile < total_tiles) {
@@ -677,7 +671,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   tc_fence_before();
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     if constexpr (PAIR)
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TMEM_COLS)
                    : "memory");
