@@ -60,6 +60,57 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gp, int nz, size
   if (h_drop) h_drop[i] = out_mask ? (hn / out_keep) * out_mask[i] : hn;
 }
 
+// Vectorised variant for the big-batch decode loop (R % 4 == 0, one split-K partial, no dropout / tape): four
+// units per thread with 128-bit accesses.  FAST (engine precision >= 1, the tensor path): sigmoid / tanh through
+// ex2.approx + rcp.approx (relative error ~1e-6 against expf / tanhf, same budget as the bf16x3 GEMM feeding it).
+template <bool FAST>
+__device__ __forceinline__ float sig_(float x) {
+  if (FAST) return __frcp_rn(1.0f + __expf(-x));
+  return 1.0f / (1.0f + expf(-x));
+}
+template <bool FAST>
+__device__ __forceinline__ float tanh_(float x) {
+  if (FAST) {
+    const float e = __expf(-2.0f * fabsf(x));           // in (0, 1]: no overflow
+    return copysignf((1.0f - e) * __frcp_rn(1.0f + e), x);
+  }
+  return tanhf(x);
+}
+template <bool FAST>
+__global__ void __launch_bounds__(256)
+lstm_pointwise4_kernel(const float* __restrict__ gates, const float* __restrict__ bias, const float* __restrict__ c_prev,
+                       const int* __restrict__ src, int src_limit, float* __restrict__ c_new, float* __restrict__ h_new,
+                       int N, int R, const int* fin_count, int t, int n_rows) {
+  if (step_stopped(fin_count, t, n_rows)) return;
+  const int R4 = R >> 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * R4) return;
+  const int n = i / R4, j = (i - n * R4) * 4;
+  const float* gr = gates + (size_t)n * 4 * R + j;
+  float4 g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v = ldg4(gr + q * R), b = ldg4(bias + q * R + j);
+    g[q] = make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
+  }
+  float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c_prev) {
+    const int r = src ? src[n] : n;
+    if (r >= 0 && r < src_limit) cp = ldg4(c_prev + (size_t)r * R + j);
+  }
+  const float gi[4] = {g[0].x, g[0].y, g[0].z, g[0].w}, gj[4] = {g[1].x, g[1].y, g[1].z, g[1].w};
+  const float gf[4] = {g[2].x, g[2].y, g[2].z, g[2].w}, go[4] = {g[3].x, g[3].y, g[3].z, g[3].w};
+  const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+  float cn[4], hn[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cn[q] = cpv[q] * sig_<FAST>(gf[q] + 1.0f) + sig_<FAST>(gi[q]) * tanh_<FAST>(gj[q]);
+    hn[q] = tanh_<FAST>(cn[q]) * sig_<FAST>(go[q]);
+  }
+  *reinterpret_cast<float4*>(c_new + (size_t)n * R + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+  *reinterpret_cast<float4*>(h_new + (size_t)n * R + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+}
+
 // Generic split-K reduction: out[m, n] = sum_z part[z][m][n] + bias[n].
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int nz, size_t zstride,
                                      const float* __restrict__ bias, float* __restrict__ out, int M, int ld,
@@ -662,6 +713,15 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
   {
     Prof pf(h, T_LSTM, st);
     int tot = N * R;
+    if (nz1 == 1 && R % 4 == 0 && !io.h_drop && !io.out_mask && !io.gates_save && N >= 128) {
+      const int tot4 = N * (R / 4);
+      if (h->precision >= 1)
+        lstm_pointwise4_kernel<true><<<(tot4 + 255) / 256, 256, 0, st>>>(sb.gates, h->w.lstm_bias, io.c_prev, io.src, io.src_limit,
+                                                                        io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows);
+      else
+        lstm_pointwise4_kernel<false><<<(tot4 + 255) / 256, 256, 0, st>>>(sb.gates, h->w.lstm_bias, io.c_prev, io.src, io.src_limit,
+                                                                         io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows);
+    } else
     lstm_pointwise_kernel<<<(tot + 255) / 256, 256, 0, st>>>(sb.gates, nz1, (size_t)N * 4 * R, h->w.lstm_bias,
                                                           io.c_prev, io.src, io.src_limit, io.c_new, io.h_new,
                                                           io.h_drop, io.out_mask, io.out_keep, N, R, io.fin_count,
