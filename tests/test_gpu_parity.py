@@ -242,7 +242,8 @@ def _beam_state(rng, B, k, V, with_finished):
 @pytest.mark.parametrize('B,k,V,lpw,fin', [(5, 3, 258, 0.0, False), (4, 3, 258, 0.0, True),
                                            (3, 7, 258, 0.7, True), (2, 3, 10000, 0.0, True),
                                            (1, 1, 300, 0.0, False), (6, 5, 64, 1.0, True),
-                                           (3, 4, 5000, 0.7, True), (2, 7, 3000, 0.0, False)])
+                                           (3, 4, 5000, 0.7, True), (2, 7, 3000, 0.0, False),
+                                           (70, 3, 258, 0.0, True), (65, 3, 258, 0.7, True), (64, 1, 300, 0.0, False)])
 def test_beam_step_bit_exact(torch_mod, B, k, V, lpw, fin):
     """K10 given identical total log-probs: ids / parents / lengths / finished
     bit-exact, ties -> lower flat index."""
