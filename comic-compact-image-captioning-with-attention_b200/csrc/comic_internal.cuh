@@ -75,7 +75,9 @@ struct comic_handle_s {
   long long* last_trace = nullptr;
   int last_trace_steps = 0;
   int persist_max_rows = 32;   // whole decode loop as one cooperative kernel up to this many rows (0 = off)
-  int stem_s2d = 1;            // tensor path: stem conv over the space-to-depth bf16-plane image (0 = fp32 NHWC4 gather)
+  int stem_s2d = 2;            // tensor path stem conv: 2 = space-to-depth planes, im2col tile built from a shared-memory
+                               // halo patch; 1 = same conv, operand rows gathered from L2 with cp.async; 0 = 7x7/2 gather
+                               // from the fp32 NHWC4 image
   int enc_planes = 0;          // 1: encoder activations as pre-split bf16 planes on the tensor path (0 = fp32 NHWC)
   int enc_chunk[3] = {256, 512, 512};  // images per encoder chunk: stem / 28x28 blocks / 14x14 + 7x7 blocks (measured r01p:
                                        // the GEMMs are L2->SM bound, not HBM bound, so fewer, longer launches win over L2 residency)

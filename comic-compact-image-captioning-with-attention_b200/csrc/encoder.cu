@@ -613,7 +613,13 @@ static int run_stem_s2d(comic_handle_t h, const float* img, int nb, float* scrat
   cudaError_t err;
   {
     Prof pf(h, T_CONV, st);
-    err = tc::launch_gemm_tc<2>(a, h->pk.tc_stem_s2d, nb * 112 * 112, 64, e, h->num_sms, st);
+    if (h->stem_s2d >= 2) {
+      AHalo ah;
+      ah.hi = xh; ah.lo = xl; ah.nimg = nb;
+      err = tc::launch_stem_halo(ah, h->pk.tc_stem_s2d, e, h->num_sms, st);
+    } else {
+      err = tc::launch_gemm_tc<2>(a, h->pk.tc_stem_s2d, nb * 112 * 112, 64, e, h->num_sms, st);
+    }
   }
   COMIC_CHECK_CUDA(err);
   return COMIC_OK;

@@ -72,10 +72,19 @@ struct AConvP {
   int KH, KW, stride, pad_t, pad_l, Ho, Wo;
 };
 
+// Stem conv over the space-to-depth image (bf16 planes [nimg,112,112,16]) with the im2col tile built from a
+// shared-memory halo patch instead of 16 L2 reads per input element (tensor path, gemm_tc.cuh AMODE 3).
+struct AHalo {
+  const uint16_t* hi;
+  const uint16_t* lo;
+  int nimg;
+};
+
 template <int AMODE> struct AParam;
 template <> struct AParam<0> { typedef APlain type; };
 template <> struct AParam<1> { typedef AConv type; };
 template <> struct AParam<2> { typedef AConvP type; };
+template <> struct AParam<3> { typedef AHalo type; };
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

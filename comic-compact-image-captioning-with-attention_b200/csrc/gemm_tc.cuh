@@ -215,7 +215,13 @@ struct RowEntry {
 // the leader and collect (remote) arrivals of both CTAs; empty / tmem_full exist in both CTAs and
 // are signalled by the leader's multicast tcgen05.commit.  Operand layouts, epilogue and the UMMA
 // order per accumulator element are the same in both modes: results are bit-identical.
-template <int BN, int STAGES, bool PAIR, int NKRES = 0>
+// halo patch of the stem conv (AMODE 3): an 8 x 16 tile of outputs of the 4 x 4 stride-1 conv reads 11 x 19 input
+// pixels of 16 channels; per plane 11 * 19 * 32 bytes, hi + lo, double buffered
+constexpr int kHaloRows = 11, kHaloCols = 19;
+constexpr int kHaloPlaneBytes = ((kHaloRows * kHaloCols * 32 + 127) / 128) * 128;   // 6784
+constexpr int kHaloBytes = 2 * 2 * kHaloPlaneBytes;
+
+template <int BN, int STAGES, bool PAIR, int NKRES = 0, bool HALO = false>
 struct SmemLayout {
   static constexpr int B_TILE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // this CTA's part of one weight tile (hi or lo)
   // NKRES > 0: the whole weight panel (<= NKRES K blocks, one N tile) is loaded ONCE per CTA and stays in shared
@@ -228,7 +234,8 @@ struct SmemLayout {
   static constexpr int EPI_STRIDE = 20;                           // floats per staged row: 16 columns + 4 pad (16-byte rows,
                                                                   // conflict-free 128-bit row writes)
   static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_STRIDE * 4;   // per-warp 32 x 16 transpose buffer
-  static constexpr int TOTAL = TILES_BYTES + kLoaderGroups * ROWTAB_BYTES + BAR_BYTES + EPI_BYTES + 1024;   // + alignment slack
+  static constexpr int HALO_OFF = TILES_BYTES + kLoaderGroups * ROWTAB_BYTES + BAR_BYTES + EPI_BYTES;
+  static constexpr int TOTAL = HALO_OFF + (HALO ? kHaloBytes : 0) + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
 };
 
@@ -236,7 +243,8 @@ template <int BN, int STAGES, int AMODE, bool PAIR, int NKRES = 0>
 __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::type& a, const CUtensorMap* tm_hi,
                                                  const CUtensorMap* tm_lo, int M, int N, int K, const Epi& epi) {
   static_assert(!(PAIR && NKRES), "resident weight panel: single-CTA kernel only");
-  using L = SmemLayout<BN, STAGES, PAIR, NKRES>;
+  static_assert(AMODE != 3 || (NKRES > 0 && BN == 64), "halo loader: resident-panel stem kernel only");
+  using L = SmemLayout<BN, STAGES, PAIR, NKRES, AMODE == 3>;
   constexpr int TM = PAIR ? 2 * BM : BM;        // rows per (pair) tile
   extern __shared__ uint8_t smem_raw[];
   if (epi.stop != nullptr && *epi.stop >= epi.stop_n) return;      // uniform over the grid
@@ -256,7 +264,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   const bool leader = rank == 0;
   const int nk = (K + BK - 1) / BK;
   const int n_tiles = (N + BN - 1) / BN;
-  const int m_tiles = (M + TM - 1) / TM;
+  const int m_tiles = (M + TM - 1) / TM;          // AMODE 3: M = nimg * 112 * 112 = nimg * 98 tiles of 8 x 16 outputs
   const int total_tiles = m_tiles * n_tiles;
   const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -264,7 +272,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   // ---- one-time setup ----
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_a[s], (AMODE == 2 ? 256 : 128) * (PAIR ? 2 : 1));
+      mbar_init(&full_a[s], (AMODE >= 2 ? 256 : 128) * (PAIR ? 2 : 1));
       mbar_init(&full_b[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -319,6 +327,17 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
       mbar_wait(&tmem_full[acc], (uint32_t)((iter >> 1) & 1));
       tc_fence_after();
       const int mw = m0 + quad * 32;                           // first row of this warp
+      // AMODE 3: tile = (image, 8-row band, 16-column band) of the 112 x 112 output map; tile row r = pixel (r >> 4, r & 15)
+      const int t_img = AMODE == 3 ? tile / 98 : 0, t_rem = AMODE == 3 ? tile - t_img * 98 : 0;
+      const int t_y0 = (t_rem / 7) * 8, t_x0 = (t_rem % 7) * 16;
+      auto row_to_m = [&](int row) -> int {
+        if constexpr (AMODE == 3) {
+          const int r = quad * 32 + row;
+          return (t_img * 112 + t_y0 + (r >> 4)) * 112 + t_x0 + (r & 15);
+        } else {
+          return mw + row;
+        }
+      };
 #pragma unroll 1
       for (int c0 = half * 16; c0 < n_umma; c0 += 32) {
         uint32_t r[16];
@@ -349,7 +368,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int row = q * 8 + srow;
-            const int m = mw + row;
+            const int m = row_to_m(row);
             if (m < M) {
               float4 v = *reinterpret_cast<const float4*>(stage_buf + row * L::EPI_STRIDE + scol);
               if (epi.scale) { v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w; }
@@ -473,7 +492,69 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
     __syncwarp();
   } else {
     // =====================  A loaders (this CTA's 128 rows)  =====================
-    if constexpr (AMODE == 2) {
+    if constexpr (AMODE == 3) {
+      // Stem conv from a shared-memory halo: per tile the 11 x 19 x 16-channel input patch (hi, lo) is fetched
+      // ONCE with cp.async (the next tile's patch is in flight while this one is used); K block di (= tap row,
+      // 4 taps x 16 channels = 64 contiguous values in the patch row) of output pixel (y, x) is the 128-byte run
+      // starting at patch pixel (y + di, x), copied shared -> shared into the swizzled operand tile.
+      const int lw = warp - kFirstLoaderWarp;                 // 0..7
+      const int tg = lw * 32 + lane;                          // 0..255
+      const int c8 = lane & 7, r4 = lane >> 3;
+      uint8_t* halo_g = smem_g + L::HALO_OFF;
+      const uint32_t halo = smem + L::HALO_OFF;
+      auto fetch_halo = [&](int tile, int buf) {
+        if (tile < total_tiles) {
+          const int img = tile / 98, rem = tile - img * 98;
+          const int y0 = (rem / 7) * 8 - 1, x0 = (rem % 7) * 16 - 1;
+          // 209 pixels x 2 planes x 2 chunks of 16 bytes
+          for (int i = tg; i < kHaloRows * kHaloCols * 4; i += 256) {
+            const int plane = i & 1, ch = (i >> 1) & 1, px = i >> 2;
+            const int hr = px / kHaloCols, hc = px - hr * kHaloCols;
+            const int y = y0 + hr, x = x0 + hc;
+            const bool ok = y >= 0 && y < 112 && x >= 0 && x < 112;
+            const long long go = ok ? (((long long)img * 112 + y) * 112 + x) * 16 + ch * 8 : 0;
+            const uint32_t so = halo + (uint32_t)((buf * 2 + plane) * kHaloPlaneBytes + px * 32 + ch * 16);
+            const uint32_t nbytes = ok ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(so), "l"((plane ? a.lo : a.hi) + go), "r"(nbytes)
+                         : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      uint32_t it = 0;
+      int tcount = 0;
+      fetch_halo(first_tile, 0);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++tcount) {
+        const int buf = tcount & 1;
+        named_bar_sync(1, 256);                               // everyone is done reading buffer buf ^ 1 (previous tile)
+        fetch_halo(tile + tile_step, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's patch (own copies) has landed
+        named_bar_sync(1, 256);                               // ... and everyone else's
+        const uint8_t* hb = halo_g + (size_t)(buf * 2) * kHaloPlaneBytes;
+        for (int kt = 0; kt < nk; ++kt, ++it) {               // kt = tap row di
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          const uint32_t a_hi = smem + s * L::STAGE_BYTES;
+          mbar_wait(&empty[s], ph ^ 1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = lw * 16 + i * 4 + r4;
+            const int src = (((row >> 4) + kt) * kHaloCols + (row & 15)) * 32 + c8 * 16;
+            const uint4 vh = *reinterpret_cast<const uint4*>(hb + src);
+            const uint4 vl = *reinterpret_cast<const uint4*>(hb + kHaloPlaneBytes + src);
+            const uint32_t so = (uint32_t)row * 128u + ((uint32_t)(c8 ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + so), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w)
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + A_TILE_BYTES + so), "r"(vl.x), "r"(vl.y),
+                         "r"(vl.z), "r"(vl.w)
+                         : "memory");
+          }
+          fence_proxy_async();
+          mbar_arrive(&full_a[s]);
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if constexpr (AMODE == 2) {
       // Pre-split bf16 planes: no conversion and no register staging.  All 8 loader warps copy every K
       // block (thread: 4 rows x one 16-byte chunk = 8 channels, per plane) with cp.async straight into the
       // swizzled tiles, and up to STAGES blocks stay in flight: block `it` is retired (wait_group ->
@@ -825,6 +906,22 @@ inline cudaError_t launch_bres(const typename AParam<AMODE>::type& a, const TcWe
   int tiles = (M + BM - 1) / BM;
   int grid = tiles < num_sms ? tiles : num_sms;
   gemm_bf16x3_bres_kernel<STAGES, NKRES, AMODE><<<grid, kThreads, L::TOTAL, st>>>(a, w.tm_hi[0], w.tm_lo[0], M, N, w.K, epi);
+  return cudaGetLastError();
+}
+
+// Stem conv (AMODE 3): a: space-to-depth planes; w: the W2 panel [64, 256]; output rows M = nimg * 12544.
+inline cudaError_t launch_stem_halo(const AHalo& a, const TcWeight& w, const Epi& epi, int num_sms, cudaStream_t st) {
+  using L = SmemLayout<64, 3, false, 4, true>;
+  static_assert(L::TOTAL <= 232448, "halo stem kernel exceeds the shared memory of an SM");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_bres_kernel<3, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int tiles = a.nimg * 98;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_bf16x3_bres_kernel<3, 4, 3><<<grid, kThreads, L::TOTAL, st>>>(a, w.tm_hi[0], w.tm_lo[0], a.nimg * 12544, 64, 256, epi);
   return cudaGetLastError();
 }
 

@@ -135,8 +135,10 @@ int comic_set_precision(comic_handle_t h, int mode);
 #define COMIC_OPT_GEMM_PAIR 7                /* 1: tensor-path GEMMs / convs on CTA pairs (tcgen05 cta_group::2, 256-row
                                              * tiles, each CTA loads half of the weight tile); process-wide */
 #define COMIC_OPT_GEMM_PAIR_MIN_TILES 8      /* ... for launches with at least this many 256-row tiles (default 74) */
-#define COMIC_OPT_STEM_S2D 9                 /* 1 (default): tensor-path stem conv as a 4x4 stride-1 conv over the
-                                             * space-to-depth image stored as bf16 planes; 0: 7x7/2 gather from NHWC4 fp32 */
+#define COMIC_OPT_STEM_S2D 9                 /* tensor-path stem conv: 2 (default) = 4x4 stride-1 conv over the space-to-depth
+                                             * image stored as bf16 planes, each 8x16-pixel tile's im2col rows built from a
+                                             * shared-memory halo patch (one L2 read per input element per tile instead of
+                                             * 16); 1 = same conv, rows gathered from L2; 0 = 7x7/2 gather from NHWC4 fp32 */
 #define COMIC_OPT_GEMM_RESIDENT_B 10         /* 1 (default): convs with <= 64 output channels and K <= 512 keep their whole
                                              * weight panel in shared memory (loaded once per CTA); 0: stream it per M tile */
 int comic_set_option(comic_handle_t h, int option, int value);

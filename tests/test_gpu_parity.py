@@ -101,7 +101,14 @@ def test_encoder_chunking_batch_independent(torch_mod):
     emb5, fm5 = eng.encode(eng.to_dev(img))
     assert rel_err(fm5.cpu().numpy(), fm2.cpu().numpy()) < 5e-5
     assert rel_err(emb5.cpu().numpy(), emb2.cpu().numpy()) < 5e-5
+    # ... and the shared-memory-halo loader (default, 2) against the L2 gather (1): same products, different
+    # grouping of output pixels into 128-row MMA tiles (8 x 16 patches vs 128 consecutive pixels); measured
+    # 1.1e-5 apart, each 2.8e-5 from FFMA (scripts/dbg_stem.py)
     eng.set_option('stem_s2d', 1)
+    emb6, fm6 = eng.encode(eng.to_dev(img))
+    assert rel_err(fm6.cpu().numpy(), fm2.cpu().numpy()) < 5e-5
+    assert rel_err(emb6.cpu().numpy(), emb2.cpu().numpy()) < 5e-5
+    eng.set_option('stem_s2d', 2)
     # tensor path, activation storage: fp32 NHWC split by every consumer (default) vs pre-split bf16
     # (hi, lo) planes written by the producing conv's epilogue (option enc_planes): both feed the MMAs
     # 16-bit operand pairs and sit inside the tensor path's own error band against FFMA
