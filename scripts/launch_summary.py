@@ -58,8 +58,11 @@ def main():
             dram(d), d.get('lts__t_sectors_srcunit_tex_op_read.sum', 0.0) * 32 / 1e6))
     tr = sum(dram(d) for d in enc) * 1e6 / max(len(enc), 1)
     print('# average DRAM bytes per conv launch: %.0f over %d launches' % (tr, len(enc)))
+    att = [d for d in step if 'attn_fused' in d['name']]
+    ta = sum(dram(d) for d in att) * 1e6 / max(len(att), 1)
+    print('# average DRAM bytes per fused-attention launch: %.0f over %d launches' % (ta, len(att)))
     if len(sys.argv) > 2:
-        json.dump({'conv': tr, 'note': 'dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d conv launches '
+        json.dump({'conv': tr, 'scores': ta, 'note': 'dram__bytes_read.sum + dram__bytes_write.sum averaged over the %d conv launches '
                                        'of one 512-image step (%s)' % (len(enc), path)}, open(sys.argv[2], 'w'))
 
 
