@@ -165,7 +165,8 @@ __device__ __forceinline__ void ln_tanh_scores(const float (&kc)[CPL], const flo
 #pragma unroll
   for (int j = 0; j < KB; ++j) {
     const float ss = fmaxf(fmaf(2.0f, dot[j], skk + sqq[j]), 0.f);
-    const float rs = rsqrtf(ss * inv_R + 1e-12f);
+    float rs;      // argument >= 1e-12: never denormal, so the plain MUFU.RSQ without range fix-ups
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(ss * inv_R + 1e-12f));
     rstd2[j] = make_float2(rs, rs);
     out[j] = FAST ? 0.f : sv;
   }
@@ -188,7 +189,8 @@ __device__ __forceinline__ void ln_tanh_scores(const float (&kc)[CPL], const flo
         const float2 xa = __fadd2_rn(make_float2(ex2_approx(fminf(y01.x, 30.0f)), ex2_approx(fminf(y23.x, 30.0f))), one2);
         const float2 xb = __fadd2_rn(make_float2(ex2_approx(fminf(y01.y, 30.0f)), ex2_approx(fminf(y23.y, 30.0f))), one2);
         const float2 p = __fmul2_rn(xa, xb);
-        const float2 n = __ffma2_rn(xa, make_float2(vv.y, vv.w), __fmul2_rn(xb, make_float2(vv.x, vv.z)));
+        // (!FAST: vv is stored as (v1, v3, v0, v2) so both operand pairs are adjacent registers)
+        const float2 n = __ffma2_rn(xa, make_float2(vv.x, vv.y), __fmul2_rn(xb, make_float2(vv.z, vv.w)));
         const float rp = rcp_approx(p.x * p.y);
         out[j] = fmaf(rp, fmaf(p.x, n.y, p.y * n.x), out[j]);
       }
@@ -264,7 +266,9 @@ attn_fused_kernel(const AttnArgs a) {
         const float sc = FAST ? 1.0f : kTwoLog2e, vs = FAST ? 1.0f : -2.0f;
         *reinterpret_cast<float4*>(sm_c + (g * 32 + lane) * 4) = make_float4(g4.x * sc, g4.y * sc, g4.z * sc, g4.w * sc);
         *reinterpret_cast<float4*>(sm_c + R + (g * 32 + lane) * 4) = make_float4(b4.x * sc, b4.y * sc, b4.z * sc, b4.w * sc);
-        *reinterpret_cast<float4*>(sm_c + 2 * R + (g * 32 + lane) * 4) = make_float4(v4.x * vs, v4.y * vs, v4.z * vs, v4.w * vs);
+        // exact-tanh path: pair order (v1, v3 | v0, v2) as consumed by the shared-reciprocal numerators
+        *reinterpret_cast<float4*>(sm_c + 2 * R + (g * 32 + lane) * 4) =
+            FAST ? make_float4(v4.x * vs, v4.y * vs, v4.z * vs, v4.w * vs) : make_float4(v4.y * vs, v4.w * vs, v4.x * vs, v4.z * vs);
       }
     }
 #pragma unroll

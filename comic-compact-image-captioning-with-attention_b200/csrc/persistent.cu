@@ -228,8 +228,9 @@ decode_loop_kernel(const PersistArgs a) {
             make_float4(g4.x * kTwoLog2e, g4.y * kTwoLog2e, g4.z * kTwoLog2e, g4.w * kTwoLog2e);
         *reinterpret_cast<float4*>(sm_c + R + (g * 32 + lane) * 4) =
             make_float4(b4.x * kTwoLog2e, b4.y * kTwoLog2e, b4.z * kTwoLog2e, b4.w * kTwoLog2e);
+        // pair order (v1, v3 | v0, v2): the layout ln_tanh_scores<.., FAST = false> consumes (attention.cuh)
         *reinterpret_cast<float4*>(sm_c + 2 * R + (g * 32 + lane) * 4) =
-            make_float4(v4.x * -2.0f, v4.y * -2.0f, v4.z * -2.0f, v4.w * -2.0f);
+            make_float4(v4.y * -2.0f, v4.w * -2.0f, v4.x * -2.0f, v4.z * -2.0f);
       }
     }
 #pragma unroll
