@@ -19,6 +19,7 @@ per step; the GPU does the sampling (greedy + beam search) and the training step
 """
 from __future__ import annotations
 
+import functools
 import math
 import pickle
 from collections import Counter, defaultdict
@@ -110,8 +111,11 @@ def captions_to_batched_ids(hypos, config, radix_wtoi=None):
 # ---------------------------------------------------------------------------
 # n-gram statistics
 # ---------------------------------------------------------------------------
+@functools.lru_cache(maxsize=65536)
 def ngram_counts(sentence, n=4):
-    """`precook`: Counter of all 1..n-grams (as tuples) of a whitespace-tokenised string."""
+    """`precook`: Counter of all 1..n-grams (as tuples) of a whitespace-tokenised string.  Memoised (the
+    result is treated as read-only): CIDEr-D and BLEU cook the same hypothesis, and the training set's
+    reference captions come back every epoch."""
     words = sentence.split()
     counts = Counter()
     for k in range(1, n + 1):
@@ -172,7 +176,13 @@ class CiderD(object):
         """gts: {id: [ref strings]}, res: {id: [hypothesis string]} -> (mean, scores in id order of gts)."""
         assert sorted(gts.keys()) == sorted(res.keys())
         ids = list(gts.keys())
-        crefs = [[ngram_counts(r, self.n)[1] for r in gts[i]] for i in ids]
+        # the SCST loop scores k sampled captions + 1 greedy caption per image against the SAME reference list
+        # object (CaptionScorer.get_hypo_scores): cook / weight each distinct list once (same arithmetic)
+        cooked = {}
+        for i in ids:
+            if id(gts[i]) not in cooked:
+                cooked[id(gts[i])] = [ngram_counts(r, self.n)[1] for r in gts[i]]
+        crefs = [cooked[id(gts[i])] for i in ids]
         ctest = [ngram_counts(res[i][0], self.n)[1] for i in ids]
         if self.df_mode == 'corpus' and not isinstance(self.df_mode, dict):
             dfreq = defaultdict(float)
@@ -183,18 +193,22 @@ class CiderD(object):
         else:
             dfreq, ref_len = self.document_frequency, self.ref_len
         scores = []
+        ref_vecs = {}
         for test, refs in zip(ctest, crefs):
             vec, norm, length = self._vec(test, dfreq, ref_len)
             score = np.zeros(self.n)
-            for ref in refs:
-                vr, nr, lr = self._vec(ref, dfreq, ref_len)
+            if id(refs) not in ref_vecs:
+                ref_vecs[id(refs)] = [self._vec(ref, dfreq, ref_len) for ref in refs]
+            for vr, nr, lr in ref_vecs[id(refs)]:
                 delta = float(length - lr)
                 pen = math.e ** (-(delta ** 2) / (2 * self.sigma ** 2))
                 for k in range(self.n):
                     v = 0.0
                     rk = vr[k]
                     for g, w in vec[k].items():
-                        wr = rk.get(g, 0.0)
+                        wr = rk.get(g)
+                        if wr is None:
+                            continue            # min(w, 0.0) * 0.0 adds a (signed) zero: v is unchanged
                         v += min(w, wr) * wr
                     if norm[k] != 0 and nr[k] != 0:
                         v /= (norm[k] * nr[k])
@@ -211,16 +225,20 @@ def bleu_closest(gts, res, n=4):
     bleu_list = [[] for _ in range(n)]
     tot_test, tot_ref = 0, 0
     tot_guess, tot_correct = [0] * n, [0] * n
+    ref_stats = {}                                      # per distinct reference list (see CiderD.compute_score)
     for i in gts:
         hypo, refs = res[i], gts[i]
         assert isinstance(hypo, list) and len(hypo) == 1 and isinstance(refs, list) and len(refs) >= 1
-        reflens, maxcounts = [], {}
-        for r in refs:
-            rl, cnt = ngram_counts(r, n)
-            reflens.append(rl)
-            for g, ct in cnt.items():
-                if ct > maxcounts.get(g, 0):
-                    maxcounts[g] = ct
+        if id(refs) not in ref_stats:
+            reflens, maxcounts = [], {}
+            for r in refs:
+                rl, cnt = ngram_counts(r, n)
+                reflens.append(rl)
+                for g, ct in cnt.items():
+                    if ct > maxcounts.get(g, 0):
+                        maxcounts[g] = ct
+            ref_stats[id(refs)] = (reflens, maxcounts)
+        reflens, maxcounts = ref_stats[id(refs)]
         testlen, counts = ngram_counts(hypo[0], n)
         reflen = min((abs(l - testlen), l) for l in reflens)[1]
         guess = [max(0, testlen - k + 1) for k in range(1, n + 1)]
