@@ -222,13 +222,49 @@ xent_kernel(const float* __restrict__ lq, int ld, int V, const int* __restrict__
 // ds = alpha (dalpha - <alpha, dalpha>)  (softmax), dT += -1/T sum ds log alpha.
 // Also dvalues[b, m, c] += alpha~[h(c), m] dctx[c]   (tied: the keys' gradient).
 // ---------------------------------------------------------------------------
+// Part 1a, parallel over position slices (grid: image x slice): dalpha~[n, h, m] = sum_{c in h} dctx[c] V[m, c]
+// into `dal_out` [N, H, M] and dV[b, m, c] += alpha~[h(c), m] dctx[c].  One CTA per image left 3/4 of the SMs idle
+// at batch 32 (257 us per step = 47 % of the training step, profiles/r02c); every (image, position) is still
+// owned by exactly one warp, so the accumulation into dV stays deterministic.
+__global__ void __launch_bounds__(256)
+attn_bwd_dalpha_kernel(const float* __restrict__ values, int VAL, const float* __restrict__ dctx, int ld_dctx,
+                       const int* __restrict__ lens, int t, const float* __restrict__ a_post,
+                       float* __restrict__ dvalues, float* __restrict__ dal_out, int k, int H, int M, int S) {
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int dv = VAL / H;
+  const int per = (M + S - 1) / S;
+  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
+  for (int beam = 0; beam < k; ++beam) {
+    const int n = b * k + beam;
+    const bool fin = lens && t >= lens[n];
+    const float* dc = dctx + (size_t)n * ld_dctx;
+    const float* ap = a_post + (size_t)n * H * M;
+    for (int m = m0 + warp; m < m1; m += 8) {
+      const float* vr = values + ((size_t)b * M + m) * VAL;
+      float* dvr = dvalues ? dvalues + ((size_t)b * M + m) * VAL : nullptr;
+      for (int hh = 0; hh < H; ++hh) {
+        float acc = 0.f;
+        const float al = ap[(size_t)hh * M + m];
+        for (int c = hh * dv + lane; c < (hh + 1) * dv; c += 32) {
+          float g = fin ? 0.f : dc[c];
+          acc = fmaf(g, vr[c], acc);
+          if (dvr && !fin) dvr[c] += al * g;
+        }
+        acc = wred_sum(acc);
+        if (lane == 0) dal_out[((size_t)n * H + hh) * M + m] = acc;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 attn_bwd_score_kernel(const float* __restrict__ values, int VAL, const float* __restrict__ dctx, int ld_dctx,
                       const int* __restrict__ lens, int t, const float* __restrict__ a_post,
                       const float* __restrict__ a_pre, const float* __restrict__ att_mask, float att_keep,
                       float map_coef, float* __restrict__ dvalues, float* __restrict__ ds_out,
                       float* __restrict__ dT_acc, float* __restrict__ map_rows, const float* __restrict__ temperature,
-                      int k, int H, int M) {
+                      int k, int H, int M, const float* dal_in) {
   extern __shared__ float sm[];            // dal [H][M]
   __shared__ float red[8];
   const int b = blockIdx.x;
@@ -239,7 +275,11 @@ attn_bwd_score_kernel(const float* __restrict__ values, int VAL, const float* __
     const bool fin = lens && t >= lens[n];   // imputed step: the cell's context output is discarded
     const float* dc = dctx + (size_t)n * ld_dctx;
     const float* ap = a_post + (size_t)n * H * M;
-    // dalpha~[h, m] = sum_{c in h} dctx[c] V[m, c]; dV += alpha~ dctx
+    // dalpha~[h, m] = sum_{c in h} dctx[c] V[m, c]; dV += alpha~ dctx  (or precomputed by attn_bwd_dalpha_kernel;
+    // dal_in may alias ds_out: it is copied to shared memory before anything is written)
+    if (dal_in) {
+      for (int i = tid; i < H * M; i += 256) sm[i] = dal_in[(size_t)n * H * M + i];
+    } else
     for (int m = warp; m < M; m += 8) {
       const float* vr = values + ((size_t)b * M + m) * VAL;
       float* dvr = dvalues ? dvalues + ((size_t)b * M + m) * VAL : nullptr;
@@ -798,10 +838,16 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
   // ---- reverse sweep ----
   for (int t = T_run - 1; t >= 0; --t) {
     float* dlq_t = tb.dlq + (size_t)t * B * LQ;
+    {
+      dim3 g1(B, tb.S);
+      attn_bwd_dalpha_kernel<<<g1, 256, 0, st>>>(values, VAL, tb.gCtx, A, lens, t, tb.apost + (size_t)t * B * HM, dvals_dst,
+                                                tb.ds, 1, h->H, M, tb.S);
+      h->launches++;
+    }
     attn_bwd_score_kernel<<<B, 256, (size_t)HM * sizeof(float), st>>>(
         values, VAL, tb.gCtx, A, lens, t, tb.apost + (size_t)t * B * HM, tb.apre + (size_t)t * B * HM,
-        mk.att ? mk.att + (size_t)t * B * HM : nullptr, att_keep, map_coef, dvals_dst, tb.ds, tb.dTacc,
-        tb.maprows + (size_t)t * B, h->w.temperature, 1, h->H, M);
+        mk.att ? mk.att + (size_t)t * B * HM : nullptr, att_keep, map_coef, nullptr, tb.ds, tb.dTacc,
+        tb.maprows + (size_t)t * B, h->w.temperature, 1, h->H, M, tb.ds);
     dim3 g2(B, tb.S);
     const float* lq_t = tb.lq + (size_t)t * B * LQ;
     if (R == 512)
