@@ -86,13 +86,25 @@ relu_bn_bwd_kernel(const float* __restrict__ dy, int ld_dy, int coff_dy, const f
   if (rl == 0 && c < n) bpart[(size_t)blockIdx.x * n + c] = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
 }
 
-// out[c] = sum_chunks part[chunk, c] (fixed order)
-__global__ void chunk_sum_kernel(const float* __restrict__ part, int chunks, int n, float* __restrict__ out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+// out[c] = sum_chunks part[chunk, c]: 32 columns x 8 chunk lanes per CTA (coalesced 128-byte rows), each lane a
+// strided partial sum, then a fixed-order sum of the 8 lanes -> deterministic, ~chunks/8 dependent loads per thread
+// instead of `chunks` (592 sequential loads per column took 31 us x 57 launches, profiles/r02f).
+__global__ void __launch_bounds__(256)
+chunk_sum_kernel(const float* __restrict__ part, int chunks, int n, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int i = 0; i < chunks; ++i) s += part[(size_t)i * n + c];
-  out[c] = s;
+  if (c < n)
+    for (int i = rl; i < chunks; i += 8) s += part[(size_t)i * n + c];
+  red[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && c < n) {
+    float t = red[0][cl];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) t += red[j][cl];
+    out[c] = t;
+  }
 }
 
 // W [k, k, ci, co] (HWIO) -> Wf [k, k, co, ci] with both spatial axes reversed: the dgrad of a
@@ -180,6 +192,76 @@ wgrad_kernel(AConv a, const float* __restrict__ dz, int ld_dz, int M, int N, int
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int k = k0 + ty * 4 + i;
+    const int n = n0 + tx * 4;
+    if (k < K && n < N)
+      *reinterpret_cast<float4*>(dst + (size_t)k * N + n) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+}
+
+// Same contraction with a 128 (k) x 64 (n) output tile, 8 x 4 per thread: 3 shared-memory vector loads per 32 FMAs
+// instead of 2 per 16 (the 64 x 64 kernel is shared-memory-load bound: 21 TFLOP/s on Conv2d_2c, profiles/r02f).
+template <int VEC>
+__global__ void __launch_bounds__(256, 2)
+wgrad128_kernel(AConv a, const float* __restrict__ dz, int ld_dz, int M, int N, int K, int m_per_split,
+                float* __restrict__ part) {
+  constexpr int BMK = 16;
+  __shared__ __align__(16) float As[2][BMK][128];
+  __shared__ __align__(16) float Bs[2][BMK][64];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 128;
+  const int mbeg = blockIdx.z * m_per_split;
+  const int mend = min(M, mbeg + m_per_split);
+  const int mm = tid >> 4, q = tid & 15;          // loads: row mm of the stage; A k-quads q and q + 16, B n-quad q
+  const int tx = tid & 15, ty = tid >> 4;         // outputs: k rows ty*4.. and 64 + ty*4.., n cols tx*4..
+  float4 ra0, ra1, rb;
+  auto gload = [&](int m0) {
+    const int m = m0 + mm;
+    RowCtx<1> rc;
+    make_row<1>(a, m, mend, rc);
+    ra0 = load_a4<1, VEC>(a, rc, k0 + q * 4, K);
+    ra1 = load_a4<1, VEC>(a, rc, k0 + 64 + q * 4, K);
+    const int n = n0 + q * 4;
+    rb = (m < mend && n < N) ? ldg4(dz + (size_t)m * ld_dz + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto sstore = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][mm][q * 4]) = ra0;
+    *reinterpret_cast<float4*>(&As[buf][mm][64 + q * 4]) = ra1;
+    *reinterpret_cast<float4*>(&Bs[buf][mm][q * 4]) = rb;
+  };
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  int buf = 0;
+  if (mbeg < mend) {
+    gload(mbeg);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int m0 = mbeg; m0 < mend; m0 += BMK) {
+    const bool more = m0 + BMK < mend;
+    if (more) gload(m0 + BMK);
+#pragma unroll
+    for (int r = 0; r < BMK; ++r) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][r][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][r][64 + ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][r][tx * 4]);
+      const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a8[i], b4[j], acc[i][j]);
+    }
+    if (more) sstore(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  float* dst = part + (size_t)blockIdx.z * K * N;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     const int n = n0 + tx * 4;
     if (k < K && n < N)
       *reinterpret_cast<float4*>(dst + (size_t)k * N + n) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -299,7 +381,7 @@ static int relu_bn_bwd(comic_handle_t h, const float* dy, int ld_dy, int coff_dy
   dim3 g(chunks, (n + 63) / 64);
   relu_bn_bwd_kernel<<<g, 256, 0, st>>>(dy, ld_dy, coff_dy, y, ld_y, coff_y, h->pk.bn_scale[ci], dz, ld_dz, coff_dz, M, n,
                                        rpc, bb.bpart);
-  chunk_sum_kernel<<<(n + 127) / 128, 128, 0, st>>>(bb.bpart, chunks, n, dbeta);
+  chunk_sum_kernel<<<(n + 31) / 32, 256, 0, st>>>(bb.bpart, chunks, n, dbeta);
   h->launches += 2;
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;
@@ -313,7 +395,9 @@ static int wgrad(comic_handle_t h, const float* x, int B, int H, int W, int ldx,
   same_pads(H, k, stride, &a.Ho, &a.pad_t);
   same_pads(W, k, stride, &a.Wo, &a.pad_l);
   const int M = B * a.Ho * a.Wo, K = k * k * cin;
-  const int tiles = ((K + 63) / 64) * ((N + 63) / 64);
+  const bool big = K >= 256;                       // 128-row tiles (<= 20 % padding from K = 256 on)
+  const int kt = big ? 128 : 64;
+  const int tiles = ((K + kt - 1) / kt) * ((N + 63) / 64);
   int nz = (4 * h->num_sms + tiles - 1) / tiles;
   int cap = (int)(kWPartFloats / ((size_t)K * N));
   if (nz > cap) nz = cap;
@@ -322,10 +406,16 @@ static int wgrad(comic_handle_t h, const float* x, int B, int H, int W, int ldx,
   int mps = (M + nz - 1) / nz;
   mps = (mps + 15) / 16 * 16;
   nz = (M + mps - 1) / mps;
-  dim3 g((N + 63) / 64, (K + 63) / 64, nz);
+  dim3 g((N + 63) / 64, (K + kt - 1) / kt, nz);
   float* dst = nz == 1 ? dW : bb.wpart;
-  if (cin % 4 == 0 && ldx % 4 == 0) wgrad_kernel<4><<<g, 256, 0, st>>>(a, dz, ld_dz, M, N, K, mps, dst);
-  else wgrad_kernel<1><<<g, 256, 0, st>>>(a, dz, ld_dz, M, N, K, mps, dst);
+  const bool vec = cin % 4 == 0 && ldx % 4 == 0;
+  if (big) {
+    if (vec) wgrad128_kernel<4><<<g, 256, 0, st>>>(a, dz, ld_dz, M, N, K, mps, dst);
+    else wgrad128_kernel<1><<<g, 256, 0, st>>>(a, dz, ld_dz, M, N, K, mps, dst);
+  } else {
+    if (vec) wgrad_kernel<4><<<g, 256, 0, st>>>(a, dz, ld_dz, M, N, K, mps, dst);
+    else wgrad_kernel<1><<<g, 256, 0, st>>>(a, dz, ld_dz, M, N, K, mps, dst);
+  }
   h->launches++;
   if (nz > 1) {
     size_t n = (size_t)K * N;
