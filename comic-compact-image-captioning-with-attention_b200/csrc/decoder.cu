@@ -269,19 +269,23 @@ attn_scores_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
 // D4 (probability fn) + D5 + D6: softmax / signorm over the M positions of each
 // (beam, head), optional attention-map dropout, alignment-history write and
 // context ctx[n, c] = sum_m alpha[n, head(c), m] * values[b, m, c].
-// Grid (B, ceil(VAL/128)); thread = value channel; CTA y==0 writes the history.
+// Grid (B, ceil(VAL/128)); 512 threads = 128 value channels x 4 position slices (fixed-order sum of the four
+// partials, deterministic): a single thread walking all M positions of its channel left the kernel latency-bound at
+// small batches (42 us at 32 images, profiles/r02e).  CTA y==0 writes the history.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int kCtxSlices = 4;
+__global__ void __launch_bounds__(128 * kCtxSlices)
 attn_ctx_kernel(const float* __restrict__ scores, const float* __restrict__ values, int VAL,
                 float* __restrict__ ctx_out, int ld_ctx, float* __restrict__ hist_t,
                 const float* __restrict__ att_mask, float att_keep, int k, int H, int M, int prob_fn,
                 const int* fin_count, int t, int n_rows, float* __restrict__ hist_pre) {
   if (step_stopped(fin_count, t, n_rows)) return;
-  extern __shared__ __align__(16) float sm_alpha[];   // [k][H][M]
+  extern __shared__ __align__(16) float sm_alpha[];   // [k][H][M] | partial contexts [kCtxSlices][4][128]
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int npair = k * H;
-  for (int pr = warp; pr < npair; pr += 4) {
+  float* sm_part = sm_alpha + (((size_t)npair * M + 3) & ~(size_t)3);
+  for (int pr = warp; pr < npair; pr += 4 * kCtxSlices) {
     const float* s = scores + ((size_t)b * npair + pr) * M;
     float* a = sm_alpha + (size_t)pr * M;
     float sum = 0.f;
@@ -312,22 +316,38 @@ attn_ctx_kernel(const float* __restrict__ scores, const float* __restrict__ valu
     }
   }
   __syncthreads();
-  const int c = blockIdx.y * 128 + threadIdx.x;
-  if (c >= VAL) return;
-  const int hd = c / (VAL / H);
-  const float* vb = values + (size_t)b * M * VAL + c;
+  const int cl = threadIdx.x & 127, sl = threadIdx.x >> 7;
+  const int c = blockIdx.y * 128 + cl;
+  const bool live = c < VAL;
+  const int hd = live ? c / (VAL / H) : 0;
+  const float* vb = values + (size_t)b * M * VAL + (live ? c : 0);
+  const int per = (M + kCtxSlices - 1) / kCtxSlices;
+  const int m0 = sl * per, m1 = min(M, m0 + per);
   for (int beam0 = 0; beam0 < k; beam0 += 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const int nb = min(4, k - beam0);
     const float* a0 = sm_alpha + ((size_t)(beam0)*H + hd) * M;
+    if (live) {
 #pragma unroll 4
-    for (int m = 0; m < M; ++m) {
-      float v = __ldg(vb + (size_t)m * VAL);
+      for (int m = m0; m < m1; ++m) {
+        float v = __ldg(vb + (size_t)m * VAL);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < nb) acc[j] = fmaf(a0[(size_t)j * H * M + m], v, acc[j]);
+        for (int j = 0; j < 4; ++j)
+          if (j < nb) acc[j] = fmaf(a0[(size_t)j * H * M + m], v, acc[j]);
+      }
     }
-    for (int j = 0; j < nb; ++j) ctx_out[(size_t)(b * k + beam0 + j) * ld_ctx + c] = acc[j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sm_part[(sl * 4 + j) * 128 + cl] = acc[j];
+    __syncthreads();
+    if (sl == 0 && live) {
+      for (int j = 0; j < nb; ++j) {
+        float tot = sm_part[(0 * 4 + j) * 128 + cl];
+#pragma unroll
+        for (int q = 1; q < kCtxSlices; ++q) tot += sm_part[(q * 4 + j) * 128 + cl];
+        ctx_out[(size_t)(b * k + beam0 + j) * ld_ctx + c] = tot;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -539,7 +559,9 @@ int decoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
 // Step driver shared by decode_step / greedy / beam.
 // ---------------------------------------------------------------------------
 static size_t step_smem_scores(int k, int R) { return (size_t)k * R * sizeof(float); }
-static size_t step_smem_ctx(int k, int H, int M) { return (size_t)k * H * M * sizeof(float); }
+static size_t step_smem_ctx(int k, int H, int M) {
+  return ((((size_t)k * H * M + 3) & ~(size_t)3) + (size_t)kCtxSlices * 4 * 128) * sizeof(float);
+}
 
 template <int R, int H>
 static cudaError_t launch_scores(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k,
@@ -767,7 +789,7 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
       dim3 grid(B, (VAL + 127) / 128);
       size_t smem = step_smem_ctx(k, h->H, h->M);
       Prof pf(h, T_CTX, st);
-      attn_ctx_kernel<<<grid, 128, smem, st>>>(sb.scores, io.values, VAL, ctx_dst, ld_ctx, io.hist_t, io.att_mask,
+      attn_ctx_kernel<<<grid, 128 * kCtxSlices, smem, st>>>(sb.scores, io.values, VAL, ctx_dst, ld_ctx, io.hist_t, io.att_mask,
                                               io.att_keep, k, h->H, h->M, h->cfg.prob_fn, io.fin_count, io.t,
                                               io.n_rows, io.alpha_pre);
     }
