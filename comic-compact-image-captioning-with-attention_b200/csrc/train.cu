@@ -381,12 +381,21 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
     const float* qp = lq + (size_t)n * ld_lq + q_off + c0;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) { q[c] = qp[c]; dq_a[c] = 0.f; }
+    const bool one_head = (D % CPL) == 0;          // a lane's CPL contiguous channels lie in one head
     for (int m = m_lo + warp; m < m_hi; m += 4) {
       const float* kr = keys + ((size_t)b * M + m) * R + c0;
       float u[CPL];
       float s = 0.f;
+      // 128-bit accesses: a lane's slice is 4*CPL contiguous, 16-byte aligned bytes (scalar loads touched every
+      // 32-byte sector of the row CPL times)
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) { u[c] = kr[c] + q[c]; s += u[c]; }
+      for (int c4 = 0; c4 < CPL / 4; ++c4) {
+        const float4 kv = ldg4(kr + c4 * 4);
+        u[c4 * 4 + 0] = kv.x + q[c4 * 4 + 0]; u[c4 * 4 + 1] = kv.y + q[c4 * 4 + 1];
+        u[c4 * 4 + 2] = kv.z + q[c4 * 4 + 2]; u[c4 * 4 + 3] = kv.w + q[c4 * 4 + 3];
+      }
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) s += u[c];
       const float mean = wred_sum(s) * (1.0f / R);
       float ss = 0.f;
 #pragma unroll
@@ -394,11 +403,12 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
       const float rstd = 1.0f / sqrtf(wred_sum(ss) * (1.0f / R) + 1e-12f);
       float du[CPL];
       float s1 = 0.f, s2 = 0.f;
+      const float dz_lane = one_head ? ds[((size_t)n * H + c0 / D) * M + m] * invT : 0.f;
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
         const float uh = u[c] * rstd;                      // normalised
         const float th = tanhf(fmaf(uh, gm[c], bt[c]));
-        const float dz = ds[((size_t)n * H + (c0 + c) / D) * M + m] * invT;
+        const float dz = one_head ? dz_lane : ds[((size_t)n * H + (c0 + c) / D) * M + m] * invT;
         dv_a[c] = fmaf(dz, th, dv_a[c]);
         const float dy = dz * vv[c] * (1.0f - th * th);
         dg_a[c] = fmaf(dy, uh, dg_a[c]);
@@ -413,10 +423,17 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
       s2 = wred_sum(s2) * (1.0f / R);
       float* dkr = dkeys + ((size_t)b * M + m) * R + c0;
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        const float g = rstd * (du[c] - s1 - u[c] * s2);
-        dkr[c] += g;
-        dq_a[c] += g;
+      for (int c4 = 0; c4 < CPL / 4; ++c4) {
+        float4 acc = *reinterpret_cast<const float4*>(dkr + c4 * 4);
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c4 * 4 + j;
+          g[j] = rstd * (du[c] - s1 - u[c] * s2);
+          dq_a[c] += g[j];
+        }
+        acc.x += g[0]; acc.y += g[1]; acc.z += g[2]; acc.w += g[3];
+        *reinterpret_cast<float4*>(dkr + c4 * 4) = acc;
       }
     }
     // dq partial of this (row, slice): fixed-order sum over the 4 warps
