@@ -82,14 +82,25 @@ __global__ void transpose_kernel(const float* __restrict__ src, int rows, int co
   }
 }
 
-// out[c] (+)= sum_r src[r, c]; one thread per column, fixed row order.
-__global__ void colsum_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ out,
-                              int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// out[c] (+)= sum_r src[r, c]; 32 columns x 8 row lanes per CTA (launch with 256 threads, grid = ceil(cols / 32)):
+// each lane a strided partial, then a fixed-order sum of the 8 lanes (deterministic).  One thread walking all
+// T*B rows of its column took 45 us per call (profiles/r02j).
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ src, int rows, int cols, int ld, float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int r = 0; r < rows; ++r) s += src[(size_t)r * ld + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < cols)
+    for (int r = rl; r < rows; r += 8) s += src[(size_t)r * ld + c];
+  red[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+    float t = red[0][cl];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) t += red[j][cl];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 __global__ void copy2d_kernel(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,
@@ -921,20 +932,20 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
   transpose(tb.xh, rows, KX, KX, tb.xhT, rows_pad, st);
   if ((rc = train_gemm(h, tb.xhT, rows_pad, tb.dG, 4 * R, grads->lstm_kernel, 4 * R, KX, 4 * R, rows_pad, tb.part,
                        tb.part_floats, st))) return rc;
-  colsum_kernel<<<(4 * R + 127) / 128, 128, 0, st>>>(tb.dG, rows, 4 * R, 4 * R, grads->lstm_bias, 0);
+  colsum_kernel<<<(4 * R + 31) / 32, 256, 0, st>>>(tb.dG, rows, 4 * R, 4 * R, grads->lstm_bias, 0);
   // d[W_o | W_q] = Hout^T . dLQ
   COMIC_CHECK_CUDA(cudaMemsetAsync(tb.hdT, 0, (size_t)R * rows_pad * sizeof(float), st));
   transpose(tb.hdrop, rows_t, R, R, tb.hdT, rows_pad, st);
   if ((rc = train_gemm(h, tb.hdT, rows_pad, tb.dlq, LQ, tb.dOutQ, LQ, R, LQ, rows_pad, tb.part, tb.part_floats, st))) return rc;
   copy2d_kernel<<<(unsigned)(((size_t)R * V + 255) / 256), 256, 0, st>>>(tb.dOutQ, LQ, grads->out_kernel, V, R, V);
   copy2d_kernel<<<(unsigned)(((size_t)R * R + 255) / 256), 256, 0, st>>>(tb.dOutQ + h->Vp, LQ, grads->query_kernel, R, R, R);
-  colsum_kernel<<<(V + 127) / 128, 128, 0, st>>>(tb.dlq, rows_t, V, LQ, grads->out_bias, 0);
+  colsum_kernel<<<(V + 31) / 32, 256, 0, st>>>(tb.dlq, rows_t, V, LQ, grads->out_bias, 0);
   // embedding
   embed_grad_kernel<<<V, 256, 0, st>>>(inputs_tm, tb.demb, rows_t, W, V, grads->embedding_map);
   // attention constants: column sums of the per-(image, slice) partials
-  colsum_kernel<<<(R + 127) / 128, 128, 0, st>>>(tb.cpart, B * tb.S, R, 3 * R, grads->attention_v, 0);
-  colsum_kernel<<<(R + 127) / 128, 128, 0, st>>>(tb.cpart + R, B * tb.S, R, 3 * R, grads->ln_gamma, 0);
-  colsum_kernel<<<(R + 127) / 128, 128, 0, st>>>(tb.cpart + 2 * R, B * tb.S, R, 3 * R, grads->ln_beta, 0);
+  colsum_kernel<<<(R + 31) / 32, 256, 0, st>>>(tb.cpart, B * tb.S, R, 3 * R, grads->attention_v, 0);
+  colsum_kernel<<<(R + 31) / 32, 256, 0, st>>>(tb.cpart + R, B * tb.S, R, 3 * R, grads->ln_gamma, 0);
+  colsum_kernel<<<(R + 31) / 32, 256, 0, st>>>(tb.cpart + 2 * R, B * tb.S, R, 3 * R, grads->ln_beta, 0);
   scalar_sum_kernel<<<1, 32, 0, st>>>(tb.dTacc, B, 1.0f, grads->temperature);
   h->launches += 11;
   // dW_k = F^T . dKeys  (tied: dKeys also holds the value-path gradient)
