@@ -258,6 +258,7 @@ def run_ours(args):
         raise SystemExit('bench.py: no CUDA device; the hot path has no CPU fallback')
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'     # NCCL_DEBUG=VERSION would put "NCCL version ..." on stdout before the JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     def barrier():
