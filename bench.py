@@ -258,7 +258,8 @@ def run_ours(args):
         raise SystemExit('bench.py: no CUDA device; the hot path has no CPU fallback')
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'     # NCCL_DEBUG=VERSION would put "NCCL version ..." on stdout before the JSON line
+        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION / WARN: keep stdout to the one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     def barrier():
