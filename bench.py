@@ -259,7 +259,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION / WARN: keep stdout to the one JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
     def barrier():

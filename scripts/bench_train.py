@@ -40,7 +40,8 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # NCCL's version banner off stdout: one JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG')      # those levels print a version banner on stdout: keep it to the one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     c = conf.make_config(train_mode=args.mode, batch_size_train=args.batch, max_step=100000)
     W = wts.init_weights(c, seed=c.rand_seed, cnn_init='he')
