@@ -143,6 +143,7 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
     case COMIC_OPT_PERSISTENT_TRACE: h->persist_trace = value; return COMIC_OK;
     case COMIC_OPT_ENC_PLANES: h->enc_planes = value; return COMIC_OK;
     case COMIC_OPT_STEM_S2D: h->stem_s2d = value; return COMIC_OK;
+    case COMIC_OPT_TC_MIN_ROWS: h->tc_min_rows = value; return COMIC_OK;
     case COMIC_OPT_GEMM_RESIDENT_B: tc::bres_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR: tc::pair_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR_MIN_TILES: tc::pair_min_tiles() = value; return COMIC_OK;

@@ -75,6 +75,8 @@ struct comic_handle_s {
   long long* last_trace = nullptr;
   int last_trace_steps = 0;
   int persist_max_rows = 32;   // whole decode loop as one cooperative kernel up to this many rows (0 = off)
+  int tc_min_rows = 64;        // GEMMs / convs with at least this many rows take the tensor path (precision >= 1); half-empty
+                               // M tiles still beat the FFMA kernel (batch 25-32 beam-3: gate GEMM 37 -> 29 us, r02p)
   int stem_s2d = 2;            // tensor path stem conv: 2 = space-to-depth planes, im2col tile built from a shared-memory
                                // halo patch; 1 = same conv, operand rows gathered from L2 with cp.async; 0 = 7x7/2 gather
                                // from the fp32 NHWC4 image
@@ -133,7 +135,7 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Carve + (unless dry) fill one tensor-path weight pack from W[K][N] (row stride ldw).
 int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, int ldw, int cin_src, int cin_dst,
                    tc::TcWeight& out, cudaStream_t st, bool dry);
-inline bool use_tc(comic_handle_t h, const tc::TcWeight& w, int M) { return h->precision >= 1 && w.ready && M >= 128; }
+inline bool use_tc(comic_handle_t h, const tc::TcWeight& w, int M) { return h->precision >= 1 && w.ready && M >= h->tc_min_rows; }
 
 // encoder.cu
 int encoder_workspace_bytes(comic_handle_t h, int B, size_t* bytes);
