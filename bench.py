@@ -250,6 +250,7 @@ def run_ours(args):
     from comic_b200 import weights as wts
     from comic_b200.engine import Engine, KERNEL_TAGS
     from comic_b200.model import CaptionModel
+    from comic_b200 import parallel as par
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -257,6 +258,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the hot path has no CPU fallback')
     torch.cuda.set_device(local)
+    # N > 1: every rank streams 0.5 GB per batch through pinned host memory; keep each rank (and the pinned buffers it
+    # is about to allocate) on the CPUs next to its GPU.  N = 1 keeps all host cores (cpu_baseline uses them).
+    numa_cpus = set()
+    if world > 1 and os.environ.get('COMIC_B200_NUMA_BIND', '1') != '0':
+        numa_cpus = par.bind_to_gpu_numa(local)
     if world > 1:
         # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION / WARN: keep stdout to the one JSON line
         if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
@@ -398,7 +404,8 @@ def run_ours(args):
             'e2e': {'value': caps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps,
                     'api': 'CaptionModel.run_stream (H2D / compute / D2H pipelined over 3 streams)',
-                    'serial_run_ms_per_step': e2e_serial_s * 1e3 / args.steps},
+                    'serial_run_ms_per_step': e2e_serial_s * 1e3 / args.steps,
+                    'host_cpus_bound': len(numa_cpus) or None},
             'gpu_launches': int(launches),
             'clocks': sampler.summary(),
             'kernel_ms_per_step': {t: round(table[t][0], 3) for t in KERNEL_TAGS if table[t][1]},

@@ -46,3 +46,39 @@ def gather_objects(obj):
     out = [None] * ws
     dist.all_gather_object(out, obj)
     return out
+
+
+def gpu_local_cpus(device_index):
+    """CPUs of the NUMA node the GPU hangs off (NVML's ideal CPU affinity), restricted to the
+    CPUs this process may use; empty set when NVML cannot tell."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        h = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(os.cpu_count() or 1, 1) + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        return cpus & set(os.sched_getaffinity(0))
+    except Exception:
+        return set()
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process (one per GPU) to the CPUs next to its GPU BEFORE it allocates pinned host
+    buffers, so the per-batch H2D / D2H copies of the inference loop stay on the GPU's own socket.
+    With 8 ranks streaming 0.5 GB per 23 ms batch each, remote-socket pinned memory is what the
+    end-to-end rate loses first.  Returns the CPU set used (empty = left unchanged)."""
+    import os
+    cpus = gpu_local_cpus(device_index)
+    if cpus and cpus != set(os.sched_getaffinity(0)):
+        try:
+            os.sched_setaffinity(0, cpus)
+        except OSError:
+            return set()
+    return cpus
