@@ -69,3 +69,18 @@ def test_gloo_world2_allreduce_and_gather():
     for rank, g, allcaps in res:
         np.testing.assert_allclose(g, want, rtol=1e-6, atol=1e-6)
         assert allcaps == ['img%d' % i for i in range(10)]
+
+
+def test_gpu_numa_binding_is_a_noop_without_nvml_or_gpu():
+    """`parallel.bind_to_gpu_numa` (called by bench.py for N > 1 before pinned buffers are allocated) may only ever
+    NARROW the CPU set to NVML's ideal CPUs for the GPU; without a GPU / NVML it must leave the process untouched."""
+    import os
+    from comic_b200 import parallel as par
+    before = set(os.sched_getaffinity(0))
+    local = par.gpu_local_cpus(0)
+    assert isinstance(local, set) and local <= before
+    used = par.bind_to_gpu_numa(0)
+    after = set(os.sched_getaffinity(0))
+    assert used == local
+    assert after == (local if local else before)
+    os.sched_setaffinity(0, before)
