@@ -479,6 +479,27 @@ def test_run_stream_pipeline_matches_run(torch_mod):
     np.testing.assert_array_equal(p, want[0][0])
 
 
+def test_run_inference_driver_on_engine(torch_mod, tmp_path):
+    """inference.run_inference (src/infer_fn.py:76-184) over the CUDA engine: captions in the json are
+    id_to_caption of what the blocking `run` decodes for the same images, whole batches only."""
+    import json
+    from comic_b200 import inference as inf
+    from comic_b200.model import CaptionModel
+    from comic_b200.scst import id_to_caption
+    c = comic_config(infer_max_length=4)
+    c.batch_size_infer = 3
+    c.save_attention_maps = True
+    c.infer_save_path = str(tmp_path)
+    m = CaptionModel(c, 'infer', weights=make_weights(c))
+    batches = [images(3, seed=s) for s in (1, 2, 3)]
+    files = ['COCO_val2014_%012d.jpg' % i for i in range(8)]            # 8 files -> 2 whole batches of 3
+    want = [cap for b in batches[:2] for cap in id_to_caption(m.run(b)[0], c)]
+    raw, coco, _ = inf.run_inference(c, 'model_compact-77', m, files, iter(batches))
+    assert [e['caption'] for e in coco] == want and [e['image_id'] for e in coco] == list(range(6))
+    assert json.load(open(tmp_path / 'captions___77.json')) == coco
+    np.testing.assert_array_equal(raw['attention'][files[4]], m.run(batches[1])[1][1])
+
+
 def test_errors(torch_mod):
     from comic_b200.engine import Engine
     with pytest.raises(ValueError):

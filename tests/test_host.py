@@ -169,3 +169,51 @@ def test_legacy_lr_schedule():
         lr = legacy_lr_reduce(c, epoch, lr)
         seen.append(lr)
     assert seen[2] == 1e-3 and seen[3] == 5e-4 and seen[7] == 2.5e-4 and seen[11] == 2e-4
+
+
+# ---------------------------------------------------------------------------
+# inference driver: result files of src/infer_fn.py:76-184
+# ---------------------------------------------------------------------------
+class _FakeInferModel(object):
+    """Stands in for CaptionModel('infer'): fixed radix ids per batch, attention maps tagged with the batch index."""
+
+    def __init__(self, ids):
+        self.ids = ids
+
+    def run_stream(self, batches):
+        import numpy as np
+        for i, b in enumerate(batches):
+            yield [self.ids, np.full((self.ids.shape[0], 8, self.ids.shape[1], 196), float(i), np.float32)]
+
+
+def test_run_inference_writes_the_reference_result_files(tmp_path):
+    """infer_fn.py:107 (whole batches only), :139-156 (image ids, coco json), :165-183 (the three files)."""
+    import json
+    import numpy as np
+    from comic_b200 import inference as inf
+    c = conf.make_config(n_words=1000, batch_size_infer=2, infer_beam_size=3, save_attention_maps=True)
+    c.infer_save_path = str(tmp_path)
+    # radix-256 digits of words 5 and 300, then EOS (257) and padding ids the decoder emits after EOS
+    ids = np.array([[0, 5, 1, 44, 257, 257], [1, 44, 0, 5, 257, 257]], np.int32)
+    files = ['COCO_val2014_000000000042.jpg', 'COCO_val2014_000000000073.jpg', 'mine@a/b/cat.jpg', 'x_7.jpg',
+             'COCO_val2014_000000000099.jpg']                      # 5 files, batch 2 -> 2 whole batches
+    batches = [np.zeros((2, 224, 224, 3), np.float32)] * 3
+    raw, coco, t = inf.run_inference(c, '/ckpt/model_compact-12345', _FakeInferModel(ids), files, batches)
+    assert [e['image_id'] for e in coco] == [42, 73, 'cat', 7]
+    assert coco[0]['caption'] == 'w5 w300' and coco[1]['caption'] == 'w300 w5'
+    assert raw['checkpoint_number'] == '12345' and raw['beam_size'] == 3
+    assert raw['attention']['x_7.jpg'].shape == (8, 6, 196) and raw['attention']['x_7.jpg'][0, 0, 0] == 1.0
+    assert json.load(open(tmp_path / 'captions___12345.json')) == coco
+    with open(tmp_path / 'outputs___12345.pkl', 'rb') as f:
+        assert sorted(pickle.load(f)['captions']) == sorted(files[:4])
+    speed = open(tmp_path / 'infer_speed.txt', newline='').read().split('\r\n')
+    assert speed[:4] == ['Using GPU #: 0', 'Inference batch size: 2', 'Inference beam size: 3', '']
+    assert float(speed[4]) > 0
+    # a second checkpoint appends one line and does not repeat the header
+    c.save_attention_maps = False
+    inf.run_inference(c, '/ckpt/model_compact-20000', _FakeInferModel(ids), files, batches)
+    assert len(open(tmp_path / 'infer_speed.txt', newline='').read().split('\r\n')) == 6
+    assert not (tmp_path / 'outputs___20000.pkl').exists()
+    assert inf.image_id_from_filename('COCO_test2014_000000000123.jpg') == 123
+    with pytest.raises(ValueError):
+        inf.image_id_from_filename('nodigits.jpg')
