@@ -836,4 +836,58 @@ int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out,
 
 }  // namespace comic
 
+// ---------------------------------------------------------------------------
+// Evaluation pre-processing of common/inputs/preprocessing/inception_preprocessing_radix.py:
+// convert_image_dtype(uint8 -> float32) (:271), resize_bilinear to 256 x 256 with TF r1.9's
+// align_corners=False rule (source = destination * in / out, no half-pixel offset) (:272),
+// resize_image_with_crop_or_pad to out_h x out_w (:230) and (x - 0.5) * 2 (:234-235), fused: only the
+// cropped pixels are interpolated, one thread per output pixel (3 channels), uint8 in / fp32 NHWC out.
+// ---------------------------------------------------------------------------
+namespace comic {
+__global__ void __launch_bounds__(256)
+preprocess_eval_kernel(const uint8_t* __restrict__ img, int B, int H, int W, int RS, int out_h, int out_w,
+                       float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * out_h * out_w) return;
+  const int x = (int)(i % out_w), y = (int)((i / out_w) % out_h), b = (int)(i / ((size_t)out_w * out_h));
+  // crop_or_pad: crop offset = (RS - out) / 2 when out < RS, pad offset = (out - RS) / 2 otherwise
+  const int ry = (out_h <= RS) ? y + (RS - out_h) / 2 : y - (out_h - RS) / 2;
+  const int rx = (out_w <= RS) ? x + (RS - out_w) / 2 : x - (out_w - RS) / 2;
+  float v[3] = {0.f, 0.f, 0.f};                       // padding is 0 BEFORE the standardisation
+  if (ry >= 0 && ry < RS && rx >= 0 && rx < RS) {
+    const float sy = (float)H / (float)RS, sx = (float)W / (float)RS;
+    const float fy = __fmul_rn((float)ry, sy), fx = __fmul_rn((float)rx, sx);
+    const int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = __fsub_rn(fy, (float)y0), lx = __fsub_rn(fx, (float)x0);
+    const uint8_t* p = img + (size_t)b * H * W * 3;
+    const float k = 1.0f / 255.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float tl = (float)p[((size_t)y0 * W + x0) * 3 + c] * k, tr = (float)p[((size_t)y0 * W + x1) * 3 + c] * k;
+      const float bl = (float)p[((size_t)y1 * W + x0) * 3 + c] * k, br = (float)p[((size_t)y1 * W + x1) * 3 + c] * k;
+      // separate multiply and add (no FMA contraction): bit-identical to TF's / the oracle's lerp
+      const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx)), bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+      v[c] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+    }
+  }
+  float* o = out + i * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = __fmul_rn(__fsub_rn(v[c], 0.5f), 2.0f);
+}
+}  // namespace comic
+
+extern "C" int comic_preprocess_eval(comic_handle_t h, const uint8_t* images, int B, int H, int W, int out_h,
+                                     int out_w, float* out, void* stream) {
+  COMIC_REQUIRE(h && images && out, COMIC_E_BADARG, "preprocess_eval: null argument");
+  COMIC_REQUIRE(B > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0, COMIC_E_SHAPE,
+                "preprocess_eval: bad shape B=%d H=%d W=%d out=%dx%d", B, H, W, out_h, out_w);
+  const size_t n = (size_t)B * out_h * out_w;
+  comic::preprocess_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(images, B, H, W, 256,
+                                                                                            out_h, out_w, out);
+  h->launches++;
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
 extern "C" const comic_conv_desc_t* comic_conv_table(void) { return comic::conv_table(); }

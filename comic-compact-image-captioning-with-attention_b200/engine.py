@@ -82,6 +82,7 @@ SIGNATURES = {
     'comic_bind_weights': (_I, [_P, C.POINTER(ComicWeights), _I, _P, _SZ, _P]),
     'comic_workspace_bytes': (_I, [_P, _I, _I, _I, _I, C.POINTER(_SZ)]),
     'comic_encode_fwd': (_I, [_P, _P, _I, _P, _P, _P, _P, _SZ, _P]),
+    'comic_preprocess_eval': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     'comic_project_fm': (_I, [_P, _P, _I, _P, _P, _P]),
     'comic_rnn_init': (_I, [_P, _P, _I, _P, _P, _P, _F, _P, _SZ, _P]),
     'comic_decode_step': (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
@@ -298,6 +299,19 @@ class Engine(object):
         self._check(self.lib.comic_encode_fwd(self._h, _ptr(images), B, _ptr(fm), _ptr(emb), _ptr(m5c),
                                               _ptr(ws), ws.numel(), self.stream()))
         return (emb, fm, m5c) if want_mixed5c else (emb, fm)
+
+    def preprocess_eval(self, images_u8, out_hw=(224, 224)):
+        """inception_preprocessing_radix.preprocess_image(is_training=False): uint8 [B,H,W,3] on device ->
+        fp32 [B,224,224,3] in [-1,1] (resize 256 bilinear, central crop, (x - 0.5) * 2)."""
+        torch = self.torch
+        images_u8 = images_u8.contiguous()
+        if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[3] != 3:
+            raise ValueError('images must be uint8 [B,H,W,3], got %s %s' % (images_u8.dtype, tuple(images_u8.shape)))
+        B, H, W = (int(v) for v in images_u8.shape[:3])
+        out = self.f32(B, int(out_hw[0]), int(out_hw[1]), 3)
+        self._check(self.lib.comic_preprocess_eval(self._h, _ptr(images_u8), B, H, W, int(out_hw[0]), int(out_hw[1]),
+                                                   _ptr(out), self.stream()))
+        return out
 
     # -- D0 -------------------------------------------------------------------
     def project_fm(self, fm):

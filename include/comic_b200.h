@@ -163,6 +163,13 @@ int comic_encode_fwd(comic_handle_t h, const float* images, int B, float* fm_out
                      float* im_embed_out, float* mixed5c_out, void* ws, size_t ws_bytes,
                      void* stream);
 
+/* Evaluation pre-processing, common/inputs/preprocessing/inception_preprocessing_radix.py:229-235, 270-273
+ * (convert_image_dtype -> resize_bilinear 256x256, align_corners=False -> central crop / zero pad to
+ * out_h x out_w -> (x - 0.5) * 2), fused.  images uint8 [B,H,W,3] (decoded RGB, one size per call);
+ * out fp32 [B,out_h,out_w,3] = the `images` argument of comic_encode_fwd. */
+int comic_preprocess_eval(comic_handle_t h, const uint8_t* images, int B, int H, int W, int out_h, int out_w,
+                          float* out, void* stream);
+
 /* D0: MultiHeadAttV3.__init__ common/ops_rnn.py:441-477: keys = fm.W_k once per
  * IMAGE (the reference does it per tiled beam row); values_out only for
  * `independent`. fm [B,M,C]; keys_out [B,M,R]; values_out [B,M,R] or NULL. */

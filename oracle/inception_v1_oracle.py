@@ -141,3 +141,34 @@ def encoder(images, W, config):
     fm = ep[config.cnn_fm_attention]                           # :98-103
     B, H, W_, C = fm.shape
     return im_embed, fm.reshape(B, H * W_, C), ep
+
+
+def preprocess_eval(images_u8, out_hw=(224, 224), resize=256):
+    """common/inputs/preprocessing/inception_preprocessing_radix.py:270-273 + :229-235 (is_training=False):
+    tf.image.convert_image_dtype(uint8 -> float32) = x * (1/255); tf.image.resize_bilinear to 256 x 256 with TF
+    r1.9's align_corners=False rule (in = out * in_size / out_size; top = floor, bottom = min(top + 1, size - 1);
+    lerp along x first, then y -- resize_bilinear_op.cc); resize_image_with_crop_or_pad (central crop offset
+    (256 - out) // 2, zero pad offset (out - 256) // 2); (x - 0.5) * 2.   PARITY UNPINNED against TF (restated)."""
+    x = np.asarray(images_u8)
+    assert x.dtype == np.uint8 and x.ndim == 4 and x.shape[3] == 3
+    B, H, W, _ = x.shape
+    f = x.astype(np.float32) * np.float32(1.0 / 255.0)
+    sy, sx = np.float32(H) / np.float32(resize), np.float32(W) / np.float32(resize)
+    fy = np.arange(resize, dtype=np.float32) * sy
+    fx = np.arange(resize, dtype=np.float32) * sx
+    y0 = np.floor(fy).astype(np.int64); x0 = np.floor(fx).astype(np.int64)
+    y1 = np.minimum(y0 + 1, H - 1); x1 = np.minimum(x0 + 1, W - 1)
+    ly = (fy - y0.astype(np.float32))[None, :, None, None]
+    lx = (fx - x0.astype(np.float32))[None, None, :, None]
+    tl = f[:, y0][:, :, x0]; tr = f[:, y0][:, :, x1]
+    bl = f[:, y1][:, :, x0]; br = f[:, y1][:, :, x1]
+    top = tl + (tr - tl) * lx
+    bot = bl + (br - bl) * lx
+    r = top + (bot - top) * ly                                        # [B, 256, 256, 3]
+    oh, ow = out_hw
+    out = np.zeros((B, oh, ow, 3), np.float32)
+    ys = (resize - oh) // 2 if oh <= resize else 0; yd = 0 if oh <= resize else (oh - resize) // 2
+    xs = (resize - ow) // 2 if ow <= resize else 0; xd = 0 if ow <= resize else (ow - resize) // 2
+    hh, ww = min(oh, resize), min(ow, resize)
+    out[:, yd:yd + hh, xd:xd + ww] = r[:, ys:ys + hh, xs:xs + ww]
+    return (out - np.float32(0.5)) * np.float32(2.0)

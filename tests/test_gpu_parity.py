@@ -500,6 +500,22 @@ def test_run_inference_driver_on_engine(torch_mod, tmp_path):
     np.testing.assert_array_equal(raw['attention'][files[4]], m.run(batches[1])[1][1])
 
 
+@pytest.mark.parametrize('B,H,W,out_hw', [(2, 37, 53, (224, 224)), (1, 480, 640, (224, 224)), (3, 256, 256, (224, 224)),
+                                          (1, 500, 333, (300, 200)), (2, 224, 224, (224, 224))])
+def test_preprocess_eval_bit_exact(torch_mod, B, H, W, out_hw):
+    """comic_preprocess_eval (uint8 -> resize 256 bilinear -> crop / pad -> (x - 0.5) * 2, fused) against the NumPy
+    restatement of inception_preprocessing_radix.py:229-235, 270-273: same fp32 operations, bit-exact."""
+    import inception_v1_oracle as I
+    torch = torch_mod
+    c = comic_config()
+    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False)
+    x = np.random.default_rng(B * 1000 + H + W).integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+    got = eng.preprocess_eval(torch.from_numpy(x).to(eng.device), out_hw).cpu().numpy()
+    np.testing.assert_array_equal(got, I.preprocess_eval(x, out_hw))
+    with pytest.raises(ValueError):
+        eng.preprocess_eval(torch.zeros((1, 8, 8, 3), device=eng.device))
+
+
 def test_errors(torch_mod):
     from comic_b200.engine import Engine
     with pytest.raises(ValueError):
