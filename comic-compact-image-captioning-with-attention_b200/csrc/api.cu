@@ -63,6 +63,10 @@ extern "C" int comic_create(const comic_cfg_t* cfg, comic_handle_t* out) {
   memset(&h->w, 0, sizeof(h->w));
   int rc = decoder_configure();
   if (rc) { delete h; return rc; }
+  if (cudaMallocHost(&h->attn2_host, 8 * sizeof(float)) != cudaSuccess) {   // see attn2_prepare (decoder.cu)
+    h->attn2_host = nullptr;
+    (void)cudaGetLastError();
+  }
   *out = h;
   return COMIC_OK;
 }
@@ -73,6 +77,7 @@ extern "C" int comic_destroy(comic_handle_t h) {
     delete[] h->prof_ev;
     delete[] h->prof_tag;
   }
+  if (h && h->attn2_host) cudaFreeHost(h->attn2_host);
   delete h;
   return COMIC_OK;
 }
@@ -144,6 +149,7 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
     case COMIC_OPT_ENC_PLANES: h->enc_planes = value; return COMIC_OK;
     case COMIC_OPT_STEM_S2D: h->stem_s2d = value; return COMIC_OK;
     case COMIC_OPT_TC_MIN_ROWS: h->tc_min_rows = value; return COMIC_OK;
+    case COMIC_OPT_ATTN2: h->attn2 = value; return COMIC_OK;
     case COMIC_OPT_GEMM_RESIDENT_B: tc::bres_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR: tc::pair_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR_MIN_TILES: tc::pair_min_tiles() = value; return COMIC_OK;
@@ -211,6 +217,7 @@ extern "C" int comic_bind_weights(comic_handle_t h, const comic_weights_t* w, in
   rc = encoder_pack(h, cv, st, !with_cnn);
   if (rc) return rc;
   h->bound = true;
+  h->attn2_state = 0;
   h->cnn_bound = with_cnn != 0;
   return COMIC_OK;
 }

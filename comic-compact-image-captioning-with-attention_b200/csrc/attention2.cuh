@@ -1,0 +1,709 @@
+// attention2.cuh -- streaming multi-head additive-LN attention for one decoder step
+// (MultiHeadAddLN.__call__, common/ops_rnn.py:531-565, and the context / alignment
+// part of MultiHeadAttentionWrapperV3.call, common/ops_rnn.py:692-716, 741-744).
+//
+// Second-generation kernel for the large-batch decode loop (tied values, softmax,
+// R = 512, 8 heads).  attention.cuh (one warp per key row, channels across lanes) spent
+// its time in shuffle-reduction chains and load-to-use stalls (profiles/r01z_ncu_attn_*:
+// 34 % short-scoreboard, issue slots 55 % busy).  Here the mapping is turned round:
+//
+//   * a LANE owns one head (64 channels) of one feature-map position, so the layer-norm
+//     statistics, the tanh sum and the head sum are serial in-thread accumulations -- the
+//     hot loop has no shuffles -- and every operand that is not the key itself (queries,
+//     gamma, beta, v) is a 128-byte conflict-free shared-memory read shared by 4 positions;
+//   * the key tensor is streamed ONCE per step: persistent CTAs (one per SM) walk a
+//     contiguous range of 4-position key slices (8 KB, contiguous in HBM) that a producer
+//     warp stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) through a
+//     ring of shared-memory stages;
+//   * warp roles: NSW score warps (slice -> 4 x 8 x k scores -> exp), 4 context warps that
+//     accumulate sum_m p[m] * key[m, :] from the SAME shared-memory slice (tied values:
+//     the old kernel re-read them from L2), one TMA warp, one query-preparation warp
+//     (centres and gamma-scales the next image's k queries while the current image is scored);
+//   * softmax without a max pass: |score| <= bound_h = sum_{c in head} |v_c| / |T| (tanh is
+//     bounded), so p = exp(score - bound_h) cannot overflow and alpha = p / sum p equals the
+//     max-subtracted form up to rounding.  The host only takes this kernel when bound_h is
+//     small enough that p cannot underflow either (attn2_prep / decoder.cu).
+//
+// Per-row statistics of the keys (mean, centred sum of squares) do not change during a decode
+// call and are computed once per call by key_stats_kernel.
+//
+// Numerics are the old kernel's: variance from (skk + sqq + 2 <k, qc>) / R, tanh(y) =
+// 1 - 2 / (2^(2 log2e y) + 1) with ex2.approx / one rcp.approx per four elements.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "attention.cuh"
+
+namespace comic {
+namespace a2 {
+
+constexpr int kR = 512;             // attention width
+constexpr int kH = 8;               // heads
+constexpr int kD = 64;              // head width
+constexpr int kPos = 4;             // positions per slice
+constexpr int kSliceFloats = kPos * kR;
+constexpr int kSliceBytes = kSliceFloats * 4;   // 8 KB
+constexpr int kCtxWarps = 4;
+constexpr float kTwoLog2e = 2.885390081777927f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+#ifndef COMIC_A2_WATCHDOG
+#define COMIC_A2_WATCHDOG 0
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+#if COMIC_A2_WATCHDOG
+  long long t0 = clock64();
+#endif
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+#if COMIC_A2_WATCHDOG
+    if (!done && clock64() - t0 > (1ll << 31)) {
+      printf("attn2 watchdog: block %d warp %d bar %u parity %u\n", blockIdx.x, threadIdx.x >> 5, addr, parity);
+      __trap();
+    }
+#endif
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// TMA bulk copy global -> shared (1-D, contiguous), completion signalled on an mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 128-bit shared-memory load at register + immediate (volatile: stays behind the mbarrier waits and keeps the
+// hand-made software pipeline order at the front-end level)
+template <int IMM>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(IMM));
+  return v;
+}
+// Prefetch a contiguous global range into L2 (no shared-memory destination, no completion tracking).
+__device__ __forceinline__ void tma_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Once per decode call: per key row mean and centred sum of squares; per head score bound.
+//   kstats [rows][2];  bound [8] = sum_{c in head} |v_c| / |T|
+// One warp per row, lane owns 16 contiguous channels (same reduction order as attention.cuh).
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) key_stats_kernel(const float* __restrict__ keys, long long rows,
+                                                               float* __restrict__ kstats, const float* __restrict__ vvec,
+                                                               const float* __restrict__ temperature,
+                                                               float* __restrict__ bound) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x < 32 * kH && bound != nullptr) {
+    // warp w < 8: head w
+    const int hd = threadIdx.x >> 5;
+    float s = fabsf(vvec[hd * kD + lane]) + fabsf(vvec[hd * kD + 32 + lane]);
+    s = wsum(s);
+    if (lane == 0) bound[hd] = s / fabsf(temperature[0]);
+  }
+  if (row >= rows) return;
+  const float* kr = keys + row * kR + lane * 16;
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    v[g] = ldg4(kr + g * 4);
+    s += (v[g].x + v[g].y) + (v[g].z + v[g].w);
+  }
+  const float mean = wsum(s) * (1.0f / kR);
+  float sq = 0.f;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float a = v[g].x - mean, b = v[g].y - mean, c = v[g].z - mean, d = v[g].w - mean;
+    sq = fmaf(a, a, sq); sq = fmaf(b, b, sq); sq = fmaf(c, c, sq); sq = fmaf(d, d, sq);
+  }
+  sq = wsum(sq);
+  if (lane == 0) {
+    kstats[row * 2 + 0] = mean;
+    kstats[row * 2 + 1] = sq;
+  }
+}
+
+struct Args {
+  const float* keys;      // [B, M, 512]; values == keys (tied)
+  const float* kstats;    // [B * M, 2]
+  const float* bound;     // [8]
+  const float* lq;        // [N, ld_lq], query at column q_off
+  int ld_lq, q_off;
+  const float* gamma;
+  const float* beta;
+  const float* vvec;
+  const float* temperature;
+  float* ctx_out;         // [N, ld_ctx]
+  int ld_ctx;
+  float* hist_t;          // [N, 8 * M] or nullptr
+  int B, M;               // M % 4 == 0
+  const int* fin_count;
+  int t, n_rows;
+  long long* trace;       // diagnostics (COMIC_A2_TRACE builds): [grid][warps][kTraceSlices][8] clock64 stamps, or nullptr
+};
+constexpr int kTraceSlices = 256;
+#ifndef COMIC_A2_TRACE
+#define COMIC_A2_TRACE 0
+#endif
+#ifndef COMIC_A2_L2_AHEAD
+#define COMIC_A2_L2_AHEAD 0       // key slices prefetched into L2 ahead of the shared-memory ring (0 = off)
+#endif
+#ifndef COMIC_A2_STREAM_ONLY
+#define COMIC_A2_STREAM_ONLY 0    // diagnostics: consumers only wait and release (times the key stream alone; outputs garbage)
+#endif
+#if COMIC_A2_TRACE
+#define A2_STAMP(slot) do { if (trc != nullptr && tn < kTraceSlices && lane == 0) trc[tn * 8 + (slot)] = clock64(); } while (0)
+#else
+#define A2_STAMP(slot) do { } while (0)
+#endif
+
+constexpr int kCtxWarps2 = 2;      // context warps of the kernel below (each takes every 2nd slice)
+
+template <int K, int NSW, int STAGES>
+struct Layout {
+  // warps: NSW score | 2 context | 1 finaliser | 1 TMA producer + query preparation
+  static constexpr int kWarps = NSW + kCtxWarps2 + 2;
+  static constexpr int kThreads = kWarps * 32;
+  // byte offsets into dynamic shared memory (base 1024-aligned)
+  static constexpr int ring = 0;
+  static constexpr int consts = ring + STAGES * kSliceBytes;       // gamma' | beta' | v' (pair order)   [3][512]
+  static constexpr int qbuf = consts + 3 * kR * 4;                 // [2][ qc [K][512] | qg [K][512] ]
+  static constexpr int qstat = qbuf + 2 * 2 * K * kR * 4;          // [2][K][2]  sqq, sum qc
+  static constexpr int ssum = qstat + 2 * K * 2 * 4;               // [K][8] 1 / sum p of the image being finalised
+  static constexpr int part = (ssum + K * kH * 4 + 15) & ~15;      // [2][K][512]: the context warps' partial sums of one image
+  static constexpr int bars = part + kCtxWarps2 * K * kR * 4;      // full[S] scored[S] empty[S] qfull[2] qempty[2] pempty[2] imgdone partfree | next slice
+  static constexpr int pbuf = (bars + (3 * STAGES + 8) * 8 + 8 + 15) & ~15;   // [2][K][8][M]
+  static __host__ __device__ size_t bytes(int M) { return (size_t)pbuf + (size_t)2 * K * kH * M * 4; }
+};
+
+// One chunk (four channels of this lane's head) of pass 2, software-pipelined by hand: `front` turns the staged
+// operands into 2^y' for the K beams (FMA + MUFU.EX2), `back` folds them into the head sums (FMA + one MUFU.RCP per
+// beam).  The caller issues the next chunk's loads and `front` before the previous chunk's `back`, so the MUFU
+// queue always has K * 4 independent exponentials in flight per warp.
+template <int K>
+struct Chunk {
+  float4 k, g, b, v;
+  float4 q[K];
+};
+// ka: key chunk address; ca: same chunk in the gamma' row of the constants (beta' / v' rows at + kR * 4, + 2 kR * 4);
+// qa: same chunk in the gamma-scaled query of beam 0 (beams at + kR * 4 each).  HF = half of the head (0 / 1).
+template <int K, int HF>
+__device__ __forceinline__ void chunk_load(Chunk<K>& c, uint32_t ka, uint32_t ca, uint32_t qa) {
+  c.k = lds128<HF * 128>(ka);
+  c.g = lds128<HF * 128>(ca);
+  c.b = lds128<HF * 128 + kR * 4>(ca);
+  c.q[0] = lds128<HF * 128>(qa);
+  if (K > 1) c.q[K > 1 ? 1 : 0] = lds128<HF * 128 + kR * 4>(qa);
+  if (K > 2) c.q[K > 2 ? 2 : 0] = lds128<HF * 128 + 2 * kR * 4>(qa);
+  c.v = lds128<HF * 128 + 2 * kR * 4>(ca);
+}
+// e[j] = (2^y0, 2^y2 | 2^y1, 2^y3) as two float2: xa = (e0, e2), xb = (e1, e3)
+template <int K>
+__device__ __forceinline__ void chunk_front(const Chunk<K>& c, const float2 nmu, const float (&rstd)[K], float2 (&xa)[K],
+                                            float2 (&xb)[K]) {
+  const float2 kg01 = __fmul2_rn(__fadd2_rn(make_float2(c.k.x, c.k.y), nmu), make_float2(c.g.x, c.g.y));
+  const float2 kg23 = __fmul2_rn(__fadd2_rn(make_float2(c.k.z, c.k.w), nmu), make_float2(c.g.z, c.g.w));
+  float2 y01[K], y23[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const float2 r2 = make_float2(rstd[j], rstd[j]);
+    y01[j] = __ffma2_rn(__fadd2_rn(kg01, make_float2(c.q[j].x, c.q[j].y)), r2, make_float2(c.b.x, c.b.y));
+    y23[j] = __ffma2_rn(__fadd2_rn(kg23, make_float2(c.q[j].z, c.q[j].w)), r2, make_float2(c.b.z, c.b.w));
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    xa[j] = make_float2(ex2_approx(fminf(y01[j].x, 30.0f)), ex2_approx(fminf(y23[j].x, 30.0f)));
+    xb[j] = make_float2(ex2_approx(fminf(y01[j].y, 30.0f)), ex2_approx(fminf(y23[j].y, 30.0f)));
+  }
+}
+template <int K>
+__device__ __forceinline__ void chunk_back(const float4 vv, const float2 (&ea)[K], const float2 (&eb)[K], float (&out)[K]) {
+  const float2 one2 = make_float2(1.0f, 1.0f);
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const float2 xa = __fadd2_rn(ea[j], one2), xb = __fadd2_rn(eb[j], one2);
+    const float2 p = __fmul2_rn(xa, xb);                     // (x0 x1, x2 x3)
+    // vv is stored as (v1, v3, v0, v2) * -2:  n = (x0 v1 + x1 v0, x2 v3 + x3 v2)
+    const float2 n = __ffma2_rn(xa, make_float2(vv.x, vv.y), __fmul2_rn(xb, make_float2(vv.z, vv.w)));
+    const float rp = rcp_approx(p.x * p.y);
+    out[j] = fmaf(rp, fmaf(p.x, n.y, p.y * n.x), out[j]);
+  }
+}
+
+template <int K, int NSW, int STAGES>
+__global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(const Args a) {
+  if (a.fin_count != nullptr && a.t > 0 && a.fin_count[a.t - 1] >= a.n_rows) return;
+  using L = Layout<K, NSW, STAGES>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int M = a.M;
+  const int spi = M / kPos;                                   // slices per image
+  float* sm_c = reinterpret_cast<float*>(smem + L::consts);
+  float* sm_q = reinterpret_cast<float*>(smem + L::qbuf);
+  float* sm_qs = reinterpret_cast<float*>(smem + L::qstat);
+  float* sm_inv = reinterpret_cast<float*>(smem + L::ssum);
+  float* sm_part = reinterpret_cast<float*>(smem + L::part);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint64_t* scored = full + STAGES;
+  uint64_t* empty = scored + STAGES;
+  uint64_t* qfull = empty + STAGES;
+  uint64_t* qempty = qfull + 2;
+  uint64_t* pempty = qempty + 2;
+  uint64_t* imgdone = pempty + 2;
+  uint64_t* partfree = imgdone + 1;
+  int* next_g = reinterpret_cast<int*>(partfree + 1);
+  float* sm_p = reinterpret_cast<float*>(smem + L::pbuf);     // [2][K][8][M]
+  const int pimg = K * kH * M;                                // floats per image in sm_p
+
+  const int img_lo = (int)(((long long)a.B * blockIdx.x) / gridDim.x);
+  const int img_hi = (int)(((long long)a.B * (blockIdx.x + 1)) / gridDim.x);
+  const int n_img = img_hi - img_lo;
+  const int n_g = n_img * spi;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&scored[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qfull[i], 1);
+      mbar_init(&qempty[i], spi);          // one arrival per scored slice of the image
+      mbar_init(&pempty[i], 1);
+    }
+    mbar_init(imgdone, kCtxWarps2);
+    mbar_init(partfree, 1);
+    *next_g = 0;
+    fence_barrier_init();
+  }
+  // LN constants: gamma' = gamma * 2 log2 e, beta' likewise, v' = -2 v in pair order (v1, v3, v0, v2)
+  for (int c4 = tid; c4 < kR / 4; c4 += L::kThreads) {
+    const float4 g4 = ldg4(a.gamma + c4 * 4), b4 = ldg4(a.beta + c4 * 4), v4 = ldg4(a.vvec + c4 * 4);
+    *reinterpret_cast<float4*>(sm_c + c4 * 4) = make_float4(g4.x * kTwoLog2e, g4.y * kTwoLog2e, g4.z * kTwoLog2e, g4.w * kTwoLog2e);
+    *reinterpret_cast<float4*>(sm_c + kR + c4 * 4) = make_float4(b4.x * kTwoLog2e, b4.y * kTwoLog2e, b4.z * kTwoLog2e, b4.w * kTwoLog2e);
+    *reinterpret_cast<float4*>(sm_c + 2 * kR + c4 * 4) = make_float4(-2.0f * v4.y, -2.0f * v4.w, -2.0f * v4.x, -2.0f * v4.z);
+  }
+  __syncthreads();
+  if (n_g == 0) return;
+#if COMIC_A2_TRACE
+  long long* trc = a.trace ? a.trace + ((size_t)blockIdx.x * L::kWarps + warp) * kTraceSlices * 8 : nullptr;
+  int tn = 0;
+#endif
+
+  if (warp < NSW) {
+    // =========================== score warps ===========================
+    const int row = lane >> 3, hp = lane & 7;                 // position within the slice, head
+    // rotated chunk order: at step u the lane reads 16-byte chunk ((u + hp) & 7) of each half head, so the 8 lanes
+    // of a position hit 8 different bank groups (keys: row-major slice; queries / constants: plain [512] rows).
+    // The 8 per-lane chunk addresses are pinned in registers (opaque to the compiler, which otherwise re-derives them
+    // with several integer instructions per load); a load address is lane register + uniform stage / buffer base +
+    // immediate.
+    uint32_t kofs[8], cadr[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t o = (uint32_t)(hp * kD * 4 + (((u + hp) & 7) << 4));   // byte offset of the chunk in a [512] float row
+      asm volatile("mov.b32 %0, %1;" : "=r"(cadr[u]) : "r"(smem_u32(sm_c) + o));
+      asm volatile("mov.b32 %0, %1;" : "=r"(kofs[u]) : "r"(smem_u32(smem + L::ring) + (uint32_t)(row * kR * 4) + o));
+    }
+    const uint32_t q_minus_c = smem_u32(sm_q) - smem_u32(sm_c);
+    float sv = 0.f;
+    for (int c = 0; c < kD; ++c) sv += a.vvec[hp * kD + c];
+    const float inv_T = 1.0f / a.temperature[0];
+    const float shift = a.bound[hp];
+    int last_img = -1;
+    float sqq[K], sumq[K];
+    // Slices are claimed one at a time, in order: at most NSW < STAGES slices are claimed and unfinished, so a warp
+    // never waits on a stage whose previous use is still pending (the parity waits would alias).
+    for (;;) {
+      A2_STAMP(0);
+      int g = 0;
+      if (lane == 0) g = atomicAdd(next_g, 1);
+      g = __shfl_sync(0xffffffffu, g, 0);
+      if (g >= n_g) break;
+      const int ii = g / spi, sl = g - ii * spi;
+      const int par = ii & 1;
+      if (ii != last_img) {
+        mbar_wait(&qfull[par], (uint32_t)((ii >> 1) & 1));
+        mbar_wait(&pempty[par], (uint32_t)(((ii >> 1) & 1) ^ 1));
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          sqq[j] = sm_qs[(par * K + j) * 2 + 0];
+          sumq[j] = sm_qs[(par * K + j) * 2 + 1];
+        }
+        last_img = ii;
+      }
+      const int m = sl * kPos + row;
+      const float2 st = __ldg(reinterpret_cast<const float2*>(a.kstats) + ((size_t)(img_lo + ii) * M + m));
+      const int s = g % STAGES;
+      A2_STAMP(1);
+      mbar_wait(&full[s], (uint32_t)((g / STAGES) & 1));
+      A2_STAMP(2);
+#if COMIC_A2_STREAM_ONLY
+      if (lane == 0) { mbar_arrive(&scored[s]); mbar_arrive(&qempty[par]); }
+      continue;
+#endif
+      const uint32_t kst = (uint32_t)(s * kSliceBytes);                         // stage offset (uniform)
+      const uint32_t qcb = q_minus_c + (uint32_t)(par * 2 * K * kR * 4);        // centred queries of this image, relative to the constants
+      const uint32_t qgb = qcb + (uint32_t)(K * kR * 4);                        // * gamma'
+      // ---- pass 1: <k, qc_j> over this lane's head (loads two chunks ahead), then across the 8 lanes of the position ----
+      float2 d2[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) d2[j] = make_float2(0.f, 0.f);
+      {
+        float4 kq[3][1 + K];                                  // rotating window: chunk i, i + 1, i + 2
+        auto ld1 = [&](float4 (&dst)[1 + K], int i) {
+          const uint32_t ka = kofs[i & 7] + kst, qa = cadr[i & 7] + qcb;
+          if ((i >> 3) == 0) {
+            dst[0] = lds128<0>(ka);
+            dst[1] = lds128<0>(qa);
+            if (K > 1) dst[K > 1 ? 2 : 1] = lds128<kR * 4>(qa);
+            if (K > 2) dst[K > 2 ? 3 : 1] = lds128<2 * kR * 4>(qa);
+          } else {
+            dst[0] = lds128<128>(ka);
+            dst[1] = lds128<128>(qa);
+            if (K > 1) dst[K > 1 ? 2 : 1] = lds128<128 + kR * 4>(qa);
+            if (K > 2) dst[K > 2 ? 3 : 1] = lds128<128 + 2 * kR * 4>(qa);
+          }
+        };
+        ld1(kq[0], 0);
+        ld1(kq[1], 1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (i + 2 < 16) ld1(kq[(i + 2) % 3], i + 2);
+          const float4 k4 = kq[i % 3][0];
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            const float4 q4 = kq[i % 3][1 + j];
+            d2[j] = __ffma2_rn(make_float2(k4.x, k4.y), make_float2(q4.x, q4.y), d2[j]);
+            d2[j] = __ffma2_rn(make_float2(k4.z, k4.w), make_float2(q4.z, q4.w), d2[j]);
+          }
+        }
+      }
+      // first chunk of pass 2 is staged while the statistics are reduced
+      Chunk<K> cur;
+      chunk_load<K, 0>(cur, kofs[0] + kst, cadr[0], cadr[0] + qgb);
+      float rstd[K], out[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        float d = d2[j].x + d2[j].y;
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        d = fmaf(-st.x, sumq[j], d);                          // <k - mean, qc> (sum qc is ~0, not exactly 0)
+        const float ss = fmaxf(fmaf(2.0f, d, st.y + sqq[j]), 0.f);
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rstd[j]) : "f"(ss * (1.0f / kR) + 1e-12f));
+        out[j] = sv;
+      }
+      A2_STAMP(3);
+      // ---- pass 2: LN + tanh + v-weighted head sum ----
+      const float2 nmu = make_float2(-st.x, -st.x);
+      float2 ea[K], eb[K];
+      float4 vcur = cur.v;
+      chunk_front<K>(cur, nmu, rstd, ea, eb);
+#pragma unroll
+      for (int i = 1; i < 16; ++i) {
+        Chunk<K> nxt;
+        if ((i >> 3) == 0) chunk_load<K, 0>(nxt, kofs[i & 7] + kst, cadr[i & 7], cadr[i & 7] + qgb);
+        else chunk_load<K, 1>(nxt, kofs[i & 7] + kst, cadr[i & 7], cadr[i & 7] + qgb);
+        float2 na[K], nb[K];
+        chunk_front<K>(nxt, nmu, rstd, na, nb);
+        chunk_back<K>(vcur, ea, eb, out);
+        vcur = nxt.v;
+#pragma unroll
+        for (int j = 0; j < K; ++j) { ea[j] = na[j]; eb[j] = nb[j]; }
+      }
+      chunk_back<K>(vcur, ea, eb, out);
+      A2_STAMP(4);
+      float* pdst = sm_p + (size_t)par * pimg + hp * M + m;
+#pragma unroll
+      for (int j = 0; j < K; ++j) pdst[(size_t)j * kH * M] = expf(out[j] * inv_T - shift);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&scored[s]);
+        mbar_arrive(&qempty[par]);
+      }
+      A2_STAMP(5);
+#if COMIC_A2_TRACE
+      if (trc != nullptr && tn < kTraceSlices && lane == 0) trc[tn * 8 + 6] = g;
+      ++tn;
+#endif
+    }
+  } else if (warp < NSW + kCtxWarps2) {
+    // =========================== context warps ===========================
+    // Context warp cw takes every 2nd slice of the CTA's sequence and accumulates sum_m p[m] * key[m, :] over all 512
+    // channels of it from the shared-memory slice (two independent release chains); at the end of an image it hands
+    // its partial sums to the finaliser warp and goes straight on to the next image.
+    const int cw = warp - NSW;
+    const int hd0 = lane >> 4;                                // quad i of this lane: channels 4 (lane + 32 i) .., head hd0 + 2 i
+    float4 acc[K][4];
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int g = 0;
+    for (int ii = 0; ii < n_img; ++ii) {
+      const int par = ii & 1;
+      for (int sl = 0; sl < spi; ++sl, ++g) {
+        if ((g & (kCtxWarps2 - 1)) != cw) continue;
+        const int s = g % STAGES;
+        A2_STAMP(0);
+        mbar_wait(&scored[s], (uint32_t)((g / STAGES) & 1));
+        A2_STAMP(1);
+        const float* tile = reinterpret_cast<const float*>(smem + L::ring + s * kSliceBytes) + lane * 4;
+        const float* pp = sm_p + (size_t)par * pimg + hd0 * M + sl * kPos;
+        float4 kr[2][kPos], p4[2][K];
+#pragma unroll
+        for (int r = 0; r < kPos; ++r) kr[0][r] = *reinterpret_cast<const float4*>(tile + r * kR);
+#pragma unroll
+        for (int j = 0; j < K; ++j) p4[0][j] = *reinterpret_cast<const float4*>(pp + (size_t)(j * kH) * M);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i + 1 < 4) {
+#pragma unroll
+            for (int r = 0; r < kPos; ++r) kr[(i + 1) & 1][r] = *reinterpret_cast<const float4*>(tile + r * kR + (i + 1) * 128);
+#pragma unroll
+            for (int j = 0; j < K; ++j) p4[(i + 1) & 1][j] = *reinterpret_cast<const float4*>(pp + (size_t)(j * kH + 2 * (i + 1)) * M);
+          }
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            const float4 p = p4[i & 1][j];
+            float2 lo = make_float2(acc[j][i].x, acc[j][i].y), hi = make_float2(acc[j][i].z, acc[j][i].w);
+            lo = __ffma2_rn(make_float2(p.x, p.x), make_float2(kr[i & 1][0].x, kr[i & 1][0].y), lo);
+            hi = __ffma2_rn(make_float2(p.x, p.x), make_float2(kr[i & 1][0].z, kr[i & 1][0].w), hi);
+            lo = __ffma2_rn(make_float2(p.y, p.y), make_float2(kr[i & 1][1].x, kr[i & 1][1].y), lo);
+            hi = __ffma2_rn(make_float2(p.y, p.y), make_float2(kr[i & 1][1].z, kr[i & 1][1].w), hi);
+            lo = __ffma2_rn(make_float2(p.z, p.z), make_float2(kr[i & 1][2].x, kr[i & 1][2].y), lo);
+            hi = __ffma2_rn(make_float2(p.z, p.z), make_float2(kr[i & 1][2].z, kr[i & 1][2].w), hi);
+            lo = __ffma2_rn(make_float2(p.w, p.w), make_float2(kr[i & 1][3].x, kr[i & 1][3].y), lo);
+            hi = __ffma2_rn(make_float2(p.w, p.w), make_float2(kr[i & 1][3].z, kr[i & 1][3].w), hi);
+            acc[j][i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        A2_STAMP(2);
+#if COMIC_A2_TRACE
+        if (tn < kTraceSlices - 1) ++tn;
+#endif
+      }
+      // ---- image complete for this warp: hand the partial sums to the finaliser ----
+      mbar_wait(partfree, (uint32_t)((ii & 1) ^ 1));          // the finaliser has read image ii - 1's partials
+      float* pw = sm_part + (size_t)cw * K * kR;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<float4*>(pw + j * kR + (lane + 32 * i) * 4) = acc[j][i];
+          acc[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(imgdone);
+      A2_STAMP(3);
+#if COMIC_A2_TRACE
+      if (tn < kTraceSlices - 1) ++tn;
+#endif
+    }
+  } else if (warp == NSW + kCtxWarps2) {
+    // =========================== finaliser ===========================
+    // Per image: sum p over the positions (fixed order), add the two context partials (warp 0 + warp 1), normalise,
+    // write the context rows and the alignment history.
+    for (int ii = 0; ii < n_img; ++ii) {
+      const int par = ii & 1;
+      const int b = img_lo + ii;
+      A2_STAMP(0);
+      mbar_wait(imgdone, (uint32_t)(ii & 1));
+      A2_STAMP(1);
+      float4 tot[K][4];
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x = *reinterpret_cast<const float4*>(sm_part + j * kR + (lane + 32 * i) * 4);
+          const float4 y = *reinterpret_cast<const float4*>(sm_part + (K + j) * kR + (lane + 32 * i) * 4);
+          tot[j][i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+        }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(partfree);
+      const float* pim = sm_p + (size_t)par * pimg;
+      const int m4 = M / 4;
+      for (int pr = 0; pr < K * kH; ++pr) {
+        float s = 0.f;
+        for (int i = lane; i < m4; i += 32) {
+          const float4 p4 = *reinterpret_cast<const float4*>(pim + (size_t)pr * M + i * 4);
+          s += (p4.x + p4.y) + (p4.z + p4.w);
+        }
+        s = wsum(s);
+        if (lane == 0) sm_inv[pr] = 1.0f / s;
+      }
+      __syncwarp();
+      const int hd0 = lane >> 4;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float inv = sm_inv[j * kH + hd0 + 2 * i];
+          *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * K + j) * a.ld_ctx + (lane + 32 * i) * 4) =
+              make_float4(tot[j][i].x * inv, tot[j][i].y * inv, tot[j][i].z * inv, tot[j][i].w * inv);
+        }
+      if (a.hist_t != nullptr) {
+        float* hdst = a.hist_t + (size_t)b * K * kH * M;      // rows b*K + j, each [8][M]: contiguous, same order as sm_p
+        for (int pr = 0; pr < K * kH; ++pr) {
+          const float inv = sm_inv[pr];
+          for (int i = lane; i < m4; i += 32) {
+            const float4 p4 = *reinterpret_cast<const float4*>(pim + (size_t)pr * M + i * 4);
+            *reinterpret_cast<float4*>(hdst + (size_t)pr * M + i * 4) = make_float4(p4.x * inv, p4.y * inv, p4.z * inv, p4.w * inv);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pempty[par]);
+      A2_STAMP(2);
+#if COMIC_A2_TRACE
+      if (tn < kTraceSlices - 1) ++tn;
+#endif
+    }
+  } else {
+    // =========================== query preparation + TMA producer ===========================
+    // Lane 0 feeds the ring; the whole warp prepares the queries of image ii + 1 half-way through image ii's slices
+    // (the prefetched stages cover the pause), so neither the first key slice nor the queries of an image are late.
+    const float* src = a.keys + (size_t)img_lo * M * kR;
+    auto prep_queries = [&](int ii) {
+      const int par = ii & 1;
+      mbar_wait(&qempty[par], (uint32_t)(((ii >> 1) & 1) ^ 1));   // buffer last used by image ii - 2
+      float* qc = sm_q + (size_t)par * 2 * K * kR;
+      float* qg = qc + K * kR;
+      float4 v[K][4];
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float* q = a.lq + (size_t)((img_lo + ii) * K + j) * a.ld_lq + a.q_off + lane * 16;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) v[j][g] = ldg4(q + g * 4);
+      }
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) s += (v[j][g].x + v[j][g].y) + (v[j][g].z + v[j][g].w);
+        const float mean = wsum(s) * (1.0f / kR);
+        float sq = 0.f, sc = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 c = make_float4(v[j][g].x - mean, v[j][g].y - mean, v[j][g].z - mean, v[j][g].w - mean);
+          const float4 g4 = *reinterpret_cast<const float4*>(sm_c + lane * 16 + g * 4);
+          *reinterpret_cast<float4*>(qc + j * kR + lane * 16 + g * 4) = c;
+          *reinterpret_cast<float4*>(qg + j * kR + lane * 16 + g * 4) = make_float4(c.x * g4.x, c.y * g4.y, c.z * g4.z, c.w * g4.w);
+          sq = fmaf(c.x, c.x, sq); sq = fmaf(c.y, c.y, sq); sq = fmaf(c.z, c.z, sq); sq = fmaf(c.w, c.w, sq);
+          sc += (c.x + c.y) + (c.z + c.w);
+        }
+        sq = wsum(sq);
+        sc = wsum(sc);
+        if (lane == 0) {
+          sm_qs[(par * K + j) * 2 + 0] = sq;
+          sm_qs[(par * K + j) * 2 + 1] = sc;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&qfull[par]);
+    };
+    prep_queries(0);
+#if COMIC_A2_L2_AHEAD > 0
+    if (lane == 0) {
+      const int npf = n_g < COMIC_A2_L2_AHEAD ? n_g : COMIC_A2_L2_AHEAD;
+      for (int g = 0; g < npf; ++g) tma_prefetch_l2(src + (size_t)g * kSliceFloats, kSliceBytes);
+    }
+#endif
+    for (int g = 0, ii = 0, sl = 0; g < n_g; ++g) {
+      if (lane == 0) {
+        const int s = g % STAGES;
+#if COMIC_A2_L2_AHEAD > 0
+        if (g + COMIC_A2_L2_AHEAD < n_g) tma_prefetch_l2(src + (size_t)(g + COMIC_A2_L2_AHEAD) * kSliceFloats, kSliceBytes);
+#endif
+        mbar_wait(&empty[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
+        mbar_arrive_expect_tx(&full[s], kSliceBytes);
+        tma_bulk_g2s(smem + L::ring + s * kSliceBytes, src + (size_t)g * kSliceFloats, kSliceBytes, &full[s]);
+      }
+      if (sl == spi / 2 && ii + 1 < n_img) {
+        __syncwarp();
+        prep_queries(ii + 1);
+      }
+      if (++sl == spi) { sl = 0; ++ii; }
+    }
+  }
+}
+
+}  // namespace a2
+}  // namespace comic
+
+namespace comic {
+namespace a2 {
+
+#ifndef COMIC_A2_NSW
+#define COMIC_A2_NSW 12
+#endif
+#ifndef COMIC_A2_STAGES
+#define COMIC_A2_STAGES 18
+#endif
+
+// Launch for k beams per image (instantiated: 1, 2, 3).  Returns cudaErrorInvalidValue for shapes the kernel
+// does not cover (the caller falls back to attention.cuh).
+template <int K, int NSW = COMIC_A2_NSW, int STAGES = COMIC_A2_STAGES>
+inline cudaError_t launch_k(const Args& a, int num_sms, int dev, cudaStream_t st) {
+  using L = Layout<K, NSW, STAGES>;
+  static_assert(STAGES > NSW, "the ring needs more stages than score warps");
+  if (a.M % kPos != 0) return cudaErrorInvalidValue;
+  const size_t smem = L::bytes(a.M);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static bool configured[64] = {};
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidValue;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attn2_kernel<K, NSW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  const int grid = a.B < num_sms ? a.B : num_sms;
+  attn2_kernel<K, NSW, STAGES><<<grid, L::kThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch(const Args& a, int k, int num_sms, int dev, cudaStream_t st) {
+  switch (k) {
+    case 1: return launch_k<1>(a, num_sms, dev, st);
+    case 2: return launch_k<2>(a, num_sms, dev, st);
+    case 3: return launch_k<3>(a, num_sms, dev, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+inline cudaError_t launch_key_stats(const float* keys, long long rows, float* kstats, const float* vvec,
+                                    const float* temperature, float* bound, cudaStream_t st) {
+  key_stats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(keys, rows, kstats, vvec, temperature, bound);
+  return cudaGetLastError();
+}
+
+}  // namespace a2
+}  // namespace comic

@@ -71,6 +71,10 @@ struct comic_handle_s {
   bool bound = false, cnn_bound = false;
   int precision = 1;   // 0: fp32 FFMA everywhere; 1: tcgen05 split-precision GEMMs with M >= 128; 2: 1 + tanh.approx
   int fused_min_images = 48;   // fused attention kernel (one CTA per image) from this batch size on
+  int attn2 = 1;               // streaming attention kernel (attention2.cuh) where it applies: tied values, add_LN, softmax,
+                               // R = 512, 8 heads, k <= 3, no attention-map dropout; 0 = always attention.cuh
+  int attn2_state = 0;         // 0: score bound of the bound weights not checked yet; 1: within range; -1: too large
+  float* attn2_host = nullptr; // pinned [8]: per-head score bound read back once per weight binding
   int persist_trace = 0;       // record per-phase clock stamps of the persistent loop (diagnostics)
   long long* last_trace = nullptr;
   int last_trace_steps = 0;
@@ -164,6 +168,8 @@ struct StepBufs {
   float* scores;       // [N][H][M]
   float* xdense;       // [N][W+A] (input-dropout path only)
   float* ctxraw;       // [N][VAL] (context-layer path only)
+  float* kstats;       // [N * M][2] per key row: mean, centred sum of squares (attention2.cuh; once per decode call)
+  float* abound;       // [8] per-head bound of |score|
 };
 
 struct StepIO {
@@ -186,9 +192,14 @@ struct StepIO {
   // training tape (train.cu): pre-activation gates [N,4R], pre-dropout alignments [N,H*M];
   // force_dense assembles x = [emb;ctx] into StepBufs::xdense even without an input mask
   float* gates_save; float* alpha_pre; int force_dense;
+  // streaming attention (attention2.cuh): key-row statistics / score bound of `keys`, or nullptr when not prepared
+  const float* kstats; const float* abound;
 };
 
 int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, cudaStream_t st);
+// Once per decode call (keys fixed): decides whether the streaming attention kernel applies to (B, k) and, if so, fills
+// sb.kstats / sb.abound and points io at them.  Returns < 0 on error.
+int attn2_prepare(comic_handle_t h, StepIO& io, const StepBufs& sb, int B, int k, bool masks, cudaStream_t st);
 void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_masks);
 int decoder_workspace_bytes(comic_handle_t h, int mode, int B, int k, int T, size_t* bytes);
 int decoder_pack(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry);

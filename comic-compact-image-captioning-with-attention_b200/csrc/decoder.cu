@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "comic_internal.cuh"
 #include "search_steps.cuh"
 
@@ -655,6 +656,17 @@ static cudaError_t launch_fused(comic_handle_t h, const AttnArgs& aa, int B, siz
 // (caller falls back to the sliced scores + context kernels), < 0 on error.
 static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, float* ctx_dst,
                           int ld_ctx, cudaStream_t st) {
+  if (io.kstats != nullptr && io.att_mask == nullptr && io.alpha_pre == nullptr) {
+    // streaming kernel (attention2.cuh); attn2_prepare has checked the configuration
+    a2::Args aa{};
+    aa.keys = io.keys; aa.kstats = io.kstats; aa.bound = io.abound; aa.lq = sb.lq; aa.ld_lq = h->LQ; aa.q_off = h->Vp;
+    aa.gamma = h->w.ln_gamma; aa.beta = h->w.ln_beta; aa.vvec = h->w.attention_v; aa.temperature = h->w.temperature;
+    aa.ctx_out = ctx_dst; aa.ld_ctx = ld_ctx; aa.hist_t = io.hist_t; aa.B = B; aa.M = h->M;
+    aa.fin_count = io.fin_count; aa.t = io.t; aa.n_rows = io.n_rows; aa.trace = nullptr;
+    Prof pf(h, T_SCORES, st);
+    COMIC_CHECK_CUDA(a2::launch(aa, k, h->num_sms, h->dev, st));
+    return 1;
+  }
   if (B < h->fused_min_images || h->VAL > 1024 || h->VAL % 4 != 0) return 0;
   size_t smem = attn_fused_smem(k, h->R, h->H, h->M, h->VAL);
   if (smem > 200 * 1024) return 0;
@@ -692,6 +704,34 @@ static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb
   if (!ok) { h->launches--; return 0; }
   COMIC_CHECK_CUDA(e);
   return 1;
+}
+
+int attn2_prepare(comic_handle_t h, StepIO& io, const StepBufs& sb, int B, int k, bool masks, cudaStream_t st) {
+  io.kstats = nullptr;
+  io.abound = nullptr;
+  if (!h->attn2 || h->attn2_state < 0 || masks) return COMIC_OK;
+  if (h->cfg.alignment != 0 || h->cfg.prob_fn != 0 || h->R != a2::kR || h->H != a2::kH || h->VAL != h->R ||
+      io.values != io.keys || k < 1 || k > 3 || h->M % a2::kPos != 0 || B < h->fused_min_images || !sb.kstats)
+    return COMIC_OK;
+  {
+    Prof pf(h, T_MISC, st);
+    COMIC_CHECK_CUDA(a2::launch_key_stats(io.keys, (long long)B * h->M, sb.kstats, h->w.attention_v, h->w.temperature,
+                                          sb.abound, st));
+  }
+  if (h->attn2_state == 0) {
+    // once per weight binding: exp(score - bound) must not underflow to zero for a whole row, so the kernel is only
+    // taken while 2 * bound stays well inside the fp32 exponent range (the one host synchronisation of this path)
+    COMIC_REQUIRE(h->attn2_host != nullptr, COMIC_E_CUDA, "attn2: no pinned buffer");
+    COMIC_CHECK_CUDA(cudaMemcpyAsync(h->attn2_host, sb.abound, a2::kH * sizeof(float), cudaMemcpyDeviceToHost, st));
+    COMIC_CHECK_CUDA(cudaStreamSynchronize(st));
+    bool ok = true;
+    for (int i = 0; i < a2::kH; ++i) ok = ok && (h->attn2_host[i] == h->attn2_host[i]) && h->attn2_host[i] <= 40.0f;
+    h->attn2_state = ok ? 1 : -1;
+    if (!ok) return COMIC_OK;
+  }
+  io.kstats = sb.kstats;
+  io.abound = sb.abound;
+  return COMIC_OK;
 }
 
 // One attention-wrapper step on N = B*k rows.
@@ -822,6 +862,9 @@ void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_ma
   sb.scores = cv.take<float>((size_t)N * h->H * h->M);
   sb.xdense = cv.take<float>(train_masks ? (size_t)N * (h->W + h->A) : 1);
   sb.ctxraw = cv.take<float>(h->cfg.context_layer ? (size_t)N * h->VAL : 1);
+  const bool a2ok = h->cfg.alignment == 0 && h->cfg.prob_fn == 0 && h->R == a2::kR && h->H == a2::kH && h->VAL == h->R;
+  sb.kstats = cv.take<float>(a2ok ? (size_t)N * h->M * 2 : 1);    // N >= number of images
+  sb.abound = cv.take<float>(a2::kH);
 }
 
 struct LoopBufs {
@@ -1009,7 +1052,9 @@ extern "C" int comic_decode_step(comic_handle_t h, const float* keys, const floa
   io.in_mask = in_mask; io.out_mask = out_mask; io.att_mask = att_mask;
   io.in_keep = in_keep; io.out_keep = out_keep; io.att_keep = att_keep;
   io.fin_count = nullptr; io.t = 0; io.n_rows = N;
-  int rc = run_step(h, io, sb, B, k, st);
+  int rc = attn2_prepare(h, io, sb, B, k, in_mask || out_mask || att_mask, st);
+  if (rc) return rc;
+  rc = run_step(h, io, sb, B, k, st);
   if (rc) return rc;
   if (logits_out)
     COMIC_CHECK_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)h->V * sizeof(float), sb.lq, (size_t)h->LQ * sizeof(float),
@@ -1051,10 +1096,17 @@ extern "C" int comic_decode_greedy(comic_handle_t h, const float* keys, const fl
   pc.step_ids = ids_out; pc.parents = nullptr; pc.sc = nullptr; pc.logits_out = logits_out; pc.bar = lb.bar; pc.trace = h->persist_trace ? lb.trace : nullptr; pc.part = lb.part;
   int persisted = (max_it > 0) ? decode_persistent(h, pc, st) : 0;
   if (persisted < 0) return persisted;
+  StepIO io_a2{};
+  io_a2.keys = keys; io_a2.values = vals;
+  if (!persisted && max_it > 0) {
+    int rc = attn2_prepare(h, io_a2, lb.sb, B, 1, false, st);
+    if (rc) return rc;
+  }
   for (int t = 0; t < max_it && !persisted; ++t) {
     int cur = t & 1;
     StepIO io{};
     io.keys = keys; io.values = vals;
+    io.kstats = io_a2.kstats; io.abound = io_a2.abound;
     io.tok = lb.tok; io.src = nullptr; io.src_limit = N;
     io.c_prev = (t == 0) ? c0 : lb.c[cur];
     io.h_prev = (t == 0) ? h0 : lb.h[cur];
@@ -1123,10 +1175,17 @@ extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const floa
   pc.step_ids = step_ids; pc.parents = parents; pc.sc = sc; pc.logits_out = nullptr; pc.bar = lb.bar; pc.trace = h->persist_trace ? lb.trace : nullptr; pc.part = lb.part;
   int persisted = (max_it > 0) ? decode_persistent(h, pc, st) : 0;
   if (persisted < 0) return persisted;
+  StepIO io_a2{};
+  io_a2.keys = keys; io_a2.values = vals;
+  if (!persisted && max_it > 0) {
+    int rc = attn2_prepare(h, io_a2, lb.sb, B, k, false, st);
+    if (rc) return rc;
+  }
   for (int t = 0; t < max_it && !persisted; ++t) {
     int cur = t & 1;
     StepIO io{};
     io.keys = keys; io.values = vals;
+    io.kstats = io_a2.kstats; io.abound = io_a2.abound;
     io.tok = lb.tok;
     if (t == 0) {
       io.src = lb.src0; io.src_limit = B;        // tile_batch: row n reads image n / k

@@ -1036,6 +1036,7 @@ extern "C" int comic_adam_step(comic_handle_t h, float* params, const float* gra
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, (float)lr_t, beta1,
                                                                             beta2, eps, grad_scale);
   h->launches++;
+  h->attn2_state = 0;   // attention_v / temperature may have moved: re-check the score bound (decoder.cu attn2_prepare)
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;
 }
@@ -1046,6 +1047,7 @@ extern "C" int comic_adam_step(comic_handle_t h, float* params, const float* gra
 extern "C" int comic_refresh_packed(comic_handle_t h, void* packed, size_t packed_bytes, void* stream) {
   COMIC_REQUIRE(h && h->bound && packed, COMIC_E_BADARG, "refresh_packed: not bound");
   (void)packed_bytes;
+  h->attn2_state = 0;
   Carver cv(packed);
   return decoder_pack(h, cv, (cudaStream_t)stream, false);
 }

@@ -141,6 +141,9 @@ int comic_set_precision(comic_handle_t h, int mode);
                                              * 16); 1 = same conv, rows gathered from L2; 0 = 7x7/2 gather from NHWC4 fp32 */
 #define COMIC_OPT_GEMM_RESIDENT_B 10         /* 1 (default): convs with <= 64 output channels and K <= 512 keep their whole
                                              * weight panel in shared memory (loaded once per CTA); 0: stream it per M tile */
+#define COMIC_OPT_ATTN2 12                   /* 1 (default): large-batch decode steps use the streaming attention kernel
+                                                (TMA-staged key slices, one HBM pass per step) where it applies: tied
+                                                values, add_LN, softmax, rnn_size 512, 8 heads, beam <= 3; 0: never */
 #define COMIC_OPT_TC_MIN_ROWS 11             /* GEMMs / convs with at least this many rows run on the tensor path when
                                              * precision >= 1 (default 64) */
 int comic_set_option(comic_handle_t h, int option, int value);
