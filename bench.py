@@ -393,7 +393,9 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': caps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': {'f32': 'f32', 'split': 'f32 storage and accumulation; GEMM / conv operands split into 3 bf16 terms on tcgen05 (bf16x3)',
+                      'fast': 'f32 storage and accumulation; bf16x3 GEMMs + tanh.approx.f32'}[args.precision],
             'data': 'synthetic',
             'config': {'workload': workload_name(args.workload, B, beam, c), 'images_per_gpu': B,
                        'global_batch': B * world, 'beam': beam, 'decode_steps': T_exec,

@@ -27,6 +27,12 @@
 // Per-row statistics of the keys (mean, centred sum of squares) do not change during a decode
 // call and are computed once per call by key_stats_kernel.
 //
+// Work split: the B * M / 4 key slices of a step are one sequence that is cut into gridDim.x equal contiguous
+// ranges, so every SM gets the same number of slices whatever B is.  An image whose slices fall into several
+// CTAs is combined by the LAST CTA to finish its part (a per-image counter): partial sum p and partial contexts
+// go through a small global scratch and are added in CTA order (deterministic); the alignment history rows are
+// written unnormalised and rescaled by the combining CTA.
+//
 // Numerics are the old kernel's: variance from (skk + sqq + 2 <k, qc>) / R, tanh(y) =
 // 1 - 2 / (2^(2 log2e y) + 1) with ex2.approx / one rcp.approx per four elements.
 #pragma once
@@ -54,6 +60,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -164,6 +173,8 @@ struct Args {
   int B, M;               // M % 4 == 0
   const int* fin_count;
   int t, n_rows;
+  float* scratch;         // [2 * gridDim.x][K * (512 + 8)]: partial contexts / sums of images split across CTAs
+  int* counters;          // [B], zero between launches: parts of an image that have arrived
   long long* trace;       // diagnostics (COMIC_A2_TRACE builds): [grid][warps][kTraceSlices][8] clock64 stamps, or nullptr
 };
 constexpr int kTraceSlices = 256;
@@ -195,54 +206,37 @@ struct Layout {
   static constexpr int qbuf = consts + 3 * kR * 4;                 // [2][ qc [K][512] | qg [K][512] ]
   static constexpr int qstat = qbuf + 2 * 2 * K * kR * 4;          // [2][K][2]  sqq, sum qc
   static constexpr int ssum = qstat + 2 * K * 2 * 4;               // [K][8] 1 / sum p of the image being finalised
-  static constexpr int part = (ssum + K * kH * 4 + 15) & ~15;      // [2][K][512]: the context warps' partial sums of one image
-  static constexpr int bars = part + kCtxWarps2 * K * kR * 4;      // full[S] scored[S] empty[S] qfull[2] qempty[2] pempty[2] imgdone partfree | next slice
+  static constexpr int part = (ssum + K * kH * 4 + 15) & ~15;      // [2][K * 520]: the context warps' partial sums of one image segment
+  static constexpr int bars = part + kCtxWarps2 * K * (kR + kH) * 4;   // per context warp: [K][512] context partials | [K][8] sum p      // full[S] scored[S] empty[S] qfull[2] qempty[2] pempty[2] imgdone partfree | next slice
   static constexpr int pbuf = (bars + (3 * STAGES + 8) * 8 + 8 + 15) & ~15;   // [2][K][8][M]
   static __host__ __device__ size_t bytes(int M) { return (size_t)pbuf + (size_t)2 * K * kH * M * 4; }
 };
 
-// One chunk (four channels of this lane's head) of pass 2, software-pipelined by hand: `front` turns the staged
-// operands into 2^y' for the K beams (FMA + MUFU.EX2), `back` folds them into the head sums (FMA + one MUFU.RCP per
-// beam).  The caller issues the next chunk's loads and `front` before the previous chunk's `back`, so the MUFU
-// queue always has K * 4 independent exponentials in flight per warp.
+// Pass 2 works on chunks of four channels, software-pipelined by hand: `front4` turns staged operands into 2^y' for
+// the K beams of ONE position (FMA + MUFU.EX2), `back4` folds them into the head sums (FMA + one MUFU.RCP per beam).
+// The caller alternates the two positions of a lane so that the exponentials of one are in flight while the other's
+// are consumed.
+// ea[j] = (2^y0, 2^y2), eb[j] = (2^y1, 2^y3)
 template <int K>
-struct Chunk {
-  float4 k, g, b, v;
-  float4 q[K];
-};
-// ka: key chunk address; ca: same chunk in the gamma' row of the constants (beta' / v' rows at + kR * 4, + 2 kR * 4);
-// qa: same chunk in the gamma-scaled query of beam 0 (beams at + kR * 4 each).  HF = half of the head (0 / 1).
-template <int K, int HF>
-__device__ __forceinline__ void chunk_load(Chunk<K>& c, uint32_t ka, uint32_t ca, uint32_t qa) {
-  c.k = lds128<HF * 128>(ka);
-  c.g = lds128<HF * 128>(ca);
-  c.b = lds128<HF * 128 + kR * 4>(ca);
-  c.q[0] = lds128<HF * 128>(qa);
-  if (K > 1) c.q[K > 1 ? 1 : 0] = lds128<HF * 128 + kR * 4>(qa);
-  if (K > 2) c.q[K > 2 ? 2 : 0] = lds128<HF * 128 + 2 * kR * 4>(qa);
-  c.v = lds128<HF * 128 + 2 * kR * 4>(ca);
-}
-// e[j] = (2^y0, 2^y2 | 2^y1, 2^y3) as two float2: xa = (e0, e2), xb = (e1, e3)
-template <int K>
-__device__ __forceinline__ void chunk_front(const Chunk<K>& c, const float2 nmu, const float (&rstd)[K], float2 (&xa)[K],
-                                            float2 (&xb)[K]) {
-  const float2 kg01 = __fmul2_rn(__fadd2_rn(make_float2(c.k.x, c.k.y), nmu), make_float2(c.g.x, c.g.y));
-  const float2 kg23 = __fmul2_rn(__fadd2_rn(make_float2(c.k.z, c.k.w), nmu), make_float2(c.g.z, c.g.w));
+__device__ __forceinline__ void front4(const float4 k, const float4 g, const float4 b, const float4 (&q)[K], const float2 nmu,
+                                       const float (&rstd)[K], float2 (&ea)[K], float2 (&eb)[K]) {
+  const float2 kg01 = __fmul2_rn(__fadd2_rn(make_float2(k.x, k.y), nmu), make_float2(g.x, g.y));
+  const float2 kg23 = __fmul2_rn(__fadd2_rn(make_float2(k.z, k.w), nmu), make_float2(g.z, g.w));
   float2 y01[K], y23[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     const float2 r2 = make_float2(rstd[j], rstd[j]);
-    y01[j] = __ffma2_rn(__fadd2_rn(kg01, make_float2(c.q[j].x, c.q[j].y)), r2, make_float2(c.b.x, c.b.y));
-    y23[j] = __ffma2_rn(__fadd2_rn(kg23, make_float2(c.q[j].z, c.q[j].w)), r2, make_float2(c.b.z, c.b.w));
+    y01[j] = __ffma2_rn(__fadd2_rn(kg01, make_float2(q[j].x, q[j].y)), r2, make_float2(b.x, b.y));
+    y23[j] = __ffma2_rn(__fadd2_rn(kg23, make_float2(q[j].z, q[j].w)), r2, make_float2(b.z, b.w));
   }
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    xa[j] = make_float2(ex2_approx(fminf(y01[j].x, 30.0f)), ex2_approx(fminf(y23[j].x, 30.0f)));
-    xb[j] = make_float2(ex2_approx(fminf(y01[j].y, 30.0f)), ex2_approx(fminf(y23[j].y, 30.0f)));
+    ea[j] = make_float2(ex2_approx(fminf(y01[j].x, 30.0f)), ex2_approx(fminf(y23[j].x, 30.0f)));
+    eb[j] = make_float2(ex2_approx(fminf(y01[j].y, 30.0f)), ex2_approx(fminf(y23[j].y, 30.0f)));
   }
 }
 template <int K>
-__device__ __forceinline__ void chunk_back(const float4 vv, const float2 (&ea)[K], const float2 (&eb)[K], float (&out)[K]) {
+__device__ __forceinline__ void back4(const float4 vv, const float2 (&ea)[K], const float2 (&eb)[K], float (&out)[K]) {
   const float2 one2 = make_float2(1.0f, 1.0f);
 #pragma unroll
   for (int j = 0; j < K; ++j) {
@@ -253,6 +247,24 @@ __device__ __forceinline__ void chunk_back(const float4 vv, const float2 (&ea)[K
     const float rp = rcp_approx(p.x * p.y);
     out[j] = fmaf(rp, fmaf(p.x, n.y, p.y * n.x), out[j]);
   }
+}
+// Operands of one chunk for the two positions of a lane: keys of row A / row A + 2 (4 KB apart in the slice), gamma',
+// beta', v' and the K gamma-scaled queries.
+template <int K>
+struct Chunk2 {
+  float4 ka, kb, g, b, v;
+  float4 q[K];
+};
+template <int K>
+__device__ __forceinline__ void chunk2_load(Chunk2<K>& c, uint32_t ka, uint32_t ca, uint32_t qa) {
+  c.ka = lds128<0>(ka);
+  c.kb = lds128<2 * kR * 4>(ka);
+  c.g = lds128<0>(ca);
+  c.b = lds128<kR * 4>(ca);
+  c.q[0] = lds128<0>(qa);
+  if (K > 1) c.q[K > 1 ? 1 : 0] = lds128<kR * 4>(qa);
+  if (K > 2) c.q[K > 2 ? 2 : 0] = lds128<2 * kR * 4>(qa);
+  c.v = lds128<2 * kR * 4>(ca);
 }
 
 template <int K, int NSW, int STAGES>
@@ -280,10 +292,19 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
   float* sm_p = reinterpret_cast<float*>(smem + L::pbuf);     // [2][K][8][M]
   const int pimg = K * kH * M;                                // floats per image in sm_p
 
-  const int img_lo = (int)(((long long)a.B * blockIdx.x) / gridDim.x);
-  const int img_hi = (int)(((long long)a.B * (blockIdx.x + 1)) / gridDim.x);
-  const int n_img = img_hi - img_lo;
-  const int n_g = n_img * spi;
+  // this CTA's contiguous range of the step's slice sequence; (b0, sl0) = image / slice of its first slice
+  const long long T_all = (long long)a.B * spi;
+  const int G = (int)gridDim.x;
+  const long long g_lo = T_all * blockIdx.x / G, g_hi = T_all * (blockIdx.x + 1) / G;
+  const int n_g = (int)(g_hi - g_lo);
+  const int b0 = (int)(g_lo / spi), sl0 = (int)(g_lo - (long long)b0 * spi);
+  const int n_seg = (sl0 + n_g + spi - 1) / spi;             // image segments in the range (only the first / last can be partial)
+  auto seg_lo = [&](int ii) { return ii == 0 ? sl0 : 0; };
+  auto seg_hi = [&](int ii) { const int r = sl0 + n_g - ii * spi; return r < spi ? r : spi; };
+  // Processing order: the LAST segment first, then segments 0, 1, ...  The two segments that can be parts of images
+  // shared with the neighbouring CTAs are thus finished (and combined) early, behind the whole images that follow.
+  const int len_last = (n_seg >= 2) ? seg_hi(n_seg - 1) : 0;       // slices of the segment processed first (it starts at slice 0)
+  auto seg_of = [&](int pos) { return len_last > 0 ? (pos == 0 ? n_seg - 1 : pos - 1) : pos; };
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -317,22 +338,25 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
 
   if (warp < NSW) {
     // =========================== score warps ===========================
-    const int row = lane >> 3, hp = lane & 7;                 // position within the slice, head
-    // rotated chunk order: at step u the lane reads 16-byte chunk ((u + hp) & 7) of each half head, so the 8 lanes
-    // of a position hit 8 different bank groups (keys: row-major slice; queries / constants: plain [512] rows).
+    // lane = (row pair rp, half head hf, head hp): the lane scores positions rp and rp + 2 of the slice over 32
+    // channels of head hp.  Per-channel operands (gamma', beta', v', queries) are loaded once for both positions,
+    // which is what keeps the shared-memory pipe (4 wavefronts per 128-bit load) off the critical path.
+    const int rp = lane >> 4, hf = (lane >> 3) & 1, hp = lane & 7;
+    // rotated chunk order: at step u the lane reads 16-byte chunk ((u + hp) & 7) of its half head, so the 8 lanes of a
+    // quarter warp hit 8 different bank groups (keys: row-major slice; queries / constants: plain [512] rows).
     // The 8 per-lane chunk addresses are pinned in registers (opaque to the compiler, which otherwise re-derives them
     // with several integer instructions per load); a load address is lane register + uniform stage / buffer base +
     // immediate.
     uint32_t kofs[8], cadr[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const uint32_t o = (uint32_t)(hp * kD * 4 + (((u + hp) & 7) << 4));   // byte offset of the chunk in a [512] float row
+      const uint32_t o = (uint32_t)(hp * kD * 4 + hf * 128 + (((u + hp) & 7) << 4));   // byte offset of the chunk in a [512] float row
       asm volatile("mov.b32 %0, %1;" : "=r"(cadr[u]) : "r"(smem_u32(sm_c) + o));
-      asm volatile("mov.b32 %0, %1;" : "=r"(kofs[u]) : "r"(smem_u32(smem + L::ring) + (uint32_t)(row * kR * 4) + o));
+      asm volatile("mov.b32 %0, %1;" : "=r"(kofs[u]) : "r"(smem_u32(smem + L::ring) + (uint32_t)(rp * kR * 4) + o));
     }
     const uint32_t q_minus_c = smem_u32(sm_q) - smem_u32(sm_c);
-    float sv = 0.f;
-    for (int c = 0; c < kD; ++c) sv += a.vvec[hp * kD + c];
+    float sv = 0.f;                                           // sum of v over this lane's 32 channels
+    for (int c = 0; c < kD / 2; ++c) sv += a.vvec[hp * kD + hf * 32 + c];
     const float inv_T = 1.0f / a.temperature[0];
     const float shift = a.bound[hp];
     int last_img = -1;
@@ -345,20 +369,23 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
       if (lane == 0) g = atomicAdd(next_g, 1);
       g = __shfl_sync(0xffffffffu, g, 0);
       if (g >= n_g) break;
-      const int ii = g / spi, sl = g - ii * spi;
-      const int par = ii & 1;
-      if (ii != last_img) {
-        mbar_wait(&qfull[par], (uint32_t)((ii >> 1) & 1));
-        mbar_wait(&pempty[par], (uint32_t)(((ii >> 1) & 1) ^ 1));
+      int pos, ii, sl;
+      if (g < len_last) { pos = 0; ii = n_seg - 1; sl = g; }
+      else { const int v = g - len_last + sl0; ii = v / spi; sl = v - ii * spi; pos = ii + (len_last > 0 ? 1 : 0); }
+      const int par = pos & 1;
+      if (pos != last_img) {
+        mbar_wait(&qfull[par], (uint32_t)((pos >> 1) & 1));
+        mbar_wait(&pempty[par], (uint32_t)(((pos >> 1) & 1) ^ 1));
 #pragma unroll
         for (int j = 0; j < K; ++j) {
           sqq[j] = sm_qs[(par * K + j) * 2 + 0];
           sumq[j] = sm_qs[(par * K + j) * 2 + 1];
         }
-        last_img = ii;
+        last_img = pos;
       }
-      const int m = sl * kPos + row;
-      const float2 st = __ldg(reinterpret_cast<const float2*>(a.kstats) + ((size_t)(img_lo + ii) * M + m));
+      const int m = sl * kPos + rp;                           // positions m and m + 2
+      const float2* ksp = reinterpret_cast<const float2*>(a.kstats) + ((size_t)(b0 + ii) * M + m);
+      const float2 stA = __ldg(ksp), stB = __ldg(ksp + 2);
       const int s = g % STAGES;
       A2_STAMP(1);
       mbar_wait(&full[s], (uint32_t)((g / STAGES) & 1));
@@ -370,78 +397,84 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
       const uint32_t kst = (uint32_t)(s * kSliceBytes);                         // stage offset (uniform)
       const uint32_t qcb = q_minus_c + (uint32_t)(par * 2 * K * kR * 4);        // centred queries of this image, relative to the constants
       const uint32_t qgb = qcb + (uint32_t)(K * kR * 4);                        // * gamma'
-      // ---- pass 1: <k, qc_j> over this lane's head (loads two chunks ahead), then across the 8 lanes of the position ----
-      float2 d2[K];
+      // ---- pass 1: <k, qc_j> over this lane's 32 channels (loads one chunk ahead), then across the 16 lanes of a position ----
+      float2 dA[K], dB[K];
 #pragma unroll
-      for (int j = 0; j < K; ++j) d2[j] = make_float2(0.f, 0.f);
+      for (int j = 0; j < K; ++j) { dA[j] = make_float2(0.f, 0.f); dB[j] = make_float2(0.f, 0.f); }
       {
-        float4 kq[3][1 + K];                                  // rotating window: chunk i, i + 1, i + 2
-        auto ld1 = [&](float4 (&dst)[1 + K], int i) {
-          const uint32_t ka = kofs[i & 7] + kst, qa = cadr[i & 7] + qcb;
-          if ((i >> 3) == 0) {
-            dst[0] = lds128<0>(ka);
-            dst[1] = lds128<0>(qa);
-            if (K > 1) dst[K > 1 ? 2 : 1] = lds128<kR * 4>(qa);
-            if (K > 2) dst[K > 2 ? 3 : 1] = lds128<2 * kR * 4>(qa);
-          } else {
-            dst[0] = lds128<128>(ka);
-            dst[1] = lds128<128>(qa);
-            if (K > 1) dst[K > 1 ? 2 : 1] = lds128<128 + kR * 4>(qa);
-            if (K > 2) dst[K > 2 ? 3 : 1] = lds128<128 + 2 * kR * 4>(qa);
-          }
+        float4 kq[2][2 + K];                                  // chunk u, u + 1: keys A, keys B, K centred queries
+        auto ld1 = [&](float4 (&dst)[2 + K], int u) {
+          const uint32_t ka = kofs[u] + kst, qa = cadr[u] + qcb;
+          dst[0] = lds128<0>(ka);
+          dst[1] = lds128<2 * kR * 4>(ka);
+          dst[2] = lds128<0>(qa);
+          if (K > 1) dst[K > 1 ? 3 : 2] = lds128<kR * 4>(qa);
+          if (K > 2) dst[K > 2 ? 4 : 2] = lds128<2 * kR * 4>(qa);
         };
         ld1(kq[0], 0);
-        ld1(kq[1], 1);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i + 2 < 16) ld1(kq[(i + 2) % 3], i + 2);
-          const float4 k4 = kq[i % 3][0];
+        for (int u = 0; u < 8; ++u) {
+          if (u + 1 < 8) ld1(kq[(u + 1) & 1], u + 1);
+          const float4 ka = kq[u & 1][0], kb = kq[u & 1][1];
 #pragma unroll
           for (int j = 0; j < K; ++j) {
-            const float4 q4 = kq[i % 3][1 + j];
-            d2[j] = __ffma2_rn(make_float2(k4.x, k4.y), make_float2(q4.x, q4.y), d2[j]);
-            d2[j] = __ffma2_rn(make_float2(k4.z, k4.w), make_float2(q4.z, q4.w), d2[j]);
+            const float4 q4 = kq[u & 1][2 + j];
+            dA[j] = __ffma2_rn(make_float2(ka.x, ka.y), make_float2(q4.x, q4.y), dA[j]);
+            dA[j] = __ffma2_rn(make_float2(ka.z, ka.w), make_float2(q4.z, q4.w), dA[j]);
+            dB[j] = __ffma2_rn(make_float2(kb.x, kb.y), make_float2(q4.x, q4.y), dB[j]);
+            dB[j] = __ffma2_rn(make_float2(kb.z, kb.w), make_float2(q4.z, q4.w), dB[j]);
           }
         }
       }
       // first chunk of pass 2 is staged while the statistics are reduced
-      Chunk<K> cur;
-      chunk_load<K, 0>(cur, kofs[0] + kst, cadr[0], cadr[0] + qgb);
-      float rstd[K], out[K];
+      Chunk2<K> c;
+      chunk2_load<K>(c, kofs[0] + kst, cadr[0], cadr[0] + qgb);
+      float rsA[K], rsB[K], outA[K], outB[K];
 #pragma unroll
       for (int j = 0; j < K; ++j) {
-        float d = d2[j].x + d2[j].y;
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
-        d += __shfl_xor_sync(0xffffffffu, d, 4);
-        d = fmaf(-st.x, sumq[j], d);                          // <k - mean, qc> (sum qc is ~0, not exactly 0)
-        const float ss = fmaxf(fmaf(2.0f, d, st.y + sqq[j]), 0.f);
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rstd[j]) : "f"(ss * (1.0f / kR) + 1e-12f));
-        out[j] = sv;
+        float da = dA[j].x + dA[j].y, db = dB[j].x + dB[j].y;
+#pragma unroll
+        for (int o = 1; o <= 8; o <<= 1) {
+          da += __shfl_xor_sync(0xffffffffu, da, o);
+          db += __shfl_xor_sync(0xffffffffu, db, o);
+        }
+        da = fmaf(-stA.x, sumq[j], da);                       // <k - mean, qc> (sum qc is ~0, not exactly 0)
+        db = fmaf(-stB.x, sumq[j], db);
+        const float sa = fmaxf(fmaf(2.0f, da, stA.y + sqq[j]), 0.f), sb = fmaxf(fmaf(2.0f, db, stB.y + sqq[j]), 0.f);
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rsA[j]) : "f"(sa * (1.0f / kR) + 1e-12f));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rsB[j]) : "f"(sb * (1.0f / kR) + 1e-12f));
+        outA[j] = sv;
+        outB[j] = sv;
       }
       A2_STAMP(3);
-      // ---- pass 2: LN + tanh + v-weighted head sum ----
-      const float2 nmu = make_float2(-st.x, -st.x);
-      float2 ea[K], eb[K];
-      float4 vcur = cur.v;
-      chunk_front<K>(cur, nmu, rstd, ea, eb);
+      // ---- pass 2: LN + tanh + v-weighted head sum; per chunk: back A(u-1) | front A(u) | back B(u-1) | front B(u) ----
+      const float2 nmuA = make_float2(-stA.x, -stA.x), nmuB = make_float2(-stB.x, -stB.x);
+      float2 eaA[K], ebA[K], eaB[K], ebB[K];
+      front4<K>(c.ka, c.g, c.b, c.q, nmuA, rsA, eaA, ebA);
+      front4<K>(c.kb, c.g, c.b, c.q, nmuB, rsB, eaB, ebB);
+      float4 vprev = c.v;
 #pragma unroll
-      for (int i = 1; i < 16; ++i) {
-        Chunk<K> nxt;
-        if ((i >> 3) == 0) chunk_load<K, 0>(nxt, kofs[i & 7] + kst, cadr[i & 7], cadr[i & 7] + qgb);
-        else chunk_load<K, 1>(nxt, kofs[i & 7] + kst, cadr[i & 7], cadr[i & 7] + qgb);
-        float2 na[K], nb[K];
-        chunk_front<K>(nxt, nmu, rstd, na, nb);
-        chunk_back<K>(vcur, ea, eb, out);
-        vcur = nxt.v;
-#pragma unroll
-        for (int j = 0; j < K; ++j) { ea[j] = na[j]; eb[j] = nb[j]; }
+      for (int u = 1; u < 8; ++u) {
+        chunk2_load<K>(c, kofs[u] + kst, cadr[u], cadr[u] + qgb);
+        back4<K>(vprev, eaA, ebA, outA);
+        front4<K>(c.ka, c.g, c.b, c.q, nmuA, rsA, eaA, ebA);
+        back4<K>(vprev, eaB, ebB, outB);
+        front4<K>(c.kb, c.g, c.b, c.q, nmuB, rsB, eaB, ebB);
+        vprev = c.v;
       }
-      chunk_back<K>(vcur, ea, eb, out);
+      back4<K>(vprev, eaA, ebA, outA);
+      back4<K>(vprev, eaB, ebB, outB);
       A2_STAMP(4);
       float* pdst = sm_p + (size_t)par * pimg + hp * M + m;
 #pragma unroll
-      for (int j = 0; j < K; ++j) pdst[(size_t)j * kH * M] = expf(out[j] * inv_T - shift);
+      for (int j = 0; j < K; ++j) {
+        const float oa = outA[j] + __shfl_xor_sync(0xffffffffu, outA[j], 8);   // two half heads
+        const float ob = outB[j] + __shfl_xor_sync(0xffffffffu, outB[j], 8);
+        if (hf == 0) {
+          pdst[(size_t)j * kH * M] = expf(oa * inv_T - shift);
+          pdst[(size_t)j * kH * M + 2] = expf(ob * inv_T - shift);
+        }
+      }
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&scored[s]);
@@ -461,14 +494,17 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
     const int cw = warp - NSW;
     const int hd0 = lane >> 4;                                // quad i of this lane: channels 4 (lane + 32 i) .., head hd0 + 2 i
     float4 acc[K][4];
+    float S[K][4];                                            // sum of p over this warp's slices, heads hd0 + 2 i
 #pragma unroll
     for (int j = 0; j < K; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 4; ++i) { acc[j][i] = make_float4(0.f, 0.f, 0.f, 0.f); S[j][i] = 0.f; }
     int g = 0;
-    for (int ii = 0; ii < n_img; ++ii) {
-      const int par = ii & 1;
-      for (int sl = 0; sl < spi; ++sl, ++g) {
+    for (int pos = 0; pos < n_seg; ++pos) {
+      const int ii = seg_of(pos);
+      const int par = pos & 1;
+      const int s_hi = seg_hi(ii);
+      for (int sl = seg_lo(ii); sl < s_hi; ++sl, ++g) {
         if ((g & (kCtxWarps2 - 1)) != cw) continue;
         const int s = g % STAGES;
         A2_STAMP(0);
@@ -492,6 +528,7 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
 #pragma unroll
           for (int j = 0; j < K; ++j) {
             const float4 p = p4[i & 1][j];
+            S[j][i] += (p.x + p.y) + (p.z + p.w);
             float2 lo = make_float2(acc[j][i].x, acc[j][i].y), hi = make_float2(acc[j][i].z, acc[j][i].w);
             lo = __ffma2_rn(make_float2(p.x, p.x), make_float2(kr[i & 1][0].x, kr[i & 1][0].y), lo);
             hi = __ffma2_rn(make_float2(p.x, p.x), make_float2(kr[i & 1][0].z, kr[i & 1][0].w), hi);
@@ -512,14 +549,16 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
 #endif
       }
       // ---- image complete for this warp: hand the partial sums to the finaliser ----
-      mbar_wait(partfree, (uint32_t)((ii & 1) ^ 1));          // the finaliser has read image ii - 1's partials
-      float* pw = sm_part + (size_t)cw * K * kR;
+      mbar_wait(partfree, (uint32_t)((pos & 1) ^ 1));         // the finaliser has read the previous segment's partials
+      float* pw = sm_part + (size_t)cw * K * (kR + kH);
 #pragma unroll
       for (int j = 0; j < K; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           *reinterpret_cast<float4*>(pw + j * kR + (lane + 32 * i) * 4) = acc[j][i];
+          if ((lane & 15) == 0) pw[K * kR + j * kH + hd0 + 2 * i] = S[j][i];
           acc[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          S[j][i] = 0.f;
         }
       __syncwarp();
       if (lane == 0) mbar_arrive(imgdone);
@@ -530,13 +569,19 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
     }
   } else if (warp == NSW + kCtxWarps2) {
     // =========================== finaliser ===========================
-    // Per image: sum p over the positions (fixed order), add the two context partials (warp 0 + warp 1), normalise,
-    // write the context rows and the alignment history.
-    for (int ii = 0; ii < n_img; ++ii) {
-      const int par = ii & 1;
-      const int b = img_lo + ii;
+    // Per image segment: sum p over its positions (fixed order), add the two context partials (warp 0 + warp 1); a
+    // whole image is normalised and written at once, a partial one goes through the global scratch (see top).
+    constexpr int kPartFloats = K * (kR + kH);
+    const int hd0 = lane >> 4;
+    const int m4 = M / 4;
+    auto cta_of = [&](long long x) { return (int)(((x + 1) * G + T_all - 1) / T_all) - 1; };   // CTA that owns slice x
+    for (int pos = 0; pos < n_seg; ++pos) {
+      const int ii = seg_of(pos);
+      const int par = pos & 1;
+      const int b = b0 + ii;
+      const int lo = seg_lo(ii), hi = seg_hi(ii);
       A2_STAMP(0);
-      mbar_wait(imgdone, (uint32_t)(ii & 1));
+      mbar_wait(imgdone, (uint32_t)(pos & 1));
       A2_STAMP(1);
       float4 tot[K][4];
 #pragma unroll
@@ -544,40 +589,121 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 x = *reinterpret_cast<const float4*>(sm_part + j * kR + (lane + 32 * i) * 4);
-          const float4 y = *reinterpret_cast<const float4*>(sm_part + (K + j) * kR + (lane + 32 * i) * 4);
+          const float4 y = *reinterpret_cast<const float4*>(sm_part + K * (kR + kH) + j * kR + (lane + 32 * i) * 4);
           tot[j][i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
         }
+      if (lane < K * kH) sm_inv[lane] = sm_part[K * kR + lane] + sm_part[K * (kR + kH) + K * kR + lane];   // sum p of the segment
       __syncwarp();
       if (lane == 0) mbar_arrive(partfree);
       const float* pim = sm_p + (size_t)par * pimg;
-      const int m4 = M / 4;
-      for (int pr = 0; pr < K * kH; ++pr) {
-        float s = 0.f;
-        for (int i = lane; i < m4; i += 32) {
-          const float4 p4 = *reinterpret_cast<const float4*>(pim + (size_t)pr * M + i * 4);
-          s += (p4.x + p4.y) + (p4.z + p4.w);
-        }
-        s = wsum(s);
-        if (lane == 0) sm_inv[pr] = 1.0f / s;
-      }
-      __syncwarp();
-      const int hd0 = lane >> 4;
+      float* hdst = a.hist_t ? a.hist_t + (size_t)b * K * kH * M : nullptr;   // rows b*K + j, each [8][M]: contiguous, same order as sm_p
+      if (lo == 0 && hi == spi) {
 #pragma unroll
-      for (int j = 0; j < K; ++j)
+        for (int j = 0; j < K; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float inv = sm_inv[j * kH + hd0 + 2 * i];
-          *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * K + j) * a.ld_ctx + (lane + 32 * i) * 4) =
-              make_float4(tot[j][i].x * inv, tot[j][i].y * inv, tot[j][i].z * inv, tot[j][i].w * inv);
-        }
-      if (a.hist_t != nullptr) {
-        float* hdst = a.hist_t + (size_t)b * K * kH * M;      // rows b*K + j, each [8][M]: contiguous, same order as sm_p
-        for (int pr = 0; pr < K * kH; ++pr) {
-          const float inv = sm_inv[pr];
-          for (int i = lane; i < m4; i += 32) {
-            const float4 p4 = *reinterpret_cast<const float4*>(pim + (size_t)pr * M + i * 4);
-            *reinterpret_cast<float4*>(hdst + (size_t)pr * M + i * 4) = make_float4(p4.x * inv, p4.y * inv, p4.z * inv, p4.w * inv);
+          for (int i = 0; i < 4; ++i) {
+            const float inv = 1.0f / sm_inv[j * kH + hd0 + 2 * i];
+            *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * K + j) * a.ld_ctx + (lane + 32 * i) * 4) =
+                make_float4(tot[j][i].x * inv, tot[j][i].y * inv, tot[j][i].z * inv, tot[j][i].w * inv);
           }
+        if (hdst != nullptr) {
+          // 4 (beam, head) rows at a time: 8 independent shared loads in flight per lane
+          for (int pr0 = 0; pr0 < K * kH; pr0 += 4) {
+            float4 v[4][2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if (lane < m4) v[r][0] = *reinterpret_cast<const float4*>(pim + (size_t)(pr0 + r) * M + lane * 4);
+              if (lane + 32 < m4) v[r][1] = *reinterpret_cast<const float4*>(pim + (size_t)(pr0 + r) * M + (lane + 32) * 4);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const float inv = 1.0f / sm_inv[pr0 + r];
+              float* d = hdst + (size_t)(pr0 + r) * M;
+              if (lane < m4) *reinterpret_cast<float4*>(d + lane * 4) = make_float4(v[r][0].x * inv, v[r][0].y * inv, v[r][0].z * inv, v[r][0].w * inv);
+              if (lane + 32 < m4) *reinterpret_cast<float4*>(d + (lane + 32) * 4) = make_float4(v[r][1].x * inv, v[r][1].y * inv, v[r][1].z * inv, v[r][1].w * inv);
+            }
+          }
+        }
+      } else {
+        // part of an image: park the partial results, the last part to arrive combines them
+        const int c_first = cta_of((long long)b * spi), c_last = cta_of((long long)(b + 1) * spi - 1);
+        auto slot_of = [&](int c) { return 2 * c + (((int)((T_all * c / G) / spi) == b) ? 0 : 1); };
+        float* sc = a.scratch + (size_t)slot_of((int)blockIdx.x) * kPartFloats;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sc + j * kR + (lane + 32 * i) * 4) = tot[j][i];
+        if (lane < K * kH) sc[K * kR + lane] = sm_inv[lane];
+        if (hdst != nullptr) {
+          for (int pr = 0; pr < K * kH; ++pr)
+            for (int i = lo + lane; i < hi; i += 32)
+              *reinterpret_cast<float4*>(hdst + (size_t)pr * M + i * 4) = *reinterpret_cast<const float4*>(pim + (size_t)pr * M + i * 4);
+        }
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) {
+          __threadfence();
+          old = atomicAdd(a.counters + b, 1);
+        }
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == c_last - c_first) {
+          __threadfence();
+          if (lane < K * kH) {
+            float s = 0.f;
+            for (int c = c_first; c <= c_last; ++c) s += __ldcg(a.scratch + (size_t)slot_of(c) * kPartFloats + K * kR + lane);
+            sm_inv[lane] = s;
+          }
+          __syncwarp();
+          // parts are added in CTA order; the loads of one beam row (4 quads x 2 parts) are issued together
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            float4 t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = c_first; c <= c_last; c += 2) {
+              const bool two = c + 1 <= c_last;
+              const float* s0 = a.scratch + (size_t)slot_of(c) * kPartFloats + j * kR;
+              const float* s1 = two ? a.scratch + (size_t)slot_of(c + 1) * kPartFloats + j * kR : s0;
+              float4 x[4], y[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                x[i] = __ldcg(reinterpret_cast<const float4*>(s0 + (lane + 32 * i) * 4));
+                y[i] = __ldcg(reinterpret_cast<const float4*>(s1 + (lane + 32 * i) * 4));
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                t[i].x += x[i].x; t[i].y += x[i].y; t[i].z += x[i].z; t[i].w += x[i].w;
+                if (two) { t[i].x += y[i].x; t[i].y += y[i].y; t[i].z += y[i].z; t[i].w += y[i].w; }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float inv = 1.0f / sm_inv[j * kH + hd0 + 2 * i];
+              *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * K + j) * a.ld_ctx + (lane + 32 * i) * 4) =
+                  make_float4(t[i].x * inv, t[i].y * inv, t[i].z * inv, t[i].w * inv);
+            }
+          }
+          if (hdst != nullptr) {
+            // rescale the unnormalised history rows of the whole image, 4 independent 16-byte loads in flight per lane
+            const int n4 = K * kH * m4;
+            for (int i0 = lane; i0 < n4; i0 += 128) {
+              float4 v[4];
+              int idx[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                idx[r] = i0 + 32 * r;
+                if (idx[r] < n4) v[r] = __ldcg(reinterpret_cast<const float4*>(hdst) + idx[r]);
+              }
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                if (idx[r] < n4) {
+                  const float inv = 1.0f / sm_inv[idx[r] / m4];
+                  reinterpret_cast<float4*>(hdst)[idx[r]] = make_float4(v[r].x * inv, v[r].y * inv, v[r].z * inv, v[r].w * inv);
+                }
+              }
+            }
+          }
+          if (lane == 0) a.counters[b] = 0;
         }
       }
       __syncwarp();
@@ -591,16 +717,16 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
     // =========================== query preparation + TMA producer ===========================
     // Lane 0 feeds the ring; the whole warp prepares the queries of image ii + 1 half-way through image ii's slices
     // (the prefetched stages cover the pause), so neither the first key slice nor the queries of an image are late.
-    const float* src = a.keys + (size_t)img_lo * M * kR;
-    auto prep_queries = [&](int ii) {
-      const int par = ii & 1;
-      mbar_wait(&qempty[par], (uint32_t)(((ii >> 1) & 1) ^ 1));   // buffer last used by image ii - 2
+    auto prep_queries = [&](int pos) {
+      const int ii = seg_of(pos);
+      const int par = pos & 1;
+      mbar_wait(&qempty[par], (uint32_t)(((pos >> 1) & 1) ^ 1));   // buffer last used by the segment before the previous one
       float* qc = sm_q + (size_t)par * 2 * K * kR;
       float* qg = qc + K * kR;
       float4 v[K][4];
 #pragma unroll
       for (int j = 0; j < K; ++j) {
-        const float* q = a.lq + (size_t)((img_lo + ii) * K + j) * a.ld_lq + a.q_off + lane * 16;
+        const float* q = a.lq + (size_t)((b0 + ii) * K + j) * a.ld_lq + a.q_off + lane * 16;
 #pragma unroll
         for (int g = 0; g < 4; ++g) v[j][g] = ldg4(q + g * 4);
       }
@@ -628,30 +754,33 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&qfull[par]);
+      if (lane == 0) {
+        // a partial segment scores fewer than spi slices: make up the difference on the buffer's release barrier
+        const int missing = spi - (seg_hi(ii) - seg_lo(ii));
+        if (missing > 0) mbar_arrive_n(&qempty[par], (uint32_t)missing);
+        mbar_arrive(&qfull[par]);
+      }
     };
     prep_queries(0);
-#if COMIC_A2_L2_AHEAD > 0
-    if (lane == 0) {
-      const int npf = n_g < COMIC_A2_L2_AHEAD ? n_g : COMIC_A2_L2_AHEAD;
-      for (int g = 0; g < npf; ++g) tma_prefetch_l2(src + (size_t)g * kSliceFloats, kSliceBytes);
-    }
-#endif
-    for (int g = 0, ii = 0, sl = 0; g < n_g; ++g) {
-      if (lane == 0) {
-        const int s = g % STAGES;
-#if COMIC_A2_L2_AHEAD > 0
-        if (g + COMIC_A2_L2_AHEAD < n_g) tma_prefetch_l2(src + (size_t)(g + COMIC_A2_L2_AHEAD) * kSliceFloats, kSliceBytes);
-#endif
-        mbar_wait(&empty[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
-        mbar_arrive_expect_tx(&full[s], kSliceBytes);
-        tma_bulk_g2s(smem + L::ring + s * kSliceBytes, src + (size_t)g * kSliceFloats, kSliceBytes, &full[s]);
+    int g = 0;
+    for (int pos = 0; pos < n_seg; ++pos) {
+      const int ii = seg_of(pos);
+      const int lo = seg_lo(ii), hi = seg_hi(ii);
+      const float* src = a.keys + ((size_t)(b0 + ii) * spi + lo) * kSliceFloats;
+      bool prepped = false;
+      for (int sl = lo; sl < hi; ++sl, ++g) {
+        if (lane == 0) {
+          const int s = g % STAGES;
+          mbar_wait(&empty[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
+          mbar_arrive_expect_tx(&full[s], kSliceBytes);
+          tma_bulk_g2s(smem + L::ring + s * kSliceBytes, src + (size_t)(sl - lo) * kSliceFloats, kSliceBytes, &full[s]);
+        }
+        if (!prepped && pos + 1 < n_seg && (sl >= spi / 2 || sl == hi - 1)) {
+          __syncwarp();
+          prep_queries(pos + 1);
+          prepped = true;
+        }
       }
-      if (sl == spi / 2 && ii + 1 < n_img) {
-        __syncwarp();
-        prep_queries(ii + 1);
-      }
-      if (++sl == spi) { sl = 0; ++ii; }
     }
   }
 }
@@ -675,7 +804,7 @@ template <int K, int NSW = COMIC_A2_NSW, int STAGES = COMIC_A2_STAGES>
 inline cudaError_t launch_k(const Args& a, int num_sms, int dev, cudaStream_t st) {
   using L = Layout<K, NSW, STAGES>;
   static_assert(STAGES > NSW, "the ring needs more stages than score warps");
-  if (a.M % kPos != 0) return cudaErrorInvalidValue;
+  if (a.M % kPos != 0 || a.M > 256) return cudaErrorInvalidValue;
   const size_t smem = L::bytes(a.M);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   static bool configured[64] = {};
@@ -685,7 +814,9 @@ inline cudaError_t launch_k(const Args& a, int num_sms, int dev, cudaStream_t st
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  const int grid = a.B < num_sms ? a.B : num_sms;
+  const long long total = (long long)a.B * (a.M / kPos);
+  const int grid = total < num_sms ? (int)total : num_sms;
+  if (a.scratch == nullptr || a.counters == nullptr) return cudaErrorInvalidValue;
   attn2_kernel<K, NSW, STAGES><<<grid, L::kThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
@@ -698,6 +829,9 @@ inline cudaError_t launch(const Args& a, int k, int num_sms, int dev, cudaStream
     default: return cudaErrorInvalidValue;
   }
 }
+
+// Global scratch of one launch: floats for up to `num_sms` CTAs (two partial-image slots each) and k <= 3 beams.
+inline size_t scratch_floats(int num_sms) { return (size_t)2 * num_sms * 3 * (kR + kH); }
 
 inline cudaError_t launch_key_stats(const float* keys, long long rows, float* kstats, const float* vvec,
                                     const float* temperature, float* bound, cudaStream_t st) {

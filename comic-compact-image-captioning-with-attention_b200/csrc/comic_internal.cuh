@@ -170,6 +170,8 @@ struct StepBufs {
   float* ctxraw;       // [N][VAL] (context-layer path only)
   float* kstats;       // [N * M][2] per key row: mean, centred sum of squares (attention2.cuh; once per decode call)
   float* abound;       // [8] per-head bound of |score|
+  float* a2_scratch;   // partial contexts / sums of images split across CTAs (attention2.cuh)
+  int* a2_counters;    // [N] arrival counters of split images, zero between launches
 };
 
 struct StepIO {
@@ -194,6 +196,7 @@ struct StepIO {
   float* gates_save; float* alpha_pre; int force_dense;
   // streaming attention (attention2.cuh): key-row statistics / score bound of `keys`, or nullptr when not prepared
   const float* kstats; const float* abound;
+  float* a2_scratch; int* a2_counters;
 };
 
 int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, cudaStream_t st);

@@ -663,6 +663,7 @@ static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb
     aa.gamma = h->w.ln_gamma; aa.beta = h->w.ln_beta; aa.vvec = h->w.attention_v; aa.temperature = h->w.temperature;
     aa.ctx_out = ctx_dst; aa.ld_ctx = ld_ctx; aa.hist_t = io.hist_t; aa.B = B; aa.M = h->M;
     aa.fin_count = io.fin_count; aa.t = io.t; aa.n_rows = io.n_rows; aa.trace = nullptr;
+    aa.scratch = io.a2_scratch; aa.counters = io.a2_counters;
     Prof pf(h, T_SCORES, st);
     COMIC_CHECK_CUDA(a2::launch(aa, k, h->num_sms, h->dev, st));
     return 1;
@@ -709,6 +710,8 @@ static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb
 int attn2_prepare(comic_handle_t h, StepIO& io, const StepBufs& sb, int B, int k, bool masks, cudaStream_t st) {
   io.kstats = nullptr;
   io.abound = nullptr;
+  io.a2_scratch = nullptr;
+  io.a2_counters = nullptr;
   if (!h->attn2 || h->attn2_state < 0 || masks) return COMIC_OK;
   if (h->cfg.alignment != 0 || h->cfg.prob_fn != 0 || h->R != a2::kR || h->H != a2::kH || h->VAL != h->R ||
       io.values != io.keys || k < 1 || k > 3 || h->M % a2::kPos != 0 || B < h->fused_min_images || !sb.kstats)
@@ -729,8 +732,11 @@ int attn2_prepare(comic_handle_t h, StepIO& io, const StepBufs& sb, int B, int k
     h->attn2_state = ok ? 1 : -1;
     if (!ok) return COMIC_OK;
   }
+  COMIC_CHECK_CUDA(cudaMemsetAsync(sb.a2_counters, 0, (size_t)B * sizeof(int), st));
   io.kstats = sb.kstats;
   io.abound = sb.abound;
+  io.a2_scratch = sb.a2_scratch;
+  io.a2_counters = sb.a2_counters;
   return COMIC_OK;
 }
 
@@ -865,6 +871,8 @@ void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_ma
   const bool a2ok = h->cfg.alignment == 0 && h->cfg.prob_fn == 0 && h->R == a2::kR && h->H == a2::kH && h->VAL == h->R;
   sb.kstats = cv.take<float>(a2ok ? (size_t)N * h->M * 2 : 1);    // N >= number of images
   sb.abound = cv.take<float>(a2::kH);
+  sb.a2_scratch = cv.take<float>(a2ok ? a2::scratch_floats(h->num_sms) : 1);
+  sb.a2_counters = cv.take<int>(a2ok ? (size_t)N : 1);
 }
 
 struct LoopBufs {
@@ -1106,7 +1114,7 @@ extern "C" int comic_decode_greedy(comic_handle_t h, const float* keys, const fl
     int cur = t & 1;
     StepIO io{};
     io.keys = keys; io.values = vals;
-    io.kstats = io_a2.kstats; io.abound = io_a2.abound;
+    io.kstats = io_a2.kstats; io.abound = io_a2.abound; io.a2_scratch = io_a2.a2_scratch; io.a2_counters = io_a2.a2_counters;
     io.tok = lb.tok; io.src = nullptr; io.src_limit = N;
     io.c_prev = (t == 0) ? c0 : lb.c[cur];
     io.h_prev = (t == 0) ? h0 : lb.h[cur];
@@ -1185,7 +1193,7 @@ extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const floa
     int cur = t & 1;
     StepIO io{};
     io.keys = keys; io.values = vals;
-    io.kstats = io_a2.kstats; io.abound = io_a2.abound;
+    io.kstats = io_a2.kstats; io.abound = io_a2.abound; io.a2_scratch = io_a2.a2_scratch; io.a2_counters = io_a2.a2_counters;
     io.tok = lb.tok;
     if (t == 0) {
       io.src = lb.src0; io.src_limit = B;        // tile_batch: row n reads image n / k

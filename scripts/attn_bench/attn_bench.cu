@@ -82,6 +82,10 @@ int main(int argc, char** argv) {
   a2::Args a{};
   a.keys = dk; a.kstats = dks; a.bound = dbound; a.lq = dq; a.ld_lq = LQ; a.q_off = QOFF; a.gamma = dg; a.beta = db; a.vvec = dv;
   a.temperature = dT; a.ctx_out = ctx1; a.ld_ctx = R; a.hist_t = hist1; a.B = B; a.M = M; a.n_rows = N;
+  float* dscratch; int* dcount;
+  CK(cudaMalloc(&dscratch, a2::scratch_floats(sms) * 4)); CK(cudaMalloc(&dcount, (size_t)B * 4));
+  CK(cudaMemset(dcount, 0, (size_t)B * 4));
+  a.scratch = dscratch; a.counters = dcount;
 #if COMIC_A2_TRACE
   const int kWarps = COMIC_A2_NSW + a2::kCtxWarps2 + 2;
   size_t ntr = (size_t)sms * kWarps * a2::kTraceSlices * 8;
@@ -114,10 +118,10 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     std::vector<long long> tr(ntr);
     CK(cudaMemcpy(tr.data(), dtr, ntr * 8, cudaMemcpyDeviceToHost));
-    const int grid = B < sms ? B : sms;
+    const int grid = (long long)B * 49 < sms ? B * 49 : sms;
     double sc[5] = {0, 0, 0, 0, 0}; long long nsc = 0;
     double cx[3] = {0, 0, 0}; long long ncx = 0, nfin = 0; double fin = 0;
-    long long span_max = 0; double span_sum = 0;
+    long long span_max = 0; double span_sum = 0; double fz = 0; long long nfz = 0;
     for (int b = 0; b < grid; ++b) {
       long long tmin = (1ll << 62), tmax = 0;
       for (int w = 0; w < kWarps; ++w) {
@@ -134,6 +138,10 @@ int main(int argc, char** argv) {
             if (e[2] != 0) { cx[0] += (double)(e[1] - e[0]); cx[1] += (double)(e[2] - e[1]); ++ncx; }
             if (e[3] != 0 && i > 0 && p[(i - 1) * 8 + 2] != 0) { fin += (double)(e[3] - p[(i - 1) * 8 + 2]); ++nfin; }
             tmax = std::max(tmax, std::max(e[2], e[3]));
+          } else if (w == COMIC_A2_NSW + a2::kCtxWarps2) {
+            if (e[2] == 0) break;
+            tmax = std::max(tmax, e[2]);   // finaliser: end of a segment's finalisation
+            fz += (double)(e[2] - e[1]); ++nfz;
           }
         }
       }
@@ -142,6 +150,7 @@ int main(int argc, char** argv) {
     printf("trace (cycles, averages): CTA span mean %.0f max %lld\n", span_sum / grid, span_max);
     printf("  score warp per slice (%lld slices): grab+setup %.0f | wait key slice %.0f | pass1+stats %.0f | pass2 %.0f | exp+store+arrive %.0f\n",
            nsc, sc[0] / nsc, sc[1] / nsc, sc[2] / nsc, sc[3] / nsc, sc[4] / nsc);
+    printf("  finaliser per segment (%lld): %.0f\n", nfz, nfz ? fz / nfz : 0.0);
     printf("  ctx warp per slice (%lld): wait scored %.0f | accumulate+release %.0f | image finalise %.0f (x%lld)\n", ncx, cx[0] / ncx,
            cx[1] / ncx, nfin ? fin / nfin : 0.0, nfin);
   }
