@@ -28,7 +28,8 @@ for _p in (ROOT, os.path.join(ROOT, 'oracle')):
 
 import numpy as np  # noqa: E402
 
-METRIC = 'captions/sec COMIC-256 beam-3'
+METRIC = 'captions/sec COMIC-256 beam-3'          # --workload word reports METRIC_WORD instead
+METRIC_WORD = 'captions/sec baseline word model (V=10,000, no fm projection, 1 head) beam-3'
 UNIT = 'captions/s'
 
 
@@ -137,6 +138,21 @@ def cpu_reference_step(c, W, images, beam):
     return res['T']
 
 
+def time_cpu_single_thread(c, W, n_images, beam):
+    """The same NumPy restatement limited to ONE BLAS / OpenMP thread, bounded sample."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        return None
+    rng = np.random.default_rng(124)
+    img = rng.uniform(-1, 1, (n_images, 224, 224, 3)).astype(np.float32)
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        cpu_reference_step(c, W, img, beam)
+        dt = time.perf_counter() - t0
+    return n_images / dt
+
+
 def time_cpu(c, W, n_images, beam, steps, warmup):
     rng = np.random.default_rng(123)
     img = rng.uniform(-1, 1, (n_images, 224, 224, 3)).astype(np.float32)
@@ -160,7 +176,8 @@ def run_reference(args):
     cores = os.cpu_count()
     val, sec = time_cpu(c, W, args.ref_batch, args.beam, args.steps, max(args.warmup, 1))
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': METRIC if args.workload == 'comic256' else METRIC_WORD, 'value': val, 'unit': UNIT,
+        'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(args.workload, args.batch, args.beam, c),
@@ -303,13 +320,21 @@ def run_ours(args):
     host_images2 = torch.empty((B, 224, 224, 3), dtype=torch.float32).pin_memory()
     host_images2.copy_(host_images.flip(0))
 
-    def e2e_loop(n):
-        """n batches through the public pipelined inference loop (CaptionModel.run_stream): every batch is
-        copied from pinned host memory and its captions + attention maps are read back to the host."""
+    # raw-pixel variant of the same batches: uint8, what an image decoder hands over (77 MB instead of 308 MB per step)
+    host_u8 = [((h + 1.0) * 127.5).clamp_(0, 255).to(torch.uint8).pin_memory() for h in (host_images, host_images2)]
+
+    def e2e_loop(n, raw_pixels=True, maps=False):
+        """n batches through the public pipelined inference loop (CaptionModel.run_stream), host buffers in, host
+        buffers out.  raw_pixels: uint8 pixels cross PCIe and the reference's evaluation pre-processing runs on the
+        device; maps: the top-beam attention maps come back too (only needed with `save_attention_maps`,
+        src/infer_fn.py:169-171).  (False, True) is round 1's variant: fp32 images in, fp32 maps out."""
+        src = host_u8 if raw_pixels else (host_images, host_images2)
+        model.collect_attention_maps = maps
         got, out = 0, None
-        for out in model.run_stream((host_images if j % 2 == 0 else host_images2) for j in range(n)):
+        for out in model.run_stream(src[j % 2] for j in range(n)):
             got += int(out[0].shape[0])
         assert got == n * B
+        model.collect_attention_maps = True
         return out
 
     # ---- kernel-class breakdown (outside the timed region) -> dominant kernel
@@ -348,13 +373,21 @@ def run_ours(args):
     from comic_b200.engine import executed_steps
     T_exec = executed_steps(r['T'])
 
-    # ---- timed region 2: end to end through CaptionModel.run from pinned host memory
+    # ---- timed region 2: end to end through CaptionModel.run_stream from pinned host memory
     out = e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
     out = e2e_loop(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    barrier()
+    # round 1's variant for continuity: fp32 images in, fp32 attention maps out
+    out_f = e2e_loop(2, raw_pixels=False, maps=True)
+    barrier()
+    t0 = time.perf_counter()
+    out_f = e2e_loop(args.steps, raw_pixels=False, maps=True)
+    torch.cuda.synchronize()
+    e2e_f_s = time.perf_counter() - t0
     barrier()
     # the same K batches one blocking CaptionModel.run call at a time (no copy/compute overlap)
     t0 = time.perf_counter()
@@ -363,13 +396,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_serial_s = time.perf_counter() - t0
     barrier()
-    h2d = host_images.numel() * 4
-    d2h = int(out[0].nbytes + out[1].nbytes)
+    h2d = host_u8[0].numel()
+    d2h = int(out[0].nbytes)
+    h2d_f = host_images.numel() * 4
+    d2h_f = int(out_f[0].nbytes + out_f[1].nbytes)
 
-    t_dev = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=eng.device)
+    t_dev = torch.tensor([ms_total, e2e_s * 1e3, e2e_f_s * 1e3], dtype=torch.float64, device=eng.device)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = [float(x) for x in t_dev.tolist()]
+    ms_total, e2e_ms, e2e_f_ms = [float(x) for x in t_dev.tolist()]
 
     if rank == 0:
         peaks = load_peaks()
@@ -391,7 +426,8 @@ def run_ours(args):
                                     'fast': 'tcgen05 bf16x3 + tanh.approx'}[args.precision] if kind == 'flop' else 'fp32'})
         caps = B * world * args.steps
         line = {
-            'metric': METRIC, 'value': caps / (ms_total * 1e-3), 'unit': UNIT, 'n_gpus': world,
+            'metric': METRIC if args.workload == 'comic256' else METRIC_WORD, 'value': caps / (ms_total * 1e-3), 'unit': UNIT,
+            'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'f32': 'f32', 'split': 'f32 storage and accumulation; GEMM / conv operands split into 3 bf16 terms on tcgen05 (bf16x3)',
@@ -405,7 +441,12 @@ def run_ours(args):
             'roofline': roof,
             'e2e': {'value': caps / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps,
-                    'api': 'CaptionModel.run_stream (H2D / compute / D2H pipelined over 3 streams)',
+                    'api': 'CaptionModel.run_stream (H2D / compute / D2H pipelined over 3 streams): uint8 pixels in, '
+                           'evaluation pre-processing on the device, word ids out (attention maps only with '
+                           'save_attention_maps, as inference.run_inference does)',
+                    'fp32_images_and_attention_maps': {'value': caps / (e2e_f_ms * 1e-3), 'unit': UNIT,
+                                                       'h2d_bytes_per_step': h2d_f, 'd2h_bytes_per_step': d2h_f,
+                                                       'ms_per_step': e2e_f_ms / args.steps},
                     'serial_run_ms_per_step': e2e_serial_s * 1e3 / args.steps,
                     'host_cpus_bound': len(numa_cpus) or None},
             'gpu_launches': int(launches),
@@ -417,7 +458,9 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count()
             val, _sec = time_cpu(c, W, args.cpu_sample, beam, 1, 1)
-            line['cpu_baseline'] = {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            st = time_cpu_single_thread(c, W, 4, beam)
+            line['cpu_baseline'] = {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'single_thread_value': st,
+                                    'single_thread_sample': '4 images, same path, BLAS / OpenMP threads limited to 1',
                                     'sample': '%d images, encoder + %d-step beam-%d decode, NumPy oracle on all host cores'
                                               % (args.cpu_sample, T, beam)}
         print(json.dumps(line))

@@ -807,12 +807,11 @@ inline cudaError_t launch_k(const Args& a, int num_sms, int dev, cudaStream_t st
   if (a.M % kPos != 0 || a.M > 256) return cudaErrorInvalidValue;
   const size_t smem = L::bytes(a.M);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static bool configured[64] = {};
-  if (dev < 0 || dev >= 64) return cudaErrorInvalidValue;
-  if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attn2_kernel<K, NSW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  (void)dev;
+  static PerDeviceOnce once;
+  {
+    cudaError_t e = once([&] { return cudaFuncSetAttribute(attn2_kernel<K, NSW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
     if (e != cudaSuccess) return e;
-    configured[dev] = true;
   }
   const long long total = (long long)a.B * (a.M / kPos);
   const int grid = total < num_sms ? (int)total : num_sms;

@@ -625,12 +625,11 @@ static int dispatch_scores(comic_handle_t h, const StepIO& io, const StepBufs& s
 // Fused scores + softmax + context (attention.cuh), one CTA per image.
 template <int R, int H, int MODE, bool FAST, int KB>
 static cudaError_t launch_fused_kb(const AttnArgs& aa, int B, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fused_kernel<R, H, MODE, FAST, KB>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static PerDeviceOnce once;
+  {
+    cudaError_t e = once([&] { return cudaFuncSetAttribute(attn_fused_kernel<R, H, MODE, FAST, KB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   attn_fused_kernel<R, H, MODE, FAST, KB><<<B, kAttnThreads, smem, st>>>(aa);
   return cudaGetLastError();

@@ -22,6 +22,24 @@
 
 namespace comic {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: a process that drives several
+// GPUs (one Engine per device) has to set it once on each.  One flag set per launch-site template instantiation.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  template <typename F>
+  cudaError_t operator()(F&& configure) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return configure();
+    if (done[dev]) return cudaSuccess;
+    e = configure();
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+  }
+};
+
+
 struct ASeg {
   const float* ptr;
   const int* idx;   // row indirection (nullptr = identity); value < 0 or >= idx_limit -> zero row

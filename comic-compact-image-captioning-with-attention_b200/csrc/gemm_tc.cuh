@@ -865,12 +865,11 @@ template <int BN, int STAGES, int AMODE>
 inline cudaError_t launch_one(const typename AParam<AMODE>::type& a, const TcWeight& w, int bn_idx, int M, int N,
                               const Epi& epi, int num_sms, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, false>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BN, STAGES, AMODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+  static PerDeviceOnce once;
+  {
+    cudaError_t e = once([&] { return cudaFuncSetAttribute(gemm_bf16x3_kernel<BN, STAGES, AMODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
   int grid = tiles < num_sms ? tiles : num_sms;
@@ -896,12 +895,11 @@ inline cudaError_t launch_bres(const typename AParam<AMODE>::type& a, const TcWe
                                int num_sms, cudaStream_t st) {
   using L = SmemLayout<64, STAGES, false, NKRES>;
   static_assert(L::TOTAL <= 232448, "resident-panel kernel exceeds the shared memory of an SM");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_bres_kernel<STAGES, NKRES, AMODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+  static PerDeviceOnce once;
+  {
+    cudaError_t e = once([&] { return cudaFuncSetAttribute(gemm_bf16x3_bres_kernel<STAGES, NKRES, AMODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   int tiles = (M + BM - 1) / BM;
   int grid = tiles < num_sms ? tiles : num_sms;
@@ -913,11 +911,10 @@ inline cudaError_t launch_bres(const typename AParam<AMODE>::type& a, const TcWe
 inline cudaError_t launch_stem_halo(const AHalo& a, const TcWeight& w, const Epi& epi, int num_sms, cudaStream_t st) {
   using L = SmemLayout<64, 3, false, 4, true>;
   static_assert(L::TOTAL <= 232448, "halo stem kernel exceeds the shared memory of an SM");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_bres_kernel<3, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+  static PerDeviceOnce once;
+  {
+    cudaError_t e = once([&] { return cudaFuncSetAttribute(gemm_bf16x3_bres_kernel<3, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int tiles = a.nimg * 98;
   const int grid = tiles < num_sms ? tiles : num_sms;
@@ -931,12 +928,11 @@ template <int BN, int STAGES, int AMODE>
 inline cudaError_t launch_pair(const typename AParam<AMODE>::type& a, const TcWeight& w, int half_idx, int M, int N,
                                const Epi& epi, int num_sms, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, true>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_pair_kernel<BN, STAGES, AMODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+  static PerDeviceOnce once;
+  {
+    cudaError_t e = once([&] { return cudaFuncSetAttribute(gemm_bf16x3_pair_kernel<BN, STAGES, AMODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   int tiles = ((N + BN - 1) / BN) * ((M + 2 * BM - 1) / (2 * BM));
   int grid = 2 * tiles < (num_sms & ~1) ? 2 * tiles : (num_sms & ~1);

@@ -729,12 +729,11 @@ static PersistPlan persist_plan(comic_handle_t h, int B, int k, bool greedy) {
 
 template <int H, int KB>
 static cudaError_t launch_persist(const PersistArgs& pa, int G, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(decode_loop_kernel<H, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         222 * 1024);
+  static PerDeviceOnce once;
+  {
+    cudaError_t e = once([&] { return cudaFuncSetAttribute(decode_loop_kernel<H, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         222 * 1024); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   void* args[] = {const_cast<PersistArgs*>(&pa)};
   return cudaLaunchCooperativeKernel((const void*)decode_loop_kernel<H, KB>, dim3(G), dim3(kPT), args, smem, st);

@@ -754,8 +754,8 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
                                    float map_loss_scale, float* loss_out, float* logits_out, float* attn_out,
                                    const comic_decoder_grads_t* grads, void* ws, size_t ws_bytes, void* stream) {
   COMIC_REQUIRE(h && h->bound, COMIC_E_BADARG, "train_fwd_bwd: weights not bound");
-  COMIC_REQUIRE(fm && im_embed && inputs_tm && targets_tm && coef_tm && lens && loss_out && grads, COMIC_E_BADARG,
-                "train_fwd_bwd: null argument");
+  COMIC_REQUIRE(fm && im_embed && inputs_tm && targets_tm && coef_tm && lens && loss_out, COMIC_E_BADARG,
+                "train_fwd_bwd: null argument");   // grads == NULL: forward only (evaluation perplexity)
   COMIC_REQUIRE(B > 0 && T > 0 && T_run > 0 && T_run <= T, COMIC_E_SHAPE, "train_fwd_bwd: bad B=%d T=%d T_run=%d", B, T, T_run);
   COMIC_REQUIRE(h->cfg.alignment == 0 && h->cfg.prob_fn == 0 && !h->cfg.context_layer && h->cfg.init_method == 0 &&
                     !h->cfg.legacy,
@@ -847,6 +847,19 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
   xent_kernel<<<T_run * B, 256, 0, st>>>(tb.lq, LQ, V, targets_tm, coef_tm, lens, B, T_run, T, tb.dlq, tb.rowloss,
                                         logits_out);
   h->launches++;
+  if (grads == nullptr) {
+    // forward only (train_fn._run_eval_loop, src/train_fn.py:320-338): cross-entropy, no gradient, no map loss
+    const int rows_fwd = T_run * B;
+    scalar_sum_kernel<<<1, 32, 0, st>>>(tb.rowloss, rows_fwd, 1.0f, loss_out + 1);
+    h->launches++;
+    if (attn_out) {
+      dim3 g(T_run, B);
+      attn_maps_kernel<<<g, 256, 0, st>>>(tb.apost, T_run, B, h->H, M, attn_out);
+      h->launches++;
+    }
+    COMIC_CHECK_CUDA(cudaGetLastError());
+    return COMIC_OK;
+  }
 
   // ---- transposed weights for the per-step backward GEMMs ----
   transpose(h->w.lstm_kernel, KX, 4 * R, 4 * R, tb.KT, KX, st);

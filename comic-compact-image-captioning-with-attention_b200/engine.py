@@ -481,10 +481,12 @@ class Engine(object):
         loss = torch.zeros(4, dtype=torch.float32, device=self.device)
         logits = self.f32(B, T, d.V) if want_logits else None
         attn = self.f32(B, d.H, T_run, d.M) if want_attn else None
-        g = ComicDecoderGrads()
-        for f in GRAD_FIELDS:
-            t = grad_views.get(f)
-            setattr(g, f, None if t is None else C.c_void_p(t.data_ptr()))
+        g = None
+        if grad_views is not None:                     # None: forward only (evaluation perplexity)
+            g = ComicDecoderGrads()
+            for f in GRAD_FIELDS:
+                t = grad_views.get(f)
+                setattr(g, f, None if t is None else C.c_void_p(t.data_ptr()))
         mk = None
         if masks is not None:
             mk = ComicTrainMasks()
@@ -500,7 +502,7 @@ class Engine(object):
         self._check(self.lib.comic_train_fwd_bwd(
             self._h, _ptr(fm), _ptr(im_embed), B, _ptr(inputs_tm), _ptr(targets_tm), _ptr(coef_tm), _ptr(lens), T,
             int(T_run), None if mk is None else C.byref(mk), float(map_loss_scale), _ptr(loss), _ptr(logits),
-            _ptr(attn), C.byref(g), _ptr(ws), ws.numel(), self.stream()))
+            _ptr(attn), None if g is None else C.byref(g), _ptr(ws), ws.numel(), self.stream()))
         return loss, logits, attn
 
     # -- cnn_finetune (encoder forward-with-tape + backward) ---------------------

@@ -68,6 +68,9 @@ def run_inference(config, curr_ckpt_path, model, filenames, batches):
                 return
             yield b
 
+    # the maps are only ever DUMPED with `save_attention_maps` (infer_fn.py:169-171): without it the decode loop keeps no
+    # alignment history and nothing but the word ids crosses PCIe
+    model.collect_attention_maps = bool(c.save_attention_maps)
     start_time = time.time()
     step = -1
     for step, (word_ids, attn_maps) in enumerate(model.run_stream(limited())):

@@ -49,7 +49,16 @@ class ModelBase(object):
         return self.mode == 'train'
 
     # -- encoder (src/model_base.py:56-104) ----------------------------------
+    # True: decode calls keep the alignment history and return the top-beam attention maps (what the reference's
+    # `sess.run(infer_output)` fetches, src/infer_fn.py:130); False: no history is written or copied -- the
+    # production setting when `save_attention_maps` is off (src/infer_fn.py:169-171 only DUMPS the maps then)
+    collect_attention_maps = True
+
     def _encoder(self, images):
+        if images.dtype == self.engine.torch.uint8:
+            # raw decoded pixels: the reference's evaluation pre-processing on the device
+            # (inception_preprocessing_radix.py:229-235, 270-273)
+            images = self.engine.preprocess_eval(images)
         self.im_embed, self.cnn_fmaps = self.engine.encode(images)
         return self.im_embed, self.cnn_fmaps
 
@@ -92,7 +101,7 @@ class ModelBase(object):
         attention_cell = rops.MultiHeadAttentionWrapperV3(
             deep_output_layer=False, context_layer=c.attn_context_layer, alignments_keep_prob=1.0,
             cell=c.rnn_name, attention_mechanism=cnn_attention, attention_layer_size=None,
-            alignment_history=True, cell_input_fn=None, output_attention=False,
+            alignment_history=self.collect_attention_maps, cell_input_fn=None, output_attention=False,
             initial_cell_state=rnn_init)
         start_id, end_id = self._start_end_ids()
         max_it = self._maximum_iterations()
@@ -120,8 +129,10 @@ class ModelBase(object):
             output_ids, logits, dec_states = rnn_raw_outputs
             logits = logits.transpose(0, 1)
             output_ids = output_ids.transpose(0, 1)
-        # the engine already returns the (reordered, top-beam) map as [B, H, T, M]
+        # the engine already returns the (reordered, top-beam) map as [B, H, T, M]; () when no history was kept
         attn_map = dec_states.alignment_history
+        if isinstance(attn_map, tuple):
+            attn_map = None
         return logits, output_ids, attn_map
 
 
@@ -161,12 +172,13 @@ class CaptionModel(ModelBase):
     def get_global_step(self):
         return 0 if self.trainer is None else self.trainer.global_step
 
-    def train_step(self, images, captions, seed=None, lr=None):
-        """One optimiser step; returns (dec_log_ppl, global_step) like train_fn.py:120."""
+    def train_step(self, images, captions, seed=None, lr=None, dropout=True):
+        """One optimiser step; returns (dec_log_ppl, global_step) like train_fn.py:120.  Dropout on by default
+        (the reference's train graph); `seed` fixes the masks, dropout=False disables them."""
         assert self.mode == 'train'
         eng = self.engine
         images = eng.torch.as_tensor(images).to(eng.device, non_blocking=True)
-        out = self.trainer.step(images, np.asarray(captions), None, seed, lr)
+        out = self.trainer.step(images, np.asarray(captions), None, seed, lr, dropout)
         self.dec_log_ppl = out['loss'][1]
         return self.dec_log_ppl, self.trainer.global_step
 
@@ -175,7 +187,8 @@ class CaptionModel(ModelBase):
         eng = self.engine
         images = eng.torch.as_tensor(images).to(eng.device, non_blocking=True)
         im_embed, fm = eng.encode(images)
-        out = self.trainer.forward_backward(fm, im_embed, np.asarray(captions))
+        # forward only: no gradient buffers are touched, and with train_mode=cnn_finetune no tape is needed
+        out = self.trainer.forward_backward(fm, im_embed, np.asarray(captions), forward_only=True)
         return out['loss'][1]
 
     def restore_model(self, weights):
@@ -204,15 +217,15 @@ class CaptionModel(ModelBase):
         if images is None:
             images = self.batch_ops[0]
         images = torch.as_tensor(images)
-        if images.dtype != torch.float32:
+        if images.dtype not in (torch.float32, torch.uint8):
             images = images.float()
         dev_images = images.to(eng.device, non_blocking=True).contiguous()
         self._encoder(dev_images)
         self._decoder_rnn()
         preds = self._to_host(self.dec_preds, 'preds')
-        attn = self._to_host(self.dec_attn_maps, 'attn')
+        attn = self._to_host(self.dec_attn_maps, 'attn') if self.dec_attn_maps is not None else None
         torch.cuda.current_stream(eng.device).synchronize()
-        return [preds.numpy(), attn.numpy()]
+        return [preds.numpy(), None if attn is None else attn.numpy()]
 
     def run_stream(self, batches, depth=2):
         """The inference loop of src/infer_fn.py:166-184 (`for each batch: sess.run(infer_output)`) as a
@@ -222,7 +235,11 @@ class CaptionModel(ModelBase):
         speed) and the device->host copy of batch i-1's results run while batch i computes, so in
         steady state a batch costs max(compute, H2D, D2H) instead of their sum.  `depth` device
         input buffers / pinned result buffers rotate: a yielded result stays valid until the
-        following `next()`.  Device-resident batches skip the input copy."""
+        following `next()`.  Device-resident batches skip the input copy.
+
+        Batches may be uint8 [B,H,W,3] raw pixels: they cross PCIe as bytes (a quarter of the fp32 volume) and the
+        reference's evaluation pre-processing runs on the device.  With `collect_attention_maps = False` the second
+        element of every result is None and neither history nor maps are written or copied."""
         eng = self.engine
         torch = eng.torch
         dev = eng.device
@@ -236,14 +253,14 @@ class CaptionModel(ModelBase):
         def stage_in(i, images):
             sl = slots[i % depth]
             images = torch.as_tensor(images)
-            if images.dtype != torch.float32:
+            if images.dtype not in (torch.float32, torch.uint8):
                 images = images.float()
             if images.is_cuda:
                 sl['dev'], sl['ev_in'] = images.contiguous(), None
                 return
             buf = sl.get('dev_in')
-            if buf is None or buf.shape != images.shape:
-                buf = sl['dev_in'] = torch.empty(images.shape, dtype=torch.float32, device=dev)
+            if buf is None or buf.shape != images.shape or buf.dtype != images.dtype:
+                buf = sl['dev_in'] = torch.empty(images.shape, dtype=images.dtype, device=dev)
             with torch.cuda.stream(s_in):
                 if sl.get('ev_comp') is not None:
                     s_in.wait_event(sl['ev_comp'])          # the slot's previous batch has been consumed
@@ -264,17 +281,20 @@ class CaptionModel(ModelBase):
                 comp.wait_event(sl['ev_in'])
             self._encoder(sl['dev'])
             self._decoder_rnn()
-            preds, attn = self.dec_preds.contiguous(), self.dec_attn_maps.contiguous()
+            preds = self.dec_preds.contiguous()
+            attn = self.dec_attn_maps.contiguous() if self.dec_attn_maps is not None else None
             ev = torch.cuda.Event()
             ev.record(comp)
             sl['ev_comp'] = ev
-            hp, ha = pinned(sl, 'h_preds', preds), pinned(sl, 'h_attn', attn)
+            hp = pinned(sl, 'h_preds', preds)
+            ha = pinned(sl, 'h_attn', attn) if attn is not None else None
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev)
                 hp.copy_(preds, non_blocking=True)
-                ha.copy_(attn, non_blocking=True)
                 preds.record_stream(s_out)
-                attn.record_stream(s_out)
+                if attn is not None:
+                    ha.copy_(attn, non_blocking=True)
+                    attn.record_stream(s_out)
                 evo = torch.cuda.Event()
                 evo.record(s_out)
             sl['ev_out'], sl['out'] = evo, (hp, ha)
@@ -282,7 +302,7 @@ class CaptionModel(ModelBase):
         def finish(i):
             sl = slots[i % depth]
             sl['ev_out'].synchronize()
-            return [sl['out'][0].numpy(), sl['out'][1].numpy()]
+            return [sl['out'][0].numpy(), None if sl['out'][1] is None else sl['out'][1].numpy()]
 
         it = iter(batches)
         cur = next(it, None)
@@ -337,7 +357,7 @@ class CaptionModel_SCST(ModelBase):
         self.dec_preds_beam, self.dec_preds_greedy = cap_beam, cap_greedy
         return cap_beam, cap_greedy
 
-    def train_scst(self, images, captions, rewards, seed=None, lr=None):
+    def train_scst(self, images, captions, rewards, seed=None, lr=None, dropout=True):
         """images: the k-times tiled batch of train_fn.py:251 (or None to reuse the features of the
         last `sample()` of the shared model, repeated k times)."""
         c, eng, tr = self._config, self.engine, self.trainer
@@ -348,10 +368,10 @@ class CaptionModel_SCST(ModelBase):
             raise ValueError('images required')
         captions = np.asarray(captions)
         masks, keeps = None, (1.0, 1.0, 1.0)
-        if seed is not None:
+        if dropout:
             from .train import process_inputs
             lens = process_inputs(captions, c.token_type)[3]
-            masks, keeps = tr.make_masks(fm.shape[0], int(lens.max()), seed)
+            masks, keeps = tr.make_masks(fm.shape[0], int(lens.max()), tr.dropout_seed(seed))
         out = tr.forward_backward(fm, im_embed, captions, np.asarray(rewards, np.float32), masks, keeps)
         tr.apply_gradients(lr)
         return out['loss'][1]

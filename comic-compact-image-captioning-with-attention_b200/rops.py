@@ -88,6 +88,7 @@ class MultiHeadAttentionWrapperV3(object):
         if bool(context_layer) != eng.dims.context_layer:
             raise ValueError('context_layer does not match the engine configuration')
         self._attention_mechanism = attention_mechanism
+        self._alignment_history = bool(alignment_history)    # False: the decode loops keep no alignment history at all
         self._alignments_keep_prob = alignments_keep_prob
         self._initial_cell_state = initial_cell_state
         self._engine = eng
@@ -150,12 +151,13 @@ def rnn_decoder_beam_search(cell, embedding_fn, output_layer, batch_size, beam_s
         raise ValueError('Non-matching batch sizes between the memory (encoder output) and the query '
                          '(decoder output).')                           # ops_rnn.py:679-690
     c0, h0 = cell._initial_cell_state
+    want_attn = getattr(cell, '_alignment_history', True)
     r = eng.decode_beam(am.keys, am.values, c0, h0, int(beam_size), float(length_penalty_weight),
-                        int(maximum_iterations))
+                        int(maximum_iterations), want_attn=want_attn)
     T = executed_steps(r['T'])                       # the one device->host sync of a decode call
     r['T_host'] = T
     state = AttentionWrapperState(cell_state=None, attention=None, time=T, alignments=None,
-                                  alignment_history=r['attn'][:, :, :T, :], attention_state=None)
+                                  alignment_history=r['attn'][:, :, :T, :] if want_attn else (), attention_state=None)
     state_extra = dict(parent_ids=r['parent_ids'][:T], step_ids=r['step_ids'][:T], lengths=r['lengths'])
     rnn_decoder_beam_search.last_extra = state_extra
     return r['predicted_ids'][:T], r['scores'][:T], state
@@ -175,8 +177,9 @@ def rnn_decoder_search(cell, embedding_fn, output_layer, batch_size, maximum_ite
         raise ValueError('Non-matching batch sizes between the memory (encoder output) and the query '
                          '(decoder output).')
     c0, h0 = cell._initial_cell_state
-    r = eng.decode_greedy(am.keys, am.values, c0, h0, int(maximum_iterations))
+    want_attn = getattr(cell, '_alignment_history', True)
+    r = eng.decode_greedy(am.keys, am.values, c0, h0, int(maximum_iterations), want_attn=want_attn)
     T = executed_steps(r['T'])
     state = AttentionWrapperState(cell_state=None, attention=None, time=T, alignments=None,
-                                  alignment_history=r['attn'][:, :, :T, :], attention_state=None)
+                                  alignment_history=r['attn'][:, :, :T, :] if want_attn else (), attention_state=None)
     return r['ids'][:T], r['logits'][:T], state

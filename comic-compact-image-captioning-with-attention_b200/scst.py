@@ -272,6 +272,11 @@ class CaptionScorer(object):
     """common/scst/scorers.py:30-171 (`captionScorer`)."""
 
     def __init__(self, path_to_cached_tokens, metric_weights):
+        # the reference also offers plain 'cider' (common/scst/scorers.py:36-39); it is not built here, and a
+        # positive weight on a metric that contributes nothing would silently change the reward
+        for key, wt in dict(metric_weights).items():
+            if key not in ('ciderD', 'bleu') and np.amax(np.asarray(wt, np.float64)) > 0:
+                raise NotImplementedError("metric '%s' is not built (ciderD and bleu are)" % key)
         self._ciderD = CiderD(df=path_to_cached_tokens)
         self.weights = metric_weights
 
@@ -339,7 +344,7 @@ def sample_captions(engine, config, images, beam, max_length=20):
     return cap_beam, cap_greedy, im_embed, fm
 
 
-def scst_step(trainer, scorer, images, refs, seed=None, lr=None):
+def scst_step(trainer, scorer, images, refs, seed=None, lr=None, dropout=True):
     """train_fn_scst loop body.  images [B,224,224,3] device tensor; refs: list (per image) of
     reference caption strings.  Returns dict(loss, rewards, sc_sample, sc_greedy, hypos)."""
     c, eng = trainer.c, trainer.engine
@@ -358,10 +363,10 @@ def scst_step(trainer, scorer, images, refs, seed=None, lr=None):
     fm_t = fm.repeat(k, 1, 1)
     im_t = im_embed.repeat(k, 1)
     masks, keeps = None, (1.0, 1.0, 1.0)
-    if seed is not None:
+    if dropout:
         from .train import process_inputs
         lens = process_inputs(hypos_idx, c.token_type)[3]
-        masks, keeps = trainer.make_masks(fm_t.shape[0], int(lens.max()), seed)
+        masks, keeps = trainer.make_masks(fm_t.shape[0], int(lens.max()), trainer.dropout_seed(seed))
     out = trainer.forward_backward(fm_t, im_t, hypos_idx, rewards, masks, keeps)
     out['lr'] = trainer.apply_gradients(lr)
     out.update(rewards=rewards, sc_sample=sc_sample, sc_greedy=sc_greedy, hypos=hypos, greedy=hyp_greedy)

@@ -69,6 +69,13 @@ class Trainer(object):
         self.finetune_cnn = c.train_mode == 'cnn_finetune'
         if self.finetune_cnn and not with_cnn:
             raise ValueError('train_mode=cnn_finetune needs the CNN weights')
+        # options the reference accepts but this path does not build: refuse instead of silently training differently
+        if getattr(c, 'rnn_recurr_dropout', False):
+            raise NotImplementedError('rnn_recurr_dropout (variational recurrent dropout) is not built')
+        if float(getattr(c, 'clip_gradient_norm', 0) or 0) != 0:
+            raise NotImplementedError('clip_gradient_norm != 0 is not built (the reference default is 0)')
+        if getattr(c, 'optimiser', 'adam') != 'adam':
+            raise NotImplementedError("optimiser '%s' is not built (adam only)" % c.optimiser)
         self.engine = eng = engine or Engine(c)
         torch = self.torch = eng.torch
         self.shapes = dict(wts.decoder_shapes(c))
@@ -117,6 +124,14 @@ class Trainer(object):
         o, n, shp = self.offsets[name]
         return self.grads[o:o + n].view(shp if len(shp) else (1,))
 
+    def dropout_seed(self, seed=None):
+        """Seed of this step's dropout masks: explicit, or derived from `config.rand_seed` and the global step so that
+        the default training call is regularised like the reference's (DropoutWrapper keep 0.65 in / out,
+        attention-map keep 0.9: src/model_base.py:636-648, common/ops_rnn.py:696-701)."""
+        if seed is not None:
+            return int(seed)
+        return (int(getattr(self.c, 'rand_seed', 48964896)) * 1000003 + self.global_step) & 0x7fffffff
+
     def make_masks(self, B, T_run, seed):
         """Seeded Philox dropout masks (DropoutWrapper in/out, attention-map dropout)."""
         c, d, eng = self.c, self.engine.dims, self.engine
@@ -131,9 +146,10 @@ class Trainer(object):
 
     # -- one fwd + bwd (+ optimiser) ---------------------------------------------
     def forward_backward(self, fm, im_embed, captions, rewards=None, masks=None, keeps=(1.0, 1.0, 1.0),
-                         want_logits=False, want_attn=False, images=None):
+                         want_logits=False, want_attn=False, images=None, forward_only=False):
         """captions [B,L] int32 host array.  Returns dict(loss=[total, xe, map, reg] device tensor, ...);
-        gradients land in self.grads."""
+        gradients land in self.grads.  forward_only: cross-entropy only (loss[1]); no backward, no L2 term, and
+        self.grads is left untouched (the evaluation graph of train_fn._run_eval_loop)."""
         c, eng, torch = self.c, self.engine, self.torch
         inputs, targets, wmask, lens = process_inputs(captions, c.token_type)
         coef = loss_coefficients(wmask, rewards)
@@ -144,10 +160,17 @@ class Trainer(object):
         targets_tm = to(targets.T, torch.int32)
         coef_tm = to(coef.T, torch.float32)
         lens_d = to(lens, torch.int32)
+        if forward_only:
+            loss, logits, attn = eng.train_fwd_bwd(fm.contiguous(), im_embed.contiguous(), inputs_tm, targets_tm, coef_tm,
+                                                   lens_d, T_run, None, masks, keeps, c.rnn_map_loss_scale,
+                                                   want_logits, want_attn)
+            loss[0:1] = loss[1:2]
+            return dict(loss=loss, logits=logits, attn=attn, T_run=T_run)
         self.grads.zero_()
         loss, logits, attn = eng.train_fwd_bwd(fm.contiguous(), im_embed.contiguous(), inputs_tm, targets_tm, coef_tm,
                                                lens_d, T_run, self.grad_views, masks, keeps, c.rnn_map_loss_scale,
                                                want_logits, want_attn)
+        mult = 1.0
         if self.finetune_cnn:
             if images is None:
                 raise ValueError('cnn_finetune: forward_backward needs the images of the last encode_train')
@@ -155,10 +178,12 @@ class Trainer(object):
             dfm, demb = eng.train_encoder_grads(fm.shape[0], T_run)
             eng.encode_bwd(images, dfm, demb, self.cnn_grad_w, self.cnn_grad_b)
             mult = float(getattr(c, 'cnn_grad_multiplier', 1.0))
-            if mult != 1.0:                                  # gradient_multipliers (src/model_base.py:387-401)
-                self.grads[self.n_decoder_flat:].mul_(mult)
         if c.l2_decay > 0:
             eng.l2_regularise(self.params, self.grads, c.l2_decay, loss[3:4])
+        if mult != 1.0:
+            # slim gradient_multipliers scale the gradient of the TOTAL loss, L2 term included, for the CNN
+            # variables (src/model_base.py:380-401)
+            self.grads[self.n_decoder_flat:].mul_(mult)
         loss[0:1] = loss[1:2] + loss[2:3] + loss[3:4]
         return dict(loss=loss, logits=logits, attn=attn, T_run=T_run)
 
@@ -178,9 +203,10 @@ class Trainer(object):
             eng.refresh_packed()
         return lr
 
-    def step(self, images, captions, rewards=None, seed=None, lr=None):
+    def step(self, images, captions, rewards=None, seed=None, lr=None, dropout=True):
         """One `sess.run([train_op])`: encoder forward (frozen, or with tape when fine-tuning), decoder
-        fwd+bwd (+ encoder backward), optimiser."""
+        fwd+bwd (+ encoder backward), optimiser.  Dropout is ON as in the reference's train graph (masks seeded by
+        `seed`, default derived from config.rand_seed and the global step); dropout=False runs without masks."""
         eng = self.engine
         if self.finetune_cnn:
             images = eng.to_dev(images)
@@ -189,9 +215,9 @@ class Trainer(object):
             im_embed, fm = eng.encode(images)
         B = im_embed.shape[0]
         masks, keeps = None, (1.0, 1.0, 1.0)
-        if seed is not None:
+        if dropout:
             _, _, _, lens = process_inputs(captions, self.c.token_type)
-            masks, keeps = self.make_masks(B, int(lens.max()), seed)
+            masks, keeps = self.make_masks(B, int(lens.max()), self.dropout_seed(seed))
         out = self.forward_backward(fm, im_embed, captions, rewards, masks, keeps,
                                     images=images if self.finetune_cnn else None)
         out['lr'] = self.apply_gradients(lr)

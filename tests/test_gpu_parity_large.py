@@ -173,3 +173,32 @@ def test_encoder_legacy_head(torch_mod, precision):
     o_emb, o_fm, _ = I.encoder(img, W, c)
     assert rel_err(fm.cpu().numpy(), o_fm) < 2e-4
     assert rel_err(emb.cpu().numpy(), o_emb) < 2e-4
+
+
+def test_run_stream_raw_pixels_and_optional_attention_maps(torch_mod):
+    """The pipelined inference loop fed with uint8 pixels (pre-processing on the device) returns what `run` returns
+    for the host-pre-processed fp32 images; with collect_attention_maps off it returns the same captions and no maps."""
+    import inception_v1_oracle as I
+    from comic_b200.model import CaptionModel
+    c = comic_config(infer_max_length=2)
+    W = make_weights(c)
+    m = CaptionModel(c, 'infer', batch_ops=None, weights=W)
+    rng = np.random.default_rng(17)
+    u8 = [rng.integers(0, 256, (3, 240, 320, 3), dtype=np.uint8) for _ in range(3)]
+    refs = []
+    for x in u8:
+        p, a = m.run(I.preprocess_eval(x))
+        refs.append((p.copy(), a.copy()))
+    outs = [(p.copy(), a.copy()) for p, a in m.run_stream(iter(u8))]
+    assert len(outs) == 3
+    for (p, a), (rp, ra) in zip(outs, refs):
+        np.testing.assert_array_equal(p, rp)
+        np.testing.assert_array_equal(a, ra)
+    m.collect_attention_maps = False
+    outs = [(p.copy(), a) for p, a in m.run_stream(iter(u8))]
+    for (p, a), (rp, _) in zip(outs, refs):
+        assert a is None
+        np.testing.assert_array_equal(p, rp)
+    p, a = m.run(u8[0])
+    assert a is None
+    np.testing.assert_array_equal(p, refs[0][0])

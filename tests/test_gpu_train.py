@@ -186,3 +186,31 @@ def test_caption_model_train_and_eval_surface(torch_mod):
     assert p1 < p0
     preds, attn = m_infer.run(img)                       # shares the updated variables
     assert preds.shape[0] == 3 and attn.shape[:2] == (3, 8)
+
+
+def test_default_train_step_applies_dropout_and_eval_is_forward_only(torch_mod):
+    """`train_step(images, captions)` regularises like the reference's train graph (DropoutWrapper +
+    attention-map dropout on by default); `eval_step` runs forward only -- it works under train_mode=cnn_finetune
+    and leaves the trainer's gradient buffer alone."""
+    from comic_b200.model import CaptionModel
+    from _common import images
+    c = comic_config(train_mode='cnn_finetune', max_step=20)
+    W = make_weights(c)
+    _, _, _, caps, _, _ = _train_case(c, B=2, L=6, seed=3, dropout=False)
+    img = images(2, seed=4)
+    m = CaptionModel(c, 'train', weights=W)
+    m_eval = CaptionModel(c, 'eval', reuse=True, share=m)
+    tr = m.trainer
+    # same weights, same data: the default call draws masks, dropout=False does not
+    eng = tr.engine
+    im_embed, fm = eng.encode(eng.to_dev(img))
+    plain = float(tr.forward_backward(fm, im_embed, np.asarray(caps), forward_only=True)['loss'][1].item())
+    ev = float(m_eval.eval_step(img, caps).item())
+    assert abs(ev - plain) < 1e-6 * max(1.0, abs(plain))
+    tr.grads.fill_(3.0)
+    m_eval.eval_step(img, caps)
+    assert float(tr.grads.min().item()) == 3.0 and float(tr.grads.max().item()) == 3.0
+    ppl_default, _ = m.train_step(img, caps, lr=0.0)
+    ppl_nodrop, _ = m.train_step(img, caps, lr=0.0, dropout=False)
+    assert abs(float(ppl_nodrop.item()) - plain) < 2e-4 * max(1.0, abs(plain))
+    assert abs(float(ppl_default.item()) - plain) > 1e-3 * max(1.0, abs(plain))

@@ -217,3 +217,28 @@ def test_run_inference_writes_the_reference_result_files(tmp_path):
     assert inf.image_id_from_filename('COCO_test2014_000000000123.jpg') == 123
     with pytest.raises(ValueError):
         inf.image_id_from_filename('nodigits.jpg')
+
+
+def test_unsupported_training_options_are_refused():
+    """Options the reference accepts but this path does not build raise instead of silently training differently
+    (ADVICE r1): recurrent dropout, gradient clipping, non-Adam optimisers, the plain 'cider' reward."""
+    from comic_b200.train import Trainer
+    from comic_b200 import scst as S
+    for kw in (dict(rnn_recurr_dropout=True), dict(clip_gradient_norm=5.0), dict(optimiser='sgd')):
+        c = conf.make_config(train_mode='decoder', **kw)
+        with pytest.raises(NotImplementedError):
+            Trainer(c, {})
+    with pytest.raises(NotImplementedError):
+        S.CaptionScorer({'document_frequency': {}, 'ref_len': 1}, dict(ciderD=1.0, cider=0.5))
+    S.CaptionScorer({'document_frequency': {}, 'ref_len': 1}, dict(ciderD=1.0, cider=0.0, bleu=[0, 0, 0, 2]))
+
+
+def test_default_dropout_seed_follows_rand_seed_and_step():
+    from comic_b200.train import Trainer
+    t = Trainer.__new__(Trainer)
+    t.c = conf.make_config(train_mode='decoder')
+    t.global_step = 0
+    s0 = t.dropout_seed()
+    t.global_step = 1
+    s1 = t.dropout_seed()
+    assert s0 != s1 and 0 <= s0 < 2 ** 31 and t.dropout_seed(7) == 7
