@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument('--ref-batch', type=int, default=32, help='images per step of the CPU reference arm')
     ap.add_argument('--cpu-sample', type=int, default=96, help='images of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the train block (BASELINE.json configs 3-5)')
+    ap.add_argument('--train-steps', type=int, default=10)
     ap.add_argument('--precision', default='split', choices=['f32', 'split', 'fast'],
                     help='engine arithmetic mode (include/comic_b200.h comic_set_precision)')
     ap.add_argument('--opt', action='append', default=[], help='engine tunable name=value (Engine.set_option)')
@@ -406,6 +408,30 @@ def run_ours(args):
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms, e2e_f_ms = [float(x) for x in t_dev.tolist()]
 
+    # ---- train block: BASELINE.json configs 3-5 on the same ranks (one NCCL sum all-reduce of the flat gradient per step)
+    train = None
+    if not args.no_train and args.workload == 'comic256':
+        sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+        import bench_train
+        train = {}
+        # cnn_finetune runs in the arithmetic mode its gradient parity test verifies (tests/test_gpu_train_cnn.py: the
+        # tape forward and the backward GEMMs in f32); the bf16x3 number is reported beside it, unverified
+        for key, mode, batch, prec in (('decoder', 'decoder', 32, args.precision), ('cnn_finetune', 'cnn_finetune', 32, 'f32'),
+                                       ('cnn_finetune_bf16x3_unverified', 'cnn_finetune', 32, args.precision),
+                                       ('scst', 'scst', 10, args.precision)):
+            r = bench_train.run_mode(mode, batch, args.train_steps, 3, prec)
+            # algorithmic bytes of one teacher-forced fwd + bwd step (~3x the forward): per time step the
+            # decoder weights (12.08 MB) and the batch's keys (B x 401,408 B) stream once forward and twice backward
+            if mode != 'scst':
+                steps_t = 41
+                alg = 3 * steps_t * (12.08e6 + batch * 401408)
+                r['roofline'] = {'bound': 'hbm', 'achieved': alg / (r['ms_per_step'] * 1e-3) / 1e9, 'peak': load_peaks()['hbm'],
+                                 'unit': 'GB/s', 'frac': alg / (r['ms_per_step'] * 1e-3) / 1e9 / load_peaks()['hbm'],
+                                 'traffic': None, 'note': 'decoder part only; launch-bound (%d launches per step)' % r['gpu_launches_per_step']}
+            r['cpu_baseline'] = None       # the NumPy oracle restates the forward and the losses; gradients are checked against
+                                           # fp64 autograd in tests/, not timed
+            train[key] = r
+
     if rank == 0:
         peaks = load_peaks()
         work, kind = algorithmic_work(dominant, eng, B, beam, T_exec)
@@ -463,6 +489,8 @@ def run_ours(args):
                                     'single_thread_sample': '4 images, same path, BLAS / OpenMP threads limited to 1',
                                     'sample': '%d images, encoder + %d-step beam-%d decode, NumPy oracle on all host cores'
                                               % (args.cpu_sample, T, beam)}
+        if train is not None:
+            line['train'] = train
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
