@@ -63,7 +63,7 @@ extern "C" int comic_create(const comic_cfg_t* cfg, comic_handle_t* out) {
   memset(&h->w, 0, sizeof(h->w));
   int rc = decoder_configure();
   if (rc) { delete h; return rc; }
-  if (cudaMallocHost(&h->attn2_host, 8 * sizeof(float)) != cudaSuccess) {   // see attn2_prepare (decoder.cu)
+  if (cudaMallocHost(&h->attn2_host, 16 * sizeof(float)) != cudaSuccess) {   // see attn2_prepare (decoder.cu)
     h->attn2_host = nullptr;
     (void)cudaGetLastError();
   }

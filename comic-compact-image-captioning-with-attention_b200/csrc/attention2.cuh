@@ -35,6 +35,14 @@
 //
 // Numerics are the old kernel's: variance from (skk + sqq + 2 <k, qc>) / R, tanh(y) =
 // 1 - 2 / (2^(2 log2e y) + 1) with ex2.approx / one rcp.approx per four elements.
+//
+// No clamp: the four reciprocals of a chunk share one MUFU.RCP through the product x0 x1 x2 x3, x = 2^y' + 1, which
+// attention.cuh keeps finite with fminf(y', 30) -- one instruction per element.  Here the exponent is shifted
+// instead: x'' = 2^(y' - s) + 2^-s = 2^-s x with s folded into beta' and 2^-s into v'.  Layer norm bounds the sum of
+// any four normalised channels by sqrt(4 R), so sum(y') <= 2 log2e (gmax sqrt(4 R) + 4 bmax) =: Y4; any s with
+// Y4 - 4 s <= 126 and 4 s <= 126 keeps the product inside the fp32 range in both directions.  key_stats_kernel
+// picks the smallest such s from max |gamma|, max |beta| and reports when none exists (the host then takes the
+// round-1 kernel).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -118,12 +126,13 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 
 // ---------------------------------------------------------------------------------------------
 // Once per decode call: per key row mean and centred sum of squares; per head score bound.
-//   kstats [rows][2];  bound [8] = sum_{c in head} |v_c| / |T|
+//   kstats [rows][2];  bound [0..7] = sum_{c in head} |v_c| / |T|, bound[8] = exponent shift s, bound[9] = s feasible
 // One warp per row, lane owns 16 contiguous channels (same reduction order as attention.cuh).
 // ---------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256) key_stats_kernel(const float* __restrict__ keys, long long rows,
                                                                float* __restrict__ kstats, const float* __restrict__ vvec,
                                                                const float* __restrict__ temperature,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                float* __restrict__ bound) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -133,6 +142,22 @@ static __global__ void __launch_bounds__(256) key_stats_kernel(const float* __re
     float s = fabsf(vvec[hd * kD + lane]) + fabsf(vvec[hd * kD + 32 + lane]);
     s = wsum(s);
     if (lane == 0) bound[hd] = s / fabsf(temperature[0]);
+    if (hd == 0) {
+      // exponent shift of the clamp-free reciprocal product (see top): bound[8] = s, bound[9] = 1 if feasible
+      float gmax = 0.f, bmax = 0.f;
+      for (int c = lane; c < kR; c += 32) {
+        gmax = fmaxf(gmax, fabsf(gamma[c]));
+        bmax = fmaxf(bmax, fabsf(beta[c]));
+      }
+      gmax = wmax(gmax);
+      bmax = wmax(bmax);
+      const float y4 = kTwoLog2e * (gmax * sqrtf(4.0f * kR) + 4.0f * bmax) * 1.0001f + 1.0f;   // small margin for rounding
+      float sh = ceilf(fmaxf(0.f, (y4 - 126.0f) * 0.25f));
+      if (lane == 0) {
+        bound[9] = (sh <= 31.0f && y4 == y4) ? 1.0f : 0.0f;
+        bound[8] = fminf(sh, 31.0f);
+      }
+    }
   }
   if (row >= rows) return;
   const float* kr = keys + row * kR + lane * 16;
@@ -231,13 +256,13 @@ __device__ __forceinline__ void front4(const float4 k, const float4 g, const flo
   }
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    ea[j] = make_float2(ex2_approx(fminf(y01[j].x, 30.0f)), ex2_approx(fminf(y23[j].x, 30.0f)));
-    eb[j] = make_float2(ex2_approx(fminf(y01[j].y, 30.0f)), ex2_approx(fminf(y23[j].y, 30.0f)));
+    ea[j] = make_float2(ex2_approx(y01[j].x), ex2_approx(y23[j].x));
+    eb[j] = make_float2(ex2_approx(y01[j].y), ex2_approx(y23[j].y));
   }
 }
 template <int K>
-__device__ __forceinline__ void back4(const float4 vv, const float2 (&ea)[K], const float2 (&eb)[K], float (&out)[K]) {
-  const float2 one2 = make_float2(1.0f, 1.0f);
+__device__ __forceinline__ void back4(const float4 vv, const float2 (&ea)[K], const float2 (&eb)[K], float (&out)[K], const float c0) {
+  const float2 one2 = make_float2(c0, c0);                   // 2^-s (1 when no exponent shift is needed)
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     const float2 xa = __fadd2_rn(ea[j], one2), xb = __fadd2_rn(eb[j], one2);
@@ -322,12 +347,16 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
     *next_g = 0;
     fence_barrier_init();
   }
-  // LN constants: gamma' = gamma * 2 log2 e, beta' likewise, v' = -2 v in pair order (v1, v3, v0, v2)
+  // LN constants: gamma' = gamma * 2 log2 e, beta' = beta * 2 log2 e - s, v' = -2 v 2^-s in pair order (v1, v3, v0, v2)
+  const float eshift = a.bound[8];                            // exponent shift s (integer valued, 0 for ordinary weights)
+  const float escale = exp2f(-eshift);                        // 2^-s, exact
   for (int c4 = tid; c4 < kR / 4; c4 += L::kThreads) {
     const float4 g4 = ldg4(a.gamma + c4 * 4), b4 = ldg4(a.beta + c4 * 4), v4 = ldg4(a.vvec + c4 * 4);
     *reinterpret_cast<float4*>(sm_c + c4 * 4) = make_float4(g4.x * kTwoLog2e, g4.y * kTwoLog2e, g4.z * kTwoLog2e, g4.w * kTwoLog2e);
-    *reinterpret_cast<float4*>(sm_c + kR + c4 * 4) = make_float4(b4.x * kTwoLog2e, b4.y * kTwoLog2e, b4.z * kTwoLog2e, b4.w * kTwoLog2e);
-    *reinterpret_cast<float4*>(sm_c + 2 * kR + c4 * 4) = make_float4(-2.0f * v4.y, -2.0f * v4.w, -2.0f * v4.x, -2.0f * v4.z);
+    *reinterpret_cast<float4*>(sm_c + kR + c4 * 4) = make_float4(b4.x * kTwoLog2e - eshift, b4.y * kTwoLog2e - eshift,
+                                                                 b4.z * kTwoLog2e - eshift, b4.w * kTwoLog2e - eshift);
+    const float vs = -2.0f * escale;
+    *reinterpret_cast<float4*>(sm_c + 2 * kR + c4 * 4) = make_float4(vs * v4.y, vs * v4.w, vs * v4.x, vs * v4.z);
   }
   __syncthreads();
   if (n_g == 0) return;
@@ -402,7 +431,7 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
 #pragma unroll
       for (int j = 0; j < K; ++j) { dA[j] = make_float2(0.f, 0.f); dB[j] = make_float2(0.f, 0.f); }
       {
-        float4 kq[2][2 + K];                                  // chunk u, u + 1: keys A, keys B, K centred queries
+        float4 kq[3][2 + K];                                  // rotating window of chunks u, u + 1, u + 2: keys A, keys B, K centred queries
         auto ld1 = [&](float4 (&dst)[2 + K], int u) {
           const uint32_t ka = kofs[u] + kst, qa = cadr[u] + qcb;
           dst[0] = lds128<0>(ka);
@@ -412,13 +441,14 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
           if (K > 2) dst[K > 2 ? 4 : 2] = lds128<2 * kR * 4>(qa);
         };
         ld1(kq[0], 0);
+        ld1(kq[1], 1);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          if (u + 1 < 8) ld1(kq[(u + 1) & 1], u + 1);
-          const float4 ka = kq[u & 1][0], kb = kq[u & 1][1];
+          if (u + 2 < 8) ld1(kq[(u + 2) % 3], u + 2);
+          const float4 ka = kq[u % 3][0], kb = kq[u % 3][1];
 #pragma unroll
           for (int j = 0; j < K; ++j) {
-            const float4 q4 = kq[u & 1][2 + j];
+            const float4 q4 = kq[u % 3][2 + j];
             dA[j] = __ffma2_rn(make_float2(ka.x, ka.y), make_float2(q4.x, q4.y), dA[j]);
             dA[j] = __ffma2_rn(make_float2(ka.z, ka.w), make_float2(q4.z, q4.w), dA[j]);
             dB[j] = __ffma2_rn(make_float2(kb.x, kb.y), make_float2(q4.x, q4.y), dB[j]);
@@ -456,14 +486,14 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
 #pragma unroll
       for (int u = 1; u < 8; ++u) {
         chunk2_load<K>(c, kofs[u] + kst, cadr[u], cadr[u] + qgb);
-        back4<K>(vprev, eaA, ebA, outA);
+        back4<K>(vprev, eaA, ebA, outA, escale);
         front4<K>(c.ka, c.g, c.b, c.q, nmuA, rsA, eaA, ebA);
-        back4<K>(vprev, eaB, ebB, outB);
+        back4<K>(vprev, eaB, ebB, outB, escale);
         front4<K>(c.kb, c.g, c.b, c.q, nmuB, rsB, eaB, ebB);
         vprev = c.v;
       }
-      back4<K>(vprev, eaA, ebA, outA);
-      back4<K>(vprev, eaB, ebB, outB);
+      back4<K>(vprev, eaA, ebA, outA, escale);
+      back4<K>(vprev, eaB, ebB, outB, escale);
       A2_STAMP(4);
       float* pdst = sm_p + (size_t)par * pimg + hp * M + m;
 #pragma unroll
@@ -768,9 +798,29 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
       const int lo = seg_lo(ii), hi = seg_hi(ii);
       const float* src = a.keys + ((size_t)(b0 + ii) * spi + lo) * kSliceFloats;
       bool prepped = false;
+#if COMIC_A2_L2_AHEAD > 0
+      if (lane == 0 && pos == 0) {
+        const int n0 = (hi - lo) < COMIC_A2_L2_AHEAD ? (hi - lo) : COMIC_A2_L2_AHEAD;
+        for (int i = 0; i < n0; ++i) tma_prefetch_l2(src + (size_t)i * kSliceFloats, kSliceBytes);
+      }
+#endif
       for (int sl = lo; sl < hi; ++sl, ++g) {
         if (lane == 0) {
           const int s = g % STAGES;
+#if COMIC_A2_L2_AHEAD > 0
+          {
+            // keep the next COMIC_A2_L2_AHEAD slices of the sequence on their way into L2: the ring then refills at
+            // L2 latency instead of HBM latency
+            const int ahead = sl + COMIC_A2_L2_AHEAD;
+            if (ahead < hi) tma_prefetch_l2(src + (size_t)(ahead - lo) * kSliceFloats, kSliceBytes);
+            else if (pos + 1 < n_seg) {
+              const int nii = seg_of(pos + 1);
+              const int nlo = seg_lo(nii), nhi = seg_hi(nii);
+              const int nsl = nlo + (ahead - hi);
+              if (nsl < nhi) tma_prefetch_l2(a.keys + ((size_t)(b0 + nii) * spi + nsl) * kSliceFloats, kSliceBytes);
+            }
+          }
+#endif
           mbar_wait(&empty[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
           mbar_arrive_expect_tx(&full[s], kSliceBytes);
           tma_bulk_g2s(smem + L::ring + s * kSliceBytes, src + (size_t)(sl - lo) * kSliceFloats, kSliceBytes, &full[s]);
@@ -832,9 +882,11 @@ inline cudaError_t launch(const Args& a, int k, int num_sms, int dev, cudaStream
 // Global scratch of one launch: floats for up to `num_sms` CTAs (two partial-image slots each) and k <= 3 beams.
 inline size_t scratch_floats(int num_sms) { return (size_t)2 * num_sms * 3 * (kR + kH); }
 
+constexpr int kBoundFloats = 12;   // [0..7] per-head score bound, [8] exponent shift, [9] shift feasible
 inline cudaError_t launch_key_stats(const float* keys, long long rows, float* kstats, const float* vvec,
-                                    const float* temperature, float* bound, cudaStream_t st) {
-  key_stats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(keys, rows, kstats, vvec, temperature, bound);
+                                    const float* temperature, const float* gamma, const float* beta, float* bound,
+                                    cudaStream_t st) {
+  key_stats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(keys, rows, kstats, vvec, temperature, gamma, beta, bound);
   return cudaGetLastError();
 }
 

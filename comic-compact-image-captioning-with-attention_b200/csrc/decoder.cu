@@ -718,15 +718,15 @@ int attn2_prepare(comic_handle_t h, StepIO& io, const StepBufs& sb, int B, int k
   {
     Prof pf(h, T_MISC, st);
     COMIC_CHECK_CUDA(a2::launch_key_stats(io.keys, (long long)B * h->M, sb.kstats, h->w.attention_v, h->w.temperature,
-                                          sb.abound, st));
+                                          h->w.ln_gamma, h->w.ln_beta, sb.abound, st));
   }
   if (h->attn2_state == 0) {
     // once per weight binding: exp(score - bound) must not underflow to zero for a whole row, so the kernel is only
     // taken while 2 * bound stays well inside the fp32 exponent range (the one host synchronisation of this path)
     COMIC_REQUIRE(h->attn2_host != nullptr, COMIC_E_CUDA, "attn2: no pinned buffer");
-    COMIC_CHECK_CUDA(cudaMemcpyAsync(h->attn2_host, sb.abound, a2::kH * sizeof(float), cudaMemcpyDeviceToHost, st));
+    COMIC_CHECK_CUDA(cudaMemcpyAsync(h->attn2_host, sb.abound, a2::kBoundFloats * sizeof(float), cudaMemcpyDeviceToHost, st));
     COMIC_CHECK_CUDA(cudaStreamSynchronize(st));
-    bool ok = true;
+    bool ok = h->attn2_host[9] == 1.0f;                       // an exponent shift for the clamp-free reciprocal product exists
     for (int i = 0; i < a2::kH; ++i) ok = ok && (h->attn2_host[i] == h->attn2_host[i]) && h->attn2_host[i] <= 40.0f;
     h->attn2_state = ok ? 1 : -1;
     if (!ok) return COMIC_OK;
@@ -869,7 +869,7 @@ void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_ma
   sb.ctxraw = cv.take<float>(h->cfg.context_layer ? (size_t)N * h->VAL : 1);
   const bool a2ok = h->cfg.alignment == 0 && h->cfg.prob_fn == 0 && h->R == a2::kR && h->H == a2::kH && h->VAL == h->R;
   sb.kstats = cv.take<float>(a2ok ? (size_t)N * h->M * 2 : 1);    // N >= number of images
-  sb.abound = cv.take<float>(a2::kH);
+  sb.abound = cv.take<float>(a2::kBoundFloats);
   sb.a2_scratch = cv.take<float>(a2ok ? a2::scratch_floats(h->num_sms) : 1);
   sb.a2_counters = cv.take<int>(a2ok ? (size_t)N : 1);
 }

@@ -103,6 +103,7 @@ class ModelBase(object):
             cell=c.rnn_name, attention_mechanism=cnn_attention, attention_layer_size=None,
             alignment_history=self.collect_attention_maps, cell_input_fn=None, output_attention=False,
             initial_cell_state=rnn_init)
+        attention_cell.im_embed = self.im_embed          # rops.rnn_decoder_training recomputes the initial state from it
         start_id, end_id = self._start_end_ids()
         max_it = self._maximum_iterations()
         if beam_search:

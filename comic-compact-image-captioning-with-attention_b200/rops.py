@@ -5,7 +5,7 @@ the reference builds is replaced by calls into libcomic_b200.so (engine.py).
 
   rnn_decoder_beam_search     common/ops_rnn.py:49-112
   rnn_decoder_search          common/ops_rnn.py:115-180
-  rnn_decoder_training        common/ops_rnn.py:183-243   (train.py, see train.py module)
+  rnn_decoder_training        common/ops_rnn.py:183-243   (forward; the fused fwd + bwd lives in train.py)
   MultiHeadAddLN / MultiHeadDot  common/ops_rnn.py:403-565, 603-632
   MultiHeadAttentionWrapperV3  common/ops_rnn.py:635-803
 """
@@ -56,6 +56,7 @@ class MultiHeadAttV3(object):
         self._feature_map_shape = list(feature_map.shape)
         self._name = name
         self.batch_size = feature_map.shape[0]
+        self.feature_map = feature_map
         self.keys, self.values = engine.project_fm(feature_map)          # ops_rnn.py:441-477
 
 
@@ -183,3 +184,48 @@ def rnn_decoder_search(cell, embedding_fn, output_layer, batch_size, maximum_ite
     state = AttentionWrapperState(cell_state=None, attention=None, time=T, alignments=None,
                                   alignment_history=r['attn'][:, :, :T, :] if want_attn else (), attention_state=None)
     return r['ids'][:T], r['logits'][:T], state
+
+
+def rnn_decoder_training(cell, embeddings, output_layer, batch_size, sequence_length, swap_memory=True):
+    """Teacher-forced decode (common/ops_rnn.py:183-243): TrainingHelper + BasicDecoder +
+    dynamic_decode(impute_finished=True), time-major.
+
+    `embeddings` are the decoder INPUT TOKEN IDS [time, batch] int32: the embedding map is bound inside the engine
+    (as for `embedding_fn` of the search functions), so the lookup of src/model_base.py:587-593 happens on the device.
+    `cell.im_embed` must hold the image embedding [batch, E] the initial state was built from (the engine's
+    teacher-forced pass recomputes that state itself).  Returns (output_ids [T,B] int32 = arg-max samples, rnn_out
+    logits [T,B,V] -- rows past their length are zero, steps past max(sequence_length) repeat the last executed step
+    (:237-241) -- and a state whose alignment_history is [B,H,T_run,M])."""
+    del output_layer, swap_memory
+    eng = cell.engine
+    torch = eng.torch
+    am = cell._attention_mechanism
+    if am.batch_size != batch_size:
+        raise ValueError('Non-matching batch sizes between the memory (encoder output) and the query '
+                         '(decoder output).')
+    im_embed = getattr(cell, 'im_embed', None)
+    if im_embed is None:
+        raise ValueError('rnn_decoder_training: set cell.im_embed to the image embedding of the initial state')
+    ids = torch.as_tensor(embeddings).to(device=eng.device, dtype=torch.int32).contiguous()
+    if ids.dim() != 2 or ids.shape[1] != batch_size:
+        raise ValueError('embeddings must be the [time, batch] input token ids, got %s' % (tuple(ids.shape),))
+    lens = torch.as_tensor(sequence_length).to(device=eng.device, dtype=torch.int32).contiguous()
+    T = int(ids.shape[0])
+    T_run = int(lens.max().item())
+    if T_run < 1 or T_run > T:
+        raise ValueError('sequence_length must lie in [1, time]')
+    zeros_i = torch.zeros_like(ids)
+    zeros_f = torch.zeros(ids.shape, dtype=torch.float32, device=eng.device)
+    _loss, logits, attn = eng.train_fwd_bwd(am.feature_map.contiguous(), im_embed.contiguous(), ids, zeros_i, zeros_f, lens,
+                                            T_run, None, None, (1.0, 1.0, 1.0), 0.0, True, True)
+    rnn_out = logits.transpose(0, 1).contiguous()                        # [T, B, V]
+    if T_run < T:
+        rnn_out[T_run:] = rnn_out[T_run - 1:T_run]
+    valid = (torch.arange(T_run, device=eng.device)[:, None] < lens[None, :])
+    output_ids = torch.zeros((T, batch_size), dtype=torch.int32, device=eng.device)
+    output_ids[:T_run] = torch.where(valid, rnn_out[:T_run].argmax(dim=-1).to(torch.int32), torch.zeros_like(output_ids[:T_run]))
+    if T_run < T:
+        output_ids[T_run:] = output_ids[T_run - 1:T_run]
+    state = AttentionWrapperState(cell_state=None, attention=None, time=T_run, alignments=None,
+                                  alignment_history=attn, attention_state=None)
+    return output_ids, rnn_out, state

@@ -8,6 +8,9 @@
 #include <cmath>
 #include <algorithm>
 #define COMIC_A2_WATCHDOG 1
+#ifndef HARNESS_GAMMA_SCALE
+#define HARNESS_GAMMA_SCALE 1.0f
+#endif
 #include "../../comic-compact-image-captioning-with-attention_b200/csrc/attention2.cuh"
 
 using namespace comic;
@@ -28,12 +31,12 @@ int main(int argc, char** argv) {
   std::vector<float> hk(nk), hq((size_t)N * LQ), hg(R), hb(R), hv(R);
   for (size_t i = 0; i < nk; ++i) hk[i] = 0.7f * nrand() + 0.3f;
   for (auto& x : hq) x = 0.8f * nrand() + 0.1f;
-  for (int c = 0; c < R; ++c) { hg[c] = 1.0f + 0.2f * nrand(); hb[c] = 0.1f * nrand(); hv[c] = 0.2f * (urand() - 0.5f); }
+  for (int c = 0; c < R; ++c) { hg[c] = (1.0f + 0.2f * nrand()) * HARNESS_GAMMA_SCALE; hb[c] = 0.1f * nrand(); hv[c] = 0.2f * (urand() - 0.5f); }
   float hT = 5.0f;
   float *dk, *dq, *dg, *db, *dv, *dT, *dks, *dbound, *ctx0, *ctx1, *hist0, *hist1;
   CK(cudaMalloc(&dk, nk * 4)); CK(cudaMalloc(&dq, hq.size() * 4));
   CK(cudaMalloc(&dg, R * 4)); CK(cudaMalloc(&db, R * 4)); CK(cudaMalloc(&dv, R * 4)); CK(cudaMalloc(&dT, 4));
-  CK(cudaMalloc(&dks, (size_t)B * M * 2 * 4)); CK(cudaMalloc(&dbound, 8 * 4));
+  CK(cudaMalloc(&dks, (size_t)B * M * 2 * 4)); CK(cudaMalloc(&dbound, 16 * 4));
   CK(cudaMalloc(&ctx0, (size_t)N * R * 4)); CK(cudaMalloc(&ctx1, (size_t)N * R * 4));
   CK(cudaMalloc(&hist0, (size_t)N * H * M * 4)); CK(cudaMalloc(&hist1, (size_t)N * H * M * 4));
   CK(cudaMemcpy(dk, hk.data(), nk * 4, cudaMemcpyHostToDevice));
@@ -74,11 +77,11 @@ int main(int argc, char** argv) {
   printf("old fused: %.2f us / launch\n", ms0 * 1000.f / iters);
 
   // ---- new: attention2.cuh ----
-  CK(a2::launch_key_stats(dk, (long long)B * M, dks, dv, dT, dbound, 0));
+  CK(a2::launch_key_stats(dk, (long long)B * M, dks, dv, dT, dg, db, dbound, 0));
   CK(cudaDeviceSynchronize());
-  float hbound[8];
-  CK(cudaMemcpy(hbound, dbound, 32, cudaMemcpyDeviceToHost));
-  printf("bound: %.3f %.3f ... %.3f\n", hbound[0], hbound[1], hbound[7]);
+  float hbound[12];
+  CK(cudaMemcpy(hbound, dbound, 48, cudaMemcpyDeviceToHost));
+  printf("bound: %.3f %.3f ... %.3f  exponent shift %.0f feasible %.0f\n", hbound[0], hbound[1], hbound[7], hbound[8], hbound[9]);
   a2::Args a{};
   a.keys = dk; a.kstats = dks; a.bound = dbound; a.lq = dq; a.ld_lq = LQ; a.q_off = QOFF; a.gamma = dg; a.beta = db; a.vvec = dv;
   a.temperature = dT; a.ctx_out = ctx1; a.ld_ctx = R; a.hist_t = hist1; a.B = B; a.M = M; a.n_rows = N;
@@ -104,7 +107,7 @@ int main(int argc, char** argv) {
   float ms1; CK(cudaEventElapsedTime(&ms1, e0, e1));
   printf("new attn2: %.2f us / launch  (NSW=%d STAGES=%d)\n", ms1 * 1000.f / iters, COMIC_A2_NSW, COMIC_A2_STAGES);
   CK(cudaEventRecord(e0));
-  CK(a2::launch_key_stats(dk, (long long)B * M, dks, dv, dT, dbound, 0));
+  CK(a2::launch_key_stats(dk, (long long)B * M, dks, dv, dT, dg, db, dbound, 0));
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms2; CK(cudaEventElapsedTime(&ms2, e0, e1));

@@ -534,3 +534,64 @@ def test_cli_drivers_run(torch_mod, capsys):
     assert cli.main(['train', '--train_mode', 'decoder', '--batch_size_train', '4', '--synthetic_steps', '2']) == 0
     out = capsys.readouterr().out
     assert 'steps/s' in out and 'step    2' in out
+
+
+@pytest.mark.parametrize('case', ['STEP', 'STEP_WITH_EOS'])
+def test_beam_step_kernel_reproduces_tf19_unit_test(torch_mod, case):
+    """The CUDA beam step on TensorFlow r1.9's own test vectors (tests/golden/tf19_vectors.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import tf19_vectors as TV
+    c = comic_config()
+    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False)
+    v = getattr(TV, case)
+    d_lp = eng.to_dev(TV.initial_log_probs())
+    d_fin = eng.to_dev(v['finished'].astype(np.uint8))
+    d_len = eng.to_dev(v['lengths'])
+    _top, word, parent = eng.beam_step(eng.to_dev(v['logits']), d_lp, d_fin, d_len, TV.END_TOKEN, TV.LENGTH_PENALTY)
+    np.testing.assert_array_equal(word.cpu().numpy(), v['predicted_ids'])
+    np.testing.assert_array_equal(parent.cpu().numpy(), v['parent_ids'])
+    np.testing.assert_array_equal(d_len.cpu().numpy(), v['next_lengths'])
+    np.testing.assert_array_equal(d_fin.cpu().numpy().astype(bool), v['next_finished'])
+
+
+def test_gather_tree_kernel_reproduces_tf19_unit_test(torch_mod):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import tf19_vectors as TV
+    c = comic_config()
+    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False)
+    g = TV.GATHER_TREE
+    out = eng.gather_tree(eng.to_dev(g['step_ids']), eng.to_dev(g['parent_ids']), eng.to_dev(g['max_sequence_lengths']),
+                          g['end_token'])
+    np.testing.assert_array_equal(out.cpu().numpy(), g['expected'])
+
+
+def test_rnn_decoder_training_matches_oracle(torch_mod):
+    """rops.rnn_decoder_training (common/ops_rnn.py:183-243): ragged lengths, impute_finished, padding by the last step."""
+    import comic_oracle as O
+    from comic_b200 import rops
+    c = comic_config()
+    W = make_weights(c, include_cnn=False)
+    eng = _engine(c, W, with_cnn=False)
+    B, T = 4, 9
+    im, fm = fake_features(B, seed=23)
+    rng = np.random.default_rng(6)
+    ids = rng.integers(0, 256, size=(B, T)).astype(np.int32)
+    lens = np.array([7, 3, 5, 1], np.int32)
+    ref = O.training_decode(O.Decoder(W, c), im, fm, ids, lens)
+    d_im, d_fm = eng.to_dev(im), eng.to_dev(fm)
+    am = rops.MultiHeadAddLN(c.rnn_size, d_fm, c.cnn_fm_projection, c.attn_num_heads, engine=eng)
+    cell = rops.MultiHeadAttentionWrapperV3(context_layer=c.attn_context_layer, cell=c.rnn_name, attention_mechanism=am,
+                                            initial_cell_state=rops.LSTMStateTuple(*eng.rnn_init(d_im)))
+    with pytest.raises(ValueError):
+        rops.rnn_decoder_training(cell, ids.T, None, B, lens)
+    cell.im_embed = d_im
+    out_ids, rnn_out, state = rops.rnn_decoder_training(cell, ids.T, None, B, lens)
+    assert rnn_out.shape == (T, B, 258) and state.time == ref['T_run'] == 7
+    assert rel_err(rnn_out.cpu().numpy(), ref['logits']) < TOL
+    np.testing.assert_array_equal(out_ids.cpu().numpy(), ref['ids'])
+    hist = ref['alignment_history'].reshape(ref['T_run'], B, 8, 196).transpose(1, 2, 0, 3)
+    assert rel_err(state.alignment_history.cpu().numpy(), hist) < 1e-3
