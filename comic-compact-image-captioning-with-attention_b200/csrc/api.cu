@@ -113,7 +113,7 @@ extern "C" int comic_profile_read(comic_handle_t h, int tag, double* total_ms, i
 
 namespace comic {
 int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, int ldw, int cin_src, int cin_dst,
-                   tc::TcWeight& out, cudaStream_t st, bool dry) {
+                   tc::TcWeight& out, cudaStream_t st, bool dry, int gate_R) {
   (void)h;
   int ntaps = K / cin_src;
   int Kd = (cin_src == cin_dst) ? K : ntaps * cin_dst;
@@ -127,7 +127,7 @@ int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, i
   out.ready = false;
   if (dry) return COMIC_OK;
   tc::pack_bt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, K, N, ldw, out.hi, out.lo, out.Kpad, out.Npad,
-                                                                 cin_src, cin_dst);
+                                                                 cin_src, cin_dst, gate_R);
   COMIC_CHECK_CUDA(cudaGetLastError());
   COMIC_REQUIRE(tc::make_weight_maps(out), COMIC_E_CUDA, "cuTensorMapEncodeTiled failed for a %d x %d weight", N, Kd);
   return COMIC_OK;
@@ -150,6 +150,7 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
     case COMIC_OPT_STEM_S2D: h->stem_s2d = value; return COMIC_OK;
     case COMIC_OPT_TC_MIN_ROWS: h->tc_min_rows = value; return COMIC_OK;
     case COMIC_OPT_ATTN2: h->attn2 = value; return COMIC_OK;
+    case COMIC_OPT_FUSE_LSTM: h->fuse_lstm = value; return COMIC_OK;
     case COMIC_OPT_GEMM_RESIDENT_B: tc::bres_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR: tc::pair_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR_MIN_TILES: tc::pair_min_tiles() = value; return COMIC_OK;

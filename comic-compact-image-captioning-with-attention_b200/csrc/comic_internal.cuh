@@ -52,6 +52,8 @@ struct Packed {
   tc::TcWeight tc_conv[COMIC_NUM_CONVS];
   tc::TcWeight tc_grp[kNumBlocks];
   tc::TcWeight tc_lstm, tc_outq, tc_mem, tc_val, tc_init;
+  tc::TcWeight tc_lstm_il;       // lstm kernel with gate-interleaved columns (fused LSTM epilogue of the gate GEMM)
+  float* lstm_bias_il = nullptr; // [4R] bias in the same column order
   tc::TcWeight tc_stem_s2d;      // Conv2d_1a_7x7 as a 4x4 conv over the space-to-depth image: W2 [4,4,16,64]
 };
 
@@ -71,6 +73,11 @@ struct comic_handle_s {
   bool bound = false, cnn_bound = false;
   int precision = 1;   // 0: fp32 FFMA everywhere; 1: tcgen05 split-precision GEMMs with M >= 128; 2: 1 + tanh.approx
   int fused_min_images = 48;   // fused attention kernel (one CTA per image) from this batch size on
+  int fuse_lstm = 0;           // 1: gate GEMM with the LSTM point-wise update in its epilogue (tensor path, no dropout / tape).
+                               // Bit-identical to the separate kernel but measured SLOWER at 1,536 rows (gates + lstm 2.86 ->
+                               // 3.02 ms per 60 steps, profiles/r06e): the GEMM has 96 tiles on 148 SMs, one per CTA, so the
+                               // epilogue's transcendentals are not hidden behind a next tile's MMAs, while the separate
+                               // kernel spreads them over the whole chip.  Off by default.
   int attn2 = 1;               // streaming attention kernel (attention2.cuh) where it applies: tied values, add_LN, softmax,
                                // R = 512, 8 heads, k <= 3, no attention-map dropout; 0 = always attention.cuh
   int attn2_state = 0;         // 0: score bound of the bound weights not checked yet; 1: within range; -1: too large
@@ -138,7 +145,7 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // Carve + (unless dry) fill one tensor-path weight pack from W[K][N] (row stride ldw).
 int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, int ldw, int cin_src, int cin_dst,
-                   tc::TcWeight& out, cudaStream_t st, bool dry);
+                   tc::TcWeight& out, cudaStream_t st, bool dry, int gate_R = 0);
 inline bool use_tc(comic_handle_t h, const tc::TcWeight& w, int M) { return h->precision >= 1 && w.ready && M >= h->tc_min_rows; }
 
 // encoder.cu

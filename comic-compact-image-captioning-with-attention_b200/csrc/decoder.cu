@@ -65,19 +65,6 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gp, int nz, size
 // units per thread with 128-bit accesses.  FAST (engine precision >= 1, the tensor path): sigmoid / tanh through
 // ex2.approx + rcp.approx (relative error ~1e-6 against expf / tanhf, same budget as the bf16x3 GEMM feeding it).
 template <bool FAST>
-__device__ __forceinline__ float sig_(float x) {
-  if (FAST) return __frcp_rn(1.0f + __expf(-x));
-  return 1.0f / (1.0f + expf(-x));
-}
-template <bool FAST>
-__device__ __forceinline__ float tanh_(float x) {
-  if (FAST) {
-    const float e = __expf(-2.0f * fabsf(x));           // in (0, 1]: no overflow
-    return copysignf((1.0f - e) * __frcp_rn(1.0f + e), x);
-  }
-  return tanhf(x);
-}
-template <bool FAST>
 __global__ void __launch_bounds__(256)
 lstm_pointwise4_kernel(const float* __restrict__ gates, const float* __restrict__ bias, const float* __restrict__ c_prev,
                        const int* __restrict__ src, int src_limit, float* __restrict__ c_new, float* __restrict__ h_new,
@@ -532,10 +519,21 @@ int decoder_configure() {
 }
 
 // Tensor-path (3xTF32) panels of the decoder weights.
+__global__ void interleave_gate_bias_kernel(const float* __restrict__ bias, float* __restrict__ out, int R) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < 4 * R) out[n] = bias[(n & 3) * R + (n >> 2)];
+}
+
 static int decoder_pack_tc(comic_handle_t h, Carver& cv, cudaStream_t st, bool dry) {
   int rc;
   const int XA = h->W + h->A;
   if ((rc = pack_tc_weight(h, cv, h->w.lstm_kernel, h->KX, 4 * h->R, 4 * h->R, 1, 1, h->pk.tc_lstm, st, dry))) return rc;
+  if ((rc = pack_tc_weight(h, cv, h->w.lstm_kernel, h->KX, 4 * h->R, 4 * h->R, 1, 1, h->pk.tc_lstm_il, st, dry, h->R))) return rc;
+  h->pk.lstm_bias_il = cv.take<float>((size_t)4 * h->R);
+  if (!dry) {
+    interleave_gate_bias_kernel<<<(4 * h->R + 255) / 256, 256, 0, st>>>(h->w.lstm_bias, h->pk.lstm_bias_il, h->R);
+    COMIC_CHECK_CUDA(cudaGetLastError());
+  }
   if ((rc = pack_tc_weight(h, cv, h->pk.outq, h->R, h->LQ, h->LQ, 1, 1, h->pk.tc_outq, st, dry))) return rc;
   if ((rc = pack_tc_weight(h, cv, h->w.memory_kernel, h->C, h->R, h->R, 1, 1, h->pk.tc_mem, st, dry))) return rc;
   if (h->cfg.fm_projection == 2)
@@ -772,12 +770,21 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
   e1.split_stride = (long long)N * 4 * R;
   e1.stop = io.fin_count ? io.fin_count + (io.t > 0 ? io.t - 1 : 0) : nullptr;
   e1.stop_n = (io.fin_count && io.t > 0) ? io.n_rows : 0x7fffffff;
-  {
+  // tensor path without dropout / tape: the LSTM point-wise update runs in the gate GEMM's epilogue over the
+  // gate-interleaved panel (same arithmetic, in the same order, as lstm_pointwise4_kernel<true>: bit-identical c / h)
+  const bool fused_lstm = tc1 && h->fuse_lstm && h->pk.tc_lstm_il.ready && !io.h_drop && !io.out_mask && !io.gates_save;
+  if (fused_lstm) {
+    e1.bias = h->pk.lstm_bias_il;
+    e1.lstm_c_prev = io.c_prev; e1.lstm_src = io.src; e1.lstm_src_limit = io.src_limit;
+    e1.lstm_c = io.c_new; e1.lstm_h = io.h_new; e1.lstm_R = R;
+    Prof pf(h, T_GATES, st);
+    COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a, h->pk.tc_lstm_il, N, 4 * R, e1, h->num_sms, st)));
+  } else {
     Prof pf(h, T_GATES, st);
     if (tc1) COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a, h->pk.tc_lstm, N, 4 * R, e1, h->num_sms, st)));
     else COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.lstm_kernel, 4 * R, N, 4 * R, h->KX, e1, p1, st)));
   }
-  {
+  if (!fused_lstm) {
     Prof pf(h, T_LSTM, st);
     int tot = N * R;
     if (nz1 == 1 && R % 4 == 0 && !io.h_drop && !io.out_mask && !io.gates_save && N >= 128) {

@@ -80,7 +80,33 @@ struct Epi {
   long long split_stride;  // elements between split-K partials of route 0
   const int* stop;         // optional device flag: skip the launch when *stop >= stop_n
   int stop_n;              // (decode loops: every beam finished in the previous step)
+  // LSTM epilogue (tensor path, gate GEMM over a GATE-INTERLEAVED weight panel: column 4 u + g = gate g of unit u, so
+  // the four consecutive columns an epilogue lane owns are i, j, f, o of one unit).  lstm_h != nullptr: instead of
+  // storing the pre-activations the epilogue adds `bias` (interleaved the same way), applies the BasicLSTMCell
+  // point-wise update (forget_bias 1.0) against c_prev[src[m]] and writes c / h [M, lstm_R].
+  const float* lstm_c_prev;
+  const int* lstm_src;
+  int lstm_src_limit;
+  float* lstm_c;
+  float* lstm_h;
+  int lstm_R;
 };
+
+// sigmoid / tanh of the big-batch decode path (engine precision >= 1): ex2.approx + rcp, relative error ~1e-6 against
+// expf / tanhf -- the same budget as the bf16x3 GEMM feeding them.  FAST = false: libm.
+template <bool FAST>
+__device__ __forceinline__ float sig_(float x) {
+  if (FAST) return __frcp_rn(1.0f + __expf(-x));
+  return 1.0f / (1.0f + expf(-x));
+}
+template <bool FAST>
+__device__ __forceinline__ float tanh_(float x) {
+  if (FAST) {
+    const float e = __expf(-2.0f * fabsf(x));           // in (0, 1]: no overflow
+    return copysignf((1.0f - e) * __frcp_rn(1.0f + e), x);
+  }
+  return tanhf(x);
+}
 
 // NHWC activations stored pre-split as two bf16 planes (tensor path, gemm_tc.cuh).
 struct AConvP {

@@ -338,9 +338,36 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
           return mw + row;
         }
       };
+      // LSTM epilogue: the rows this lane stores are fixed for the tile -> resolve the state-row indirection once, and
+      // fetch c_prev one column block ahead (the dependent src -> c_prev loads would otherwise sit in every iteration)
+      const float* cprow[4] = {nullptr, nullptr, nullptr, nullptr};
+      float cp_next[4] = {0.f, 0.f, 0.f, 0.f};
+      if (epi.lstm_h != nullptr && epi.lstm_c_prev != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int m = row_to_m(q * 8 + srow);
+          if (m < M) {
+            const int rr = epi.lstm_src ? epi.lstm_src[m] : m;
+            if (rr >= 0 && rr < epi.lstm_src_limit) cprow[q] = epi.lstm_c_prev + (size_t)rr * epi.lstm_R;
+          }
+        }
+        const int u0 = (n0 + half * 16 + scol) >> 2;
+        if (n0 + half * 16 + scol < N) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (cprow[q]) cp_next[q] = __ldg(cprow[q] + u0);
+        }
+      }
 #pragma unroll 1
       for (int c0 = half * 16; c0 < n_umma; c0 += 32) {
         uint32_t r[16];
+        float cp_cur[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cp_cur[q] = cp_next[q];
+        if (epi.lstm_h != nullptr && c0 + 32 < n_umma && n0 + c0 + 32 + scol < N) {
+          const int un = (n0 + c0 + 32 + scol) >> 2;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cp_next[q] = cprow[q] ? __ldg(cprow[q] + un) : 0.f;
+        }
         uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
@@ -365,6 +392,25 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
           const long long cofs = (long long)epi.r[rt].coff - epi.r[rt].n0 + n;
           const float4 sc = epi.scale ? ldg4(epi.scale + n) : make_float4(1.f, 1.f, 1.f, 1.f);
           const float4 bs = epi.bias ? ldg4(epi.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (epi.lstm_h != nullptr) {
+            // gate-interleaved panel: columns n .. n + 3 are the i, j, f, o pre-activations of unit n / 4
+            const int u = n >> 2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int row = q * 8 + srow;
+              const int m = row_to_m(row);
+              if (m < M) {
+                const float4 v = *reinterpret_cast<const float4*>(stage_buf + row * L::EPI_STRIDE + scol);
+                const float cp = cp_cur[q];
+                const float cn = cp * sig_<true>((v.z + bs.z) + 1.0f) + sig_<true>(v.x + bs.x) * tanh_<true>(v.y + bs.y);
+                const float hn = tanh_<true>(cn) * sig_<true>(v.w + bs.w);
+                epi.lstm_c[(size_t)m * epi.lstm_R + u] = cn;
+                epi.lstm_h[(size_t)m * epi.lstm_R + u] = hn;
+              }
+            }
+            __syncwarp();
+            continue;
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int row = q * 8 + srow;
@@ -838,12 +884,16 @@ inline bool make_weight_maps(TcWeight& w) {
 
 // B^T bf16 hi/lo packing: src W[k][n] (row stride ldw); optional channel padding of an
 // HWIO conv kernel (cin_src -> cin_dst, e.g. 3 -> 4 for the NHWC4 stem input).
+// gate_R > 0: the source is an LSTM kernel [K, 4 gate_R] in gate order i | j | f | o; packed row n takes source column
+// (n & 3) * gate_R + (n >> 2), i.e. the panel is gate-INTERLEAVED (see Epi::lstm_h).
 static __global__ void pack_bt_kernel(const float* __restrict__ W, int K, int N, int ldw, uint16_t* __restrict__ hi,
-                                      uint16_t* __restrict__ lo, int Kpad, int Npad, int cin_src, int cin_dst) {
+                                      uint16_t* __restrict__ lo, int Kpad, int Npad, int cin_src, int cin_dst,
+                                      int gate_R = 0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)Npad * Kpad) return;
   int n = (int)(i / Kpad), kp = (int)(i % Kpad);
   float v = 0.f;
+  const int n_src = gate_R > 0 ? (n & 3) * gate_R + (n >> 2) : n;
   if (n < N) {
     int k = kp;
     bool ok = kp < K;
@@ -852,7 +902,7 @@ static __global__ void pack_bt_kernel(const float* __restrict__ W, int K, int N,
       ok = ci < cin_src && tap < K / cin_src;
       k = tap * cin_src + ci;
     }
-    if (ok) v = W[(size_t)k * ldw + n];
+    if (ok) v = W[(size_t)k * ldw + n_src];
   }
   uint32_t h = pack_bf16x2(v, 0.f) & 0xffffu;
   float hf = __uint_as_float(h << 16);

@@ -144,6 +144,9 @@ int comic_set_precision(comic_handle_t h, int mode);
 #define COMIC_OPT_ATTN2 12                   /* 1 (default): large-batch decode steps use the streaming attention kernel
                                                 (TMA-staged key slices, one HBM pass per step) where it applies: tied
                                                 values, add_LN, softmax, rnn_size 512, 8 heads, beam <= 3; 0: never */
+#define COMIC_OPT_FUSE_LSTM 13               /* 1: on the tensor path the LSTM point-wise update runs in the gate GEMM's epilogue
+                                                (gate-interleaved weight panel; bit-identical results); 0 (default): separate
+                                                kernel -- measured faster at the benchmarked shape, see comic_internal.cuh */
 #define COMIC_OPT_TC_MIN_ROWS 11             /* GEMMs / convs with at least this many rows run on the tensor path when
                                              * precision >= 1 (default 64) */
 int comic_set_option(comic_handle_t h, int option, int value);

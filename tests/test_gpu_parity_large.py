@@ -202,3 +202,24 @@ def test_run_stream_raw_pixels_and_optional_attention_maps(torch_mod):
     p, a = m.run(u8[0])
     assert a is None
     np.testing.assert_array_equal(p, refs[0][0])
+
+
+def test_lstm_epilogue_fusion_is_bit_identical(torch_mod):
+    """The LSTM point-wise update inside the gate GEMM's epilogue (gate-interleaved weight panel) against the separate
+    point-wise kernel: the same fp32 operations in the same order, so every output of a decode must be identical."""
+    c = comic_config()
+    W = make_weights(c, include_cnn=False)
+    im, fm = fake_features(50, seed=19)
+    outs = []
+    for fuse in (1, 0):
+        eng = _engine(c, W)
+        eng.set_option('fuse_lstm', fuse)
+        keys, values = eng.project_fm(eng.to_dev(fm))
+        c0, h0 = eng.rnn_init(eng.to_dev(im))
+        n0 = eng.launch_count()
+        outs.append(eng.decode_beam(keys, values, c0, h0, 3, 0.0, 10))
+        outs[-1]['launches'] = eng.launch_count() - n0
+    a, b = outs
+    assert a['launches'] == b['launches'] - 10            # one launch per step less
+    for key in ('step_ids', 'parent_ids', 'predicted_ids', 'lengths', 'scores', 'attn'):
+        assert torch_mod.equal(a[key], b[key]), key
