@@ -844,15 +844,25 @@ int encoder_forward(comic_handle_t h, const float* images, int B, float* fm_out,
 // cropped pixels are interpolated, one thread per output pixel (3 channels), uint8 in / fp32 NHWC out.
 // ---------------------------------------------------------------------------
 namespace comic {
+// crop_yx == nullptr: evaluation (central crop / zero pad).  Otherwise training (preprocess_for_train,
+// inception_preprocessing_radix.py:158-201): per image an optional left-right flip of the resized RS x RS image
+// (flip[b] != 0) followed by the crop whose top-left corner is crop_yx[b] = (y0, x0); the random draws themselves are
+// the caller's (TF's random streams cannot be reproduced).
 __global__ void __launch_bounds__(256)
 preprocess_eval_kernel(const uint8_t* __restrict__ img, int B, int H, int W, int RS, int out_h, int out_w,
-                       float* __restrict__ out) {
+                       float* __restrict__ out, const int* __restrict__ crop_yx = nullptr,
+                       const uint8_t* __restrict__ flip = nullptr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * out_h * out_w) return;
   const int x = (int)(i % out_w), y = (int)((i / out_w) % out_h), b = (int)(i / ((size_t)out_w * out_h));
   // crop_or_pad: crop offset = (RS - out) / 2 when out < RS, pad offset = (out - RS) / 2 otherwise
-  const int ry = (out_h <= RS) ? y + (RS - out_h) / 2 : y - (out_h - RS) / 2;
-  const int rx = (out_w <= RS) ? x + (RS - out_w) / 2 : x - (out_w - RS) / 2;
+  int ry = (out_h <= RS) ? y + (RS - out_h) / 2 : y - (out_h - RS) / 2;
+  int rx = (out_w <= RS) ? x + (RS - out_w) / 2 : x - (out_w - RS) / 2;
+  if (crop_yx != nullptr) {
+    ry = y + crop_yx[2 * b];
+    rx = x + crop_yx[2 * b + 1];
+    if (flip != nullptr && flip[b]) rx = RS - 1 - rx;           // the crop is taken from the flipped image
+  }
   float v[3] = {0.f, 0.f, 0.f};                       // padding is 0 BEFORE the standardisation
   if (ry >= 0 && ry < RS && rx >= 0 && rx < RS) {
     const float sy = (float)H / (float)RS, sx = (float)W / (float)RS;
@@ -885,6 +895,20 @@ extern "C" int comic_preprocess_eval(comic_handle_t h, const uint8_t* images, in
   const size_t n = (size_t)B * out_h * out_w;
   comic::preprocess_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(images, B, H, W, 256,
                                                                                             out_h, out_w, out);
+  h->launches++;
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+extern "C" int comic_preprocess_train(comic_handle_t h, const uint8_t* images, int B, int H, int W, int out_h, int out_w,
+                                      const int32_t* crop_yx, const uint8_t* flip, float* out, void* stream) {
+  COMIC_REQUIRE(h && images && out && crop_yx, COMIC_E_BADARG, "preprocess_train: null argument");
+  COMIC_REQUIRE(B > 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && out_h <= 256 && out_w <= 256, COMIC_E_SHAPE,
+                "preprocess_train: bad shape B=%d H=%d W=%d out=%dx%d (tf.random_crop needs out <= 256)", B, H, W, out_h,
+                out_w);
+  const size_t n = (size_t)B * out_h * out_w;
+  comic::preprocess_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(images, B, H, W, 256,
+                                                                                            out_h, out_w, out, crop_yx, flip);
   h->launches++;
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;

@@ -95,6 +95,7 @@ SIGNATURES = {
     'comic_launch_count': (_I, [_P, C.POINTER(C.c_int64)]),
     'comic_set_precision': (_I, [_P, _I]),
     'comic_set_option': (_I, [_P, _I, _I]),
+    'comic_preprocess_train': (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     'comic_decode_trace': (_I, [_P, _P, _I, _P, _P]),
     'comic_train_workspace_bytes': (_I, [_P, _I, _I, C.POINTER(_SZ)]),
     'comic_dropout_masks': (_I, [_P, _P, _SZ, _F, C.c_uint64, C.c_uint64, _P]),
@@ -311,6 +312,26 @@ class Engine(object):
         out = self.f32(B, int(out_hw[0]), int(out_hw[1]), 3)
         self._check(self.lib.comic_preprocess_eval(self._h, _ptr(images_u8), B, H, W, int(out_hw[0]), int(out_hw[1]),
                                                    _ptr(out), self.stream()))
+        return out
+
+    def preprocess_train(self, images_u8, crop_yx, flip=None, out_hw=(224, 224)):
+        """inception_preprocessing_radix.preprocess_image(is_training=True): uint8 [B,H,W,3] on device -> resize 256
+        bilinear -> left-right flip where flip[b] -> crop at crop_yx[b] = (y0, x0) -> (x - 0.5) * 2.  `crop_yx` int32
+        [B,2] and `flip` uint8 [B] are the caller's random draws (see train.random_crop_flip)."""
+        torch = self.torch
+        images_u8 = images_u8.contiguous()
+        if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[3] != 3:
+            raise ValueError('images must be uint8 [B,H,W,3], got %s %s' % (images_u8.dtype, tuple(images_u8.shape)))
+        B, H, W = (int(v) for v in images_u8.shape[:3])
+        crop = torch.as_tensor(crop_yx).to(device=self.device, dtype=torch.int32).contiguous()
+        if tuple(crop.shape) != (B, 2):
+            raise ValueError('crop_yx must be [B, 2]')
+        if int(crop.min()) < 0 or int(crop[:, 0].max()) > 256 - out_hw[0] or int(crop[:, 1].max()) > 256 - out_hw[1]:
+            raise ValueError('crop offsets must lie in [0, 256 - out]')
+        fl = None if flip is None else torch.as_tensor(flip).to(device=self.device, dtype=torch.uint8).contiguous()
+        out = self.f32(B, int(out_hw[0]), int(out_hw[1]), 3)
+        self._check(self.lib.comic_preprocess_train(self._h, _ptr(images_u8), B, H, W, int(out_hw[0]), int(out_hw[1]),
+                                                    _ptr(crop), _ptr(fl), _ptr(out), self.stream()))
         return out
 
     # -- D0 -------------------------------------------------------------------

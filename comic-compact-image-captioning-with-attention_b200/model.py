@@ -167,6 +167,7 @@ class CaptionModel(ModelBase):
                 weights = wts.init_weights(config, seed=getattr(config, 'rand_seed', 48964896))
             engine.bind_weights(weights)
         self.engine = engine
+        self._weights = weights if weights is not None else getattr(share, '_weights', None)
         self._pinned = {}
 
     # -- ModelBase.get_global_step / update_lr (src/model_base.py:767-773) ----
@@ -192,9 +193,32 @@ class CaptionModel(ModelBase):
         out = self.trainer.forward_backward(fm, im_embed, np.asarray(captions), forward_only=True)
         return out['loss'][1]
 
-    def restore_model(self, weights):
-        """ModelBase.restore_model (src/model_base.py:422-490): bind a W-table."""
-        self.engine.bind_weights(weights)
+    def restore_model(self, weights=None, checkpoint_path=None):
+        """ModelBase.restore_model (src/model_base.py:422-490).  `weights`: a W-table to bind as is; otherwise the
+        TF V2 checkpoint at `checkpoint_path` (default `config.checkpoint_path`; a directory resolves through its
+        `checkpoint` state file) is read with the reference's rules -- resume / whole model minus
+        `checkpoint_exclude_scopes` / CNN only (checkpoint.restore_weights) -- over the current variables.
+        Returns the restore info dict (mode, restored names, optimiser tensors when resuming)."""
+        from . import checkpoint as ckpt
+        info = dict(mode='table', restored=sorted(weights) if weights is not None else [])
+        if weights is None:
+            cur = self.current_weights()
+            weights, info = ckpt.restore_weights(self._config, cur, checkpoint_path=checkpoint_path)
+        if self.trainer is not None:
+            self.trainer.load_variables(weights, info.get('extra'))
+        else:
+            self.engine.bind_weights(weights)
+        self._weights = weights
+        return info
+
+    def current_weights(self):
+        """The model's variables as a W-table of numpy arrays (the trainer's flat buffer when training)."""
+        if self.trainer is not None:
+            return self.trainer.variables_numpy()
+        W = getattr(self, '_weights', None)
+        if W is None:
+            raise ValueError('no W-table is attached to this model (pass weights= when constructing it)')
+        return {k: np.asarray(v) for k, v in W.items()}
 
     def _to_host(self, t, key):
         """Device -> pinned host staging buffer (reused across calls)."""

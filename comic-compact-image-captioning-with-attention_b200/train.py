@@ -58,6 +58,17 @@ def legacy_lr_reduce(config, epoch, learning_rate):
     return learning_rate
 
 
+def random_crop_flip(batch, out_hw=(224, 224), rng=None, resized=256):
+    """The two random draws of `preprocess_for_train` (inception_preprocessing_radix.py:182-185): a fair coin per image
+    for tf.image.random_flip_left_right and a uniform top-left corner for tf.random_crop of the 256 x 256 image.
+    Returns (crop_yx int32 [B,2], flip uint8 [B]) for Engine.preprocess_train."""
+    rng = rng or np.random.default_rng()
+    crop = np.stack([rng.integers(0, resized - out_hw[0] + 1, size=batch),
+                     rng.integers(0, resized - out_hw[1] + 1, size=batch)], axis=1).astype(np.int32)
+    flip = (rng.random(batch) < 0.5).astype(np.uint8)
+    return crop, flip
+
+
 class Trainer(object):
     """Flat fp32 parameter / gradient / Adam-slot buffers over the decoder variables, one
     engine handle, one optimiser step per `step()`."""
@@ -103,6 +114,7 @@ class Trainer(object):
             self.params[o:o + n].copy_(torch.as_tensor(np.asarray(W[name], np.float32).reshape(-1)))
             W[name] = self.params[o:o + n].view(shp if len(shp) else (1,))
         eng.bind_weights(W, with_cnn=with_cnn)
+        self._bound, self._with_cnn = W, with_cnn
         fields = eng.variable_to_grad_field()
         self.grad_views = {}
         for name, (o, n, shp) in self.offsets.items():
@@ -131,6 +143,31 @@ class Trainer(object):
         if seed is not None:
             return int(seed)
         return (int(getattr(self.c, 'rand_seed', 48964896)) * 1000003 + self.global_step) & 0x7fffffff
+
+    def variables_numpy(self):
+        """The trainable variables (views of the flat buffer) plus the bound constants, as host arrays."""
+        W = {k: np.asarray(v) if not hasattr(v, 'cpu') else v.detach().cpu().numpy() for k, v in self._bound.items()}
+        for name in self.offsets:
+            W[name] = self.variable(name).detach().cpu().numpy().reshape(self.offsets[name][2])
+        return W
+
+    def load_variables(self, weights, extra=None):
+        """Overwrite the flat parameter buffer (and, when resuming from a TF checkpoint, the Adam slots `<var>/Adam`,
+        `<var>/Adam_1` and `global_step`) from a W-table; re-binds and re-packs the engine."""
+        torch, eng = self.torch, self.engine
+        W = dict(self._bound)
+        W.update(weights)
+        for name, (o, n, shp) in self.offsets.items():
+            self.params[o:o + n].copy_(torch.as_tensor(np.asarray(W[name], np.float32).reshape(-1)))
+            W[name] = self.params[o:o + n].view(shp if len(shp) else (1,))
+            if extra:
+                for slot, buf in (('/Adam', self.adam_m), ('/Adam_1', self.adam_v)):
+                    if name + slot in extra:
+                        buf[o:o + n].copy_(torch.as_tensor(np.asarray(extra[name + slot], np.float32).reshape(-1)))
+        if extra and 'global_step' in extra:
+            self.global_step = int(np.asarray(extra['global_step']))
+        self._bound = W
+        eng.bind_weights(W, with_cnn=self._with_cnn)
 
     def make_masks(self, B, T_run, seed):
         """Seeded Philox dropout masks (DropoutWrapper in/out, attention-map dropout)."""

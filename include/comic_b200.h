@@ -176,6 +176,14 @@ int comic_encode_fwd(comic_handle_t h, const float* images, int B, float* fm_out
 int comic_preprocess_eval(comic_handle_t h, const uint8_t* images, int B, int H, int W, int out_h, int out_w,
                           float* out, void* stream);
 
+/* Training-time pre-processing (inception_preprocessing_radix.py:158-201 `preprocess_for_train`, after the shared
+ * convert_image_dtype + resize_bilinear(256, 256) of :270-273): optional left-right flip of the resized image
+ * (flip[b] != 0; NULL = never), crop of out_h x out_w at crop_yx[b] = (y0, x0) with 0 <= y0 <= 256 - out_h, same for x
+ * (tf.random_crop), (x - 0.5) * 2.  The random draws are the caller's.  images uint8 [B,H,W,3] device, out fp32
+ * [B,out_h,out_w,3] device. */
+int comic_preprocess_train(comic_handle_t h, const uint8_t* images, int B, int H, int W, int out_h, int out_w,
+                           const int32_t* crop_yx, const uint8_t* flip, float* out, void* stream);
+
 /* D0: MultiHeadAttV3.__init__ common/ops_rnn.py:441-477: keys = fm.W_k once per
  * IMAGE (the reference does it per tiled beam row); values_out only for
  * `independent`. fm [B,M,C]; keys_out [B,M,R]; values_out [B,M,R] or NULL. */

@@ -172,3 +172,18 @@ def preprocess_eval(images_u8, out_hw=(224, 224), resize=256):
     hh, ww = min(oh, resize), min(ow, resize)
     out[:, yd:yd + hh, xd:xd + ww] = r[:, ys:ys + hh, xs:xs + ww]
     return (out - np.float32(0.5)) * np.float32(2.0)
+
+
+def preprocess_train(images_u8, crop_yx, flip=None, out_hw=(224, 224), resize=256):
+    """common/inputs/preprocessing/inception_preprocessing_radix.py:270-273 + :158-201 (is_training=True) with the random
+    draws given: convert_image_dtype, resize_bilinear(256, 256), tf.image.random_flip_left_right (flip[b]),
+    tf.random_crop at crop_yx[b], (x - 0.5) * 2.   PARITY UNPINNED against TF (restated)."""
+    x = np.asarray(images_u8)
+    B = x.shape[0]
+    full = preprocess_eval(x, (resize, resize), resize)                 # resized image, already standardised
+    out = np.empty((B, out_hw[0], out_hw[1], 3), np.float32)
+    for b in range(B):
+        im = full[b, :, ::-1] if (flip is not None and flip[b]) else full[b]
+        y0, x0 = int(crop_yx[b][0]), int(crop_yx[b][1])
+        out[b] = im[y0:y0 + out_hw[0], x0:x0 + out_hw[1]]
+    return out

@@ -595,3 +595,24 @@ def test_rnn_decoder_training_matches_oracle(torch_mod):
     np.testing.assert_array_equal(out_ids.cpu().numpy(), ref['ids'])
     hist = ref['alignment_history'].reshape(ref['T_run'], B, 8, 196).transpose(1, 2, 0, 3)
     assert rel_err(state.alignment_history.cpu().numpy(), hist) < 1e-3
+
+
+@pytest.mark.parametrize('B,H,W', [(3, 240, 320), (2, 480, 640), (2, 100, 75)])
+def test_preprocess_train_bit_exact(torch_mod, B, H, W):
+    """comic_preprocess_train (resize 256 -> flip -> crop at the given corner -> standardise) against the NumPy
+    restatement of preprocess_for_train with the same draws."""
+    import inception_v1_oracle as I
+    from comic_b200.train import random_crop_flip
+    torch = torch_mod
+    c = comic_config()
+    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False)
+    rng = np.random.default_rng(H + W)
+    x = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    crop, flip = random_crop_flip(B, rng=rng)
+    crop[0] = (0, 32)                                # the corners of the offset range
+    crop[-1] = (32, 0)
+    flip[0], flip[-1] = 1, 0
+    got = eng.preprocess_train(torch.from_numpy(x).to(eng.device), crop, flip).cpu().numpy()
+    np.testing.assert_array_equal(got, I.preprocess_train(x, crop, flip))
+    with pytest.raises(ValueError):
+        eng.preprocess_train(torch.from_numpy(x).to(eng.device), np.array([[0, 33]] * B), flip)

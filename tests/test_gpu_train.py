@@ -214,3 +214,34 @@ def test_default_train_step_applies_dropout_and_eval_is_forward_only(torch_mod):
     ppl_nodrop, _ = m.train_step(img, caps, lr=0.0, dropout=False)
     assert abs(float(ppl_nodrop.item()) - plain) < 2e-4 * max(1.0, abs(plain))
     assert abs(float(ppl_default.item()) - plain) > 1e-3 * max(1.0, abs(plain))
+
+
+def test_restore_model_from_a_v2_checkpoint(torch_mod, tmp_path):
+    """CaptionModel.restore_model with a TF V2 checkpoint path: variables, Adam slots and global_step come back
+    (src/model_base.py:422-490, resume case) and the restored model decodes like the one that wrote it."""
+    from comic_b200.model import CaptionModel
+    from comic_b200 import checkpoint as ck
+    from _common import images
+    c = comic_config(train_mode='decoder', max_step=20, infer_max_length=2)
+    W = make_weights(c)
+    m = CaptionModel(c, 'train', weights=W)
+    _, _, _, caps, _, _ = _train_case(c, B=2, L=6, seed=3, dropout=False)
+    img = images(2, seed=4)
+    m.train_step(img, caps, seed=1, lr=1e-3)
+    tr = m.trainer
+    tensors = tr.variables_numpy()
+    for name, (o, n, shp) in tr.offsets.items():
+        tensors[name + '/Adam'] = tr.adam_m[o:o + n].cpu().numpy().reshape(shp)
+        tensors[name + '/Adam_1'] = tr.adam_v[o:o + n].cpu().numpy().reshape(shp)
+    tensors['global_step'] = np.array(tr.global_step, np.int64)
+    prefix = str(tmp_path / 'model_compact-1')
+    ck.write_v2(prefix, tensors, with_data_crc=False)
+    c2 = comic_config(train_mode='decoder', max_step=20, infer_max_length=2, checkpoint_path=str(tmp_path), resume_training=True)
+    m2 = CaptionModel(c2, 'train', weights=make_weights(c2, seed=99))
+    info = m2.restore_model()
+    assert info['mode'] == 'resume' and m2.trainer.global_step == 1
+    assert torch_mod.equal(m2.trainer.params, tr.params) and torch_mod.equal(m2.trainer.adam_m, tr.adam_m)
+    a = CaptionModel(c, 'infer', reuse=True, share=m).run(img)
+    b = CaptionModel(c2, 'infer', reuse=True, share=m2).run(img)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
