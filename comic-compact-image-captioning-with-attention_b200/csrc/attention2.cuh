@@ -61,6 +61,7 @@ constexpr int kSliceFloats = kPos * kR;
 constexpr int kSliceBytes = kSliceFloats * 4;   // 8 KB
 constexpr int kCtxWarps = 4;
 constexpr float kTwoLog2e = 2.885390081777927f;
+constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -200,6 +201,8 @@ struct Args {
   int t, n_rows;
   float* scratch;         // [2 * gridDim.x][K * (512 + 8)]: partial contexts / sums of images split across CTAs
   int* counters;          // [B], zero between launches: parts of an image that have arrived
+  float* hist_scale;       // optional [n_rows][8]: when set, hist_t keeps the UNNORMALISED weights and 1 / sum goes here (the
+                           // consumer multiplies: attn_top_gather_kernel); when null the history rows are rescaled in place
   long long* trace;       // diagnostics (COMIC_A2_TRACE builds): [grid][warps][kTraceSlices][8] clock64 stamps, or nullptr
 };
 constexpr int kTraceSlices = 256;
@@ -231,10 +234,10 @@ struct Layout {
   static constexpr int qbuf = consts + 3 * kR * 4;                 // [2][ qc [K][512] | qg [K][512] ]
   static constexpr int qstat = qbuf + 2 * 2 * K * kR * 4;          // [2][K][2]  sqq, sum qc
   static constexpr int ssum = qstat + 2 * K * 2 * 4;               // [K][8] 1 / sum p of the image being finalised
-  static constexpr int part = (ssum + K * kH * 4 + 15) & ~15;      // [2][K * 520]: the context warps' partial sums of one image segment
+  static constexpr int part = (ssum + 2 * K * kH * 4 + 15) & ~15;      // [2][K * 520]: the context warps' partial sums of one image segment
   static constexpr int bars = part + kCtxWarps2 * K * (kR + kH) * 4;   // per context warp: [K][512] context partials | [K][8] sum p      // full[S] scored[S] empty[S] qfull[2] qempty[2] pempty[2] imgdone partfree | next slice
-  static constexpr int pbuf = (bars + (3 * STAGES + 8) * 8 + 8 + 15) & ~15;   // [2][K][8][M]
-  static __host__ __device__ size_t bytes(int M) { return (size_t)pbuf + (size_t)2 * K * kH * M * 4; }
+  static constexpr int pbuf = (bars + (3 * STAGES + 8) * 8 + 8 + 15) & ~15;   // [STAGES][K][8][4]: unnormalised weights of the slice in each stage
+  static __host__ __device__ size_t bytes(int) { return (size_t)pbuf + (size_t)STAGES * K * kH * kPos * 4; }
 };
 
 // Pass 2 works on chunks of four channels, software-pipelined by hand: `front4` turns staged operands into 2^y' for
@@ -314,8 +317,8 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
   uint64_t* imgdone = pempty + 2;
   uint64_t* partfree = imgdone + 1;
   int* next_g = reinterpret_cast<int*>(partfree + 1);
-  float* sm_p = reinterpret_cast<float*>(smem + L::pbuf);     // [2][K][8][M]
-  const int pimg = K * kH * M;                                // floats per image in sm_p
+  float* sm_p = reinterpret_cast<float*>(smem + L::pbuf);     // [STAGES][K][8][4]
+  constexpr int kPStage = K * kH * kPos;                      // floats per stage in sm_p
 
   // this CTA's contiguous range of the step's slice sequence; (b0, sl0) = image / slice of its first slice
   const long long T_all = (long long)a.B * spi;
@@ -386,25 +389,28 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
     const uint32_t q_minus_c = smem_u32(sm_q) - smem_u32(sm_c);
     float sv = 0.f;                                           // sum of v over this lane's 32 channels
     for (int c = 0; c < kD / 2; ++c) sv += a.vvec[hp * kD + hf * 32 + c];
-    const float inv_T = 1.0f / a.temperature[0];
-    const float shift = a.bound[hp];
+    const float inv_T = kLog2e / a.temperature[0];            // p = 2^((score / T - bound) log2 e)
+    const float shift = a.bound[hp] * kLog2e;
     int last_img = -1;
     float sqq[K], sumq[K];
-    // Slices are claimed one at a time, in order: at most NSW < STAGES slices are claimed and unfinished, so a warp
-    // never waits on a stage whose previous use is still pending (the parity waits would alias).
-    for (;;) {
+    // Score warp w takes slices w, w + NSW, ... of the CTA's sequence (no claim counter: a shared-memory atomic, a
+    // shuffle and an integer division per slice were ~1.5 k cycles of dependent scalar code).  At most NSW < STAGES
+    // slices are in work, so a warp never waits on a stage whose previous use is still pending (the parity waits
+    // would alias).
+    const float spi_inv = 1.0f / (float)spi;
+    for (int g = warp; g < n_g; g += NSW) {
       A2_STAMP(0);
-      int g = 0;
-      if (lane == 0) g = atomicAdd(next_g, 1);
-      g = __shfl_sync(0xffffffffu, g, 0);
-      if (g >= n_g) break;
       int pos, ii, sl;
       if (g < len_last) { pos = 0; ii = n_seg - 1; sl = g; }
-      else { const int v = g - len_last + sl0; ii = v / spi; sl = v - ii * spi; pos = ii + (len_last > 0 ? 1 : 0); }
+      else {
+        const int v = g - len_last + sl0;
+        ii = (int)(((float)v + 0.5f) * spi_inv);               // v / spi, exact for v < 2^20
+        sl = v - ii * spi;
+        pos = ii + (len_last > 0 ? 1 : 0);
+      }
       const int par = pos & 1;
       if (pos != last_img) {
         mbar_wait(&qfull[par], (uint32_t)((pos >> 1) & 1));
-        mbar_wait(&pempty[par], (uint32_t)(((pos >> 1) & 1) ^ 1));
 #pragma unroll
         for (int j = 0; j < K; ++j) {
           sqq[j] = sm_qs[(par * K + j) * 2 + 0];
@@ -495,14 +501,14 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
       back4<K>(vprev, eaA, ebA, outA, escale);
       back4<K>(vprev, eaB, ebB, outB, escale);
       A2_STAMP(4);
-      float* pdst = sm_p + (size_t)par * pimg + hp * M + m;
+      float* pdst = sm_p + s * kPStage + hp * kPos + rp;
 #pragma unroll
       for (int j = 0; j < K; ++j) {
         const float oa = outA[j] + __shfl_xor_sync(0xffffffffu, outA[j], 8);   // two half heads
         const float ob = outB[j] + __shfl_xor_sync(0xffffffffu, outB[j], 8);
         if (hf == 0) {
-          pdst[(size_t)j * kH * M] = expf(oa * inv_T - shift);
-          pdst[(size_t)j * kH * M + 2] = expf(ob * inv_T - shift);
+          pdst[j * kH * kPos] = ex2_approx(fmaf(oa, inv_T, -shift));
+          pdst[j * kH * kPos + 2] = ex2_approx(fmaf(ob, inv_T, -shift));
         }
       }
       __syncwarp();
@@ -532,28 +538,32 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
     int g = 0;
     for (int pos = 0; pos < n_seg; ++pos) {
       const int ii = seg_of(pos);
-      const int par = pos & 1;
       const int s_hi = seg_hi(ii);
+      // unnormalised weights go straight to the history rows of the image ([K][8][M], contiguous); the finaliser
+      // rescales them in place once the image's sums are known
+      float* hrow = a.hist_t ? a.hist_t + ((size_t)(b0 + ii) * K * kH + lane) * M : nullptr;
       for (int sl = seg_lo(ii); sl < s_hi; ++sl, ++g) {
         if ((g & (kCtxWarps2 - 1)) != cw) continue;
         const int s = g % STAGES;
         A2_STAMP(0);
         mbar_wait(&scored[s], (uint32_t)((g / STAGES) & 1));
         A2_STAMP(1);
+        if (hrow != nullptr && lane < K * kH)
+          *reinterpret_cast<float4*>(hrow + sl * kPos) = *reinterpret_cast<const float4*>(sm_p + s * kPStage + lane * kPos);
         const float* tile = reinterpret_cast<const float*>(smem + L::ring + s * kSliceBytes) + lane * 4;
-        const float* pp = sm_p + (size_t)par * pimg + hd0 * M + sl * kPos;
+        const float* pp = sm_p + s * kPStage + hd0 * kPos;
         float4 kr[2][kPos], p4[2][K];
 #pragma unroll
         for (int r = 0; r < kPos; ++r) kr[0][r] = *reinterpret_cast<const float4*>(tile + r * kR);
 #pragma unroll
-        for (int j = 0; j < K; ++j) p4[0][j] = *reinterpret_cast<const float4*>(pp + (size_t)(j * kH) * M);
+        for (int j = 0; j < K; ++j) p4[0][j] = *reinterpret_cast<const float4*>(pp + (j * kH) * kPos);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i + 1 < 4) {
 #pragma unroll
             for (int r = 0; r < kPos; ++r) kr[(i + 1) & 1][r] = *reinterpret_cast<const float4*>(tile + r * kR + (i + 1) * 128);
 #pragma unroll
-            for (int j = 0; j < K; ++j) p4[(i + 1) & 1][j] = *reinterpret_cast<const float4*>(pp + (size_t)(j * kH + 2 * (i + 1)) * M);
+            for (int j = 0; j < K; ++j) p4[(i + 1) & 1][j] = *reinterpret_cast<const float4*>(pp + (j * kH + 2 * (i + 1)) * kPos);
           }
 #pragma unroll
           for (int j = 0; j < K; ++j) {
@@ -590,6 +600,8 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
           acc[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
           S[j][i] = 0.f;
         }
+      if (!(seg_lo(ii) == 0 && s_hi == spi) && hrow != nullptr && a.hist_scale == nullptr)
+        __threadfence();                                      // part of an image: its history rows are rescaled by another CTA
       __syncwarp();
       if (lane == 0) mbar_arrive(imgdone);
       A2_STAMP(3);
@@ -605,148 +617,9 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
     const int hd0 = lane >> 4;
     const int m4 = M / 4;
     auto cta_of = [&](long long x) { return (int)(((x + 1) * G + T_all - 1) / T_all) - 1; };   // CTA that owns slice x
-    for (int pos = 0; pos < n_seg; ++pos) {
-      const int ii = seg_of(pos);
-      const int par = pos & 1;
-      const int b = b0 + ii;
-      const int lo = seg_lo(ii), hi = seg_hi(ii);
-      A2_STAMP(0);
-      mbar_wait(imgdone, (uint32_t)(pos & 1));
-      A2_STAMP(1);
-      float4 tot[K][4];
-#pragma unroll
-      for (int j = 0; j < K; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 x = *reinterpret_cast<const float4*>(sm_part + j * kR + (lane + 32 * i) * 4);
-          const float4 y = *reinterpret_cast<const float4*>(sm_part + K * (kR + kH) + j * kR + (lane + 32 * i) * 4);
-          tot[j][i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
-        }
-      if (lane < K * kH) sm_inv[lane] = sm_part[K * kR + lane] + sm_part[K * (kR + kH) + K * kR + lane];   // sum p of the segment
-      __syncwarp();
-      if (lane == 0) mbar_arrive(partfree);
-      const float* pim = sm_p + (size_t)par * pimg;
-      float* hdst = a.hist_t ? a.hist_t + (size_t)b * K * kH * M : nullptr;   // rows b*K + j, each [8][M]: contiguous, same order as sm_p
-      if (lo == 0 && hi == spi) {
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float inv = 1.0f / sm_inv[j * kH + hd0 + 2 * i];
-            *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * K + j) * a.ld_ctx + (lane + 32 * i) * 4) =
-                make_float4(tot[j][i].x * inv, tot[j][i].y * inv, tot[j][i].z * inv, tot[j][i].w * inv);
-          }
-        if (hdst != nullptr) {
-          // 4 (beam, head) rows at a time: 8 independent shared loads in flight per lane
-          for (int pr0 = 0; pr0 < K * kH; pr0 += 4) {
-            float4 v[4][2];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              if (lane < m4) v[r][0] = *reinterpret_cast<const float4*>(pim + (size_t)(pr0 + r) * M + lane * 4);
-              if (lane + 32 < m4) v[r][1] = *reinterpret_cast<const float4*>(pim + (size_t)(pr0 + r) * M + (lane + 32) * 4);
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const float inv = 1.0f / sm_inv[pr0 + r];
-              float* d = hdst + (size_t)(pr0 + r) * M;
-              if (lane < m4) *reinterpret_cast<float4*>(d + lane * 4) = make_float4(v[r][0].x * inv, v[r][0].y * inv, v[r][0].z * inv, v[r][0].w * inv);
-              if (lane + 32 < m4) *reinterpret_cast<float4*>(d + (lane + 32) * 4) = make_float4(v[r][1].x * inv, v[r][1].y * inv, v[r][1].z * inv, v[r][1].w * inv);
-            }
-          }
-        }
-      } else {
-        // part of an image: park the partial results, the last part to arrive combines them
-        const int c_first = cta_of((long long)b * spi), c_last = cta_of((long long)(b + 1) * spi - 1);
-        auto slot_of = [&](int c) { return 2 * c + (((int)((T_all * c / G) / spi) == b) ? 0 : 1); };
-        float* sc = a.scratch + (size_t)slot_of((int)blockIdx.x) * kPartFloats;
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sc + j * kR + (lane + 32 * i) * 4) = tot[j][i];
-        if (lane < K * kH) sc[K * kR + lane] = sm_inv[lane];
-        if (hdst != nullptr) {
-          for (int pr = 0; pr < K * kH; ++pr)
-            for (int i = lo + lane; i < hi; i += 32)
-              *reinterpret_cast<float4*>(hdst + (size_t)pr * M + i * 4) = *reinterpret_cast<const float4*>(pim + (size_t)pr * M + i * 4);
-        }
-        __syncwarp();
-        int old = 0;
-        if (lane == 0) {
-          __threadfence();
-          old = atomicAdd(a.counters + b, 1);
-        }
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old == c_last - c_first) {
-          __threadfence();
-          if (lane < K * kH) {
-            float s = 0.f;
-            for (int c = c_first; c <= c_last; ++c) s += __ldcg(a.scratch + (size_t)slot_of(c) * kPartFloats + K * kR + lane);
-            sm_inv[lane] = s;
-          }
-          __syncwarp();
-          // parts are added in CTA order; the loads of one beam row (4 quads x 2 parts) are issued together
-#pragma unroll
-          for (int j = 0; j < K; ++j) {
-            float4 t[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int c = c_first; c <= c_last; c += 2) {
-              const bool two = c + 1 <= c_last;
-              const float* s0 = a.scratch + (size_t)slot_of(c) * kPartFloats + j * kR;
-              const float* s1 = two ? a.scratch + (size_t)slot_of(c + 1) * kPartFloats + j * kR : s0;
-              float4 x[4], y[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                x[i] = __ldcg(reinterpret_cast<const float4*>(s0 + (lane + 32 * i) * 4));
-                y[i] = __ldcg(reinterpret_cast<const float4*>(s1 + (lane + 32 * i) * 4));
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                t[i].x += x[i].x; t[i].y += x[i].y; t[i].z += x[i].z; t[i].w += x[i].w;
-                if (two) { t[i].x += y[i].x; t[i].y += y[i].y; t[i].z += y[i].z; t[i].w += y[i].w; }
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float inv = 1.0f / sm_inv[j * kH + hd0 + 2 * i];
-              *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * K + j) * a.ld_ctx + (lane + 32 * i) * 4) =
-                  make_float4(t[i].x * inv, t[i].y * inv, t[i].z * inv, t[i].w * inv);
-            }
-          }
-          if (hdst != nullptr) {
-            // rescale the unnormalised history rows of the whole image, 4 independent 16-byte loads in flight per lane
-            const int n4 = K * kH * m4;
-            for (int i0 = lane; i0 < n4; i0 += 128) {
-              float4 v[4];
-              int idx[4];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                idx[r] = i0 + 32 * r;
-                if (idx[r] < n4) v[r] = __ldcg(reinterpret_cast<const float4*>(hdst) + idx[r]);
-              }
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                if (idx[r] < n4) {
-                  const float inv = 1.0f / sm_inv[idx[r] / m4];
-                  reinterpret_cast<float4*>(hdst)[idx[r]] = make_float4(v[r].x * inv, v[r].y * inv, v[r].z * inv, v[r].w * inv);
-                }
-              }
-            }
-          }
-          if (lane == 0) a.counters[b] = 0;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&pempty[par]);
-      A2_STAMP(2);
-#if COMIC_A2_TRACE
-      if (tn < kTraceSlices - 1) ++tn;
-#endif
-    }
-  } else {
-    // =========================== query preparation + TMA producer ===========================
-    // Lane 0 feeds the ring; the whole warp prepares the queries of image ii + 1 half-way through image ii's slices
-    // (the prefetched stages cover the pause), so neither the first key slice nor the queries of an image are late.
+    // Query preparation (centred queries, their gamma'-scaled copies, sum of squares) for segment pos into buffer
+    // pos & 1: segments 0 and 1 up front, segment pos + 2 as soon as segment pos is complete (its buffer is then free
+    // and the score warps need the new contents only after all of segment pos + 1).
     auto prep_queries = [&](int pos) {
       const int ii = seg_of(pos);
       const int par = pos & 1;
@@ -792,12 +665,152 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
       }
     };
     prep_queries(0);
+    if (n_seg > 1) prep_queries(1);
+    for (int pos = 0; pos < n_seg; ++pos) {
+      const int ii = seg_of(pos);
+      const int b = b0 + ii;
+      const int lo = seg_lo(ii), hi = seg_hi(ii);
+      A2_STAMP(0);
+      mbar_wait(imgdone, (uint32_t)(pos & 1));
+      A2_STAMP(1);
+      if (pos + 2 < n_seg) prep_queries(pos + 2);
+      float4 tot[K][4];
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x = *reinterpret_cast<const float4*>(sm_part + j * kR + (lane + 32 * i) * 4);
+          const float4 y = *reinterpret_cast<const float4*>(sm_part + K * (kR + kH) + j * kR + (lane + 32 * i) * 4);
+          tot[j][i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+        }
+      if (lane < K * kH) sm_inv[lane] = sm_part[K * kR + lane] + sm_part[K * (kR + kH) + K * kR + lane];   // sum p of the segment
+      __syncwarp();
+      if (lane == 0) mbar_arrive(partfree);
+      float* hdst = a.hist_t ? a.hist_t + (size_t)b * K * kH * M : nullptr;   // rows b*K + j, each [8][M]: contiguous
+      // rescale the unnormalised history rows of the whole image in place (written by the context warps of this CTA, or,
+      // for a split image, of all its CTAs), 8 independent 16-byte loads in flight per lane
+      auto rescale_history = [&]() {
+        const int n4 = K * kH * m4;
+        for (int i0 = lane; i0 < n4; i0 += 256) {
+          float4 v[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (i0 + 32 * r < n4) v[r] = __ldcg(reinterpret_cast<const float4*>(hdst) + i0 + 32 * r);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int idx = i0 + 32 * r;
+            if (idx < n4) {
+              const float inv = sm_inv[K * kH + idx / m4];
+              reinterpret_cast<float4*>(hdst)[idx] = make_float4(v[r].x * inv, v[r].y * inv, v[r].z * inv, v[r].w * inv);
+            }
+          }
+        }
+      };
+      if (lo == 0 && hi == spi) {
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float inv = 1.0f / sm_inv[j * kH + hd0 + 2 * i];
+            *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * K + j) * a.ld_ctx + (lane + 32 * i) * 4) =
+                make_float4(tot[j][i].x * inv, tot[j][i].y * inv, tot[j][i].z * inv, tot[j][i].w * inv);
+          }
+        if (hdst != nullptr) {
+          if (a.hist_scale != nullptr) {
+            if (lane < K * kH) a.hist_scale[(size_t)b * K * kH + lane] = 1.0f / sm_inv[lane];
+          } else {
+            if (lane < K * kH) sm_inv[K * kH + lane] = 1.0f / sm_inv[lane];
+            __syncwarp();
+            rescale_history();
+          }
+        }
+      } else {
+        // part of an image: park the partial results, the last part to arrive combines them
+        const int c_first = cta_of((long long)b * spi), c_last = cta_of((long long)(b + 1) * spi - 1);
+        auto slot_of = [&](int c) { return 2 * c + (((int)((T_all * c / G) / spi) == b) ? 0 : 1); };
+        float* sc = a.scratch + (size_t)slot_of((int)blockIdx.x) * kPartFloats;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sc + j * kR + (lane + 32 * i) * 4) = tot[j][i];
+        if (lane < K * kH) sc[K * kR + lane] = sm_inv[lane];
+        __syncwarp();
+        A2_STAMP(6);
+        int old = 0;
+        if (lane == 0) {
+          __threadfence();
+          old = atomicAdd(a.counters + b, 1);
+        }
+        old = __shfl_sync(0xffffffffu, old, 0);
+        A2_STAMP(3);
+        if (old == c_last - c_first) {
+          __threadfence();
+          if (lane < K * kH) {
+            float s = 0.f;
+            for (int c = c_first; c <= c_last; ++c) s += __ldcg(a.scratch + (size_t)slot_of(c) * kPartFloats + K * kR + lane);
+            sm_inv[lane] = s;
+          }
+          __syncwarp();
+          // parts are added in CTA order; the loads of one beam row (4 quads x 2 parts) are issued together
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            float4 t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = c_first; c <= c_last; c += 2) {
+              const bool two = c + 1 <= c_last;
+              const float* s0 = a.scratch + (size_t)slot_of(c) * kPartFloats + j * kR;
+              const float* s1 = two ? a.scratch + (size_t)slot_of(c + 1) * kPartFloats + j * kR : s0;
+              float4 x[4], y[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                x[i] = __ldcg(reinterpret_cast<const float4*>(s0 + (lane + 32 * i) * 4));
+                y[i] = __ldcg(reinterpret_cast<const float4*>(s1 + (lane + 32 * i) * 4));
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                t[i].x += x[i].x; t[i].y += x[i].y; t[i].z += x[i].z; t[i].w += x[i].w;
+                if (two) { t[i].x += y[i].x; t[i].y += y[i].y; t[i].z += y[i].z; t[i].w += y[i].w; }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float inv = 1.0f / sm_inv[j * kH + hd0 + 2 * i];
+              *reinterpret_cast<float4*>(a.ctx_out + (size_t)(b * K + j) * a.ld_ctx + (lane + 32 * i) * 4) =
+                  make_float4(t[i].x * inv, t[i].y * inv, t[i].z * inv, t[i].w * inv);
+            }
+          }
+          A2_STAMP(4);
+          if (hdst != nullptr) {
+            if (a.hist_scale != nullptr) {
+              if (lane < K * kH) a.hist_scale[(size_t)b * K * kH + lane] = 1.0f / sm_inv[lane];
+            } else {
+              if (lane < K * kH) sm_inv[K * kH + lane] = 1.0f / sm_inv[lane];
+              __syncwarp();
+              rescale_history();
+            }
+          }
+          A2_STAMP(5);
+          if (lane == 0) a.counters[b] = 0;
+        }
+      }
+      __syncwarp();
+      A2_STAMP(2);
+#if COMIC_A2_TRACE
+      if (tn < kTraceSlices - 1) ++tn;
+#endif
+    }
+  } else {
+    // =========================== TMA producer ===========================
+    // Lane 0 feeds the ring and does nothing else: it never waits on anything but a free stage.  (It used to prepare
+    // the queries of the next segment as well, which needs the segment before the current one completely scored; the
+    // producer runs up to STAGES slices ahead of that point, so it stalled ~10 k cycles twice per CTA and drained the
+    // ring -- profiles/r07a_attn2_trace_dist.txt.)
     int g = 0;
     for (int pos = 0; pos < n_seg; ++pos) {
       const int ii = seg_of(pos);
       const int lo = seg_lo(ii), hi = seg_hi(ii);
       const float* src = a.keys + ((size_t)(b0 + ii) * spi + lo) * kSliceFloats;
-      bool prepped = false;
 #if COMIC_A2_L2_AHEAD > 0
       if (lane == 0 && pos == 0) {
         const int n0 = (hi - lo) < COMIC_A2_L2_AHEAD ? (hi - lo) : COMIC_A2_L2_AHEAD;
@@ -825,11 +838,6 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
           mbar_arrive_expect_tx(&full[s], kSliceBytes);
           tma_bulk_g2s(smem + L::ring + s * kSliceBytes, src + (size_t)(sl - lo) * kSliceFloats, kSliceBytes, &full[s]);
         }
-        if (!prepped && pos + 1 < n_seg && (sl >= spi / 2 || sl == hi - 1)) {
-          __syncwarp();
-          prep_queries(pos + 1);
-          prepped = true;
-        }
       }
     }
   }
@@ -845,7 +853,7 @@ namespace a2 {
 #define COMIC_A2_NSW 12
 #endif
 #ifndef COMIC_A2_STAGES
-#define COMIC_A2_STAGES 18
+#define COMIC_A2_STAGES 21
 #endif
 
 // Launch for k beams per image (instantiated: 1, 2, 3).  Returns cudaErrorInvalidValue for shapes the kernel

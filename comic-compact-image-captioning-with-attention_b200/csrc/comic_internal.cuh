@@ -195,6 +195,7 @@ struct StepIO {
   float* h_drop;           // [N, R] or nullptr (train): query/logits use this when set
   float* ctx_new;          // [N, A]
   float* hist_t;           // [N, H*M] or nullptr
+  float* hist_scale;       // [N, H] or nullptr: streaming attention kernel only -- hist_t stays unnormalised, 1 / sum goes here
   const float* in_mask; const float* out_mask; const float* att_mask;
   float in_keep, out_keep, att_keep;
   const int* fin_count; int t; int n_rows;

@@ -583,17 +583,20 @@ __global__ void sorted_top_beam_kernel(const int* __restrict__ parent_ids, const
 }
 
 // attn_out[b, h, t, m] = hist[t, b*k + sorted0[t,b], h*M + m]  (t < T), else 0.
-__global__ void attn_top_gather_kernel(const float* __restrict__ hist, const int* __restrict__ sorted0,
-                                       const int* __restrict__ T_dev, int Tmax, int B, int k, int HM, int M,
-                                       float* __restrict__ out) {
+// scale (optional, [T, B*k, H]): the streaming attention kernel leaves the history unnormalised and stores 1 / sum there.
+__global__ void attn_top_gather_kernel(const float* __restrict__ hist, const float* __restrict__ scale,
+                                       const int* __restrict__ sorted0, const int* __restrict__ T_dev, int Tmax, int B,
+                                       int k, int HM, int M, float* __restrict__ out) {
   int t = blockIdx.x, b = blockIdx.y;
   int T = *T_dev;
   int s = sorted0 ? sorted0[(size_t)t * B + b] : 0;
   int H = HM / M;
-  const float* src = (t < T && s >= 0) ? hist + ((size_t)t * B * k + (size_t)b * k + s) * HM : nullptr;
+  const size_t row = (size_t)t * B * k + (size_t)b * k + (s >= 0 ? s : 0);
+  const float* src = (t < T && s >= 0) ? hist + row * HM : nullptr;
+  const float* sc = (src && scale) ? scale + row * H : nullptr;
   for (int i = threadIdx.x; i < HM; i += blockDim.x) {
     int hh = i / M, m = i - hh * M;
-    out[(((size_t)b * H + hh) * Tmax + t) * M + m] = src ? src[i] : 0.f;
+    out[(((size_t)b * H + hh) * Tmax + t) * M + m] = src ? (sc ? src[i] * sc[hh] : src[i]) : 0.f;
   }
 }
 
@@ -777,7 +780,7 @@ static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb
     a2::Args aa{};
     aa.keys = io.keys; aa.kstats = io.kstats; aa.bound = io.abound; aa.lq = sb.lq; aa.ld_lq = h->LQ; aa.q_off = h->Vp;
     aa.gamma = h->w.ln_gamma; aa.beta = h->w.ln_beta; aa.vvec = h->w.attention_v; aa.temperature = h->w.temperature;
-    aa.ctx_out = ctx_dst; aa.ld_ctx = ld_ctx; aa.hist_t = io.hist_t; aa.B = B; aa.M = h->M;
+    aa.ctx_out = ctx_dst; aa.ld_ctx = ld_ctx; aa.hist_t = io.hist_t; aa.hist_scale = io.hist_scale; aa.B = B; aa.M = h->M;
     aa.fin_count = io.fin_count; aa.t = io.t; aa.n_rows = io.n_rows; aa.trace = nullptr;
     aa.scratch = io.a2_scratch; aa.counters = io.a2_counters;
     Prof pf(h, T_SCORES, st);
@@ -1004,6 +1007,7 @@ struct LoopBufs {
   StepBufs sb;
   float *c[2], *h[2], *ctx[2];
   float* hist;
+  float* hist_scale;       // [T, N, H]: see attn_top_gather_kernel
   int *tok, *src, *src0;
   float* cum;
   uint8_t* fin;
@@ -1025,6 +1029,7 @@ static void carve_loop(comic_handle_t h, Carver& cv, int B, int k, int T, bool w
     lb.ctx[i] = cv.take<float>((size_t)N * h->A);
   }
   lb.hist = cv.take<float>(want_hist ? (size_t)T * N * h->H * h->M : 1);
+  lb.hist_scale = cv.take<float>(want_hist ? (size_t)T * N * h->H : 1);
   lb.tok = cv.take<int>(N);
   lb.src = cv.take<int>(N);
   lb.src0 = cv.take<int>(N);
@@ -1246,6 +1251,7 @@ extern "C" int comic_decode_greedy(comic_handle_t h, const float* keys, const fl
     io.ctx_prev = lb.ctx[cur];
     io.c_new = lb.c[cur ^ 1]; io.h_new = lb.h[cur ^ 1]; io.ctx_new = lb.ctx[cur ^ 1];
     io.hist_t = attn_out ? lb.hist + (size_t)t * N * h->H * h->M : nullptr;
+    io.hist_scale = (attn_out && io.kstats) ? lb.hist_scale + (size_t)t * N * h->H : nullptr;
     io.in_keep = io.out_keep = io.att_keep = 1.f;
     io.fin_count = lb.fin_count; io.t = t; io.n_rows = N;
     int rc = run_step(h, io, lb.sb, B, 1, st);
@@ -1260,7 +1266,8 @@ extern "C" int comic_decode_greedy(comic_handle_t h, const float* keys, const fl
     compute_T_kernel<<<1, 32, 0, st>>>(lb.fin_count, max_it, N, T_out, persisted ? lb.bar + 1 : nullptr);
     if (attn_out && max_it > 0) {
       dim3 g(max_it, B);
-      attn_top_gather_kernel<<<g, 256, 0, st>>>(lb.hist, nullptr, T_out, max_it, B, 1, h->H * h->M, h->M, attn_out);
+      attn_top_gather_kernel<<<g, 256, 0, st>>>(lb.hist, io_a2.kstats ? lb.hist_scale : nullptr, nullptr, T_out, max_it, B, 1,
+                                               h->H * h->M, h->M, attn_out);
       h->launches++;
     }
   }
@@ -1330,6 +1337,7 @@ extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const floa
     }
     io.c_new = lb.c[cur ^ 1]; io.h_new = lb.h[cur ^ 1]; io.ctx_new = lb.ctx[cur ^ 1];
     io.hist_t = attn_top_out ? lb.hist + (size_t)t * N * h->H * h->M : nullptr;
+    io.hist_scale = (attn_top_out && io.kstats) ? lb.hist_scale + (size_t)t * N * h->H : nullptr;
     io.in_keep = io.out_keep = io.att_keep = 1.f;
     io.fin_count = lb.fin_count; io.t = t; io.n_rows = N;
     int rc = run_step(h, io, lb.sb, B, k, st);
@@ -1349,8 +1357,8 @@ extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const floa
   if (attn_top_out && max_it > 0) {
     sorted_top_beam_kernel<<<(B + 127) / 128, 128, 0, st>>>(parents, lb.len, max_it, T_out, B, k, lb.sorted0);
     dim3 g(max_it, B);
-    attn_top_gather_kernel<<<g, 256, 0, st>>>(lb.hist, lb.sorted0, T_out, max_it, B, k, h->H * h->M, h->M,
-                                             attn_top_out);
+    attn_top_gather_kernel<<<g, 256, 0, st>>>(lb.hist, io_a2.kstats ? lb.hist_scale : nullptr, lb.sorted0, T_out, max_it, B, k,
+                                             h->H * h->M, h->M, attn_top_out);
     h->launches += 2;
   }
   COMIC_CHECK_CUDA(cudaGetLastError());

@@ -260,6 +260,56 @@ maxpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned
 }
 
 
+// 3x3 / stride 1 SAME max-pool (the inception blocks' Branch_3): one thread per (image, pair of output rows, 4
+// channels) walks along the row keeping the column maxima of the last two columns, so an output costs 2 loads instead
+// of 9.  The one-thread-per-output kernel above pulled 1.9x the tensor's bytes through L2 -> SM (14.9 GB per 512-image
+// step against 7.9 GB of DRAM traffic, profiles/r01z_launch_summary_batch512.txt) and ran at 3 TB/s.
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+maxpool3s1_rows_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned total, int H, int W, int C4, int HB) {
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= total) return;
+  const unsigned c4 = i % (unsigned)C4, q = i / (unsigned)C4;
+  const int hb = (int)(q % (unsigned)HB);
+  const unsigned b = q / (unsigned)HB;
+  const int ho0 = hb * ROWS;
+  const float4* xb = reinterpret_cast<const float4*>(x) + (size_t)b * H * W * C4 + c4;
+  float4* yb = reinterpret_cast<float4*>(y) + (size_t)b * H * W * C4 + c4;
+  const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  auto mx = [](const float4& a, const float4& c) {
+    return make_float4(fmaxf(a.x, c.x), fmaxf(a.y, c.y), fmaxf(a.z, c.z), fmaxf(a.w, c.w));
+  };
+  bool ok[ROWS + 2];
+#pragma unroll
+  for (int j = 0; j < ROWS + 2; ++j) ok[j] = (ho0 - 1 + j) >= 0 && (ho0 - 1 + j) < H;
+  float4 p1[ROWS], p2[ROWS];
+#pragma unroll
+  for (int o = 0; o < ROWS; ++o) { p1[o] = ninf; p2[o] = ninf; }
+#pragma unroll 4
+  for (int w = 0; w <= W; ++w) {
+    float4 cm[ROWS];
+    if (w < W) {
+      float4 r[ROWS + 2];
+#pragma unroll
+      for (int j = 0; j < ROWS + 2; ++j)
+        r[j] = ok[j] ? __ldg(xb + ((size_t)(ho0 - 1 + j) * W + w) * C4) : ninf;
+#pragma unroll
+      for (int o = 0; o < ROWS; ++o) cm[o] = mx(mx(r[o], r[o + 1]), r[o + 2]);
+    } else {
+#pragma unroll
+      for (int o = 0; o < ROWS; ++o) cm[o] = ninf;
+    }
+    if (w >= 1) {
+#pragma unroll
+      for (int o = 0; o < ROWS; ++o)
+        if (ho0 + o < H) yb[((size_t)(ho0 + o) * W + (w - 1)) * C4] = mx(mx(p2[o], p1[o]), cm[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < ROWS; ++o) { p2[o] = p1[o]; p1[o] = cm[o]; }
+  }
+}
+
+
 // --------------------------------------------------------------------------
 // bf16-plane activations (tensor path): every conv output is stored once as an error-compensated
 // bf16 pair (hi, lo) by the producing GEMM's epilogue, so the consuming conv's loader is a plain
@@ -484,7 +534,11 @@ int run_maxpool(comic_handle_t h, const float* x, float* y, int B, int H, int W,
   unsigned grid = (unsigned)((total + 255) / 256);
   {
     Prof pf(h, T_POOL, st);
-    if (k == 3)
+    if (k == 3 && s == 1) {
+      const int HB = (H + 1) / 2;
+      const size_t tot = (size_t)B * HB * (C / 4);
+      maxpool3s1_rows_kernel<2><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, y, (unsigned)tot, H, W, C / 4, HB);
+    } else if (k == 3)
       maxpool_nhwc_kernel<3><<<grid, 256, 0, st>>>(x, y, (unsigned)total, H, W, C / 4, s, pt, pl, Ho, Wo);
     else
       maxpool_nhwc_kernel<2><<<grid, 256, 0, st>>>(x, y, (unsigned)total, H, W, C / 4, s, pt, pl, Ho, Wo);

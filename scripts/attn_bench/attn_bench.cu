@@ -25,6 +25,7 @@ int main(int argc, char** argv) {
   int B = argc > 1 ? atoi(argv[1]) : 512;
   int k = argc > 2 ? atoi(argv[2]) : 3;
   int iters = argc > 3 ? atoi(argv[3]) : 20;
+  const int scale_mode = argc > 4 ? atoi(argv[4]) : 1;   // 1: history unnormalised + 1 / sum side buffer (decode loops); 0: rescaled in place
   const int R = 512, H = 8, M = 196, N = B * k, LQ = 512 + 256, QOFF = 256;
   printf("attn_bench B=%d k=%d\n", B, k);
   size_t nk = (size_t)B * M * R;
@@ -89,6 +90,8 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dscratch, a2::scratch_floats(sms) * 4)); CK(cudaMalloc(&dcount, (size_t)B * 4));
   CK(cudaMemset(dcount, 0, (size_t)B * 4));
   a.scratch = dscratch; a.counters = dcount;
+  float* dscale = nullptr;
+  if (scale_mode) { CK(cudaMalloc(&dscale, (size_t)N * H * 4)); a.hist_scale = dscale; }
 #if COMIC_A2_TRACE
   const int kWarps = COMIC_A2_NSW + a2::kCtxWarps2 + 2;
   size_t ntr = (size_t)sms * kWarps * a2::kTraceSlices * 8;
@@ -150,6 +153,54 @@ int main(int argc, char** argv) {
       }
       span_max = std::max(span_max, tmax - tmin); span_sum += (double)(tmax - tmin);
     }
+    {
+      // distributions: per slice index of the warp, and bucketed
+      const int NB = 8; const long long edge[NB] = {250, 500, 1000, 2000, 4000, 8000, 16000, 1ll << 60};
+      long long hist[5][NB] = {};
+      std::vector<double> byidx(a2::kTraceSlices * 5, 0.0); std::vector<long long> nidx(a2::kTraceSlices, 0);
+      for (int b = 0; b < grid; ++b)
+        for (int w = 0; w < COMIC_A2_NSW; ++w) {
+          const long long* p = tr.data() + ((size_t)b * kWarps + w) * a2::kTraceSlices * 8;
+          for (int i = 0; i < a2::kTraceSlices; ++i) {
+            const long long* e = p + i * 8;
+            if (e[5] == 0) break;
+            for (int q = 0; q < 5; ++q) {
+              const long long d = e[q + 1] - e[q];
+              int bk = 0; while (d >= edge[bk]) ++bk;
+              ++hist[q][bk];
+              byidx[i * 5 + q] += (double)d;
+            }
+            ++nidx[i];
+          }
+        }
+      printf("  buckets (<250 <500 <1k <2k <4k <8k <16k more):\n");
+      const char* nm[5] = {"grab+setup", "wait key", "pass1", "pass2", "exp+store"};
+      for (int q = 0; q < 5; ++q) { printf("    %-10s", nm[q]); for (int k2 = 0; k2 < NB; ++k2) printf(" %7lld", hist[q][k2]); printf("\n"); }
+      printf("  by slice index of the warp (n | grab wait pass1 pass2 exp):\n");
+      for (int i = 0; i < a2::kTraceSlices && nidx[i]; ++i)
+        printf("    %2d %6lld | %6.0f %6.0f %6.0f %6.0f %6.0f\n", i, nidx[i], byidx[i * 5] / nidx[i], byidx[i * 5 + 1] / nidx[i],
+               byidx[i * 5 + 2] / nidx[i], byidx[i * 5 + 3] / nidx[i], byidx[i * 5 + 4] / nidx[i]);
+      // timeline of CTA 7: per warp, slice g and stamp times relative to the CTA's first stamp
+      const int bb = 7 < grid ? 7 : 0;
+      long long t0 = 1ll << 62;
+      for (int w = 0; w < kWarps; ++w) { const long long* p = tr.data() + ((size_t)bb * kWarps + w) * a2::kTraceSlices * 8; if (p[0] && p[0] < t0) t0 = p[0]; }
+      printf("  timeline CTA %d (warp: [g t0 grab wait p1 p2 exp] ...):\n", bb);
+      for (int w = 0; w < COMIC_A2_NSW; ++w) {
+        const long long* p = tr.data() + ((size_t)bb * kWarps + w) * a2::kTraceSlices * 8;
+        printf("    w%02d:", w);
+        for (int i = 0; i < a2::kTraceSlices; ++i) { const long long* e = p + i * 8; if (e[5] == 0) break;
+          printf(" [%lld @%lld %lld %lld %lld %lld %lld]", e[6], e[0] - t0, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - e[4]); }
+        printf("\n");
+      }
+      for (int w = COMIC_A2_NSW; w < kWarps; ++w) {
+        const long long* p = tr.data() + ((size_t)bb * kWarps + w) * a2::kTraceSlices * 8;
+        printf("    w%02d raw:", w);
+        for (int i = 0; i < a2::kTraceSlices; ++i) { const long long* e = p + i * 8; if (e[0] == 0 && e[1] == 0 && e[2] == 0 && e[3] == 0) break;
+          printf(" [%lld %lld %lld %lld | %lld %lld %lld]", e[0] ? e[0] - t0 : 0, e[1] ? e[1] - t0 : 0, e[2] ? e[2] - t0 : 0, e[3] ? e[3] - t0 : 0,
+                 e[6] ? e[6] - t0 : 0, e[4] ? e[4] - t0 : 0, e[5] ? e[5] - t0 : 0); }
+        printf("\n");
+      }
+    }
     printf("trace (cycles, averages): CTA span mean %.0f max %lld\n", span_sum / grid, span_max);
     printf("  score warp per slice (%lld slices): grab+setup %.0f | wait key slice %.0f | pass1+stats %.0f | pass2 %.0f | exp+store+arrive %.0f\n",
            nsc, sc[0] / nsc, sc[1] / nsc, sc[2] / nsc, sc[3] / nsc, sc[4] / nsc);
@@ -164,6 +215,11 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(c1.data(), ctx1, c1.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(h0.data(), hist0, h0.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(h1.data(), hist1, h1.size() * 4, cudaMemcpyDeviceToHost));
+  if (scale_mode) {
+    std::vector<float> sc((size_t)N * H);
+    CK(cudaMemcpy(sc.data(), dscale, sc.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < (size_t)N * H; ++r) for (int m = 0; m < M; ++m) h1[r * M + m] *= sc[r];
+  }
   double dc = 0, mc = 0, dh = 0, mh = 0, drel = 0;
   size_t bad = 0;
   for (size_t i = 0; i < c0.size(); ++i) { double d = fabs((double)c0[i] - c1[i]); if (!(d == d)) ++bad; dc = std::max(dc, d); mc = std::max(mc, (double)fabs(c0[i])); }
