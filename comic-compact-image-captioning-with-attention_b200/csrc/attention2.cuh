@@ -101,6 +101,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
   } while (!done);
 }
+// one non-blocking probe of a phase (lane-local result)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // TMA bulk copy global -> shared (1-D, contiguous), completion signalled on an mbarrier.
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -222,11 +234,19 @@ constexpr int kTraceSlices = 256;
 #endif
 
 constexpr int kCtxWarps2 = 2;      // context warps of the kernel below (each takes every 2nd slice)
+#ifndef COMIC_A2_NSW
+#define COMIC_A2_NSW 10           // score warps
+#endif
+#ifndef COMIC_A2_STATW
+#define COMIC_A2_STATW 3
+#endif
+static_assert(COMIC_A2_STATW == 2 || COMIC_A2_STATW == 3, "two or three statistics warps");
+constexpr int kStatWarps = COMIC_A2_STATW;      // LN-statistics warps (warp i takes slices i, i + kStatWarps, ...)
 
 template <int K, int NSW, int STAGES>
 struct Layout {
   // warps: NSW score | 2 context | 1 finaliser | 1 TMA producer + query preparation
-  static constexpr int kWarps = NSW + kCtxWarps2 + 2;
+  static constexpr int kWarps = NSW + kCtxWarps2 + 1 + kStatWarps;
   static constexpr int kThreads = kWarps * 32;
   // byte offsets into dynamic shared memory (base 1024-aligned)
   static constexpr int ring = 0;
@@ -236,8 +256,10 @@ struct Layout {
   static constexpr int ssum = qstat + 2 * K * 2 * 4;               // [K][8] 1 / sum p of the image being finalised
   static constexpr int part = (ssum + 2 * K * kH * 4 + 15) & ~15;      // [2][K * 520]: the context warps' partial sums of one image segment
   static constexpr int bars = part + kCtxWarps2 * K * (kR + kH) * 4;   // per context warp: [K][512] context partials | [K][8] sum p      // full[S] scored[S] empty[S] qfull[2] qempty[2] pempty[2] imgdone partfree | next slice
-  static constexpr int pbuf = (bars + (3 * STAGES + 8) * 8 + 8 + 15) & ~15;   // [STAGES][K][8][4]: unnormalised weights of the slice in each stage
-  static __host__ __device__ size_t bytes(int) { return (size_t)pbuf + (size_t)STAGES * K * kH * kPos * 4; }
+  static constexpr int pbuf = (bars + (4 * STAGES + 8) * 8 + 8 + 15) & ~15;   // [STAGES][K][8][4]: unnormalised weights of the slice in each stage
+  static constexpr int sbuf = pbuf + STAGES * K * kH * kPos * 4;             // [STAGES][4 positions] x {var_0 + eps, var_1 + eps, var_2 + eps, -mean}
+  static constexpr int kStatBytes = 4 * 16;
+  static __host__ __device__ size_t bytes(int) { return (size_t)sbuf + (size_t)STAGES * kStatBytes; }
 };
 
 // Pass 2 works on chunks of four channels, software-pipelined by hand: `front4` turns staged operands into 2^y' for
@@ -245,6 +267,18 @@ struct Layout {
 // The caller alternates the two positions of a lane so that the exponentials of one are in flight while the other's
 // are consumed.
 // ea[j] = (2^y0, 2^y2), eb[j] = (2^y1, 2^y3)
+// Timing experiments (harness builds only; results are wrong): COMIC_A2_KNOCK bit 0: no MUFU in pass 2 (cheap FP
+// stand-ins), bit 1: pass 1 dot products skipped, bit 2: pass 2 skipped.
+#ifndef COMIC_A2_KNOCK
+#define COMIC_A2_KNOCK 0
+#endif
+#if COMIC_A2_KNOCK & 1
+#define A2_EX2(x) ((x) * 1.0001f)
+#define A2_RCP(x) ((x) * 0.5f)
+#else
+#define A2_EX2(x) ex2_approx(x)
+#define A2_RCP(x) rcp_approx(x)
+#endif
 template <int K>
 __device__ __forceinline__ void front4(const float4 k, const float4 g, const float4 b, const float4 (&q)[K], const float2 nmu,
                                        const float (&rstd)[K], float2 (&ea)[K], float2 (&eb)[K]) {
@@ -259,8 +293,8 @@ __device__ __forceinline__ void front4(const float4 k, const float4 g, const flo
   }
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    ea[j] = make_float2(ex2_approx(y01[j].x), ex2_approx(y23[j].x));
-    eb[j] = make_float2(ex2_approx(y01[j].y), ex2_approx(y23[j].y));
+    ea[j] = make_float2(A2_EX2(y01[j].x), A2_EX2(y23[j].x));
+    eb[j] = make_float2(A2_EX2(y01[j].y), A2_EX2(y23[j].y));
   }
 }
 template <int K>
@@ -272,7 +306,7 @@ __device__ __forceinline__ void back4(const float4 vv, const float2 (&ea)[K], co
     const float2 p = __fmul2_rn(xa, xb);                     // (x0 x1, x2 x3)
     // vv is stored as (v1, v3, v0, v2) * -2:  n = (x0 v1 + x1 v0, x2 v3 + x3 v2)
     const float2 n = __ffma2_rn(xa, make_float2(vv.x, vv.y), __fmul2_rn(xb, make_float2(vv.z, vv.w)));
-    const float rp = rcp_approx(p.x * p.y);
+    const float rp = A2_RCP(p.x * p.y);
     out[j] = fmaf(rp, fmaf(p.x, n.y, p.y * n.x), out[j]);
   }
 }
@@ -295,8 +329,44 @@ __device__ __forceinline__ void chunk2_load(Chunk2<K>& c, uint32_t ka, uint32_t 
   c.v = lds128<2 * kR * 4>(ca);
 }
 
+// role << 4 | index, per warp (see "Warp roles" in the kernel)
+#ifndef COMIC_A2_LAYOUT
+#define COMIC_A2_LAYOUT 1
+#endif
+#define A2S(i) (0x00 | (i))
+#define A2C(i) (0x10 | (i))
+#define A2F 0x20
+#define A2T(i) (0x30 | (i))
+#if COMIC_A2_STATW == 2 && COMIC_A2_NSW == 11
+#if COMIC_A2_LAYOUT == 0
+// sub-partitions: 0: s s s ctx1 | 1: s s s fin | 2: s s s stat0 | 3: s s ctx0 stat1
+__device__ constexpr unsigned char kRoles[16] = {A2S(0), A2S(1), A2S(2), A2S(3), A2S(4), A2S(5), A2S(6), A2S(7),
+                                                 A2S(8), A2S(9), A2S(10), A2C(0), A2C(1), A2F, A2T(0), A2T(1)};
+#else
+// sub-partitions: 0: s s s ctx0 | 1: s s s ctx1 | 2: s s s stat0 | 3: s s stat1 fin
+__device__ constexpr unsigned char kRoles[16] = {A2S(0), A2S(1), A2S(2), A2S(3), A2S(4), A2S(5), A2S(6), A2S(7),
+                                                 A2S(8), A2S(9), A2S(10), A2T(1), A2C(0), A2C(1), A2T(0), A2F};
+#endif
+#elif COMIC_A2_STATW == 3 && COMIC_A2_NSW == 10
+#if COMIC_A2_LAYOUT == 0
+// sub-partitions: 0: s s s fin | 1: s s s stat0 | 2: s s ctx0 stat1 | 3: s s ctx1 stat2
+__device__ constexpr unsigned char kRoles[16] = {A2S(0), A2S(1), A2S(2), A2S(3), A2S(4), A2S(5), A2S(6), A2S(7),
+                                                 A2S(8), A2S(9), A2C(0), A2C(1), A2F, A2T(0), A2T(1), A2T(2)};
+#else
+// sub-partitions: 0: s s s stat0 | 1: s s s stat1 | 2: s s stat2 ctx0 | 3: s s ctx1 fin
+__device__ constexpr unsigned char kRoles[16] = {A2S(0), A2S(1), A2S(2), A2S(3), A2S(4), A2S(5), A2S(6), A2S(7),
+                                                 A2S(8), A2S(9), A2T(2), A2C(1), A2T(0), A2T(1), A2C(0), A2F};
+#endif
+#else
+#error "attention2: no warp-role table for this COMIC_A2_NSW / COMIC_A2_STATW"
+#endif
+#undef A2S
+#undef A2C
+#undef A2F
+#undef A2T
+
 template <int K, int NSW, int STAGES>
-__global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(const Args a) {
+__global__ void __launch_bounds__((NSW + kCtxWarps2 + 1 + kStatWarps) * 32, 1) attn2_kernel(const Args a) {
   if (a.fin_count != nullptr && a.t > 0 && a.fin_count[a.t - 1] >= a.n_rows) return;
   using L = Layout<K, NSW, STAGES>;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -316,7 +386,8 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
   uint64_t* pempty = qempty + 2;
   uint64_t* imgdone = pempty + 2;
   uint64_t* partfree = imgdone + 1;
-  int* next_g = reinterpret_cast<int*>(partfree + 1);
+  unsigned char* sm_st = smem + L::sbuf;
+  uint64_t* statrdy = partfree + 1;                           // [STAGES] (after the 8 single barriers)
   float* sm_p = reinterpret_cast<float*>(smem + L::pbuf);     // [STAGES][K][8][4]
   constexpr int kPStage = K * kH * kPos;                      // floats per stage in sm_p
 
@@ -334,11 +405,19 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
   const int len_last = (n_seg >= 2) ? seg_hi(n_seg - 1) : 0;       // slices of the segment processed first (it starts at slice 0)
   auto seg_of = [&](int pos) { return len_last > 0 ? (pos == 0 ? n_seg - 1 : pos - 1) : pos; };
 
+  // request slice sl of image b0 + ii into stage s (one TMA bulk copy of the 4 key rows)
+  auto request_slice = [&](int s, int ii, int sl) {
+    const size_t row0 = ((size_t)(b0 + ii) * spi + sl) * kPos;
+    mbar_arrive_expect_tx(&full[s], kSliceBytes);
+    tma_bulk_g2s(smem + L::ring + s * kSliceBytes, a.keys + row0 * kR, kSliceBytes, &full[s]);
+  };
+
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&scored[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&statrdy[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qfull[i], 1);
@@ -347,7 +426,6 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
     }
     mbar_init(imgdone, kCtxWarps2);
     mbar_init(partfree, 1);
-    *next_g = 0;
     fence_barrier_init();
   }
   // LN constants: gamma' = gamma * 2 log2 e, beta' = beta * 2 log2 e - s, v' = -2 v 2^-s in pair order (v1, v3, v0, v2)
@@ -368,130 +446,84 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
   int tn = 0;
 #endif
 
-  if (warp < NSW) {
+  // Warp roles.  Warp w issues on sub-partition w & 3, and where the helpers sit matters (+-10 %, profiles/r07l, r07m):
+  // two statistics warps on one sub-partition starve each other, and every score warp waits for their output.
+  // role: 0 score (index = rank among the score warps), 1 context, 2 finaliser, 3 statistics.
+  const int role = (int)(kRoles[warp] >> 4), ridx = (int)(kRoles[warp] & 15);
+  if (role == 0) {
     // =========================== score warps ===========================
     // lane = (row pair rp, half head hf, head hp): the lane scores positions rp and rp + 2 of the slice over 32
     // channels of head hp.  Per-channel operands (gamma', beta', v', queries) are loaded once for both positions,
     // which is what keeps the shared-memory pipe (4 wavefronts per 128-bit load) off the critical path.
     const int rp = lane >> 4, hf = (lane >> 3) & 1, hp = lane & 7;
-    // rotated chunk order: at step u the lane reads 16-byte chunk ((u + hp) & 7) of its half head, so the 8 lanes of a
-    // quarter warp hit 8 different bank groups (keys: row-major slice; queries / constants: plain [512] rows).
-    // The 8 per-lane chunk addresses are pinned in registers (opaque to the compiler, which otherwise re-derives them
-    // with several integer instructions per load); a load address is lane register + uniform stage / buffer base +
-    // immediate.
-    uint32_t kofs[8], cadr[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const uint32_t o = (uint32_t)(hp * kD * 4 + hf * 128 + (((u + hp) & 7) << 4));   // byte offset of the chunk in a [512] float row
-      asm volatile("mov.b32 %0, %1;" : "=r"(cadr[u]) : "r"(smem_u32(sm_c) + o));
-      asm volatile("mov.b32 %0, %1;" : "=r"(kofs[u]) : "r"(smem_u32(smem + L::ring) + (uint32_t)(rp * kR * 4) + o));
+    // swizzled chunk order: at step u the lane reads 16-byte chunk (u ^ hp) of its half head, so the 8 lanes of a
+    // quarter warp hit 8 different bank groups (keys: row-major slice; queries / constants: plain [512] rows).  All
+    // region bases are multiples of 128 bytes, so the chunk address is one lane register XOR (u << 4) -- a single
+    // LOP3 per chunk instead of 16 pinned address registers (which pushed the loop into local-memory spills).
+    uint32_t kofs0, cadr0;
+    {
+      const uint32_t o = (uint32_t)(hp * kD * 4 + hf * 128 + (hp << 4));
+      asm volatile("mov.b32 %0, %1;" : "=r"(cadr0) : "r"(smem_u32(sm_c) + o));
+      asm volatile("mov.b32 %0, %1;" : "=r"(kofs0) : "r"(smem_u32(smem + L::ring) + (uint32_t)(rp * kR * 4) + o));
     }
+    auto kofs = [&](int u) { return kofs0 ^ (uint32_t)(u << 4); };
+    auto cadr = [&](int u) { return cadr0 ^ (uint32_t)(u << 4); };
     const uint32_t q_minus_c = smem_u32(sm_q) - smem_u32(sm_c);
     float sv = 0.f;                                           // sum of v over this lane's 32 channels
     for (int c = 0; c < kD / 2; ++c) sv += a.vvec[hp * kD + hf * 32 + c];
     const float inv_T = kLog2e / a.temperature[0];            // p = 2^((score / T - bound) log2 e)
     const float shift = a.bound[hp] * kLog2e;
     int last_img = -1;
-    float sqq[K], sumq[K];
-    // Score warp w takes slices w, w + NSW, ... of the CTA's sequence (no claim counter: a shared-memory atomic, a
-    // shuffle and an integer division per slice were ~1.5 k cycles of dependent scalar code).  At most NSW < STAGES
-    // slices are in work, so a warp never waits on a stage whose previous use is still pending (the parity waits
-    // would alias).
-    const float spi_inv = 1.0f / (float)spi;
-    for (int g = warp; g < n_g; g += NSW) {
+    // Score warp w takes slices w, w + NSW, ... of the CTA's sequence.  At most NSW < STAGES slices are in work, so a
+    // warp never waits on a stage whose previous use is still pending (the parity waits would alias).  The LN
+    // statistics of the slice (1 / std per position and beam, -mean per position) come from the statistics warp.
+    for (int g = ridx; g < n_g; g += NSW) {
       A2_STAMP(0);
       int pos, ii, sl;
       if (g < len_last) { pos = 0; ii = n_seg - 1; sl = g; }
       else {
-        const int v = g - len_last + sl0;
-        ii = (int)(((float)v + 0.5f) * spi_inv);               // v / spi, exact for v < 2^20
-        sl = v - ii * spi;
+        int v = g - len_last + sl0;                             // v / spi by subtraction (at most n_seg rounds; an integer
+        ii = 0;                                                 // or float division would queue behind the MUFU work)
+        while (v >= spi) { v -= spi; ++ii; }
+        sl = v;
         pos = ii + (len_last > 0 ? 1 : 0);
       }
       const int par = pos & 1;
       if (pos != last_img) {
         mbar_wait(&qfull[par], (uint32_t)((pos >> 1) & 1));
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-          sqq[j] = sm_qs[(par * K + j) * 2 + 0];
-          sumq[j] = sm_qs[(par * K + j) * 2 + 1];
-        }
         last_img = pos;
       }
-      const int m = sl * kPos + rp;                           // positions m and m + 2
-      const float2* ksp = reinterpret_cast<const float2*>(a.kstats) + ((size_t)(b0 + ii) * M + m);
-      const float2 stA = __ldg(ksp), stB = __ldg(ksp + 2);
       const int s = g % STAGES;
       A2_STAMP(1);
-      mbar_wait(&full[s], (uint32_t)((g / STAGES) & 1));
+      mbar_wait(&statrdy[s], (uint32_t)((g / STAGES) & 1));
+      mbar_wait(&full[s], (uint32_t)((g / STAGES) & 1));     // completed long ago: makes the TMA writes visible to this warp
       A2_STAMP(2);
-#if COMIC_A2_STREAM_ONLY
-      if (lane == 0) { mbar_arrive(&scored[s]); mbar_arrive(&qempty[par]); }
-      continue;
-#endif
       const uint32_t kst = (uint32_t)(s * kSliceBytes);                         // stage offset (uniform)
       const uint32_t qcb = q_minus_c + (uint32_t)(par * 2 * K * kR * 4);        // centred queries of this image, relative to the constants
       const uint32_t qgb = qcb + (uint32_t)(K * kR * 4);                        // * gamma'
-      // ---- pass 1: <k, qc_j> over this lane's 32 channels (loads one chunk ahead), then across the 16 lanes of a position ----
-      float2 dA[K], dB[K];
-#pragma unroll
-      for (int j = 0; j < K; ++j) { dA[j] = make_float2(0.f, 0.f); dB[j] = make_float2(0.f, 0.f); }
-      {
-        float4 kq[3][2 + K];                                  // rotating window of chunks u, u + 1, u + 2: keys A, keys B, K centred queries
-        auto ld1 = [&](float4 (&dst)[2 + K], int u) {
-          const uint32_t ka = kofs[u] + kst, qa = cadr[u] + qcb;
-          dst[0] = lds128<0>(ka);
-          dst[1] = lds128<2 * kR * 4>(ka);
-          dst[2] = lds128<0>(qa);
-          if (K > 1) dst[K > 1 ? 3 : 2] = lds128<kR * 4>(qa);
-          if (K > 2) dst[K > 2 ? 4 : 2] = lds128<2 * kR * 4>(qa);
-        };
-        ld1(kq[0], 0);
-        ld1(kq[1], 1);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (u + 2 < 8) ld1(kq[(u + 2) % 3], u + 2);
-          const float4 ka = kq[u % 3][0], kb = kq[u % 3][1];
-#pragma unroll
-          for (int j = 0; j < K; ++j) {
-            const float4 q4 = kq[u % 3][2 + j];
-            dA[j] = __ffma2_rn(make_float2(ka.x, ka.y), make_float2(q4.x, q4.y), dA[j]);
-            dA[j] = __ffma2_rn(make_float2(ka.z, ka.w), make_float2(q4.z, q4.w), dA[j]);
-            dB[j] = __ffma2_rn(make_float2(kb.x, kb.y), make_float2(q4.x, q4.y), dB[j]);
-            dB[j] = __ffma2_rn(make_float2(kb.z, kb.w), make_float2(q4.z, q4.w), dB[j]);
-          }
-        }
-      }
-      // first chunk of pass 2 is staged while the statistics are reduced
+      // first chunk of pass 2 is staged behind the statistics loads
+      const float4 stA = *reinterpret_cast<const float4*>(sm_st + s * L::kStatBytes + rp * 16);
+      const float4 stB = *reinterpret_cast<const float4*>(sm_st + s * L::kStatBytes + (rp + 2) * 16);
       Chunk2<K> c;
-      chunk2_load<K>(c, kofs[0] + kst, cadr[0], cadr[0] + qgb);
+      chunk2_load<K>(c, kofs(0) + kst, cadr(0), cadr(0) + qgb);
       float rsA[K], rsB[K], outA[K], outB[K];
 #pragma unroll
       for (int j = 0; j < K; ++j) {
-        float da = dA[j].x + dA[j].y, db = dB[j].x + dB[j].y;
-#pragma unroll
-        for (int o = 1; o <= 8; o <<= 1) {
-          da += __shfl_xor_sync(0xffffffffu, da, o);
-          db += __shfl_xor_sync(0xffffffffu, db, o);
-        }
-        da = fmaf(-stA.x, sumq[j], da);                       // <k - mean, qc> (sum qc is ~0, not exactly 0)
-        db = fmaf(-stB.x, sumq[j], db);
-        const float sa = fmaxf(fmaf(2.0f, da, stA.y + sqq[j]), 0.f), sb = fmaxf(fmaf(2.0f, db, stB.y + sqq[j]), 0.f);
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rsA[j]) : "f"(sa * (1.0f / kR) + 1e-12f));
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rsB[j]) : "f"(sb * (1.0f / kR) + 1e-12f));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rsA[j]) : "f"(j == 0 ? stA.x : (j == 1 ? stA.y : stA.z)));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rsB[j]) : "f"(j == 0 ? stB.x : (j == 1 ? stB.y : stB.z)));
         outA[j] = sv;
         outB[j] = sv;
       }
       A2_STAMP(3);
       // ---- pass 2: LN + tanh + v-weighted head sum; per chunk: back A(u-1) | front A(u) | back B(u-1) | front B(u) ----
-      const float2 nmuA = make_float2(-stA.x, -stA.x), nmuB = make_float2(-stB.x, -stB.x);
+      const float2 nmuA = make_float2(stA.w, stA.w), nmuB = make_float2(stB.w, stB.w);
       float2 eaA[K], ebA[K], eaB[K], ebB[K];
       front4<K>(c.ka, c.g, c.b, c.q, nmuA, rsA, eaA, ebA);
       front4<K>(c.kb, c.g, c.b, c.q, nmuB, rsB, eaB, ebB);
       float4 vprev = c.v;
 #pragma unroll
-      for (int u = 1; u < 8; ++u) {
-        chunk2_load<K>(c, kofs[u] + kst, cadr[u], cadr[u] + qgb);
+      for (int u = 1; u < ((COMIC_A2_KNOCK & 4) ? 1 : 8); ++u) {
+        chunk2_load<K>(c, kofs(u) + kst, cadr(u), cadr(u) + qgb);
         back4<K>(vprev, eaA, ebA, outA, escale);
         front4<K>(c.ka, c.g, c.b, c.q, nmuA, rsA, eaA, ebA);
         back4<K>(vprev, eaB, ebB, outB, escale);
@@ -522,12 +554,12 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
       ++tn;
 #endif
     }
-  } else if (warp < NSW + kCtxWarps2) {
+  } else if (role == 1) {
     // =========================== context warps ===========================
     // Context warp cw takes every 2nd slice of the CTA's sequence and accumulates sum_m p[m] * key[m, :] over all 512
     // channels of it from the shared-memory slice (two independent release chains); at the end of an image it hands
     // its partial sums to the finaliser warp and goes straight on to the next image.
-    const int cw = warp - NSW;
+    const int cw = ridx;
     const int hd0 = lane >> 4;                                // quad i of this lane: channels 4 (lane + 32 i) .., head hd0 + 2 i
     float4 acc[K][4];
     float S[K][4];                                            // sum of p over this warp's slices, heads hd0 + 2 i
@@ -535,6 +567,24 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
     for (int j = 0; j < K; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) { acc[j][i] = make_float4(0.f, 0.f, 0.f, 0.f); S[j][i] = 0.f; }
+    // The context warps are also the TMA producers: a stage is refilled by the warp that releases it (no "empty"
+    // barrier, no producer warp); each first requests its share of the first STAGES slices.
+    // r_*: the next slice this warp will request (up front: the slices < STAGES with the parity of cw + STAGES; then
+    // slice g + STAGES when it releases slice g), tracked incrementally -- the request sits on the release path
+    int r_g = 0, r_pos = 0, r_sl = seg_lo(seg_of(0)), r_hi = seg_hi(seg_of(0));
+    auto r_adv = [&](int n) {
+      r_g += n; r_sl += n;
+      while (r_pos < n_seg && r_sl >= r_hi) {
+        const int over = r_sl - r_hi;
+        if (++r_pos < n_seg) { r_sl = seg_lo(seg_of(r_pos)) + over; r_hi = seg_hi(seg_of(r_pos)); }
+      }
+    };
+    static_assert(kCtxWarps2 == 2, "request sequence below assumes two context warps");
+    r_adv((cw + STAGES) % kCtxWarps2);                        // so that the up-front sequence runs straight into cw + STAGES
+    while (r_g < STAGES && r_g < n_g) {
+      if (lane == 0) request_slice(r_g % STAGES, seg_of(r_pos), r_sl);
+      r_adv(kCtxWarps2);
+    }
     int g = 0;
     for (int pos = 0; pos < n_seg; ++pos) {
       const int ii = seg_of(pos);
@@ -582,7 +632,10 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        if (r_g < n_g) {                                      // every reader of the stage is done: refill it (r_g == g + STAGES)
+          if (lane == 0) request_slice(s, seg_of(r_pos), r_sl);
+          r_adv(kCtxWarps2);
+        }
         A2_STAMP(2);
 #if COMIC_A2_TRACE
         if (tn < kTraceSlices - 1) ++tn;
@@ -609,7 +662,7 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
       if (tn < kTraceSlices - 1) ++tn;
 #endif
     }
-  } else if (warp == NSW + kCtxWarps2) {
+  } else if (role == 2) {
     // =========================== finaliser ===========================
     // Per image segment: sum p over its positions (fixed order), add the two context partials (warp 0 + warp 1); a
     // whole image is normalised and written at once, a partial one goes through the global scratch (see top).
@@ -801,43 +854,109 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
 #endif
     }
   } else {
-    // =========================== TMA producer ===========================
-    // Lane 0 feeds the ring and does nothing else: it never waits on anything but a free stage.  (It used to prepare
-    // the queries of the next segment as well, which needs the segment before the current one completely scored; the
-    // producer runs up to STAGES slices ahead of that point, so it stalled ~10 k cycles twice per CTA and drained the
-    // ring -- profiles/r07a_attn2_trace_dist.txt.)
+    // =========================== LN statistics ===========================
+    // Statistics warp sw takes every 2nd landed slice and computes <k_m - mean, qc_j> for the 4 positions x K beams -- the centred queries of the image
+    // live in registers, lane owns float4 chunks lane + 32 i, so a slice costs 16 shared loads and 96 packed FMAs for
+    // all score warps together (they used to spend a quarter of their time on it, 40 loads + 96 FMAs + 48 shuffle /
+    // add steps EACH per slice) -- and publishes 1 / std per (position, beam) and -mean per position.
+    static_assert(K <= 3, "statistics record: {rstd_0, rstd_1, rstd_2, -mean}");
+    const int sw = ridx;
+    float4 qreg[K][4];
+    float sqq[K], sumq[K];
+    const int r_own = lane >> 3, j_own = lane & 7;             // after the reduction: lane group r_own holds position r_own
     int g = 0;
     for (int pos = 0; pos < n_seg; ++pos) {
       const int ii = seg_of(pos);
+      const int par = pos & 1;
       const int lo = seg_lo(ii), hi = seg_hi(ii);
-      const float* src = a.keys + ((size_t)(b0 + ii) * spi + lo) * kSliceFloats;
-#if COMIC_A2_L2_AHEAD > 0
-      if (lane == 0 && pos == 0) {
-        const int n0 = (hi - lo) < COMIC_A2_L2_AHEAD ? (hi - lo) : COMIC_A2_L2_AHEAD;
-        for (int i = 0; i < n0; ++i) tma_prefetch_l2(src + (size_t)i * kSliceFloats, kSliceBytes);
+      {
+        // no slice of this segment for this warp (1-slice segment): skip it without touching its barriers (a warp
+        // that waits for a query buffer two preparations late would wait on an aliased parity)
+        const int first = g + (sw - g % kStatWarps + kStatWarps) % kStatWarps;
+        if (first >= g + (hi - lo)) { g += hi - lo; continue; }
       }
-#endif
+      mbar_wait(&qfull[par], (uint32_t)((pos >> 1) & 1));
+      {
+        const float* qc = sm_q + (size_t)par * 2 * K * kR;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) qreg[j][i] = *reinterpret_cast<const float4*>(qc + j * kR + (lane + 32 * i) * 4);
+          sqq[j] = sm_qs[(par * K + j) * 2 + 0];
+          sumq[j] = sm_qs[(par * K + j) * 2 + 1];
+        }
+      }
       for (int sl = lo; sl < hi; ++sl, ++g) {
-        if (lane == 0) {
-          const int s = g % STAGES;
-#if COMIC_A2_L2_AHEAD > 0
-          {
-            // keep the next COMIC_A2_L2_AHEAD slices of the sequence on their way into L2: the ring then refills at
-            // L2 latency instead of HBM latency
-            const int ahead = sl + COMIC_A2_L2_AHEAD;
-            if (ahead < hi) tma_prefetch_l2(src + (size_t)(ahead - lo) * kSliceFloats, kSliceBytes);
-            else if (pos + 1 < n_seg) {
-              const int nii = seg_of(pos + 1);
-              const int nlo = seg_lo(nii), nhi = seg_hi(nii);
-              const int nsl = nlo + (ahead - hi);
-              if (nsl < nhi) tma_prefetch_l2(a.keys + ((size_t)(b0 + nii) * spi + nsl) * kSliceFloats, kSliceBytes);
+        if (g % kStatWarps != sw) continue;
+        const int s = g % STAGES;
+        A2_STAMP(0);
+        // mean, centred sum of squares of key row r_own of the slice: needed last, fetched first
+        const float2 ks = __ldg(reinterpret_cast<const float2*>(a.kstats) + ((size_t)(b0 + ii) * M + sl * kPos + r_own));
+        mbar_wait(&full[s], (uint32_t)((g / STAGES) & 1));
+        A2_STAMP(1);
+        const float* tile = reinterpret_cast<const float*>(smem + L::ring + s * kSliceBytes) + lane * 4;
+        float v[kPos * K];
+        {
+          float4 kr[2][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) kr[0][i] = *reinterpret_cast<const float4*>(tile + i * 128);
+#pragma unroll
+          for (int r = 0; r < kPos; ++r) {
+            if (r + 1 < kPos) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) kr[(r + 1) & 1][i] = *reinterpret_cast<const float4*>(tile + (r + 1) * kR + i * 128);
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+              float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                acc = __ffma2_rn(make_float2(kr[r & 1][i].x, kr[r & 1][i].y), make_float2(qreg[j][i].x, qreg[j][i].y), acc);
+                acc = __ffma2_rn(make_float2(kr[r & 1][i].z, kr[r & 1][i].w), make_float2(qreg[j][i].z, qreg[j][i].w), acc);
+              }
+              v[r * K + j] = acc.x + acc.y;
             }
           }
-#endif
-          mbar_wait(&empty[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
-          mbar_arrive_expect_tx(&full[s], kSliceBytes);
-          tma_bulk_g2s(smem + L::ring + s * kSliceBytes, src + (size_t)(sl - lo) * kSliceFloats, kSliceBytes, &full[s]);
         }
+        // reduce-scatter over the 32 lanes: xor 16 halves the positions {0,1 | 2,3}, xor 8 again, then a butterfly
+        float w[2 * K], x[K];
+        {
+          const bool up = (lane & 16) != 0;
+#pragma unroll
+          for (int t = 0; t < 2 * K; ++t) {
+            const float send = up ? v[t] : v[t + 2 * K], keep = up ? v[t + 2 * K] : v[t];
+            w[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+          const bool up8 = (lane & 8) != 0;
+#pragma unroll
+          for (int t = 0; t < K; ++t) {
+            const float send = up8 ? w[t] : w[t + K], keep = up8 ? w[t + K] : w[t];
+            x[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int o = 4; o >= 1; o >>= 1)
+#pragma unroll
+            for (int t = 0; t < K; ++t) x[t] += __shfl_xor_sync(0xffffffffu, x[t], o);
+        }
+        {
+          float* rec = reinterpret_cast<float*>(sm_st + s * L::kStatBytes + r_own * 16);
+          if (j_own < K) {
+            const float xd = j_own == 0 ? x[0] : (j_own == 1 ? x[K > 1 ? 1 : 0] : x[K > 2 ? 2 : 0]);
+            const float sq = j_own == 0 ? sqq[0] : (j_own == 1 ? sqq[K > 1 ? 1 : 0] : sqq[K > 2 ? 2 : 0]);
+            const float sm = j_own == 0 ? sumq[0] : (j_own == 1 ? sumq[K > 1 ? 1 : 0] : sumq[K > 2 ? 2 : 0]);
+            const float d = fmaf(-ks.x, sm, xd);                // <k - mean, qc> (sum qc is ~0, not exactly 0)
+            const float sa = fmaxf(fmaf(2.0f, d, ks.y + sq), 0.f);
+            rec[j_own] = sa * (1.0f / kR) + 1e-12f;        // variance + eps: the score warps take the rsqrt (no MUFU queue here)
+          } else if (j_own == 3) {
+            rec[3] = -ks.x;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&statrdy[s]);
+        A2_STAMP(2);
+#if COMIC_A2_TRACE
+        if (tn < kTraceSlices - 1) ++tn;
+#endif
       }
     }
   }
@@ -849,9 +968,6 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 2) * 32, 1) attn2_kernel(c
 namespace comic {
 namespace a2 {
 
-#ifndef COMIC_A2_NSW
-#define COMIC_A2_NSW 12
-#endif
 #ifndef COMIC_A2_STAGES
 #define COMIC_A2_STAGES 21
 #endif

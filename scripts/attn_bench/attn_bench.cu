@@ -93,7 +93,7 @@ int main(int argc, char** argv) {
   float* dscale = nullptr;
   if (scale_mode) { CK(cudaMalloc(&dscale, (size_t)N * H * 4)); a.hist_scale = dscale; }
 #if COMIC_A2_TRACE
-  const int kWarps = COMIC_A2_NSW + a2::kCtxWarps2 + 2;
+  const int kWarps = COMIC_A2_NSW + a2::kCtxWarps2 + 1 + a2::kStatWarps;
   size_t ntr = (size_t)sms * kWarps * a2::kTraceSlices * 8;
   long long* dtr;
   CK(cudaMalloc(&dtr, ntr * 8));
@@ -139,12 +139,12 @@ int main(int argc, char** argv) {
             for (int q = 0; q < 5; ++q) sc[q] += (double)(e[q + 1] - e[q]);
             ++nsc;
             tmin = std::min(tmin, e[0]); tmax = std::max(tmax, e[5]);
-          } else if (w < COMIC_A2_NSW + a2::kCtxWarps2) {
+          } else if (w == COMIC_A2_NSW + 1 || w == COMIC_A2_NSW + 2) {   // context warps (2 statistics warps layout)
             if (e[2] == 0 && e[3] == 0) break;
             if (e[2] != 0) { cx[0] += (double)(e[1] - e[0]); cx[1] += (double)(e[2] - e[1]); ++ncx; }
             if (e[3] != 0 && i > 0 && p[(i - 1) * 8 + 2] != 0) { fin += (double)(e[3] - p[(i - 1) * 8 + 2]); ++nfin; }
             tmax = std::max(tmax, std::max(e[2], e[3]));
-          } else if (w == COMIC_A2_NSW + a2::kCtxWarps2) {
+          } else if (w == COMIC_A2_NSW + 3) {   // finaliser
             if (e[2] == 0) break;
             tmax = std::max(tmax, e[2]);   // finaliser: end of a segment's finalisation
             fz += (double)(e[2] - e[1]); ++nfz;
