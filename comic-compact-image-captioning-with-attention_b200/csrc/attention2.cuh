@@ -7,22 +7,33 @@
 // its time in shuffle-reduction chains and load-to-use stalls (profiles/r01z_ncu_attn_*:
 // 34 % short-scoreboard, issue slots 55 % busy).  Here the mapping is turned round:
 //
-//   * a LANE owns one head (64 channels) of one feature-map position, so the layer-norm
-//     statistics, the tanh sum and the head sum are serial in-thread accumulations -- the
-//     hot loop has no shuffles -- and every operand that is not the key itself (queries,
-//     gamma, beta, v) is a 128-byte conflict-free shared-memory read shared by 4 positions;
-//   * the key tensor is streamed ONCE per step: persistent CTAs (one per SM) walk a
-//     contiguous range of 4-position key slices (8 KB, contiguous in HBM) that a producer
-//     warp stages with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) through a
-//     ring of shared-memory stages;
-//   * warp roles: NSW score warps (slice -> 4 x 8 x k scores -> exp), 4 context warps that
-//     accumulate sum_m p[m] * key[m, :] from the SAME shared-memory slice (tied values:
-//     the old kernel re-read them from L2), one TMA warp, one query-preparation warp
-//     (centres and gamma-scales the next image's k queries while the current image is scored);
+//   * a score-warp LANE owns half a head (32 channels) of two feature-map positions, so the tanh sum is a serial
+//     in-thread accumulation -- the hot loop has no shuffles -- and every operand that is not the key itself
+//     (gamma-scaled queries, gamma', beta', v') is a conflict-free 128-bit shared-memory read shared by both positions;
+//   * the key tensor is streamed ONCE per step: persistent CTAs (one per SM) walk a contiguous range of 4-position key
+//     slices (8 KB, contiguous in HBM) staged by TMA bulk copies (cp.async.bulk + mbarrier complete_tx) through a ring
+//     of STAGES shared-memory stages;
+//   * 16 warps, five roles (table kRoles): NSW score warps (slice -> LN + tanh + head sums -> p = exp(score - bound));
+//     kStatWarps statistics warps (per landed slice the 4 x k dot products <k_m, qc_j> that the LN variance needs, with
+//     the image's centred queries held in registers -- for ALL score warps together this costs 16 shared loads and 96
+//     packed FMAs per slice, where each score warp used to spend a quarter of its time on it); 2 context warps
+//     (sum_m p[m] * key[m, :] from the SAME shared-memory slice -- tied values -- unnormalised weights to the history,
+//     then they REFILL the stage they have just released: no producer warp, no "empty" barriers); 1 finaliser
+//     (query preparation for the segment after next, per-image normalisation, the split-image combination);
 //   * softmax without a max pass: |score| <= bound_h = sum_{c in head} |v_c| / |T| (tanh is
 //     bounded), so p = exp(score - bound_h) cannot overflow and alpha = p / sum p equals the
 //     max-subtracted form up to rounding.  The host only takes this kernel when bound_h is
-//     small enough that p cannot underflow either (attn2_prep / decoder.cu).
+//     small enough that p cannot underflow either (attn2_prepare / decoder.cu);
+//   * inside a decode loop the history stays unnormalised and 1 / sum p goes to a side buffer (Args.hist_scale) that
+//     the top-beam gather applies: a rescaling pass over the history costs ~3 k cycles per L2 round trip behind the
+//     TMA queue (profiles/r07e) and sat on the tail of every CTA.
+//
+// Barriers per stage: full (TMA landed) -> statrdy (statistics published) -> scored (weights in the stage's p buffer)
+// -> [context warp accumulates, requests the next slice into the stage] -> full ...
+// What the clock64 traces showed on the way (profiles/r07*): a producer that also prepared queries stalled ~10 k cycles
+// twice per CTA; claim counters / integer divisions per slice cost ~1 k cycles of scalar latency behind the MUFU
+// queue; two statistics warps on one sub-partition starve each other; dynamic in-order claims are slower than a fixed
+// round-robin share.
 //
 // Per-row statistics of the keys (mean, centred sum of squares) do not change during a decode
 // call and are computed once per call by key_stats_kernel.

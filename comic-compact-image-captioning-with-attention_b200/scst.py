@@ -59,7 +59,10 @@ def id_to_caption(ids, config):
         joiner = ' ' if c.token_type == 'word' else ''
         for i in range(ids.shape[0]):
             row = [int(w) for w in ids[i, :] if w >= 0 and w != eos]
-            captions.append(joiner.join(c.itow[str(w)] for w in row))
+            # (JSON-loaded tables are str-keyed; the char table InputManager_Char builds is int-keyed and leaves id 37
+            # unassigned -- the reference would raise KeyError on it; it is skipped here)
+            toks = [c.itow.get(str(w), c.itow.get(w)) for w in row]
+            captions.append(joiner.join(t for t in toks if t is not None))
     return captions
 
 

@@ -245,3 +245,37 @@ def test_restore_model_from_a_v2_checkpoint(torch_mod, tmp_path):
     b = CaptionModel(c2, 'infer', reuse=True, share=m2).run(img)
     np.testing.assert_array_equal(a[0], b[0])
     np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_char_tokens_through_input_manager_train_eval_infer(torch_mod, tmp_path):
+    """token_type=char end to end -- InputManager_Char batches -> train steps -> the validation
+    perplexity loop of src/train_fn.py:320-338 -> beam-search inference -> id_to_caption."""
+    from comic_b200 import inputs, scst
+    from comic_b200.model import CaptionModel
+    from test_inputs import _dataset, _config
+    from _common import images
+    _dataset(tmp_path, n_train=16, n_valid=8)
+    c = _config(tmp_path, 'char', train_mode='decoder', infer_max_length=4)
+    loader = lambda paths: images(len(paths), seed=len(paths[0]))
+    man = inputs.get_input_manager(c, image_loader=loader)
+    assert c.vocab_size == 40 and c.max_step == int(16 / 4 * 3)
+    W = make_weights(c)
+    assert W['Model/decoder/rnn_decoder/embedding_map'].shape[0] == 40
+    m = CaptionModel(c, 'train', weights=W)
+    m_eval = CaptionModel(c, 'eval', reuse=True, share=m)
+    valid = list(man.batches('valid', epochs=1))
+    assert len(valid) >= 1
+    p0 = inputs.run_eval_loop(m_eval, valid)
+    n = 0
+    for img, caps in man.batches('train', epochs=2):
+        assert caps.min() >= -1 and caps.max() == 39
+        m.train_step(img, caps, seed=5, lr=3e-3, dropout=False)
+        n += 1
+    assert n >= 4
+    p1 = inputs.run_eval_loop(m_eval, valid)
+    assert np.isfinite(p0) and np.isfinite(p1) and p1 < p0
+    m_inf = CaptionModel(c, 'infer', reuse=True, share=m)
+    preds, _ = m_inf.run(images(2, seed=3))
+    assert preds.shape == (2, 4 * 5) and preds.max() <= 39            # char: infer_max_length x 5 steps
+    caps = scst.id_to_caption(preds, c)
+    assert len(caps) == 2 and all(set(s.replace('<GO>', '')) <= set(' 0123456789abcdefghijklmnopqrstuvwxyz') for s in caps)
