@@ -154,6 +154,10 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
     case COMIC_OPT_GEMM_RESIDENT_B: tc::bres_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR: tc::pair_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR_MIN_TILES: tc::pair_min_tiles() = value; return COMIC_OK;
+    case COMIC_OPT_GEMM_MC:
+      if (value != 0 && value != 1 && value != 2 && value != 4) break;
+      tc::mc_mode() = value;
+      return COMIC_OK;
     case COMIC_OPT_ENC_CHUNK_STEM:
     case COMIC_OPT_ENC_CHUNK_28:
     case COMIC_OPT_ENC_CHUNK_14:

@@ -73,6 +73,10 @@ struct comic_handle_s {
   bool bound = false, cnn_bound = false;
   int precision = 1;   // 0: fp32 FFMA everywhere; 1: tcgen05 split-precision GEMMs with M >= 128; 2: 1 + tanh.approx
   int fused_min_images = 48;   // fused attention kernel (one CTA per image) from this batch size on
+  int attn2_min_images = 12;   // streaming kernel (attention2.cuh) from this batch size on while fused_min_images is at its
+                               // default: its slice-granular work split fills the SMs from ~12 images (39 vs 48 us at 12
+                               // images x 3 beams, 33 vs 48 at 25, profiles/r08c_attn_small_batch.txt); an explicit
+                               // fused_min_images moves both thresholds
   int fuse_lstm = 0;           // 1: gate GEMM with the LSTM point-wise update in its epilogue (tensor path, no dropout / tape).
                                // Bit-identical to the separate kernel but measured SLOWER at 1,536 rows (gates + lstm 2.86 ->
                                // 3.02 ms per 60 steps, profiles/r06e): the GEMM has 96 tiles on 148 SMs, one per CTA, so the

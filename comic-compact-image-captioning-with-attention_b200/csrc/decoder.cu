@@ -833,7 +833,8 @@ int attn2_prepare(comic_handle_t h, StepIO& io, const StepBufs& sb, int B, int k
   io.a2_counters = nullptr;
   if (!h->attn2 || h->attn2_state < 0 || masks) return COMIC_OK;
   if (h->cfg.alignment != 0 || h->cfg.prob_fn != 0 || h->R != a2::kR || h->H != a2::kH || h->VAL != h->R ||
-      io.values != io.keys || k < 1 || k > 3 || h->M % a2::kPos != 0 || B < h->fused_min_images || !sb.kstats)
+      io.values != io.keys || k < 1 || k > 3 || h->M % a2::kPos != 0 ||
+      B < (h->fused_min_images == 48 ? h->attn2_min_images : h->fused_min_images) || !sb.kstats)
     return COMIC_OK;
   {
     Prof pf(h, T_MISC, st);

@@ -196,6 +196,23 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       ::"r"(smem_u32(bar)), "h"((uint16_t)3)
       : "memory");
 }
+// ---- weight-tile multicast (MC CTAs of a cluster share an N tile) ---------------------------------
+// TMA load delivered to the same shared-memory offset of every CTA in `mask`; each destination's barrier (same offset)
+// receives the bytes of the box.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// one arrival on the barrier at this offset in every CTA of `mask` when this CTA's earlier UMMAs retire
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
@@ -239,13 +256,21 @@ struct SmemLayout {
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
 };
 
-template <int BN, int STAGES, int AMODE, bool PAIR, int NKRES = 0>
+// MC > 1 (PAIR = false): the MC CTAs of a cluster work on MC consecutive M tiles of the SAME N tile.  Each loads 1 / MC of
+// the weight tile and multicasts it into all of them, so the panel crosses L2 -> SM once per cluster instead of once per
+// CTA (the decoder's gate GEMM and the wide convolutions are bound by exactly that traffic).  A stage may be overwritten
+// only when every CTA's UMMAs have consumed it: `empty` collects one multicast commit per CTA.
+template <int BN, int STAGES, int AMODE, bool PAIR, int NKRES = 0, int MC = 1>
 __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::type& a, const CUtensorMap* tm_hi,
                                                  const CUtensorMap* tm_lo, int M, int N, int K, const Epi& epi) {
   static_assert(!(PAIR && NKRES), "resident weight panel: single-CTA kernel only");
+  static_assert(MC == 1 || (!PAIR && NKRES == 0 && AMODE != 3 && (BN / MC) % 64 == 0), "multicast: plain kernel, slices of >= 64 rows");
+  constexpr bool CL = PAIR || MC > 1;           // launched as a cluster
+  constexpr uint16_t kMcMask = (uint16_t)((1u << MC) - 1u);
   static_assert(AMODE != 3 || (NKRES > 0 && BN == 64), "halo loader: resident-panel stem kernel only");
   using L = SmemLayout<BN, STAGES, PAIR, NKRES, AMODE == 3>;
-  constexpr int TM = PAIR ? 2 * BM : BM;        // rows per (pair) tile
+  constexpr int TM = (PAIR ? 2 : MC) * BM;      // rows per (pair / cluster) tile
+  constexpr int MMA_M = PAIR ? 2 * BM : BM;
   extern __shared__ uint8_t smem_raw[];
   if (epi.stop != nullptr && *epi.stop >= epi.stop_n) return;      // uniform over the grid
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-window address of the tiles
@@ -260,21 +285,21 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
+  const uint32_t rank = CL ? cluster_ctarank() : 0u;
+  const bool leader = PAIR ? rank == 0 : true;
   const int nk = (K + BK - 1) / BK;
   const int n_tiles = (N + BN - 1) / BN;
   const int m_tiles = (M + TM - 1) / TM;          // AMODE 3: M = nimg * 112 * 112 = nimg * 98 tiles of 8 x 16 outputs
   const int total_tiles = m_tiles * n_tiles;
-  const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x / MC;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x / MC;
 
   // ---- one-time setup ----
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_a[s], (AMODE >= 2 ? 256 : 128) * (PAIR ? 2 : 1));
       mbar_init(&full_b[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], MC);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -297,7 +322,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast
+  if constexpr (CL) cluster_sync_all();     // every CTA's barriers exist before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -453,7 +478,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
         const int n0 = (tile % n_tiles) * BN;
         const int acc = iter & 1;
         const int n_umma = min(BN, ((N - n0) + 15) & ~15);
-        const uint32_t idesc = make_idesc_bf16(TM, n_umma);
+        const uint32_t idesc = make_idesc_bf16(MMA_M, n_umma);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         if constexpr (PAIR) mbar_wait_cluster(&tmem_empty[acc], (uint32_t)(((iter >> 1) & 1) ^ 1));
         else mbar_wait(&tmem_empty[acc], (uint32_t)(((iter >> 1) & 1) ^ 1));
@@ -491,6 +516,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
           }
           // frees the stage (PAIR: in both CTAs) when the MMAs above retire
           if constexpr (PAIR) umma_commit_pair(&empty[s]);
+          else if constexpr (MC > 1) umma_commit_mc(&empty[s], kMcMask);
           else umma_commit(&empty[s]);
         }
         // accumulator complete -> epilogue (PAIR: of both CTAs)
@@ -516,7 +542,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int n0 = (tile % n_tiles) * BN;
         const int n_umma = min(BN, ((N - n0) + 15) & ~15);
-        const int nrow = PAIR ? n0 + (int)rank * (n_umma >> 1) : n0;      // first row of B^T this CTA loads
+        const int nrow = PAIR ? n0 + (int)rank * (n_umma >> 1) : n0 + (int)rank * (BN / MC);   // first row of B^T this CTA loads
         for (int kt = 0; kt < nk; ++kt, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -527,6 +553,12 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
             if (leader) mbar_arrive_expect_tx(&full_b[s], 4 * L::B_TILE_BYTES);   // both CTAs' hi + lo boxes
             tma_load_2d_pair(b_hi, tm_hi, &full_b[s], kt * BK, nrow);
             tma_load_2d_pair(b_lo, tm_lo, &full_b[s], kt * BK, nrow);
+          } else if constexpr (MC > 1) {
+            // the whole tile lands here: this CTA's slice + the peers' (their complete_tx may precede this arrive)
+            mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES);
+            const uint32_t slice = rank * (uint32_t)((BN / MC) * BK * 2);
+            tma_load_2d_mc(b_hi + slice, tm_hi, &full_b[s], kt * BK, nrow, kMcMask);
+            tma_load_2d_mc(b_lo + slice, tm_lo, &full_b[s], kt * BK, nrow, kMcMask);
           } else {
             mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES);
             tma_load_2d(b_hi, tm_hi, &full_b[s], kt * BK, nrow);
@@ -797,7 +829,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   // ---- teardown (PAIR: the peer's shared / tensor memory is in use until the leader's last UMMA retired) ----
   tc_fence_before();
   __syncthreads();
-  if constexpr (PAIR) cluster_sync_all();
+  if constexpr (CL) cluster_sync_all();
   if (warp == kMmaWarp) {
     if constexpr (PAIR)
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TMEM_COLS)
@@ -821,6 +853,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16x3_bres_kernel(const __grid_constant__ typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
                         const __grid_constant__ CUtensorMap tm_lo, int M, int N, int K, const __grid_constant__ Epi epi) {
   gemm_bf16x3_body<64, STAGES, AMODE, false, NKRES>(a, &tm_hi, &tm_lo, M, N, K, epi);
+}
+
+// MC CTAs per cluster share the weight tiles (cluster shape given at launch)
+template <int BN, int STAGES, int AMODE, int MC>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16x3_mc_kernel(const __grid_constant__ typename AParam<AMODE>::type a, const __grid_constant__ CUtensorMap tm_hi,
+                      const __grid_constant__ CUtensorMap tm_lo, int M, int N, int K, const __grid_constant__ Epi epi) {
+  gemm_bf16x3_body<BN, STAGES, AMODE, false, 0, MC>(a, &tm_hi, &tm_lo, M, N, K, epi);
 }
 
 template <int BN, int STAGES, int AMODE>
@@ -992,6 +1032,46 @@ inline cudaError_t launch_pair(const typename AParam<AMODE>::type& a, const TcWe
   return cudaGetLastError();
 }
 
+// Weight-tile multicast launch: box_idx = tensor map whose box holds BN / MC rows.
+template <int BN, int STAGES, int AMODE, int MC>
+inline cudaError_t launch_mc(const typename AParam<AMODE>::type& a, const TcWeight& w, int box_idx, int M, int N,
+                             const Epi& epi, int num_sms, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES, false>;
+  auto kern = gemm_bf16x3_mc_kernel<BN, STAGES, AMODE, MC>;
+  static PerDeviceOnce once;
+  {
+    cudaError_t e = once([&] {
+      cudaError_t e1 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+      if (e1 != cudaSuccess) return e1;
+      return cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+    });
+    if (e != cudaSuccess) return e;
+  }
+  const int super_tiles = ((N + BN - 1) / BN) * ((M + MC * BM - 1) / (MC * BM));
+  const int max_clusters = num_sms / MC;
+  const int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * MC), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = MC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int K = w.K;
+  return cudaLaunchKernelEx(&cfg, kern, a, w.tm_hi[box_idx], w.tm_lo[box_idx], M, N, K, epi);
+}
+
+// Multicast cluster size for launches with enough M tiles (0 / 1 = off, 2, 4): process-wide, set through comic_set_option.
+// Off by default: measured at the benchmarked shapes (profiles/r08c_bench512_mc*.json) clusters of 2 change nothing
+// (conv 7.07 vs 7.10 ms, gate GEMM 37.2 vs 36.8 us) and clusters of 4 lose 40 % on the encoder -- the CTAs of a cluster
+// advance in lock-step through the shared `empty` barriers, which costs what the halved weight traffic saves.
+inline int& mc_mode() { static int v = 0; return v; }
+
 // 0: single-CTA kernels only; 1: CTA-pair (cta_group::2) kernel for launches with at least
 // `pair_min_tiles` 256-row pair tiles (process-wide switch, set through comic_set_option).
 inline int& pair_mode() { static int v = 0; return v; }
@@ -1020,6 +1100,15 @@ inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const T
       if (nkb <= 4) return launch_bres<4, 4, AMODE>(a, w, M, N, epi, num_sms, st);
       if (nkb <= 6) return launch_bres<3, 6, AMODE>(a, w, M, N, epi, num_sms, st);
       if (nkb <= 8) return launch_bres<2, 8, AMODE>(a, w, M, N, epi, num_sms, st);
+    }
+  }
+  if constexpr (AMODE != 2 && AMODE != 3) {
+    const int mc = mc_mode();
+    const int m_tiles = (M + BM - 1) / BM;
+    if (mc >= 2 && bn >= 128 && m_tiles >= 2 * mc) {
+      if (bn == 128) return launch_mc<128, 3, AMODE, 2>(a, w, 0, M, N, epi, num_sms, st);
+      if (mc >= 4) return launch_mc<256, 2, AMODE, 4>(a, w, 0, M, N, epi, num_sms, st);
+      return launch_mc<256, 2, AMODE, 2>(a, w, 1, M, N, epi, num_sms, st);
     }
   }
   if (bn == 64) return launch_one<64, 4, AMODE>(a, w, 0, M, N, epi, num_sms, st);

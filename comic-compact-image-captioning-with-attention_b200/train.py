@@ -15,6 +15,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import numpy as np
 
 from . import weights as wts
@@ -115,6 +117,12 @@ class Trainer(object):
             W[name] = self.params[o:o + n].view(shp if len(shp) else (1,))
         eng.bind_weights(W, with_cnn=with_cnn)
         self._bound, self._with_cnn = W, with_cnn
+        # The teacher-forced forward + backward is ~1,100 small launches at batch 32 (25 per time step x 41 steps): replayed
+        # as ONE CUDA graph per (batch, length) shape after two eager calls of that shape.  COMIC_B200_TRAIN_GRAPH=0 or
+        # `trainer.cuda_graph = False` keeps every step eager.
+        self.cuda_graph = os.environ.get('COMIC_B200_TRAIN_GRAPH', '1') != '0'
+        self._graphs = {}
+        self.replayed_launches = 0       # kernel launches executed through graph replays (the engine counts host launches)
         fields = eng.variable_to_grad_field()
         self.grad_views = {}
         for name, (o, n, shp) in self.offsets.items():
@@ -204,9 +212,13 @@ class Trainer(object):
             loss[0:1] = loss[1:2]
             return dict(loss=loss, logits=logits, attn=attn, T_run=T_run)
         self.grads.zero_()
-        loss, logits, attn = eng.train_fwd_bwd(fm.contiguous(), im_embed.contiguous(), inputs_tm, targets_tm, coef_tm,
-                                               lens_d, T_run, self.grad_views, masks, keeps, c.rnn_map_loss_scale,
-                                               want_logits, want_attn)
+        if self.cuda_graph and not want_logits and not want_attn:
+            loss, logits, attn = self._graphed_fwd_bwd(fm, im_embed, inputs_tm, targets_tm, coef_tm, lens_d, T_run, masks,
+                                                       keeps), None, None
+        else:
+            loss, logits, attn = eng.train_fwd_bwd(fm.contiguous(), im_embed.contiguous(), inputs_tm, targets_tm,
+                                                   coef_tm, lens_d, T_run, self.grad_views, masks, keeps,
+                                                   c.rnn_map_loss_scale, want_logits, want_attn)
         mult = 1.0
         if self.finetune_cnn:
             if images is None:
@@ -223,6 +235,54 @@ class Trainer(object):
             self.grads[self.n_decoder_flat:].mul_(mult)
         loss[0:1] = loss[1:2] + loss[2:3] + loss[3:4]
         return dict(loss=loss, logits=logits, attn=attn, T_run=T_run)
+
+    def _graphed_fwd_bwd(self, fm, im_embed, inputs_tm, targets_tm, coef_tm, lens_d, T_run, masks, keeps):
+        """`Engine.train_fwd_bwd` through a CUDA graph: the launch sequence of `comic_train_fwd_bwd` depends only on the
+        shapes (the per-row lengths are device data), so after two eager calls of a shape the third captures it over
+        static input buffers and later calls copy their inputs in and replay.  Gradients land in self.grads either way."""
+        torch, eng, c = self.torch, self.engine, self.c
+        names = tuple(sorted(masks)) if masks else ()
+        key = (tuple(fm.shape), tuple(inputs_tm.shape), int(T_run), names, tuple(float(k) for k in keeps))
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = {'calls': 0, 'graph': None}
+        ent['calls'] += 1
+        live = dict(fm=fm.contiguous(), im=im_embed.contiguous(), inp=inputs_tm, tgt=targets_tm, coef=coef_tm, lens=lens_d)
+        for n in names:
+            live['m_' + n] = masks[n]
+        ws = eng._ws.get('train')
+        if ent['graph'] is not None and (ws is None or ws.data_ptr() != ent['ws_ptr']):
+            ent['graph'] = None                          # the engine's workspace moved (a longer batch came by): recapture
+        if ent['graph'] is None and ent['calls'] <= 2:
+            return eng.train_fwd_bwd(live['fm'], live['im'], inputs_tm, targets_tm, coef_tm, lens_d, T_run, self.grad_views,
+                                     masks, keeps, c.rnn_map_loss_scale, False, False)[0]
+        if ent['graph'] is None:
+            ent['static'] = {k: v.clone() for k, v in live.items()}
+            st = ent['static']
+            smasks = {n: st['m_' + n] for n in names} if names else None
+            torch.cuda.synchronize(eng.device)
+            g = torch.cuda.CUDAGraph()
+            n0 = eng.launch_count()
+            try:
+                with torch.cuda.graph(g):
+                    ent['loss'] = eng.train_fwd_bwd(st['fm'], st['im'], st['inp'], st['tgt'], st['coef'], st['lens'], T_run,
+                                                    self.grad_views, smasks, keeps, c.rnn_map_loss_scale, False, False)[0]
+                ent['graph'] = g
+                ent['launches'] = eng.launch_count() - n0
+                ent['ws_ptr'] = eng._ws['train'].data_ptr()
+            except Exception:                           # capture refused (e.g. profiling events active): stay eager
+                self.cuda_graph = False
+                torch.cuda.synchronize(eng.device)
+                self.grads.zero_()
+                return eng.train_fwd_bwd(live['fm'], live['im'], inputs_tm, targets_tm, coef_tm, lens_d, T_run,
+                                         self.grad_views, masks, keeps, c.rnn_map_loss_scale, False, False)[0]
+            self.grads.zero_()                           # (the capture itself does not execute the kernels)
+        st = ent['static']
+        for k, v in live.items():
+            st[k].copy_(v)
+        ent['graph'].replay()
+        self.replayed_launches += ent['launches']
+        return ent['loss'].clone()
 
     def apply_gradients(self, lr=None):
         """NCCL all-reduce (mean over ranks) + TF-form Adam + repack (model_base.py:387-401)."""

@@ -147,6 +147,11 @@ int comic_set_precision(comic_handle_t h, int mode);
 #define COMIC_OPT_FUSE_LSTM 13               /* 1: on the tensor path the LSTM point-wise update runs in the gate GEMM's epilogue
                                                 (gate-interleaved weight panel; bit-identical results); 0 (default): separate
                                                 kernel -- measured faster at the benchmarked shape, see comic_internal.cuh */
+#define COMIC_OPT_GEMM_MC 14                 /* tensor-path GEMMs / convs with >= 2 x value M tiles: clusters of `value` CTAs (2 or 4;
+                                               0 = off, default) work on consecutive M tiles of one N tile and multicast the
+                                               weight tile (each loads 1 / value of it): the panel crosses L2 -> SM once per
+                                               cluster.  Bit-identical to the single-CTA kernel; measured no faster (2) /
+                                               slower (4) at the benchmarked shapes, kept as an option. */
 #define COMIC_OPT_TC_MIN_ROWS 11             /* GEMMs / convs with at least this many rows run on the tensor path when
                                              * precision >= 1 (default 64) */
 int comic_set_option(comic_handle_t h, int option, int value);

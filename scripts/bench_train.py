@@ -61,7 +61,7 @@ def run_mode(mode, batch=32, steps=20, warmup=3, precision='split'):
         torch.cuda.synchronize()
     for i in range(warmup):
         out = step(i)
-    l0 = eng.launch_count()
+    l0, r0 = eng.launch_count(), tr.replayed_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -70,7 +70,8 @@ def run_mode(mode, batch=32, steps=20, warmup=3, precision='split'):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - l0
+    host_launches = eng.launch_count() - l0
+    launches = host_launches + (tr.replayed_launches - r0)     # kernels replayed from the step's CUDA graph included
     # the gradient exchange alone: NCCL sum all-reduce of the flat fp32 gradient buffer
     ar_ms = 0.0
     if world > 1:
@@ -98,7 +99,9 @@ def run_mode(mode, batch=32, steps=20, warmup=3, precision='split'):
                    'allreduce_bytes': int(tr.n_flat * 4)},
         'allreduce_ms': ar_ms,
         'loss': [float(x) for x in out['loss'].cpu().tolist()],
-        'gpu_launches_per_step': int(launches // max(steps, 1))}
+        'gpu_launches_per_step': int(launches // max(steps, 1)),
+        'host_launches_per_step': int(host_launches // max(steps, 1)) + (1 if tr.replayed_launches > r0 else 0),
+        'cuda_graph': bool(tr.replayed_launches > r0)}
     del tr, eng
     torch.cuda.empty_cache()
     return res

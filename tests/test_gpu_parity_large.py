@@ -223,3 +223,27 @@ def test_lstm_epilogue_fusion_is_bit_identical(torch_mod):
     assert a['launches'] == b['launches'] - 10            # one launch per step less
     for key in ('step_ids', 'parent_ids', 'predicted_ids', 'lengths', 'scores', 'attn'):
         assert torch_mod.equal(a[key], b[key]), key
+
+
+def test_weight_multicast_gemm_is_bit_identical(torch_mod):
+    """Clusters of 2 / 4 CTAs that multicast the weight tile (option gemm_mc) run the same UMMAs per accumulator element
+    in the same order as the single-CTA kernel: encoder output and a whole beam decode must be identical, including the
+    shapes whose last cluster is only partly inside M (70 images: 428.75 tiles of 128 rows at 28 x 28)."""
+    from _common import images
+    c = comic_config()
+    W = make_weights(c)
+    img = images(70, seed=23)
+    outs = []
+    for mc in (0, 2, 4):
+        eng = _engine(c, W, with_cnn=True)
+        eng.set_option('gemm_mc', mc)
+        emb, fm = eng.encode(eng.to_dev(img))
+        keys, values = eng.project_fm(fm)
+        c0, h0 = eng.rnn_init(emb)
+        dec = eng.decode_beam(keys, values, c0, h0, 3, 0.0, 8)
+        outs.append((emb, fm, keys, dec))
+    eng.set_option('gemm_mc', 0)                     # process-wide switch: back to the default
+    for emb, fm, keys, dec in outs[1:]:
+        assert torch_mod.equal(fm, outs[0][1]) and torch_mod.equal(emb, outs[0][0]) and torch_mod.equal(keys, outs[0][2])
+        for key in ('step_ids', 'parent_ids', 'predicted_ids', 'lengths', 'scores', 'attn'):
+            assert torch_mod.equal(dec[key], outs[0][3][key]), key

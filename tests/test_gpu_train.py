@@ -254,11 +254,11 @@ def test_char_tokens_through_input_manager_train_eval_infer(torch_mod, tmp_path)
     from comic_b200.model import CaptionModel
     from test_inputs import _dataset, _config
     from _common import images
-    _dataset(tmp_path, n_train=16, n_valid=8)
+    _dataset(tmp_path, n_train=32, n_valid=32)
     c = _config(tmp_path, 'char', train_mode='decoder', infer_max_length=4)
     loader = lambda paths: images(len(paths), seed=len(paths[0]))
     man = inputs.get_input_manager(c, image_loader=loader)
-    assert c.vocab_size == 40 and c.max_step == int(16 / 4 * 3)
+    assert c.vocab_size == 40 and c.max_step == int(32 / 4 * 3)
     W = make_weights(c)
     assert W['Model/decoder/rnn_decoder/embedding_map'].shape[0] == 40
     m = CaptionModel(c, 'train', weights=W)
@@ -279,3 +279,31 @@ def test_char_tokens_through_input_manager_train_eval_infer(torch_mod, tmp_path)
     assert preds.shape == (2, 4 * 5) and preds.max() <= 39            # char: infer_max_length x 5 steps
     caps = scst.id_to_caption(preds, c)
     assert len(caps) == 2 and all(set(s.replace('<GO>', '')) <= set(' 0123456789abcdefghijklmnopqrstuvwxyz') for s in caps)
+
+
+def test_cuda_graph_replay_of_fwd_bwd_is_bit_identical(torch_mod):
+    """Trainer replays the teacher-forced forward + backward as one CUDA graph from the third call of a shape on: loss and
+    the flat gradient buffer must equal the eager launches bit for bit (fixed-order reductions), with new inputs copied
+    into the graph's static buffers on every replay, dropout masks included."""
+    from comic_b200.train import Trainer
+    c = comic_config(train_mode='decoder', max_step=100)
+    W, im, fm, caps, _, _ = _train_case(c, B=5, L=8, seed=7, dropout=False)
+    rng = np.random.default_rng(3)
+    runs = {}
+    for graphed in (False, True):
+        tr = Trainer(c, W, with_cnn=False)
+        tr.cuda_graph = graphed
+        eng = tr.engine
+        got = []
+        for i in range(5):
+            scale = 1.0 + 0.1 * i                       # different inputs every call
+            fm_d, im_d = eng.to_dev(fm * scale), eng.to_dev(im * scale)
+            masks, keeps = tr.make_masks(5, int((caps[:, 1:] >= 0).sum(1).max()), 100 + i)
+            out = tr.forward_backward(fm_d, im_d, caps, None, masks, keeps)
+            got.append((out['loss'].clone(), tr.grads.clone()))
+        if graphed:
+            assert any(e['graph'] is not None for e in tr._graphs.values())
+        runs[graphed] = got
+    for (l0, g0), (l1, g1) in zip(runs[False], runs[True]):
+        assert torch_mod.equal(l0, l1) and torch_mod.equal(g0, g1)
+    assert not torch_mod.equal(runs[True][3][1], runs[True][4][1])
