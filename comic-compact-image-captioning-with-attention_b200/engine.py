@@ -242,6 +242,7 @@ class Engine(object):
             dev[k] = torch.as_tensor(np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v,
                                      dtype=torch.float32).to(self.device).contiguous()
         self._dev_weights = dev
+        self._bind_generation = getattr(self, '_bind_generation', 0) + 1      # invalidates captured graphs (Engine.graphed)
         D, ENC, CNN = wts.DEC, wts.ENC, wts.CNN
         cs = wts.cell_scope(c)
         att = D + 'multi_add_attention/'
@@ -464,7 +465,55 @@ class Engine(object):
         mask = 0
         for t in tags:
             mask |= 1 << KERNEL_TAGS.index(t)
+        self._profiling = mask != 0
         self._check(self.lib.comic_profile_enable(self._h, mask))
+
+    # -- CUDA graphs -------------------------------------------------------------
+    def graphed(self, key, fn, *inputs):
+        """fn(*inputs) through a CUDA graph: the inference path is ~370 dependent launches per batch (60 decode steps x 5
+        kernels), and a replayed graph launches each node ~2 us sooner than the stream does.  The first call of a
+        signature runs eagerly (it sizes the workspaces and does the one-time kernel attribute calls), the second captures,
+        later ones replay.  The signature is the inputs' addresses / shapes / dtypes, the weight binding and the workspace
+        addresses; when any of them changes the graph is dropped and rebuilt.  The returned tensors are the graph's own
+        output buffers: consume them before the next call with the same key.  COMIC_B200_INFER_GRAPH=0 disables it; so
+        does an active kernel-class profile (its events cannot be captured)."""
+        torch = self.torch
+        if not getattr(self, 'infer_graph', True) or getattr(self, '_profiling', False):
+            return fn(*inputs)
+        if not hasattr(self, '_graphs'):
+            self._graphs, self.replayed_launches = {}, 0
+            self.infer_graph = os.environ.get('COMIC_B200_INFER_GRAPH', '1') != '0'
+            if not self.infer_graph:
+                return fn(*inputs)
+
+        def signature():
+            return (tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in inputs), getattr(self, '_bind_generation', 0),
+                    tuple(sorted((k, v.data_ptr()) for k, v in self._ws.items() if hasattr(v, 'data_ptr'))))
+        ent = self._graphs.get(key)
+        if ent is not None and ent['sig'] != signature():
+            ent = None
+        if ent is None:
+            out = fn(*inputs)
+            self._graphs[key] = {'sig': signature(), 'graph': None}
+            return out
+        if ent['graph'] is None:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            n0 = self.launch_count()
+            try:
+                with torch.cuda.graph(g):
+                    ent['out'] = fn(*inputs)
+            except Exception:
+                self.infer_graph = False
+                torch.cuda.synchronize(self.device)
+                return fn(*inputs)
+            ent['graph'], ent['launches'] = g, self.launch_count() - n0
+            if ent['sig'] != signature():                  # the capture itself allocated a workspace: not replayable as keyed
+                self._graphs.pop(key)
+                return fn(*inputs)
+        ent['graph'].replay()
+        self.replayed_launches += ent['launches']
+        return ent['out']
 
     def profile_read(self, tag):
         ms, n = C.c_double(), C.c_int64()
@@ -589,6 +638,7 @@ class Engine(object):
         self._check(self.lib.comic_refresh_packed(self._h, _ptr(self._packed), self._packed.numel(), self.stream()))
 
     def launch_count(self):
+        """Kernel launches so far: the library's host-side count plus the kernels executed through graph replays."""
         n = C.c_int64()
         self._check(self.lib.comic_launch_count(self._h, C.byref(n)))
-        return n.value
+        return n.value + getattr(self, 'replayed_launches', 0)

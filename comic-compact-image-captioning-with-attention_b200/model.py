@@ -13,7 +13,7 @@ import numpy as np
 
 from . import rops
 from . import weights as wts
-from .engine import Engine
+from .engine import ComicError, Engine
 
 
 def number_to_base(n, base):
@@ -104,6 +104,7 @@ class ModelBase(object):
             alignment_history=self.collect_attention_maps, cell_input_fn=None, output_attention=False,
             initial_cell_state=rnn_init)
         attention_cell.im_embed = self.im_embed          # rops.rnn_decoder_training recomputes the initial state from it
+        attention_cell._defer_T = bool(getattr(self, '_defer_T', False))
         start_id, end_id = self._start_end_ids()
         max_it = self._maximum_iterations()
         if beam_search:
@@ -113,6 +114,7 @@ class ModelBase(object):
             raw = rops.rnn_decoder_search(attention_cell, None, None, batch_size, max_it, start_id, end_id)
         logits, output_ids, attn_maps = self._decoder_post_process(raw, top_beam=True)
         self.dec_preds, self.dec_logits, self.dec_attn_maps = output_ids, logits, attn_maps
+        self.dec_time = raw[2].time                      # executed steps: host int, or a device tensor with _defer_T
         return logits, output_ids, attn_maps
 
     # -- src/model_base.py:272-314 ---------------------------------------------
@@ -304,30 +306,46 @@ class CaptionModel(ModelBase):
             sl = slots[i % depth]
             if sl['ev_in'] is not None:
                 comp.wait_event(sl['ev_in'])
-            self._encoder(sl['dev'])
-            self._decoder_rnn()
-            preds = self.dec_preds.contiguous()
-            attn = self.dec_attn_maps.contiguous() if self.dec_attn_maps is not None else None
+            def device_step(images):
+                # no host sync inside (rops: _defer_T): full-length results + the device step count, trimmed in finish()
+                self._defer_T = True
+                try:
+                    self._encoder(images)
+                    self._decoder_rnn()
+                finally:
+                    self._defer_T = False
+                return (self.dec_preds.contiguous(),
+                        self.dec_attn_maps.contiguous() if self.dec_attn_maps is not None else None,
+                        self.dec_time.reshape(1))
+            # one CUDA graph per input slot (Engine.graphed): replayed from the slot's third batch on
+            preds, attn, t_dev = eng.graphed(('run_stream', i % depth, bool(self.collect_attention_maps)), device_step,
+                                             sl['dev'])
             ev = torch.cuda.Event()
             ev.record(comp)
             sl['ev_comp'] = ev
             hp = pinned(sl, 'h_preds', preds)
             ha = pinned(sl, 'h_attn', attn) if attn is not None else None
+            ht = pinned(sl, 'h_time', t_dev)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev)
                 hp.copy_(preds, non_blocking=True)
+                ht.copy_(t_dev, non_blocking=True)
                 preds.record_stream(s_out)
                 if attn is not None:
                     ha.copy_(attn, non_blocking=True)
                     attn.record_stream(s_out)
                 evo = torch.cuda.Event()
                 evo.record(s_out)
-            sl['ev_out'], sl['out'] = evo, (hp, ha)
+            sl['ev_out'], sl['out'] = evo, (hp, ha, ht)
 
         def finish(i):
             sl = slots[i % depth]
             sl['ev_out'].synchronize()
-            return [sl['out'][0].numpy(), None if sl['out'][1] is None else sl['out'][1].numpy()]
+            hp, ha, ht = sl['out']
+            T = int(ht[0])
+            if T < 0:
+                raise ComicError('decode loop aborted: the persistent kernel gave up at a grid barrier')
+            return [hp.numpy()[:, :T], None if ha is None else ha.numpy()[:, :, :T, :]]
 
         it = iter(batches)
         cur = next(it, None)

@@ -155,6 +155,15 @@ def rnn_decoder_beam_search(cell, embedding_fn, output_layer, batch_size, beam_s
     want_attn = getattr(cell, '_alignment_history', True)
     r = eng.decode_beam(am.keys, am.values, c0, h0, int(beam_size), float(length_penalty_weight),
                         int(maximum_iterations), want_attn=want_attn)
+    if getattr(cell, '_defer_T', False):
+        # pipelined / graph-captured callers: no host sync here.  All maximum_iterations rows are returned (rows past the
+        # executed count hold end_id / zero maps, as gather_tree and the map gather leave them) and `state.time` is the
+        # DEVICE step count; the caller trims after its own copy to the host.
+        T = int(maximum_iterations)
+        state = AttentionWrapperState(cell_state=None, attention=None, time=r['T'], alignments=None,
+                                      alignment_history=r['attn'] if want_attn else (), attention_state=None)
+        rnn_decoder_beam_search.last_extra = dict(parent_ids=r['parent_ids'], step_ids=r['step_ids'], lengths=r['lengths'])
+        return r['predicted_ids'], r['scores'], state
     T = executed_steps(r['T'])                       # the one device->host sync of a decode call
     r['T_host'] = T
     state = AttentionWrapperState(cell_state=None, attention=None, time=T, alignments=None,
@@ -180,6 +189,10 @@ def rnn_decoder_search(cell, embedding_fn, output_layer, batch_size, maximum_ite
     c0, h0 = cell._initial_cell_state
     want_attn = getattr(cell, '_alignment_history', True)
     r = eng.decode_greedy(am.keys, am.values, c0, h0, int(maximum_iterations), want_attn=want_attn)
+    if getattr(cell, '_defer_T', False):             # see rnn_decoder_beam_search
+        state = AttentionWrapperState(cell_state=None, attention=None, time=r['T'], alignments=None,
+                                      alignment_history=r['attn'] if want_attn else (), attention_state=None)
+        return r['ids'], r['logits'], state
     T = executed_steps(r['T'])
     state = AttentionWrapperState(cell_state=None, attention=None, time=T, alignments=None,
                                   alignment_history=r['attn'][:, :, :T, :] if want_attn else (), attention_state=None)

@@ -184,16 +184,18 @@ def test_run_stream_raw_pixels_and_optional_attention_maps(torch_mod):
     W = make_weights(c)
     m = CaptionModel(c, 'infer', batch_ops=None, weights=W)
     rng = np.random.default_rng(17)
-    u8 = [rng.integers(0, 256, (3, 240, 320, 3), dtype=np.uint8) for _ in range(3)]
-    refs = []
+    u8 = [rng.integers(0, 256, (3, 240, 320, 3), dtype=np.uint8) for _ in range(7)]   # 7 batches: each of the two input
+    refs = []                                                                           # slots runs eager, captures, replays
     for x in u8:
         p, a = m.run(I.preprocess_eval(x))
         refs.append((p.copy(), a.copy()))
     outs = [(p.copy(), a.copy()) for p, a in m.run_stream(iter(u8))]
-    assert len(outs) == 3
+    assert len(outs) == 7
     for (p, a), (rp, ra) in zip(outs, refs):
         np.testing.assert_array_equal(p, rp)
         np.testing.assert_array_equal(a, ra)
+    g = [e for k, e in m.engine._graphs.items() if k[0] == 'run_stream']
+    assert len(g) == 2 and all(e['graph'] is not None and e['launches'] > 10 for e in g)   # CUDA-graph replays were used
     m.collect_attention_maps = False
     outs = [(p.copy(), a) for p, a in m.run_stream(iter(u8))]
     for (p, a), (rp, _) in zip(outs, refs):
