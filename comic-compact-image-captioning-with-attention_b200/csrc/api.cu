@@ -151,6 +151,8 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
     case COMIC_OPT_TC_MIN_ROWS: h->tc_min_rows = value; return COMIC_OK;
     case COMIC_OPT_ATTN2: h->attn2 = value; return COMIC_OK;
     case COMIC_OPT_FUSE_LSTM: h->fuse_lstm = value; return COMIC_OK;
+    case COMIC_OPT_TMA_A: h->tma_a = value; return COMIC_OK;
+    case COMIC_OPT_GEMM_SMALL_TILES: tc::small_tiles() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_RESIDENT_B: tc::bres_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR: tc::pair_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR_MIN_TILES: tc::pair_min_tiles() = value; return COMIC_OK;

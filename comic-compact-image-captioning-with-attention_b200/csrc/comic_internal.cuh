@@ -82,6 +82,8 @@ struct comic_handle_s {
                                // 3.02 ms per 60 steps, profiles/r06e): the GEMM has 96 tiles on 148 SMs, one per CTA, so the
                                // epilogue's transcendentals are not hidden behind a next tile's MMAs, while the separate
                                // kernel spreads them over the whole chip.  Off by default.
+  int tma_a = 1;               // bit 0: [logits | query] GEMM, bit 1: gate GEMM read their A operand as bf16 planes through
+                               // TMA (no gather / split in the GEMM's loader warps)
   int attn2 = 1;               // streaming attention kernel (attention2.cuh) where it applies: tied values, add_LN, softmax,
                                // R = 512, 8 heads, k <= 3, no attention-map dropout; 0 = always attention.cuh
   int attn2_state = 0;         // 0: score bound of the bound weights not checked yet; 1: within range; -1: too large
@@ -183,6 +185,12 @@ struct StepBufs {
   float* abound;       // [8] per-head bound of |score|
   float* a2_scratch;   // partial contexts / sums of images split across CTAs (attention2.cuh)
   int* a2_counters;    // [N] arrival counters of split images, zero between launches
+  // TMA-staged A operands of the two decoder GEMMs (tensor path, >= 128 rows, no dropout): bf16 (hi, lo) planes of
+  // x = [emb(tok) ; ctx[src] ; h[src]] (built once per step) and of h' (written by the LSTM kernel), with their tensor maps
+  uint16_t *xp_hi, *xp_lo;   // [N][KX]
+  uint16_t *hp_hi, *hp_lo;   // [N][R]
+  ATma xmaps, hmaps;
+  bool tma_a;
 };
 
 struct StepIO {

@@ -68,7 +68,8 @@ template <bool FAST>
 __global__ void __launch_bounds__(256)
 lstm_pointwise4_kernel(const float* __restrict__ gates, const float* __restrict__ bias, const float* __restrict__ c_prev,
                        const int* __restrict__ src, int src_limit, float* __restrict__ c_new, float* __restrict__ h_new,
-                       int N, int R, const int* fin_count, int t, int n_rows) {
+                       int N, int R, const int* fin_count, int t, int n_rows, uint16_t* __restrict__ h_hi = nullptr,
+                       uint16_t* __restrict__ h_lo = nullptr) {
   if (step_stopped(fin_count, t, n_rows)) return;
   const int R4 = R >> 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,6 +98,39 @@ lstm_pointwise4_kernel(const float* __restrict__ gates, const float* __restrict_
   }
   *reinterpret_cast<float4*>(c_new + (size_t)n * R + j) = make_float4(cn[0], cn[1], cn[2], cn[3]);
   *reinterpret_cast<float4*>(h_new + (size_t)n * R + j) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+  if (h_hi != nullptr) {
+    // the [logits | q] GEMM reads h' as bf16 (hi, lo) planes through TMA: same split as its fp32 loader would do
+    uint2 hi, lo;
+    tc::split4(make_float4(hn[0], hn[1], hn[2], hn[3]), hi, lo);
+    *reinterpret_cast<uint2*>(h_hi + (size_t)n * R + j) = hi;
+    *reinterpret_cast<uint2*>(h_lo + (size_t)n * R + j) = lo;
+  }
+}
+
+// x = [emb(tok) ; ctx[src] ; h[src]] of one decode step as bf16 (hi, lo) planes [N][W + A + R] for the gate GEMM's TMA-staged A
+// operand: the gather (token / parent-beam indirection, zero rows for ids out of range) and the split happen ONCE per step
+// here instead of once per N tile inside the GEMM (8 N tiles at 4R = 2048: 8 x the loads and conversions).
+__global__ void __launch_bounds__(256)
+build_x_planes_kernel(const float* __restrict__ emb, const int* __restrict__ tok, int V, const float* __restrict__ ctx_prev,
+                      const float* __restrict__ h_prev, const int* __restrict__ src, int src_limit, int N, int W, int A, int R,
+                      uint16_t* __restrict__ x_hi, uint16_t* __restrict__ x_lo, const int* fin_count, int t, int n_rows) {
+  if (step_stopped(fin_count, t, n_rows)) return;
+  const int KX4 = (W + A + R) >> 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * KX4) return;
+  const int n = i / KX4, k = (i - n * KX4) * 4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k < W) {
+    const int tk = tok[n];
+    if (tk >= 0 && tk < V) v = ldg4(emb + (size_t)tk * W + k);
+  } else {
+    const int r = src ? src[n] : n;
+    if (r >= 0 && r < src_limit) v = (k < W + A) ? ldg4(ctx_prev + (size_t)r * A + (k - W)) : ldg4(h_prev + (size_t)r * R + (k - W - A));
+  }
+  uint2 hi, lo;
+  tc::split4(v, hi, lo);
+  *reinterpret_cast<uint2*>(x_hi + (size_t)n * (W + A + R) + k) = hi;
+  *reinterpret_cast<uint2*>(x_lo + (size_t)n * (W + A + R) + k) = lo;
 }
 
 // Generic split-K reduction: out[m, n] = sum_z part[z][m][n] + bias[n].
@@ -896,12 +930,26 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
   // tensor path without dropout / tape: the LSTM point-wise update runs in the gate GEMM's epilogue over the
   // gate-interleaved panel (same arithmetic, in the same order, as lstm_pointwise4_kernel<true>: bit-identical c / h)
   const bool fused_lstm = tc1 && h->fuse_lstm && h->pk.tc_lstm_il.ready && !io.h_drop && !io.out_mask && !io.gates_save;
+  // A operands as bf16 planes through TMA (inference decode on the tensor path: no dropout, no tape)
+  const bool tma_ok = sb.tma_a && h->tma_a && h->precision >= 1 && !io.in_mask && !io.force_dense && !io.h_drop &&
+                      !io.out_mask && !io.gates_save;
+  const bool tma_gates = tma_ok && (h->tma_a & 2) && tc1 && !fused_lstm;
+  // h' planes exist when the 4-units-per-thread LSTM kernel below runs
+  const bool tma_lq = tma_ok && (h->tma_a & 1) && !fused_lstm && (tc1 ? 1 : gemm_num_partials(h->KX, p1)) == 1 && R % 4 == 0 && N >= 128 &&
+                      use_tc(h, h->pk.tc_outq, N);
   if (fused_lstm) {
     e1.bias = h->pk.lstm_bias_il;
     e1.lstm_c_prev = io.c_prev; e1.lstm_src = io.src; e1.lstm_src_limit = io.src_limit;
     e1.lstm_c = io.c_new; e1.lstm_h = io.h_new; e1.lstm_R = R;
     Prof pf(h, T_GATES, st);
     COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a, h->pk.tc_lstm_il, N, 4 * R, e1, h->num_sms, st)));
+  } else if (tma_gates) {
+    Prof pf(h, T_GATES, st, 2);
+    const int tot4 = N * (h->KX / 4);
+    build_x_planes_kernel<<<(tot4 + 255) / 256, 256, 0, st>>>(h->w.embedding_map, io.tok, h->V, io.ctx_prev, io.h_prev, io.src,
+                                                             io.src_limit, N, W, A, R, sb.xp_hi, sb.xp_lo, io.fin_count, io.t,
+                                                             io.n_rows);
+    COMIC_CHECK_CUDA((tc::launch_gemm_tc<4>(sb.xmaps, h->pk.tc_lstm, N, 4 * R, e1, h->num_sms, st)));
   } else {
     Prof pf(h, T_GATES, st);
     if (tc1) COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a, h->pk.tc_lstm, N, 4 * R, e1, h->num_sms, st)));
@@ -914,7 +962,8 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
       const int tot4 = N * (R / 4);
       if (h->precision >= 1)
         lstm_pointwise4_kernel<true><<<(tot4 + 255) / 256, 256, 0, st>>>(sb.gates, h->w.lstm_bias, io.c_prev, io.src, io.src_limit,
-                                                                        io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows);
+                                                                        io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows,
+                                                                        tma_lq ? sb.hp_hi : nullptr, tma_lq ? sb.hp_lo : nullptr);
       else
         lstm_pointwise4_kernel<false><<<(tot4 + 255) / 256, 256, 0, st>>>(sb.gates, h->w.lstm_bias, io.c_prev, io.src, io.src_limit,
                                                                          io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows);
@@ -940,7 +989,8 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
     e2.bias = h->pk.outq_bias;
     e2.r[0] = Route{0, h->LQ, sb.lq, h->LQ, 0};
     Prof pf(h, T_LQ, st);
-    if (tc2) COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a2, h->pk.tc_outq, N, h->LQ, e2, h->num_sms, st)));
+    if (tc2 && tma_lq) COMIC_CHECK_CUDA((tc::launch_gemm_tc<4>(sb.hmaps, h->pk.tc_outq, N, h->LQ, e2, h->num_sms, st)));
+    else if (tc2) COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a2, h->pk.tc_outq, N, h->LQ, e2, h->num_sms, st)));
     else COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->pk.outq, h->LQ, N, h->LQ, R, e2, p2, st)));
   } else {
     e2.r[0] = Route{0, h->LQ, sb.lq_part, h->LQ, 0};
@@ -1002,6 +1052,15 @@ void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_ma
   sb.abound = cv.take<float>(a2::kBoundFloats);
   sb.a2_scratch = cv.take<float>(a2ok ? a2::scratch_floats(h->num_sms) : 1);
   sb.a2_counters = cv.take<int>(a2ok ? (size_t)N : 1);
+  // TMA-staged A planes (see StepBufs); the maps are encoded when the workspace is real
+  const bool planes = h->tma_a && !train_masks && N >= 128 && h->KX % 8 == 0 && h->R % 8 == 0 && h->W % 4 == 0 && h->A % 4 == 0;
+  sb.xp_hi = cv.take<uint16_t>(planes ? (size_t)N * h->KX : 8);
+  sb.xp_lo = cv.take<uint16_t>(planes ? (size_t)N * h->KX : 8);
+  sb.hp_hi = cv.take<uint16_t>(planes ? (size_t)N * h->R : 8);
+  sb.hp_lo = cv.take<uint16_t>(planes ? (size_t)N * h->R : 8);
+  sb.tma_a = false;
+  if (planes && cv.base != nullptr)
+    sb.tma_a = tc::make_a_maps(sb.xmaps, sb.xp_hi, sb.xp_lo, N, h->KX) && tc::make_a_maps(sb.hmaps, sb.hp_hi, sb.hp_lo, N, h->R);
 }
 
 struct LoopBufs {

@@ -17,6 +17,7 @@
 // 256 threads, BMxBNxBK tiles, TMxTN register tiles, register-prefetch double
 // buffering through shared memory, 128-bit loads/stores.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -129,6 +130,12 @@ template <> struct AParam<0> { typedef APlain type; };
 template <> struct AParam<1> { typedef AConv type; };
 template <> struct AParam<2> { typedef AConvP type; };
 template <> struct AParam<3> { typedef AHalo type; };
+// AMODE 4 (tensor path only): the A operand exists as bf16 (hi, lo) planes [rows, K] in global memory and is staged by
+// TMA like the weights -- no loader warps, no per-CTA gather / split (decoder GEMMs: gemm_tc.cuh, decoder.cu)
+struct ATma {
+  CUtensorMap hi, lo;
+};
+template <> struct AParam<4> { typedef ATma type; };
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

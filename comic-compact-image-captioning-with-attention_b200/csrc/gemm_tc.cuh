@@ -253,7 +253,7 @@ struct SmemLayout {
   static constexpr int EPI_BYTES = kEpiWarps * 32 * EPI_STRIDE * 4;   // per-warp 32 x 16 transpose buffer
   static constexpr int HALO_OFF = TILES_BYTES + kLoaderGroups * ROWTAB_BYTES + BAR_BYTES + EPI_BYTES;
   static constexpr int TOTAL = HALO_OFF + (HALO ? kHaloBytes : 0) + 1024;   // + alignment slack
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers (power of two)
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;   // two accumulator buffers; allocations are powers of two
 };
 
 // MC > 1 (PAIR = false): the MC CTAs of a cluster work on MC consecutive M tiles of the SAME N tile.  Each loads 1 / MC of
@@ -265,6 +265,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
                                                  const CUtensorMap* tm_lo, int M, int N, int K, const Epi& epi) {
   static_assert(!(PAIR && NKRES), "resident weight panel: single-CTA kernel only");
   static_assert(MC == 1 || (!PAIR && NKRES == 0 && AMODE != 3 && (BN / MC) % 64 == 0), "multicast: plain kernel, slices of >= 64 rows");
+  static_assert(AMODE != 4 || (!PAIR && NKRES == 0 && MC == 1), "TMA-staged A: plain kernel only");
   constexpr bool CL = PAIR || MC > 1;           // launched as a cluster
   constexpr uint16_t kMcMask = (uint16_t)((1u << MC) - 1u);
   static_assert(AMODE != 3 || (NKRES > 0 && BN == 64), "halo loader: resident-panel stem kernel only");
@@ -490,7 +491,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
             mbar_wait_cluster(&full_a[s], ph);
             mbar_wait_cluster(&full_b[s], ph);
           } else {
-            mbar_wait(&full_a[s], ph);
+            if constexpr (AMODE != 4) mbar_wait(&full_a[s], ph);      // AMODE 4: A arrives with B on full_b
             if constexpr (NKRES == 0) mbar_wait(&full_b[s], ph);
           }
           tc_fence_after();
@@ -559,6 +560,15 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
             const uint32_t slice = rank * (uint32_t)((BN / MC) * BK * 2);
             tma_load_2d_mc(b_hi + slice, tm_hi, &full_b[s], kt * BK, nrow, kMcMask);
             tma_load_2d_mc(b_lo + slice, tm_lo, &full_b[s], kt * BK, nrow, kMcMask);
+          } else if constexpr (AMODE == 4) {
+            // both operands by TMA: 128 rows of the (hi, lo) A planes + the weight tile, one transaction
+            const int m0 = (tile / n_tiles) * TM;
+            const uint32_t a_hi = smem + s * L::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES + 2 * A_TILE_BYTES);
+            tma_load_2d(a_hi, &a.hi, &full_b[s], kt * BK, m0);
+            tma_load_2d(a_hi + A_TILE_BYTES, &a.lo, &full_b[s], kt * BK, m0);
+            tma_load_2d(b_hi, tm_hi, &full_b[s], kt * BK, nrow);
+            tma_load_2d(b_lo, tm_lo, &full_b[s], kt * BK, nrow);
           } else {
             mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES);
             tma_load_2d(b_hi, tm_hi, &full_b[s], kt * BK, nrow);
@@ -570,7 +580,9 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
     __syncwarp();
   } else {
     // =====================  A loaders (this CTA's 128 rows)  =====================
-    if constexpr (AMODE == 3) {
+    if constexpr (AMODE == 4) {
+      // the TMA warp stages A: nothing to do
+    } else if constexpr (AMODE == 3) {
       // Stem conv from a shared-memory halo: per tile the 11 x 19 x 16-channel input patch (hi, lo) is fetched
       // ONCE with cp.async (the next tile's patch is in flight while this one is used); K block di (= tap row,
       // 4 taps x 16 channels = 64 contiguous values in the patch row) of output pixel (y, x) is the 128-byte run
@@ -881,7 +893,7 @@ struct TcWeight {
   uint16_t* hi = nullptr;
   uint16_t* lo = nullptr;
   int N = 0, K = 0, Npad = 0, Kpad = 0;   // K = extent of the A operand's K index space
-  CUtensorMap tm_hi[3], tm_lo[3];   // BN = 64, 128, 256
+  CUtensorMap tm_hi[4], tm_lo[4];   // BN = 64, 128, 256, 176
   bool ready = false;
 };
 
@@ -904,8 +916,8 @@ inline EncodeTiledFn get_encode_fn() {
 inline bool make_weight_maps(TcWeight& w) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return false;
-  const int bns[3] = {64, 128, 256};
-  for (int i = 0; i < 3; ++i) {
+  const int bns[4] = {64, 128, 256, 176};
+  for (int i = 0; i < 4; ++i) {
     cuuint64_t dims[2] = {(cuuint64_t)w.Kpad, (cuuint64_t)w.Npad};
     cuuint64_t strides[1] = {(cuuint64_t)w.Kpad * sizeof(uint16_t)};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bns[i]};
@@ -971,11 +983,27 @@ inline cudaError_t launch_one(const typename AParam<AMODE>::type& a, const TcWei
 // N tile = shared-memory / TMEM allocation; the UMMA N is the exact remainder per tile.
 // A launch that cannot fill the SMs with 256-wide tiles takes 128-wide ones when those still fit in one wave
 // (e.g. the [logits | query] GEMM at 1,536 rows: 48 -> 84 tiles, each half as long).
-inline int pick_bn(int M, int N, int num_sms) {
+// A launch that is less than one wave of 256-wide tiles (the decoder GEMMs at 1,536 rows: 96 and 36 tiles on 148 SMs) is
+// tile-quantisation bound -- with three MMAs per operand pair a 128 x 256 x 64 block is 0.83 us of tensor time -- so it takes
+// the width that minimises waves x (tile width + fixed cost): 176 for the gate GEMM (12 x 12 = 144 tiles), 64 for
+// [logits | query] (144 tiles).  small_ok: the caller's kernel family has the 176 / 64 instantiations.
+inline int pick_bn(int M, int N, int num_sms, bool small_ok = false) {
   if (N <= 64) return 64;
   if (N <= 128) return 128;
   const int mt = (M + BM - 1) / BM;
   const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
+  if (small_ok && t256 < num_sms) {
+    const int cand[4] = {256, 176, 128, 64};
+    int best = 256;
+    long best_cost = -1;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cand[i];
+      const int tiles = mt * ((N + bn - 1) / bn);
+      const long cost = (long)((tiles + num_sms - 1) / num_sms) * (bn + 48);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+  }
   if (t256 < num_sms && t128 <= num_sms) return 128;
   return 256;
 }
@@ -1066,6 +1094,9 @@ inline cudaError_t launch_mc(const typename AParam<AMODE>::type& a, const TcWeig
   return cudaLaunchKernelEx(&cfg, kern, a, w.tm_hi[box_idx], w.tm_lo[box_idx], M, N, K, epi);
 }
 
+// 1 (default): plain GEMMs that are less than one wave of 256-wide tiles pick their tile width by pick_bn's cost rule.
+inline int& small_tiles() { static int v = 1; return v; }
+
 // Multicast cluster size for launches with enough M tiles (0 / 1 = off, 2, 4): process-wide, set through comic_set_option.
 // Off by default: measured at the benchmarked shapes (profiles/r08c_bench512_mc*.json) clusters of 2 change nothing
 // (conv 7.07 vs 7.10 ms, gate GEMM 37.2 vs 36.8 us) and clusters of 4 lose 40 % on the encoder -- the CTAs of a cluster
@@ -1077,10 +1108,27 @@ inline int& mc_mode() { static int v = 0; return v; }
 inline int& pair_mode() { static int v = 0; return v; }
 inline int& pair_min_tiles() { static int v = 74; return v; }
 
+// Tensor maps of a bf16 (hi, lo) A operand [rows, K] (row stride K elements; K % 8 == 0), box = one 128 x 64 A tile.
+inline bool make_a_maps(ATma& a, const uint16_t* hi, const uint16_t* lo, int rows, int K) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(uint16_t)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r1 = enc(&a.hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(hi), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r2 = enc(&a.lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(lo), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
+}
+
 template <int AMODE>
 inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const TcWeight& w, int M, int N,
                                   const Epi& epi, int num_sms, cudaStream_t st) {
-  if constexpr (AMODE != 2) {
+  if constexpr (AMODE != 2 && AMODE != 4) {
     if (pair_mode() && N > 64) {
       bool planes = false;
       for (int r = 0; r < epi.nroute; ++r) planes = planes || epi.r[r].hi != nullptr;
@@ -1092,8 +1140,11 @@ inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const T
       }
     }
   }
-  int bn = pick_bn(M, N, num_sms);
-  if constexpr (AMODE != 0) {
+  int bn = pick_bn(M, N, num_sms, (AMODE == 0 || AMODE == 4) && small_tiles());
+  if constexpr (AMODE == 0 || AMODE == 4) {
+    if (bn == 176) return launch_one<176, 2, AMODE>(a, w, 3, M, N, epi, num_sms, st);
+  }
+  if constexpr (AMODE != 0 && AMODE != 4) {
     // narrow convs (N <= 64): the whole weight panel fits beside the A ring -> load it once per CTA
     if (bn == 64 && bres_mode() && (M + BM - 1) / BM >= 2 * num_sms) {
       const int nkb = (w.K + BK - 1) / BK;
@@ -1102,7 +1153,7 @@ inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const T
       if (nkb <= 8) return launch_bres<2, 8, AMODE>(a, w, M, N, epi, num_sms, st);
     }
   }
-  if constexpr (AMODE != 2 && AMODE != 3) {
+  if constexpr (AMODE != 2 && AMODE != 3 && AMODE != 4) {
     const int mc = mc_mode();
     const int m_tiles = (M + BM - 1) / BM;
     if (mc >= 2 && bn >= 128 && m_tiles >= 2 * mc) {

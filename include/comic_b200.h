@@ -147,6 +147,12 @@ int comic_set_precision(comic_handle_t h, int mode);
 #define COMIC_OPT_FUSE_LSTM 13               /* 1: on the tensor path the LSTM point-wise update runs in the gate GEMM's epilogue
                                                 (gate-interleaved weight panel; bit-identical results); 0 (default): separate
                                                 kernel -- measured faster at the benchmarked shape, see comic_internal.cuh */
+#define COMIC_OPT_TMA_A 15                   /* bit 0: [logits | query] GEMM, bit 1: gate GEMM -- on the tensor path the GEMM reads its A
+                                               operand as bf16 (hi, lo) planes through TMA (h' planes are written by the LSTM kernel;
+                                               x = [emb ; ctx ; h] is gathered and split once per step by a small kernel) instead of
+                                               gathering and splitting fp32 rows in every N tile's loader warps.  Default 1. */
+#define COMIC_OPT_GEMM_SMALL_TILES 16        /* 1 (default): plain GEMMs smaller than one wave of 256-wide tiles choose the tile width
+                                               (256 / 176 / 128 / 64) that minimises waves x width; 0: round-1 rule */
 #define COMIC_OPT_GEMM_MC 14                 /* tensor-path GEMMs / convs with >= 2 x value M tiles: clusters of `value` CTAs (2 or 4;
                                                0 = off, default) work on consecutive M tiles of one N tile and multicast the
                                                weight tile (each loads 1 / value of it): the panel crosses L2 -> SM once per

@@ -215,6 +215,7 @@ def test_lstm_epilogue_fusion_is_bit_identical(torch_mod):
     outs = []
     for fuse in (1, 0):
         eng = _engine(c, W)
+        eng.set_option('tma_a', 0)                     # (its once-per-step operand kernel would change the launch count)
         eng.set_option('fuse_lstm', fuse)
         keys, values = eng.project_fm(eng.to_dev(fm))
         c0, h0 = eng.rnn_init(eng.to_dev(im))
@@ -249,3 +250,24 @@ def test_weight_multicast_gemm_is_bit_identical(torch_mod):
         assert torch_mod.equal(fm, outs[0][1]) and torch_mod.equal(emb, outs[0][0]) and torch_mod.equal(keys, outs[0][2])
         for key in ('step_ids', 'parent_ids', 'predicted_ids', 'lengths', 'scores', 'attn'):
             assert torch_mod.equal(dec[key], outs[0][3][key]), key
+
+
+def test_tma_staged_a_operand_is_bit_identical(torch_mod):
+    """Decoder GEMMs with their A operand staged by TMA from bf16 (hi, lo) planes (option tma_a: x gathered and split once
+    per step, h' planes written by the LSTM kernel) against the loader-warp path: the same bf16 operand pairs reach the same
+    UMMAs, so a whole beam decode must be identical -- including the step-0 tile_batch indirection, the parent-beam
+    gather, and a row count that is not a multiple of the 128-row tile (150 rows)."""
+    c = comic_config()
+    W = make_weights(c, include_cnn=False)
+    for B in (50, 64):
+        im, fm = fake_features(B, seed=29)
+        outs = []
+        for on in (3, 0):
+            eng = _engine(c, W)
+            eng.set_option('tma_a', on)
+            keys, values = eng.project_fm(eng.to_dev(fm))
+            c0, h0 = eng.rnn_init(eng.to_dev(im))
+            outs.append(eng.decode_beam(keys, values, c0, h0, 3, 0.0, 12))
+        a, b = outs
+        for key in ('step_ids', 'parent_ids', 'predicted_ids', 'lengths', 'scores', 'attn'):
+            assert torch_mod.equal(a[key], b[key]), (B, key)
