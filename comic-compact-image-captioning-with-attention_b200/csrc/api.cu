@@ -153,6 +153,7 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
     case COMIC_OPT_FUSE_LSTM: h->fuse_lstm = value; return COMIC_OK;
     case COMIC_OPT_TMA_A: h->tma_a = value; return COMIC_OK;
     case COMIC_OPT_GEMM_SMALL_TILES: tc::small_tiles() = value; return COMIC_OK;
+    case COMIC_OPT_PDL: pdl_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_RESIDENT_B: tc::bres_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR: tc::pair_mode() = value; return COMIC_OK;
     case COMIC_OPT_GEMM_PAIR_MIN_TILES: tc::pair_min_tiles() = value; return COMIC_OK;

@@ -60,6 +60,7 @@
 #include <stdint.h>
 
 #include "attention.cuh"
+#include "pdl.cuh"
 
 namespace comic {
 namespace a2 {
@@ -378,7 +379,7 @@ __device__ constexpr unsigned char kRoles[16] = {A2S(0), A2S(1), A2S(2), A2S(3),
 
 template <int K, int NSW, int STAGES>
 __global__ void __launch_bounds__((NSW + kCtxWarps2 + 1 + kStatWarps) * 32, 1) attn2_kernel(const Args a) {
-  if (a.fin_count != nullptr && a.t > 0 && a.fin_count[a.t - 1] >= a.n_rows) return;
+  pdl_launch_dependents();
   using L = Layout<K, NSW, STAGES>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -451,6 +452,10 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 1 + kStatWarps) * 32, 1) a
     *reinterpret_cast<float4*>(sm_c + 2 * kR + c4 * 4) = make_float4(vs * v4.y, vs * v4.w, vs * v4.x, vs * v4.z);
   }
   __syncthreads();
+  // the prologue above read only weights and the per-call score bound: as a programmatic dependent it overlaps the tail of
+  // the [logits | query] GEMM; the queries (and the step gate) are read from here on
+  pdl_wait();
+  if (a.fin_count != nullptr && a.t > 0 && a.fin_count[a.t - 1] >= a.n_rows) return;
   if (n_g == 0) return;
 #if COMIC_A2_TRACE
   long long* trc = a.trace ? a.trace + ((size_t)blockIdx.x * L::kWarps + warp) * kTraceSlices * 8 : nullptr;
@@ -1001,8 +1006,7 @@ inline cudaError_t launch_k(const Args& a, int num_sms, int dev, cudaStream_t st
   const long long total = (long long)a.B * (a.M / kPos);
   const int grid = total < num_sms ? (int)total : num_sms;
   if (a.scratch == nullptr || a.counters == nullptr) return cudaErrorInvalidValue;
-  attn2_kernel<K, NSW, STAGES><<<grid, L::kThreads, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(attn2_kernel<K, NSW, STAGES>, dim3(grid), dim3(L::kThreads), smem, st, a);
 }
 
 inline cudaError_t launch(const Args& a, int k, int num_sms, int dev, cudaStream_t st) {

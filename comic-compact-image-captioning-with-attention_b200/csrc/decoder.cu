@@ -70,6 +70,8 @@ lstm_pointwise4_kernel(const float* __restrict__ gates, const float* __restrict_
                        const int* __restrict__ src, int src_limit, float* __restrict__ c_new, float* __restrict__ h_new,
                        int N, int R, const int* fin_count, int t, int n_rows, uint16_t* __restrict__ h_hi = nullptr,
                        uint16_t* __restrict__ h_lo = nullptr) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (step_stopped(fin_count, t, n_rows)) return;
   const int R4 = R >> 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,6 +405,8 @@ beam_step_warp_kernel(const float* __restrict__ logits, int ld, int B, int k, in
                       float* __restrict__ log_probs, uint8_t* __restrict__ finished, long long* __restrict__ lengths,
                       float* __restrict__ scores_out, int* __restrict__ word_out, int* __restrict__ parent_out,
                       int* __restrict__ tok_next, int* __restrict__ src_next, int* fin_count, int t, int n_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (step_stopped(fin_count, t, n_rows)) {
     if (blockIdx.x == 0 && threadIdx.x == 0) fin_count[t] = n_rows;
     return;
@@ -502,9 +506,9 @@ static void launch_beam_step(const float* logits, int ld, int B, int k, int V, i
                              int* tok_next, int* src_next, int* fin_count, int t, int n_rows, cudaStream_t st) {
   if (k * V <= 1536 && k <= 32 && B >= 2 * kBeamWarpImages) {
     const size_t smem = (size_t)kBeamWarpImages * k * V * sizeof(float);
-    beam_step_warp_kernel<<<(B + kBeamWarpImages - 1) / kBeamWarpImages, 32 * kBeamWarpImages, smem, st>>>(
-        logits, ld, B, k, V, eos, lpw, log_probs, finished, lengths, scores_out, word_out, parent_out, tok_next, src_next,
-        fin_count, t, n_rows);
+    launch_pdl(beam_step_warp_kernel, dim3((B + kBeamWarpImages - 1) / kBeamWarpImages), dim3(32 * kBeamWarpImages), smem, st,
+               logits, ld, B, k, V, eos, lpw, log_probs, finished, lengths, scores_out, word_out, parent_out, tok_next, src_next,
+               fin_count, t, n_rows);
   } else {
     beam_step_kernel<<<B, 256, 0, st>>>(logits, ld, k, V, eos, lpw, log_probs, finished, lengths, scores_out, word_out,
                                         parent_out, tok_next, src_next, fin_count, t, n_rows);
@@ -927,6 +931,7 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
   e1.split_stride = (long long)N * 4 * R;
   e1.stop = io.fin_count ? io.fin_count + (io.t > 0 ? io.t - 1 : 0) : nullptr;
   e1.stop_n = (io.fin_count && io.t > 0) ? io.n_rows : 0x7fffffff;
+  e1.pdl = 1;
   // tensor path without dropout / tape: the LSTM point-wise update runs in the gate GEMM's epilogue over the
   // gate-interleaved panel (same arithmetic, in the same order, as lstm_pointwise4_kernel<true>: bit-identical c / h)
   const bool fused_lstm = tc1 && h->fuse_lstm && h->pk.tc_lstm_il.ready && !io.h_drop && !io.out_mask && !io.gates_save;
@@ -961,9 +966,9 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
     if (nz1 == 1 && R % 4 == 0 && !io.h_drop && !io.out_mask && !io.gates_save && N >= 128) {
       const int tot4 = N * (R / 4);
       if (h->precision >= 1)
-        lstm_pointwise4_kernel<true><<<(tot4 + 255) / 256, 256, 0, st>>>(sb.gates, h->w.lstm_bias, io.c_prev, io.src, io.src_limit,
-                                                                        io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows,
-                                                                        tma_lq ? sb.hp_hi : nullptr, tma_lq ? sb.hp_lo : nullptr);
+        launch_pdl(lstm_pointwise4_kernel<true>, dim3((tot4 + 255) / 256), dim3(256), 0, st, sb.gates, h->w.lstm_bias, io.c_prev,
+                   io.src, io.src_limit, io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows,
+                   tma_lq ? sb.hp_hi : nullptr, tma_lq ? sb.hp_lo : nullptr);
       else
         lstm_pointwise4_kernel<false><<<(tot4 + 255) / 256, 256, 0, st>>>(sb.gates, h->w.lstm_bias, io.c_prev, io.src, io.src_limit,
                                                                          io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows);
@@ -985,6 +990,7 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
   e2.nroute = 1;
   e2.stop = e1.stop;
   e2.stop_n = e1.stop_n;
+  e2.pdl = 1;
   if (nz2 == 1) {
     e2.bias = h->pk.outq_bias;
     e2.r[0] = Route{0, h->LQ, sb.lq, h->LQ, 0};

@@ -18,6 +18,8 @@
 // buffering through shared memory, 128-bit loads/stores.
 #pragma once
 #include <cuda.h>
+
+#include "pdl.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -81,6 +83,7 @@ struct Epi {
   long long split_stride;  // elements between split-K partials of route 0
   const int* stop;         // optional device flag: skip the launch when *stop >= stop_n
   int stop_n;              // (decode loops: every beam finished in the previous step)
+  int pdl;                 // host side only: launch as a programmatic dependent (tensor path, launch_one)
   // LSTM epilogue (tensor path, gate GEMM over a GATE-INTERLEAVED weight panel: column 4 u + g = gate g of unit u, so
   // the four consecutive columns an epilogue lane owns are i, j, f, o of one unit).  lstm_h != nullptr: instead of
   // storing the pre-activations the epilogue adds `bias` (interleaved the same way), applies the BasicLSTMCell

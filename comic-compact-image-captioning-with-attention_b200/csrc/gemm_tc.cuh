@@ -273,7 +273,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   constexpr int TM = (PAIR ? 2 : MC) * BM;      // rows per (pair / cluster) tile
   constexpr int MMA_M = PAIR ? 2 * BM : BM;
   extern __shared__ uint8_t smem_raw[];
-  if (epi.stop != nullptr && *epi.stop >= epi.stop_n) return;      // uniform over the grid
+  pdl_launch_dependents();           // the next kernel of the stream may start its own prologue (it waits before it reads)
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-window address of the tiles
   uint8_t* smem_g = smem_raw + (smem - smem_u32(smem_raw));
   uint8_t* rowtab0 = smem_g + L::TILES_BYTES;
@@ -326,8 +326,14 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   if constexpr (CL) cluster_sync_all();     // every CTA's barriers exist before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only this CTA's shared / tensor memory: a programmatic dependent launch overlaps it with the
+  // predecessor's tail.  From here on global memory is read and written.
+  pdl_wait();
+  const bool stopped = epi.stop != nullptr && *epi.stop >= epi.stop_n;      // uniform over the grid
 
-  if (warp < kEpiWarps) {
+  if (stopped) {
+    // every beam had finished before this step: nothing to compute
+  } else if (warp < kEpiWarps) {
     // =====================  epilogue (this CTA's 128 rows)  =====================
     // The accumulator comes out of tensor memory one ROW per lane (32x32b); written like that, a
     // warp store touches 32 different rows (32 sectors per request).  Each 32 x 16 block is therefore
@@ -975,6 +981,8 @@ inline cudaError_t launch_one(const typename AParam<AMODE>::type& a, const TcWei
   }
   int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
   int grid = tiles < num_sms ? tiles : num_sms;
+  if (epi.pdl) return launch_pdl(gemm_bf16x3_kernel<BN, STAGES, AMODE>, dim3(grid), dim3(kThreads), L::TOTAL, st, a,
+                                 w.tm_hi[bn_idx], w.tm_lo[bn_idx], M, N, w.K, epi);
   gemm_bf16x3_kernel<BN, STAGES, AMODE><<<grid, kThreads, L::TOTAL, st>>>(a, w.tm_hi[bn_idx], w.tm_lo[bn_idx], M,
                                                                           N, w.K, epi);
   return cudaGetLastError();

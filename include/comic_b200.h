@@ -153,6 +153,10 @@ int comic_set_precision(comic_handle_t h, int mode);
                                                gathering and splitting fp32 rows in every N tile's loader warps.  Default 1. */
 #define COMIC_OPT_GEMM_SMALL_TILES 16        /* 1 (default): plain GEMMs smaller than one wave of 256-wide tiles choose the tile width
                                                (256 / 176 / 128 / 64) that minimises waves x width; 0: round-1 rule */
+#define COMIC_OPT_PDL 17                     /* 1 (default 0: measured 3.5 % slower under graph replay): the kernels of a decode step (gate GEMM, LSTM, [logits | query] GEMM, streaming
+                                               attention, beam step) are launched as programmatic dependents: each runs its
+                                               prologue (barrier / tensor-memory set-up, constants) under the tail of its
+                                               predecessor and waits (griddepcontrol.wait) before it touches global memory */
 #define COMIC_OPT_GEMM_MC 14                 /* tensor-path GEMMs / convs with >= 2 x value M tiles: clusters of `value` CTAs (2 or 4;
                                                0 = off, default) work on consecutive M tiles of one N tile and multicast the
                                                weight tile (each loads 1 / value of it): the panel crosses L2 -> SM once per
