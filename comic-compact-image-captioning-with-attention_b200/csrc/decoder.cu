@@ -500,11 +500,125 @@ beam_step_warp_kernel(const float* __restrict__ logits, int ld, int B, int k, in
   }
 }
 
+// Same step with one warp per BEAM ROW for the log-softmax part (k warps per image, kBeamRowImages images per CTA): the
+// three serial row passes of the kernel above (max, sum exp, scores: ~2.5 k instructions per lane at V = 258) run side by
+// side; the first warp of the image then draws the k winners exactly as above.  Per-candidate arithmetic and the order
+// of every reduction are those of beam_step_warp_kernel: bit-identical outputs.
+constexpr int kBeamRowImages = 2;
+__global__ void __launch_bounds__(32 * 8 * kBeamRowImages)
+beam_step_rows_kernel(const float* __restrict__ logits, int ld, int B, int k, int V, int eos, float lpw,
+                      float* __restrict__ log_probs, uint8_t* __restrict__ finished, long long* __restrict__ lengths,
+                      float* __restrict__ scores_out, int* __restrict__ word_out, int* __restrict__ parent_out,
+                      int* __restrict__ tok_next, int* __restrict__ src_next, int* fin_count, int t, int n_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (step_stopped(fin_count, t, n_rows)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) fin_count[t] = n_rows;
+    return;
+  }
+  extern __shared__ float s_sc[];                       // [kBeamRowImages][k * V] candidate scores | [kBeamRowImages][k][2] max, lse
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int li = warp / k, j = warp - li * k;           // image within the CTA, beam row
+  const int b = blockIdx.x * kBeamRowImages + li;
+  const int ncand = k * V;
+  float* sc = s_sc + (size_t)li * ncand;
+  float* st = s_sc + (size_t)kBeamRowImages * ncand + (size_t)li * k * 2;
+  const bool live = b < B;
+  const float* base = logits + (size_t)(live ? b : 0) * k * ld;
+  if (live) {
+    const float cumj = log_probs[b * k + j];
+    const bool finj = finished[b * k + j] != 0;
+    const long long lenj = lengths[b * k + j];
+    const float* row = base + (size_t)j * ld;
+    float* srow = sc + j * V;
+    float mx = -INFINITY;
+    for (int i = lane; i < V; i += 32) {
+      const float x = row[i];
+      srow[i] = x;
+      mx = fmaxf(mx, x);
+    }
+    mx = warp_max(mx);
+    float sm = 0.f;
+    for (int i = lane; i < V; i += 32) sm += expf(srow[i] - mx);
+    sm = warp_sum(sm);
+    const float lse = logf(sm);
+    if (lane == 0) { st[j * 2] = mx; st[j * 2 + 1] = lse; }
+    const float pen_live = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj + (finj ? 0 : 1), lpw);
+    const float pen_eos = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj, lpw);
+    for (int i = lane; i < V; i += 32) {
+      float lp;
+      if (finj) lp = (i == eos) ? 0.0f : -FLT_MAX;
+      else lp = (srow[i] - mx) - lse;
+      const float tot = cumj + lp;
+      srow[i] = (lpw == 0.0f) ? tot : tot / ((i == eos) ? pen_eos : pen_live);
+    }
+  }
+  __syncthreads();
+  if (!live || j != 0) return;
+  // lane j' < k keeps the state of beam row j'
+  float cum = 0.f, mxr = 0.f, lser = 0.f;
+  int fin = 0;
+  long long len = 0;
+  if (lane < k) {
+    cum = log_probs[b * k + lane];
+    fin = finished[b * k + lane];
+    len = lengths[b * k + lane];
+    mxr = st[lane * 2];
+    lser = st[lane * 2 + 1];
+  }
+  float pv = INFINITY, myv = 0.f;
+  int pi = -1, myi = 0x7fffffff;
+  for (int sel = 0; sel < k; ++sel) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int idx = lane; idx < ncand; idx += 32) {
+      const float s = sc[idx];
+      const bool eligible = (s < pv) || (s == pv && idx > pi);
+      if (eligible && better(s, idx, bv, bi)) { bv = s; bi = idx; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    pv = bv; pi = bi;
+    if (lane == sel) { myv = bv; myi = bi; }
+  }
+  int idx = myi;
+  if (idx == 0x7fffffff) idx = 0;                      // only if every candidate is NaN
+  const int par = (lane < k) ? idx / V : 0, w = idx - par * V;
+  const float cum_p = __shfl_sync(0xffffffffu, cum, par), mx_p = __shfl_sync(0xffffffffu, mxr, par);
+  const float lse_p = __shfl_sync(0xffffffffu, lser, par);
+  const int fin_p = __shfl_sync(0xffffffffu, fin, par);
+  const long long len_p = __shfl_sync(0xffffffffu, len, par);
+  if (lane < k) {
+    float lp;
+    if (fin_p) lp = (w == eos) ? 0.0f : -FLT_MAX;
+    else lp = (base[(size_t)par * ld + w] - mx_p) - lse_p;
+    const bool nfin = fin_p || (w == eos);
+    log_probs[b * k + lane] = cum_p + lp;
+    finished[b * k + lane] = nfin ? 1 : 0;
+    lengths[b * k + lane] = len_p + (fin_p ? 0 : 1);
+    scores_out[b * k + lane] = myv;
+    word_out[b * k + lane] = w;
+    parent_out[b * k + lane] = par;
+    if (tok_next) tok_next[b * k + lane] = w;
+    if (src_next) src_next[b * k + lane] = b * k + par;
+    if (fin_count && nfin) atomicAdd(&fin_count[t], 1);
+  }
+}
+
 // Host-side choice between the two beam-step kernels.
 static void launch_beam_step(const float* logits, int ld, int B, int k, int V, int eos, float lpw, float* log_probs,
                              uint8_t* finished, long long* lengths, float* scores_out, int* word_out, int* parent_out,
                              int* tok_next, int* src_next, int* fin_count, int t, int n_rows, cudaStream_t st) {
-  if (k * V <= 1536 && k <= 32 && B >= 2 * kBeamWarpImages) {
+  if (k * V <= 1536 && k >= 2 && k <= 8 && B >= 2 * kBeamWarpImages) {
+    const size_t smem = (size_t)kBeamRowImages * (k * V + 2 * k) * sizeof(float);
+    launch_pdl(beam_step_rows_kernel, dim3((B + kBeamRowImages - 1) / kBeamRowImages), dim3(32 * k * kBeamRowImages), smem, st,
+               logits, ld, B, k, V, eos, lpw, log_probs, finished, lengths, scores_out, word_out, parent_out, tok_next, src_next,
+               fin_count, t, n_rows);
+  } else if (k * V <= 1536 && k <= 32 && B >= 2 * kBeamWarpImages) {
     const size_t smem = (size_t)kBeamWarpImages * k * V * sizeof(float);
     launch_pdl(beam_step_warp_kernel, dim3((B + kBeamWarpImages - 1) / kBeamWarpImages), dim3(32 * kBeamWarpImages), smem, st,
                logits, ld, B, k, V, eos, lpw, log_probs, finished, lengths, scores_out, word_out, parent_out, tok_next, src_next,

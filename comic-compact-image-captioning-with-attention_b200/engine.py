@@ -619,6 +619,7 @@ class Engine(object):
                                               _ptr(ws), ws.numel(), self.stream()))
 
     def refresh_packed_cnn(self):
+        self._bind_generation = getattr(self, '_bind_generation', 0) + 1      # see refresh_packed
         self._check(self.lib.comic_refresh_packed_cnn(self._h, _ptr(self._packed), self._packed.numel(),
                                                       self.stream()))
 
@@ -635,6 +636,9 @@ class Engine(object):
                                              float(grad_scale), self.stream()))
 
     def refresh_packed(self):
+        # the weights changed in place: captured inference graphs (Engine.graphed) are dropped, so that their next eager call
+        # re-validates the streaming attention kernel's score bound on the host
+        self._bind_generation = getattr(self, '_bind_generation', 0) + 1
         self._check(self.lib.comic_refresh_packed(self._h, _ptr(self._packed), self._packed.numel(), self.stream()))
 
     def launch_count(self):

@@ -176,6 +176,7 @@ class Trainer(object):
             self.global_step = int(np.asarray(extra['global_step']))
         self._bound = W
         eng.bind_weights(W, with_cnn=self._with_cnn)
+        self._graphs.clear()                             # captured steps hold the previous binding's device pointers
 
     def make_masks(self, B, T_run, seed):
         """Seeded Philox dropout masks (DropoutWrapper in/out, attention-map dropout)."""
