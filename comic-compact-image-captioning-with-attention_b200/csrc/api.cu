@@ -146,6 +146,10 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
     case COMIC_OPT_FUSED_ATTN_MIN_IMAGES: h->fused_min_images = value; return COMIC_OK;
     case COMIC_OPT_PERSISTENT_MAX_ROWS: h->persist_max_rows = value; return COMIC_OK;
     case COMIC_OPT_PERSISTENT_TRACE: h->persist_trace = value; return COMIC_OK;
+    case COMIC_OPT_PERSISTENT_WATCHDOG_MS:
+      if (value < 0) break;
+      h->persist_watchdog_ms = value;
+      return COMIC_OK;
     case COMIC_OPT_ENC_PLANES: h->enc_planes = value; return COMIC_OK;
     case COMIC_OPT_STEM_S2D: h->stem_s2d = value; return COMIC_OK;
     case COMIC_OPT_TC_MIN_ROWS: h->tc_min_rows = value; return COMIC_OK;

@@ -91,6 +91,7 @@ struct comic_handle_s {
   int persist_trace = 0;       // record per-phase clock stamps of the persistent loop (diagnostics)
   long long* last_trace = nullptr;
   int last_trace_steps = 0;
+  int persist_watchdog_ms = 2000;   // grid-barrier watchdog of the persistent loop (0 = disabled)
   int persist_max_rows = 32;   // whole decode loop as one cooperative kernel up to this many rows (0 = off)
   int tc_min_rows = 64;        // GEMMs / convs with at least this many rows take the tensor path (precision >= 1); half-empty
                                // M tiles still beat the FFMA kernel (batch 25-32 beam-3: gate GEMM 37 -> 29 us, r02p)

@@ -75,6 +75,7 @@ struct PersistArgs {
   float* sc;                  // beam: [T][N] scores
   float* logits_out;          // greedy: [T][N][V] or nullptr
   unsigned* bar;              // [0] barrier counter, [1] abort flag
+  long long spin_limit;       // grid-barrier watchdog in clock cycles (0 = none)
   long long* trace;           // [max_it][2][16] clock64 stamps of CTA 0 and the first selection CTA, or nullptr
   // partition / smem plan (floats)
   int KG, KS, CB, nB, S, rps, cps, nh_max, keys_res, vals_res, n_sel;
@@ -89,7 +90,10 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 
 // All CTAs of the (cooperative) grid meet here.  Returns false when the launch was aborted.
-__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned& target, unsigned nblocks, int* s_abort) {
+// spin_limit: clock64 cycles a CTA may wait before it declares the launch dead (0 = wait for ever: time-sliced GPUs,
+// debuggers); COMIC_OPT_PERSISTENT_WATCHDOG_MS.
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned& target, unsigned nblocks, int* s_abort,
+                                             long long spin_limit) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += nblocks;
@@ -99,7 +103,7 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned& target, un
     int ab = 0;
     while (ld_acquire_u32(bar) < target) {
       if (ld_acquire_u32(bar + 1) != 0u) { ab = 1; break; }
-      if (clock64() - t0 > 4000000000ll) {   // ~2 s at 1.9 GHz: publish the abort and leave
+      if (spin_limit > 0 && clock64() - t0 > spin_limit) {   // default ~2 s at 1.9 GHz: publish the abort and leave
         atomicExch(bar + 1, 1u);
         ab = 1;
         break;
@@ -340,7 +344,7 @@ decode_loop_kernel(const PersistArgs a) {
       }
     }
     stamp(t, 11);
-    if (!grid_barrier(a.bar, bar_target, G, &s_abort)) return;
+    if (!grid_barrier(a.bar, bar_target, G, &s_abort, a.spin_limit)) return;
     stamp(t, 12);
 
     // ============================ phase A2: fixed-order sum over the K groups + bias, LSTM cell -> c', h'
@@ -374,7 +378,7 @@ decode_loop_kernel(const PersistArgs a) {
       }
     }
     stamp(t, 1);
-    if (!grid_barrier(a.bar, bar_target, G, &s_abort)) return;
+    if (!grid_barrier(a.bar, bar_target, G, &s_abort, a.spin_limit)) return;
     stamp(t, 2);
 
     // ============================ phase B: [logits | q] = h' . [W_o | W_q] + bias
@@ -443,7 +447,7 @@ decode_loop_kernel(const PersistArgs a) {
       cp_async_wait<0>();
     }
     stamp(t, 3);
-    if (!grid_barrier(a.bar, bar_target, G, &s_abort)) return;
+    if (!grid_barrier(a.bar, bar_target, G, &s_abort, a.spin_limit)) return;
     stamp(t, 4);
 
     // ============================ phase C1: attention scores  ||  beam / greedy selection
@@ -546,7 +550,7 @@ decode_loop_kernel(const PersistArgs a) {
                                   a.logits_out ? a.logits_out + (size_t)t * N * a.V : nullptr, a.tok, a.fin,
                                   a.fin_count, t);
       }
-    } else if (!grid_barrier(a.bar, bar_target, G, &s_abort)) {
+    } else if (!grid_barrier(a.bar, bar_target, G, &s_abort, a.spin_limit)) {
       return;
     }
     stamp(t, 6);
@@ -642,7 +646,7 @@ decode_loop_kernel(const PersistArgs a) {
       }
     }
     stamp(t, 7);
-    if (!grid_barrier(a.bar, bar_target, G, &s_abort)) return;
+    if (!grid_barrier(a.bar, bar_target, G, &s_abort, a.spin_limit)) return;
     stamp(t, 8);
 
     // every row finished in this step -> the loop ends (dynamic_decode's all(finished))
@@ -765,6 +769,7 @@ int decode_persistent(comic_handle_t h, const PersistCall& pc, cudaStream_t st) 
   a.lq = pc.lq; a.scores = pc.scores; a.hist = pc.hist; a.tok = pc.tok; a.src = pc.src; a.cum = pc.cum;
   a.fin = pc.fin; a.len = pc.len; a.fin_count = pc.fin_count; a.step_ids = pc.step_ids; a.parents = pc.parents;
   a.sc = pc.sc; a.logits_out = pc.logits_out; a.bar = pc.bar; a.trace = pc.trace;
+  a.spin_limit = (long long)h->persist_watchdog_ms * 1900000ll;           // ms -> cycles at ~1.9 GHz
   h->last_trace = pc.trace; h->last_trace_steps = pc.trace ? pc.max_it : 0;
   a.KG = p.KG; a.KS = p.KS; a.part = pc.part; a.CB = p.CB; a.nB = p.nB; a.S = p.S; a.rps = p.rps; a.cps = p.cps;
   a.nh_max = p.nh_max; a.keys_res = p.keys_res; a.vals_res = p.vals_res; a.n_sel = pc.B;

@@ -157,6 +157,9 @@ int comic_set_precision(comic_handle_t h, int mode);
                                                attention, beam step) are launched as programmatic dependents: each runs its
                                                prologue (barrier / tensor-memory set-up, constants) under the tail of its
                                                predecessor and waits (griddepcontrol.wait) before it touches global memory */
+#define COMIC_OPT_PERSISTENT_WATCHDOG_MS 18   /* how long a CTA of the persistent decode loop may spin at a grid barrier before the
+                                               launch is declared dead (T_out = -1); default 2000, 0 = never (time-sliced GPUs,
+                                               debuggers) */
 #define COMIC_OPT_GEMM_MC 14                 /* tensor-path GEMMs / convs with >= 2 x value M tiles: clusters of `value` CTAs (2 or 4;
                                                0 = off, default) work on consecutive M tiles of one N tile and multicast the
                                                weight tile (each loads 1 / value of it): the panel crosses L2 -> SM once per
