@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include "attention.cuh"
+#include "beam_warp.cuh"
 #include "attention2.cuh"
 #include "comic_internal.cuh"
 #include "search_steps.cuh"
@@ -401,103 +402,18 @@ beam_step_kernel(const float* __restrict__ logits, int ld, int k, int V, int eos
 // ascending).  Same per-candidate arithmetic as beam_step_block; only the order of the sum inside log-sum-exp differs.
 constexpr int kBeamWarpImages = 4;
 __global__ void __launch_bounds__(32 * kBeamWarpImages)
-beam_step_warp_kernel(const float* __restrict__ logits, int ld, int B, int k, int V, int eos, float lpw,
-                      float* __restrict__ log_probs, uint8_t* __restrict__ finished, long long* __restrict__ lengths,
-                      float* __restrict__ scores_out, int* __restrict__ word_out, int* __restrict__ parent_out,
-                      int* __restrict__ tok_next, int* __restrict__ src_next, int* fin_count, int t, int n_rows) {
+beam_step_warp_kernel(const BeamWarpArgs g, int B, int n_rows) {
   pdl_launch_dependents();
   pdl_wait();
-  if (step_stopped(fin_count, t, n_rows)) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) fin_count[t] = n_rows;
+  if (step_stopped(g.fin_count, g.t, n_rows)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) g.fin_count[g.t] = n_rows;
     return;
   }
   extern __shared__ float s_sc[];                       // [kBeamWarpImages][k * V] candidate scores
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * kBeamWarpImages + warp;
   if (b >= B) return;
-  const int ncand = k * V;
-  float* sc = s_sc + (size_t)warp * ncand;
-  const float* base = logits + (size_t)b * k * ld;
-  // lane j < k keeps the state and the log-softmax statistics of beam row j
-  float cum = 0.f, mxr = 0.f, lser = 0.f;
-  int fin = 0;
-  long long len = 0;
-  if (lane < k) {
-    cum = log_probs[b * k + lane];
-    fin = finished[b * k + lane];
-    len = lengths[b * k + lane];
-  }
-  for (int j = 0; j < k; ++j) {
-    const float* row = base + (size_t)j * ld;
-    float* srow = sc + j * V;
-    float mx = -INFINITY;
-    for (int i = lane; i < V; i += 32) {
-      const float x = row[i];
-      srow[i] = x;
-      mx = fmaxf(mx, x);
-    }
-    mx = warp_max(mx);
-    float sm = 0.f;
-    for (int i = lane; i < V; i += 32) sm += expf(srow[i] - mx);
-    sm = warp_sum(sm);
-    const float lse = logf(sm);
-    if (lane == j) { mxr = mx; lser = lse; }
-    const float cumj = __shfl_sync(0xffffffffu, cum, j);
-    const bool finj = __shfl_sync(0xffffffffu, fin, j) != 0;
-    const long long lenj = __shfl_sync(0xffffffffu, len, j);
-    const float pen_live = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj + (finj ? 0 : 1), lpw);
-    const float pen_eos = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj, lpw);
-    for (int i = lane; i < V; i += 32) {
-      float lp;
-      if (finj) lp = (i == eos) ? 0.0f : -FLT_MAX;
-      else lp = (srow[i] - mx) - lse;
-      const float tot = cumj + lp;
-      srow[i] = (lpw == 0.0f) ? tot : tot / ((i == eos) ? pen_eos : pen_live);
-    }
-  }
-  __syncwarp();
-  float pv = INFINITY, myv = 0.f;
-  int pi = -1, myi = 0x7fffffff;
-  for (int sel = 0; sel < k; ++sel) {
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int idx = lane; idx < ncand; idx += 32) {
-      const float s = sc[idx];
-      const bool eligible = (s < pv) || (s == pv && idx > pi);
-      if (eligible && better(s, idx, bv, bi)) { bv = s; bi = idx; }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-    }
-    pv = bv; pi = bi;
-    if (lane == sel) { myv = bv; myi = bi; }
-  }
-  // lane `sel` < k finishes selection `sel`
-  int idx = myi;
-  if (idx == 0x7fffffff) idx = 0;                      // only if every candidate is NaN
-  const int par = (lane < k) ? idx / V : 0, w = idx - par * V;
-  const float cum_p = __shfl_sync(0xffffffffu, cum, par), mx_p = __shfl_sync(0xffffffffu, mxr, par);
-  const float lse_p = __shfl_sync(0xffffffffu, lser, par);
-  const int fin_p = __shfl_sync(0xffffffffu, fin, par);
-  const long long len_p = __shfl_sync(0xffffffffu, len, par);
-  if (lane < k) {
-    float lp;
-    if (fin_p) lp = (w == eos) ? 0.0f : -FLT_MAX;
-    else lp = (base[(size_t)par * ld + w] - mx_p) - lse_p;
-    const bool nfin = fin_p || (w == eos);
-    log_probs[b * k + lane] = cum_p + lp;
-    finished[b * k + lane] = nfin ? 1 : 0;
-    lengths[b * k + lane] = len_p + (fin_p ? 0 : 1);
-    scores_out[b * k + lane] = myv;
-    word_out[b * k + lane] = w;
-    parent_out[b * k + lane] = par;
-    if (tok_next) tok_next[b * k + lane] = w;
-    if (src_next) src_next[b * k + lane] = b * k + par;
-    if (fin_count && nfin) atomicAdd(&fin_count[t], 1);
-  }
+  beam_step_one_warp(g, b, s_sc + (size_t)warp * g.k * g.V, lane);
 }
 
 // Same step with one warp per BEAM ROW for the log-softmax part (k warps per image, kBeamRowImages images per CTA): the
@@ -620,9 +536,10 @@ static void launch_beam_step(const float* logits, int ld, int B, int k, int V, i
                fin_count, t, n_rows);
   } else if (k * V <= 1536 && k <= 32 && B >= 2 * kBeamWarpImages) {
     const size_t smem = (size_t)kBeamWarpImages * k * V * sizeof(float);
-    launch_pdl(beam_step_warp_kernel, dim3((B + kBeamWarpImages - 1) / kBeamWarpImages), dim3(32 * kBeamWarpImages), smem, st,
-               logits, ld, B, k, V, eos, lpw, log_probs, finished, lengths, scores_out, word_out, parent_out, tok_next, src_next,
-               fin_count, t, n_rows);
+    BeamWarpArgs g{logits, ld, k, V, eos, lpw, log_probs, finished, lengths, scores_out, word_out, parent_out, tok_next, src_next,
+                   fin_count, t};
+    launch_pdl(beam_step_warp_kernel, dim3((B + kBeamWarpImages - 1) / kBeamWarpImages), dim3(32 * kBeamWarpImages), smem, st, g,
+               B, n_rows);
   } else {
     beam_step_kernel<<<B, 256, 0, st>>>(logits, ld, k, V, eos, lpw, log_probs, finished, lengths, scores_out, word_out,
                                         parent_out, tok_next, src_next, fin_count, t, n_rows);
@@ -1520,6 +1437,9 @@ extern "C" int comic_decode_beam(comic_handle_t h, const float* keys, const floa
     io.hist_scale = (attn_top_out && io.kstats) ? lb.hist_scale + (size_t)t * N * h->H : nullptr;
     io.in_keep = io.out_keep = io.att_keep = 1.f;
     io.fin_count = lb.fin_count; io.t = t; io.n_rows = N;
+    // (Tried: the beam-search step of an image inside the streaming attention kernel's finaliser warp -- it needs only the
+    // logits -- to save the step's fifth launch.  The finaliser then prepares the next segment's queries late and the
+    // attention launch grows by 29 us for the 15 us saved: profiles/r10a_bench512_fuse_beam=*.json.  Not kept.)
     int rc = run_step(h, io, lb.sb, B, k, st);
     if (rc) return rc;
     {
