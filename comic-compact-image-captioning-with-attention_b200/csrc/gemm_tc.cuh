@@ -1152,6 +1152,11 @@ inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const T
   if constexpr (AMODE == 0 || AMODE == 4) {
     if (bn == 176) return launch_one<176, 2, AMODE>(a, w, 3, M, N, epi, num_sms, st);
   }
+  if constexpr (AMODE == 1) {
+    // convolutions a little wider than one 256-column tile (Mixed_4e / 4f 3x3: N = 288 / 320): two tiles of 176 + rest
+    // instead of 256 + a 32..64-column tile that pays a full pass over the im2col operand for a sliver of MMA work
+    if (small_tiles() && N > 256 && N <= 352 && w.K >= 512) return launch_one<176, 2, 1>(a, w, 3, M, N, epi, num_sms, st);
+  }
   if constexpr (AMODE != 0 && AMODE != 4) {
     // narrow convs (N <= 64): the whole weight panel fits beside the A ring -> load it once per CTA
     if (bn == 64 && bres_mode() && (M + BM - 1) / BM >= 2 * num_sms) {

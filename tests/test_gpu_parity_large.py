@@ -271,3 +271,22 @@ def test_tma_staged_a_operand_is_bit_identical(torch_mod):
         a, b = outs
         for key in ('step_ids', 'parent_ids', 'predicted_ids', 'lengths', 'scores', 'attn'):
             assert torch_mod.equal(a[key], b[key]), (B, key)
+
+
+def test_programmatic_dependent_launch_is_bit_identical(torch_mod):
+    """Option pdl: the decode-step kernels launched as programmatic dependents (prologue under the predecessor's tail,
+    griddepcontrol.wait before the first global access) must produce the same decode as ordinary stream launches."""
+    c = comic_config()
+    W = make_weights(c, include_cnn=False)
+    im, fm = fake_features(50, seed=31)
+    outs = []
+    for on in (1, 0):
+        eng = _engine(c, W)
+        eng.set_option('pdl', on)
+        keys, values = eng.project_fm(eng.to_dev(fm))
+        c0, h0 = eng.rnn_init(eng.to_dev(im))
+        outs.append(eng.decode_beam(keys, values, c0, h0, 3, 0.0, 10))
+    eng.set_option('pdl', 0)                         # process-wide switch: back to the default
+    a, b = outs
+    for key in ('step_ids', 'parent_ids', 'predicted_ids', 'lengths', 'scores', 'attn'):
+        assert torch_mod.equal(a[key], b[key]), key
