@@ -899,7 +899,7 @@ struct TcWeight {
   uint16_t* hi = nullptr;
   uint16_t* lo = nullptr;
   int N = 0, K = 0, Npad = 0, Kpad = 0;   // K = extent of the A operand's K index space
-  CUtensorMap tm_hi[4], tm_lo[4];   // BN = 64, 128, 256, 176
+  CUtensorMap tm_hi[5], tm_lo[5];   // BN = 64, 128, 256, 176, 192
   bool ready = false;
 };
 
@@ -922,8 +922,8 @@ inline EncodeTiledFn get_encode_fn() {
 inline bool make_weight_maps(TcWeight& w) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return false;
-  const int bns[4] = {64, 128, 256, 176};
-  for (int i = 0; i < 4; ++i) {
+  const int bns[5] = {64, 128, 256, 176, 192};
+  for (int i = 0; i < 5; ++i) {
     cuuint64_t dims[2] = {(cuuint64_t)w.Kpad, (cuuint64_t)w.Npad};
     cuuint64_t strides[1] = {(cuuint64_t)w.Kpad * sizeof(uint16_t)};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bns[i]};
@@ -1156,6 +1156,10 @@ inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const T
     // convolutions a little wider than one 256-column tile (Mixed_4e / 4f 3x3: N = 288 / 320): two tiles of 176 + rest
     // instead of 256 + a 32..64-column tile that pays a full pass over the im2col operand for a sliver of MMA work
     if (small_tiles() && N > 256 && N <= 352 && w.K >= 512) return launch_one<176, 2, 1>(a, w, 3, M, N, epi, num_sms, st);
+    // 3x3 convolutions with exactly 192 outputs and one 64-channel block per tap (Conv2d_2c): a 192-column tile leaves
+    // 40 KB less shared memory allocated, the L1 carve-out grows from 28 to 60 KB and the horizontally neighbouring taps of
+    // consecutive K blocks (same pixels shifted by one, 32 KB apart) hit L1 instead of L2
+    if (small_tiles() && N == 192 && a.KH == 3 && a.Cin == 64) return launch_one<192, 2, 1>(a, w, 4, M, N, epi, num_sms, st);
   }
   if constexpr (AMODE != 0 && AMODE != 4) {
     // narrow convs (N <= 64): the whole weight panel fits beside the A ring -> load it once per CTA
