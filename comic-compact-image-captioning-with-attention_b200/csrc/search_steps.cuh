@@ -98,7 +98,19 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
   for (int j = 0; j < k; ++j) {
     const float* row = base + (size_t)j * ldr;
     float mx = -INFINITY;
-    for (int i = tid; i < V; i += 256) mx = fmaxf(mx, ld_logit(row + i));
+    if (staged) {
+      for (int i = tid; i < V; i += 256) mx = fmaxf(mx, ld_logit(row + i));
+    } else {
+      // word vocabularies read the row from L2: 8 independent loads in flight per thread instead of one dependent load
+      // per iteration (39 round trips per pass at V = 10,000); the order of every accumulation is unchanged
+      for (int i0 = tid; i0 < V; i0 += 256 * 8) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = (i0 + 256 * u < V) ? ld_logit(row + i0 + 256 * u) : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx = fmaxf(mx, x[u]);
+      }
+    }
     mx = warp_max(mx);
     if (lane == 0) S.s_rv[warp] = mx;
     group_sync(1, 256);
@@ -112,7 +124,14 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
     } else {
       // word vocabularies: 10^4 exponentials per row -- ex2.approx-based exp (relative error ~1e-6 per
       // term, far below the fp32 rounding of the log-prob it feeds)
-      for (int i = tid; i < V; i += 256) sm += __expf(ld_logit(row + i) - m2);
+      for (int i0 = tid; i0 < V; i0 += 256 * 8) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = (i0 + 256 * u < V) ? ld_logit(row + i0 + 256 * u) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (i0 + 256 * u < V) sm += __expf(x[u] - m2);
+      }
     }
     sm = warp_sum(sm);
     if (lane == 0) S.s_rv[warp] = sm;
@@ -156,10 +175,17 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
       const float pen_live = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj + (finj ? 0 : 1), lpw);
       const float pen_eos = (lpw == 0.0f) ? 1.0f : length_penalty_dev(lenj, lpw);
       const int off = j * V;
-      for (int w = tid; w < V; w += 256) {
+      for (int w0 = tid; w0 < V; w0 += 256 * 8) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = (!finj && w0 + 256 * u < V) ? ld_logit(row + w0 + 256 * u) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+        const int w = w0 + 256 * u;
+        if (w >= V) break;
         float lp;
         if (finj) lp = (w == eos) ? 0.0f : -FLT_MAX;
-        else lp = (ld_logit(row + w) - mxj) - lsej;
+        else lp = (x[u] - mxj) - lsej;
         const float tot = cumj + lp;
         const float sc = (lpw == 0.0f) ? tot : tot / ((w == eos) ? pen_eos : pen_live);
         const int idx = off + w;
@@ -173,6 +199,7 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
             }
           }
         }
+        }   // u
       }
     }
     for (int sel = 0; sel < k; ++sel) {
