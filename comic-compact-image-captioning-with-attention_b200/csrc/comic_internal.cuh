@@ -215,6 +215,8 @@ struct StepIO {
   // training tape (train.cu): pre-activation gates [N,4R], pre-dropout alignments [N,H*M];
   // force_dense assembles x = [emb;ctx] into StepBufs::xdense even without an input mask
   float* gates_save; float* alpha_pre; int force_dense;
+  // training with signorm attention (train.cu): keep the raw scores of the step in StepBufs::scores (sliced kernels only)
+  int no_fused;
   // streaming attention (attention2.cuh): key-row statistics / score bound of `keys`, or nullptr when not prepared
   const float* kstats; const float* abound;
   float* a2_scratch; int* a2_counters;

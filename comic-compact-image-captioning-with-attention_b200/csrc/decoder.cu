@@ -844,6 +844,7 @@ static cudaError_t launch_fused(comic_handle_t h, const AttnArgs& aa, int B, siz
 // (caller falls back to the sliced scores + context kernels), < 0 on error.
 static int dispatch_fused(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int k, float* ctx_dst,
                           int ld_ctx, cudaStream_t st) {
+  if (io.no_fused) return 0;
   if (io.kstats != nullptr && io.att_mask == nullptr && io.alpha_pre == nullptr) {
     // streaming kernel (attention2.cuh); attn2_prepare has checked the configuration
     a2::Args aa{};

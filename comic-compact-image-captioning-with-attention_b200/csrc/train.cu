@@ -275,7 +275,7 @@ attn_bwd_score_kernel(const float* __restrict__ values, int VAL, const float* __
                       const float* __restrict__ a_pre, const float* __restrict__ att_mask, float att_keep,
                       float map_coef, float* __restrict__ dvalues, float* __restrict__ ds_out,
                       float* __restrict__ dT_acc, float* __restrict__ map_rows, const float* __restrict__ temperature,
-                      int k, int H, int M, const float* dal_in) {
+                      int k, int H, int M, const float* dal_in, const float* __restrict__ s_in) {
   extern __shared__ float sm[];            // dal [H][M]
   __shared__ float red[8];
   const int b = blockIdx.x;
@@ -341,8 +341,15 @@ attn_bwd_score_kernel(const float* __restrict__ values, int VAL, const float* __
       for (int m = lane; m < M; m += 32) {
         float a = al[m];
         float ds = a * (sm[hh * M + m] - dot);
+        if (s_in) {
+          // _signorm (src/model_base.py:599-603): alpha = g / sum g, g = sigmoid(s)  ->  ds = alpha (dalpha - <alpha, dalpha>) (1 - g)
+          const float sv = s_in[((size_t)n * H + hh) * M + m];
+          ds *= 1.0f - sigm(sv);
+          dT_part += ds * sv;
+        } else {
+          dT_part += ds * logf(fmaxf(a, 1e-37f));       // = ds * s up to a per-row constant (sum ds = 0)
+        }
         ds_out[((size_t)n * H + hh) * M + m] = ds;
-        dT_part += ds * logf(fmaxf(a, 1e-37f));
       }
     }
     dT_part = wred_sum(dT_part);
@@ -352,7 +359,7 @@ attn_bwd_score_kernel(const float* __restrict__ values, int VAL, const float* __
     if (tid == 0) {
       float s = 0.f;
       for (int w = 0; w < 8; ++w) s += red[w];
-      dT_acc[n] += -s / temperature[0];
+      if (temperature) dT_acc[n] += -s / temperature[0];   // MultiHeadDot has no temperature (common/ops_rnn.py:603-632)
     }
     __syncthreads();
   }
@@ -464,6 +471,65 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
       cp[(size_t)which * R + j] += (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
     __syncthreads();
   }
+}
+
+// MultiHeadDot backward (common/ops_rnn.py:603-632): s[n, h, m] = <k[b, m, h], q[n, h]> / sqrt(D).  Same grid, lane
+// ownership and partial-sum layout as attn_bwd_ln_kernel (single owner per (image, position) -> deterministic).
+template <int R>
+__global__ void __launch_bounds__(128)
+attn_bwd_dot_kernel(const float* __restrict__ keys, const float* __restrict__ lq, int ld_lq, int q_off,
+                    const float* __restrict__ ds, float* __restrict__ dkeys, float* __restrict__ dq_part, int k, int H,
+                    int M, int S, int N) {
+  constexpr int CPL = R / 32;
+  const int b = blockIdx.x, sl = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = lane * CPL;
+  const int D = R / H;
+  const int m_lo = (int)(((long long)M * sl) / S), m_hi = (int)(((long long)M * (sl + 1)) / S);
+  const float inv = 1.0f / sqrtf((float)D);
+  __shared__ float red[4][R];
+  for (int beam = 0; beam < k; ++beam) {
+    const int n = b * k + beam;
+    float q[CPL], dq_a[CPL];
+    const float* qp = lq + (size_t)n * ld_lq + q_off + c0;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { q[c] = qp[c]; dq_a[c] = 0.f; }
+    for (int m = m_lo + warp; m < m_hi; m += 4) {
+      const float* kr = keys + ((size_t)b * M + m) * R + c0;
+      float* dkr = dkeys + ((size_t)b * M + m) * R + c0;
+#pragma unroll
+      for (int c4 = 0; c4 < CPL / 4; ++c4) {
+        const float4 kv = ldg4(kr + c4 * 4);
+        float4 acc = *reinterpret_cast<const float4*>(dkr + c4 * 4);
+        const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
+        float g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c4 * 4 + j;
+          const float dz = ds[((size_t)n * H + (c0 + c) / D) * M + m] * inv;
+          dq_a[c] = fmaf(dz, kk[j], dq_a[c]);
+          g[j] = dz * q[c];
+        }
+        acc.x += g[0]; acc.y += g[1]; acc.z += g[2]; acc.w += g[3];
+        *reinterpret_cast<float4*>(dkr + c4 * 4) = acc;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) red[warp][c0 + c] = dq_a[c];
+    __syncthreads();
+    for (int j = threadIdx.x; j < R; j += 128)
+      dq_part[((size_t)sl * N + n) * R + j] = (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
+    __syncthreads();
+  }
+}
+
+// dst[b, :] = (t >= lens[b]) ? 0 : src[b, :]   (imputed rows do not reach the context layer)
+__global__ void mask_fin_copy_kernel(const float* __restrict__ src, const int* __restrict__ lens, int t,
+                                     float* __restrict__ dst, int B, int A) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * A) return;
+  const int b = (int)(i / A);
+  dst[i] = (lens && t >= lens[b]) ? 0.f : src[i];
 }
 
 // dlq[n, q_off + j] = sum_s dq_part[s][n][j]
@@ -655,6 +721,8 @@ struct TrainBufs {
   float *dkeys, *dvals, *keys, *vals, *dx0;
   float *KT, *outqT, *xh, *xhT, *hdT, *fmT, *embT, *dOutQ, *part, *scal;
   float *encT, *dfm_tmp;   // cnn_finetune: transposed W_k / W_v / W_I, second dfm term (independent)
+  // variants: raw scores per step (signorm), context-layer input / masked output gradient per step, a_layer^T
+  float *stape, *ctxraw, *gctx_tape, *dctxraw, *aT, *ctxrawT;
   size_t part_floats;
   int S, rows_pad;
 };
@@ -718,6 +786,13 @@ static void carve_train(comic_handle_t h, Carver& cv, int B, int T_run, TrainBuf
     tb.encT = cv.take<float>(a > b ? a : b);
     tb.dfm_tmp = cv.take<float>(h->cfg.fm_projection == 2 ? (size_t)B * h->M * h->C : 1);
   }
+  tb.stape = cv.take<float>(h->cfg.prob_fn == 1 ? (size_t)T_run * B * HM : 1);
+  const bool cl = h->cfg.context_layer != 0;
+  tb.ctxraw = cv.take<float>(cl ? (size_t)T_run * B * h->VAL : 1);
+  tb.gctx_tape = cv.take<float>(cl ? (size_t)tb.rows_pad * A : 1);
+  tb.dctxraw = cv.take<float>(cl ? (size_t)B * h->VAL : 1);
+  tb.aT = cv.take<float>(cl ? (size_t)A * h->VAL : 1);
+  tb.ctxrawT = cv.take<float>(cl ? (size_t)h->VAL * tb.rows_pad : 1);
 }
 
 int train_workspace_bytes(comic_handle_t h, int B, int T_run, size_t* bytes) {
@@ -757,10 +832,10 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
   COMIC_REQUIRE(fm && im_embed && inputs_tm && targets_tm && coef_tm && lens && loss_out, COMIC_E_BADARG,
                 "train_fwd_bwd: null argument");   // grads == NULL: forward only (evaluation perplexity)
   COMIC_REQUIRE(B > 0 && T > 0 && T_run > 0 && T_run <= T, COMIC_E_SHAPE, "train_fwd_bwd: bad B=%d T=%d T_run=%d", B, T, T_run);
-  COMIC_REQUIRE(h->cfg.alignment == 0 && h->cfg.prob_fn == 0 && !h->cfg.context_layer && h->cfg.init_method == 0 &&
-                    !h->cfg.legacy,
-                COMIC_E_UNSUPPORTED,
-                "train_fwd_bwd: only add_LN + softmax attention, first_input init, no context layer are built");
+  COMIC_REQUIRE(!h->cfg.legacy, COMIC_E_UNSUPPORTED,
+                "train_fwd_bwd: the legacy image-embedding head (trainable LN_tanh + im_embed, src/model_base.py:80-91) is not built");
+  COMIC_REQUIRE(!h->cfg.context_layer || (h->w.a_layer && (!grads || grads->a_layer)), COMIC_E_BADARG,
+                "train_fwd_bwd: attn_context_layer needs a_layer/kernel and its gradient buffer");
   COMIC_REQUIRE(h->R == 512 || h->R == 256 || h->R == 1024, COMIC_E_UNSUPPORTED, "train_fwd_bwd: rnn_size %d", h->R);
   cudaStream_t st = (cudaStream_t)stream;
   size_t need;
@@ -782,8 +857,26 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
   if ((rc = comic_project_fm(h, fm, B, keys_buf, vals_buf, stream))) return rc;
   const float* values = h->cfg.fm_projection == 1 ? keys_buf : (h->cfg.fm_projection == 2 ? vals_buf : fm);
 
-  // ---- init state: first_input (model_base.py:675-686), tape slot 0 ----
-  {
+  // ---- init state, tape slot 0 ----
+  if (h->cfg.init_method == 1) {
+    // project_hidden (model_base.py:658-667): h0 = im_embed . W, c0 = 0; there is no init LSTM step, so slot 0 of the
+    // x / gate tapes stays zero (its rows then add nothing to the batched kernel gradient)
+    APlain a{};
+    a.nseg = 1;
+    a.seg[0] = ASeg{im_embed, nullptr, E, E, B};
+    Epi e{};
+    e.nroute = 1;
+    e.stop_n = 0x7fffffff;
+    e.r[0] = Route{0, R, tb.h, R, 0};
+    GemmPlan p = plan_gemm(B, R, E, h->num_sms, false);
+    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, h->w.init_weight, R, B, R, E, e, p, st)));
+    COMIC_CHECK_CUDA(cudaMemsetAsync(tb.c, 0, (size_t)B * R * sizeof(float), st));
+    COMIC_CHECK_CUDA(cudaMemsetAsync(tb.xd, 0, (size_t)B * XA * sizeof(float), st));
+    COMIC_CHECK_CUDA(cudaMemsetAsync(tb.gates, 0, (size_t)B * 4 * R * sizeof(float), st));
+    COMIC_CHECK_CUDA(cudaMemsetAsync(tb.ctx, 0, (size_t)B * A * sizeof(float), st));
+    h->launches += 1;
+  } else {
+    // first_input (model_base.py:675-686)
     APlain a{};
     a.nseg = 1;
     a.seg[0] = ASeg{im_embed, nullptr, E, E, B};
@@ -836,6 +929,11 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
     StepBufs sb = tb.sb;
     sb.xdense = tb.xd + (size_t)(t + 1) * B * XA;
     sb.lq = tb.lq + (size_t)t * B * LQ;
+    if (h->cfg.prob_fn == 1) {   // signorm: its backward needs the raw scores -> sliced kernels, scores kept per step
+      io.no_fused = 1;
+      sb.scores = tb.stape + (size_t)t * B * HM;
+    }
+    if (h->cfg.context_layer) sb.ctxraw = tb.ctxraw + (size_t)t * B * VAL;
     if ((rc = run_step(h, io, sb, B, 1, st))) return rc;
     impute_state_kernel<<<B, 128, 0, st>>>(lens, t, B, R, A, io.c_prev, io.h_prev, io.ctx_prev, io.c_new, io.h_new,
                                           io.ctx_new);
@@ -875,23 +973,49 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
   h->launches += 2;
   const float map_coef = (map_loss_scale > 0.f) ? -2.0f * map_loss_scale / ((float)B * (float)T_run * (float)M) : 0.f;
   float* dvals_dst = h->cfg.fm_projection == 1 ? tb.dkeys : tb.dvals;
+  const bool ctx_layer = h->cfg.context_layer != 0, dot = h->cfg.alignment == 1, signorm = h->cfg.prob_fn == 1;
+  if (ctx_layer) {
+    COMIC_CHECK_CUDA(cudaMemsetAsync(tb.gctx_tape, 0, (size_t)tb.rows_pad * A * sizeof(float), st));
+    transpose(h->w.a_layer, VAL, A, A, tb.aT, VAL, st);       // [A, VAL]
+    h->launches++;
+  }
 
   // ---- reverse sweep ----
   for (int t = T_run - 1; t >= 0; --t) {
     float* dlq_t = tb.dlq + (size_t)t * B * LQ;
+    const float* dctx = tb.gCtx;
+    int ld_dctx = A;
+    if (ctx_layer) {
+      // attention = ctxraw . a_layer (common/ops_rnn.py:734-739): the live rows' gradient is kept for the batched
+      // d a_layer = ctxraw^T . g and pulled back to the raw context
+      float* g_t = tb.gctx_tape + (size_t)t * B * A;
+      mask_fin_copy_kernel<<<(unsigned)(((size_t)B * A + 255) / 256), 256, 0, st>>>(tb.gCtx, lens, t, g_t, B, A);
+      h->launches++;
+      if ((rc = train_gemm(h, g_t, A, tb.aT, VAL, tb.dctxraw, VAL, B, VAL, A, tb.part, tb.part_floats, st))) return rc;
+      dctx = tb.dctxraw;
+      ld_dctx = VAL;
+    }
     {
       dim3 g1(B, tb.S);
-      attn_bwd_dalpha_kernel<<<g1, 256, 0, st>>>(values, VAL, tb.gCtx, A, lens, t, tb.apost + (size_t)t * B * HM, dvals_dst,
+      attn_bwd_dalpha_kernel<<<g1, 256, 0, st>>>(values, VAL, dctx, ld_dctx, lens, t, tb.apost + (size_t)t * B * HM, dvals_dst,
                                                 tb.ds, 1, h->H, M, tb.S);
       h->launches++;
     }
     attn_bwd_score_kernel<<<B, 256, (size_t)HM * sizeof(float), st>>>(
-        values, VAL, tb.gCtx, A, lens, t, tb.apost + (size_t)t * B * HM, tb.apre + (size_t)t * B * HM,
+        values, VAL, dctx, ld_dctx, lens, t, tb.apost + (size_t)t * B * HM, tb.apre + (size_t)t * B * HM,
         mk.att ? mk.att + (size_t)t * B * HM : nullptr, att_keep, map_coef, nullptr, tb.ds, tb.dTacc,
-        tb.maprows + (size_t)t * B, h->w.temperature, 1, h->H, M, tb.ds);
+        tb.maprows + (size_t)t * B, dot ? nullptr : h->w.temperature, 1, h->H, M, tb.ds,
+        signorm ? tb.stape + (size_t)t * B * HM : nullptr);
     dim3 g2(B, tb.S);
     const float* lq_t = tb.lq + (size_t)t * B * LQ;
-    if (R == 512)
+    if (dot) {
+      if (R == 512)
+        attn_bwd_dot_kernel<512><<<g2, 128, 0, st>>>(keys_buf, lq_t, LQ, h->Vp, tb.ds, tb.dkeys, tb.dqpart, 1, h->H, M, tb.S, B);
+      else if (R == 256)
+        attn_bwd_dot_kernel<256><<<g2, 128, 0, st>>>(keys_buf, lq_t, LQ, h->Vp, tb.ds, tb.dkeys, tb.dqpart, 1, h->H, M, tb.S, B);
+      else
+        attn_bwd_dot_kernel<1024><<<g2, 128, 0, st>>>(keys_buf, lq_t, LQ, h->Vp, tb.ds, tb.dkeys, tb.dqpart, 1, h->H, M, tb.S, B);
+    } else if (R == 512)
       attn_bwd_ln_kernel<512><<<g2, 128, 0, st>>>(keys_buf, lq_t, LQ, h->Vp, h->w.ln_gamma, h->w.ln_beta, h->w.attention_v,
                                                  h->w.temperature, tb.ds, tb.dkeys, tb.dqpart, tb.cpart, 1, h->H, M, tb.S, B);
     else if (R == 256)
@@ -914,24 +1038,31 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
     h->launches += 2;
   }
   // ---- init step backward ----
-  lstm_bwd_kernel<<<(B * R + 255) / 256, 256, 0, st>>>(tb.gates, nullptr, nullptr, nullptr, 1.f, nullptr, 0, tb.gH, tb.gC,
-                                                      tb.gHp, tb.dG, B, R);
-  if ((rc = train_gemm(h, tb.dG, 4 * R, tb.KT, KX, tb.dxh, KX, B, KX, 4 * R, tb.part, tb.part_floats, st))) return rc;
-  // dx0 = dxh[:, :XA] * init mask / keep
   float* dx0 = tb.dx0;
   COMIC_CHECK_CUDA(cudaMemsetAsync(dx0, 0, (size_t)((B + 3) / 4 * 4) * XA * sizeof(float), st));
-  copy2d_kernel<<<(unsigned)(((size_t)B * XA + 255) / 256), 256, 0, st>>>(tb.dxh, KX, dx0, XA, B, XA);
-  if (mk.init_in) {
-    size_t nx = (size_t)B * XA;
-    mask_scale_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(dx0, mk.init_in, in_keep, nx);
+  const int NI = (h->cfg.init_method == 1) ? R : XA;     // columns of the init weight
+  if (h->cfg.init_method == 1) {
+    // project_hidden: h0 = im_embed . W  ->  dW = im_embed^T . dh0; dx0 [B, R] holds dh0 for comic_train_encoder_grads
+    copy2d_kernel<<<(unsigned)(((size_t)B * R + 255) / 256), 256, 0, st>>>(tb.gH, R, dx0, R, B, R);
+    h->launches += 1;
+  } else {
+    lstm_bwd_kernel<<<(B * R + 255) / 256, 256, 0, st>>>(tb.gates, nullptr, nullptr, nullptr, 1.f, nullptr, 0, tb.gH, tb.gC,
+                                                        tb.gHp, tb.dG, B, R);
+    if ((rc = train_gemm(h, tb.dG, 4 * R, tb.KT, KX, tb.dxh, KX, B, KX, 4 * R, tb.part, tb.part_floats, st))) return rc;
+    // dx0 = dxh[:, :XA] * init mask / keep
+    copy2d_kernel<<<(unsigned)(((size_t)B * XA + 255) / 256), 256, 0, st>>>(tb.dxh, KX, dx0, XA, B, XA);
+    if (mk.init_in) {
+      size_t nx = (size_t)B * XA;
+      mask_scale_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(dx0, mk.init_in, in_keep, nx);
+    }
+    h->launches += 3;
   }
-  h->launches += 3;
-  // dW_I [E, XA] = im_embed^T [E, B] . dx0 [B, XA]
+  // dW_I [E, NI] = im_embed^T [E, B] . dx0 [B, NI]
   {
     int Bp = (B + 3) / 4 * 4;
     COMIC_CHECK_CUDA(cudaMemsetAsync(tb.embT, 0, (size_t)E * Bp * sizeof(float), st));
     transpose(im_embed, B, E, E, tb.embT, Bp, st);
-    if ((rc = train_gemm(h, tb.embT, Bp, dx0, XA, grads->init_weight, XA, E, XA, Bp, tb.part, tb.part_floats, st))) return rc;
+    if ((rc = train_gemm(h, tb.embT, Bp, dx0, NI, grads->init_weight, NI, E, NI, Bp, tb.part, tb.part_floats, st))) return rc;
   }
 
   // ---- batched weight gradients ----
@@ -961,6 +1092,14 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
   colsum_kernel<<<(R + 31) / 32, 256, 0, st>>>(tb.cpart + 2 * R, B * tb.S, R, 3 * R, grads->ln_beta, 0);
   scalar_sum_kernel<<<1, 32, 0, st>>>(tb.dTacc, B, 1.0f, grads->temperature);
   h->launches += 11;
+  if (ctx_layer) {
+    // d a_layer [VAL, A] = ctxraw^T [VAL, T*B] . g [T*B, A]   (rows of finished steps are zero in g)
+    COMIC_CHECK_CUDA(cudaMemsetAsync(tb.ctxrawT, 0, (size_t)VAL * rows_pad * sizeof(float), st));
+    transpose(tb.ctxraw, rows_t, VAL, VAL, tb.ctxrawT, rows_pad, st);
+    if ((rc = train_gemm(h, tb.ctxrawT, rows_pad, tb.gctx_tape, A, grads->a_layer, A, VAL, A, rows_pad, tb.part,
+                         tb.part_floats, st))) return rc;
+    h->launches++;
+  }
   // dW_k = F^T . dKeys  (tied: dKeys also holds the value-path gradient)
   {
     int bm = B * M, bmp = (bm + 3) / 4 * 4;
@@ -996,8 +1135,7 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
 extern "C" int comic_train_encoder_grads(comic_handle_t h, int B, int T_run, float* dfm_out, float* dim_embed_out,
                                          void* ws, size_t ws_bytes, void* stream) {
   COMIC_REQUIRE(h && h->bound && dfm_out && dim_embed_out && ws, COMIC_E_BADARG, "train_encoder_grads: bad argument");
-  COMIC_REQUIRE(h->cfg.init_method == 0 && !h->cfg.legacy, COMIC_E_UNSUPPORTED,
-                "train_encoder_grads: only the first_input rnn init is built");
+  COMIC_REQUIRE(!h->cfg.legacy, COMIC_E_UNSUPPORTED, "train_encoder_grads: the legacy image-embedding head is not built");
   cudaStream_t st = (cudaStream_t)stream;
   size_t need;
   train_workspace_bytes(h, B, T_run, &need);
@@ -1021,9 +1159,10 @@ extern "C" int comic_train_encoder_grads(comic_handle_t h, int B, int T_run, flo
     add_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dfm_out, tb.dvals, n);   // values = fm itself
     h->launches++;
   }
-  // dim_embed = dx0 . W_I^T
-  transpose(h->w.init_weight, E, XA, XA, tb.encT, E, st);
-  if ((rc = train_gemm(h, tb.dx0, XA, tb.encT, E, dim_embed_out, E, B, E, XA, tb.part, tb.part_floats, st))) return rc;
+  // dim_embed = dx0 . W_I^T   (project_hidden: dx0 holds dh0 [B, R] and W_I is [E, R])
+  const int NI = (h->cfg.init_method == 1) ? R : XA;
+  transpose(h->w.init_weight, E, NI, NI, tb.encT, E, st);
+  if ((rc = train_gemm(h, tb.dx0, NI, tb.encT, E, dim_embed_out, E, B, E, NI, tb.part, tb.part_floats, st))) return rc;
   h->launches += 2;
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;

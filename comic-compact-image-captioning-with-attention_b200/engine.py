@@ -49,7 +49,7 @@ class ComicTrainMasks(C.Structure):
 
 
 GRAD_FIELDS = ('lstm_kernel', 'lstm_bias', 'init_weight', 'memory_kernel', 'value_kernel', 'query_kernel',
-               'attention_v', 'ln_gamma', 'ln_beta', 'temperature', 'out_kernel', 'out_bias', 'embedding_map')
+               'attention_v', 'ln_gamma', 'ln_beta', 'temperature', 'out_kernel', 'out_bias', 'embedding_map', 'a_layer')
 
 
 class ComicDecoderGrads(C.Structure):
@@ -533,7 +533,8 @@ class Engine(object):
              att + 'query_layer/kernel': 'query_kernel', att + 'attention_v': 'attention_v',
              att + 'LN_tanh/gamma': 'ln_gamma', att + 'LN_tanh/beta': 'ln_beta',
              D + 'softmax_temperature': 'temperature', D + 'output_projection/kernel': 'out_kernel',
-             D + 'output_projection/bias': 'out_bias', D + 'embedding_map': 'embedding_map'}
+             D + 'output_projection/bias': 'out_bias', D + 'embedding_map': 'embedding_map',
+             D + 'a_layer/kernel': 'a_layer'}
         return m
 
     def dropout_masks(self, shape, keep, seed, stream_id):

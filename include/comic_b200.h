@@ -299,6 +299,7 @@ typedef struct {
   float* lstm_kernel; float* lstm_bias; float* init_weight; float* memory_kernel; float* value_kernel;
   float* query_kernel; float* attention_v; float* ln_gamma; float* ln_beta; float* temperature;
   float* out_kernel; float* out_bias; float* embedding_map;
+  float* a_layer;                /* [VAL, R] (attn_context_layer, common/ops_rnn.py:734-739) or NULL */
 } comic_decoder_grads_t;
 
 int comic_train_workspace_bytes(comic_handle_t h, int B, int T_run, size_t* bytes);

@@ -36,6 +36,17 @@ CASES = {
     'word_none_h1_xe': (lambda: word_config(n_words=300, train_mode='decoder'), True, False),
     'independent_h4': (lambda: comic_config(train_mode='decoder', cnn_fm_projection='independent', attn_num_heads=4),
                        True, False),
+    # the cell variants of src/model_base.py:599-603, 622-667 and common/ops_rnn.py:603-632, 734-739
+    'dot': (lambda: comic_config(train_mode='decoder', attn_alignment_method='dot'), True, False),
+    'sigmoid': (lambda: comic_config(train_mode='decoder', attn_probability_fn='sigmoid'), True, False),
+    'context_layer': (lambda: comic_config(train_mode='decoder', attn_context_layer=True), True, False),
+    'project_hidden': (lambda: comic_config(train_mode='decoder', rnn_init_method='project_hidden'), True, False),
+    'dot_sigmoid_ctx_ph_indep_h4': (lambda: comic_config(train_mode='scst', attn_alignment_method='dot',
+                                                         attn_probability_fn='sigmoid', attn_context_layer=True,
+                                                         rnn_init_method='project_hidden',
+                                                         cnn_fm_projection='independent', attn_num_heads=4), True, True),
+    'word_none_ctx_sigmoid': (lambda: word_config(n_words=300, train_mode='decoder', attn_context_layer=True,
+                                                  attn_probability_fn='sigmoid'), True, False),
 }
 
 

@@ -80,7 +80,7 @@ def training_loss(P, c, im_embed, fm, captions, masks=None, keeps=(1.0, 1.0, 1.0
     else:
         hs = im_t @ P[DEC + 'rnn_initial_state/weight']
         cs = torch.zeros_like(hs)
-    ctx = torch.zeros((B, vals.shape[-1]), dtype=dt)
+    ctx = torch.zeros((B, R if c.attn_context_layer else vals.shape[-1]), dtype=dt)
 
     def embed(ids):
         ids = np.asarray(ids)
@@ -100,12 +100,16 @@ def training_loss(P, c, im_embed, fm, captions, masks=None, keeps=(1.0, 1.0, 1.0
         hout = _drop(hn, out_keep, None if 'out' not in m else t(m['out'][step]))
         logits = hout @ P[DEC + 'output_projection/kernel'] + P[DEC + 'output_projection/bias']
         q = hout @ P[ATT + 'query_layer/kernel']
-        u = keys + q[:, None, :]
-        mu = u.mean(-1, keepdim=True)
-        var = ((u - mu) ** 2).mean(-1, keepdim=True)
-        y = (u - mu) / torch.sqrt(var + 1e-12) * P[ATT + 'LN_tanh/gamma'] + P[ATT + 'LN_tanh/beta']
-        z = torch.tanh(y) * P[ATT + 'attention_v']
-        s = z.reshape(B, M, H, R // H).sum(-1).permute(0, 2, 1) / P[DEC + 'softmax_temperature']
+        if c.attn_alignment_method == 'add_LN':
+            u = keys + q[:, None, :]
+            mu = u.mean(-1, keepdim=True)
+            var = ((u - mu) ** 2).mean(-1, keepdim=True)
+            y = (u - mu) / torch.sqrt(var + 1e-12) * P[ATT + 'LN_tanh/gamma'] + P[ATT + 'LN_tanh/beta']
+            z = torch.tanh(y) * P[ATT + 'attention_v']
+            s = z.reshape(B, M, H, R // H).sum(-1).permute(0, 2, 1) / P[DEC + 'softmax_temperature']
+        else:                                                                 # MultiHeadDot, ops_rnn.py:603-632
+            z = keys * q[:, None, :]
+            s = z.reshape(B, M, H, R // H).sum(-1).permute(0, 2, 1) / float(np.sqrt(R / H))
         if c.attn_probability_fn == 'softmax':
             al = torch.softmax(s, -1)
         else:
@@ -113,6 +117,8 @@ def training_loss(P, c, im_embed, fm, captions, masks=None, keeps=(1.0, 1.0, 1.0
             al = sg / sg.sum(-1, keepdim=True)
         al = _drop(al, att_keep, None if 'att' not in m else t(m['att'][step]))
         cnew = torch.einsum('nhm,nmhd->nhd', al, vals.reshape(B, M, H, dv)).reshape(B, -1)
+        if c.attn_context_layer:                                              # ops_rnn.py:734-739
+            cnew = cnew @ P[DEC + 'a_layer/kernel']
         hist.append(al)
         outs.append(torch.where(fin, torch.zeros_like(logits), logits))       # impute_finished
         cs = torch.where(fin, cs, cn)
