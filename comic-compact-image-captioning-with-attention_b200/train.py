@@ -83,8 +83,6 @@ class Trainer(object):
         if self.finetune_cnn and not with_cnn:
             raise ValueError('train_mode=cnn_finetune needs the CNN weights')
         # options the reference accepts but this path does not build: refuse instead of silently training differently
-        if getattr(c, 'rnn_recurr_dropout', False):
-            raise NotImplementedError('rnn_recurr_dropout (variational recurrent dropout) is not built')
         if float(getattr(c, 'clip_gradient_norm', 0) or 0) != 0:
             raise NotImplementedError('clip_gradient_norm != 0 is not built (the reference default is 0)')
         if getattr(c, 'optimiser', 'adam') != 'adam':
@@ -183,9 +181,19 @@ class Trainer(object):
         c, d, eng = self.c, self.engine.dims, self.engine
         keeps = (1.0 - c.dropout_rnn_in, 1.0 - c.dropout_rnn_out, c.attn_keep_prob)
         XA = d.W + d.A
-        masks = dict(init_in=eng.dropout_masks((B, XA), keeps[0], seed, 0),
-                     inp=eng.dropout_masks((T_run, B, XA), keeps[0], seed, 1),
-                     out=eng.dropout_masks((T_run, B, d.R), keeps[1], seed, 2))
+        if getattr(c, 'rnn_recurr_dropout', False):
+            # DropoutWrapper(variational_recurrent=True) (src/model_base.py:641-647; TF r1.9 rnn_cell_impl.py builds its
+            # noise with a leading dimension of 1: "the same dropout mask for all batch elements"): ONE input mask [1, W+A]
+            # and ONE output mask [1, R] per step of the optimiser, shared by every row and every time step -- and by the
+            # rnn-init call, which runs through the same wrapped cell.  state_keep_prob stays 1.
+            mi = eng.dropout_masks((1, XA), keeps[0], seed, 1)
+            mo = eng.dropout_masks((1, d.R), keeps[1], seed, 2)
+            masks = dict(init_in=mi.expand(B, XA).contiguous(), inp=mi.expand(T_run, B, XA).contiguous(),
+                         out=mo.expand(T_run, B, d.R).contiguous())
+        else:
+            masks = dict(init_in=eng.dropout_masks((B, XA), keeps[0], seed, 0),
+                         inp=eng.dropout_masks((T_run, B, XA), keeps[0], seed, 1),
+                         out=eng.dropout_masks((T_run, B, d.R), keeps[1], seed, 2))
         if keeps[2] < 1.0:
             masks['att'] = eng.dropout_masks((T_run, B, d.H * d.M), keeps[2], seed, 3)
         return masks, keeps

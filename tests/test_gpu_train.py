@@ -85,6 +85,30 @@ def test_gradients_match_autograd(torch_mod, name):
     assert not bad, (bad, worst)
 
 
+@pytest.mark.parametrize('name', ['comic256_xe_dropout', 'project_hidden', 'dot_sigmoid_ctx_ph_indep_h4',
+                                  'word_none_ctx_sigmoid'])
+def test_encoder_output_gradients_match_autograd(torch_mod, name):
+    """comic_train_encoder_grads (what cnn_finetune feeds the CNN backward): d loss / d fm and d loss / d im_embed."""
+    import torch_ref as TR
+    from comic_b200.train import Trainer
+    mk, dropout, scst = CASES[name]
+    c = mk()
+    W, im, fm, caps, masks, keeps = _train_case(c, B=4, L=8, seed=3, dropout=dropout)
+    rewards = np.array([0.4, -0.3, 1.2, 0.05], np.float32) if scst else None
+    P = TR.to_params(W)
+    tot, _, _, _, aux = TR.training_loss(P, c, im, fm, caps, masks, keeps, rewards, fm_requires_grad=True)
+    tot.backward()
+    tr = Trainer(c, W, with_cnn=False)
+    eng = tr.engine
+    eng.set_precision('f32')
+    dmasks = dict(init_in=eng.to_dev(masks['init_in']), inp=eng.to_dev(masks['inp']), out=eng.to_dev(masks['out']),
+                  att=eng.to_dev(masks['att'].reshape(masks['att'].shape[0], masks['att'].shape[1], -1)))
+    out = tr.forward_backward(eng.to_dev(fm), eng.to_dev(im), caps, rewards, dmasks, keeps)
+    dfm, demb = eng.train_encoder_grads(4, out['T_run'])
+    assert rel_err(dfm.cpu().numpy(), aux['fm'].grad.numpy()) < 1e-3
+    assert rel_err(demb.cpu().numpy(), aux['im'].grad.numpy()) < 1e-3
+
+
 def test_adam_and_l2_match_oracle(torch_mod):
     import comic_oracle as O
     from comic_b200.engine import Engine
@@ -121,6 +145,24 @@ def test_dropout_masks_are_seeded_bernoulli(torch_mod):
     assert (a != c2).mean() > 0.3
     assert abs(a.mean() - 0.65) < 5e-3
     assert abs(np.corrcoef(a.reshape(-1)[:-1], a.reshape(-1)[1:])[0, 1]) < 0.01
+
+
+def test_recurrent_dropout_masks_are_shared_over_rows_and_steps(torch_mod):
+    """rnn_recurr_dropout=True: DropoutWrapper(variational_recurrent=True) draws one input and one output mask per
+    optimiser step (leading dimension 1 in TF r1.9), used by every row, every time step and the rnn-init call."""
+    from comic_b200.train import Trainer
+    c = comic_config(train_mode='decoder', rnn_recurr_dropout=True)
+    W, im, fm, caps, _, _ = _train_case(c, B=3, L=7, seed=2, dropout=False)
+    tr = Trainer(c, W, with_cnn=False)
+    masks, keeps = tr.make_masks(3, 5, seed=11)
+    inp, out, init = masks['inp'].cpu().numpy(), masks['out'].cpu().numpy(), masks['init_in'].cpu().numpy()
+    assert inp.shape == (5, 3, 768) and out.shape == (5, 3, 512) and init.shape == (3, 768)
+    assert (inp == inp[0, 0]).all() and (out == out[0, 0]).all() and (init == inp[0, 0]).all()
+    assert 0.5 < inp[0, 0].mean() < 0.8 and set(np.unique(inp)) <= {0.0, 1.0}
+    m2, _ = tr.make_masks(3, 5, seed=12)
+    assert (m2['inp'].cpu().numpy()[0, 0] != inp[0, 0]).any()
+    out1 = tr.forward_backward(tr.engine.to_dev(fm), tr.engine.to_dev(im), caps, None, masks, keeps)
+    assert np.isfinite(float(out1['loss'][0]))
 
 
 def test_training_steps_reduce_loss(torch_mod):
