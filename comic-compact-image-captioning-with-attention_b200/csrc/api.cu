@@ -153,6 +153,7 @@ extern "C" int comic_set_option(comic_handle_t h, int option, int value) {
     case COMIC_OPT_ENC_PLANES: h->enc_planes = value; return COMIC_OK;
     case COMIC_OPT_STEM_S2D: h->stem_s2d = value; return COMIC_OK;
     case COMIC_OPT_TC_MIN_ROWS: h->tc_min_rows = value; return COMIC_OK;
+    case COMIC_OPT_TC_SPLITK: h->tc_splitk = value; return COMIC_OK;
     case COMIC_OPT_ATTN2: h->attn2 = value; return COMIC_OK;
     case COMIC_OPT_FUSE_LSTM: h->fuse_lstm = value; return COMIC_OK;
     case COMIC_OPT_TMA_A: h->tma_a = value; return COMIC_OK;

@@ -93,6 +93,7 @@ struct comic_handle_s {
   int last_trace_steps = 0;
   int persist_watchdog_ms = 2000;   // grid-barrier watchdog of the persistent loop (0 = disabled)
   int persist_max_rows = 32;   // whole decode loop as one cooperative kernel up to this many rows (0 = off)
+  int tc_splitk = 3;           // bit 0: gate GEMM, bit 1: [logits | query] GEMM -- split-K for tensor-path decoder GEMMs of one M tile (tc_ksplit below); COMIC_OPT_TC_SPLITK
   int tc_min_rows = 64;        // GEMMs / convs with at least this many rows take the tensor path (precision >= 1); half-empty
                                // M tiles still beat the FFMA kernel (batch 25-32 beam-3: gate GEMM 37 -> 29 us, r02p)
   int stem_s2d = 2;            // tensor path stem conv: 2 = space-to-depth planes, im2col tile built from a shared-memory
@@ -154,6 +155,22 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, int ldw, int cin_src, int cin_dst,
                    tc::TcWeight& out, cudaStream_t st, bool dry, int gate_R = 0);
 inline bool use_tc(comic_handle_t h, const tc::TcWeight& w, int M) { return h->precision >= 1 && w.ready && M >= h->tc_min_rows; }
+// Split-K factor of a tensor-path GEMM with one M tile (decode steps at 33..128 rows: batch 25 x beam 3 = 75 rows is the
+// reference's default inference shape, src/infer.py:72).  One 128-row tile per 128 columns leaves 16 of 148 SMs walking
+// 20 K blocks at ~1.3 us each; cutting K puts (column tiles x ranges) CTAs on the chip with >= 2 K blocks each.
+inline int tc_ksplit(comic_handle_t h, int M, int N, int K, int which) {   // which: 1 = gate GEMM, 2 = [logits | query]
+  if (!(h->tc_splitk & which) || M > 128) return 1;
+  const int nk = (K + 63) / 64, n_tiles = (N + 127) / 128;
+  int ks = h->num_sms / n_tiles;
+  if (ks > nk / 2) ks = nk / 2;
+  if (ks > 8) ks = 8;
+  return ks < 1 ? 1 : ks;
+}
+// Decode-step GEMMs: with the K split the tensor path also wins from 33 rows on (batch 16 x beam 3: gate GEMM 22.9 -> 14.9 us,
+// profiles/r12e_*); 32 rows and fewer belong to the persistent loop / the FFMA kernel.
+inline bool use_tc_step(comic_handle_t h, const tc::TcWeight& w, int M, int N, int K, int which) {
+  return use_tc(h, w, M) || (h->precision >= 1 && w.ready && M > 32 && tc_ksplit(h, M, N, K, which) > 1);
+}
 
 // encoder.cu
 int encoder_workspace_bytes(comic_handle_t h, int B, size_t* bytes);

@@ -954,25 +954,27 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
     a.seg[1] = ASeg{io.ctx_prev, io.src, A, A, io.src_limit};
     a.seg[2] = ASeg{io.h_prev, io.src, R, R, io.src_limit};
   }
-  const bool tc1 = use_tc(h, h->pk.tc_lstm, N);
+  const bool tc1 = use_tc_step(h, h->pk.tc_lstm, N, 4 * R, h->KX, 1);
   GemmPlan p1 = plan_gemm(N, 4 * R, h->KX, h->num_sms, true);
-  int nz1 = tc1 ? 1 : gemm_num_partials(h->KX, p1);
+  const int ks1 = tc1 ? tc_ksplit(h, N, 4 * R, h->KX, 1) : 1;
+  int nz1 = tc1 ? ks1 : gemm_num_partials(h->KX, p1);
   Epi e1{};
   e1.nroute = 1;
   e1.r[0] = Route{0, 4 * R, sb.gates, 4 * R, 0};
   e1.split_stride = (long long)N * 4 * R;
+  e1.ksplit = ks1;
   e1.stop = io.fin_count ? io.fin_count + (io.t > 0 ? io.t - 1 : 0) : nullptr;
   e1.stop_n = (io.fin_count && io.t > 0) ? io.n_rows : 0x7fffffff;
   e1.pdl = 1;
   // tensor path without dropout / tape: the LSTM point-wise update runs in the gate GEMM's epilogue over the
   // gate-interleaved panel (same arithmetic, in the same order, as lstm_pointwise4_kernel<true>: bit-identical c / h)
-  const bool fused_lstm = tc1 && h->fuse_lstm && h->pk.tc_lstm_il.ready && !io.h_drop && !io.out_mask && !io.gates_save;
+  const bool fused_lstm = tc1 && ks1 == 1 && h->fuse_lstm && h->pk.tc_lstm_il.ready && !io.h_drop && !io.out_mask && !io.gates_save;
   // A operands as bf16 planes through TMA (inference decode on the tensor path: no dropout, no tape)
   const bool tma_ok = sb.tma_a && h->tma_a && h->precision >= 1 && !io.in_mask && !io.force_dense && !io.h_drop &&
                       !io.out_mask && !io.gates_save;
-  const bool tma_gates = tma_ok && (h->tma_a & 2) && tc1 && !fused_lstm;
+  const bool tma_gates = tma_ok && (h->tma_a & 2) && tc1 && ks1 == 1 && !fused_lstm;
   // h' planes exist when the 4-units-per-thread LSTM kernel below runs
-  const bool tma_lq = tma_ok && (h->tma_a & 1) && !fused_lstm && (tc1 ? 1 : gemm_num_partials(h->KX, p1)) == 1 && R % 4 == 0 && N >= 128 &&
+  const bool tma_lq = tma_ok && (h->tma_a & 1) && !fused_lstm && nz1 == 1 && R % 4 == 0 && N >= 128 &&
                       use_tc(h, h->pk.tc_outq, N);
   if (fused_lstm) {
     e1.bias = h->pk.lstm_bias_il;
@@ -1015,9 +1017,10 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
   APlain a2{};
   a2.nseg = 1;
   a2.seg[0] = ASeg{hq, nullptr, R, R, N};
-  const bool tc2 = use_tc(h, h->pk.tc_outq, N);
+  const bool tc2 = use_tc_step(h, h->pk.tc_outq, N, h->LQ, R, 2);
   GemmPlan p2 = plan_gemm(N, h->LQ, R, h->num_sms, true);
-  int nz2 = tc2 ? 1 : gemm_num_partials(R, p2);
+  const int ks2 = (tc2 && !tma_lq) ? tc_ksplit(h, N, h->LQ, R, 2) : 1;
+  int nz2 = tc2 ? ks2 : gemm_num_partials(R, p2);
   Epi e2{};
   e2.nroute = 1;
   e2.stop = e1.stop;
@@ -1033,8 +1036,10 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
   } else {
     e2.r[0] = Route{0, h->LQ, sb.lq_part, h->LQ, 0};
     e2.split_stride = (long long)N * h->LQ;
+    e2.ksplit = tc2 ? ks2 : 0;
     Prof pf(h, T_LQ, st, 2);
-    COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->pk.outq, h->LQ, N, h->LQ, R, e2, p2, st)));
+    if (tc2) COMIC_CHECK_CUDA((tc::launch_gemm_tc<0>(a2, h->pk.tc_outq, N, h->LQ, e2, h->num_sms, st)));
+    else COMIC_CHECK_CUDA((launch_gemm<0, 4>(a2, h->pk.outq, h->LQ, N, h->LQ, R, e2, p2, st)));
     size_t tot = (size_t)N * h->LQ;
     splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(sb.lq_part, nz2, (size_t)N * h->LQ,
                                                                        h->pk.outq_bias, sb.lq, N, h->LQ,
@@ -1077,9 +1082,11 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
 void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_masks) {
   GemmPlan p1 = plan_gemm(N, 4 * h->R, h->KX, h->num_sms, true);
   int nz1 = gemm_num_partials(h->KX, p1);
+  if (nz1 < 8 && N <= 128) nz1 = 8;                 // tensor-path split-K partials (tc_ksplit <= 8)
   GemmPlan p2 = plan_gemm(N, h->LQ, h->R, h->num_sms, true);
   int nz2 = gemm_num_partials(h->R, p2);
   sb.gates = cv.take<float>((size_t)nz1 * N * 4 * h->R);
+  if (nz2 < 8 && N <= 128) nz2 = 8;
   sb.lq_part = cv.take<float>(nz2 > 1 ? (size_t)nz2 * N * h->LQ : 1);
   sb.lq = cv.take<float>((size_t)N * h->LQ);
   sb.scores = cv.take<float>((size_t)N * h->H * h->M);

@@ -81,6 +81,8 @@ struct Epi {
   int nroute;
   Route r[3];
   long long split_stride;  // elements between split-K partials of route 0
+  int ksplit;              // tensor path (gemm_tc.cuh, AMODE 0, single-CTA kernel): K blocks cut into this many ranges, partial
+                           // z of tile (m, n) goes to route dst + z * split_stride (0 / 1 = off); no bias / scale then
   const int* stop;         // optional device flag: skip the launch when *stop >= stop_n
   int stop_n;              // (decode loops: every beam finished in the previous step)
   int pdl;                 // host side only: launch as a programmatic dependent (tensor path, launch_one)

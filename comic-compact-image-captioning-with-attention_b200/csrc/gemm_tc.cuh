@@ -291,7 +291,12 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
   const int nk = (K + BK - 1) / BK;
   const int n_tiles = (N + BN - 1) / BN;
   const int m_tiles = (M + TM - 1) / TM;          // AMODE 3: M = nimg * 112 * 112 = nimg * 98 tiles of 8 x 16 outputs
-  const int total_tiles = m_tiles * n_tiles;
+  // split-K (launches of one or two M tiles, e.g. the decoder GEMMs at 33..128 rows, where a tile's K loop is a chain of
+  // ~1.3 us operand-staging latencies): work item = (K range z, tile mn); the partial sums go to dst + z * split_stride
+  // and are added in a fixed order by the consumer
+  const int ksplit = (AMODE == 0 && !PAIR && MC == 1 && NKRES == 0 && epi.ksplit > 1) ? epi.ksplit : 1;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int total_tiles = mn_tiles * ksplit;
   const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x / MC;
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x / MC;
 
@@ -352,8 +357,9 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
     const int srow = lane >> 2, scol = (lane & 3) * 4;       // store phase: row within a group of 8, first column
     int iter = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
-      const int m0 = (tile / n_tiles) * TM + (int)rank * BM;
-      const int n0 = (tile % n_tiles) * BN;
+      const int kz = tile / mn_tiles, mn = tile - kz * mn_tiles;
+      const int m0 = (mn / n_tiles) * TM + (int)rank * BM;
+      const int n0 = (mn % n_tiles) * BN;
       const int acc = iter & 1;
       const int n_umma = min(BN, ((N - n0) + 15) & ~15);
       mbar_wait(&tmem_full[acc], (uint32_t)((iter >> 1) & 1));
@@ -421,7 +427,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
           uint16_t* const hdst = epi.r[rt].hi;
           uint16_t* const ldst = epi.r[rt].lo;
           const long long ld = epi.r[rt].ld;
-          const long long cofs = (long long)epi.r[rt].coff - epi.r[rt].n0 + n;
+          const long long cofs = (long long)epi.r[rt].coff - epi.r[rt].n0 + n + (long long)kz * epi.split_stride;
           const float4 sc = epi.scale ? ldg4(epi.scale + n) : make_float4(1.f, 1.f, 1.f, 1.f);
           const float4 bs = epi.bias ? ldg4(epi.bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
           if (epi.lstm_h != nullptr) {
@@ -482,7 +488,9 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
       uint32_t it = 0;
       if constexpr (NKRES > 0) mbar_wait(&full_b[0], 0);      // resident weight panel landed
       for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++iter) {
-        const int n0 = (tile % n_tiles) * BN;
+        const int kz = tile / mn_tiles, mn = tile - kz * mn_tiles;
+        const int kt0 = (int)(((long long)kz * nk) / ksplit), kt1 = (int)(((long long)(kz + 1) * nk) / ksplit);
+        const int n0 = (mn % n_tiles) * BN;
         const int acc = iter & 1;
         const int n_umma = min(BN, ((N - n0) + 15) & ~15);
         const uint32_t idesc = make_idesc_bf16(MMA_M, n_umma);
@@ -490,7 +498,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
         if constexpr (PAIR) mbar_wait_cluster(&tmem_empty[acc], (uint32_t)(((iter >> 1) & 1) ^ 1));
         else mbar_wait(&tmem_empty[acc], (uint32_t)(((iter >> 1) & 1) ^ 1));
         tc_fence_after();
-        for (int kt = 0; kt < nk; ++kt, ++it) {
+        for (int kt = kt0; kt < kt1; ++kt, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           if constexpr (PAIR) {
@@ -510,7 +518,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
 #pragma unroll
           for (int k16 = 0; k16 < BK / 16; ++k16) {
             const uint64_t adv = (uint64_t)((k16 * 16 * 2) >> 4);    // 32 bytes per K=16 step inside the swizzle row
-            const uint32_t first = (kt > 0 || k16 > 0) ? 1u : 0u;
+            const uint32_t first = (kt > kt0 || k16 > 0) ? 1u : 0u;
             if constexpr (PAIR) {
               umma_bf16_pair(d_tmem, dah + adv, dbh + adv, idesc, first);
               umma_bf16_pair(d_tmem, dal + adv, dbh + adv, idesc, 1u);
@@ -547,10 +555,12 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int n0 = (tile % n_tiles) * BN;
+        const int kz = tile / mn_tiles, mn = tile - kz * mn_tiles;
+        const int kt0 = (int)(((long long)kz * nk) / ksplit), kt1 = (int)(((long long)(kz + 1) * nk) / ksplit);
+        const int n0 = (mn % n_tiles) * BN;
         const int n_umma = min(BN, ((N - n0) + 15) & ~15);
         const int nrow = PAIR ? n0 + (int)rank * (n_umma >> 1) : n0 + (int)rank * (BN / MC);   // first row of B^T this CTA loads
-        for (int kt = 0; kt < nk; ++kt, ++it) {
+        for (int kt = kt0; kt < kt1; ++kt, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -568,7 +578,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
             tma_load_2d_mc(b_lo + slice, tm_lo, &full_b[s], kt * BK, nrow, kMcMask);
           } else if constexpr (AMODE == 4) {
             // both operands by TMA: 128 rows of the (hi, lo) A planes + the weight tile, one transaction
-            const int m0 = (tile / n_tiles) * TM;
+            const int m0 = (mn / n_tiles) * TM;
             const uint32_t a_hi = smem + s * L::STAGE_BYTES;
             mbar_arrive_expect_tx(&full_b[s], 2 * L::B_TILE_BYTES + 2 * A_TILE_BYTES);
             tma_load_2d(a_hi, &a.hi, &full_b[s], kt * BK, m0);
@@ -734,7 +744,9 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
     uint8_t* rowtab = rowtab0 + grp * L::ROWTAB_BYTES;
     uint32_t it = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-      const int m0 = (tile / n_tiles) * TM + (int)rank * BM;
+      const int kz = tile / mn_tiles, mn = tile - kz * mn_tiles;
+      const int kt0 = (int)(((long long)kz * nk) / ksplit), kt1 = (int)(((long long)(kz + 1) * nk) / ksplit);
+      const int m0 = (mn / n_tiles) * TM + (int)rank * BM;
       // per-tile row table (this group's private copy)
       named_bar_sync(1 + grp, 128);
       {
@@ -773,7 +785,7 @@ __device__ __forceinline__ void gemm_bf16x3_body(const typename AParam<AMODE>::t
         }
       }
       named_bar_sync(1 + grp, 128);
-      for (int kt = 0; kt < nk; ++kt, ++it) {
+      for (int kt = kt0; kt < kt1; ++kt, ++it) {
         if ((int)(it % kLoaderGroups) != grp) continue;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -979,7 +991,7 @@ inline cudaError_t launch_one(const typename AParam<AMODE>::type& a, const TcWei
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL); });
     if (e != cudaSuccess) return e;
   }
-  int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM) * ((AMODE == 0 && epi.ksplit > 1) ? epi.ksplit : 1);
   int grid = tiles < num_sms ? tiles : num_sms;
   if (epi.pdl) return launch_pdl(gemm_bf16x3_kernel<BN, STAGES, AMODE>, dim3(grid), dim3(kThreads), L::TOTAL, st, a,
                                  w.tm_hi[bn_idx], w.tm_lo[bn_idx], M, N, w.K, epi);
@@ -1149,6 +1161,9 @@ inline cudaError_t launch_gemm_tc(const typename AParam<AMODE>::type& a, const T
     }
   }
   int bn = pick_bn(M, N, num_sms, (AMODE == 0 || AMODE == 4) && small_tiles());
+  if constexpr (AMODE == 0) {
+    if (epi.ksplit > 1) return launch_one<128, 3, 0>(a, w, 1, M, N, epi, num_sms, st);    // tc_ksplit() assumed 128-wide tiles
+  }
   if constexpr (AMODE == 0 || AMODE == 4) {
     if (bn == 176) return launch_one<176, 2, AMODE>(a, w, 3, M, N, epi, num_sms, st);
   }

@@ -160,6 +160,9 @@ int comic_set_precision(comic_handle_t h, int mode);
 #define COMIC_OPT_PERSISTENT_WATCHDOG_MS 18   /* how long a CTA of the persistent decode loop may spin at a grid barrier before the
                                                launch is declared dead (T_out = -1); default 2000, 0 = never (time-sliced GPUs,
                                                debuggers) */
+#define COMIC_OPT_TC_SPLITK 19                /* bit 0: gate GEMM, bit 1: [logits | query] GEMM (default 3): tensor-path decoder GEMMs with at most 128 rows (batch 25 x beam 3 = 75,
+                                               the reference's default inference shape) cut their K loop into up to 8 ranges,
+                                               one CTA each; the partial sums are added in a fixed order by the consumer */
 #define COMIC_OPT_GEMM_MC 14                 /* tensor-path GEMMs / convs with >= 2 x value M tiles: clusters of `value` CTAs (2 or 4;
                                                0 = off, default) work on consecutive M tiles of one N tile and multicast the
                                                weight tile (each loads 1 / value of it): the panel crosses L2 -> SM once per

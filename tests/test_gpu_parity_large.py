@@ -83,6 +83,32 @@ def test_comic256_beam3_64_images_60_steps(torch_mod):
     assert n_same >= 60
 
 
+def test_comic256_beam3_25_images_the_reference_default_batch(torch_mod):
+    """batch_size_infer = 25 x beam 3 = 75 rows (src/infer.py:72): one M tile of the tensor path, K loop split over
+    CTAs (COMIC_OPT_TC_SPLITK), streaming attention."""
+    n_same, near = _run_and_audit(comic_config(), 25, 3, 40, seed=23)
+    assert n_same >= 22
+
+
+def test_tensor_split_k_equals_unsplit_up_to_summation_order(torch_mod):
+    """The same 75-row decode with and without the K split: identical tokens, scores equal to fp32 summation order."""
+    c = comic_config()
+    W = make_weights(c, include_cnn=False)
+    im, fm = fake_features(25, seed=31)
+    outs = []
+    for sk in (1, 0):
+        eng = _engine(c, W)
+        eng.set_option('tc_splitk', sk)
+        keys, values = eng.project_fm(eng.to_dev(fm))
+        c0, h0 = eng.rnn_init(eng.to_dev(im))
+        outs.append(eng.decode_beam(keys, values, c0, h0, 3, 0.0, 12))
+    a, b = outs
+    np.testing.assert_array_equal(a['step_ids'].cpu().numpy(), b['step_ids'].cpu().numpy())
+    np.testing.assert_array_equal(a['parent_ids'].cpu().numpy(), b['parent_ids'].cpu().numpy())
+    assert rel_err(a['scores'].cpu().numpy(), b['scores'].cpu().numpy()) < 2e-5
+    assert rel_err(a['attn'].cpu().numpy(), b['attn'].cpu().numpy()) < 2e-5
+
+
 def test_word_model_v10000_beam3_48_images_30_steps(torch_mod):
     """BASELINE.json config 2 as written: word vocabulary 10,000, no feature-map projection, one head."""
     c = word_config(n_words=10000)
