@@ -671,6 +671,43 @@ __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__
   theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// tf.train.MomentumOptimizer(use_nesterov=False) dense update (src/model_base.py:868-880): accum = momentum * accum + g;
+// theta -= lr * accum.
+__global__ void momentum_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ accum, size_t n,
+                                float lr, float momentum, float grad_scale) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = momentum * accum[i] + g[i] * grad_scale;
+  accum[i] = a;
+  theta[i] -= lr * a;
+}
+
+// slim.learning.clip_gradient_norms (create_train_op(clip_gradient_norm=c), src/model_base.py:394-401): every variable's
+// gradient is clipped by ITS OWN l2 norm, g <- g * c / max(|g|, c).  One CTA per variable, fixed-order block reduction.
+__global__ void __launch_bounds__(1024)
+clip_by_norm_kernel(float* __restrict__ grads, const long long* __restrict__ offsets, const long long* __restrict__ sizes,
+                    float max_norm) {
+  __shared__ float red[32];
+  __shared__ float s_scale;
+  float* g = grads + offsets[blockIdx.x];
+  const long long n = sizes[blockIdx.x];
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(g[i], g[i], s);
+  s = wred_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    const float nrm = sqrtf(tot);
+    s_scale = nrm > max_norm ? max_norm / nrm : 1.0f;
+  }
+  __syncthreads();
+  const float sc = s_scale;
+  if (sc != 1.0f)
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) g[i] *= sc;
+}
+
 // ---------------------------------------------------------------------------
 // Host side.
 // ---------------------------------------------------------------------------
@@ -1189,6 +1226,27 @@ extern "C" int comic_adam_step(comic_handle_t h, float* params, const float* gra
                                                                             beta2, eps, grad_scale);
   h->launches++;
   h->attn2_state = 0;   // attention_v / temperature may have moved: re-check the score bound (decoder.cu attn2_prepare)
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+extern "C" int comic_momentum_step(comic_handle_t h, float* params, const float* grads, float* accum, size_t n, float lr,
+                                   float momentum, float grad_scale, void* stream) {
+  COMIC_REQUIRE(h && params && grads && accum, COMIC_E_BADARG, "momentum_step: bad argument");
+  momentum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, accum, n, lr, momentum,
+                                                                                grad_scale);
+  h->launches++;
+  h->attn2_state = 0;
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+extern "C" int comic_clip_by_norm(comic_handle_t h, float* grads, const int64_t* offsets, const int64_t* sizes, int nvars,
+                                  float max_norm, void* stream) {
+  COMIC_REQUIRE(h && grads && offsets && sizes && nvars > 0 && max_norm > 0.f, COMIC_E_BADARG, "clip_by_norm: bad argument");
+  clip_by_norm_kernel<<<nvars, 1024, 0, (cudaStream_t)stream>>>(grads, reinterpret_cast<const long long*>(offsets),
+                                                               reinterpret_cast<const long long*>(sizes), max_norm);
+  h->launches++;
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;
 }

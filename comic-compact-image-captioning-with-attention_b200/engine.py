@@ -103,6 +103,8 @@ SIGNATURES = {
                                  C.POINTER(ComicDecoderGrads), _P, _SZ, _P]),
     'comic_l2_regularise': (_I, [_P, _P, _P, _SZ, _F, _P, _P, _SZ, _P]),
     'comic_adam_step': (_I, [_P, _P, _P, _P, _P, _SZ, _F, _F, _F, _F, _I, _F, _P]),
+    'comic_momentum_step': (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _P]),
+    'comic_clip_by_norm': (_I, [_P, _P, _P, _P, _I, _F, _P]),
     'comic_refresh_packed': (_I, [_P, _P, _SZ, _P]),
     'comic_refresh_packed_cnn': (_I, [_P, _P, _SZ, _P]),
     'comic_train_encoder_grads': (_I, [_P, _I, _I, _P, _P, _P, _SZ, _P]),
@@ -635,6 +637,15 @@ class Engine(object):
         self._check(self.lib.comic_adam_step(self._h, _ptr(params), _ptr(grads), _ptr(m), _ptr(v), params.numel(),
                                              float(lr), float(beta1), float(beta2), float(eps), int(step),
                                              float(grad_scale), self.stream()))
+
+    def momentum_step(self, params, grads, accum, lr, momentum=0.9, grad_scale=1.0):
+        self._check(self.lib.comic_momentum_step(self._h, _ptr(params), _ptr(grads), _ptr(accum), params.numel(), float(lr),
+                                                 float(momentum), float(grad_scale), self.stream()))
+
+    def clip_by_norm(self, grads, offsets, sizes, max_norm):
+        """offsets / sizes: int64 device tensors, one entry per variable of the flat gradient buffer."""
+        self._check(self.lib.comic_clip_by_norm(self._h, _ptr(grads), _ptr(offsets), _ptr(sizes), int(offsets.numel()),
+                                                float(max_norm), self.stream()))
 
     def refresh_packed(self):
         # the weights changed in place: captured inference graphs (Engine.graphed) are dropped, so that their next eager call

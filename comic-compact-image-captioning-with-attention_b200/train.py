@@ -83,10 +83,8 @@ class Trainer(object):
         if self.finetune_cnn and not with_cnn:
             raise ValueError('train_mode=cnn_finetune needs the CNN weights')
         # options the reference accepts but this path does not build: refuse instead of silently training differently
-        if float(getattr(c, 'clip_gradient_norm', 0) or 0) != 0:
-            raise NotImplementedError('clip_gradient_norm != 0 is not built (the reference default is 0)')
-        if getattr(c, 'optimiser', 'adam') != 'adam':
-            raise NotImplementedError("optimiser '%s' is not built (adam only)" % c.optimiser)
+        if getattr(c, 'optimiser', 'adam') not in ('adam', 'sgd'):
+            raise ValueError('Unknown optimiser.')                                 # src/model_base.py:881-882
         self.engine = eng = engine or Engine(c)
         torch = self.torch = eng.torch
         self.shapes = dict(wts.decoder_shapes(c))
@@ -132,6 +130,10 @@ class Trainer(object):
             self.cnn_grad_b = [self.gradient(wts.CNN + sc + '/BatchNorm/beta') for sc, *_ in convs]
         self.global_step = 0
         self.reg = torch.zeros(1, dtype=torch.float32, device=eng.device)
+        # slim clip_gradient_norms: per-variable slices of the flat gradient buffer (device tables for comic_clip_by_norm)
+        self.clip_norm = float(getattr(c, 'clip_gradient_norm', 0) or 0)
+        self._var_off = torch.tensor([o for o, n, _ in self.offsets.values()], dtype=torch.int64, device=eng.device)
+        self._var_len = torch.tensor([n for o, n, _ in self.offsets.values()], dtype=torch.int64, device=eng.device)
 
     # -- views ------------------------------------------------------------------
     def variable(self, name):
@@ -167,7 +169,9 @@ class Trainer(object):
             self.params[o:o + n].copy_(torch.as_tensor(np.asarray(W[name], np.float32).reshape(-1)))
             W[name] = self.params[o:o + n].view(shp if len(shp) else (1,))
             if extra:
-                for slot, buf in (('/Adam', self.adam_m), ('/Adam_1', self.adam_v)):
+                slots = ((('/Momentum', self.adam_m),) if getattr(self.c, 'optimiser', 'adam') == 'sgd'
+                         else (('/Adam', self.adam_m), ('/Adam_1', self.adam_v)))
+                for slot, buf in slots:
                     if name + slot in extra:
                         buf[o:o + n].copy_(torch.as_tensor(np.asarray(extra[name + slot], np.float32).reshape(-1)))
         if extra and 'global_step' in extra:
@@ -301,8 +305,15 @@ class Trainer(object):
         self.global_step += 1
         if lr is None:
             lr = cosine_lr(self.global_step - 1, c.max_step, c.lr_start, c.lr_end)
-        eng.adam_step(self.params, self.grads, self.adam_m, self.adam_v, lr, self.global_step, 0.9, 0.999,
-                      c.adam_epsilon, 1.0 / world)
+        if self.clip_norm > 0:
+            # clip(g / world, c) = clip(g, c * world) / world: the 1 / world of the mean stays folded into the optimiser
+            eng.clip_by_norm(self.grads, self._var_off, self._var_len, self.clip_norm * world)
+        if getattr(c, 'optimiser', 'adam') == 'sgd':
+            # tf.train.MomentumOptimizer(lr, 0.9, use_nesterov=False); its accumulator lives in the adam_m slot buffer
+            eng.momentum_step(self.params, self.grads, self.adam_m, lr, 0.9, 1.0 / world)
+        else:
+            eng.adam_step(self.params, self.grads, self.adam_m, self.adam_v, lr, self.global_step, 0.9, 0.999,
+                          c.adam_epsilon, 1.0 / world)
         if self.finetune_cnn:
             eng.refresh_packed_cnn()
         else:

@@ -371,6 +371,16 @@ int comic_l2_regularise(comic_handle_t h, const float* params, float* grads, siz
 int comic_adam_step(comic_handle_t h, float* params, const float* grads, float* m, float* v, size_t n,
                     float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* tf.train.MomentumOptimizer(momentum, use_nesterov=False) dense update, `--optimiser sgd` (src/model_base.py:868-880):
+ * accum = momentum * accum + grad * grad_scale; params -= lr * accum. */
+int comic_momentum_step(comic_handle_t h, float* params, const float* grads, float* accum, size_t n, float lr,
+                        float momentum, float grad_scale, void* stream);
+
+/* slim.learning.create_train_op(clip_gradient_norm = max_norm) (src/model_base.py:394-401): each variable's gradient
+ * (a slice [offsets[i], offsets[i] + sizes[i]) of the flat buffer; device arrays) is clipped by its own l2 norm. */
+int comic_clip_by_norm(comic_handle_t h, float* grads, const int64_t* offsets, const int64_t* sizes, int nvars,
+                       float max_norm, void* stream);
+
 /* After the optimiser changed the variables in place: rebuild the decoder's packed copies. */
 int comic_refresh_packed(comic_handle_t h, void* packed, size_t packed_bytes, void* stream);
 /* Same, decoder AND CNN (folded BN shifts, grouped 1x1 panels, tensor-path panels). */

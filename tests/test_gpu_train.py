@@ -165,6 +165,36 @@ def test_recurrent_dropout_masks_are_shared_over_rows_and_steps(torch_mod):
     assert np.isfinite(float(out1['loss'][0]))
 
 
+def test_momentum_sgd_and_per_variable_clipping(torch_mod):
+    """--optimiser sgd (tf.train.MomentumOptimizer(lr, 0.9), src/model_base.py:868-880) and clip_gradient_norm
+    (slim clip_gradient_norms: each variable by its own norm) against NumPy on the Trainer's own gradients."""
+    from comic_b200.train import Trainer
+    c = comic_config(train_mode='decoder', optimiser='sgd', clip_gradient_norm=0.05, max_step=100)
+    W, im, fm, caps, _, _ = _train_case(c, B=4, L=8, seed=6, dropout=False)
+    tr = Trainer(c, W, with_cnn=False)
+    eng = tr.engine
+    fm_d, im_d = eng.to_dev(fm), eng.to_dev(im)
+    theta = tr.params.cpu().numpy().astype(np.float64)
+    acc = np.zeros_like(theta)
+    clipped_any = False
+    for it in range(2):
+        tr.forward_backward(fm_d, im_d, caps)
+        g = tr.grads.cpu().numpy().astype(np.float64)
+        for name, (o, n, _) in tr.offsets.items():
+            nrm = np.sqrt((g[o:o + n] ** 2).sum())
+            if nrm > 0.05:
+                g[o:o + n] *= 0.05 / nrm
+                clipped_any = True
+        acc = 0.9 * acc + g
+        theta = theta - 1e-2 * acc
+        tr.apply_gradients(lr=1e-2)
+        assert rel_err(tr.params.cpu().numpy(), theta) < 1e-5
+        assert rel_err(tr.adam_m.cpu().numpy(), acc) < 1e-5
+        theta = tr.params.cpu().numpy().astype(np.float64)
+        acc = tr.adam_m.cpu().numpy().astype(np.float64)
+    assert clipped_any
+
+
 def test_training_steps_reduce_loss(torch_mod):
     """A few optimiser steps on one fixed batch (teacher forcing, dropout off): XE loss goes down,
     and the packed decoder copies follow the updated variables (greedy decode changes)."""

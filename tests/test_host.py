@@ -221,14 +221,13 @@ def test_run_inference_writes_the_reference_result_files(tmp_path):
 
 def test_unsupported_training_options_are_refused():
     """Options the reference accepts but this path does not build raise instead of silently training differently
-    (ADVICE r1): gradient clipping, non-Adam optimisers, the plain 'cider' reward.  (Recurrent dropout is built:
-    tests/test_gpu_train.py::test_recurrent_dropout_masks_are_shared_over_rows_and_steps.)"""
+    (ADVICE r1): unknown optimisers, the plain 'cider' reward.  (Recurrent dropout, per-variable gradient clipping and
+    the momentum-SGD optimiser are built: tests/test_gpu_train.py.)"""
     from comic_b200.train import Trainer
     from comic_b200 import scst as S
-    for kw in (dict(clip_gradient_norm=5.0), dict(optimiser='sgd')):
-        c = conf.make_config(train_mode='decoder', **kw)
-        with pytest.raises(NotImplementedError):
-            Trainer(c, {})
+    c = conf.make_config(train_mode='decoder', optimiser='rmsprop')
+    with pytest.raises(ValueError):                                               # src/model_base.py:881-882
+        Trainer(c, {})
     with pytest.raises(NotImplementedError):
         S.CaptionScorer({'document_frequency': {}, 'ref_len': 1}, dict(ciderD=1.0, cider=0.5))
     S.CaptionScorer({'document_frequency': {}, 'ref_len': 1}, dict(ciderD=1.0, cider=0.0, bleu=[0, 0, 0, 2]))
