@@ -379,6 +379,11 @@ __device__ constexpr unsigned char kRoles[16] = {A2S(0), A2S(1), A2S(2), A2S(3),
 
 template <int K, int NSW, int STAGES>
 __global__ void __launch_bounds__((NSW + kCtxWarps2 + 1 + kStatWarps) * 32, 1) attn2_kernel(const Args a) {
+#if COMIC_A2_TRACE
+  const long long t_entry = clock64();
+  unsigned long long g_entry;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
+#endif
   pdl_launch_dependents();
   using L = Layout<K, NSW, STAGES>;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -460,6 +465,7 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 1 + kStatWarps) * 32, 1) a
 #if COMIC_A2_TRACE
   long long* trc = a.trace ? a.trace + ((size_t)blockIdx.x * L::kWarps + warp) * kTraceSlices * 8 : nullptr;
   int tn = 0;
+  const long long t_prologue = clock64();
 #endif
 
   // Warp roles.  Warp w issues on sub-partition w & 3, and where the helpers sit matters (+-10 %, profiles/r07l, r07m):
@@ -814,33 +820,52 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 1 + kStatWarps) * 32, 1) a
         A2_STAMP(3);
         if (old == c_last - c_first) {
           __threadfence();
-          if (lane < K * kH) {
+          // Parts are added in CTA order.  At small batches an image is cut into many parts (25 images: 6) and this
+          // combine is the tail of the launch: with two parts in flight per round and the slot arithmetic (64-bit
+          // divisions) inside the loop it took 32 k of the launch's 64 k cycles (profiles/r12g_attn2_combine_trace.txt).
+          // Now: the slot of part l is computed once by lane l, and four parts x four quads of loads are in flight.
+          const int nparts = c_last - c_first + 1;
+          const int slot_l = slot_of(c_first + (lane < nparts ? lane : 0));
+          auto slot_at = [&](int idx) {                                  // whole warp, idx uniform
+            return nparts <= 32 ? __shfl_sync(0xffffffffu, slot_l, idx & 31) : slot_of(c_first + idx);
+          };
+          {
             float s = 0.f;
-            for (int c = c_first; c <= c_last; ++c) s += __ldcg(a.scratch + (size_t)slot_of(c) * kPartFloats + K * kR + lane);
-            sm_inv[lane] = s;
+            for (int p0 = 0; p0 < nparts; p0 += 4) {
+              float v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int sl = slot_at(p0 + q < nparts ? p0 + q : p0);
+                v[q] = (p0 + q < nparts && lane < K * kH) ? __ldcg(a.scratch + (size_t)sl * kPartFloats + K * kR + lane) : 0.f;
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) if (p0 + q < nparts) s += v[q];
+            }
+            if (lane < K * kH) sm_inv[lane] = s;
           }
           __syncwarp();
-          // parts are added in CTA order; the loads of one beam row (4 quads x 2 parts) are issued together
-#pragma unroll
+#pragma unroll 1
           for (int j = 0; j < K; ++j) {
             float4 t[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int c = c_first; c <= c_last; c += 2) {
-              const bool two = c + 1 <= c_last;
-              const float* s0 = a.scratch + (size_t)slot_of(c) * kPartFloats + j * kR;
-              const float* s1 = two ? a.scratch + (size_t)slot_of(c + 1) * kPartFloats + j * kR : s0;
-              float4 x[4], y[4];
+            for (int p0 = 0; p0 < nparts; p0 += 4) {
+              float4 x[4][4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                x[i] = __ldcg(reinterpret_cast<const float4*>(s0 + (lane + 32 * i) * 4));
-                y[i] = __ldcg(reinterpret_cast<const float4*>(s1 + (lane + 32 * i) * 4));
+              for (int q = 0; q < 4; ++q) {
+                const int sl = slot_at(p0 + q < nparts ? p0 + q : p0);
+                const float* sp = a.scratch + (size_t)sl * kPartFloats + j * kR;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  x[q][i] = (p0 + q < nparts) ? __ldcg(reinterpret_cast<const float4*>(sp + (lane + 32 * i) * 4))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
               }
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                t[i].x += x[i].x; t[i].y += x[i].y; t[i].z += x[i].z; t[i].w += x[i].w;
-                if (two) { t[i].x += y[i].x; t[i].y += y[i].y; t[i].z += y[i].z; t[i].w += y[i].w; }
-              }
+              for (int q = 0; q < 4; ++q)
+                if (p0 + q < nparts) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) { t[i].x += x[q][i].x; t[i].y += x[q][i].y; t[i].z += x[q][i].z; t[i].w += x[q][i].w; }
+                }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -976,6 +1001,15 @@ __global__ void __launch_bounds__((NSW + kCtxWarps2 + 1 + kStatWarps) * 32, 1) a
       }
     }
   }
+#if COMIC_A2_TRACE
+  // whole-warp residency: entry / end of prologue / exit (SM clock) and entry / exit on the global timer (ns), last record
+  if (trc != nullptr && lane == 0) {
+    unsigned long long g_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
+    long long* e = trc + (kTraceSlices - 1) * 8;
+    e[0] = t_entry; e[1] = t_prologue; e[2] = clock64(); e[3] = (long long)g_entry; e[4] = (long long)g_exit;
+  }
+#endif
 }
 
 }  // namespace a2

@@ -155,16 +155,20 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 int pack_tc_weight(comic_handle_t h, Carver& cv, const float* W, int K, int N, int ldw, int cin_src, int cin_dst,
                    tc::TcWeight& out, cudaStream_t st, bool dry, int gate_R = 0);
 inline bool use_tc(comic_handle_t h, const tc::TcWeight& w, int M) { return h->precision >= 1 && w.ready && M >= h->tc_min_rows; }
-// Split-K factor of a tensor-path GEMM with one M tile (decode steps at 33..128 rows: batch 25 x beam 3 = 75 rows is the
-// reference's default inference shape, src/infer.py:72).  One 128-row tile per 128 columns leaves 16 of 148 SMs walking
-// 20 K blocks at ~1.3 us each; cutting K puts (column tiles x ranges) CTAs on the chip with >= 2 K blocks each.
-inline int tc_ksplit(comic_handle_t h, int M, int N, int K, int which) {   // which: 1 = gate GEMM, 2 = [logits | query]
-  if (!(h->tc_splitk & which) || M > 128) return 1;
-  const int nk = (K + 63) / 64, n_tiles = (N + 127) / 128;
-  int ks = h->num_sms / n_tiles;
+// Split-K factor of a tensor-path decode-step GEMM that is far from filling the chip (33..~400 rows: batch 25 x beam 3 = 75
+// rows is the reference's default inference shape, src/infer.py:72).  One 128-row tile per 128 columns leaves 16 of 148
+// SMs walking 20 K blocks at ~1.3 us each; cutting K puts (tiles x ranges) CTAs on the chip with >= 2 K blocks each.
+inline int tc_ksplit_shape(int num_sms, int M, int N, int K) {
+  const int nk = (K + 63) / 64, tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  int ks = num_sms / tiles;
   if (ks > nk / 2) ks = nk / 2;
   if (ks > 8) ks = 8;
-  return ks < 1 ? 1 : ks;
+  return ks < 2 ? 1 : ks;
+}
+inline int tc_ksplit(comic_handle_t h, int M, int N, int K, int which) {   // which: 1 = gate GEMM, 2 = [logits | query]
+  if (!(h->tc_splitk & which)) return 1;
+  if (which == 2 && M > 128) return 1;      // [logits | query] (8 K blocks): the extra reduce launch costs more than the split saves
+  return tc_ksplit_shape(h->num_sms, M, N, K);
 }
 // Decode-step GEMMs: with the K split the tensor path also wins from 33 rows on (batch 16 x beam 3: gate GEMM 22.9 -> 14.9 us,
 // profiles/r12e_*); 32 rows and fewer belong to the persistent loop / the FFMA kernel.

@@ -65,12 +65,12 @@ __global__ void lstm_pointwise_kernel(const float* __restrict__ gp, int nz, size
 // Vectorised variant for the big-batch decode loop (R % 4 == 0, one split-K partial, no dropout / tape): four
 // units per thread with 128-bit accesses.  FAST (engine precision >= 1, the tensor path): sigmoid / tanh through
 // ex2.approx + rcp.approx (relative error ~1e-6 against expf / tanhf, same budget as the bf16x3 GEMM feeding it).
-template <bool FAST>
+template <bool FAST, bool PART = false>
 __global__ void __launch_bounds__(256)
 lstm_pointwise4_kernel(const float* __restrict__ gates, const float* __restrict__ bias, const float* __restrict__ c_prev,
                        const int* __restrict__ src, int src_limit, float* __restrict__ c_new, float* __restrict__ h_new,
                        int N, int R, const int* fin_count, int t, int n_rows, uint16_t* __restrict__ h_hi = nullptr,
-                       uint16_t* __restrict__ h_lo = nullptr) {
+                       uint16_t* __restrict__ h_lo = nullptr, int nz = 1, size_t zstride = 0) {
   pdl_launch_dependents();
   pdl_wait();
   if (step_stopped(fin_count, t, n_rows)) return;
@@ -82,7 +82,14 @@ lstm_pointwise4_kernel(const float* __restrict__ gates, const float* __restrict_
   float4 g[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float4 v = ldg4(gr + q * R), b = ldg4(bias + q * R + j);
+    float4 v = ldg4(gr + q * R);
+    const float4 b = ldg4(bias + q * R + j);
+    if (PART) {
+      for (int z = 1; z < nz; ++z) {                     // split-K partials of the gate GEMM, fixed order
+        const float4 p = ldg4(gr + z * zstride + q * R);
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+      }
+    }
     g[q] = make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
   }
   float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -974,7 +981,8 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
                       !io.out_mask && !io.gates_save;
   const bool tma_gates = tma_ok && (h->tma_a & 2) && tc1 && ks1 == 1 && !fused_lstm;
   // h' planes exist when the 4-units-per-thread LSTM kernel below runs
-  const bool tma_lq = tma_ok && (h->tma_a & 1) && !fused_lstm && nz1 == 1 && R % 4 == 0 && N >= 128 &&
+  const bool lstm4 = R % 4 == 0 && !io.h_drop && !io.out_mask && !io.gates_save && N >= 128 && (nz1 == 1 || (tc1 && h->precision >= 1));
+  const bool tma_lq = tma_ok && (h->tma_a & 1) && !fused_lstm && lstm4 && R % 4 == 0 && N >= 128 &&
                       use_tc(h, h->pk.tc_outq, N);
   if (fused_lstm) {
     e1.bias = h->pk.lstm_bias_il;
@@ -997,12 +1005,16 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
   if (!fused_lstm) {
     Prof pf(h, T_LSTM, st);
     int tot = N * R;
-    if (nz1 == 1 && R % 4 == 0 && !io.h_drop && !io.out_mask && !io.gates_save && N >= 128) {
+    if (lstm4) {
       const int tot4 = N * (R / 4);
-      if (h->precision >= 1)
-        launch_pdl(lstm_pointwise4_kernel<true>, dim3((tot4 + 255) / 256), dim3(256), 0, st, sb.gates, h->w.lstm_bias, io.c_prev,
+      if (h->precision >= 1 && nz1 > 1)
+        launch_pdl(lstm_pointwise4_kernel<true, true>, dim3((tot4 + 255) / 256), dim3(256), 0, st, sb.gates, h->w.lstm_bias, io.c_prev,
                    io.src, io.src_limit, io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows,
-                   tma_lq ? sb.hp_hi : nullptr, tma_lq ? sb.hp_lo : nullptr);
+                   tma_lq ? sb.hp_hi : nullptr, tma_lq ? sb.hp_lo : nullptr, nz1, (size_t)N * 4 * R);
+      else if (h->precision >= 1)
+        launch_pdl(lstm_pointwise4_kernel<true, false>, dim3((tot4 + 255) / 256), dim3(256), 0, st, sb.gates, h->w.lstm_bias, io.c_prev,
+                   io.src, io.src_limit, io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows,
+                   tma_lq ? sb.hp_hi : nullptr, tma_lq ? sb.hp_lo : nullptr, 1, (size_t)0);
       else
         lstm_pointwise4_kernel<false><<<(tot4 + 255) / 256, 256, 0, st>>>(sb.gates, h->w.lstm_bias, io.c_prev, io.src, io.src_limit,
                                                                          io.c_new, io.h_new, N, R, io.fin_count, io.t, io.n_rows);
@@ -1082,11 +1094,11 @@ int run_step(comic_handle_t h, const StepIO& io, const StepBufs& sb, int B, int 
 void carve_step(comic_handle_t h, Carver& cv, int N, StepBufs& sb, bool train_masks) {
   GemmPlan p1 = plan_gemm(N, 4 * h->R, h->KX, h->num_sms, true);
   int nz1 = gemm_num_partials(h->KX, p1);
-  if (nz1 < 8 && N <= 128) nz1 = 8;                 // tensor-path split-K partials (tc_ksplit <= 8)
+  { const int ks = tc_ksplit_shape(h->num_sms, N, 4 * h->R, h->KX); if (nz1 < ks) nz1 = ks; }   // tensor-path split-K partials
   GemmPlan p2 = plan_gemm(N, h->LQ, h->R, h->num_sms, true);
   int nz2 = gemm_num_partials(h->R, p2);
   sb.gates = cv.take<float>((size_t)nz1 * N * 4 * h->R);
-  if (nz2 < 8 && N <= 128) nz2 = 8;
+  { const int ks = tc_ksplit_shape(h->num_sms, N, h->LQ, h->R); if (nz2 < ks) nz2 = ks; }
   sb.lq_part = cv.take<float>(nz2 > 1 ? (size_t)nz2 * N * h->LQ : 1);
   sb.lq = cv.take<float>((size_t)N * h->LQ);
   sb.scores = cv.take<float>((size_t)N * h->H * h->M);

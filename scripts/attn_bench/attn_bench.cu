@@ -154,6 +154,35 @@ int main(int argc, char** argv) {
       span_max = std::max(span_max, tmax - tmin); span_sum += (double)(tmax - tmin);
     }
     {
+      // whole-warp residency (last trace record of every warp): entry -> end of prologue -> exit
+      long long g0 = (1ll << 62), g1 = 0; double pro = 0, res = 0; long long res_max = 0; int res_max_w = -1, res_max_b = -1; long long n = 0;
+      std::vector<double> by_w(kWarps, 0.0);
+      for (int b = 0; b < grid; ++b)
+        for (int w = 0; w < kWarps; ++w) {
+          const long long* e = tr.data() + (((size_t)b * kWarps + w) * a2::kTraceSlices + (a2::kTraceSlices - 1)) * 8;
+          if (e[2] == 0) continue;
+          g0 = std::min(g0, e[3]); g1 = std::max(g1, e[4]);
+          pro += (double)(e[1] - e[0]); res += (double)(e[2] - e[0]); by_w[w] += (double)(e[2] - e[0]); ++n;
+          if (e[2] - e[0] > res_max) { res_max = e[2] - e[0]; res_max_w = w; res_max_b = b; }
+        }
+      printf("residency: kernel %lld ns on the global timer; per warp prologue %.0f, entry->exit mean %.0f max %lld cycles (CTA %d warp %d)\n",
+             g1 - g0, pro / n, res / n, res_max, res_max_b, res_max_w);
+      if (res_max_b >= 0) {
+        const long long* p = tr.data() + ((size_t)res_max_b * kWarps + (kWarps - 1)) * a2::kTraceSlices * 8;
+        const long long t0 = p[(a2::kTraceSlices - 1) * 8];
+        printf("  finaliser of CTA %d, per segment (cycles after entry): wait-imgdone-from waited parked counted combined hist end\n", res_max_b);
+        for (int i = 0; i < 6; ++i) {
+          const long long* e = p + i * 8;
+          if (e[0] == 0) break;
+          auto rel = [&](long long v) { return v ? v - t0 : 0; };
+          printf("    seg %d: %lld %lld %lld %lld %lld %lld %lld\n", i, rel(e[0]), rel(e[1]), rel(e[6]), rel(e[3]), rel(e[4]), rel(e[5]), rel(e[2]));
+        }
+      }
+      printf("  entry->exit mean by warp:");
+      for (int w = 0; w < kWarps; ++w) printf(" %.0f", by_w[w] / grid);
+      printf("\n");
+    }
+    {
       // distributions: per slice index of the warp, and bucketed
       const int NB = 8; const long long edge[NB] = {250, 500, 1000, 2000, 4000, 8000, 16000, 1ll << 60};
       long long hist[5][NB] = {};
