@@ -206,6 +206,42 @@ def parity_block(model, kept, beam):
             'near-ties (< 1e-6 relative); attention maps 1e-3 relative'}
 
 
+def cpu_train_step_baseline(batch=32, T=41):
+    """BASELINE.json config 3 on the host cores: frozen InceptionV1 forward + teacher-forced decoder forward + backward
+    (torch CPU autograd of the restatement in tests/torch_ref.py, the checker of the CUDA gradients; fp32, all cores) +
+    the Adam update, ONE step of the same shapes as the GPU line (batch x T radix steps, every row full length)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch_ref as TR
+    import comic_b200  # noqa: F401
+    from comic_b200 import configuration as conf, weights as wts
+    c = conf.make_config(train_mode='decoder', batch_size_train=batch)
+    W = wts.init_weights(c, seed=c.rand_seed, cnn_init='he')
+    rng = np.random.default_rng(0)
+    images = rng.uniform(-1, 1, (batch, 224, 224, 3)).astype(np.float32)
+    caps = np.concatenate([np.full((batch, 1), 256), rng.integers(0, 256, size=(batch, T - 1)), np.full((batch, 1), 257)],
+                          axis=1).astype(np.int32)
+    P = TR.to_params(W, dtype=torch.float32)
+    PC = TR.cnn_params(W, dtype=torch.float32)
+    m = {k: torch.zeros_like(v) for k, v in P.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in P.items()}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        emb, fm = TR.encoder_forward(PC, images)
+    tot = TR.training_loss(P, c, emb.double().numpy(), fm.double().numpy(), caps, dtype=torch.float32)[0]
+    tot.backward()
+    with torch.no_grad():
+        for k, p_ in P.items():                       # tf.train.AdamOptimizer, step 1
+            g = p_.grad
+            m[k] += (g - m[k]) * 0.1
+            v2[k] += (g * g - v2[k]) * 0.001
+            p_ -= 1e-2 * m[k] / (v2[k].sqrt() + c.adam_epsilon)
+    sec = time.perf_counter() - t0
+    return {'value': 1.0 / sec, 'unit': 'steps/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '1 step, batch %d x %d steps: torch-CPU fp32 restatement (tests/torch_ref.py: InceptionV1 forward, '
+                      'decoder forward + autograd backward, Adam)' % (batch, T)}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -486,8 +522,12 @@ def run_ours(args):
                 r['roofline'] = {'bound': 'hbm', 'achieved': alg / (r['ms_per_step'] * 1e-3) / 1e9, 'peak': load_peaks()['hbm'],
                                  'unit': 'GB/s', 'frac': alg / (r['ms_per_step'] * 1e-3) / 1e9 / load_peaks()['hbm'],
                                  'traffic': None, 'note': 'decoder part only; launch-bound (%d launches per step)' % r['gpu_launches_per_step']}
-            r['cpu_baseline'] = None       # the NumPy oracle restates the forward and the losses; gradients are checked against
-                                           # fp64 autograd in tests/, not timed
+            r['cpu_baseline'] = None       # the NumPy oracle restates the forward and the losses only
+            if key == 'decoder' and world == 1 and not args.no_cpu_baseline:
+                try:
+                    r['cpu_baseline'] = cpu_train_step_baseline(batch)
+                except Exception as e:     # a reported baseline, never a reason to lose the line
+                    r['cpu_baseline'] = {'unavailable': repr(e)[:200]}
             train[key] = r
 
     if rank == 0:

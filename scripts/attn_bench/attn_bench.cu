@@ -178,6 +178,29 @@ int main(int argc, char** argv) {
           printf("    seg %d: %lld %lld %lld %lld %lld %lld %lld\n", i, rel(e[0]), rel(e[1]), rel(e[6]), rel(e[3]), rel(e[4]), rel(e[5]), rel(e[2]));
         }
       }
+      {
+        // per CTA on the global timer: entry of its first warp and exit of its last warp, ns after the first entry of the grid
+        std::vector<long long> ent, ext, dur;
+        for (int b = 0; b < grid; ++b) {
+          long long e0 = (1ll << 62), e1 = 0;
+          for (int w = 0; w < kWarps; ++w) {
+            const long long* e = tr.data() + (((size_t)b * kWarps + w) * a2::kTraceSlices + (a2::kTraceSlices - 1)) * 8;
+            if (e[2] == 0) continue;
+            e0 = std::min(e0, e[3]); e1 = std::max(e1, e[4]);
+          }
+          if (e1) { ent.push_back(e0 - g0); ext.push_back(e1 - g0); dur.push_back(e1 - e0); }
+        }
+        auto pr = [&](const char* nm, std::vector<long long> v) {
+          std::sort(v.begin(), v.end());
+          const size_t n2 = v.size();
+          printf("  %s (ns): min %lld p10 %lld p25 %lld p50 %lld p75 %lld p90 %lld max %lld\n", nm, v[0], v[n2 / 10], v[n2 / 4], v[n2 / 2],
+                 v[3 * n2 / 4], v[9 * n2 / 10], v[n2 - 1]);
+        };
+        pr("CTA entry", ent); pr("CTA exit ", ext); pr("CTA resident", dur);
+        printf("  CTA resident ns by block index (every 4th):");
+        for (size_t b = 0; b < dur.size(); b += 4) printf(" %lld", dur[b]);
+        printf("\n");
+      }
       printf("  entry->exit mean by warp:");
       for (int w = 0; w < kWarps; ++w) printf(" %.0f", by_w[w] / grid);
       printf("\n");

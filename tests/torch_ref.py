@@ -43,10 +43,10 @@ def _drop(x, keep, mask):
 
 
 def training_loss(P, c, im_embed, fm, captions, masks=None, keeps=(1.0, 1.0, 1.0), rewards=None,
-                  fm_requires_grad=False):
+                  fm_requires_grad=False, dtype=torch.float64):
     """Returns (total, xe, map, reg, aux) as fp64 torch scalars; `aux` holds logits [T,B,V]
     (imputed) and attention maps [B,H,T_run,M].  captions [B,L] int (PAD = -1)."""
-    dt = torch.float64
+    dt = dtype
     # fm / im_embed may be torch tensors still attached to the CNN graph (cnn_finetune)
     t = lambda a: a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a), dtype=dt)
     H, R = c.attn_num_heads, c.rnn_size
@@ -88,7 +88,7 @@ def training_loss(P, c, im_embed, fm, captions, masks=None, keeps=(1.0, 1.0, 1.0
             return E[torch.as_tensor(ids)]
         valid = (ids >= 0) & (ids < V)
         out = E[torch.as_tensor(np.where(valid, ids, 0))]
-        return out * torch.as_tensor(valid.astype(np.float64))[:, None]
+        return out * torch.as_tensor(valid.astype(np.float64)).to(dt)[:, None]
 
     T_run = int(lens.max()) if B else 0
     outs, hist = [], []
