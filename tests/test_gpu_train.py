@@ -109,6 +109,34 @@ def test_encoder_output_gradients_match_autograd(torch_mod, name):
     assert rel_err(demb.cpu().numpy(), aux['im'].grad.numpy()) < 1e-3
 
 
+@pytest.mark.parametrize('name', ['comic256_xe_dropout', 'dot', 'context_layer', 'dot_sigmoid_ctx_ph_indep_h4'])
+def test_training_forward_through_the_fused_attention_kernel(torch_mod, name):
+    """From 48 images on the training forward takes attn_fused_kernel (one launch for scores, softmax, dropout and context)
+    instead of the sliced kernels the small parity cases run: forced here on the 4-row case, it must leave the same
+    tape, i.e. the same losses and gradients up to summation order (signorm keeps the sliced kernels by design)."""
+    from comic_b200.train import Trainer
+    mk, dropout, scst = CASES[name]
+    c = mk()
+    W, im, fm, caps, masks, keeps = _train_case(c, B=4, L=8, seed=3, dropout=dropout)
+    rewards = np.array([0.4, -0.3, 1.2, 0.05], np.float32) if scst else None
+    res = []
+    for min_images in (1, 10000):
+        tr = Trainer(c, W, with_cnn=False)
+        eng = tr.engine
+        eng.set_precision('f32')
+        eng.set_option('fused_attn_min_images', min_images)
+        dmasks = dict(init_in=eng.to_dev(masks['init_in']), inp=eng.to_dev(masks['inp']), out=eng.to_dev(masks['out']),
+                      att=eng.to_dev(masks['att'].reshape(masks['att'].shape[0], masks['att'].shape[1], -1)))
+        n0 = eng.launch_count()
+        out = tr.forward_backward(eng.to_dev(fm), eng.to_dev(im), caps, rewards, dmasks, keeps, want_logits=True)
+        res.append((out['loss'].cpu().numpy(), tr.grads.cpu().numpy().copy(), eng.launch_count() - n0))
+    (l1, g1, n1), (l2, g2, n2) = res
+    if c.attn_probability_fn == 'softmax':
+        assert n1 < n2, 'the fused kernel replaces two launches per step'
+    np.testing.assert_allclose(l1, l2, rtol=2e-5, atol=1e-6)
+    assert rel_err(g1, g2) < 2e-5
+
+
 def test_adam_and_l2_match_oracle(torch_mod):
     import comic_oracle as O
     from comic_b200.engine import Engine
