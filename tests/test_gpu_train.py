@@ -137,6 +137,28 @@ def test_training_forward_through_the_fused_attention_kernel(torch_mod, name):
     assert rel_err(g1, g2) < 2e-5
 
 
+def test_training_forward_on_the_k_split_tensor_path(torch_mod):
+    """48 rows in the default precision: the teacher-forced forward runs its gate / [logits | query] GEMMs on the tensor path
+    with the K loop split over CTAs (partials summed by the LSTM kernel that also writes the gate tape).  Same losses and
+    gradients as the all-FFMA f32 mode, within the bf16x3 budget."""
+    from comic_b200.train import Trainer
+    c = comic_config(train_mode='decoder')
+    W, im, fm, caps, masks, keeps = _train_case(c, B=48, L=7, seed=9, dropout=True)
+    res = []
+    for prec in ('split', 'f32'):
+        tr = Trainer(c, W, with_cnn=False)
+        eng = tr.engine
+        eng.set_precision(prec)
+        dmasks = dict(init_in=eng.to_dev(masks['init_in']), inp=eng.to_dev(masks['inp']), out=eng.to_dev(masks['out']),
+                      att=eng.to_dev(masks['att'].reshape(masks['att'].shape[0], masks['att'].shape[1], -1)))
+        out = tr.forward_backward(eng.to_dev(fm), eng.to_dev(im), caps, None, dmasks, keeps, want_logits=True)
+        res.append((out['loss'].cpu().numpy(), out['logits'].cpu().numpy(), tr.grads.cpu().numpy().copy()))
+    (l1, lg1, g1), (l2, lg2, g2) = res
+    np.testing.assert_allclose(l1, l2, rtol=1e-4, atol=1e-6)
+    assert rel_err(lg1, lg2) < 2e-4
+    assert rel_err(g1, g2) < 1e-3
+
+
 def test_adam_and_l2_match_oracle(torch_mod):
     import comic_oracle as O
     from comic_b200.engine import Engine
