@@ -922,7 +922,8 @@ int attn2_prepare(comic_handle_t h, StepIO& io, const StepBufs& sb, int B, int k
     // once per weight binding: exp(score - bound) must not underflow to zero for a whole row, so the kernel is only
     // taken while 2 * bound stays well inside the fp32 exponent range (the one host synchronisation of this path)
     COMIC_REQUIRE(h->attn2_host != nullptr, COMIC_E_CUDA, "attn2: no pinned buffer");
-    COMIC_CHECK_CUDA(cudaMemcpyAsync(h->attn2_host, sb.abound, a2::kBoundFloats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // the kernel writes entries 0..9 (8 head bounds, exponent shift, feasibility flag); the rest of the buffer is padding
+    COMIC_CHECK_CUDA(cudaMemcpyAsync(h->attn2_host, sb.abound, 10 * sizeof(float), cudaMemcpyDeviceToHost, st));
     COMIC_CHECK_CUDA(cudaStreamSynchronize(st));
     bool ok = h->attn2_host[9] == 1.0f;                       // an exponent shift for the clamp-free reciprocal product exists
     for (int i = 0; i < a2::kH; ++i) ok = ok && (h->attn2_host[i] == h->attn2_host[i]) && h->attn2_host[i] <= 40.0f;
