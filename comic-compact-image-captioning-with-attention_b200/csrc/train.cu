@@ -708,6 +708,58 @@ clip_by_norm_kernel(float* __restrict__ grads, const long long* __restrict__ off
     for (long long i = threadIdx.x; i < n; i += blockDim.x) g[i] *= sc;
 }
 
+// Legacy image-embedding head (src/model_base.py:80-91), recomputed for its backward: one CTA per image.
+//   pool = mean over the 49 positions of Mixed_5c; xhat = (pool - mean) / sqrt(var + 1e-12); t1 = tanh(xhat * gamma + beta)
+__global__ void __launch_bounds__(256)
+legacy_head_recompute_kernel(const float* __restrict__ m5c, const float* __restrict__ gamma, const float* __restrict__ beta,
+                             float* __restrict__ xhat, float* __restrict__ t1, int P, int C) {
+  __shared__ float red[8];
+  __shared__ float s_stat[2];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* src = m5c + (size_t)b * P * C;
+  float pool[4] = {0.f, 0.f, 0.f, 0.f};                       // C = 1024 = 4 channels per thread
+  for (int j = 0; j < 4; ++j) {
+    const int c = tid + 256 * j;
+    float s = 0.f;
+    if (c < C)
+      for (int p2 = 0; p2 < P; ++p2) s += src[(size_t)p2 * C + c];
+    pool[j] = s * (1.0f / (float)P);
+  }
+  float s = (pool[0] + pool[1]) + (pool[2] + pool[3]);
+  s = wred_sum(s);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; s_stat[0] = t / (float)C; }
+  __syncthreads();
+  const float mean = s_stat[0];
+  float v = 0.f;
+  for (int j = 0; j < 4; ++j) { const float d = (tid + 256 * j < C) ? pool[j] - mean : 0.f; v = fmaf(d, d, v); }
+  v = wred_sum(v);
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; s_stat[1] = 1.0f / sqrtf(t / (float)C + 1e-12f); }
+  __syncthreads();
+  const float rstd = s_stat[1];
+  for (int j = 0; j < 4; ++j) {
+    const int c = tid + 256 * j;
+    if (c < C) {
+      const float xh = (pool[j] - mean) * rstd;
+      xhat[(size_t)b * C + c] = xh;
+      t1[(size_t)b * C + c] = tanhf(fmaf(xh, gamma[c], beta[c]));
+    }
+  }
+}
+
+// d_ln = d_t1 * (1 - t1^2) (-> d beta rows) and gx = d_ln * xhat (-> d gamma rows), in place of d_t1 / xhat
+__global__ void legacy_head_dln_kernel(float* __restrict__ d_t1, float* __restrict__ xhat, const float* __restrict__ t1, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = t1[i];
+  const float d = d_t1[i] * (1.0f - t * t);
+  d_t1[i] = d;
+  xhat[i] = d * xhat[i];
+}
+
 // ---------------------------------------------------------------------------
 // Host side.
 // ---------------------------------------------------------------------------
@@ -869,8 +921,6 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
   COMIC_REQUIRE(fm && im_embed && inputs_tm && targets_tm && coef_tm && lens && loss_out, COMIC_E_BADARG,
                 "train_fwd_bwd: null argument");   // grads == NULL: forward only (evaluation perplexity)
   COMIC_REQUIRE(B > 0 && T > 0 && T_run > 0 && T_run <= T, COMIC_E_SHAPE, "train_fwd_bwd: bad B=%d T=%d T_run=%d", B, T, T_run);
-  COMIC_REQUIRE(!h->cfg.legacy, COMIC_E_UNSUPPORTED,
-                "train_fwd_bwd: the legacy image-embedding head (trainable LN_tanh + im_embed, src/model_base.py:80-91) is not built");
   COMIC_REQUIRE(!h->cfg.context_layer || (h->w.a_layer && (!grads || grads->a_layer)), COMIC_E_BADARG,
                 "train_fwd_bwd: attn_context_layer needs a_layer/kernel and its gradient buffer");
   COMIC_REQUIRE(h->R == 512 || h->R == 256 || h->R == 1024, COMIC_E_UNSUPPORTED, "train_fwd_bwd: rnn_size %d", h->R);
@@ -1172,7 +1222,6 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
 extern "C" int comic_train_encoder_grads(comic_handle_t h, int B, int T_run, float* dfm_out, float* dim_embed_out,
                                          void* ws, size_t ws_bytes, void* stream) {
   COMIC_REQUIRE(h && h->bound && dfm_out && dim_embed_out && ws, COMIC_E_BADARG, "train_encoder_grads: bad argument");
-  COMIC_REQUIRE(!h->cfg.legacy, COMIC_E_UNSUPPORTED, "train_encoder_grads: the legacy image-embedding head is not built");
   cudaStream_t st = (cudaStream_t)stream;
   size_t need;
   train_workspace_bytes(h, B, T_run, &need);
@@ -1201,6 +1250,59 @@ extern "C" int comic_train_encoder_grads(comic_handle_t h, int B, int T_run, flo
   transpose(h->w.init_weight, E, NI, NI, tb.encT, E, st);
   if ((rc = train_gemm(h, tb.dx0, NI, tb.encT, E, dim_embed_out, E, B, E, NI, tb.part, tb.part_floats, st))) return rc;
   h->launches += 2;
+  COMIC_CHECK_CUDA(cudaGetLastError());
+  return COMIC_OK;
+}
+
+// floats of workspace comic_legacy_head_bwd needs for B images
+static size_t legacy_head_ws_floats(int B) {
+  const size_t Bp = (size_t)(B + 3) / 4 * 4, C = 1024;
+  return 5 * Bp * C + C * C + C * Bp + (size_t)4 * 1024 * 1024 + 64;
+}
+
+extern "C" int comic_legacy_head_bwd_bytes(comic_handle_t h, int B, size_t* bytes) {
+  COMIC_REQUIRE(h && bytes && B > 0, COMIC_E_BADARG, "legacy_head_bwd_bytes: bad argument");
+  *bytes = legacy_head_ws_floats(B) * sizeof(float);
+  return COMIC_OK;
+}
+
+extern "C" int comic_legacy_head_bwd(comic_handle_t h, const float* mixed5c, int B, const float* d_im_embed, float* d_gamma,
+                                     float* d_beta, float* d_weight, void* ws, size_t ws_bytes, void* stream) {
+  COMIC_REQUIRE(h && h->bound && mixed5c && d_im_embed && d_gamma && d_beta && d_weight && ws && B > 0, COMIC_E_BADARG,
+                "legacy_head_bwd: bad argument");
+  COMIC_REQUIRE(h->cfg.legacy && h->w.enc_ln_gamma && h->w.enc_ln_beta && h->w.enc_embed_weight, COMIC_E_BADARG,
+                "legacy_head_bwd: the model has no legacy head");
+  COMIC_REQUIRE(ws_bytes >= legacy_head_ws_floats(B) * sizeof(float), COMIC_E_WORKSPACE, "legacy_head_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = 1024, Bp = (B + 3) / 4 * 4;
+  Carver cv(ws);
+  float* xhat = cv.take<float>((size_t)Bp * C);
+  float* t1 = cv.take<float>((size_t)Bp * C);
+  float* d_t1 = cv.take<float>((size_t)Bp * C);
+  float* d_im_p = cv.take<float>((size_t)Bp * C);
+  float* t1T = cv.take<float>((size_t)C * Bp);
+  float* WT = cv.take<float>((size_t)C * C);
+  const size_t part_floats = (size_t)4 * 1024 * 1024;
+  float* part = cv.take<float>(part_floats);
+  int rc;
+  legacy_head_recompute_kernel<<<B, 256, 0, st>>>(mixed5c, h->w.enc_ln_gamma, h->w.enc_ln_beta, xhat, t1, 49, C);
+  // d t1 = d im_embed . W^T
+  transpose(h->w.enc_embed_weight, C, C, C, WT, C, st);
+  if ((rc = train_gemm(h, d_im_embed, C, WT, C, d_t1, C, B, C, C, part, part_floats, st))) return rc;
+  // d W [C, C] = t1^T [C, B] . d im_embed [B, C]   (rows padded to a multiple of 4 with zeros)
+  COMIC_CHECK_CUDA(cudaMemsetAsync(t1T, 0, (size_t)C * Bp * sizeof(float), st));
+  COMIC_CHECK_CUDA(cudaMemsetAsync(d_im_p, 0, (size_t)Bp * C * sizeof(float), st));
+  transpose(t1, B, C, C, t1T, Bp, st);
+  COMIC_CHECK_CUDA(cudaMemcpyAsync(d_im_p, d_im_embed, (size_t)B * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if ((rc = train_gemm(h, t1T, Bp, d_im_p, C, d_weight, C, C, C, Bp, part, part_floats, st))) return rc;
+  // through tanh and the layer norm's affine part: d beta = sum_b d_ln, d gamma = sum_b d_ln * xhat
+  {
+    const size_t n = (size_t)B * C;
+    legacy_head_dln_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_t1, xhat, t1, n);
+  }
+  colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(d_t1, B, C, C, d_beta, 0);
+  colsum_kernel<<<(C + 31) / 32, 256, 0, st>>>(xhat, B, C, C, d_gamma, 0);
+  h->launches += 7;
   COMIC_CHECK_CUDA(cudaGetLastError());
   return COMIC_OK;
 }

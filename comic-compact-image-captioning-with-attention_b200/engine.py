@@ -108,6 +108,8 @@ SIGNATURES = {
     'comic_refresh_packed': (_I, [_P, _P, _SZ, _P]),
     'comic_refresh_packed_cnn': (_I, [_P, _P, _SZ, _P]),
     'comic_train_encoder_grads': (_I, [_P, _I, _I, _P, _P, _P, _SZ, _P]),
+    'comic_legacy_head_bwd_bytes': (_I, [_P, _I, _P]),
+    'comic_legacy_head_bwd': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     'comic_encode_train_bytes': (_I, [_P, _I, C.POINTER(_SZ), C.POINTER(_SZ)]),
     'comic_encode_train_fwd': (_I, [_P, _P, _I, _P, _P, _P, _SZ, _P, _SZ, _P]),
     'comic_encode_bwd': (_I, [_P, _P, _I, _P, _P, _P, _SZ, C.POINTER(ComicCnnGrads), _P, _SZ, _P]),
@@ -607,6 +609,19 @@ class Engine(object):
         self._check(self.lib.comic_train_encoder_grads(self._h, B, int(T_run), _ptr(dfm), _ptr(demb), _ptr(ws),
                                                        ws.numel(), self.stream()))
         return dfm, demb
+
+    def legacy_head_bwd(self, mixed5c, d_im_embed, d_gamma, d_beta, d_weight):
+        """--legacy, train_mode=decoder: gradients of Model/encoder/LN_tanh/{gamma, beta} and Model/encoder/im_embed/weight
+        from Mixed_5c [B,7,7,1024] and d loss / d im_embed [B,1024] (comic_legacy_head_bwd)."""
+        B = mixed5c.shape[0]
+        n = C.c_size_t()
+        self._check(self.lib.comic_legacy_head_bwd_bytes(self._h, B, C.byref(n)))
+        ws = self._ws.get('legacy_head')
+        if ws is None or ws.numel() < n.value:
+            ws = self._ws['legacy_head'] = self.torch.empty(n.value, dtype=self.torch.uint8, device=self.device)
+        self._check(self.lib.comic_legacy_head_bwd(self._h, _ptr(mixed5c.contiguous()), B, _ptr(d_im_embed.contiguous()),
+                                                   _ptr(d_gamma), _ptr(d_beta), _ptr(d_weight), _ptr(ws), ws.numel(),
+                                                   self.stream()))
 
     def encode_bwd(self, images, dfm, dim_embed, conv_grads, beta_grads):
         """Backward of the last `encode_train`: conv_grads / beta_grads are lists of 57 device tensors

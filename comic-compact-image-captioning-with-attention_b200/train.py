@@ -88,6 +88,13 @@ class Trainer(object):
         self.engine = eng = engine or Engine(c)
         torch = self.torch = eng.torch
         self.shapes = dict(wts.decoder_shapes(c))
+        # --legacy: the image-embedding head (LN_tanh + im_embed, src/model_base.py:80-91) sits outside Model/encoder/cnn, so it
+        # trains with the decoder; the reference only trains legacy models in train_mode=decoder (src/train.py:242, 253)
+        self.legacy_head = bool(getattr(c, 'legacy', False))
+        if self.legacy_head:
+            if c.train_mode != 'decoder':
+                raise NotImplementedError("--legacy models train in train_mode=decoder only (src/train.py:242, 253)")
+            self.shapes.update(wts.encoder_head_shapes(c))
         self.n_decoder_vars = len(self.shapes)
         if self.finetune_cnn:
             # trainable CNN variables: conv kernels + BN betas (BN runs with is_training=False,
@@ -204,7 +211,7 @@ class Trainer(object):
 
     # -- one fwd + bwd (+ optimiser) ---------------------------------------------
     def forward_backward(self, fm, im_embed, captions, rewards=None, masks=None, keeps=(1.0, 1.0, 1.0),
-                         want_logits=False, want_attn=False, images=None, forward_only=False):
+                         want_logits=False, want_attn=False, images=None, forward_only=False, mixed5c=None):
         """captions [B,L] int32 host array.  Returns dict(loss=[total, xe, map, reg] device tensor, ...);
         gradients land in self.grads.  forward_only: cross-entropy only (loss[1]); no backward, no L2 term, and
         self.grads is left untouched (the evaluation graph of train_fn._run_eval_loop)."""
@@ -233,6 +240,13 @@ class Trainer(object):
                                                    coef_tm, lens_d, T_run, self.grad_views, masks, keeps,
                                                    c.rnn_map_loss_scale, want_logits, want_attn)
         mult = 1.0
+        if self.legacy_head:
+            if mixed5c is None:
+                raise ValueError('--legacy: forward_backward needs Mixed_5c of the encoder forward (Engine.encode(images, '
+                                 'want_mixed5c=True)) for the gradient of the image-embedding head')
+            _dfm, demb = eng.train_encoder_grads(fm.shape[0], T_run)
+            eng.legacy_head_bwd(mixed5c, demb, self.gradient(wts.ENC + 'LN_tanh/gamma'), self.gradient(wts.ENC + 'LN_tanh/beta'),
+                                self.gradient(wts.ENC + 'im_embed/weight'))
         if self.finetune_cnn:
             if images is None:
                 raise ValueError('cnn_finetune: forward_backward needs the images of the last encode_train')
@@ -325,9 +339,12 @@ class Trainer(object):
         fwd+bwd (+ encoder backward), optimiser.  Dropout is ON as in the reference's train graph (masks seeded by
         `seed`, default derived from config.rand_seed and the global step); dropout=False runs without masks."""
         eng = self.engine
+        m5c = None
         if self.finetune_cnn:
             images = eng.to_dev(images)
             im_embed, fm = eng.encode_train(images)
+        elif self.legacy_head:
+            im_embed, fm, m5c = eng.encode(images, want_mixed5c=True)
         else:
             im_embed, fm = eng.encode(images)
         B = im_embed.shape[0]
@@ -336,6 +353,6 @@ class Trainer(object):
             _, _, _, lens = process_inputs(captions, self.c.token_type)
             masks, keeps = self.make_masks(B, int(lens.max()), self.dropout_seed(seed))
         out = self.forward_backward(fm, im_embed, captions, rewards, masks, keeps,
-                                    images=images if self.finetune_cnn else None)
+                                    images=images if self.finetune_cnn else None, mixed5c=m5c)
         out['lr'] = self.apply_gradients(lr)
         return out

@@ -336,6 +336,15 @@ int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const float* im_embed
 int comic_train_encoder_grads(comic_handle_t h, int B, int T_run, float* dfm_out, float* dim_embed_out,
                               void* ws, size_t ws_bytes, void* stream);
 
+/* --legacy models in train_mode=decoder (the only mode the reference trains them in, src/train.py:242, 253): the image
+ * embedding is im_embed = tanh(LN(pool)) . W with pool = mean over the 7x7 positions of Mixed_5c (src/model_base.py:80-91),
+ * and LN_tanh/{gamma, beta} and im_embed/weight are trainable (they are not under freeze_scopes = Model/encoder/cnn).
+ * Given mixed5c [B,7,7,1024] (comic_encode_fwd's optional output) and d loss / d im_embed [B,1024]
+ * (comic_train_encoder_grads), writes d gamma [1024], d beta [1024], d weight [1024,1024]. */
+int comic_legacy_head_bwd_bytes(comic_handle_t h, int B, size_t* bytes);
+int comic_legacy_head_bwd(comic_handle_t h, const float* mixed5c, int B, const float* d_im_embed, float* d_gamma,
+                          float* d_beta, float* d_weight, void* ws, size_t ws_bytes, void* stream);
+
 /* Gradient buffers of the trainable CNN variables (src/train.py:241-250: cnn_finetune clears
  * freeze_scopes; BN runs with is_training=False, src/model_base.py:71-77, so only the conv
  * kernels [HWIO] and the BN betas train).  Order = comic_conv_table(). */

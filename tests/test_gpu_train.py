@@ -159,6 +159,69 @@ def test_training_forward_on_the_k_split_tensor_path(torch_mod):
     assert rel_err(g1, g2) < 1e-3
 
 
+def test_legacy_head_trains_in_decoder_mode(torch_mod):
+    """--legacy, train_mode=decoder (the only mode the reference trains legacy models in, src/train.py:242, 253): the
+    image-embedding head LN_tanh + im_embed is trainable (src/model_base.py:80-91).  Every decoder gradient and the three
+    head gradients against fp64 autograd of one graph Mixed_5c -> head -> decoder -> loss."""
+    import torch
+    import torch_ref as TR
+    from comic_b200.train import Trainer
+    from comic_b200 import weights as wts
+    c = comic_config(train_mode='decoder', legacy=True)
+    W, _im, fm, caps, masks, keeps = _train_case(c, B=4, L=8, seed=3, dropout=True)
+    rng = np.random.default_rng(12)
+    m5c = np.maximum(rng.standard_normal((4, 7, 7, 1024)), 0).astype(np.float32)
+    P = TR.to_params(W)
+    PH = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=True) for k, v in W.items()
+          if k.startswith(wts.ENC) and not k.startswith(wts.CNN)}
+    assert len(PH) == 3
+    im_t = TR.legacy_head(PH, m5c)
+    tot, xe, mp, reg, aux = TR.training_loss(P, c, im_t, fm, caps, masks, keeps)
+    for v in PH.values():                                  # the head's variables are in tvars: L2 applies (model_base.py:368-380)
+        tot = tot + (v ** 2).sum() / 2 * c.l2_decay
+        reg = reg + (v ** 2).sum() / 2 * c.l2_decay
+    tot.backward()
+    tr = Trainer(c, W, with_cnn=False)
+    eng = tr.engine
+    eng.set_precision('f32')
+    dmasks = dict(init_in=eng.to_dev(masks['init_in']), inp=eng.to_dev(masks['inp']), out=eng.to_dev(masks['out']),
+                  att=eng.to_dev(masks['att'].reshape(masks['att'].shape[0], masks['att'].shape[1], -1)))
+    out = tr.forward_backward(eng.to_dev(fm), eng.to_dev(im_t.detach().numpy().astype(np.float32)), caps, None, dmasks, keeps,
+                              mixed5c=eng.to_dev(m5c))
+    loss = out['loss'].cpu().numpy()
+    assert abs(loss[1] - float(xe)) < 1e-4 * max(1.0, abs(float(xe)))
+    assert abs(loss[3] - float(reg)) < 1e-4 * max(1e-3, abs(float(reg)))
+    worst = {}
+    for vname in wts.decoder_shapes(c):
+        worst[vname] = rel_err(tr.gradient(vname).cpu().numpy().reshape(P[vname].shape), P[vname].grad.numpy())
+    for vname, v in PH.items():
+        worst[vname] = rel_err(tr.gradient(vname).cpu().numpy().reshape(v.shape), v.grad.numpy())
+    bad = {k: v for k, v in worst.items() if not v < 1e-3}
+    assert not bad, (bad, worst)
+    with pytest.raises(NotImplementedError):               # src/train.py:242, 253
+        Trainer(comic_config(train_mode='scst', legacy=True), W, with_cnn=False)
+
+
+def test_legacy_model_train_step_end_to_end(torch_mod):
+    """Trainer.step on a --legacy model: images -> frozen CNN (Mixed_5c kept) -> head -> decoder fwd + bwd -> Adam; the
+    head's variables move, and the next encode uses them."""
+    from _common import images
+    from comic_b200.train import Trainer
+    from comic_b200 import weights as wts
+    c = comic_config(train_mode='decoder', legacy=True, max_step=100)
+    W = make_weights(c, seed=5)
+    _, _, _, caps, _, _ = _train_case(c, B=2, L=7, seed=4, dropout=False)
+    tr = Trainer(c, W)
+    img = tr.engine.to_dev(images(2, seed=3))
+    emb0, _ = tr.engine.encode(img)
+    w0 = tr.variable(wts.ENC + 'im_embed/weight').clone()
+    losses = [float(tr.step(img, caps, lr=1e-2)['loss'][1]) for _ in range(3)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert float((tr.variable(wts.ENC + 'im_embed/weight') - w0).abs().max()) > 0
+    emb1, _ = tr.engine.encode(img)
+    assert float((emb1 - emb0).abs().max()) > 0
+
+
 def test_adam_and_l2_match_oracle(torch_mod):
     import comic_oracle as O
     from comic_b200.engine import Engine

@@ -28,6 +28,19 @@ def to_params(W, dtype=torch.float64):
             for k, v in W.items() if k.startswith('Model/decoder')}
 
 
+def legacy_head(PH, mixed5c):
+    """--legacy image embedding (src/model_base.py:80-91; oracle/inception_v1_oracle.encoder): tanh(LN(pool)) . W with
+    pool = the 7x7 average of Mixed_5c, layer norm over the 1024 channels with epsilon 1e-12.  PH: leaf tensors of
+    Model/encoder/LN_tanh/{gamma, beta} and Model/encoder/im_embed/weight."""
+    ENC = 'Model/encoder/'
+    g = PH[ENC + 'LN_tanh/gamma']
+    pool = torch.as_tensor(np.asarray(mixed5c), dtype=g.dtype).mean(dim=(1, 2))
+    mu = pool.mean(-1, keepdim=True)
+    var = ((pool - mu) ** 2).mean(-1, keepdim=True)
+    y = (pool - mu) / torch.sqrt(var + 1e-12) * g + PH[ENC + 'LN_tanh/beta']
+    return torch.tanh(y) @ PH[ENC + 'im_embed/weight']
+
+
 def _lstm(P, c, x, cp, hp):
     g = torch.cat([x, hp], 1) @ P[_cell_scope(c) + 'kernel'] + P[_cell_scope(c) + 'bias']
     i, j, f, o = g.chunk(4, 1)
