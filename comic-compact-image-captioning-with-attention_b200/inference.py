@@ -41,6 +41,25 @@ def image_id_from_filename(f):
     raise ValueError('Expected `image_id` to be list or string, saw `{}`'.format(type(found)))
 
 
+def write_result_files(c, ckpt_num, raw_outputs, coco_json, images_per_second):
+    """The three artefacts `evaluate_model` and the COCO scorers read (src/infer_fn.py:165-184), in the reference's
+    formats: `captions___<ckpt>.json` (list of {image_id, caption}), `outputs___<ckpt>.pkl` (only with
+    `save_attention_maps`) and `infer_speed.txt` -- a three-line header written once per directory, then one
+    images-per-second figure appended per run, all separated by CRLF."""
+    out_dir = c.infer_save_path
+    if c.save_attention_maps:
+        with open(pjoin(out_dir, 'outputs___%s.pkl' % ckpt_num), 'wb') as f:
+            pickle.dump(raw_outputs, f, pickle.HIGHEST_PROTOCOL)
+    with open(pjoin(out_dir, 'captions___%s.json' % ckpt_num), 'w') as f:
+        json.dump(coco_json, f)
+    speed_file = pjoin(out_dir, 'infer_speed.txt')
+    header = '' if os.path.isfile(speed_file) else '\r\n'.join(
+        ['Using GPU #: %s' % c.gpu, 'Inference batch size: %s' % c.batch_size_infer,
+         'Inference beam size: %s' % c.infer_beam_size, ''])
+    with open(speed_file, 'a') as f:
+        f.write('%s\r\n%s' % (header, images_per_second))
+
+
 def run_inference(config, curr_ckpt_path, model, filenames, batches):
     """infer_fn.py:76-184 with the model and the input batches supplied by the caller.
 
@@ -88,28 +107,13 @@ def run_inference(config, curr_ckpt_path, model, filenames, batches):
     print("\nExample captions:\n{}\n".format("\n".join(captions[:3])))
     t = time.time() - start_time
 
-    # Ensure correctness (infer_fn.py:160-163)
-    filenames = filenames[:num_batches * batch_size] if step + 1 == num_batches else filenames
-    assert len(filenames) == len(list(set(filenames)))
-    assert len(filenames) == len(coco_json)
-    assert len(filenames) == len(raw_outputs['image_ids'].keys())
-
-    raw_output_fname = 'outputs___{}.pkl'.format(ckpt_num)
-    coco_json_fname = 'captions___{}.json'.format(ckpt_num)
-    if c.save_attention_maps:
-        with open(pjoin(c.infer_save_path, raw_output_fname), 'wb') as f:
-            pickle.dump(raw_outputs, f, pickle.HIGHEST_PROTOCOL)
-    with open(pjoin(c.infer_save_path, coco_json_fname), 'w') as f:
-        json.dump(coco_json, f)
-    speed_file = pjoin(c.infer_save_path, 'infer_speed.txt')
-    if not os.path.isfile(speed_file):
-        out = ['Using GPU #: {}'.format(c.gpu),
-               'Inference batch size: {}'.format(c.batch_size_infer),
-               'Inference beam size: {}'.format(c.infer_beam_size),
-               '']
-        with open(speed_file, 'a') as f:
-            f.write('\r\n'.join(out))
-    with open(speed_file, 'a') as f:
-        f.write('\r\n{}'.format(len(filenames) / t))
+    if step + 1 == num_batches:
+        filenames = filenames[:num_batches * batch_size]
+    # every image exactly once in every result container (the reference's three asserts, infer_fn.py:160-163)
+    n_images = len(filenames)
+    if not (len(set(filenames)) == n_images == len(coco_json) == len(raw_outputs['image_ids'])):
+        raise AssertionError('inference results do not cover the file list exactly once: %d files, %d captions, %d ids'
+                             % (n_images, len(coco_json), len(raw_outputs['image_ids'])))
+    write_result_files(c, ckpt_num, raw_outputs, coco_json, n_images / t)
     print("\nINFO: Inference completed. Time taken: {:4.2f} mins\n".format(t / 60))
     return raw_outputs, coco_json, t
