@@ -63,6 +63,12 @@ struct BeamStepSmem {
   int s_ri[8];
   float s_selv[KMAX];
   int s_seli[KMAX];
+  // large vocabularies: candidates that reach the block's score threshold (see beam_step_block)
+  static constexpr int CAND_CAP = 128;
+  int s_cnt;
+  float s_theta;
+  float s_cv[CAND_CAP];
+  int s_ci[CAND_CAP];
 };
 
 // One image's beam step, executed by EXACTLY the first 256 threads of the CTA (tid < 256);
@@ -95,9 +101,11 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
   }
   if (staged) group_sync(1, 256);
   // log-softmax statistics per beam row: max, log(sum(exp(x - max)))
+  float tbest = -INFINITY;          // large vocabularies: the best score among one real candidate per row of this thread
   for (int j = 0; j < k; ++j) {
     const float* row = base + (size_t)j * ldr;
     float mx = -INFINITY;
+    int amx = -1;                   // (non-staged) column of this thread's largest logit in row j
     if (staged) {
       for (int i = tid; i < V; i += 256) mx = fmaxf(mx, ld_logit(row + i));
     } else {
@@ -108,9 +116,11 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
 #pragma unroll
         for (int u = 0; u < 8; ++u) x[u] = (i0 + 256 * u < V) ? ld_logit(row + i0 + 256 * u) : -INFINITY;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) mx = fmaxf(mx, x[u]);
+        for (int u = 0; u < 8; ++u)
+          if (x[u] > mx) { mx = x[u]; amx = i0 + 256 * u; }
       }
     }
+    const float tmx = mx;           // this thread's own row maximum (before the block reduction)
     mx = warp_max(mx);
     if (lane == 0) S.s_rv[warp] = mx;
     group_sync(1, 256);
@@ -143,6 +153,17 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
       S.s_lse[j] = logf(tot);
     }
     group_sync(1, 256);
+    if (!staged && amx >= 0) {
+      // the score of candidate (j, amx), with exactly the arithmetic of the selection scan below
+      const bool finj = S.s_fin[j] != 0;
+      float lp;
+      if (finj) lp = (amx == eos) ? 0.0f : -FLT_MAX;
+      else lp = (tmx - S.s_max[j]) - S.s_lse[j];
+      const float tot = S.s_cum[j] + lp;
+      float sc = tot;
+      if (lpw != 0.0f) sc = tot / length_penalty_dev(S.s_len[j] + ((!finj && amx != eos) ? 1 : 0), lpw);
+      if (sc > tbest) tbest = sc;
+    }
   }
   const int ncand = k * V;
   auto total_of = [&](int idx) -> float {
@@ -158,15 +179,41 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
     long long len = S.s_len[j] + ((!S.s_fin[j] && w != eos) ? 1 : 0);
     return tot / length_penalty_dev(len, lpw);
   };
+  bool selected = false;
   if (!staged && k <= 8) {
-    // Large vocabularies: ONE scan.  Every thread keeps the 8 best of its own candidates (sorted by
-    // (score desc, flat index asc), in registers); the k winners are then drawn in k rounds of a block
-    // arg-max over the threads' list heads, the winning thread popping its head.  Same candidates, same
-    // per-candidate arithmetic and the same total order as the k-pass selection below.
-    float tv[8];
-    int ti[8];
+    // Large vocabularies.  The k-th largest of the 256 threads' `tbest` values is a lower bound (theta) of the k-th best
+    // score of the image -- they are the scores of k distinct real candidates -- so one scan that keeps only candidates
+    // with score >= theta (a handful out of k * V) followed by an exact top-k over those few gives the same winners as
+    // the k-pass selection below, in the same total order (score descending, flat index ascending).  The per-thread
+    // sorted top-8 list this replaces ran its insertion code with 1-3 active lanes on almost every iteration
+    // (ncu, V = 10,000: 64 M warp instructions per launch at 14 of 32 threads active, issue-bound at 98 us;
+    // profiles/r12w_ncu_beam_word_summary.txt).
+    {
+      float v = tbest;
+      float theta = -INFINITY;
+      for (int sel = 0; sel < k; ++sel) {
+        float bv = v;
+        int bi = tid;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { tv[q] = -INFINITY; ti[q] = 0x7fffffff; }
+        for (int o = 16; o; o >>= 1) {
+          float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { S.s_rv[warp] = bv; S.s_ri[warp] = bi; }
+        group_sync(1, 256);
+        bv = S.s_rv[0]; bi = S.s_ri[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w)
+          if (better(S.s_rv[w], S.s_ri[w], bv, bi)) { bv = S.s_rv[w]; bi = S.s_ri[w]; }
+        group_sync(1, 256);
+        if (bi == tid) v = -INFINITY;            // pop the winner
+        theta = bv;
+      }
+      if (tid == 0) { S.s_theta = theta; S.s_cnt = 0; }
+      group_sync(1, 256);
+    }
+    const float theta = S.s_theta;
     for (int j = 0; j < k; ++j) {
       const float* row = base + (size_t)j * ldr;
       const float mxj = S.s_max[j], lsej = S.s_lse[j], cumj = S.s_cum[j];
@@ -181,51 +228,49 @@ __device__ __forceinline__ void beam_step_block(BeamStepSmem& S, float* stage, i
         for (int u = 0; u < 8; ++u) x[u] = (!finj && w0 + 256 * u < V) ? ld_logit(row + w0 + 256 * u) : 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-        const int w = w0 + 256 * u;
-        if (w >= V) break;
-        float lp;
-        if (finj) lp = (w == eos) ? 0.0f : -FLT_MAX;
-        else lp = (x[u] - mxj) - lsej;
-        const float tot = cumj + lp;
-        const float sc = (lpw == 0.0f) ? tot : tot / ((w == eos) ? pen_eos : pen_live);
-        const int idx = off + w;
-        if (better(sc, idx, tv[7], ti[7])) {
-          tv[7] = sc; ti[7] = idx;
-#pragma unroll
-          for (int q = 7; q > 0; --q) {
-            if (better(tv[q], ti[q], tv[q - 1], ti[q - 1])) {
-              const float fv = tv[q]; tv[q] = tv[q - 1]; tv[q - 1] = fv;
-              const int fi = ti[q]; ti[q] = ti[q - 1]; ti[q - 1] = fi;
-            }
+          const int w = w0 + 256 * u;
+          if (w >= V) break;
+          float lp;
+          if (finj) lp = (w == eos) ? 0.0f : -FLT_MAX;
+          else lp = (x[u] - mxj) - lsej;
+          const float tot = cumj + lp;
+          const float sc = (lpw == 0.0f) ? tot : tot / ((w == eos) ? pen_eos : pen_live);
+          if (sc >= theta) {
+            const int pos = atomicAdd(&S.s_cnt, 1);
+            if (pos < BeamStepSmem::CAND_CAP) { S.s_cv[pos] = sc; S.s_ci[pos] = off + w; }
           }
         }
-        }   // u
       }
     }
-    for (int sel = 0; sel < k; ++sel) {
-      float bv = tv[0];
-      int bi = ti[0];
+    group_sync(1, 256);
+    const int cnt = S.s_cnt;
+    if (cnt <= BeamStepSmem::CAND_CAP) {         // (more: massive ties -- the k-pass selection below handles them)
+      selected = true;
+      if (warp == 0) {
+        float pv = INFINITY;
+        int pi = -1;
+        for (int sel = 0; sel < k; ++sel) {
+          float bv = -INFINITY;
+          int bi = 0x7fffffff;
+          for (int e = lane; e < cnt; e += 32) {
+            const float sc = S.s_cv[e];
+            const int idx = S.s_ci[e];
+            const bool eligible = (sc < pv) || (sc == pv && idx > pi);
+            if (eligible && better(sc, idx, bv, bi)) { bv = sc; bi = idx; }
+          }
 #pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+          for (int o = 16; o; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+          }
+          pv = bv; pi = bi;
+          if (lane == 0) { S.s_selv[sel] = bv; S.s_seli[sel] = bi; }
+        }
       }
-      if (lane == 0) { S.s_rv[warp] = bv; S.s_ri[warp] = bi; }
-      group_sync(1, 256);
-      bv = S.s_rv[0]; bi = S.s_ri[0];
-#pragma unroll
-      for (int w = 1; w < 8; ++w)
-        if (better(S.s_rv[w], S.s_ri[w], bv, bi)) { bv = S.s_rv[w]; bi = S.s_ri[w]; }
-      group_sync(1, 256);
-      if (ti[0] == bi && bi != 0x7fffffff) {      // this thread owned the winner: pop it
-#pragma unroll
-        for (int q = 0; q < 7; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
-        tv[7] = -INFINITY; ti[7] = 0x7fffffff;
-      }
-      if (tid == 0) { S.s_selv[sel] = bv; S.s_seli[sel] = bi; }
     }
-  } else {
+  }
+  if (!selected) {
   float pv = INFINITY;
   int pi = -1;
   for (int sel = 0; sel < k; ++sel) {

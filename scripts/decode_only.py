@@ -11,12 +11,12 @@ import torch
 import __graft_entry__ as G
 
 G.build()
-from _common import comic_config, make_weights, fake_features
+from _common import comic_config, word_config, make_weights, fake_features
 from comic_b200.engine import Engine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
-c = comic_config()
+c = word_config(n_words=10000) if (len(sys.argv) > 3 and sys.argv[3] == 'word') else comic_config()   # BASELINE config 2 / 1
 W = make_weights(c, include_cnn=False)
 eng = Engine(c)
 eng.bind_weights(W, with_cnn=False)

@@ -281,6 +281,30 @@ def test_beam_step_bit_exact(torch_mod, B, k, V, lpw, fin):
     np.testing.assert_allclose(d_lp.cpu().numpy(), new_lp, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize('B,k,V,lpw', [(6, 3, 10000, 0.0), (4, 5, 7001, 0.7), (3, 8, 4000, 0.0), (5, 3, 10000, 0.7)])
+def test_beam_step_large_vocabulary_threshold_selection(torch_mod, B, k, V, lpw):
+    """Word vocabularies with ordinary (tie-free) logits: the block's score threshold keeps a handful of the k x V
+    candidates and the exact top-k is drawn from those (search_steps.cuh); the coarse-grid cases of
+    test_beam_step_bit_exact overflow the candidate list instead and take the k-pass fallback."""
+    import comic_oracle as O
+    c = comic_config()
+    eng = _engine(c, make_weights(c, include_cnn=False), with_cnn=False)
+    rng = np.random.default_rng(1000 + B * 10 + k)
+    logits = (rng.standard_normal((B, k, V)) * 3).astype(np.float32)
+    eos = V - 1
+    lp, finished, lengths = _beam_state(rng, B, k, V, True)
+    top, word, parent, new_lp, new_fin, new_len, total = O.beam_search_step(
+        logits, lp.copy(), finished.copy(), lengths.copy(), k, eos, lpw)
+    d_lp, d_fin, d_len = eng.to_dev(lp), eng.to_dev(finished.astype(np.uint8)), eng.to_dev(lengths)
+    g_top, g_word, g_parent = eng.beam_step(eng.to_dev(logits), d_lp, d_fin, d_len, eos, lpw)
+    np.testing.assert_array_equal(g_word.cpu().numpy(), word)
+    np.testing.assert_array_equal(g_parent.cpu().numpy(), parent)
+    np.testing.assert_array_equal(d_fin.cpu().numpy().astype(bool), new_fin)
+    np.testing.assert_array_equal(d_len.cpu().numpy(), new_len)
+    np.testing.assert_allclose(g_top.cpu().numpy(), top, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(d_lp.cpu().numpy(), new_lp, rtol=1e-5, atol=1e-5)
+
+
 def test_gather_tree_bit_exact(torch_mod):
     import comic_oracle as O
     c = comic_config()
