@@ -225,6 +225,16 @@ class Trainer(object):
         targets_tm = to(targets.T, torch.int32)
         coef_tm = to(coef.T, torch.float32)
         lens_d = to(lens, torch.int32)
+        if masks:
+            # the kernels index the masks by executed step: a mask set drawn for fewer steps would be read out of bounds
+            Bm = inputs.shape[0]
+            for name in ('inp', 'out', 'att'):
+                m_ = masks.get(name)
+                if m_ is not None and (m_.shape[0] < T_run or m_.shape[1] != Bm):
+                    raise ValueError("dropout mask '%s' has shape %s; this batch executes %d steps of %d rows"
+                                     % (name, tuple(m_.shape), T_run, Bm))
+            if masks.get('init_in') is not None and masks['init_in'].shape[0] != Bm:
+                raise ValueError("dropout mask 'init_in' has %d rows; the batch has %d" % (masks['init_in'].shape[0], Bm))
         if forward_only:
             loss, logits, attn = eng.train_fwd_bwd(fm.contiguous(), im_embed.contiguous(), inputs_tm, targets_tm, coef_tm,
                                                    lens_d, T_run, None, masks, keeps, c.rnn_map_loss_scale,

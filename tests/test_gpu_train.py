@@ -266,16 +266,21 @@ def test_recurrent_dropout_masks_are_shared_over_rows_and_steps(torch_mod):
     from comic_b200.train import Trainer
     c = comic_config(train_mode='decoder', rnn_recurr_dropout=True)
     W, im, fm, caps, _, _ = _train_case(c, B=3, L=7, seed=2, dropout=False)
+    from comic_b200.train import process_inputs
     tr = Trainer(c, W, with_cnn=False)
-    masks, keeps = tr.make_masks(3, 5, seed=11)
+    T_run = int(process_inputs(caps, c.token_type)[3].max())         # executed steps of this batch (tokens + <EOS>)
+    masks, keeps = tr.make_masks(3, T_run, seed=11)
     inp, out, init = masks['inp'].cpu().numpy(), masks['out'].cpu().numpy(), masks['init_in'].cpu().numpy()
-    assert inp.shape == (5, 3, 768) and out.shape == (5, 3, 512) and init.shape == (3, 768)
+    assert inp.shape == (T_run, 3, 768) and out.shape == (T_run, 3, 512) and init.shape == (3, 768)
     assert (inp == inp[0, 0]).all() and (out == out[0, 0]).all() and (init == inp[0, 0]).all()
     assert 0.5 < inp[0, 0].mean() < 0.8 and set(np.unique(inp)) <= {0.0, 1.0}
-    m2, _ = tr.make_masks(3, 5, seed=12)
+    m2, _ = tr.make_masks(3, T_run, seed=12)
     assert (m2['inp'].cpu().numpy()[0, 0] != inp[0, 0]).any()
     out1 = tr.forward_backward(tr.engine.to_dev(fm), tr.engine.to_dev(im), caps, None, masks, keeps)
     assert np.isfinite(float(out1['loss'][0]))
+    short, _ = tr.make_masks(3, T_run - 1, seed=11)
+    with pytest.raises(ValueError):                       # masks for fewer steps than the batch executes are refused
+        tr.forward_backward(tr.engine.to_dev(fm), tr.engine.to_dev(im), caps, None, short, keeps)
 
 
 def test_momentum_sgd_and_per_variable_clipping(torch_mod):
