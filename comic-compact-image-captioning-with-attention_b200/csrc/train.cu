@@ -269,6 +269,63 @@ attn_bwd_dalpha_kernel(const float* __restrict__ values, int VAL, const float* _
   }
 }
 
+// The same with lane-contiguous channels (VAL / 32 per lane, 128-bit accesses; needs head size % (VAL / 32) == 0): d ctx of
+// the row is loaded once per beam instead of once per position and head, a position costs one round of independent loads
+// (the scalar version's head loop was a chain of dependent L2 round trips: 36 us per launch at batch 32, long-scoreboard
+// stall 17.9 per issued instruction, profiles/r12t_train_attn_summary.txt), and the per-head dot product is reduced over
+// the 2..32 lanes of the head only.
+template <int VAL>
+__global__ void __launch_bounds__(256)
+attn_bwd_dalpha_vec_kernel(const float* __restrict__ values, const float* __restrict__ dctx, int ld_dctx,
+                           const int* __restrict__ lens, int t, const float* __restrict__ a_post,
+                           float* __restrict__ dvalues, float* __restrict__ dal_out, int k, int H, int M, int S) {
+  constexpr int CPL = VAL / 32;
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int dv = VAL / H;
+  const int c0 = lane * CPL;
+  const int hh = c0 / dv;                       // this lane's head
+  const int lph = dv / CPL;                     // lanes per head (a power of two)
+  const int per = (M + S - 1) / S;
+  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
+  for (int beam = 0; beam < k; ++beam) {
+    const int n = b * k + beam;
+    const bool fin = lens && t >= lens[n];
+    float g[CPL];
+#pragma unroll
+    for (int c4 = 0; c4 < CPL / 4; ++c4) {
+      const float4 v = fin ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg4(dctx + (size_t)n * ld_dctx + c0 + c4 * 4);
+      g[c4 * 4 + 0] = v.x; g[c4 * 4 + 1] = v.y; g[c4 * 4 + 2] = v.z; g[c4 * 4 + 3] = v.w;
+    }
+    const float* ap = a_post + ((size_t)n * H + hh) * M;
+    for (int m = m0 + warp; m < m1; m += 8) {
+      const float* vr = values + ((size_t)b * M + m) * VAL + c0;
+      const float al = ap[m];
+      float acc = 0.f;
+      float4 vv[CPL / 4];
+#pragma unroll
+      for (int c4 = 0; c4 < CPL / 4; ++c4) vv[c4] = ldg4(vr + c4 * 4);
+      if (dvalues != nullptr && !fin) {
+        float* dvr = dvalues + ((size_t)b * M + m) * VAL + c0;
+#pragma unroll
+        for (int c4 = 0; c4 < CPL / 4; ++c4) {
+          float4 d = *reinterpret_cast<const float4*>(dvr + c4 * 4);
+          d.x = fmaf(al, g[c4 * 4 + 0], d.x); d.y = fmaf(al, g[c4 * 4 + 1], d.y);
+          d.z = fmaf(al, g[c4 * 4 + 2], d.z); d.w = fmaf(al, g[c4 * 4 + 3], d.w);
+          *reinterpret_cast<float4*>(dvr + c4 * 4) = d;
+        }
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < CPL / 4; ++c4) {
+        acc = fmaf(g[c4 * 4 + 0], vv[c4].x, acc); acc = fmaf(g[c4 * 4 + 1], vv[c4].y, acc);
+        acc = fmaf(g[c4 * 4 + 2], vv[c4].z, acc); acc = fmaf(g[c4 * 4 + 3], vv[c4].w, acc);
+      }
+      for (int o = lph >> 1; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if ((lane & (lph - 1)) == 0) dal_out[((size_t)n * H + hh) * M + m] = acc;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 attn_bwd_score_kernel(const float* __restrict__ values, int VAL, const float* __restrict__ dctx, int ld_dctx,
                       const int* __restrict__ lens, int t, const float* __restrict__ a_post,
@@ -817,7 +874,11 @@ struct TrainBufs {
 };
 
 static int attn_slices(int B, int num_sms) {
-  int S = (2 * num_sms + B - 1) / B;
+  // (image x position-slice) CTAs of the attention backward.  attn_bwd_ln_kernel<512> holds 212 registers x 128 threads:
+  // two CTAs per SM, and its time is mostly a per-CTA fixed cost (28 slices: 3 waves = 64 us per launch against 51 us for
+  // 10 slices, ncu launch lists profiles/r12t / r12u) -- so the grid is sized to ONE wave of 2 x SMs CTAs, rounded DOWN
+  // (batch 32: 10 slices = 320 CTAs were 296 + a second wave of 24)
+  int S = (2 * num_sms) / B;
   if (S < 1) S = 1;
   if (S > 28) S = 28;
   return S;
@@ -1084,8 +1145,21 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
     }
     {
       dim3 g1(B, tb.S);
-      attn_bwd_dalpha_kernel<<<g1, 256, 0, st>>>(values, VAL, dctx, ld_dctx, lens, t, tb.apost + (size_t)t * B * HM, dvals_dst,
-                                                tb.ds, 1, h->H, M, tb.S);
+      const int dvh = VAL / h->H;
+      const bool vec_ok = VAL % 128 == 0 && dvh % (VAL / 32) == 0 && ((dvh / (VAL / 32)) & ((dvh / (VAL / 32)) - 1)) == 0 &&
+                          ld_dctx % 4 == 0;
+      if (vec_ok && VAL == 512)
+        attn_bwd_dalpha_vec_kernel<512><<<g1, 256, 0, st>>>(values, dctx, ld_dctx, lens, t, tb.apost + (size_t)t * B * HM,
+                                                           dvals_dst, tb.ds, 1, h->H, M, tb.S);
+      else if (vec_ok && VAL == 256)
+        attn_bwd_dalpha_vec_kernel<256><<<g1, 256, 0, st>>>(values, dctx, ld_dctx, lens, t, tb.apost + (size_t)t * B * HM,
+                                                           dvals_dst, tb.ds, 1, h->H, M, tb.S);
+      else if (vec_ok && VAL == 1024)
+        attn_bwd_dalpha_vec_kernel<1024><<<g1, 256, 0, st>>>(values, dctx, ld_dctx, lens, t, tb.apost + (size_t)t * B * HM,
+                                                            dvals_dst, tb.ds, 1, h->H, M, tb.S);
+      else
+        attn_bwd_dalpha_kernel<<<g1, 256, 0, st>>>(values, VAL, dctx, ld_dctx, lens, t, tb.apost + (size_t)t * B * HM, dvals_dst,
+                                                  tb.ds, 1, h->H, M, tb.S);
       h->launches++;
     }
     attn_bwd_score_kernel<<<B, 256, (size_t)HM * sizeof(float), st>>>(
