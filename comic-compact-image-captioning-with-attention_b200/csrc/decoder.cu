@@ -321,6 +321,43 @@ attn_ctx_kernel(const float* __restrict__ scores, const float* __restrict__ valu
     const float* s = scores + ((size_t)b * npair + pr) * M;
     float* a = sm_alpha + (size_t)pr * M;
     float sum = 0.f;
+    if (M <= 256) {
+      // up to 8 positions per lane: the row's scores and its dropout mask are fetched in ONE round of independent loads
+      // (the generic loops below walk them one L2 round trip at a time: long-scoreboard stall 20 per issued
+      // instruction, 28 us per launch at batch 32, profiles/r13b_*); same arithmetic in the same order
+      const float* mk8 = att_mask ? att_mask + ((size_t)b * npair + pr) * M : nullptr;
+      float sv[8], mv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = lane + 32 * i;
+        sv[i] = (m < M) ? s[m] : 0.f;
+        mv[i] = (mk8 != nullptr && m < M) ? mk8[m] : 1.0f;
+      }
+      if (prob_fn == 0) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (lane + 32 * i < M) mx = fmaxf(mx, sv[i]);
+        mx = warp_max(mx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (lane + 32 * i < M) { sv[i] = expf(sv[i] - mx); sum += sv[i]; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (lane + 32 * i < M) { sv[i] = sigmoidf_(sv[i]); sum += sv[i]; }
+      }
+      sum = warp_sum(sum);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = lane + 32 * i;
+        if (m < M) {
+          float al = sv[i] / sum;
+          if (hist_pre && blockIdx.y == 0) hist_pre[((size_t)b * npair + pr) * M + m] = al;
+          if (mk8) al = (al / att_keep) * mv[i];
+          a[m] = al;
+          if (hist_t && blockIdx.y == 0) hist_t[((size_t)b * npair + pr) * M + m] = al;
+        }
+      }
+      continue;
+    }
     if (prob_fn == 0) {
       float mx = -INFINITY;
       for (int m = lane; m < M; m += 32) mx = fmaxf(mx, s[m]);
@@ -360,7 +397,7 @@ attn_ctx_kernel(const float* __restrict__ scores, const float* __restrict__ valu
     const int nb = min(4, k - beam0);
     const float* a0 = sm_alpha + ((size_t)(beam0)*H + hd) * M;
     if (live) {
-#pragma unroll 4
+#pragma unroll 16
       for (int m = m0; m < m1; ++m) {
         float v = __ldg(vb + (size_t)m * VAL);
 #pragma unroll

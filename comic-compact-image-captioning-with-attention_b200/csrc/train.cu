@@ -444,8 +444,14 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
   const int m_lo = (int)(((long long)M * sl) / S), m_hi = (int)(((long long)M * (sl + 1)) / S);
   const float invT = 1.0f / temperature[0];
   float gm[CPL], bt[CPL], vv[CPL];
+  // 128-bit loads: as scalars these three rows were 3 * CPL requests of 32 sectors each per warp -- a per-CTA fixed cost
 #pragma unroll
-  for (int c = 0; c < CPL; ++c) { gm[c] = gamma[c0 + c]; bt[c] = beta[c0 + c]; vv[c] = vvec[c0 + c]; }
+  for (int c4 = 0; c4 < CPL / 4; ++c4) {
+    const float4 g4 = ldg4(gamma + c0 + c4 * 4), b4 = ldg4(beta + c0 + c4 * 4), v4 = ldg4(vvec + c0 + c4 * 4);
+    gm[c4 * 4 + 0] = g4.x; gm[c4 * 4 + 1] = g4.y; gm[c4 * 4 + 2] = g4.z; gm[c4 * 4 + 3] = g4.w;
+    bt[c4 * 4 + 0] = b4.x; bt[c4 * 4 + 1] = b4.y; bt[c4 * 4 + 2] = b4.z; bt[c4 * 4 + 3] = b4.w;
+    vv[c4 * 4 + 0] = v4.x; vv[c4 * 4 + 1] = v4.y; vv[c4 * 4 + 2] = v4.z; vv[c4 * 4 + 3] = v4.w;
+  }
   float dv_a[CPL], dg_a[CPL], db_a[CPL];
 #pragma unroll
   for (int c = 0; c < CPL; ++c) { dv_a[c] = 0.f; dg_a[c] = 0.f; db_a[c] = 0.f; }
@@ -454,8 +460,18 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
     const int n = b * k + beam;
     float q[CPL], dq_a[CPL];
     const float* qp = lq + (size_t)n * ld_lq + q_off + c0;
+    if (((ld_lq | q_off) & 3) == 0) {
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) { q[c] = qp[c]; dq_a[c] = 0.f; }
+      for (int c4 = 0; c4 < CPL / 4; ++c4) {
+        const float4 q4 = ldg4(qp + c4 * 4);
+        q[c4 * 4 + 0] = q4.x; q[c4 * 4 + 1] = q4.y; q[c4 * 4 + 2] = q4.z; q[c4 * 4 + 3] = q4.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) q[c] = qp[c];
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) dq_a[c] = 0.f;
     const bool one_head = (D % CPL) == 0;          // a lane's CPL contiguous channels lie in one head
     for (int m = m_lo + warp; m < m_hi; m += 4) {
       const float* kr = keys + ((size_t)b * M + m) * R + c0;
