@@ -624,7 +624,8 @@ __global__ void sum_slices_kernel(const float* __restrict__ part, int S, int N, 
 __global__ void lstm_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
                                 const float* __restrict__ dhout, const float* __restrict__ out_mask, float out_keep,
                                 const int* __restrict__ lens, int t, float* __restrict__ gH, float* __restrict__ gC,
-                                float* __restrict__ gH_pass, float* __restrict__ dgates, int B, int R) {
+                                float* __restrict__ gH_pass, float* __restrict__ dgates, int B, int R, int nz = 1,
+                                size_t zstride = 0) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * R) return;
   int b = i / R, j = i - b * R;
@@ -636,6 +637,7 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ gates, const float* __
   const float cn = cp * sf + si * tj;
   const float tc = tanhf(cn);
   float dh = dhout ? dhout[i] : 0.f;
+  for (int z = 1; z < nz; ++z) dh += dhout[z * zstride + i];      // split-K partials of the producing GEMM, fixed order
   if (out_mask) dh = (dh / out_keep) * out_mask[i];
   const float gh = gH[i], gc = gC[i];
   if (!fin) dh += gh;
@@ -653,11 +655,12 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ gates, const float* __
 __global__ void dx_split_kernel(const float* __restrict__ dxh, int KX, int W, int A, int R,
                                 const float* __restrict__ in_mask, float in_keep, const int* __restrict__ lens, int t,
                                 float* __restrict__ demb, float* __restrict__ gCtx, float* __restrict__ gH,
-                                const float* __restrict__ gH_pass, int B) {
+                                const float* __restrict__ gH_pass, int B, int nz = 1, size_t zstride = 0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * KX) return;
   int b = (int)(i / KX), j = (int)(i % KX);
   float v = dxh[i];
+  for (int z = 1; z < nz; ++z) v += dxh[z * zstride + i];         // split-K partials of the producing GEMM, fixed order
   const bool fin = lens && t >= lens[b];
   if (j < W + A) {
     if (in_mask) v = (v / in_keep) * in_mask[(size_t)b * (W + A) + j];
@@ -836,8 +839,10 @@ __global__ void legacy_head_dln_kernel(float* __restrict__ d_t1, float* __restri
 // ---------------------------------------------------------------------------
 // Host side.
 // ---------------------------------------------------------------------------
+// nz_out != nullptr: when the plan splits K, the partial sums stay in `part` ([nz][M][N]) for a consumer that adds them
+// itself (in the same fixed order) and *nz_out = nz; otherwise *nz_out = 1 and C holds the product.
 static int train_gemm(comic_handle_t h, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M,
-                      int N, int K, float* part, size_t part_floats, cudaStream_t st) {
+                      int N, int K, float* part, size_t part_floats, cudaStream_t st, int* nz_out = nullptr) {
   APlain a{};
   a.nseg = 1;
   a.seg[0] = ASeg{A, nullptr, lda, K, M};
@@ -848,6 +853,7 @@ static int train_gemm(comic_handle_t h, const float* A, int lda, const float* Bm
   e.nroute = 1;
   e.stop_n = 0x7fffffff;
   const bool vec = (K % 4 == 0) && (lda % 4 == 0);
+  if (nz_out) *nz_out = 1;
   if (nz == 1) {
     e.r[0] = Route{0, N, C, ldc, 0};
     if (vec) COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, Bm, ldb, M, N, K, e, p, st)));
@@ -859,6 +865,12 @@ static int train_gemm(comic_handle_t h, const float* A, int lda, const float* Bm
   e.split_stride = (long long)M * N;
   if (vec) COMIC_CHECK_CUDA((launch_gemm<0, 4>(a, Bm, ldb, M, N, K, e, p, st)));
   else COMIC_CHECK_CUDA((launch_gemm<0, 1>(a, Bm, ldb, M, N, K, e, p, st)));
+  if (nz_out && ldc == N) {
+    *nz_out = nz;
+    h->launches++;
+    COMIC_CHECK_CUDA(cudaGetLastError());
+    return COMIC_OK;
+  }
   // fixed-order reduction of the partials into C (ldc may differ from N)
   {
     size_t tot = (size_t)M * N;
@@ -1203,15 +1215,17 @@ extern "C" int comic_train_fwd_bwd(comic_handle_t h, const float* fm, const floa
                                                   h->w.temperature, tb.ds, tb.dkeys, tb.dqpart, tb.cpart, 1, h->H, M, tb.S, B);
     sum_slices_kernel<<<(B * R + 255) / 256, 256, 0, st>>>(tb.dqpart, tb.S, B, R, dlq_t, LQ, h->Vp);
     h->launches += 3;
-    if ((rc = train_gemm(h, dlq_t, LQ, tb.outqT, R, tb.dHout, R, B, R, LQ, tb.part, tb.part_floats, st))) return rc;
+    // the two skinny GEMMs of the step split K; their consumers add the partials themselves (no reduce launches)
+    int nzh = 1, nzx = 1;
+    if ((rc = train_gemm(h, dlq_t, LQ, tb.outqT, R, tb.dHout, R, B, R, LQ, tb.part, tb.part_floats, st, &nzh))) return rc;
     float* dG_t = tb.dG + (size_t)(t + 1) * B * 4 * R;
     lstm_bwd_kernel<<<(B * R + 255) / 256, 256, 0, st>>>(tb.gates + (size_t)(t + 1) * B * 4 * R, tb.c + (size_t)t * B * R,
-                                                        tb.dHout, mk.out ? mk.out + (size_t)t * B * R : nullptr, out_keep,
-                                                        lens, t, tb.gH, tb.gC, tb.gHp, dG_t, B, R);
-    if ((rc = train_gemm(h, dG_t, 4 * R, tb.KT, KX, tb.dxh, KX, B, KX, 4 * R, tb.part, tb.part_floats, st))) return rc;
+                                                        nzh > 1 ? tb.part : tb.dHout, mk.out ? mk.out + (size_t)t * B * R : nullptr,
+                                                        out_keep, lens, t, tb.gH, tb.gC, tb.gHp, dG_t, B, R, nzh, (size_t)B * R);
+    if ((rc = train_gemm(h, dG_t, 4 * R, tb.KT, KX, tb.dxh, KX, B, KX, 4 * R, tb.part, tb.part_floats, st, &nzx))) return rc;
     dx_split_kernel<<<(unsigned)(((size_t)B * KX + 255) / 256), 256, 0, st>>>(
-        tb.dxh, KX, W, A, R, mk.inp ? mk.inp + (size_t)t * B * XA : nullptr, in_keep, lens, t,
-        tb.demb + (size_t)t * B * W, tb.gCtx, tb.gH, tb.gHp, B);
+        nzx > 1 ? tb.part : tb.dxh, KX, W, A, R, mk.inp ? mk.inp + (size_t)t * B * XA : nullptr, in_keep, lens, t,
+        tb.demb + (size_t)t * B * W, tb.gCtx, tb.gH, tb.gHp, B, nzx, (size_t)B * KX);
     h->launches += 2;
   }
   // ---- init step backward ----
