@@ -454,7 +454,10 @@ inline GemmPlan plan_gemm(int M, int N, int K, int num_sms, bool allow_split) {
     int bk = p.cfg == 2 ? 32 : 16;
     int maxsplit = K / (bk * 4);   // at least 4 K-tiles per split
     if (maxsplit < 1) maxsplit = 1;
-    while (t * p.splitk * 2 <= num_sms + num_sms / 2 && p.splitk * 2 <= maxsplit && p.splitk < 16) p.splitk *= 2;
+    // small-M launches are K-loop latency chains (load -> barrier -> FMA per K tile, ~35 % issue activity at 8 warps per SM):
+    // two CTAs per SM overlap them, so the split may fill up to 2.5 waves of one CTA per SM (was 1.5)
+    const int fill = (p.cfg == 2) ? 2 * num_sms + num_sms / 2 : num_sms + num_sms / 2;
+    while (t * p.splitk * 2 <= fill && p.splitk * 2 <= maxsplit && p.splitk < 16) p.splitk *= 2;
   }
   return p;
 }
