@@ -456,6 +456,14 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
 #pragma unroll
   for (int c = 0; c < CPL; ++c) { dv_a[c] = 0.f; dg_a[c] = 0.f; db_a[c] = 0.f; }
   __shared__ float red[4][R];
+  // running sums of this (image, slice) over the time steps: fetched now, added to at the end (their three dependent
+  // L2 round trips were part of every CTA's tail)
+  float* cp = cpart + ((size_t)b * S + sl) * 3 * R;
+  float cpv[3][R / 128];
+#pragma unroll
+  for (int which = 0; which < 3; ++which)
+#pragma unroll
+    for (int i = 0; i < R / 128; ++i) cpv[which][i] = cp[(size_t)which * R + threadIdx.x + 128 * i];
   for (int beam = 0; beam < k; ++beam) {
     const int n = b * k + beam;
     float q[CPL], dq_a[CPL];
@@ -475,8 +483,14 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
     const bool one_head = (D % CPL) == 0;          // a lane's CPL contiguous channels lie in one head
     for (int m = m_lo + warp; m < m_hi; m += 4) {
       const float* kr = keys + ((size_t)b * M + m) * R + c0;
+      float* dkr = dkeys + ((size_t)b * M + m) * R + c0;
       float u[CPL];
       float s = 0.f;
+      // the gradient row this position accumulates into is fetched WITH the key row: read at the end of the iteration
+      // (where it is needed) its L2 round trip sat on the critical path of every position
+      float4 dk[CPL / 4];
+#pragma unroll
+      for (int c4 = 0; c4 < CPL / 4; ++c4) dk[c4] = *reinterpret_cast<const float4*>(dkr + c4 * 4);
       // 128-bit accesses: a lane's slice is 4*CPL contiguous, 16-byte aligned bytes (scalar loads touched every
       // 32-byte sector of the row CPL times)
 #pragma unroll
@@ -512,10 +526,9 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
       }
       s1 = wred_sum(s1) * (1.0f / R);
       s2 = wred_sum(s2) * (1.0f / R);
-      float* dkr = dkeys + ((size_t)b * M + m) * R + c0;
 #pragma unroll
       for (int c4 = 0; c4 < CPL / 4; ++c4) {
-        float4 acc = *reinterpret_cast<const float4*>(dkr + c4 * 4);
+        float4 acc = dk[c4];
         float g[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -535,13 +548,16 @@ attn_bwd_ln_kernel(const float* __restrict__ keys, const float* __restrict__ lq,
       dq_part[((size_t)sl * N + n) * R + j] = (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
     __syncthreads();
   }
-  float* cp = cpart + ((size_t)b * S + sl) * 3 * R;
+#pragma unroll
   for (int which = 0; which < 3; ++which) {
 #pragma unroll
     for (int c = 0; c < CPL; ++c) red[warp][c0 + c] = which == 0 ? dv_a[c] : (which == 1 ? dg_a[c] : db_a[c]);
     __syncthreads();
-    for (int j = threadIdx.x; j < R; j += 128)
-      cp[(size_t)which * R + j] += (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
+#pragma unroll
+    for (int i = 0; i < R / 128; ++i) {
+      const int j = threadIdx.x + 128 * i;
+      cp[(size_t)which * R + j] = cpv[which][i] + ((red[0][j] + red[1][j]) + (red[2][j] + red[3][j]));
+    }
     __syncthreads();
   }
 }
